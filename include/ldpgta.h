@@ -1,0 +1,152 @@
+/*
+ * include/ldpgta.h -- C-ABI of libldpgta.so, the B200 (sm_100a) implementation of
+ * LD-PGTA's windowed haplotype-likelihood engine.
+ *
+ * The reference (mccoy-lab/LD-PGTA) is pure Python and has no FFI of its own; the
+ * entry points below are the operations its hot path performs, cut where the
+ * reference's model classes and driver call into big-int arithmetic.  Each one
+ * cites the reference code it replaces (paths into the reference repository).
+ * The Python classes in ld-pgta_b200/ (homogeneous, recent_admixture,
+ * distant_admixture, bootstrap, aneuploidy_test) bind these with ctypes; the
+ * stub a reference maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative LDPGTA_E_* code;
+ *     ldpgta_last_error() returns a thread-local description of the last failure
+ *   - plain pointers and sizes only; `const T *` inputs are caller-owned HOST buffers
+ *     unless the name ends in _dev, outputs are caller-allocated
+ *   - a context owns one CUDA device, one stream and the packed panel rows of one
+ *     (sample, chromosome); it is thread-compatible, not thread-safe
+ *   - haplotype rows are little-endian arrays of 64-bit words, bit i of word j =
+ *     haplotype 64*j+i (any bijection haplotype->bit gives the same popcounts);
+ *     bits at or above the group's haplotype count MUST be zero on input
+ *   - a "draw" is the ordered tuple of reads sampled from one genomic window by
+ *     ANEUPLOIDY_TEST.pick_reads (:226-233); read i of a draw is bit i of the
+ *     subset masks that index joint-frequency tables
+ */
+#ifndef LDPGTA_H
+#define LDPGTA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ldpgta_ctx ldpgta_ctx;
+
+enum {
+    LDPGTA_OK = 0,
+    LDPGTA_E_INVALID = -1,     /* bad argument (the message says which)            */
+    LDPGTA_E_CUDA = -2,        /* CUDA runtime failure                              */
+    LDPGTA_E_UNSUPPORTED = -3, /* outside the implemented envelope  */
+    LDPGTA_E_STATE = -4        /* call order: rows/masks not uploaded yet           */
+};
+
+/* Model classes: HOMOGENOUES_MODELS.homogeneous, RECENT_ADMIXTURE_MODELS.recent_admixture,
+ * DISTANT_ADMIXTURE_MODELS.distant_admixture (selection: ANEUPLOIDY_TEST.py:263-273). */
+enum { LDPGTA_HOMOGENEOUS = 0, LDPGTA_RECENT_ADMIXTURE = 1, LDPGTA_DISTANT_ADMIXTURE = 2 };
+
+#define LDPGTA_MAX_GROUPS 8
+#define LDPGTA_MAX_READS_PER_DRAW 16   /* reads per draw handled on device; the reference ships tables to 18 */
+#define LDPGTA_NUM_LLR_PAIRS 5         /* (BPH,SPH) (disomy,monosomy) (BPH,disomy) (disomy,SPH) (SPH,monosomy) */
+
+const char *ldpgta_last_error(void);
+int ldpgta_version(void);
+int ldpgta_device_count(void);
+
+/* One context per (sample, chromosome) and per model object: replaces the state built by
+ * homogeneous.__init__ (HOMOGENOUES_MODELS.py:52-73) and twins.  n_hap[g] = number of
+ * haplotypes in reference-panel group g (number_of_haplotypes_per_group). */
+int ldpgta_create(int device, int n_groups, const uint32_t *n_hap, ldpgta_ctx **out);
+int ldpgta_destroy(ldpgta_ctx *ctx);
+/* words of a caller-side row of group g = ceil(n_hap[g] / 64) */
+int ldpgta_row_words(const ldpgta_ctx *ctx, int group);
+
+/* hap_dict (build_hap_dict, HOMOGENOUES_MODELS.py:76-100): one row per observed
+ * (pos, base) allele, rows[n_rows][ldpgta_row_words].  complement[i] != 0 means the
+ * allele is the REF allele: the device stores row ^ (2^N - 1) (:94); pass NULL for none.
+ * Every group must receive the same number of rows, in the same allele order. */
+int ldpgta_upload_allele_rows(ldpgta_ctx *ctx, int group, const uint64_t *rows, int64_t n_rows,
+                              const uint8_t *complement);
+
+/* build_intrenal_hap_dict (HOMOGENOUES_MODELS.py:102-127) hoisted out of the draw loop:
+ * mask of read r = AND of the allele rows allele_idx[read_offsets[r] .. read_offsets[r+1]),
+ * computed on device for every group.  Replaces any earlier read masks. */
+int ldpgta_build_read_masks(ldpgta_ctx *ctx, const int32_t *allele_idx, const int64_t *read_offsets,
+                            int64_t n_reads);
+
+/* Alternative to the two calls above: upload ready-made read masks. */
+int ldpgta_upload_read_masks(ldpgta_ctx *ctx, int group, const uint64_t *rows, int64_t n_rows);
+/* Read masks straight from device memory laid out [n_rows][padded_words] with
+ * padded_words = ldpgta_padded_row_words(); the context keeps the pointer, no copy. */
+int ldpgta_padded_row_words(const ldpgta_ctx *ctx, int group);
+int ldpgta_attach_read_masks_dev(ldpgta_ctx *ctx, int group, const uint64_t *rows_dev, int64_t n_rows);
+int64_t ldpgta_num_reads(const ldpgta_ctx *ctx);
+
+/* joint_frequencies_combo(normalize=False) (HOMOGENOUES_MODELS.py:129-163) for ONE draw of
+ * n reads (2..16): out_counts[g][S] for S = 0 .. 2^n-1 (S = subset bitmask, entry 0 unused = 0).
+ * Parity hook: counts are bit-exact. */
+int ldpgta_joint_counts(ldpgta_ctx *ctx, const int32_t *read_idx, int n, uint32_t *out_counts);
+
+/* One call of model.get_likelihoods(alleles) / model.likelihoods(alleles) on an arbitrary tuple of
+ * "haplotypes" (HOMOGENOUES_MODELS.py:272-286 / :185-225): haplotype i is the list of allele rows
+ * allele_idx[read_offsets[i] .. read_offsets[i+1]) (build_intrenal_hap_dict :102-127 runs on device
+ * into scratch rows).  general_formula != 0 forces the partition polynomials of likelihoods() even
+ * for 2..4 haplotypes.  out[4]; counts_out (optional) [G][2^n] as in ldpgta_joint_counts. */
+int ldpgta_get_likelihoods(ldpgta_ctx *ctx, int model_kind, const int32_t *allele_idx,
+                           const int64_t *read_offsets, int n, const double *proportions,
+                           int general_formula, double *out, uint32_t *counts_out);
+
+/* get_likelihoods (HOMOGENOUES_MODELS.py:272-286, RECENT_...:314-328, DISTANT_...:300-316)
+ * for a batch of draws = the body of the bootstrap loop ANEUPLOIDY_TEST.py:277-286.
+ *   read_idx      concatenated read indices (rows of the read-mask table)
+ *   draw_offsets  n_draws+1 offsets into read_idx; draw d has 2..16 reads
+ *   proportions   LDPGTA_DISTANT_ADMIXTURE only: ancestral proportion per group, in the
+ *                 order of the ancestral_makeup dict (sum order of DISTANT_...:138-139)
+ *   out           [n_draws][4] = monosomy, disomy, SPH, BPH (likelihoods_tuple order)
+ * Dispatch follows the reference: 2,3,4 reads use the closed forms on normalised
+ * frequencies, other sizes the general partition polynomials on integer counts. */
+int ldpgta_likelihoods_batch(ldpgta_ctx *ctx, int model_kind, const int32_t *read_idx,
+                             const int64_t *draw_offsets, int64_t n_draws, const double *proportions,
+                             double *out);
+
+/* Same computation for draws of one size n with everything already resident in HBM:
+ * read_idx_dev[n_draws][n], out_dev[n_draws][4].  Asynchronous on the context's stream;
+ * ldpgta_synchronize() waits.  This is the call bench.py times for `value`. */
+int ldpgta_likelihoods_uniform_dev(ldpgta_ctx *ctx, int model_kind, int n, const int32_t *read_idx_dev,
+                                   int64_t n_draws, const double *proportions, double *out_dev);
+int ldpgta_synchronize(ldpgta_ctx *ctx);
+/* cudaStream_t of the context (as an integer) so callers can record events on it. */
+uint64_t ldpgta_stream(const ldpgta_ctx *ctx);
+/* number of kernels this context has launched since creation */
+int64_t ldpgta_launch_count(const ldpgta_ctx *ctx);
+
+/* LLR + reductions of statistics() (ANEUPLOIDY_TEST.py:78-90, 51-56, 65-76, 289-325) for one
+ * chromosome shard.  lik[n_draws][4] as produced above, windows = consecutive runs of draws:
+ * window w owns draws [window_offsets[w], window_offsets[w+1]).
+ *   llr            [5][n_draws]        per-draw log-likelihood ratios (sentinels +-1.23456789, 0)
+ *   window_mean_var[5][n_windows][2]   mean and SAMPLE variance per window (variance = NaN when
+ *                                      a window has a single draw; the reference raises there)
+ *   chrom_partials [5][n_cols + 3]     per pair: [0] sum over windows of (sum_i x_wi),
+ *                                      [1] number of windows, [2] number of windows with mean < 0,
+ *                                      [3 + i] column sums  sum_w x_wi  for i < n_cols
+ * n_cols = the smallest draw count over the windows of the WHOLE chromosome (zip truncation of
+ * :73); shards of one chromosome add their chrom_partials (that sum is the only cross-GPU
+ * exchange of the path) and ldpgta_finish_chromosome() turns the sum into mean/std. */
+int ldpgta_window_stats(ldpgta_ctx *ctx, const double *lik, const int64_t *window_offsets,
+                        int64_t n_windows, int n_cols, double *llr, double *window_mean_var,
+                        double *chrom_partials);
+/* mean_and_std_of_mean_of_rnd_var (ANEUPLOIDY_TEST.py:65-76) from summed partials; pure host
+ * arithmetic.  first_window_draws = len(A[0]) of the reference.  out[5][3] = mean_of_mean,
+ * std_of_mean, fraction_of_negative_LLRs. */
+int ldpgta_finish_chromosome(const double *chrom_partials, int n_cols, int first_window_draws, double *out);
+
+/* Page-locked host buffers so that the batch calls above copy without staging. */
+int ldpgta_host_alloc(void **ptr, int64_t bytes);
+int ldpgta_host_free(void *ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDPGTA_H */

@@ -1,0 +1,32 @@
+"""
+Drop-in for the reference module HOMOGENOUES_MODELS: `homogeneous` with the same
+constructor, methods and result record, computed on a B200 (see models.py).
+Importable flat (`import HOMOGENOUES_MODELS` with this directory on sys.path) or as
+`ldpgta_b200.HOMOGENOUES_MODELS`.
+"""
+import collections as _collections
+import os as _os
+import sys as _sys
+
+try:
+    from ldpgta_b200 import models as _models
+except ImportError:                      # flat import: make the repository root importable
+    _sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
+    from ldpgta_b200 import models as _models
+
+leg_tuple = _models.leg_tuple
+obs_tuple = _models.obs_tuple
+popcount = _models.popcount
+
+# The reference pickles likelihoods_tuple instances under the bare module name
+# 'HOMOGENOUES_MODELS' (*.LLR.p files); keep that name so old readers unpickle them.
+likelihoods_tuple = _collections.namedtuple('likelihoods_tuple', ('monosomy', 'disomy', 'SPH', 'BPH'))
+if _sys.modules.setdefault('HOMOGENOUES_MODELS', _sys.modules[__name__]) is _sys.modules[__name__]:
+    likelihoods_tuple.__module__ = 'HOMOGENOUES_MODELS'
+else:
+    likelihoods_tuple.__module__ = __name__
+
+
+class homogeneous(_models.homogeneous):
+    __doc__ = _models.homogeneous.__doc__
+    tuple_type = likelihoods_tuple

@@ -1,0 +1,385 @@
+// k_general.cuh -- draws of 5..16 reads: one CTA per (window, draw).
+//
+// Phase 1  stage the n sampled read masks of every group in shared memory.
+// Phase 2  joint-frequency table F[S] = popcount(AND_{i in S} mask_i) for all 2^n subsets
+//          (joint_frequencies_combo, HOMOGENOUES_MODELS.py:129-163), meet-in-the-middle:
+//          the reads are split into a low set (kl reads) and a high set (kh = n-kl reads);
+//          L[lo][w] and H[hi][w] hold the ANDs of each half for a chunk of wc words, and
+//          F[hi<<kl | lo] = sum_w popc(H[hi][w] & L[lo][w]) -- exactly one AND + one POPC
+//          per (subset, word), the algorithmic minimum, with no dependent chains.  A warp
+//          register-tiles TH his x (32*TL) los; L is laid out [w][lo] so a warp's loads are
+//          conflict-free, H[w][hi] is a broadcast.
+// Phase 3  the partition polynomials of likelihoods() (HOMOGENOUES_MODELS.py:185-225,
+//          RECENT_ADMIXTURE_MODELS.py:198-247, DISTANT_ADMIXTURE_MODELS.py:215-256) straight
+//          from the table, without the reference's model tables: sums over unordered
+//          2-partitions {A, full\A} and 3-partitions {A,B,C} (A owns the last read, B owns
+//          the lowest read outside A).  Integer class sums are exact (64/128-bit).
+//
+// Algorithmic work per draw: G*(2^n-1)*W word AND+POPC; 2^(n-1)-1 two-block products and
+// S(n,3) three-block products.
+#pragma once
+#include "common.cuh"
+
+namespace ldpgta {
+
+struct GeneralArgs {
+    PanelView pv;
+    int kind;
+    int n, kl, kh;           // reads per draw; low/high split
+    int wc;                  // words per table chunk
+    const int32_t *idx;      // [n_draws][n]
+    int64_t n_draws;
+    const int64_t *pos;      // optional scatter positions
+    double *out;             // [*][4]
+    uint32_t *counts_out;    // optional [n_draws][G][2^n]
+};
+
+struct GeneralSmem {         // byte offsets into dynamic shared memory
+    int masks, ltab, htab, ftab, red, total;
+};
+
+template <typename CT>
+__host__ __device__ inline GeneralSmem general_smem_layout(const PanelView &pv, int n, int kl, int kh, int wc)
+{
+    GeneralSmem s;
+    int off = 64;                                        // s_idx[16]
+    s.masks = off;
+    int words = 0;
+    for (int g = 0; g < pv.G; ++g) words += n * pv.wp[g];
+    off += words * 8;
+    s.ltab = off; off += (wc << kl) * 8;
+    s.htab = off; off += (wc << kh) * 8;
+    s.ftab = off; off += (int)(sizeof(CT) * pv.G) << n;
+    off = (off + 15) & ~15;
+    s.red = off; off += 32 * 12 * 8;
+    s.total = off;
+    return s;
+}
+
+// block-wide sum of NV 64-bit values; result valid in thread 0
+template <int NV>
+__device__ __forceinline__ void block_sum_u64(u64 *v, u64 *red)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = warp_sum_u64(v[k]);
+    if (nw == 1) return;
+    __syncthreads();
+    if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < NV; ++k) red[warp * NV + k] = v[k];
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int w = 1; w < nw; ++w)
+#pragma unroll
+            for (int k = 0; k < NV; ++k) v[k] += red[w * NV + k];
+}
+
+__device__ __forceinline__ void split_u128(u128 x, u64 *limb)
+{
+#pragma unroll
+    for (int k = 0; k < 4; ++k) limb[k] = (u64)(uint32_t)(x >> (32 * k));
+}
+__device__ __forceinline__ u128 join_u128(const u64 *limb)
+{
+    u128 x = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) x += (u128)limb[k] << (32 * k);
+    return x;
+}
+
+// Splits the free reads of `rest` (all but its lowest) between the 32 lanes: the highest
+// (up to five) free bits are fixed by the lane id, the others are enumerated by every lane.
+struct LaneSplit {
+    uint32_t low, x_hi, hi_mask, lo_mask;
+    bool active;
+};
+__device__ __forceinline__ LaneSplit lane_split(uint32_t rest, int lane)
+{
+    LaneSplit s;
+    s.low = rest & (0u - rest);
+    uint32_t tmp = rest ^ s.low;
+    const int nf = __popc(tmp), nh = nf < 5 ? nf : 5;
+    s.x_hi = 0; s.hi_mask = 0;
+    for (int k = 0; k < nh; ++k) {
+        const uint32_t bit = 1u << (31 - __clz(tmp));
+        tmp ^= bit;
+        s.hi_mask |= bit;
+        if ((lane >> (nh - 1 - k)) & 1) s.x_hi |= bit;
+    }
+    s.lo_mask = tmp;
+    s.active = lane < (1 << nh);
+    return s;
+}
+
+template <int TH, int TL, typename CT>
+__global__ void k_general(const GeneralArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int n = a.n, kl = a.kl, kh = a.kh, G = a.pv.G;
+    const int LS = 1 << kl, HS = 1 << kh, NS = 1 << n;
+    const GeneralSmem lay = general_smem_layout<CT>(a.pv, n, kl, kh, a.wc);
+    int32_t *s_idx = reinterpret_cast<int32_t *>(smem);
+    u64 *s_masks = reinterpret_cast<u64 *>(smem + lay.masks);
+    u64 *ltab = reinterpret_cast<u64 *>(smem + lay.ltab);
+    u64 *htab = reinterpret_cast<u64 *>(smem + lay.htab);
+    CT *ftab = reinterpret_cast<CT *>(smem + lay.ftab);
+    u64 *red = reinterpret_cast<u64 *>(smem + lay.red);
+
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, NW = T >> 5;
+    const uint32_t full = (uint32_t)NS - 1u, top = 1u << (n - 1);
+
+    for (int64_t draw = blockIdx.x; draw < a.n_draws; draw += gridDim.x) {
+        __syncthreads();                                     // previous draw done with shared memory
+        if (tid < n) s_idx[tid] = __ldg(a.idx + draw * n + tid);
+        __syncthreads();
+
+        // ---- phase 1: stage the masks ---------------------------------------------------
+        {
+            int goff = 0;
+            for (int g = 0; g < G; ++g) {
+                const int wp = a.pv.wp[g], slots = wp >> 1;
+                for (int e = tid; e < n * slots; e += T) {
+                    const int i = e / slots, s = e - i * slots;
+                    const uint4 v = ldg128(a.pv.masks[g] + (int64_t)s_idx[i] * wp + 2 * s);
+                    *reinterpret_cast<uint4 *>(s_masks + goff + i * wp + 2 * s) = v;
+                }
+                goff += n * wp;
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 2: joint-frequency tables ---------------------------------------------
+        {
+            int goff = 0;
+            for (int g = 0; g < G; ++g) {
+                const int wp = a.pv.wp[g];
+                const u64 *M = s_masks + goff;
+                CT *F = ftab + ((size_t)g << n);
+                for (int w0 = 0; w0 < wp; w0 += a.wc) {
+                    const int cw = min(a.wc, wp - w0);
+                    if (w0) __syncthreads();                 // tables of the previous chunk consumed
+                    for (int e = tid; e < (cw << kl); e += T) {
+                        const int w = e >> kl, id = e & (LS - 1);
+                        u64 v = ~0ull;
+                        for (int i = 0; i < kl; ++i)
+                            if ((id >> i) & 1) v &= M[i * wp + w0 + w];
+                        ltab[e] = v;
+                    }
+                    for (int e = tid; e < (cw << kh); e += T) {
+                        const int w = e >> kh, id = e & (HS - 1);
+                        u64 v = ~0ull;
+                        for (int i = 0; i < kh; ++i)
+                            if ((id >> i) & 1) v &= M[(kl + i) * wp + w0 + w];
+                        htab[e] = v;
+                    }
+                    __syncthreads();
+                    const int ntiles = HS / TH;
+                    for (int tile = warp; tile < ntiles; tile += NW) {
+                        const int hi0 = tile * TH;
+                        uint32_t acc[TH][TL];
+#pragma unroll
+                        for (int h = 0; h < TH; ++h)
+#pragma unroll
+                            for (int j = 0; j < TL; ++j) acc[h][j] = 0;
+#pragma unroll 2
+                        for (int w = 0; w < cw; ++w) {
+                            u64 l[TL];
+#pragma unroll
+                            for (int j = 0; j < TL; ++j) l[j] = (lane + 32 * j < LS) ? ltab[(w << kl) + lane + 32 * j] : 0ull;
+#pragma unroll
+                            for (int h = 0; h < TH; ++h) {
+                                const u64 hv = htab[(w << kh) + hi0 + h];
+#pragma unroll
+                                for (int j = 0; j < TL; ++j) acc[h][j] += __popcll(hv & l[j]);
+                            }
+                        }
+#pragma unroll
+                        for (int h = 0; h < TH; ++h)
+#pragma unroll
+                            for (int j = 0; j < TL; ++j) {
+                                const int fi = ((hi0 + h) << kl) | (lane + 32 * j);
+                                if (lane + 32 * j >= LS) continue;          // fewer than 32 low subsets (n < 5)
+                                if (w0 == 0) F[fi] = (CT)acc[h][j];
+                                else F[fi] = (CT)(F[fi] + acc[h][j]);
+                            }
+                    }
+                }
+                goff += n * wp;
+            }
+        }
+        __syncthreads();
+        if (tid < G) ftab[(size_t)tid << n] = 0;             // the empty subset is not a joint frequency
+        __syncthreads();
+
+        if (a.counts_out) {
+            uint32_t *o = a.counts_out + ((draw * G) << n);
+            for (int e = tid; e < (G << n); e += T) o[e] = ftab[e];
+        }
+
+        // ---- phase 3: partition polynomials ----------------------------------------------
+        const double p2n1 = (double)(1u << (n - 1));
+        double p3n1 = 1.0;
+        for (int i = 1; i < n; ++i) p3n1 *= 3.0;
+        const double p3n = 3.0 * p3n1, p2n = 2.0 * p2n1;
+        double res[4];
+
+        if (a.kind == LDPGTA_HOMOGENEOUS) {
+            const CT *F = ftab;
+            u64 two = 0, two_sph = 0;
+            u128 three = 0;
+            for (uint32_t A = top + warp; A < full; A += NW) {
+                const uint32_t rest = full ^ A;
+                const u64 Fa = F[A];
+                if (lane == 0) {
+                    const u64 prod = Fa * (u64)F[rest];
+                    two += prod;
+                    two_sph += prod * ((1ull << __popc(A)) + (1ull << __popc(rest)));
+                }
+                const LaneSplit s = lane_split(rest, lane);
+                if (s.active && Fa) {
+                    uint32_t x_lo = s.lo_mask;
+                    bool go = true;
+                    if (s.x_hi == s.hi_mask) {               // x == all free reads would leave C empty
+                        go = s.lo_mask != 0;
+                        x_lo = (s.lo_mask - 1) & s.lo_mask;
+                    }
+                    u64 inner = 0;
+                    while (go) {
+                        const uint32_t B = s.low | s.x_hi | x_lo;
+                        inner += (u64)F[B] * (u64)F[rest ^ B];
+                        go = x_lo != 0;
+                        x_lo = (x_lo - 1) & s.lo_mask;
+                    }
+                    three += (u128)Fa * inner;
+                }
+            }
+            u64 v[6];
+            v[0] = two; v[1] = two_sph;
+            split_u128(three, v + 2);
+            block_sum_u64<6>(v, red);
+            if (tid == 0) {
+                const double N = (double)a.pv.nhap[0];
+                const u64 Ff = F[full];
+                const double d_two = (double)v[0], d_sph = (double)v[1], d_three = u128_to_double(join_u128(v + 2));
+                res[0] = (double)Ff / N;
+                res[1] = (double)Ff / (p2n1 * N) + d_two / p2n1 / (N * N);
+                res[2] = (double)(Ff * ((1ull << n) + 1ull)) / (p3n * N) + d_sph / p3n / (N * N);
+                res[3] = (double)Ff / (p3n1 * N) + (2.0 * d_two) / p3n1 / (N * N) + (2.0 * d_three) / p3n1 / (N * N * N);
+            }
+        } else if (a.kind == LDPGTA_RECENT_ADMIXTURE) {
+            const CT *F = ftab, *Gt = ftab + NS;
+            u64 ff = 0, gg = 0, fg = 0, fg_sph = 0;
+            u128 ffg = 0, ggf = 0;
+            for (uint32_t A = top + warp; A < full; A += NW) {
+                const uint32_t rest = full ^ A;
+                const u64 Fa = F[A], Ga = Gt[A];
+                if (lane == 0) {
+                    const u64 cross = Fa * (u64)Gt[rest] + Ga * (u64)F[rest];
+                    ff += Fa * (u64)F[rest];
+                    gg += Ga * (u64)Gt[rest];
+                    fg += cross;
+                    fg_sph += cross * ((1ull << __popc(A)) + (1ull << __popc(rest)));
+                }
+                const LaneSplit s = lane_split(rest, lane);
+                if (s.active && (Fa | Ga)) {
+                    uint32_t x_lo = s.lo_mask;
+                    bool go = true;
+                    if (s.x_hi == s.hi_mask) {
+                        go = s.lo_mask != 0;
+                        x_lo = (s.lo_mask - 1) & s.lo_mask;
+                    }
+                    u64 in_ff = 0, in_gg = 0, in_fg = 0;
+                    while (go) {
+                        const uint32_t B = s.low | s.x_hi | x_lo, C = rest ^ B;
+                        const u64 fb = F[B], fc = F[C], gb = Gt[B], gc = Gt[C];
+                        in_ff += fb * fc;
+                        in_gg += gb * gc;
+                        in_fg += fb * gc + gb * fc;
+                        go = x_lo != 0;
+                        x_lo = (x_lo - 1) & s.lo_mask;
+                    }
+                    ffg += (u128)Ga * in_ff + (u128)Fa * in_fg;
+                    ggf += (u128)Fa * in_gg + (u128)Ga * in_fg;
+                }
+            }
+            u64 v[12];
+            v[0] = ff; v[1] = gg; v[2] = fg; v[3] = fg_sph;
+            split_u128(ffg, v + 4);
+            split_u128(ggf, v + 8);
+            block_sum_u64<12>(v, red);
+            if (tid == 0) {
+                const double M = (double)a.pv.nhap[0], N = (double)a.pv.nhap[1];
+                const double s = (double)F[full] / M + (double)Gt[full] / N;
+                const double d_ff = (double)v[0], d_gg = (double)v[1], d_fg = (double)v[2], d_sph = (double)v[3];
+                const double d_ffg = u128_to_double(join_u128(v + 4)), d_ggf = u128_to_double(join_u128(v + 8));
+                res[0] = s / 2.0;
+                res[1] = s / p2n + d_fg / p2n1 / (2.0 * M * N);
+                res[2] = s * (double)((1ull << n) + 1ull) / (2.0 * p3n) + d_sph / p3n / (2.0 * M * N);
+                res[3] = s / (2.0 * p3n1)
+                       + (d_ff / (M * M) + d_gg / (N * N) + 2.0 * d_fg / (M * N)) * 2.0 / p3n1 / 6.0
+                       + (d_ffg / M + d_ggf / N) * 2.0 / p3n1 / (6.0 * M * N);
+            }
+        } else {
+            // distant admixture: e(S) = sum_g p_g * cnt_g(S) / N_g (DISTANT_ADMIXTURE_MODELS.py:136-139)
+            double cg[MAXG];
+            for (int g = 0; g < G; ++g) cg[g] = a.pv.coef[g];
+            auto E = [&](uint32_t S) {
+                double e = 0.0;
+                for (int g = 0; g < G; ++g) e = e + cg[g] * (double)ftab[((size_t)g << n) + S] / (double)a.pv.nhap[g];
+                return e;
+            };
+            double two = 0, two_sph = 0, three = 0;
+            for (uint32_t A = top + warp; A < full; A += NW) {
+                const uint32_t rest = full ^ A;
+                const double Ea = E(A);
+                if (lane == 0) {
+                    const double prod = Ea * E(rest);
+                    two += prod;
+                    two_sph += prod * (double)((1ull << __popc(A)) + (1ull << __popc(rest)));
+                }
+                const LaneSplit s = lane_split(rest, lane);
+                if (s.active && Ea != 0.0) {
+                    uint32_t x_lo = s.lo_mask;
+                    bool go = true;
+                    if (s.x_hi == s.hi_mask) {
+                        go = s.lo_mask != 0;
+                        x_lo = (s.lo_mask - 1) & s.lo_mask;
+                    }
+                    double inner = 0;
+                    while (go) {
+                        const uint32_t B = s.low | s.x_hi | x_lo;
+                        inner += E(B) * E(rest ^ B);
+                        go = x_lo != 0;
+                        x_lo = (x_lo - 1) & s.lo_mask;
+                    }
+                    three += Ea * inner;
+                }
+            }
+            two = warp_sum_f64(two); two_sph = warp_sum_f64(two_sph); three = warp_sum_f64(three);
+            double *redd = reinterpret_cast<double *>(red);
+            if (NW > 1) {
+                __syncthreads();
+                if (lane == 0) { redd[warp * 3] = two; redd[warp * 3 + 1] = two_sph; redd[warp * 3 + 2] = three; }
+                __syncthreads();
+                if (tid == 0)
+                    for (int w = 1; w < NW; ++w) { two += redd[w * 3]; two_sph += redd[w * 3 + 1]; three += redd[w * 3 + 2]; }
+            }
+            if (tid == 0) {
+                const double Ef = E(full);
+                res[0] = Ef;
+                res[1] = Ef / p2n1 + two / p2n1;
+                res[2] = (double)((1ull << n) + 1ull) / p3n * Ef + two_sph / p3n;
+                res[3] = Ef / p3n1 + 2.0 * two / p3n1 + 2.0 * three / p3n1;
+            }
+        }
+        if (tid == 0) {
+            const int64_t o = a.pos ? a.pos[draw] : draw;
+            double2 *dst = reinterpret_cast<double2 *>(a.out + 4 * o);
+            dst[0] = make_double2(res[0], res[1]);
+            dst[1] = make_double2(res[2], res[3]);
+        }
+    }
+}
+
+}  // namespace ldpgta

@@ -1,0 +1,159 @@
+// k_stats.cuh -- mask construction and the reductions that follow the bootstrap loop.
+#pragma once
+#include "common.cuh"
+
+namespace ldpgta {
+
+// Pads caller rows [n_rows][words] to [n_rows][wp] and complements REF alleles inside the
+// group's N bits (hap ^ (2^N - 1), HOMOGENOUES_MODELS.py:87,94).
+__global__ void k_pack_rows(const uint64_t *__restrict__ src, const uint8_t *__restrict__ complement,
+                            uint64_t *__restrict__ dst, int64_t n_rows, int words, int wp, uint32_t nhap)
+{
+    const int64_t total = n_rows * wp;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / wp;
+        const int w = (int)(e - r * wp);
+        u64 v = 0;
+        if (w < words) {
+            v = src[r * words + w];
+            const int bits = (int)nhap - 64 * w;                 // valid bits in this word
+            const u64 valid = bits >= 64 ? ~0ull : ((1ull << bits) - 1ull);
+            if (complement && complement[r]) v = ~v;
+            v &= valid;
+        }
+        dst[e] = v;
+    }
+}
+
+// mask[r] = AND of allele rows allele_idx[off[r] .. off[r+1])  (build_intrenal_hap_dict,
+// HOMOGENOUES_MODELS.py:112-123, once per read instead of once per draw)
+__global__ void k_build_read_masks(const uint64_t *__restrict__ rows, const int32_t *__restrict__ allele_idx,
+                                   const int64_t *__restrict__ off, int64_t n_reads, int wp, uint64_t *__restrict__ out)
+{
+    const int slots = wp >> 1;
+    const int64_t total = n_reads * slots;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / slots;
+        const int s = (int)(e - r * slots);
+        uint4 v = make_uint4(~0u, ~0u, ~0u, ~0u);
+        const int64_t b = off[r], eend = off[r + 1];
+        if (b == eend) v = make_uint4(0, 0, 0, 0);
+        for (int64_t k = b; k < eend; ++k) {
+            const uint4 m = ldg128(rows + (int64_t)allele_idx[k] * wp + 2 * s);
+            v.x &= m.x; v.y &= m.y; v.z &= m.z; v.w &= m.w;
+        }
+        *reinterpret_cast<uint4 *>(out + r * wp + 2 * s) = v;
+    }
+}
+
+// LLR(y, x), ANEUPLOIDY_TEST.py:78-90
+__device__ __forceinline__ double llr(double y, double x)
+{
+    if (x != 0.0 && y != 0.0) return log(y / x);
+    if (x != 0.0) return -1.23456789;
+    if (y != 0.0) return +1.23456789;
+    return 0.0;
+}
+
+// pairs of statistics() (ANEUPLOIDY_TEST.py:298): indices into (monosomy, disomy, SPH, BPH)
+__device__ __constant__ int c_pair_num[5] = {3, 1, 3, 1, 2};
+__device__ __constant__ int c_pair_den[5] = {2, 0, 1, 2, 0};
+
+__global__ void k_llr(const double *__restrict__ lik, int64_t n_draws, double *__restrict__ out)
+{
+    for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < n_draws; d += (int64_t)gridDim.x * blockDim.x) {
+        const double2 a = reinterpret_cast<const double2 *>(lik)[2 * d], b = reinterpret_cast<const double2 *>(lik)[2 * d + 1];
+        const double v[4] = {a.x, a.y, b.x, b.y};
+#pragma unroll
+        for (int p = 0; p < 5; ++p) out[p * n_draws + d] = llr(v[c_pair_num[p]], v[c_pair_den[p]]);
+    }
+}
+
+// error-free accumulation (Neumaier) so that window means match the reference's
+// exact-rational statistics.mean/variance (ANEUPLOIDY_TEST.py:51-56) to the last bits
+struct Comp {
+    double s, c;
+    __device__ __forceinline__ void add(double x)
+    {
+        const double t = s + x;
+        c += (fabs(s) >= fabs(x)) ? ((s - t) + x) : ((x - t) + s);
+        s = t;
+    }
+    __device__ __forceinline__ double value() const { return s + c; }
+};
+
+__device__ __forceinline__ double warp_sum_comp(Comp a)
+{
+#pragma unroll
+    for (int m = 16; m; m >>= 1) {
+        const double os = __shfl_xor_sync(0xffffffffu, a.s, m), oc = __shfl_xor_sync(0xffffffffu, a.c, m);
+        a.add(os);
+        a.c += oc;
+    }
+    return a.value();
+}
+
+// one warp per (pair, window): mean and sample variance of the window's LLRs
+__global__ void k_window_mean_var(const double *__restrict__ llrs, const int64_t *__restrict__ woff, int64_t n_windows,
+                                  int64_t n_draws, double *__restrict__ mean_var)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (gw >= 5 * n_windows) return;
+    const int p = (int)(gw / n_windows);
+    const int64_t w = gw - (int64_t)p * n_windows;
+    const int64_t b = woff[w], e = woff[w + 1];
+    const double *x = llrs + (int64_t)p * n_draws;
+    Comp acc = {0.0, 0.0};
+    for (int64_t i = b + lane; i < e; i += 32) acc.add(x[i]);
+    const double cnt = (double)(e - b);
+    const double mean = warp_sum_comp(acc) / cnt;
+    Comp sq = {0.0, 0.0};
+    for (int64_t i = b + lane; i < e; i += 32) { const double d = x[i] - mean; sq.add(d * d); }
+    const double ss = warp_sum_comp(sq);
+    if (lane == 0) {
+        mean_var[2 * gw] = mean;
+        mean_var[2 * gw + 1] = (e - b > 1) ? ss / (cnt - 1.0) : nan("");
+    }
+}
+
+// one block per (pair, column): deterministic sums over windows.
+//   column 0: sum_w sum_i x_wi ; column 1: #windows ; column 2: #windows with mean < 0 ;
+//   column 3+i: sum_w x_wi (i < n_cols)
+__global__ void k_chrom_partials(const double *__restrict__ llrs, const int64_t *__restrict__ woff, int64_t n_windows,
+                                 int64_t n_draws, const double *__restrict__ mean_var, int n_cols,
+                                 double *__restrict__ partials)
+{
+    __shared__ double sh_s[32], sh_c[32];
+    const int p = blockIdx.y, col = blockIdx.x;
+    const double *x = llrs + (int64_t)p * n_draws;
+    Comp acc = {0.0, 0.0};
+    if (col == 0) {
+        for (int64_t i = threadIdx.x; i < n_draws; i += blockDim.x) acc.add(x[i]);
+    } else if (col == 1) {
+        if (threadIdx.x == 0) acc.add((double)n_windows);
+    } else if (col == 2) {
+        for (int64_t w = threadIdx.x; w < n_windows; w += blockDim.x)
+            if (mean_var[2 * ((int64_t)p * n_windows + w)] < 0.0) acc.add(1.0);
+    } else {
+        const int i = col - 3;
+        for (int64_t w = threadIdx.x; w < n_windows; w += blockDim.x) acc.add(x[woff[w] + i]);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // combine compensated partials: first within the warp, then across warps
+#pragma unroll
+    for (int m = 16; m; m >>= 1) {
+        const double os = __shfl_xor_sync(0xffffffffu, acc.s, m), oc = __shfl_xor_sync(0xffffffffu, acc.c, m);
+        acc.add(os);
+        acc.c += oc;
+    }
+    if (lane == 0) { sh_s[warp] = acc.s; sh_c[warp] = acc.c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        Comp t = {0.0, 0.0};
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { t.add(sh_s[w]); t.c += sh_c[w]; }
+        partials[(int64_t)p * (n_cols + 3) + col] = t.value();
+    }
+}
+
+}  // namespace ldpgta

@@ -1,0 +1,633 @@
+// ldpgta_api.cu -- the C-ABI of include/ldpgta.h on top of the sm_100a kernels.
+// Build (see __graft_entry__.build):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
+#include <stdarg.h>
+#include <math.h>
+#include <algorithm>
+
+#include "common.cuh"
+#include "k_small.cuh"
+#include "k_general.cuh"
+#include "k_stats.cuh"
+
+namespace ldpgta {
+
+thread_local std::string g_last_error;
+
+inline int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+static int ensure_dev(ldpgta_ctx *c, size_t bytes)
+{
+    if (c->d_buf_bytes >= bytes) return 0;
+    if (c->d_buf) LDPGTA_CUDA(cudaFree(c->d_buf));
+    c->d_buf = nullptr; c->d_buf_bytes = 0;
+    bytes = bytes + bytes / 4 + 4096;
+    LDPGTA_CUDA(cudaMalloc(&c->d_buf, bytes));
+    c->d_buf_bytes = bytes;
+    return 0;
+}
+
+static int ensure_pin(ldpgta_ctx *c, size_t bytes)
+{
+    if (c->h_pin_bytes >= bytes) return 0;
+    if (c->h_pin) LDPGTA_CUDA(cudaFreeHost(c->h_pin));
+    c->h_pin = nullptr; c->h_pin_bytes = 0;
+    bytes = bytes + bytes / 4 + 4096;
+    LDPGTA_CUDA(cudaMallocHost(&c->h_pin, bytes));
+    c->h_pin_bytes = bytes;
+    return 0;
+}
+
+static bool is_pinned_or_device(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+static PanelView make_view(const ldpgta_ctx *c, const double *proportions)
+{
+    PanelView pv;
+    memset(&pv, 0, sizeof pv);
+    pv.G = c->G;
+    for (int g = 0; g < c->G; ++g) {
+        pv.masks[g] = c->read_masks[g];
+        pv.wp[g] = c->wp[g];
+        pv.nhap[g] = c->nhap[g];
+        pv.coef[g] = proportions ? proportions[g] : 0.0;
+    }
+    return pv;
+}
+
+static int check_kind(const ldpgta_ctx *c, int kind, const double *proportions)
+{
+    if (kind == LDPGTA_HOMOGENEOUS && c->G != 1)
+        return fail(LDPGTA_E_INVALID, "homogeneous model needs exactly one reference-panel group, context has %d", c->G);
+    if (kind == LDPGTA_RECENT_ADMIXTURE && c->G != 2)
+        return fail(LDPGTA_E_INVALID, "recent-admixture model needs exactly two reference-panel groups, context has %d", c->G);
+    if (kind == LDPGTA_DISTANT_ADMIXTURE && !proportions)
+        return fail(LDPGTA_E_INVALID, "distant-admixture model needs ancestral proportions");
+    if (kind < 0 || kind > 2) return fail(LDPGTA_E_INVALID, "unknown model kind %d", kind);
+    for (int g = 0; g < c->G; ++g)
+        if (!c->read_masks[g] || c->n_reads_g[g] != c->n_reads)
+            return fail(LDPGTA_E_STATE, "read masks of group %d are missing (upload or build them first)", g);
+    return 0;
+}
+
+// ------------------------------------------------------------------ launchers
+
+template <int NR>
+static int launch_small(ldpgta_ctx *c, const SmallArgs &a)
+{
+    int wmax = 0;
+    for (int g = 0; g < c->G; ++g) wmax = std::max(wmax, c->wp[g]);
+    const int64_t nd = a.n_draws;
+    auto go = [&](auto kern, int lpd) -> int {
+        const int threads = 128;
+        const int64_t blocks = (nd * lpd + threads - 1) / threads;
+        if (blocks > 0x7fffffffLL) return fail(LDPGTA_E_UNSUPPORTED, "batch too large for one launch");
+        kern<<<(unsigned)blocks, threads, 0, c->stream>>>(a);
+        c->launches++;
+        LDPGTA_CUDA(cudaGetLastError());
+        return 0;
+    };
+    // lanes per draw x words per lane, smallest tile that covers a row in one pass
+    if (wmax <= 8)  return go(k_small<NR, 4, 2>, 4);
+    if (wmax <= 16) return go(k_small<NR, 4, 4>, 4);
+    if (wmax <= 32) return go(k_small<NR, 8, 4>, 8);
+    if (wmax <= 48) return go(k_small<NR, 8, 6>, 8);
+    if (wmax <= 64) return go(k_small<NR, 8, 8>, 8);
+    if (wmax <= 80) return go(k_small<NR, 8, 10>, 8);
+    if (wmax <= 128) return go(k_small<NR, 16, 8>, 16);
+    return go(k_small<NR, 32, 8>, 32);                    // loops over 256-word chunks
+}
+
+struct GeneralPlan { int th, tl, nw, kl, kh, wc; bool u16; size_t smem; };
+
+static int plan_general(const ldpgta_ctx *c, int n, GeneralPlan *p)
+{
+    static const int TH[17] = {0, 0, 0, 0, 0, 1, 2, 4, 8, 4, 8, 8, 8, 8, 8, 8, 8};
+    static const int TL[17] = {0, 0, 0, 0, 0, 1, 1, 1, 1, 4, 4, 4, 4, 4, 4, 4, 4};
+    static const int NW[17] = {0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 2, 4, 8, 16, 16, 16};
+    static const int BUDGET_KB[17] = {0, 0, 16, 16, 16, 16, 16, 20, 24, 28, 32, 48, 72, 110, 220, 220, 220};
+    if (n < 5) { p->th = 1; p->tl = 1; p->nw = 1; p->kl = n; }       // likelihoods() forced on 2..4 reads
+    else { p->th = TH[n]; p->tl = TL[n]; p->nw = NW[n]; p->kl = p->tl == 1 ? 5 : 7; }
+    p->kh = n - p->kl;
+    uint32_t nmax = 0; int wmax = 0, wsum = 0;
+    for (int g = 0; g < c->G; ++g) { nmax = std::max(nmax, c->nhap[g]); wmax = std::max(wmax, c->wp[g]); wsum += c->wp[g]; }
+    p->u16 = ((size_t)c->G << n) * 4 > 64 * 1024;
+    if (p->u16 && nmax > 65535u)
+        return fail(LDPGTA_E_UNSUPPORTED, "draws of %d reads need 16-bit count tables, panel group has %u > 65535 haplotypes", n, nmax);
+    const size_t ct = p->u16 ? 2 : 4;
+    const size_t fixed = 64 + (size_t)n * wsum * 8 + ((ct * c->G) << n) + 16 + 32 * 12 * 8;
+    const size_t per_word = ((size_t)8 << p->kl) + ((size_t)8 << p->kh);
+    const size_t cap = std::min<size_t>((size_t)c->max_smem_optin, (size_t)BUDGET_KB[n] * 1024);
+    if (fixed + 2 * per_word > (size_t)c->max_smem_optin)
+        return fail(LDPGTA_E_UNSUPPORTED, "draws of %d reads with %d group(s) do not fit shared memory (%zu B fixed)", n, c->G, fixed);
+    size_t avail = cap > fixed ? cap - fixed : 0;
+    int wc = (int)(avail / per_word);
+    wc = std::max(wc, 2);
+    wc = std::min(wc, wmax);
+    // equalise the chunks: ceil(wmax / ceil(wmax / wc))
+    const int chunks = (wmax + wc - 1) / wc;
+    wc = (wmax + chunks - 1) / chunks;
+    p->wc = wc;
+    PanelView pv = make_view(c, nullptr);
+    p->smem = p->u16 ? general_smem_layout<uint16_t>(pv, n, p->kl, p->kh, wc).total
+                     : general_smem_layout<uint32_t>(pv, n, p->kl, p->kh, wc).total;
+    if (p->smem > (size_t)c->max_smem_optin)
+        return fail(LDPGTA_E_UNSUPPORTED, "draws of %d reads need %zu B of shared memory", n, p->smem);
+    return 0;
+}
+
+template <int TH, int TL, typename CT>
+static int launch_general_t(ldpgta_ctx *c, const GeneralArgs &a, const GeneralPlan &p)
+{
+    auto kern = k_general<TH, TL, CT>;
+    LDPGTA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    int per_sm = 0;
+    LDPGTA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * p.nw, p.smem));
+    if (per_sm < 1) return fail(LDPGTA_E_UNSUPPORTED, "general kernel does not fit an SM (n=%d, smem=%zu)", a.n, p.smem);
+    const int64_t resident = (int64_t)per_sm * c->sm_count;
+    const unsigned blocks = (unsigned)std::min<int64_t>(a.n_draws, resident);
+    kern<<<blocks, 32 * p.nw, p.smem, c->stream>>>(a);
+    c->launches++;
+    LDPGTA_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int launch_general(ldpgta_ctx *c, GeneralArgs a)
+{
+    GeneralPlan p;
+    if (int rc = plan_general(c, a.n, &p)) return rc;
+    a.kl = p.kl; a.kh = p.kh; a.wc = p.wc;
+#define LDPGTA_CASE(TH_, TL_)                                                         \
+    if (p.th == TH_ && p.tl == TL_)                                                   \
+        return p.u16 ? launch_general_t<TH_, TL_, uint16_t>(c, a, p) : launch_general_t<TH_, TL_, uint32_t>(c, a, p);
+    LDPGTA_CASE(1, 1) LDPGTA_CASE(2, 1) LDPGTA_CASE(4, 1) LDPGTA_CASE(8, 1) LDPGTA_CASE(4, 4) LDPGTA_CASE(8, 4)
+#undef LDPGTA_CASE
+    return fail(LDPGTA_E_UNSUPPORTED, "no kernel instance for n=%d", a.n);
+}
+
+// draws of one size, device-resident indices and outputs
+static int run_uniform(ldpgta_ctx *c, int kind, int n, const int32_t *idx_dev, int64_t n_draws, const int64_t *pos_dev,
+                       const double *proportions, double *out_dev, uint32_t *counts_dev, bool force_general = false,
+                       const PanelView *override_view = nullptr)
+{
+    if (n_draws == 0) return 0;
+    if (n < 2 || n > MAXN) return fail(LDPGTA_E_UNSUPPORTED, "draws of %d reads are outside the supported range 2..%d", n, MAXN);
+    if (n <= 4 && !force_general) {
+        SmallArgs a;
+        a.pv = override_view ? *override_view : make_view(c, proportions);
+        a.kind = kind; a.idx = idx_dev; a.n_draws = n_draws; a.pos = pos_dev; a.out = out_dev; a.counts_out = counts_dev;
+        if (n == 2) return launch_small<2>(c, a);
+        if (n == 3) return launch_small<3>(c, a);
+        return launch_small<4>(c, a);
+    }
+    GeneralArgs a;
+    a.pv = override_view ? *override_view : make_view(c, proportions);
+    a.kind = kind; a.n = n; a.kl = a.kh = a.wc = 0;
+    a.idx = idx_dev; a.n_draws = n_draws; a.pos = pos_dev; a.out = out_dev; a.counts_out = counts_dev;
+    return launch_general(c, a);
+}
+
+}  // namespace ldpgta
+
+using namespace ldpgta;
+
+// ============================================================================ C-ABI
+
+extern "C" {
+
+const char *ldpgta_last_error(void) { return g_last_error.c_str(); }
+int ldpgta_version(void) { return 100; }
+
+int ldpgta_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int ldpgta_create(int device, int n_groups, const uint32_t *n_hap, ldpgta_ctx **out)
+{
+    if (!out || !n_hap) return fail(LDPGTA_E_INVALID, "null argument");
+    if (n_groups < 1 || n_groups > MAXG) return fail(LDPGTA_E_INVALID, "n_groups must be 1..%d, got %d", MAXG, n_groups);
+    for (int g = 0; g < n_groups; ++g)
+        if (n_hap[g] == 0) return fail(LDPGTA_E_INVALID, "group %d has no haplotypes", g);
+    int ndev = ldpgta_device_count();
+    if (ndev < 1) return fail(LDPGTA_E_CUDA, "no CUDA device is visible: the likelihood engine has no CPU path");
+    if (device < 0 || device >= ndev) return fail(LDPGTA_E_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
+    LDPGTA_CUDA(cudaSetDevice(device));
+    ldpgta_ctx *c = new ldpgta_ctx();
+    c->device = device; c->G = n_groups;
+    for (int g = 0; g < n_groups; ++g) {
+        c->nhap[g] = n_hap[g];
+        c->words[g] = (int)((n_hap[g] + 63u) / 64u);
+        c->wp[g] = (c->words[g] + 1) & ~1;
+    }
+    cudaDeviceProp prop;
+    LDPGTA_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    LDPGTA_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    *out = c;
+    return 0;
+}
+
+int ldpgta_destroy(ldpgta_ctx *c)
+{
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (int g = 0; g < c->G; ++g) {
+        if (c->allele_rows[g]) cudaFree(c->allele_rows[g]);
+        if (c->read_masks[g] && c->masks_owned[g]) cudaFree(c->read_masks[g]);
+    }
+    if (c->d_buf) cudaFree(c->d_buf);
+    if (c->h_pin) cudaFreeHost(c->h_pin);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+int ldpgta_row_words(const ldpgta_ctx *c, int group)
+{
+    if (!c || group < 0 || group >= c->G) return fail(LDPGTA_E_INVALID, "bad context or group");
+    return c->words[group];
+}
+
+int ldpgta_padded_row_words(const ldpgta_ctx *c, int group)
+{
+    if (!c || group < 0 || group >= c->G) return fail(LDPGTA_E_INVALID, "bad context or group");
+    return c->wp[group];
+}
+
+int64_t ldpgta_num_reads(const ldpgta_ctx *c) { return c ? c->n_reads : 0; }
+uint64_t ldpgta_stream(const ldpgta_ctx *c) { return c ? (uint64_t)(uintptr_t)c->stream : 0; }
+int64_t ldpgta_launch_count(const ldpgta_ctx *c) { return c ? c->launches : 0; }
+
+int ldpgta_synchronize(ldpgta_ctx *c)
+{
+    if (!c) return fail(LDPGTA_E_INVALID, "null context");
+    LDPGTA_CUDA(cudaSetDevice(c->device));
+    LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int pack_to_device(ldpgta_ctx *c, int group, const uint64_t *rows, int64_t n_rows, const uint8_t *complement,
+                          uint64_t **dst)
+{
+    const int words = c->words[group], wp = c->wp[group];
+    const size_t src_bytes = (size_t)n_rows * words * 8, flag_bytes = complement ? (size_t)n_rows : 0;
+    const size_t flag_off = (src_bytes + 15) & ~(size_t)15;
+    if (int rc = ensure_dev(c, flag_off + flag_bytes + 16)) return rc;
+    if (*dst) { LDPGTA_CUDA(cudaFree(*dst)); *dst = nullptr; }
+    LDPGTA_CUDA(cudaMalloc((void **)dst, std::max<size_t>((size_t)n_rows * wp * 8, 16)));
+    if (n_rows == 0) return 0;
+    LDPGTA_CUDA(cudaMemcpyAsync(c->d_buf, rows, src_bytes, cudaMemcpyHostToDevice, c->stream));
+    if (complement)
+        LDPGTA_CUDA(cudaMemcpyAsync((char *)c->d_buf + flag_off, complement, flag_bytes, cudaMemcpyHostToDevice, c->stream));
+    const int64_t total = n_rows * wp;
+    const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)c->sm_count * 16);
+    k_pack_rows<<<blocks, 256, 0, c->stream>>>((const uint64_t *)c->d_buf,
+                                               complement ? (const uint8_t *)c->d_buf + flag_off : nullptr, *dst, n_rows,
+                                               words, wp, c->nhap[group]);
+    c->launches++;
+    LDPGTA_CUDA(cudaGetLastError());
+    LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int ldpgta_upload_allele_rows(ldpgta_ctx *c, int group, const uint64_t *rows, int64_t n_rows, const uint8_t *complement)
+{
+    if (!c || group < 0 || group >= c->G) return fail(LDPGTA_E_INVALID, "bad context or group");
+    if (n_rows < 0 || (n_rows > 0 && !rows)) return fail(LDPGTA_E_INVALID, "bad rows");
+    LDPGTA_CUDA(cudaSetDevice(c->device));
+    if (int rc = pack_to_device(c, group, rows, n_rows, complement, &c->allele_rows[group])) return rc;
+    c->n_alleles[group] = n_rows;
+    return 0;
+}
+
+int ldpgta_upload_read_masks(ldpgta_ctx *c, int group, const uint64_t *rows, int64_t n_rows)
+{
+    if (!c || group < 0 || group >= c->G) return fail(LDPGTA_E_INVALID, "bad context or group");
+    if (n_rows < 0 || (n_rows > 0 && !rows)) return fail(LDPGTA_E_INVALID, "bad rows");
+    LDPGTA_CUDA(cudaSetDevice(c->device));
+    if (c->read_masks[group] && !c->masks_owned[group]) c->read_masks[group] = nullptr;
+    if (int rc = pack_to_device(c, group, rows, n_rows, nullptr, &c->read_masks[group])) return rc;
+    c->masks_owned[group] = true;
+    c->n_reads_g[group] = n_rows;
+    c->n_reads = n_rows;
+    return 0;
+}
+
+int ldpgta_attach_read_masks_dev(ldpgta_ctx *c, int group, const uint64_t *rows_dev, int64_t n_rows)
+{
+    if (!c || group < 0 || group >= c->G) return fail(LDPGTA_E_INVALID, "bad context or group");
+    if (!rows_dev || n_rows < 0) return fail(LDPGTA_E_INVALID, "bad rows");
+    if (((uintptr_t)rows_dev & 15) != 0) return fail(LDPGTA_E_INVALID, "device rows must be 16-byte aligned");
+    LDPGTA_CUDA(cudaSetDevice(c->device));
+    if (c->read_masks[group] && c->masks_owned[group]) LDPGTA_CUDA(cudaFree(c->read_masks[group]));
+    c->read_masks[group] = const_cast<uint64_t *>(rows_dev);
+    c->masks_owned[group] = false;
+    c->n_reads_g[group] = n_rows;
+    c->n_reads = n_rows;
+    return 0;
+}
+
+int ldpgta_build_read_masks(ldpgta_ctx *c, const int32_t *allele_idx, const int64_t *read_offsets, int64_t n_reads)
+{
+    if (!c || !read_offsets || n_reads < 0) return fail(LDPGTA_E_INVALID, "bad arguments");
+    LDPGTA_CUDA(cudaSetDevice(c->device));
+    const int64_t n_alleles = c->n_alleles[0];
+    for (int g = 0; g < c->G; ++g) {
+        if (!c->allele_rows[g]) return fail(LDPGTA_E_STATE, "allele rows of group %d were not uploaded", g);
+        if (c->n_alleles[g] != n_alleles) return fail(LDPGTA_E_STATE, "groups hold different numbers of allele rows");
+    }
+    const int64_t nnz = read_offsets[n_reads];
+    if (read_offsets[0] != 0) return fail(LDPGTA_E_INVALID, "read_offsets must start at 0");
+    for (int64_t r = 0; r < n_reads; ++r)
+        if (read_offsets[r + 1] < read_offsets[r]) return fail(LDPGTA_E_INVALID, "read_offsets must be non-decreasing");
+    if (nnz > 0 && !allele_idx) return fail(LDPGTA_E_INVALID, "null allele_idx");
+    for (int64_t k = 0; k < nnz; ++k)
+        if (allele_idx[k] < 0 || allele_idx[k] >= n_alleles)
+            return fail(LDPGTA_E_INVALID, "allele index %d at %lld is outside 0..%lld", allele_idx[k], (long long)k, (long long)n_alleles - 1);
+    const size_t idx_bytes = ((size_t)nnz * 4 + 15) & ~(size_t)15, off_bytes = (size_t)(n_reads + 1) * 8;
+    if (int rc = ensure_dev(c, idx_bytes + off_bytes)) return rc;
+    int32_t *d_idx = (int32_t *)c->d_buf;
+    int64_t *d_off = (int64_t *)((char *)c->d_buf + idx_bytes);
+    if (nnz) LDPGTA_CUDA(cudaMemcpyAsync(d_idx, allele_idx, (size_t)nnz * 4, cudaMemcpyHostToDevice, c->stream));
+    LDPGTA_CUDA(cudaMemcpyAsync(d_off, read_offsets, off_bytes, cudaMemcpyHostToDevice, c->stream));
+    for (int g = 0; g < c->G; ++g) {
+        if (c->read_masks[g] && c->masks_owned[g]) LDPGTA_CUDA(cudaFree(c->read_masks[g]));
+        c->read_masks[g] = nullptr;
+        LDPGTA_CUDA(cudaMalloc((void **)&c->read_masks[g], std::max<size_t>((size_t)n_reads * c->wp[g] * 8, 16)));
+        c->masks_owned[g] = true;
+        c->n_reads_g[g] = n_reads;
+        if (n_reads) {
+            const int64_t total = n_reads * (c->wp[g] >> 1);
+            const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)c->sm_count * 16);
+            k_build_read_masks<<<blocks, 256, 0, c->stream>>>(c->allele_rows[g], d_idx, d_off, n_reads, c->wp[g], c->read_masks[g]);
+            c->launches++;
+            LDPGTA_CUDA(cudaGetLastError());
+        }
+    }
+    c->n_reads = n_reads;
+    LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int ldpgta_joint_counts(ldpgta_ctx *c, const int32_t *read_idx, int n, uint32_t *out_counts)
+{
+    if (!c || !read_idx || !out_counts) return fail(LDPGTA_E_INVALID, "null argument");
+    if (n < 2 || n > MAXN) return fail(LDPGTA_E_UNSUPPORTED, "draws of %d reads are outside the supported range 2..%d", n, MAXN);
+    LDPGTA_CUDA(cudaSetDevice(c->device));
+    // counts do not depend on the model; pick the kind that matches the number of groups
+    double prop[MAXG];
+    for (int g = 0; g < MAXG; ++g) prop[g] = 1.0 / c->G;
+    const int kind = c->G == 1 ? LDPGTA_HOMOGENEOUS : LDPGTA_DISTANT_ADMIXTURE;
+    if (int rc = check_kind(c, kind, prop)) return rc;
+    for (int i = 0; i < n; ++i)
+        if (read_idx[i] < 0 || read_idx[i] >= c->n_reads)
+            return fail(LDPGTA_E_INVALID, "read index %d is outside 0..%lld", read_idx[i], (long long)c->n_reads - 1);
+    const size_t cnt_bytes = ((size_t)c->G << n) * 4;
+    if (int rc = ensure_dev(c, 64 + 32 + cnt_bytes)) return rc;
+    int32_t *d_idx = (int32_t *)c->d_buf;
+    double *d_out = (double *)((char *)c->d_buf + 64);
+    uint32_t *d_cnt = (uint32_t *)((char *)c->d_buf + 96);
+    LDPGTA_CUDA(cudaMemcpyAsync(d_idx, read_idx, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+    if (int rc = run_uniform(c, kind, n, d_idx, 1, nullptr, prop, d_out, d_cnt)) return rc;
+    LDPGTA_CUDA(cudaMemcpyAsync(out_counts, d_cnt, cnt_bytes, cudaMemcpyDeviceToHost, c->stream));
+    LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int ldpgta_get_likelihoods(ldpgta_ctx *c, int kind, const int32_t *allele_idx, const int64_t *read_offsets, int n,
+                           const double *proportions, int general_formula, double *out, uint32_t *counts_out)
+{
+    if (!c || !allele_idx || !read_offsets || !out) return fail(LDPGTA_E_INVALID, "null argument");
+    if (n < 2 || n > MAXN) return fail(LDPGTA_E_UNSUPPORTED, "%d haplotypes per call are outside the supported range 2..%d", n, MAXN);
+    LDPGTA_CUDA(cudaSetDevice(c->device));
+    if (kind == LDPGTA_HOMOGENEOUS && c->G != 1) return fail(LDPGTA_E_INVALID, "homogeneous model needs exactly one group");
+    if (kind == LDPGTA_RECENT_ADMIXTURE && c->G != 2) return fail(LDPGTA_E_INVALID, "recent-admixture model needs exactly two groups");
+    if (kind == LDPGTA_DISTANT_ADMIXTURE && !proportions) return fail(LDPGTA_E_INVALID, "distant-admixture model needs ancestral proportions");
+    if (kind < 0 || kind > 2) return fail(LDPGTA_E_INVALID, "unknown model kind %d", kind);
+    const int64_t n_alleles = c->n_alleles[0];
+    for (int g = 0; g < c->G; ++g) {
+        if (!c->allele_rows[g]) return fail(LDPGTA_E_STATE, "allele rows of group %d were not uploaded", g);
+        if (c->n_alleles[g] != n_alleles) return fail(LDPGTA_E_STATE, "groups hold different numbers of allele rows");
+    }
+    if (read_offsets[0] != 0) return fail(LDPGTA_E_INVALID, "read_offsets must start at 0");
+    const int64_t nnz = read_offsets[n];
+    for (int i = 0; i < n; ++i)
+        if (read_offsets[i + 1] <= read_offsets[i]) return fail(LDPGTA_E_INVALID, "haplotype %d has no alleles", i);
+    for (int64_t k = 0; k < nnz; ++k)
+        if (allele_idx[k] < 0 || allele_idx[k] >= n_alleles)
+            return fail(LDPGTA_E_INVALID, "allele index %d is outside 0..%lld", allele_idx[k], (long long)n_alleles - 1);
+    // scratch layout: [allele_idx][offsets][draw idx 0..n-1][out 4][counts][scratch rows per group]
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 15) & ~(size_t)15; return o; };
+    const size_t o_idx = take((size_t)nnz * 4), o_off = take((size_t)(n + 1) * 8), o_draw = take((size_t)n * 4);
+    const size_t o_out = take(32), o_cnt = take(((size_t)c->G << n) * 4);
+    size_t o_rows[MAXG];
+    for (int g = 0; g < c->G; ++g) o_rows[g] = take((size_t)n * c->wp[g] * 8);
+    if (int rc = ensure_dev(c, off)) return rc;
+    char *base = (char *)c->d_buf;
+    int32_t h_draw[MAXN];
+    for (int i = 0; i < n; ++i) h_draw[i] = i;
+    LDPGTA_CUDA(cudaMemcpyAsync(base + o_idx, allele_idx, (size_t)nnz * 4, cudaMemcpyHostToDevice, c->stream));
+    LDPGTA_CUDA(cudaMemcpyAsync(base + o_off, read_offsets, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    LDPGTA_CUDA(cudaMemcpyAsync(base + o_draw, h_draw, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+    PanelView pv = make_view(c, proportions);
+    for (int g = 0; g < c->G; ++g) {
+        uint64_t *rows = (uint64_t *)(base + o_rows[g]);
+        k_build_read_masks<<<1, 256, 0, c->stream>>>(c->allele_rows[g], (const int32_t *)(base + o_idx),
+                                                     (const int64_t *)(base + o_off), n, c->wp[g], rows);
+        c->launches++;
+        pv.masks[g] = rows;
+    }
+    LDPGTA_CUDA(cudaGetLastError());
+    if (int rc = run_uniform(c, kind, n, (const int32_t *)(base + o_draw), 1, nullptr, proportions, (double *)(base + o_out),
+                             counts_out ? (uint32_t *)(base + o_cnt) : nullptr, general_formula != 0, &pv))
+        return rc;
+    LDPGTA_CUDA(cudaMemcpyAsync(out, base + o_out, 32, cudaMemcpyDeviceToHost, c->stream));
+    if (counts_out)
+        LDPGTA_CUDA(cudaMemcpyAsync(counts_out, base + o_cnt, ((size_t)c->G << n) * 4, cudaMemcpyDeviceToHost, c->stream));
+    LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int ldpgta_likelihoods_uniform_dev(ldpgta_ctx *c, int kind, int n, const int32_t *read_idx_dev, int64_t n_draws,
+                                   const double *proportions, double *out_dev)
+{
+    if (!c || !read_idx_dev || !out_dev || n_draws < 0) return fail(LDPGTA_E_INVALID, "bad arguments");
+    LDPGTA_CUDA(cudaSetDevice(c->device));
+    if (int rc = check_kind(c, kind, proportions)) return rc;
+    return run_uniform(c, kind, n, read_idx_dev, n_draws, nullptr, proportions, out_dev, nullptr);
+}
+
+int ldpgta_likelihoods_batch(ldpgta_ctx *c, int kind, const int32_t *read_idx, const int64_t *draw_offsets, int64_t n_draws,
+                             const double *proportions, double *out)
+{
+    if (!c || !draw_offsets || !out || n_draws < 0) return fail(LDPGTA_E_INVALID, "bad arguments");
+    LDPGTA_CUDA(cudaSetDevice(c->device));
+    if (int rc = check_kind(c, kind, proportions)) return rc;
+    if (n_draws == 0) return 0;
+    if (!read_idx) return fail(LDPGTA_E_INVALID, "null read_idx");
+    if (draw_offsets[0] != 0) return fail(LDPGTA_E_INVALID, "draw_offsets must start at 0");
+
+    // size classes
+    int64_t per_n[MAXN + 1] = {};
+    bool uniform = true;
+    const int n0 = (int)(draw_offsets[1] - draw_offsets[0]);
+    for (int64_t d = 0; d < n_draws; ++d) {
+        const int64_t n = draw_offsets[d + 1] - draw_offsets[d];
+        if (n < 2 || n > MAXN)
+            return fail(LDPGTA_E_UNSUPPORTED, "draw %lld has %lld reads, supported range is 2..%d", (long long)d, (long long)n, MAXN);
+        if (kind == LDPGTA_DISTANT_ADMIXTURE && n == 5)
+            return fail(LDPGTA_E_UNSUPPORTED, "distant_admixture has no likelihoods5 (reference: DISTANT_ADMIXTURE_MODELS.py:312-313 raises AttributeError)");
+        per_n[n]++;
+        uniform = uniform && n == n0;
+    }
+    const int64_t nnz = draw_offsets[n_draws];
+    for (int64_t k = 0; k < nnz; ++k)
+        if (read_idx[k] < 0 || read_idx[k] >= c->n_reads)
+            return fail(LDPGTA_E_INVALID, "read index %d at %lld is outside 0..%lld", read_idx[k], (long long)k, (long long)c->n_reads - 1);
+
+    const size_t idx_bytes = ((size_t)nnz * 4 + 15) & ~(size_t)15;
+    const size_t pos_bytes = uniform ? 0 : (size_t)n_draws * 8;
+    const size_t out_bytes = (size_t)n_draws * 32;
+    if (int rc = ensure_dev(c, idx_bytes + pos_bytes + out_bytes)) return rc;
+    int32_t *d_idx = (int32_t *)c->d_buf;
+    int64_t *d_pos = (int64_t *)((char *)c->d_buf + idx_bytes);
+    double *d_out = (double *)((char *)c->d_buf + idx_bytes + pos_bytes);
+
+    if (uniform) {
+        const void *src = read_idx;
+        if (!is_pinned_or_device(read_idx)) {
+            if (int rc = ensure_pin(c, std::max(idx_bytes, out_bytes))) return rc;
+            memcpy(c->h_pin, read_idx, (size_t)nnz * 4);
+            src = c->h_pin;
+        }
+        LDPGTA_CUDA(cudaMemcpyAsync(d_idx, src, (size_t)nnz * 4, cudaMemcpyHostToDevice, c->stream));
+        if (int rc = run_uniform(c, kind, n0, d_idx, n_draws, nullptr, proportions, d_out, nullptr)) return rc;
+    } else {
+        // regroup the draws by size; outputs are scattered back to their original positions
+        if (int rc = ensure_pin(c, idx_bytes + pos_bytes)) return rc;
+        int32_t *h_idx = (int32_t *)c->h_pin;
+        int64_t *h_pos = (int64_t *)((char *)c->h_pin + idx_bytes);
+        int64_t idx_start[MAXN + 2] = {}, pos_start[MAXN + 2] = {};
+        for (int n = 2; n <= MAXN; ++n) {
+            idx_start[n + 1] = idx_start[n] + per_n[n] * n;
+            pos_start[n + 1] = pos_start[n] + per_n[n];
+        }
+        int64_t fill[MAXN + 1] = {};
+        for (int64_t d = 0; d < n_draws; ++d) {
+            const int n = (int)(draw_offsets[d + 1] - draw_offsets[d]);
+            const int64_t k = fill[n]++;
+            memcpy(h_idx + idx_start[n] + k * n, read_idx + draw_offsets[d], (size_t)n * 4);
+            h_pos[pos_start[n] + k] = d;
+        }
+        LDPGTA_CUDA(cudaMemcpyAsync(d_idx, h_idx, (size_t)nnz * 4, cudaMemcpyHostToDevice, c->stream));
+        LDPGTA_CUDA(cudaMemcpyAsync(d_pos, h_pos, pos_bytes, cudaMemcpyHostToDevice, c->stream));
+        for (int n = 2; n <= MAXN; ++n)
+            if (per_n[n])
+                if (int rc = run_uniform(c, kind, n, d_idx + idx_start[n], per_n[n], d_pos + pos_start[n], proportions, d_out, nullptr))
+                    return rc;
+    }
+    if (is_pinned_or_device(out)) {
+        LDPGTA_CUDA(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+        LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
+    } else {
+        LDPGTA_CUDA(cudaStreamSynchronize(c->stream));     // pinned staging may still feed the H2D copy
+        if (int rc = ensure_pin(c, out_bytes)) return rc;
+        LDPGTA_CUDA(cudaMemcpyAsync(c->h_pin, d_out, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+        LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
+        memcpy(out, c->h_pin, out_bytes);
+    }
+    return 0;
+}
+
+int ldpgta_window_stats(ldpgta_ctx *c, const double *lik, const int64_t *window_offsets, int64_t n_windows, int n_cols,
+                        double *llr_out, double *window_mean_var, double *chrom_partials)
+{
+    if (!c || !lik || !window_offsets || n_windows < 0 || n_cols < 0) return fail(LDPGTA_E_INVALID, "bad arguments");
+    LDPGTA_CUDA(cudaSetDevice(c->device));
+    if (window_offsets[0] != 0) return fail(LDPGTA_E_INVALID, "window_offsets must start at 0");
+    const int64_t n_draws = window_offsets[n_windows];
+    for (int64_t w = 0; w < n_windows; ++w) {
+        const int64_t k = window_offsets[w + 1] - window_offsets[w];
+        if (k < 1) return fail(LDPGTA_E_INVALID, "window %lld has no draws", (long long)w);
+        if (k < n_cols) return fail(LDPGTA_E_INVALID, "window %lld has %lld draws < n_cols=%d", (long long)w, (long long)k, n_cols);
+    }
+    const int ncp = n_cols + 3;
+    const size_t lik_b = (size_t)n_draws * 32, off_b = ((size_t)(n_windows + 1) * 8 + 15) & ~(size_t)15;
+    const size_t llr_b = (size_t)n_draws * 5 * 8, mv_b = (size_t)n_windows * 5 * 2 * 8, cp_b = (size_t)5 * ncp * 8;
+    if (int rc = ensure_dev(c, lik_b + off_b + llr_b + mv_b + cp_b + 64)) return rc;
+    char *p = (char *)c->d_buf;
+    double *d_lik = (double *)p; p += lik_b;
+    int64_t *d_off = (int64_t *)p; p += off_b;
+    double *d_llr = (double *)p; p += llr_b;
+    double *d_mv = (double *)p; p += mv_b;
+    double *d_cp = (double *)p;
+    if (n_draws) LDPGTA_CUDA(cudaMemcpyAsync(d_lik, lik, lik_b, cudaMemcpyHostToDevice, c->stream));
+    LDPGTA_CUDA(cudaMemcpyAsync(d_off, window_offsets, (size_t)(n_windows + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    if (n_draws) {
+        const unsigned b1 = (unsigned)std::min<int64_t>((n_draws + 255) / 256, (int64_t)c->sm_count * 8);
+        k_llr<<<b1, 256, 0, c->stream>>>(d_lik, n_draws, d_llr);
+        c->launches++;
+        const int64_t warps = 5 * n_windows;
+        k_window_mean_var<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, c->stream>>>(d_llr, d_off, n_windows, n_draws, d_mv);
+        c->launches++;
+    }
+    k_chrom_partials<<<dim3(ncp, 5), 256, 0, c->stream>>>(d_llr, d_off, n_windows, n_draws, d_mv, n_cols, d_cp);
+    c->launches++;
+    LDPGTA_CUDA(cudaGetLastError());
+    if (llr_out && n_draws) LDPGTA_CUDA(cudaMemcpyAsync(llr_out, d_llr, llr_b, cudaMemcpyDeviceToHost, c->stream));
+    if (window_mean_var && n_windows) LDPGTA_CUDA(cudaMemcpyAsync(window_mean_var, d_mv, mv_b, cudaMemcpyDeviceToHost, c->stream));
+    if (chrom_partials) LDPGTA_CUDA(cudaMemcpyAsync(chrom_partials, d_cp, cp_b, cudaMemcpyDeviceToHost, c->stream));
+    LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int ldpgta_finish_chromosome(const double *cp, int n_cols, int first_window_draws, double *out)
+{
+    if (!cp || !out || n_cols < 0 || first_window_draws < 1) return fail(LDPGTA_E_INVALID, "bad arguments");
+    const int ncp = n_cols + 3;
+    for (int p = 0; p < 5; ++p) {
+        const double *q = cp + (size_t)p * ncp;
+        const double M = q[1], N = (double)first_window_draws;
+        const double mu = q[0] / N;                                   // sum_w (sum_i x_wi) / N   (:72)
+        double ss = 0.0;
+        for (int i = 0; i < n_cols; ++i) { const double d = q[3 + i] - mu; ss += d * d; }   // (:73)
+        out[3 * p + 0] = mu / M;                                      // (:75)
+        out[3 * p + 1] = sqrt(ss / (N - 1.0)) / M;                    // (:74); N = 1 divides by zero as the reference does
+        out[3 * p + 2] = q[2] / M;                                    // fraction_of_negative_LLRs (:313)
+    }
+    return 0;
+}
+
+int ldpgta_host_alloc(void **ptr, int64_t bytes)
+{
+    if (!ptr || bytes < 0) return fail(LDPGTA_E_INVALID, "bad arguments");
+    LDPGTA_CUDA(cudaMallocHost(ptr, (size_t)std::max<int64_t>(bytes, 16)));
+    return 0;
+}
+
+int ldpgta_host_free(void *ptr)
+{
+    if (ptr) LDPGTA_CUDA(cudaFreeHost(ptr));
+    return 0;
+}
+
+}  // extern "C"

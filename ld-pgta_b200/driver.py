@@ -1,0 +1,428 @@
+"""
+Drop-in for the driver ANEUPLOIDY_TEST.py: same functions, arguments, return
+structures, pickle formats and CLI.  The bootstrap loop (:277-286) is executed
+as ONE batched device call: every draw of every window is sampled first, with
+the same `random.sample` call sequence as the reference (so a given seed and
+PYTHONHASHSEED reproduce the reference's draws), then all draws are evaluated
+by libldpgta.so; LLRs and their per-window / per-chromosome reductions
+(statistics(), :289-325) also run on the device.
+"""
+import bz2
+import collections
+import gzip
+import os
+import pickle
+import random
+import re
+import sys
+import time
+from itertools import product
+from math import comb
+from statistics import StatisticsError, mean, pstdev, variance
+
+import numpy as np
+
+from . import _native as N
+from .engine import Engine, LLR_PAIRS, finish_chromosome
+from .models import ImplicitModels, distant_admixture, homogeneous, likelihoods_tuple, recent_admixture
+
+leg_tuple = collections.namedtuple('leg_tuple', ('chr_id', 'pos', 'ref', 'alt'))
+obs_tuple = collections.namedtuple('obs_tuple', ('pos', 'read_id', 'base'))
+comb_tuple = collections.namedtuple('comb_tuple', ('ref', 'alt', 'hap'))
+
+
+def popcount(x):
+    return x.bit_count()
+
+
+def mean_and_var(x):
+    """ Mean and sample variance (ANEUPLOIDY_TEST.py:51-56). """
+    cache = tuple(x)
+    m = mean(cache)
+    return m, variance(cache, xbar=m)
+
+
+def mean_and_std(x):
+    """ Mean and population standard deviation (ANEUPLOIDY_TEST.py:58-63). """
+    cache = tuple(x)
+    m = mean(cache)
+    return m, pstdev(cache, mu=m)
+
+
+def mean_and_std_of_mean_of_rnd_var(A):
+    """ ANEUPLOIDY_TEST.py:65-76 on host containers (the device version is Engine.window_stats). """
+    if type(A) == dict:
+        A = tuple(tuple(i) for i in A.values())
+    M, Nn = len(A), len(A[0])
+    mu = sum(sum(row) / Nn for row in A)
+    std = (sum((sum(col) - mu) ** 2 for col in zip(*A)) / (Nn - 1)) ** .5 / M
+    return mu / M, std
+
+
+def LLR(y, x):
+    """ log(y/x) with the sentinels of ANEUPLOIDY_TEST.py:78-90. """
+    from math import log
+    if x and y:
+        return log(y / x)
+    if x and not y:
+        return -1.23456789
+    if not x and y:
+        return +1.23456789
+    return 0
+
+
+def invert(x, n):
+    """ Inverts the n low bits of a non-negative integer (ANEUPLOIDY_TEST.py:92-94). """
+    return x ^ ((1 << n) - 1)
+
+
+class supporting_dictionaries:
+    """ reads / overlaps / positions / per-group panel rows / read scores, as
+    ANEUPLOIDY_TEST.supporting_dictionaries (:96-189). Host-side in this round. """
+
+    def __init__(self, obs_tab, leg_tab, hap_tab_per_group, number_of_haplotypes_per_group, ancestral_makeup, min_HF):
+        self.number_of_haplotypes_per_group = number_of_haplotypes_per_group
+        self.min_HF = min_HF
+        if type(ancestral_makeup) == dict:
+            self.ancestral_makeup = {group2: ancestral_makeup[group2] for group2 in hap_tab_per_group}
+        else:
+            self.ancestral_makeup = {group2: 1 / len(ancestral_makeup) for group2 in hap_tab_per_group}
+        self.leg_dict = {l[1]: (l[2], l[3]) for l in leg_tab}
+        self.reads = self.build_reads_dict(obs_tab, self.leg_dict)
+        self.overlaps = self.build_overlaps_dict(obs_tab, self.leg_dict)
+        self.positions = (*self.overlaps.keys(),)
+        self.hap_tab_per_group = self.build_hap_tab_per_group(hap_tab_per_group, leg_tab, self.positions)
+        self.score = self.build_score_dict(self.reads, self.hap_tab_per_group, self.number_of_haplotypes_per_group,
+                                           self.ancestral_makeup, self.min_HF)
+
+    def build_reads_dict(self, obs_tab, leg_dict):
+        reads = collections.defaultdict(list)
+        for pos, read_id, base in obs_tab:
+            if base in leg_dict.get(pos, ()):
+                reads[read_id].append((pos, base))
+        return reads
+
+    def build_overlaps_dict(self, obs_tab, leg_dict):
+        overlaps = collections.defaultdict(list)
+        for pos, read_id, base in obs_tab:
+            if base in leg_dict.get(pos, ()):
+                overlaps[pos].append(read_id)
+        return overlaps
+
+    def build_hap_tab_per_group(self, hap_tab_per_group, leg_tab, positions):
+        wanted = set(positions)
+        return {group2: {leg[1]: hap for leg, hap in zip(leg_tab, hap_tab) if leg[1] in wanted}
+                for group2, hap_tab in hap_tab_per_group.items()}
+
+    def build_score_dict(self, reads_dict, hap_tab_per_group, number_of_haplotypes_per_group, ancestral_makeup, min_HF):
+        """ Number of allele/complement combinations of a read whose effective haplotype
+        frequency lies in [min_HF, 1-min_HF]; SNPs with effective allele frequency outside
+        [0.01, 0.99] are ignored (ANEUPLOIDY_TEST.py:151-189). """
+        max_HF = 1 - min_HF
+        alpha = {g: ancestral_makeup[g] / n for g, n in number_of_haplotypes_per_group.items()}
+        ones = {g: (1 << n) - 1 for g, n in number_of_haplotypes_per_group.items()}
+        # :181-184 consumes per-group generators after the comprehension that made them has
+        # finished, so every group ends up weighted by the LAST group's alpha; kept for parity.
+        a_last = list(alpha.values())[-1]
+        score = {}
+        for read_id, alleles in reads_dict.items():
+            rows = collections.defaultdict(list)
+            for pos, _base in alleles:
+                freq = sum(a * hap_tab_per_group[g][pos].bit_count() for g, a in alpha.items())
+                if 0.01 <= freq <= 0.99:
+                    for g, b in ones.items():
+                        h = hap_tab_per_group[g][pos]
+                        rows[g].append((h, h ^ b))
+            if rows:
+                per_group = []
+                for g in alpha:
+                    vals = []
+                    for choice in product(*rows[g]):
+                        m = choice[0]
+                        for r in choice[1:]:
+                            m &= r
+                        vals.append(a_last * m.bit_count())
+                    per_group.append(vals)
+                score[read_id] = sum(min_HF <= sum(t) <= max_HF for t in zip(*per_group))
+            else:
+                score[read_id] = 0
+        return score
+
+
+def build_gw_dict(obs, window_size, offset, min_reads, max_reads, min_score):
+    """ Genomic windows -> read IDs, fixed or adaptive (ANEUPLOIDY_TEST.py:191-224). The last
+    window of a chromosome is never emitted and empty windows are kept, as in the reference. """
+    max_dist, max_win_size, initial_win_size = 100000, 350000, 10000
+    adaptive, window_size = (False, int(window_size)) if window_size else (True, initial_win_size)
+    offset = int(offset)
+    assert len(obs.positions), 'error: the observation table is empty.'
+    first, last = obs.positions[0] + offset, obs.positions[-1] + window_size
+    a, b = first, first + window_size
+    readIDs_in_window = set()
+    gw_dict = {}
+    for pos, overlapping_reads in obs.overlaps.items():
+        if pos < first:
+            continue
+        while b < last:
+            if a <= pos < b:
+                readIDs_in_window.update(r for r in overlapping_reads if min_score <= obs.score[r])
+                break
+            elif adaptive and 0 < len(readIDs_in_window) < min_reads and b - pos <= max_dist and b - a <= max_win_size:
+                b += 10000
+            else:
+                gw_dict[a, b - 1] = tuple(readIDs_in_window)
+                a, b = b, b + window_size
+                readIDs_in_window = set()
+    return gw_dict
+
+
+def pick_reads(reads_dict, read_IDs, max_reads):
+    """ One draw without replacement of min(R-1, max_reads) reads (ANEUPLOIDY_TEST.py:226-233). """
+    drawn_read_IDs = random.sample(read_IDs, min(len(read_IDs) - 1, max_reads))
+    return tuple(reads_dict[read_ID] for read_ID in drawn_read_IDs)
+
+
+def effective_number_of_subsamples(num_of_reads, min_reads, max_reads, subsamples):
+    """ ANEUPLOIDY_TEST.py:235-248. """
+    if min_reads <= num_of_reads and num_of_reads > max_reads:
+        return min(comb(num_of_reads, max_reads), subsamples)
+    if min_reads <= num_of_reads <= max_reads:
+        return min(num_of_reads, subsamples)
+    return 0
+
+
+def make_examiner(obs_tab, leg_tab, hap_tab, number_of_haplotypes, ancestral_makeup, models_dict, device=0):
+    """ Model selection of ANEUPLOIDY_TEST.py:263-273. """
+    if type(ancestral_makeup) == set and len(ancestral_makeup) == 1:
+        print('Assuming one ancestral population: %s.' % next(iter(ancestral_makeup)))
+        return homogeneous(obs_tab, leg_tab, hap_tab, number_of_haplotypes, models_dict, device=device)
+    if type(ancestral_makeup) == set and len(ancestral_makeup) == 2:
+        print('Assuming recent-admixture between %s and %s.' % tuple(ancestral_makeup))
+        return recent_admixture(obs_tab, leg_tab, hap_tab, number_of_haplotypes, models_dict, device=device)
+    if type(ancestral_makeup) == dict:
+        print('Assuming the following ancestral makeup:', ", ".join("{:.1f}% {}".format(100 * v, k) for k, v in ancestral_makeup.items()))
+        return distant_admixture(obs_tab, leg_tab, hap_tab, number_of_haplotypes, models_dict, ancestral_makeup, device=device)
+    raise Exception('error: unsupported ancestral-makeup.')
+
+
+def plan_draws(genomic_windows, min_reads, max_reads, subsamples, replay=None):
+    """ Every draw of the bootstrap loop, in the reference's order: for each window with
+    effN > 0, effN calls of random.sample(read_IDs, min(R-1, max_reads)) (:277-284).
+    `replay` = {window: [tuple(read ids), ...]} substitutes recorded draws. """
+    draws = {}
+    for window, read_IDs in genomic_windows.items():
+        effN = effective_number_of_subsamples(len(read_IDs), min_reads, max_reads, subsamples)
+        if effN:
+            if replay is not None:
+                draws[window] = [tuple(d) for d in replay[window][:effN]]
+            else:
+                k = min(len(read_IDs) - 1, max_reads)
+                draws[window] = [tuple(random.sample(read_IDs, k)) for _ in range(effN)]
+    return draws
+
+
+def evaluate_draws(examine, reads_dict, draws):
+    """ All draws in one device batch.  Returns {window: tuple(likelihoods_tuple)}. """
+    read_index = {}
+    allele_idx, read_offsets = [], [0]
+    rows_of = examine._rows_of
+    flat_idx, draw_offsets, sizes = [], [0], []
+    for window, ds in draws.items():
+        for ids in ds:
+            for r in ids:
+                i = read_index.get(r)
+                if i is None:
+                    i = read_index[r] = len(read_offsets) - 1
+                    allele_idx.extend(rows_of((reads_dict[r],))[0])
+                    read_offsets.append(len(allele_idx))
+                flat_idx.append(i)
+            draw_offsets.append(len(flat_idx))
+            sizes.append(len(ids))
+    if not sizes:
+        return {}
+    for n in set(sizes):
+        if n not in (2, 3, 4):
+            examine._check_table(n)
+        if n == 5 and examine.kind == N.DISTANT_ADMIXTURE:
+            raise AttributeError("'distant_admixture' object has no attribute 'likelihoods5'")
+    eng = examine._engine
+    eng.build_read_masks(allele_idx, read_offsets)
+    lik = eng.likelihoods_batch(examine.kind, flat_idx, draw_offsets, proportions=examine._proportions())
+    T = examine.tuple_type
+    out, k = {}, 0
+    rows = lik.tolist()
+    for window, ds in draws.items():
+        out[window] = tuple(T(*rows[k + j]) for j in range(len(ds)))
+        k += len(ds)
+    return out
+
+
+def bootstrap(obs_tab, leg_tab, hap_tab, number_of_haplotypes, ancestral_makeup, models_dict, window_size, subsamples,
+              offset, min_reads, max_reads, min_score, min_HF, replay=None, device=0):
+    """ ANEUPLOIDY_TEST.bootstrap (:250-287): (likelihoods, genomic_windows, fraction_of_matches). """
+    obs = supporting_dictionaries(obs_tab, leg_tab, hap_tab, number_of_haplotypes, ancestral_makeup, min_HF)
+    genomic_windows = build_gw_dict(obs, window_size, offset, min_reads, max_reads, min_score)
+    examine = make_examiner(obs_tab, leg_tab, hap_tab, number_of_haplotypes, ancestral_makeup, models_dict, device=device)
+    try:
+        draws = plan_draws(genomic_windows, min_reads, max_reads, subsamples, replay=replay)
+        likelihoods = evaluate_draws(examine, obs.reads, draws)
+        return likelihoods, genomic_windows, examine.fraction_of_matches
+    finally:
+        examine.close()
+
+
+_stats_engine = {}
+
+
+def _engine_for_stats(device=0):
+    if device not in _stats_engine:
+        _stats_engine[device] = Engine([1], device=device)
+    return _stats_engine[device]
+
+
+def chromosome_arrays(likelihoods):
+    """ {window: tuple(likelihoods_tuple)} -> (float64[n_draws, 4], window offsets, min draws, first window's draws). """
+    counts = [len(v) for v in likelihoods.values()]
+    off = np.zeros(len(counts) + 1, dtype=np.int64)
+    off[1:] = np.cumsum(counts)
+    lik = np.array([tuple(l) for v in likelihoods.values() for l in v], dtype=np.float64).reshape(-1, 4)
+    return lik, off, min(counts), counts[0]
+
+
+def statistics(likelihoods, genomic_windows, device=0):
+    """ ANEUPLOIDY_TEST.statistics (:289-325) with the LLRs and their reductions on the device. """
+    if not likelihoods:
+        return {'num_of_windows': 0}
+    window_size_mean, window_size_std = mean_and_std((j - i + 1 for (i, j) in likelihoods))
+    reads_mean, reads_std = mean_and_std((len(read_IDs) for window, read_IDs in genomic_windows.items() if window in likelihoods))
+    lik, off, n_cols, first = chromosome_arrays(likelihoods)
+    if min(np.diff(off)) < 2:
+        raise StatisticsError('variance requires at least two data points')     # statistics.variance, via :55
+    _llr, mean_var, partials = _engine_for_stats(device).window_stats(lik, off, n_cols)
+    chrom = finish_chromosome(partials, n_cols, first)
+    windows = list(likelihoods)
+    per_window = {pair: {w: (float(mean_var[p, k, 0]), float(mean_var[p, k, 1])) for k, w in enumerate(windows)}
+                  for p, pair in enumerate(LLR_PAIRS)}
+    per_chrom = {pair: {'mean_of_mean': float(chrom[p, 0]), 'std_of_mean': float(chrom[p, 1]),
+                        'fraction_of_negative_LLRs': float(chrom[p, 2])} for p, pair in enumerate(LLR_PAIRS)}
+    return {'num_of_windows': len(likelihoods), 'reads_mean': reads_mean, 'reads_std': reads_std,
+            'window_size_mean': window_size_mean, 'window_size_std': window_size_std,
+            'LLRs_per_genomic_window': per_window, 'LLRs_per_chromosome': per_chrom}
+
+
+def print_summary(obs_filename, info):
+    """ ANEUPLOIDY_TEST.print_summary (:327-343). """
+    S = info['statistics']
+    ancestral_makeup = ", ".join("{:.1f}% {}".format(100 * v, k) for k, v in info['ancestral_makeup'].items()) \
+        if type(info['ancestral_makeup']) == dict else ', '.join(info['ancestral_makeup'])
+    matched_alleles = ", ".join("{}: {:.1f}%".format(k, 100 * v) for k, v in info['statistics']['matched_alleles'].items())
+    print('\nFilename: %s' % obs_filename)
+    print('\nSummary statistics')
+    print('------------------')
+    print('Chromosome ID: %s, Depth: %.2f.' % (info['chr_id'], info['depth']))
+    print('Number of genomic windows: %d, Mean and standard error of genomic window size: %d, %d.' %
+          (S.get('num_of_windows', 0), S.get('window_size_mean', 0), S.get('window_size_std', 0)))
+    print('Mean and standard error of meaningful reads per genomic window: %.1f, %.1f.' % (S.get('reads_mean', 0), S.get('reads_std', 0)))
+    print('Ancestral makeup: %s, Fraction of alleles matched to the reference panel: %s.' % (ancestral_makeup, matched_alleles))
+    if S.get('LLRs_per_chromosome', None):
+        for (i, j), L in S['LLRs_per_chromosome'].items():
+            print(f"--- Chromosome-wide LLR between {i:s} and {j:s} ----")
+            print(f"Mean LLR: {L['mean_of_mean']:.3f}, Standard error of the mean LLR: {L['std_of_mean']:.3f}")
+            print(f"Fraction of genomic windows with a negative LLR: {L['fraction_of_negative_LLRs']:.3f}")
+
+
+def save_results(likelihoods, info, compress, obs_filename, output_filename, output_dir):
+    """ Two consecutive protocol-4 pickles, optional gz/bz2 (ANEUPLOIDY_TEST.py:345-366). """
+    Open = {'bz2': bz2.open, 'gz': gzip.open}.get(compress, open)
+    ext = ('.' + compress) * (compress in ('bz2', 'gz'))
+    obs_filename_stripped = obs_filename.rsplit('/', 1).pop()
+    default_output_filename = re.sub('(.*)obs.p(.*)', f'\\1LLR.p{ext:s}', obs_filename_stripped, 1)
+    if output_filename == '':
+        output_filename = default_output_filename
+    else:
+        output_filename += ext
+    output_dir = output_dir.rstrip('/') + '/'
+    if output_dir != '' and not os.path.exists(output_dir):
+        os.makedirs(output_dir)
+    with Open(output_dir + output_filename, "wb") as f:
+        pickle.dump(likelihoods, f, protocol=4)
+        pickle.dump(info, f, protocol=4)
+    return output_dir + output_filename
+
+
+def _opener(filename):
+    return {'bz2': bz2.open, 'gz': gzip.open}.get(filename.rsplit('.', 1)[1], open)
+
+
+def aneuploidy_test(obs_filename, leg_filename, hap_filename, ancestral_makeup, window_size, subsamples, offset, min_reads,
+                    max_reads, min_score, min_HF, output_filename, compress, **kwargs):
+    """ ANEUPLOIDY_TEST.aneuploidy_test (:368-429): same arguments, files and return value.
+    kwargs: seed, model (MODELS*.p path; optional here -- the device needs no tables), output_dir, device. """
+    time0 = time.time()
+    random.seed(a=kwargs.get('seed', None), version=2)
+
+    with _opener(obs_filename)(obs_filename, 'rb') as obs_in:
+        obs_tab = pickle.load(obs_in)
+        info = pickle.load(obs_in)
+    with _opener(hap_filename)(hap_filename, 'rb') as hap_in:
+        hap_tab = pickle.load(hap_in)
+        number_of_haplotypes = pickle.load(hap_in)
+    with _opener(leg_filename)(leg_filename, 'rb') as leg_in:
+        leg_tab = pickle.load(leg_in)
+
+    models_filename = kwargs.get('model', None)
+    if models_filename is not None:
+        with _opener(models_filename)(models_filename, 'rb') as model_in:
+            models_dict = pickle.load(model_in)
+    else:
+        models_dict = ImplicitModels()
+
+    ancestry = set(ancestral_makeup.keys()) if type(ancestral_makeup) == dict else set(ancestral_makeup)
+    assert ancestry == {*hap_tab}, 'error: the given ancestral makup does match the superpopulations (group2) in the reference panel.'
+
+    device = kwargs.get('device', 0)
+    likelihoods, genomic_windows, matched_alleles = bootstrap(obs_tab, leg_tab, hap_tab, number_of_haplotypes, ancestral_makeup,
+                                                              models_dict, window_size, subsamples, offset, min_reads,
+                                                              max_reads, min_score, min_HF, device=device)
+    some_statistics = {'matched_alleles': matched_alleles, 'runtime': time.time() - time0}
+    info.update({'ancestral_makeup': ancestral_makeup, 'window_size': window_size, 'subsamples': subsamples, 'offset': offset,
+                 'min_reads': min_reads, 'max_reads': max_reads, 'min_score': min_score, 'min_HF': min_HF,
+                 'statistics': {**statistics(likelihoods, genomic_windows, device=device), **some_statistics}})
+    if output_filename != None:
+        save_results(likelihoods, info, compress, obs_filename, output_filename, kwargs.get('output_dir', 'results'))
+    print_summary(obs_filename, info)
+    print('Done calculating LLRs for all the genomic windows in %.3f sec.' % (time.time() - time0))
+    return likelihoods, info
+
+
+def main(argv=None):
+    """ The CLI of ANEUPLOIDY_TEST.py:440-493. """
+    import argparse
+    parser = argparse.ArgumentParser(
+        description='Builds a dictionary that lists genomic windows that contain at least three reads and gives the '
+                    'associated log-likelihood BPH/SPH ratio (LLR), on a B200 GPU.')
+    parser.add_argument('obs_filename', metavar='OBS_FILENAME', type=str, help='An observations file created by MAKE_OBS_TAB.')
+    parser.add_argument('leg_filename', metavar='LEG_FILENAME', type=str, help='A legend file of the reference panel.')
+    parser.add_argument('hap_filename', metavar='HAP_FILENAME', type=str, help='A haplotype file of the reference panel.')
+    parser.add_argument('ancestral_makeup', metavar='ANCESTRAL_MAKEUP', nargs='+',
+                        help='One superpopulation (non-admixed), two (recent admixture), or NAME PROPORTION pairs (distant admixture).')
+    parser.add_argument('-w', '--window-size', type=int, metavar='INT', default='100000')
+    parser.add_argument('-s', '--subsamples', type=int, metavar='INT', default='32')
+    parser.add_argument('-o', '--offset', type=int, metavar='INT', default=0)
+    parser.add_argument('-m', '--min-reads', type=int, metavar='INT', default=6)
+    parser.add_argument('-M', '--max-reads', type=int, metavar='INT', default=4)
+    parser.add_argument('-F', '--min-HF', type=float, metavar='FLOAT', default=0.05)
+    parser.add_argument('-S', '--min-score', type=int, metavar='INT', default=2)
+    parser.add_argument('-O', '--output-filename', type=str, metavar='output_filename', default='')
+    parser.add_argument('-C', '--compress', metavar='gz/bz2/unc', type=str, default='unc', choices=['gz', 'bz2', 'unc'])
+    args = vars(parser.parse_args(argv))
+    strings_even = all(i.isalpha() for i in args['ancestral_makeup'][0::2])
+    strings_odd = all(i.isalpha() for i in args['ancestral_makeup'][1::2])
+    floats_odd = all(i.replace('.', '', 1).isdigit() for i in args['ancestral_makeup'][1::2])
+    if strings_even and strings_odd and len(args['ancestral_makeup']) in (1, 2):
+        args['ancestral_makeup'] = set(args['ancestral_makeup'])
+    elif strings_even and floats_odd:
+        args['ancestral_makeup'] = dict(zip(args['ancestral_makeup'][0::2], map(float, args['ancestral_makeup'][1::2])))
+    else:
+        raise Exception('error: Invalid argument supplied for ancestral makeup.')
+    return aneuploidy_test(**args)

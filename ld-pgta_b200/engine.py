@@ -1,0 +1,180 @@
+"""
+Host side of the likelihood engine: packs reference-panel rows into 64-bit
+haplotype bit-planes, keeps them resident on one GPU and exposes the batched
+operations of libldpgta.so (include/ldpgta.h) on numpy arrays.
+
+One `Engine` = one (sample, chromosome) = the state the reference builds in
+homogeneous.__init__ / recent_admixture.__init__ / distant_admixture.__init__
+(HOMOGENOUES_MODELS.py:52-73 and twins).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _native as N
+
+LLR_PAIRS = (('BPH', 'SPH'), ('disomy', 'monosomy'), ('BPH', 'disomy'), ('disomy', 'SPH'), ('SPH', 'monosomy'))
+
+
+def pack_ints(ints, n_bits):
+    """ Python ints (bit i = haplotype i, as produced by MAKE_REF_PANEL.py:238,315)
+    -> uint64[len, ceil(n_bits/64)], little-endian word order.  Values must fit
+    in n_bits (TEST_MODULE.py:29-30 can emit 1 << N, which no panel contains). """
+    W = (n_bits + 63) // 64
+    nbytes = 8 * W
+    limit = 1 << n_bits
+    out = bytearray(len(ints) * nbytes)
+    for i, x in enumerate(ints):
+        if x < 0 or x >= limit:
+            raise ValueError('haplotype row %d does not fit in %d bits' % (i, n_bits))
+        out[i * nbytes:(i + 1) * nbytes] = x.to_bytes(nbytes, 'little')
+    return np.frombuffer(bytes(out), dtype='<u8').reshape(len(ints), W)
+
+
+def unpack_row(row):
+    """ uint64[W] -> Python int. """
+    return int.from_bytes(np.ascontiguousarray(row, dtype='<u8').tobytes(), 'little')
+
+
+class Engine:
+    def __init__(self, haplotypes_per_group, device=0):
+        self.lib = N.load()
+        self.n_hap = [int(x) for x in haplotypes_per_group]
+        self.G = len(self.n_hap)
+        self.device = device
+        nh = np.asarray(self.n_hap, dtype=np.uint32)
+        self._ctx = ctypes.c_void_p()
+        N.check(self.lib.ldpgta_create(device, self.G, N.ptr(nh), ctypes.byref(self._ctx)))
+        self.words = [N.check(self.lib.ldpgta_row_words(self._ctx, g)) for g in range(self.G)]
+        self.padded_words = [N.check(self.lib.ldpgta_padded_row_words(self._ctx, g)) for g in range(self.G)]
+        self.n_alleles = 0
+        self._keepalive = []
+
+    # ---- lifetime -------------------------------------------------------
+    def close(self):
+        if self._ctx is not None and self._ctx.value:
+            self.lib.ldpgta_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ---- panel residency --------------------------------------------------
+    def upload_allele_rows(self, group, rows, complement=None):
+        """ rows: uint64[n_alleles, words[group]] or a sequence of Python ints;
+        complement: per-row flag, 1 = REF allele (row is complemented on device). """
+        if not isinstance(rows, np.ndarray):
+            rows = pack_ints(list(rows), self.n_hap[group])
+        rows = np.ascontiguousarray(rows, dtype=np.uint64)
+        if rows.ndim != 2 or rows.shape[1] != self.words[group]:
+            raise ValueError('rows of group %d must have shape [n, %d]' % (group, self.words[group]))
+        comp = None if complement is None else np.ascontiguousarray(complement, dtype=np.uint8)
+        if comp is not None and comp.shape != (rows.shape[0],):
+            raise ValueError('complement must have one flag per row')
+        N.check(self.lib.ldpgta_upload_allele_rows(self._ctx, group, N.ptr(rows), rows.shape[0], N.ptr(comp)))
+        self.n_alleles = rows.shape[0]
+
+    def build_read_masks(self, allele_idx, read_offsets):
+        idx = np.ascontiguousarray(allele_idx, dtype=np.int32)
+        off = np.ascontiguousarray(read_offsets, dtype=np.int64)
+        N.check(self.lib.ldpgta_build_read_masks(self._ctx, N.ptr(idx), N.ptr(off), len(off) - 1))
+
+    def upload_read_masks(self, group, rows):
+        if not isinstance(rows, np.ndarray):
+            rows = pack_ints(list(rows), self.n_hap[group])
+        rows = np.ascontiguousarray(rows, dtype=np.uint64)
+        if rows.ndim != 2 or rows.shape[1] != self.words[group]:
+            raise ValueError('rows of group %d must have shape [n, %d]' % (group, self.words[group]))
+        N.check(self.lib.ldpgta_upload_read_masks(self._ctx, group, N.ptr(rows), rows.shape[0]))
+
+    def attach_read_masks_dev(self, group, dev_ptr, n_rows, keepalive=None):
+        """ Device-resident rows [n_rows][padded_words[group]] (e.g. a torch tensor's data_ptr). """
+        N.check(self.lib.ldpgta_attach_read_masks_dev(self._ctx, group, ctypes.c_void_p(dev_ptr), n_rows))
+        if keepalive is not None:
+            self._keepalive.append(keepalive)
+
+    @property
+    def n_reads(self):
+        return int(self.lib.ldpgta_num_reads(self._ctx))
+
+    # ---- the hot path -------------------------------------------------------
+    def joint_counts(self, read_idx):
+        idx = np.ascontiguousarray(read_idx, dtype=np.int32)
+        n = len(idx)
+        out = np.zeros((self.G, 1 << n), dtype=np.uint32)
+        N.check(self.lib.ldpgta_joint_counts(self._ctx, N.ptr(idx), n, N.ptr(out)))
+        return out
+
+    def get_likelihoods(self, kind, allele_lists, proportions=None, general=False, want_counts=False):
+        """ One draw given as lists of allele-row indices (one list per haplotype). """
+        n = len(allele_lists)
+        off = np.zeros(n + 1, dtype=np.int64)
+        off[1:] = np.cumsum([len(a) for a in allele_lists])
+        idx = np.ascontiguousarray([i for a in allele_lists for i in a], dtype=np.int32)
+        out = np.zeros(4, dtype=np.float64)
+        counts = np.zeros((self.G, 1 << n), dtype=np.uint32) if want_counts and 2 <= n <= N.MAX_READS_PER_DRAW else None
+        prop = None if proportions is None else np.ascontiguousarray(proportions, dtype=np.float64)
+        N.check(self.lib.ldpgta_get_likelihoods(self._ctx, kind, N.ptr(idx), N.ptr(off), n, N.ptr(prop),
+                                                1 if general else 0, N.ptr(out), N.ptr(counts)))
+        return (out, counts) if want_counts else out
+
+    def likelihoods_batch(self, kind, read_idx, draw_offsets, proportions=None, out=None):
+        """ get_likelihoods for a batch of draws (the bootstrap loop ANEUPLOIDY_TEST.py:277-286).
+        Returns float64[n_draws, 4] = monosomy, disomy, SPH, BPH. """
+        idx = np.ascontiguousarray(read_idx, dtype=np.int32)
+        off = np.ascontiguousarray(draw_offsets, dtype=np.int64)
+        nd = len(off) - 1
+        if out is None:
+            out = np.empty((nd, 4), dtype=np.float64)
+        prop = None if proportions is None else np.ascontiguousarray(proportions, dtype=np.float64)
+        N.check(self.lib.ldpgta_likelihoods_batch(self._ctx, kind, N.ptr(idx), N.ptr(off), nd, N.ptr(prop), N.ptr(out)))
+        return out
+
+    def likelihoods_uniform_dev(self, kind, n, idx_dev_ptr, n_draws, out_dev_ptr, proportions=None):
+        """ Device-resident variant (asynchronous on the engine's stream). """
+        prop = None if proportions is None else np.ascontiguousarray(proportions, dtype=np.float64)
+        N.check(self.lib.ldpgta_likelihoods_uniform_dev(self._ctx, kind, n, ctypes.c_void_p(idx_dev_ptr), n_draws,
+                                                        N.ptr(prop), ctypes.c_void_p(out_dev_ptr)))
+
+    def synchronize(self):
+        N.check(self.lib.ldpgta_synchronize(self._ctx))
+
+    @property
+    def stream(self):
+        return int(self.lib.ldpgta_stream(self._ctx))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.ldpgta_launch_count(self._ctx))
+
+    # ---- reductions -----------------------------------------------------------
+    def window_stats(self, lik, window_offsets, n_cols):
+        """ LLRs, per-window mean / sample variance and the chromosome partial sums
+        (statistics(), ANEUPLOIDY_TEST.py:289-325) for consecutive windows of draws. """
+        lik = np.ascontiguousarray(lik, dtype=np.float64)
+        off = np.ascontiguousarray(window_offsets, dtype=np.int64)
+        nw, nd = len(off) - 1, lik.shape[0]
+        llr = np.empty((N.NUM_LLR_PAIRS, nd), dtype=np.float64)
+        mean_var = np.empty((N.NUM_LLR_PAIRS, nw, 2), dtype=np.float64)
+        partials = np.empty((N.NUM_LLR_PAIRS, n_cols + 3), dtype=np.float64)
+        N.check(self.lib.ldpgta_window_stats(self._ctx, N.ptr(lik), N.ptr(off), nw, n_cols, N.ptr(llr), N.ptr(mean_var),
+                                             N.ptr(partials)))
+        return llr, mean_var, partials
+
+
+def finish_chromosome(partials, n_cols, first_window_draws):
+    """ mean_of_mean, std_of_mean, fraction_of_negative_LLRs per LLR pair from
+    (summed) chromosome partials -- ANEUPLOIDY_TEST.py:65-76, 311-313. """
+    partials = np.ascontiguousarray(partials, dtype=np.float64)
+    out = np.empty((N.NUM_LLR_PAIRS, 3), dtype=np.float64)
+    N.check(N.load().ldpgta_finish_chromosome(N.ptr(partials), n_cols, first_window_draws, N.ptr(out)))
+    return out

@@ -1,0 +1,380 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C-ABI
+(ctypes) and through the reference-shaped Python classes, against the oracle and the golden
+vectors produced by the unmodified reference.
+
+Bars (BASELINE.json north_star): joint-frequency popcounts bit-exact; per-draw likelihoods
+within 1e-12 relative; chromosome-level LLR mean / std within 1e-9.
+"""
+import random
+
+import numpy as np
+import pytest
+
+import coracle as C
+import ldpgta_oracle as O
+from conftest import CHROM_CONFIGS, chrom_case, rel_err
+
+import ldpgta_b200 as L
+from ldpgta_b200 import driver
+
+pytestmark = pytest.mark.gpu
+
+LIK_TOL = 1e-12          # per-draw likelihoods, relative
+STAT_TOL = 1e-9          # chromosome-level LLR mean / std
+
+
+def max_rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    denom = np.maximum(np.maximum(np.abs(a), np.abs(b)), 1e-300)
+    return float(np.max(np.abs(a - b) / denom)) if a.size else 0.0
+
+
+def ld_rows(rng, n_rows, n_hap, founders=10, density=0.6):
+    """ Correlated rows (mosaic of a few founder patterns) so deep intersections stay non-empty. """
+    words = (n_hap + 63) // 64
+    base = rng.integers(0, 2 ** 64, size=(founders, words), dtype=np.uint64)
+    extra = rng.integers(0, 2 ** 64, size=(n_rows, words), dtype=np.uint64)
+    pick = rng.integers(0, founders, size=n_rows)
+    rows = base[pick] | (extra & rng.integers(0, 2 ** 64, size=(n_rows, words), dtype=np.uint64))
+    if density > 0.7:
+        rows |= rng.integers(0, 2 ** 64, size=(n_rows, words), dtype=np.uint64)
+    tail = n_hap - 64 * (words - 1)
+    if tail < 64:
+        rows[:, -1] &= np.uint64((1 << tail) - 1)
+    return rows
+
+
+def uniform_draws(rng, n_reads, n, n_draws):
+    idx = np.stack([rng.choice(n_reads, size=n, replace=False) for _ in range(n_draws)]).astype(np.int32)
+    return idx.ravel(), np.arange(0, n * n_draws + 1, n, dtype=np.int64)
+
+
+# ----------------------------------------------------------------------------------------
+# golden vectors of the reference, through the reference-shaped classes
+# ----------------------------------------------------------------------------------------
+
+def test_testmodule_golden_three_model_classes(golden_testmodule):
+    g = golden_testmodule
+    obs, leg, hap, nh = g['obs_tab'], g['leg_tab'], g['hap_tab'], g['number_of_haplotypes']
+    models = L.ImplicitModels()
+    homog = {grp: L.homogeneous(obs, leg, {grp: hap[grp]}, {grp: nh[grp]}, models) for grp in hap}
+    recent = L.recent_admixture(obs, leg, hap, nh, models)
+    distant = [L.distant_admixture(obs, leg, hap, nh, models, mk) for mk in g['makeups']]
+    worst = 0.0
+    for grp, m in homog.items():
+        assert m.fraction_of_matches == g['fraction_of_matches'][grp]
+    for rec in g['records']:
+        al = rec['alleles']
+        for grp, m in homog.items():
+            assert m.joint_frequencies_combo(al, normalize=False) == rec['homog_counts_' + grp]      # bit-exact
+            worst = max(worst, max_rel(m.likelihoods(al), rec['homog_general_' + grp]))
+            worst = max(worst, max_rel(m.get_likelihoods(al), rec['homog_get_' + grp]))
+        worst = max(worst, max_rel(recent.likelihoods(al), rec['recent_general']))
+        worst = max(worst, max_rel(recent.get_likelihoods(al), rec['recent_get']))
+        for grp in hap:
+            assert recent.joint_frequencies_combo(al, grp, normalize=False) == rec['homog_counts_' + grp]
+        for i, d in enumerate(distant):
+            freq = d.joint_frequencies_combo(al)
+            assert max(rel_err(freq[s], v) for s, v in rec['distant%d_freq' % i].items()) < 1e-15
+            worst = max(worst, max_rel(d.likelihoods(al), rec['distant%d_general' % i]))
+            if rec['n'] == 5:
+                with pytest.raises(AttributeError):
+                    d.get_likelihoods(al)
+            else:
+                worst = max(worst, max_rel(d.get_likelihoods(al), rec['distant%d_get' % i]))
+    assert worst < LIK_TOL, worst
+    # closed forms of the single-population model follow CPython's operation order: expect bit equality
+    exact = sum(tuple(homog['group0'].get_likelihoods(r['alleles'])) == tuple(r['homog_get_group0'])
+                for r in g['records'] if r['n'] in (2, 3, 4))
+    total = sum(1 for r in g['records'] if r['n'] in (2, 3, 4))
+    assert exact == total, (exact, total)
+    with pytest.raises(KeyError):
+        homog['group0'].get_likelihoods(((1, 'A'), (2, 'C')))          # unknown allele, like the reference
+    for m in list(homog.values()) + [recent] + distant:
+        m.close()
+
+
+@pytest.mark.parametrize('name', CHROM_CONFIGS)
+def test_bootstrap_replay_matches_reference(name, golden_inputs):
+    args, out = chrom_case(name, golden_inputs)
+    cfg = args['cfg']
+    lik, windows, matches = L.bootstrap(args['obs_tab'], args['leg_tab'], args['hap_tab'], args['number_of_haplotypes'],
+                                        args['ancestral_makeup'], L.ImplicitModels(), cfg['window_size'], cfg['subsamples'],
+                                        cfg['offset'], cfg['min_reads'], cfg['max_reads'], cfg['min_score'], cfg['min_HF'],
+                                        replay=out['draws'])
+    assert list(windows) == list(out['windows'])
+    assert matches == out['fraction_of_matches']
+    assert list(lik) == list(out['likelihoods'])
+    worst = 0.0
+    for w, ls in lik.items():
+        assert len(ls) == len(out['likelihoods'][w])
+        for mine, ref in zip(ls, out['likelihoods'][w]):
+            assert mine._fields == ('monosomy', 'disomy', 'SPH', 'BPH')
+            worst = max(worst, max_rel(mine, ref))
+    assert worst < LIK_TOL, worst
+    # statistics() on the device vs the reference's numbers (its likelihoods as input)
+    ref_lik = {w: tuple(L.likelihoods_tuple(*l) for l in ls) for w, ls in out['likelihoods'].items()}
+    st = L.statistics(ref_lik, out['windows'])
+    gs = out['statistics']
+    for key in ('num_of_windows', 'reads_mean', 'reads_std', 'window_size_mean', 'window_size_std'):
+        assert st[key] == gs[key]
+    for pair in L.LLR_PAIRS:
+        for key in ('mean_of_mean', 'std_of_mean', 'fraction_of_negative_LLRs'):
+            a, b = st['LLRs_per_chromosome'][pair][key], gs['LLRs_per_chromosome'][pair][key]
+            assert abs(a - b) <= STAT_TOL * max(1.0, abs(b)), (pair, key, a, b)
+        for w, (m, v) in gs['LLRs_per_genomic_window'][pair].items():
+            mm, vv = st['LLRs_per_genomic_window'][pair][w]
+            assert abs(mm - m) <= STAT_TOL * max(1.0, abs(m)) and abs(vv - v) <= STAT_TOL * max(1.0, abs(v))
+    # and end to end: device likelihoods -> device statistics
+    st2 = L.statistics(lik, windows)
+    for key in ('mean_of_mean', 'std_of_mean'):
+        a, b = st2['LLRs_per_chromosome'][('BPH', 'SPH')][key], gs['LLRs_per_chromosome'][('BPH', 'SPH')][key]
+        assert abs(a - b) <= STAT_TOL * max(1.0, abs(b))
+
+
+# ----------------------------------------------------------------------------------------
+# C-ABI against the C oracle on seeded inputs
+# ----------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize('n_hap', [50, 64, 65, 331, 2504, 5008])
+def test_homogeneous_all_draw_sizes(n_hap):
+    rng = np.random.default_rng(n_hap)
+    rows = ld_rows(rng, 96, n_hap)
+    with L.Engine([n_hap]) as eng:
+        eng.upload_read_masks(0, rows)
+        for n in range(2, 17):
+            nd = 40 if n <= 8 else (6 if n <= 13 else 2)
+            idx, off = uniform_draws(rng, 96, n, nd)
+            got = eng.likelihoods_batch(L.HOMOGENEOUS, idx, off)
+            want = C.batch([rows], [n_hap], idx, off, 0)
+            assert max_rel(got, want) < LIK_TOL, (n, max_rel(got, want))
+            cnt = eng.joint_counts(idx[:n])
+            assert np.array_equal(cnt[0], C.joint_counts(rows[idx[:n]])), n          # bit-exact popcounts
+
+
+def test_dense_panel_deep_intersections_n16():
+    """ Dense correlated rows: the 16-read intersections are non-zero, so every term of the
+    three-block sum contributes. """
+    rng = np.random.default_rng(16)
+    n_hap = 5008
+    rows = ld_rows(rng, 32, n_hap, founders=3, density=0.9)
+    with L.Engine([n_hap]) as eng:
+        eng.upload_read_masks(0, rows)
+        for n in (12, 15, 16):
+            idx, off = uniform_draws(rng, 32, n, 3)
+            cnt = eng.joint_counts(idx[:n])
+            ref = C.joint_counts(rows[idx[:n]])
+            assert ref[-1] > 0
+            assert np.array_equal(cnt[0], ref)
+            got = eng.likelihoods_batch(L.HOMOGENEOUS, idx, off)
+            want = C.batch([rows], [n_hap], idx, off, 0)
+            assert max_rel(got, want) < LIK_TOL, (n, max_rel(got, want))
+
+
+@pytest.mark.parametrize('sizes', [(331, 200), (2504, 2504), (50, 5008)])
+def test_recent_and_distant_admixture(sizes):
+    rng = np.random.default_rng(sum(sizes))
+    rows = [ld_rows(rng, 80, s) for s in sizes]
+    with L.Engine(list(sizes)) as eng:
+        for g in range(2):
+            eng.upload_read_masks(g, rows[g])
+        for n in list(range(2, 13)) + [14]:
+            nd = 24 if n <= 8 else 3
+            idx, off = uniform_draws(rng, 80, n, nd)
+            got = eng.likelihoods_batch(L.RECENT_ADMIXTURE, idx, off)
+            want = C.batch(_common_width(rows), list(sizes), idx, off, 1)
+            assert max_rel(got, want) < LIK_TOL, ('recent', n, max_rel(got, want))
+            if n != 5:
+                prop = [0.3, 0.7]
+                got = eng.likelihoods_batch(L.DISTANT_ADMIXTURE, idx, off, proportions=prop)
+                want = C.batch(_common_width(rows), list(sizes), idx, off, 2, prop)
+                assert max_rel(got, want) < LIK_TOL, ('distant', n, max_rel(got, want))
+            cnt = eng.joint_counts(idx[:n])
+            for g in range(2):
+                assert np.array_equal(cnt[g], C.joint_counts(rows[g][idx[:n]]))
+
+
+def _common_width(rows):
+    W = max(r.shape[1] for r in rows)
+    out = []
+    for r in rows:
+        p = np.zeros((r.shape[0], W), dtype=np.uint64)
+        p[:, :r.shape[1]] = r
+        out.append(p)
+    return out
+
+
+def test_three_group_distant_admixture():
+    rng = np.random.default_rng(3)
+    sizes = [120, 331, 77]
+    rows = [ld_rows(rng, 40, s) for s in sizes]
+    prop = [0.5, 0.3, 0.2]
+    with L.Engine(sizes) as eng:
+        for g in range(3):
+            eng.upload_read_masks(g, rows[g])
+        for n in (2, 3, 4, 6, 9):
+            idx, off = uniform_draws(rng, 40, n, 10)
+            got = eng.likelihoods_batch(L.DISTANT_ADMIXTURE, idx, off, proportions=prop)
+            want = C.batch(_common_width(rows), sizes, idx, off, 2, prop)
+            assert max_rel(got, want) < LIK_TOL
+
+
+def test_ragged_batch_and_scatter_order():
+    """ Draw sizes mixed inside one batch (windows with R <= max_reads draw R-1 reads). """
+    rng = np.random.default_rng(11)
+    n_hap = 5008
+    rows = ld_rows(rng, 200, n_hap)
+    sizes = rng.choice([2, 3, 4, 4, 4, 5, 6, 8, 9, 12], size=300)
+    idx = np.concatenate([rng.choice(200, size=s, replace=False) for s in sizes]).astype(np.int32)
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    with L.Engine([n_hap]) as eng:
+        eng.upload_read_masks(0, rows)
+        got = eng.likelihoods_batch(L.HOMOGENEOUS, idx, off)
+    want = C.batch([rows], [n_hap], idx, off, 0)
+    assert max_rel(got, want) < LIK_TOL
+
+
+def test_device_side_mask_construction():
+    """ ldpgta_upload_allele_rows (complement of REF alleles) + ldpgta_build_read_masks. """
+    rng = random.Random(9)
+    n_hap = 331
+    panel = [rng.getrandbits(n_hap) for _ in range(300)]
+    comp = [rng.random() < 0.5 for _ in panel]
+    ones = (1 << n_hap) - 1
+    reads = [[rng.randrange(300) for _ in range(rng.choice((1, 1, 2, 3, 5)))] for _ in range(120)]
+    masks = []
+    for r in reads:
+        m = ones
+        for a in r:
+            m &= panel[a] ^ ones if comp[a] else panel[a]
+        masks.append(m)
+    off = np.concatenate([[0], np.cumsum([len(r) for r in reads])]).astype(np.int64)
+    flat = np.array([a for r in reads for a in r], dtype=np.int32)
+    nprng = np.random.default_rng(1)
+    with L.Engine([n_hap]) as eng:
+        eng.upload_allele_rows(0, panel, np.array(comp, dtype=np.uint8))
+        eng.build_read_masks(flat, off)
+        assert eng.n_reads == 120
+        for n in (3, 4, 7):
+            idx, doff = uniform_draws(nprng, 120, n, 12)
+            for d in range(12):
+                draw = idx[d * n:(d + 1) * n]
+                assert eng.joint_counts(draw)[0].tolist()[1:] == O.joint_counts([masks[i] for i in draw])[1:]
+
+
+def test_error_behaviour():
+    rng = np.random.default_rng(2)
+    rows = ld_rows(rng, 30, 100)
+    with L.Engine([100]) as eng:
+        with pytest.raises(L.LdpgtaError):                    # masks not uploaded
+            eng.likelihoods_batch(L.HOMOGENEOUS, [0, 1], [0, 2])
+        eng.upload_read_masks(0, rows)
+        with pytest.raises(L.LdpgtaError, match='outside'):
+            eng.likelihoods_batch(L.HOMOGENEOUS, [0, 30], [0, 2])
+        with pytest.raises(L.LdpgtaError, match='supported range'):
+            eng.likelihoods_batch(L.HOMOGENEOUS, list(range(17)), [0, 17])
+        with pytest.raises(L.LdpgtaError, match='two'):
+            eng.likelihoods_batch(L.RECENT_ADMIXTURE, [0, 1], [0, 2])
+        assert eng.likelihoods_batch(L.HOMOGENEOUS, [], [0]).shape == (0, 4)
+    with L.Engine([100, 100]) as eng:
+        eng.upload_read_masks(0, rows)
+        eng.upload_read_masks(1, rows)
+        with pytest.raises(L.LdpgtaError, match='likelihoods5'):
+            eng.likelihoods_batch(L.DISTANT_ADMIXTURE, list(range(5)), [0, 5], proportions=[0.5, 0.5])
+    with L.Engine([70000]) as eng:                             # more than 65535 haplotypes: 32-bit count tables only
+        big = ld_rows(rng, 20, 70000)
+        eng.upload_read_masks(0, big)
+        idx, off = uniform_draws(rng, 20, 6, 4)
+        assert max_rel(eng.likelihoods_batch(L.HOMOGENEOUS, idx, off), C.batch([big], [70000], idx, off, 0)) < LIK_TOL
+        idx, off = uniform_draws(rng, 20, 4, 4)
+        assert max_rel(eng.likelihoods_batch(L.HOMOGENEOUS, idx, off), C.batch([big], [70000], idx, off, 0)) < LIK_TOL
+        with pytest.raises(L.LdpgtaError, match='65535'):
+            eng.likelihoods_batch(L.HOMOGENEOUS, list(range(15)), [0, 15])
+
+
+# ----------------------------------------------------------------------------------------
+# size-independent properties at BASELINE.json's full shapes
+# ----------------------------------------------------------------------------------------
+
+def test_full_size_properties_n4_genome_scale():
+    """ 5008 haplotypes, ~29k windows x 32 draws of 4 reads (config 2 shape): sampled draws against
+    the oracle, determinism, invariance to the order of reads inside a draw, and the bounds
+    0 <= likelihood <= 1, monosomy = f(all reads). """
+    rng = np.random.default_rng(2024)
+    n_hap, n_reads, n_draws = 5008, 40000, 28700 * 32
+    rows = ld_rows(rng, n_reads, n_hap)
+    win = rng.integers(0, n_reads - 150, size=n_draws // 32)
+    # four distinct reads out of the window's 150: a random start plus strictly increasing steps (< 150 in total)
+    steps = np.concatenate([rng.integers(0, 30, size=(n_draws, 1)), rng.integers(1, 40, size=(n_draws, 3))], axis=1)
+    idx = (np.repeat(win, 32)[:, None] + np.cumsum(steps, axis=1)).astype(np.int32)
+    idx = np.take_along_axis(idx, np.argsort(rng.random((n_draws, 4)), axis=1), axis=1)    # draws are unordered
+    off = np.arange(0, 4 * n_draws + 1, 4, dtype=np.int64)
+    with L.Engine([n_hap]) as eng:
+        eng.upload_read_masks(0, rows)
+        a = eng.likelihoods_batch(L.HOMOGENEOUS, idx.ravel(), off)
+        b = eng.likelihoods_batch(L.HOMOGENEOUS, idx.ravel(), off)
+        assert np.array_equal(a, b)                                            # deterministic
+        perm = eng.likelihoods_batch(L.HOMOGENEOUS, idx[:, ::-1].copy().ravel(), off)
+        assert max_rel(a, perm) < 1e-14                                       # symmetric in the reads
+        assert np.all(a >= 0) and np.all(a <= 1)
+        sample = rng.choice(n_draws, size=3000, replace=False)
+        sidx = idx[sample].ravel()
+        want = C.batch([rows], [n_hap], sidx, np.arange(0, 4 * 3000 + 1, 4, dtype=np.int64), 0)
+        assert max_rel(a[sample], want) < LIK_TOL
+        f_all = np.array([C.joint_counts(rows[idx[d]])[-1] for d in sample[:200]]) / n_hap
+        assert np.array_equal(a[sample[:200], 0], f_all)                      # monosomy = joint frequency of all reads
+
+
+def test_joint_count_table_properties_n16():
+    """ 2^16 subsets: monotone under adding a read, singletons = row popcounts, duplicate read leaves
+    the intersection unchanged. """
+    rng = np.random.default_rng(5)
+    n_hap = 5008
+    rows = ld_rows(rng, 16, n_hap, founders=2, density=0.9)
+    rows[7] = rows[3]                                                         # a duplicated read
+    with L.Engine([n_hap]) as eng:
+        eng.upload_read_masks(0, rows)
+        F = eng.joint_counts(np.arange(16, dtype=np.int32))[0].astype(np.int64)
+    pop = np.array([sum(int(w).bit_count() for w in r) for r in rows])
+    assert np.array_equal(F[1 << np.arange(16)], pop)
+    S = np.arange(1, 1 << 16)
+    for i in range(16):
+        with_i = S | (1 << i)
+        assert np.all(F[with_i] <= F[S])
+    has3 = S[(S >> 3) & 1 == 1]
+    assert np.array_equal(F[has3 | (1 << 7)], F[has3])
+    assert F[0] == 0
+
+
+def test_window_stats_against_python_statistics():
+    rng = np.random.default_rng(8)
+    counts = rng.integers(2, 33, size=200)
+    counts[0] = 32
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    lik = rng.random((off[-1], 4)) * 1e-3
+    lik[rng.random(off[-1]) < 0.05, 3] = 0.0                                   # sentinels
+    lik[rng.random(off[-1]) < 0.05, 2] = 0.0
+    likd = {(k, k): tuple(O.likelihoods_tuple(*lik[i]) for i in range(off[k], off[k + 1])) for k in range(200)}
+    want = O.statistics(likd, {w: tuple(range(10)) for w in likd})
+    n_cols = int(counts.min())
+    with L.Engine([1]) as eng:
+        llr, mean_var, partials = eng.window_stats(lik, off, n_cols)
+    chrom = L.finish_chromosome(partials, n_cols, int(counts[0]))
+    for p, pair in enumerate(L.LLR_PAIRS):
+        for k, w in enumerate(likd):
+            m, v = want['LLRs_per_genomic_window'][pair][w]
+            assert abs(mean_var[p, k, 0] - m) <= 1e-13 * max(1, abs(m))
+            assert abs(mean_var[p, k, 1] - v) <= 1e-12 * max(1, abs(v))
+        c = want['LLRs_per_chromosome'][pair]
+        assert abs(chrom[p, 0] - c['mean_of_mean']) <= STAT_TOL * max(1, abs(c['mean_of_mean']))
+        assert abs(chrom[p, 1] - c['std_of_mean']) <= STAT_TOL * max(1, abs(c['std_of_mean']))
+        assert chrom[p, 2] == c['fraction_of_negative_LLRs']
+        ref_llr = [O.LLR(getattr(l, pair[0]), getattr(l, pair[1])) for ls in likd.values() for l in ls]
+        assert max_rel(llr[p], ref_llr) < 1e-14
+    # sharding: partials of two halves of the chromosome add up to the whole (the only cross-GPU exchange)
+    with L.Engine([1]) as eng:
+        h = 100
+        _, _, p1 = eng.window_stats(lik[:off[h]], off[:h + 1], n_cols)
+        _, _, p2 = eng.window_stats(lik[off[h]:], off[h:] - off[h], n_cols)
+    both = L.finish_chromosome(p1 + p2, n_cols, int(counts[0]))
+    assert np.max(np.abs(both - chrom)) < 1e-12

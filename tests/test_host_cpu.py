@@ -1,0 +1,134 @@
+"""CPU-only tests: the C-ABI library loads and exports what include/ldpgta.h declares,
+host-side logic (packing, windowing, scores, draw planning) matches the reference's
+golden vectors, and the product fails loudly without a GPU."""
+import os
+import pickle
+import random
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import ldpgta_oracle as O
+from conftest import CHROM_CONFIGS, ROOT, chrom_case
+
+import ldpgta_b200 as L
+from ldpgta_b200 import _native, driver
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, 'include', 'ldpgta.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(ldpgta_[a-z_0-9]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = L.load()
+    declared = header_functions()
+    assert len(declared) >= 20
+    bound = sorted(name for name, _, _ in _native.SYMBOLS)
+    assert declared == bound
+    for name in declared:
+        assert getattr(lib, name) is not None
+    out = subprocess.check_output(['nm', '-D', '--defined-only', L.LIB_PATH]).decode()
+    exported = set(re.findall(r' T (ldpgta_[a-z_0-9]+)', out))
+    assert set(declared) <= exported
+    assert lib.ldpgta_version() >= 100
+
+
+def test_library_is_sm100a_native():
+    out = subprocess.run(['cuobjdump', '-lelf', L.LIB_PATH], capture_output=True, text=True).stdout
+    assert 'sm_100a' in out
+
+
+def test_no_gpu_means_loud_failure():
+    lib = L.load()
+    if lib.ldpgta_device_count() > 0:
+        pytest.skip('a GPU is visible')
+    with pytest.raises(L.LdpgtaError, match='no CUDA device'):
+        L.Engine([5008])
+
+
+def test_product_does_not_import_the_oracle():
+    """ oracle/ is test infrastructure: nothing under the package may import, load or execute it. """
+    pkg = os.path.join(ROOT, 'ld-pgta_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+\S*oracle', text, flags=re.M), f
+                assert 'liboracle' not in text and 'oracle_c' not in text and 'oracle/' not in text, f
+
+
+def test_pack_ints_roundtrip_and_range():
+    rng = random.Random(5)
+    for nbits in (1, 50, 64, 65, 331, 5008):
+        ints = [rng.getrandbits(nbits) for _ in range(7)] + [0, (1 << nbits) - 1]
+        rows = L.pack_ints(ints, nbits)
+        assert rows.shape == (9, (nbits + 63) // 64)
+        from ldpgta_b200.engine import unpack_row
+        assert [unpack_row(r) for r in rows] == ints
+    with pytest.raises(ValueError):
+        L.pack_ints([1 << 50], 50)        # TEST_MODULE.py:29-30 can emit this
+
+
+@pytest.mark.parametrize('name', CHROM_CONFIGS)
+def test_windowing_scores_and_draw_plan_match_reference(name, golden_inputs):
+    args, out = chrom_case(name, golden_inputs)
+    cfg = args['cfg']
+    obs = driver.supporting_dictionaries(args['obs_tab'], args['leg_tab'], args['hap_tab'], args['number_of_haplotypes'],
+                                         args['ancestral_makeup'], cfg['min_HF'])
+    assert dict(obs.score) == out['score']
+    gw = driver.build_gw_dict(obs, cfg['window_size'], cfg['offset'], cfg['min_reads'], cfg['max_reads'], cfg['min_score'])
+    assert list(gw) == list(out['windows'])
+    assert {w: frozenset(r) for w, r in gw.items()} == {w: frozenset(r) for w, r in out['windows'].items()}
+    # replayed plan = the reference's draws; fresh plan consumes random.sample exactly like the reference loop
+    plan = driver.plan_draws(out['windows'], cfg['min_reads'], cfg['max_reads'], cfg['subsamples'], replay=out['draws'])
+    assert {w: [tuple(d) for d in ds] for w, ds in plan.items()} == {w: [tuple(d) for d in ds] for w, ds in out['draws'].items()}
+    random.seed(2021)
+    fresh = driver.plan_draws(out['windows'], cfg['min_reads'], cfg['max_reads'], cfg['subsamples'])
+    assert fresh == {w: [tuple(d) for d in ds] for w, ds in out['draws'].items()}
+
+
+def test_effective_number_of_subsamples_matches_oracle():
+    for R in range(0, 40):
+        for mn, mx, s in ((6, 4, 32), (3, 4, 2), (18, 12, 100), (12, 16, 7)):
+            assert driver.effective_number_of_subsamples(R, mn, mx, s) == O.effective_number_of_subsamples(R, mn, mx, s)
+
+
+def test_dropin_modules_keep_reference_names():
+    code = r'''
+import sys, pickle
+sys.path.insert(0, %r)
+import HOMOGENOUES_MODELS, RECENT_ADMIXTURE_MODELS, DISTANT_ADMIXTURE_MODELS
+import ANEUPLOIDY_TEST
+t = HOMOGENOUES_MODELS.likelihoods_tuple(1.0, 2.0, 3.0, 4.0)
+assert t._fields == ('monosomy', 'disomy', 'SPH', 'BPH')
+blob = pickle.dumps(t, protocol=4)
+assert b'HOMOGENOUES_MODELS' in blob and b'ldpgta' not in blob
+assert pickle.loads(blob) == t
+for m, c in ((HOMOGENOUES_MODELS, 'homogeneous'), (RECENT_ADMIXTURE_MODELS, 'recent_admixture'), (DISTANT_ADMIXTURE_MODELS, 'distant_admixture')):
+    cls = getattr(m, c)
+    for meth in ('get_likelihoods', 'likelihoods', 'likelihoods2', 'likelihoods3', 'likelihoods4', 'joint_frequencies_combo',
+                 'joint_frequencies_redundant', 'build_hap_dict', 'build_intrenal_hap_dict'):
+        assert hasattr(cls, meth), (c, meth)
+assert hasattr(DISTANT_ADMIXTURE_MODELS.distant_admixture, 'effective_joint_frequency')
+for f in ('bootstrap', 'aneuploidy_test', 'statistics', 'LLR', 'mean_and_var', 'mean_and_std_of_mean_of_rnd_var', 'pick_reads',
+          'effective_number_of_subsamples', 'build_gw_dict', 'supporting_dictionaries', 'save_results', 'print_summary'):
+    assert hasattr(ANEUPLOIDY_TEST, f), f
+print('ok')
+''' % os.path.join(ROOT, 'ld-pgta_b200')
+    out = subprocess.check_output([sys.executable, '-c', code], cwd='/tmp').decode()
+    assert out.strip().endswith('ok')
+
+
+def test_host_statistics_helpers_match_oracle():
+    rng = random.Random(3)
+    A = {w: tuple(rng.uniform(-1, 1) for _ in range(6)) for w in range(9)}
+    assert driver.mean_and_std_of_mean_of_rnd_var(A) == O.mean_and_std_of_mean_of_rnd_var(A)
+    xs = [rng.uniform(-3, 3) for _ in range(17)]
+    assert driver.mean_and_var(xs) == O.mean_and_var(xs)
+    for y, x in ((0.0, 0.5), (0.5, 0.0), (0.0, 0.0), (0.25, 0.5)):
+        assert driver.LLR(y, x) == O.LLR(y, x)
