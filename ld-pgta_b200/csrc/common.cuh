@@ -29,6 +29,8 @@ inline int fail(int code, const char *fmt, ...) __attribute__((format(printf, 2,
 // Device-side view of the packed read masks of every group (passed by value to kernels).
 struct PanelView {
     const uint64_t *masks[MAXG];  // [n_reads][wp[g]] 64-bit words, pad bits/words zero
+    const uint32_t *popc[MAXG];   // [n_reads] popcount of each row (the singleton joint frequencies)
+    const double *norm[MAXG];     // [nhap+1] x / nhap for x = 0..nhap, IEEE division done once (exact normalisation by lookup)
     int wp[MAXG];                 // padded row length in words (even: rows are 16-byte aligned)
     uint32_t nhap[MAXG];          // haplotypes per group
     double coef[MAXG];            // distant admixture: ancestral proportion of the group
@@ -65,6 +67,59 @@ __device__ __forceinline__ double warp_sum_f64(double v)
     return v;
 }
 
+// ---- carry-save popcount of N 64-bit words --------------------------------------------
+// POPC issues at 16 lanes/clk/SM, LOP3 at 64 (profiles/INT_PEAKS.json), and the two pipes
+// run concurrently.  A carry-save adder (2 LOP3 per 32-bit half) turns three words of weight
+// w into one of weight w and one of weight 2w, so popc(x0)+...+popc(x9) needs 5 POPC.64
+// instead of 10.  Recursion: groups of three at each weight until at most two words remain.
+__device__ __forceinline__ void csa(u64 a, u64 b, u64 c, u64 &sum, u64 &carry)
+{
+    const u64 ab = a ^ b;
+    sum = ab ^ c;
+    carry = (a & b) | (ab & c);
+}
+
+template <int N>
+struct PopcSum {
+    static __device__ __forceinline__ uint32_t run(const u64 *x)
+    {
+        constexpr int K = N / 3, REM = N % 3;
+        u64 ones[K + REM], twos[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) csa(x[3 * k], x[3 * k + 1], x[3 * k + 2], ones[k], twos[k]);
+#pragma unroll
+        for (int r = 0; r < REM; ++r) ones[K + r] = x[3 * K + r];
+        return PopcSum<K + REM>::run(ones) + 2u * PopcSum<K>::run(twos);
+    }
+};
+template <> struct PopcSum<0> { static __device__ __forceinline__ uint32_t run(const u64 *) { return 0u; } };
+template <> struct PopcSum<1> { static __device__ __forceinline__ uint32_t run(const u64 *x) { return __popcll(x[0]); } };
+template <> struct PopcSum<2> { static __device__ __forceinline__ uint32_t run(const u64 *x) { return __popcll(x[0]) + __popcll(x[1]); } };
+
+// the same on 32-bit words (no 64-bit register pairing constraints for the allocator)
+__device__ __forceinline__ void csa32(uint32_t a, uint32_t b, uint32_t c, uint32_t &sum, uint32_t &carry)
+{
+    sum = a ^ b ^ c;                       // one LOP3 (0x96)
+    carry = (a & b) | (c & (a | b));       // one LOP3 (0xe8, majority)
+}
+
+template <int N>
+struct PopcSum32 {
+    static __device__ __forceinline__ uint32_t run(const uint32_t *x)
+    {
+        constexpr int K = N / 3, REM = N % 3;
+        uint32_t ones[K + REM], twos[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) csa32(x[3 * k], x[3 * k + 1], x[3 * k + 2], ones[k], twos[k]);
+#pragma unroll
+        for (int r = 0; r < REM; ++r) ones[K + r] = x[3 * K + r];
+        return PopcSum32<K + REM>::run(ones) + 2u * PopcSum32<K>::run(twos);
+    }
+};
+template <> struct PopcSum32<0> { static __device__ __forceinline__ uint32_t run(const uint32_t *) { return 0u; } };
+template <> struct PopcSum32<1> { static __device__ __forceinline__ uint32_t run(const uint32_t *x) { return __popc(x[0]); } };
+template <> struct PopcSum32<2> { static __device__ __forceinline__ uint32_t run(const uint32_t *x) { return __popc(x[0]) + __popc(x[1]); } };
+
 __device__ __forceinline__ double u128_to_double(u128 v)
 {
     return (double)(u64)(v >> 64) * 18446744073709551616.0 + (double)(u64)v;
@@ -86,6 +141,8 @@ struct ldpgta_ctx {
     uint64_t *allele_rows[ldpgta::MAXG] = {};
     int64_t n_alleles[ldpgta::MAXG] = {};
     uint64_t *read_masks[ldpgta::MAXG] = {};
+    uint32_t *read_popc[ldpgta::MAXG] = {};   // popcount of every read mask
+    double *norm[ldpgta::MAXG] = {};          // x / nhap lookup per group
     bool masks_owned[ldpgta::MAXG] = {};
     int64_t n_reads_g[ldpgta::MAXG] = {};
     int64_t n_reads = 0;

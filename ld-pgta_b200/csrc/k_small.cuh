@@ -1,23 +1,39 @@
-// k_small.cuh -- draws of 2, 3 or 4 reads (the CLI default -M 4): everything in registers.
+// k_small.cuh -- draws of 2, 3 or 4 reads (the CLI default -M 4).
 //
-// A group of LPD lanes owns one draw.  Each lane loads its share of the NR read masks
-// straight from HBM/L2 with 128-bit loads (lane l of the group takes 16-byte slot
-// j*LPD + l of the row, so a group reads 16*LPD contiguous bytes per instruction),
-// forms every non-empty subset intersection with one AND per subset (parent AND one
-// read, joint_frequencies_combo HOMOGENOUES_MODELS.py:129-163), popcounts, and the
-// 2^NR-1 partial counts are summed across the group's lanes with xor-shuffles.  The
-// closed-form polynomials (poly_closed.cuh) run in the same kernel in float64.
+// A group of LPD lanes owns one draw, a warp owns a tile of 32/LPD draws, and every warp of a
+// persistent one-CTA-per-SM grid walks its tiles through a two-buffer shared-memory pipeline:
+//
+//   producer  the NR*32/LPD lanes that hold the tile's read indices each issue ONE bulk copy
+//             (cp.async.bulk, the 1-D TMA path: UBLKCP) of a whole read mask, HBM/L2 -> shared,
+//             completing on the buffer's mbarrier.  The copies for the next TWO tiles are always
+//             in flight while a tile is being computed (a buffer is refilled as soon as its
+//             masks have been pulled into registers), so the kernel is not exposed to DRAM latency.
+//   consumer  each lane pulls its 16-byte slots of the NR masks into registers (lane l of a draw's
+//             group takes slot j*LPD + l: conflict-free LDS.128), forms every subset intersection
+//             of two or more reads (joint_frequencies_combo, HOMOGENOUES_MODELS.py:129-163; one
+//             LOP3 ANDs up to three reads), popcounts the lane's words of a subset together through
+//             a carry-save adder tree (POPC is the scarce pipe: 16/clk/SM against 64 LOP3), and the
+//             partial counts are summed across the group's lanes with xor-shuffles.  Single-read
+//             frequencies are row popcounts, precomputed once per read and prefetched with the
+//             indices.  The closed-form polynomials (poly_closed.cuh) follow in float64; counts are
+//             normalised through an exact x/N lookup table instead of 15 divisions.
 //
 // Algorithmic work per draw: G*(2^NR-1)*W word AND+POPC, G*NR*W*8 mask bytes in, 32 B out.
+//
+// k_small_direct is the unpipelined variant (masks loaded straight into registers) used for rows
+// longer than one pass of a lane group (more than 8192 haplotypes).
 #pragma once
 #include "common.cuh"
 #include "poly_closed.cuh"
+
+#ifndef LDPGTA_SMALL_MINB
+#define LDPGTA_SMALL_MINB 4      // k_small_direct: resident 128-thread blocks per SM the register allocation must allow
+#endif
 
 namespace ldpgta {
 
 struct SmallArgs {
     PanelView pv;
-    int kind;
     const int32_t *idx;      // [n_draws][NR]
     int64_t n_draws;
     const int64_t *pos;      // optional scatter positions of the outputs
@@ -25,36 +41,292 @@ struct SmallArgs {
     uint32_t *counts_out;    // optional [n_draws][G][2^NR]
 };
 
-template <int NR, int LPD, int WPL>
-__global__ void __launch_bounds__(128) k_small(const SmallArgs a)
+// ---- PTX: mbarrier + bulk async copy (TMA 1-D) ---------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---- the arithmetic shared by both variants --------------------------------------------------
+// m[i][j] = 16-byte slot j of read i's mask held by this lane; adds the lane's partial counts of every
+// subset of two or more reads to c[].
+template <int NR, int WPL>
+__device__ __forceinline__ void small_subset_counts(const uint4 (&m)[NR][WPL / 2], uint32_t *c)
+{
+    constexpr int NS = 1 << NR, SLOTS = WPL / 2;
+#pragma unroll
+    for (int s = 3; s < NS; ++s) {
+        if ((s & (s - 1)) == 0) continue;               // singletons come from the per-read table
+        uint32_t t[2 * WPL];
+#pragma unroll
+        for (int j = 0; j < SLOTS; ++j) {
+            uint32_t x = ~0u, y = ~0u, z = ~0u, w = ~0u;
+#pragma unroll
+            for (int i = 0; i < NR; ++i)
+                if ((s >> i) & 1) { x &= m[i][j].x; y &= m[i][j].y; z &= m[i][j].z; w &= m[i][j].w; }
+            t[4 * j] = x; t[4 * j + 1] = y; t[4 * j + 2] = z; t[4 * j + 3] = w;
+        }
+        c[s] += PopcSum32<2 * WPL>::run(t);
+    }
+}
+
+// sums c[] over the LPD lanes of a draw; every lane ends with the totals
+template <int NR, int LPD>
+__device__ __forceinline__ void small_group_sum(uint32_t *c, bool packed)
+{
+    constexpr int NS = 1 << NR;
+    if (packed) {                         // fewer than 65536 haplotypes: two 16-bit counters per shuffle
+#pragma unroll
+        for (int s = 0; s < NS; s += 2) {
+            uint32_t v = c[s] | (c[s + 1] << 16);
+#pragma unroll
+            for (int msk = LPD / 2; msk; msk >>= 1) v += __shfl_xor_sync(0xffffffffu, v, msk);
+            c[s] = v & 0xffffu;
+            c[s + 1] = v >> 16;
+        }
+    } else {
+#pragma unroll
+        for (int s = 1; s < NS; ++s)
+#pragma unroll
+            for (int msk = LPD / 2; msk; msk >>= 1) c[s] += __shfl_xor_sync(0xffffffffu, c[s], msk);
+    }
+}
+
+// Folds one group's counts into the model state and, after the last group, evaluates the polynomials.
+template <int NR, int KIND>
+struct SmallModel {
+    static constexpr int NS = 1 << NR;
+    uint32_t c0[KIND == LDPGTA_RECENT_ADMIXTURE ? NS : 1];
+    double f[KIND == LDPGTA_DISTANT_ADMIXTURE ? NS : 1];
+
+    __device__ __forceinline__ void init()
+    {
+        if (KIND == LDPGTA_DISTANT_ADMIXTURE)
+#pragma unroll
+            for (int s = 0; s < NS; ++s) f[s] = 0.0;
+    }
+    // returns true when res[] is final
+    __device__ __forceinline__ bool fold(const PanelView &pv, int g, const uint32_t *c, double *res)
+    {
+        if (KIND == LDPGTA_HOMOGENEOUS) {
+            const double *norm = pv.norm[0];
+            double fr[NS];
+#pragma unroll
+            for (int s = 1; s < NS; ++s) fr[s] = __ldg(norm + c[s]);             // = c[s] / N exactly
+            closed_single<NR>(fr, res);
+            return true;
+        } else if (KIND == LDPGTA_RECENT_ADMIXTURE) {
+            if (g == 0) {
+#pragma unroll
+                for (int s = 1; s < NS; ++s) c0[s] = c[s];
+                return false;
+            }
+            const double *norm0 = pv.norm[0], *norm1 = pv.norm[1];
+            double fr[NS], gr[NS];
+#pragma unroll
+            for (int s = 1; s < NS; ++s) { fr[s] = __ldg(norm0 + c0[s]); gr[s] = __ldg(norm1 + c[s]); }
+            closed_recent<NR>(fr, gr, res);
+            return true;
+        } else {
+            // effective_joint_frequency, DISTANT_ADMIXTURE_MODELS.py:136-139: sum_g p_g * cnt_g / N_g, in group order
+            const double nh = (double)pv.nhap[g], p = pv.coef[g];
+#pragma unroll
+            for (int s = 1; s < NS; ++s) f[s] = f[s] + p * (double)c[s] / nh;
+            if (g + 1 < pv.G) return false;
+            closed_single<NR>(f, res);
+            return true;
+        }
+    }
+};
+
+__device__ __forceinline__ void small_store(const SmallArgs &a, int64_t draw, const double *res)
+{
+    const int64_t o = a.pos ? a.pos[draw] : draw;
+    double2 *dst = reinterpret_cast<double2 *>(a.out + 4 * o);
+    dst[0] = make_double2(res[0], res[1]);
+    dst[1] = make_double2(res[2], res[3]);
+}
+
+template <int NR>
+__device__ __forceinline__ void small_dump(const SmallArgs &a, int64_t draw, int g, const uint32_t *c)
+{
+    uint32_t *o = a.counts_out + (draw * a.pv.G + g) * (1 << NR);
+    o[0] = 0;
+#pragma unroll
+    for (int s = 1; s < (1 << NR); ++s) o[s] = c[s];
+}
+
+// ---- pipelined persistent kernel ---------------------------------------------------------------
+template <int NR, int WPL>
+struct SmallPipe {
+    static constexpr int STAGE_BYTES = 256 * NR * WPL;                       // (32/LPD) draws * NR rows * LPD*WPL words * 8 B
+    static constexpr int NWARPS_RAW = (220 * 1024) / (2 * STAGE_BYTES);
+    static constexpr int NWARPS = NWARPS_RAW > 16 ? 16 : (NWARPS_RAW & ~3);     // register file is allocated per 4 warps
+    static constexpr int SMEM = NWARPS * (2 * STAGE_BYTES + 16);
+};
+
+template <int NR, int LPD, int WPL, int KIND>
+__global__ void __launch_bounds__(SmallPipe<NR, WPL>::NWARPS * 32, 1) k_small(const SmallArgs a)
 {
     static_assert(WPL % 2 == 0, "rows are read in 16-byte slots");
-    constexpr int NS = 1 << NR;
-    constexpr int SLOTS = WPL / 2;
+    using P = SmallPipe<NR, WPL>;
+    constexpr int NS = 1 << NR, SLOTS = WPL / 2, DPW = 32 / LPD, ROWS = DPW * NR;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane_in = lane % LPD, dgrp = lane / LPD;
+    unsigned char *wbase = smem + (size_t)warp * (2 * P::STAGE_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)P::NWARPS * 2 * P::STAGE_BYTES) + 2 * warp;
+
+    if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
+    fence_proxy_async();
+    __syncwarp();
+
+    const int G = a.pv.G;
+    const int64_t n_tiles = (a.n_draws + DPW - 1) / DPW;
+    const int64_t tile0 = (int64_t)blockIdx.x * P::NWARPS + warp, tstride = (int64_t)gridDim.x * P::NWARPS;
+    // stages are (tile, group) pairs in order; stage q of this warp: tile = tile0 + (q / G) * tstride, group = q % G
+    const int64_t my_tiles = tile0 < n_tiles ? (n_tiles - tile0 + tstride - 1) / tstride : 0;
+    const int64_t n_stages = my_tiles * G;
+
+    // producer lanes: lane l < ROWS owns row (draw l / NR, read l % NR) of every tile
+    auto load_idx = [&](int64_t tile) -> int32_t {
+        if (lane >= ROWS) return 0;
+        int64_t d = tile * DPW + lane / NR;
+        if (d >= a.n_draws) d = a.n_draws - 1;                                 // ragged last tile: harmless duplicates
+        return __ldg(a.idx + d * NR + lane % NR);
+    };
+    auto issue = [&](int buf, int g, int32_t ridx) -> uint32_t {
+        const int wp = a.pv.wp[g];
+        const uint32_t row_bytes = (uint32_t)wp * 8u;
+        uint32_t pc = 0;
+        if (lane == 0) mbar_arrive_expect_tx(&bars[buf], row_bytes * ROWS);
+        __syncwarp();
+        if (lane < ROWS) {
+            bulk_copy_g2s(wbase + (size_t)buf * P::STAGE_BYTES + (size_t)lane * row_bytes,
+                          a.pv.masks[g] + (int64_t)ridx * wp, row_bytes, &bars[buf]);
+            pc = __ldg(a.pv.popc[g] + ridx);
+        }
+        return pc;
+    };
+
+    // (tile, group) of the stage being consumed (cur), and of the next stage to issue (nxt = cur + 2 stages)
+    int64_t cur_tile = tile0, nxt_tile = tile0;
+    int cur_g = 0, nxt_g = 0;
+    auto advance = [&](int64_t &tile, int &g) { if (++g == G) { g = 0; tile += tstride; } };
+
+    // prologue: stages 0 and 1 in flight, indices of the stage after them loaded
+    uint32_t pc0 = 0, pc1 = 0;               // row popcounts of the stages in buffers 0 and 1
+    int32_t idx_nxt = 0;                     // row index of the next stage to issue
+    if (n_stages > 0) { pc0 = issue(0, nxt_g, load_idx(nxt_tile)); advance(nxt_tile, nxt_g); }
+    if (n_stages > 1) { pc1 = issue(1, nxt_g, load_idx(nxt_tile)); advance(nxt_tile, nxt_g); }
+    if (n_stages > 2) idx_nxt = load_idx(nxt_tile);
+
+    SmallModel<NR, KIND> model;
+    uint32_t parity0 = 0, parity1 = 0;
+    for (int64_t q = 0; q < n_stages; ++q) {
+        const int buf = (int)(q & 1), g = cur_g;
+        const int64_t draw = cur_tile * DPW + dgrp;
+        const bool writer = draw < a.n_draws && lane_in == 0;
+        const int wp = a.pv.wp[g];
+        if (g == 0) model.init();
+        advance(cur_tile, cur_g);
+
+        // single-read counts of this stage (prefetched with the indices), before the buffer state moves on
+        uint32_t c[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) c[s] = 0;
+        {
+            const uint32_t pc = buf ? pc1 : pc0;
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                const uint32_t v = __shfl_sync(0xffffffffu, pc, dgrp * NR + i);
+                if (lane_in == 0) c[1 << i] = v;
+            }
+        }
+
+        if (buf) { mbar_wait(&bars[1], parity1); parity1 ^= 1u; }
+        else     { mbar_wait(&bars[0], parity0); parity0 ^= 1u; }
+
+        uint4 m[NR][SLOTS];
+        {
+            const unsigned char *st = wbase + (size_t)buf * P::STAGE_BYTES + (size_t)(dgrp * NR) * wp * 8;
+#pragma unroll
+            for (int j = 0; j < SLOTS; ++j) {
+                const int w = (j * LPD + lane_in) * 2;
+                const bool in = w < wp;
+#pragma unroll
+                for (int i = 0; i < NR; ++i)
+                    m[i][j] = in ? *reinterpret_cast<const uint4 *>(st + ((size_t)i * wp + w) * 8) : make_uint4(0, 0, 0, 0);
+            }
+        }
+        // the buffer is free again: refill it with stage q+2 before computing
+        __syncwarp();
+        if (q + 2 < n_stages) {
+            fence_proxy_async();
+            const uint32_t pc_new = issue(buf, nxt_g, idx_nxt);
+            if (buf) pc1 = pc_new; else pc0 = pc_new;
+            advance(nxt_tile, nxt_g);
+            if (q + 3 < n_stages) idx_nxt = load_idx(nxt_tile);
+        }
+
+        small_subset_counts<NR, WPL>(m, c);
+        small_group_sum<NR, LPD>(c, a.pv.nhap[g] <= 65535u);
+        if (a.counts_out && writer) small_dump<NR>(a, draw, g, c);
+        double res[4];
+        if (model.fold(a.pv, g, c, res) && writer) small_store(a, draw, res);
+    }
+}
+
+// ---- direct kernel (no staging): rows longer than one pass of a lane group ---------------------
+template <int NR, int LPD, int WPL, int KIND>
+__global__ void __launch_bounds__(128, LDPGTA_SMALL_MINB) k_small_direct(const SmallArgs a)
+{
+    constexpr int NS = 1 << NR, SLOTS = WPL / 2;
     const int lane_in = threadIdx.x % LPD;
     int64_t draw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPD;
     const bool live = draw < a.n_draws;
     if (!live) draw = a.n_draws - 1;        // keep the lanes in the shuffles
+    const bool writer = live && lane_in == 0;
 
     int32_t r[NR];
 #pragma unroll
     for (int i = 0; i < NR; ++i) r[i] = __ldg(a.idx + draw * NR + i);
 
-    double f[NS], g2[NS];                   // normalised frequencies (g2: second group of recent admixture)
-#pragma unroll
-    for (int s = 0; s < NS; ++s) { f[s] = 0.0; g2[s] = 0.0; }
-
+    SmallModel<NR, KIND> model;
+    model.init();
     for (int g = 0; g < a.pv.G; ++g) {
         const int wp = a.pv.wp[g];
-        const uint64_t *base = a.pv.masks[g];
         const uint64_t *row[NR];
 #pragma unroll
-        for (int i = 0; i < NR; ++i) row[i] = base + (int64_t)r[i] * wp;
-
+        for (int i = 0; i < NR; ++i) row[i] = a.pv.masks[g] + (int64_t)r[i] * wp;
         uint32_t c[NS];
 #pragma unroll
         for (int s = 0; s < NS; ++s) c[s] = 0;
-
         for (int w0 = 0; w0 < wp; w0 += LPD * WPL) {
             uint4 m[NR][SLOTS];
 #pragma unroll
@@ -64,69 +336,16 @@ __global__ void __launch_bounds__(128) k_small(const SmallArgs a)
 #pragma unroll
                 for (int i = 0; i < NR; ++i) m[i][j] = in ? ldg128(row[i] + w) : make_uint4(0, 0, 0, 0);
             }
-#pragma unroll
-            for (int j = 0; j < SLOTS; ++j) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    u64 x[NS];
-#pragma unroll
-                    for (int s = 1; s < NS; ++s) {
-                        const int top = 31 - __clz(s);          // compile-time after unrolling
-                        const int rest = s ^ (1 << top);
-                        const uint4 v = m[top][j];
-                        const u64 word = h ? (((u64)v.w << 32) | v.z) : (((u64)v.y << 32) | v.x);
-                        x[s] = rest ? (x[rest] & word) : word;
-                        c[s] += __popcll(x[s]);
-                    }
-                }
-            }
+            small_subset_counts<NR, WPL>(m, c);
         }
-        // sum the partial counts over the LPD lanes of the draw
-        if (a.pv.nhap[g] <= 65535u) {       // two 16-bit counters per shuffle
+        if (lane_in == 0) {
 #pragma unroll
-            for (int s = 0; s < NS; s += 2) {
-                uint32_t v = c[s] | (c[s + 1] << 16);
-#pragma unroll
-                for (int msk = LPD / 2; msk; msk >>= 1) v += __shfl_xor_sync(0xffffffffu, v, msk);
-                c[s] = v & 0xffffu;
-                c[s + 1] = v >> 16;
-            }
-        } else {
-#pragma unroll
-            for (int s = 1; s < NS; ++s)
-#pragma unroll
-                for (int msk = LPD / 2; msk; msk >>= 1) c[s] += __shfl_xor_sync(0xffffffffu, c[s], msk);
+            for (int i = 0; i < NR; ++i) c[1 << i] = __ldg(a.pv.popc[g] + r[i]);
         }
-        if (a.counts_out && live && lane_in == 0) {
-            uint32_t *o = a.counts_out + (draw * a.pv.G + g) * NS;
-            o[0] = 0;
-#pragma unroll
-            for (int s = 1; s < NS; ++s) o[s] = c[s];
-        }
-        const double nh = (double)a.pv.nhap[g];
-        if (a.kind == LDPGTA_DISTANT_ADMIXTURE) {
-            // effective_joint_frequency, DISTANT_ADMIXTURE_MODELS.py:136-139: sum_g p_g * cnt / N_g
-            const double p = a.pv.coef[g];
-#pragma unroll
-            for (int s = 1; s < NS; ++s) f[s] = f[s] + p * (double)c[s] / nh;
-        } else if (g == 0) {
-#pragma unroll
-            for (int s = 1; s < NS; ++s) f[s] = (double)c[s] / nh;
-        } else {
-#pragma unroll
-            for (int s = 1; s < NS; ++s) g2[s] = (double)c[s] / nh;
-        }
-    }
-
-    double res[4];
-    if (a.kind == LDPGTA_RECENT_ADMIXTURE) closed_recent<NR>(f, g2, res);
-    else closed_single<NR>(f, res);
-
-    if (live && lane_in == 0) {
-        const int64_t o = a.pos ? a.pos[draw] : draw;
-        double2 *dst = reinterpret_cast<double2 *>(a.out + 4 * o);
-        dst[0] = make_double2(res[0], res[1]);
-        dst[1] = make_double2(res[2], res[3]);
+        small_group_sum<NR, LPD>(c, a.pv.nhap[g] <= 65535u);
+        if (a.counts_out && writer) small_dump<NR>(a, draw, g, c);
+        double res[4];
+        if (model.fold(a.pv, g, c, res) && writer) small_store(a, draw, res);
     }
 }
 

@@ -46,6 +46,29 @@ __global__ void k_build_read_masks(const uint64_t *__restrict__ rows, const int3
     }
 }
 
+// norm[x] = x / nhap with IEEE division: joint_frequencies_combo(normalize=True) divides every count
+// by N (HOMOGENOUES_MODELS.py:160-161); counts are integers in 0..N, so a table is exact and turns
+// 15 float64 divisions per draw into 15 cached loads.
+__global__ void k_norm_table(double *__restrict__ out, uint32_t nhap)
+{
+    for (uint32_t x = blockIdx.x * blockDim.x + threadIdx.x; x <= nhap; x += gridDim.x * blockDim.x)
+        out[x] = (double)x / (double)nhap;
+}
+
+// popcount of every row (the single-read joint frequencies), one warp per row
+__global__ void k_row_popc(const uint64_t *__restrict__ rows, int64_t n_rows, int wp, uint32_t *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_rows; r += warps) {
+        uint32_t c = 0;
+        for (int w = lane; w < wp; w += 32) c += __popcll(rows[r * wp + w]);
+#pragma unroll
+        for (int m = 16; m; m >>= 1) c += __shfl_xor_sync(0xffffffffu, c, m);
+        if (lane == 0) out[r] = c;
+    }
+}
+
 // LLR(y, x), ANEUPLOIDY_TEST.py:78-90
 __device__ __forceinline__ double llr(double y, double x)
 {

@@ -61,11 +61,28 @@ static PanelView make_view(const ldpgta_ctx *c, const double *proportions)
     pv.G = c->G;
     for (int g = 0; g < c->G; ++g) {
         pv.masks[g] = c->read_masks[g];
+        pv.popc[g] = c->read_popc[g];
+        pv.norm[g] = c->norm[g];
         pv.wp[g] = c->wp[g];
         pv.nhap[g] = c->nhap[g];
         pv.coef[g] = proportions ? proportions[g] : 0.0;
     }
     return pv;
+}
+
+// (re)computes the per-read popcount table of group g after its masks changed
+static int refresh_popc(ldpgta_ctx *c, int g)
+{
+    if (c->read_popc[g]) { LDPGTA_CUDA(cudaFree(c->read_popc[g])); c->read_popc[g] = nullptr; }
+    const int64_t n = c->n_reads_g[g];
+    LDPGTA_CUDA(cudaMalloc((void **)&c->read_popc[g], std::max<size_t>((size_t)n * 4, 16)));
+    if (n) {
+        const unsigned blocks = (unsigned)std::min<int64_t>((n * 32 + 255) / 256, (int64_t)c->sm_count * 16);
+        k_row_popc<<<blocks, 256, 0, c->stream>>>(c->read_masks[g], n, c->wp[g], c->read_popc[g]);
+        c->launches++;
+        LDPGTA_CUDA(cudaGetLastError());
+    }
+    return 0;
 }
 
 static int check_kind(const ldpgta_ctx *c, int kind, const double *proportions)
@@ -85,30 +102,50 @@ static int check_kind(const ldpgta_ctx *c, int kind, const double *proportions)
 
 // ------------------------------------------------------------------ launchers
 
-template <int NR>
-static int launch_small(ldpgta_ctx *c, const SmallArgs &a)
+template <int NR, int LPD, int WPL, int KIND>
+static int launch_small_pipe(ldpgta_ctx *c, const SmallArgs &a)
+{
+    using P = SmallPipe<NR, WPL>;
+    auto kern = k_small<NR, LPD, WPL, KIND>;
+    LDPGTA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM));
+    constexpr int DPW = 32 / LPD;
+    const int64_t tiles = (a.n_draws + DPW - 1) / DPW;
+    const int64_t want = (tiles + P::NWARPS - 1) / P::NWARPS;
+    const unsigned blocks = (unsigned)std::min<int64_t>(want, c->sm_count);      // persistent: one CTA per SM
+    kern<<<blocks, P::NWARPS * 32, P::SMEM, c->stream>>>(a);
+    c->launches++;
+    LDPGTA_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int NR, int KIND>
+static int launch_small_k(ldpgta_ctx *c, const SmallArgs &a)
 {
     int wmax = 0;
     for (int g = 0; g < c->G; ++g) wmax = std::max(wmax, c->wp[g]);
-    const int64_t nd = a.n_draws;
-    auto go = [&](auto kern, int lpd) -> int {
-        const int threads = 128;
-        const int64_t blocks = (nd * lpd + threads - 1) / threads;
-        if (blocks > 0x7fffffffLL) return fail(LDPGTA_E_UNSUPPORTED, "batch too large for one launch");
-        kern<<<(unsigned)blocks, threads, 0, c->stream>>>(a);
-        c->launches++;
-        LDPGTA_CUDA(cudaGetLastError());
-        return 0;
-    };
-    // lanes per draw x words per lane, smallest tile that covers a row in one pass
-    if (wmax <= 8)  return go(k_small<NR, 4, 2>, 4);
-    if (wmax <= 16) return go(k_small<NR, 4, 4>, 4);
-    if (wmax <= 32) return go(k_small<NR, 8, 4>, 8);
-    if (wmax <= 48) return go(k_small<NR, 8, 6>, 8);
-    if (wmax <= 64) return go(k_small<NR, 8, 8>, 8);
-    if (wmax <= 80) return go(k_small<NR, 8, 10>, 8);
-    if (wmax <= 128) return go(k_small<NR, 16, 8>, 16);
-    return go(k_small<NR, 32, 8>, 32);                    // loops over 256-word chunks
+    // lanes per draw x words per lane: the smallest tile that covers a row in one pass
+    if (wmax <= 16) return launch_small_pipe<NR, 4, 4, KIND>(c, a);
+    if (wmax <= 32) return launch_small_pipe<NR, 8, 4, KIND>(c, a);
+    if (wmax <= 40) return launch_small_pipe<NR, 4, 10, KIND>(c, a);
+    if (wmax <= 64) return launch_small_pipe<NR, 8, 8, KIND>(c, a);
+    if (wmax <= 80) return launch_small_pipe<NR, 8, 10, KIND>(c, a);
+    if (wmax <= 128) return launch_small_pipe<NR, 16, 8, KIND>(c, a);
+    // longer rows (more than 8192 haplotypes): unpipelined kernel looping over 256-word chunks
+    const int threads = 128;
+    const int64_t blocks = (a.n_draws * 32 + threads - 1) / threads;
+    if (blocks > 0x7fffffffLL) return fail(LDPGTA_E_UNSUPPORTED, "batch too large for one launch");
+    k_small_direct<NR, 32, 8, KIND><<<(unsigned)blocks, threads, 0, c->stream>>>(a);
+    c->launches++;
+    LDPGTA_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int NR>
+static int launch_small(ldpgta_ctx *c, const SmallArgs &a, int kind)
+{
+    if (kind == LDPGTA_HOMOGENEOUS) return launch_small_k<NR, LDPGTA_HOMOGENEOUS>(c, a);
+    if (kind == LDPGTA_RECENT_ADMIXTURE) return launch_small_k<NR, LDPGTA_RECENT_ADMIXTURE>(c, a);
+    return launch_small_k<NR, LDPGTA_DISTANT_ADMIXTURE>(c, a);
 }
 
 struct GeneralPlan { int th, tl, nw, kl, kh, wc; bool u16; size_t smem; };
@@ -188,10 +225,10 @@ static int run_uniform(ldpgta_ctx *c, int kind, int n, const int32_t *idx_dev, i
     if (n <= 4 && !force_general) {
         SmallArgs a;
         a.pv = override_view ? *override_view : make_view(c, proportions);
-        a.kind = kind; a.idx = idx_dev; a.n_draws = n_draws; a.pos = pos_dev; a.out = out_dev; a.counts_out = counts_dev;
-        if (n == 2) return launch_small<2>(c, a);
-        if (n == 3) return launch_small<3>(c, a);
-        return launch_small<4>(c, a);
+        a.idx = idx_dev; a.n_draws = n_draws; a.pos = pos_dev; a.out = out_dev; a.counts_out = counts_dev;
+        if (n == 2) return launch_small<2>(c, a, kind);
+        if (n == 3) return launch_small<3>(c, a, kind);
+        return launch_small<4>(c, a, kind);
     }
     GeneralArgs a;
     a.pv = override_view ? *override_view : make_view(c, proportions);
@@ -240,6 +277,13 @@ int ldpgta_create(int device, int n_groups, const uint32_t *n_hap, ldpgta_ctx **
     c->sm_count = prop.multiProcessorCount;
     c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     LDPGTA_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (int g = 0; g < n_groups; ++g) {
+        LDPGTA_CUDA(cudaMalloc((void **)&c->norm[g], ((size_t)n_hap[g] + 1) * 8));
+        k_norm_table<<<(n_hap[g] + 256) / 256, 256, 0, c->stream>>>(c->norm[g], n_hap[g]);
+        c->launches++;
+    }
+    LDPGTA_CUDA(cudaGetLastError());
+    LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
     *out = c;
     return 0;
 }
@@ -252,6 +296,8 @@ int ldpgta_destroy(ldpgta_ctx *c)
     for (int g = 0; g < c->G; ++g) {
         if (c->allele_rows[g]) cudaFree(c->allele_rows[g]);
         if (c->read_masks[g] && c->masks_owned[g]) cudaFree(c->read_masks[g]);
+        if (c->read_popc[g]) cudaFree(c->read_popc[g]);
+        if (c->norm[g]) cudaFree(c->norm[g]);
     }
     if (c->d_buf) cudaFree(c->d_buf);
     if (c->h_pin) cudaFreeHost(c->h_pin);
@@ -328,6 +374,8 @@ int ldpgta_upload_read_masks(ldpgta_ctx *c, int group, const uint64_t *rows, int
     c->masks_owned[group] = true;
     c->n_reads_g[group] = n_rows;
     c->n_reads = n_rows;
+    if (int rc = refresh_popc(c, group)) return rc;
+    LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }
 
@@ -342,6 +390,8 @@ int ldpgta_attach_read_masks_dev(ldpgta_ctx *c, int group, const uint64_t *rows_
     c->masks_owned[group] = false;
     c->n_reads_g[group] = n_rows;
     c->n_reads = n_rows;
+    if (int rc = refresh_popc(c, group)) return rc;
+    LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }
 
@@ -381,6 +431,7 @@ int ldpgta_build_read_masks(ldpgta_ctx *c, const int32_t *allele_idx, const int6
             c->launches++;
             LDPGTA_CUDA(cudaGetLastError());
         }
+        if (int rc = refresh_popc(c, g)) return rc;
     }
     c->n_reads = n_reads;
     LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
@@ -439,8 +490,8 @@ int ldpgta_get_likelihoods(ldpgta_ctx *c, int kind, const int32_t *allele_idx, c
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 15) & ~(size_t)15; return o; };
     const size_t o_idx = take((size_t)nnz * 4), o_off = take((size_t)(n + 1) * 8), o_draw = take((size_t)n * 4);
     const size_t o_out = take(32), o_cnt = take(((size_t)c->G << n) * 4);
-    size_t o_rows[MAXG];
-    for (int g = 0; g < c->G; ++g) o_rows[g] = take((size_t)n * c->wp[g] * 8);
+    size_t o_rows[MAXG], o_pc[MAXG];
+    for (int g = 0; g < c->G; ++g) { o_rows[g] = take((size_t)n * c->wp[g] * 8); o_pc[g] = take((size_t)n * 4); }
     if (int rc = ensure_dev(c, off)) return rc;
     char *base = (char *)c->d_buf;
     int32_t h_draw[MAXN];
@@ -453,8 +504,10 @@ int ldpgta_get_likelihoods(ldpgta_ctx *c, int kind, const int32_t *allele_idx, c
         uint64_t *rows = (uint64_t *)(base + o_rows[g]);
         k_build_read_masks<<<1, 256, 0, c->stream>>>(c->allele_rows[g], (const int32_t *)(base + o_idx),
                                                      (const int64_t *)(base + o_off), n, c->wp[g], rows);
-        c->launches++;
+        k_row_popc<<<1, 256, 0, c->stream>>>(rows, n, c->wp[g], (uint32_t *)(base + o_pc[g]));
+        c->launches += 2;
         pv.masks[g] = rows;
+        pv.popc[g] = (const uint32_t *)(base + o_pc[g]);
     }
     LDPGTA_CUDA(cudaGetLastError());
     if (int rc = run_uniform(c, kind, n, (const int32_t *)(base + o_draw), 1, nullptr, proportions, (double *)(base + o_out),

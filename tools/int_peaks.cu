@@ -10,6 +10,7 @@
 
 constexpr int ITERS = 4096;
 constexpr int CHAINS = 8;
+static double g_clock_khz = 1965000.0;
 
 template <int MODE>
 __global__ void __launch_bounds__(256) k_peak(uint32_t *out, long long *cycles, uint32_t seed)
@@ -94,9 +95,9 @@ static int time_it(F launch, int blocks, double ops_per_thread, const char *name
     CK(cudaMemcpy(&cyc, d_cyc, sizeof cyc, cudaMemcpyDeviceToHost));
     const double total = ops_per_thread * 256.0 * blocks;
     const double per_s = total / (best * 1e-3);
-    const double blocks_per_sm = (double)blocks / sms;
-    const double per_clk_sm = ops_per_thread * 256.0 * blocks_per_sm / (double)cyc;   // all resident blocks run concurrently
-    printf("  \"%s\": {\"ops_per_s\": %.4e, \"ops_per_clk_per_sm\": %.2f, \"ms\": %.4f, \"block_cycles\": %lld}%s\n",
+    // per clock at the maximum SM clock (the device may run a little below it under load)
+    const double per_clk_sm = per_s / sms / (g_clock_khz * 1e3);
+    printf("  \"%s\": {\"ops_per_s\": %.4e, \"ops_per_clk_per_sm_at_max_clock\": %.2f, \"ms\": %.4f, \"block0_cycles\": %lld}%s\n",
            name, per_s, per_clk_sm, best, cyc, last ? "" : ",");
     return 0;
 }
@@ -105,6 +106,7 @@ int main()
 {
     cudaDeviceProp p;
     CK(cudaGetDeviceProperties(&p, 0));
+    g_clock_khz = p.clockRate;
     const int sms = p.multiProcessorCount, blocks = sms * 8;       // 8 x 256 threads = 64 warps per SM
     uint32_t *d_out; long long *d_cyc;
     CK(cudaMalloc(&d_out, (size_t)blocks * 256 * 4));
