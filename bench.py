@@ -47,12 +47,14 @@ WINDOW = 100000
 FOUNDERS = 64
 
 
-def workload_shape(depth, seed, min_reads=6):
+def workload_shape(depth, seed, min_reads=6, max_windows=0):
     """ windows per chromosome and informative reads per window (~1500 * depth). """
     rng = np.random.default_rng(seed)
     wins = [L // WINDOW for L in AUTOSOME_LENGTHS]
     n_windows = int(sum(wins))
     reads = np.maximum(rng.poisson(1500.0 * depth, size=n_windows), min_reads).astype(np.int64)
+    if max_windows:
+        reads = reads[:max_windows]
     return wins, reads
 
 
@@ -215,7 +217,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    wins, reads = workload_shape(args.depth, args.seed)
+    wins, reads = workload_shape(args.depth, args.seed, min_reads=args.max_reads + 2, max_windows=args.windows)
     per_step_windows = min(max(cores * 8, 64), len(reads))   # bounded sample, the same windows every step
     need = per_step_windows
     masks = synth_masks(torch, 'cpu', reads, N_HAP, args.seed, window_slice=slice(0, need)).numpy().view(np.uint64)
@@ -251,7 +253,8 @@ def run_reference(args):
 
 
 def workload_config(args, n_windows, n_reads):
-    return {'workload': 'configs[1]: 22-autosome synthetic embryo, depth %.2fx, homogeneous model, monosomy/disomy/SPH/BPH' % args.depth,
+    tag = 'configs[1]' if (args.max_reads == 4 and args.depth == 0.1 and not args.windows) else 'exploration run'
+    return {'workload': '%s: 22-autosome synthetic embryo, depth %.2fx, homogeneous model, monosomy/disomy/SPH/BPH' % (tag, args.depth),
             'haplotypes': N_HAP, 'windows_per_gpu': n_windows, 'reads_per_gpu': n_reads, 'window_size': WINDOW,
             'subsamples': args.subsamples, 'max_reads': args.max_reads, 'min_reads': 6,
             'panel': 'LD-structured (64-founder mosaic), synthetic', 'l2': 'inputs larger than L2 (read masks %.2f GB per GPU)' % (n_reads * 640 / 1e9),
@@ -268,6 +271,7 @@ def main():
     ap.add_argument('--subsamples', type=int, default=32)
     ap.add_argument('--max-reads', type=int, default=4)
     ap.add_argument('--seed', type=int, default=12345)
+    ap.add_argument('--windows', type=int, default=0, help='limit the number of windows (exploration runs; 0 = whole genome)')
     ap.add_argument('--cpu-seconds', type=float, default=12.0, help='budget of the single-core CPU baseline leg')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
@@ -292,7 +296,7 @@ def main():
         dist.init_process_group('nccl', device_id=device)
 
     # ---- workload: one embryo per rank ------------------------------------------------------
-    wins, reads = workload_shape(args.depth, args.seed + 1000 * rank)
+    wins, reads = workload_shape(args.depth, args.seed + 1000 * rank, min_reads=args.max_reads + 2, max_windows=args.windows)
     n_windows, n_reads = len(reads), int(reads.sum())
     masks = synth_masks(torch, device, reads, N_HAP, args.seed + 1000 * rank)
     idx_host, win_of_draw = plan_draws(reads, args.subsamples, args.max_reads, args.seed + 1 + 1000 * rank)
@@ -444,7 +448,7 @@ def main():
                 'd2h_bytes_per_step': int(pin_out.array.nbytes), 'ms_per_step': 1e3 * e2e_s / args.steps,
                 'api': 'Engine.likelihoods_batch -> ldpgta_likelihoods_batch (pinned host buffers)'},
         'gpu_launches': int(launches),
-        'roofline': {'bound': 'hbm', 'kernel': 'k_small<4,8,10>', 'achieved': achieved_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
+        'roofline': {'bound': 'hbm', 'kernel': 'k_small<%d,8,10>' % n if n <= 4 else 'k_general (n=%d)' % n, 'achieved': achieved_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
                      'frac': achieved_gbs / hbm_peak, 'traffic': None, 'peak_source': peak_src,
                      'algorithmic_bytes_per_draw': bytes_per_draw, 'kernel_ms': k_ms},
         'int_roofline': {'bound': 'popc', 'achieved': achieved_wordops, 'peak': int_peak, 'unit': 'word AND+POPC/s',

@@ -16,7 +16,7 @@ constexpr int MAXN = LDPGTA_MAX_READS_PER_DRAW;
 
 extern thread_local std::string g_last_error;
 
-inline int fail(int code, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
+int fail(int code, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
 
 #define LDPGTA_CUDA(expr)                                                                      \
     do {                                                                                       \
@@ -151,5 +151,36 @@ struct ldpgta_ctx {
     void *h_pin = nullptr;  size_t h_pin_bytes = 0;
     void *d_buf = nullptr;  size_t d_buf_bytes = 0;
 
+    // colourings of the high reads used by the three-block polynomial, one list per h = n - 5 (built on first use)
+    uint64_t *hi_terms[12] = {};
+    int64_t n_hi_terms[12] = {};
+
     int64_t launches = 0;
 };
+
+namespace ldpgta {
+
+inline PanelView make_view(const ldpgta_ctx *c, const double *proportions)
+{
+    PanelView pv;
+    memset(&pv, 0, sizeof pv);
+    pv.G = c->G;
+    for (int g = 0; g < c->G; ++g) {
+        pv.masks[g] = c->read_masks[g];
+        pv.popc[g] = c->read_popc[g];
+        pv.norm[g] = c->norm[g];
+        pv.wp[g] = c->wp[g];
+        pv.nhap[g] = c->nhap[g];
+        pv.coef[g] = proportions ? proportions[g] : 0.0;
+    }
+    return pv;
+}
+
+
+struct SmallArgs;
+struct GeneralArgs;
+// kernel launchers, one translation unit each (small.cu, general.cu)
+int launch_small(ldpgta_ctx *c, const SmallArgs &a, int n, int kind);
+int launch_general(ldpgta_ctx *c, GeneralArgs a);
+
+}  // namespace ldpgta

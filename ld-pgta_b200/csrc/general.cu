@@ -1,0 +1,111 @@
+// general.cu -- kernels, shared-memory planning and launcher for draws of 5..16 reads (k_general.cuh).
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "k_general.cuh"
+
+namespace ldpgta {
+
+struct GeneralPlan { int th, tl, nw, kl, kh, wc; bool u16; size_t smem; };
+
+static int plan_general(const ldpgta_ctx *c, int n, GeneralPlan *p)
+{
+    static const int TH[17] = {0, 0, 0, 0, 0, 1, 2, 4, 8, 4, 8, 8, 8, 8, 8, 8, 8};
+    static const int TL[17] = {0, 0, 0, 0, 0, 1, 1, 1, 1, 4, 4, 4, 4, 4, 4, 4, 4};
+    static const int NW[17] = {0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 2, 4, 8, 16, 16, 16};
+    static const int BUDGET_KB[17] = {0, 0, 16, 16, 16, 16, 16, 20, 24, 28, 32, 48, 72, 110, 220, 220, 220};
+    if (n < 5) { p->th = 1; p->tl = 1; p->nw = 1; p->kl = n; }       // likelihoods() forced on 2..4 reads
+    else { p->th = TH[n]; p->tl = TL[n]; p->nw = NW[n]; p->kl = p->tl == 1 ? 5 : 7; }
+    p->kh = n - p->kl;
+    uint32_t nmax = 0; int wmax = 0, wsum = 0;
+    for (int g = 0; g < c->G; ++g) { nmax = std::max(nmax, c->nhap[g]); wmax = std::max(wmax, c->wp[g]); wsum += c->wp[g]; }
+    p->u16 = ((size_t)c->G << n) * 4 > 64 * 1024;
+    if (p->u16 && nmax > 65535u)
+        return fail(LDPGTA_E_UNSUPPORTED, "draws of %d reads need 16-bit count tables, panel group has %u > 65535 haplotypes", n, nmax);
+    const size_t ct = p->u16 ? 2 : 4;
+    const size_t fixed = 64 + (size_t)n * wsum * 8 + ((ct * c->G) << n) + 64 + 16 + 32 * 12 * 8;
+    const size_t per_word = ((size_t)8 << p->kl) + ((size_t)8 << p->kh);
+    const size_t cap = std::min<size_t>((size_t)c->max_smem_optin, (size_t)BUDGET_KB[n] * 1024);
+    if (fixed + 2 * per_word > (size_t)c->max_smem_optin)
+        return fail(LDPGTA_E_UNSUPPORTED, "draws of %d reads with %d group(s) do not fit shared memory (%zu B fixed)", n, c->G, fixed);
+    size_t avail = cap > fixed ? cap - fixed : 0;
+    int wc = (int)(avail / per_word);
+    wc = std::max(wc, 2);
+    wc = std::min(wc, wmax);
+    // equalise the chunks: ceil(wmax / ceil(wmax / wc))
+    const int chunks = (wmax + wc - 1) / wc;
+    wc = (wmax + chunks - 1) / chunks;
+    p->wc = wc;
+    PanelView pv = make_view(c, nullptr);
+    p->smem = p->u16 ? general_smem_layout<uint16_t>(pv, n, p->kl, p->kh, wc).total
+                     : general_smem_layout<uint32_t>(pv, n, p->kl, p->kh, wc).total;
+    if (p->smem > (size_t)c->max_smem_optin)
+        return fail(LDPGTA_E_UNSUPPORTED, "draws of %d reads need %zu B of shared memory", n, p->smem);
+    return 0;
+}
+
+template <int TH, int TL, typename CT>
+static int launch_general_t(ldpgta_ctx *c, const GeneralArgs &a, const GeneralPlan &p)
+{
+    auto kern = k_general<TH, TL, CT>;
+    LDPGTA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    int per_sm = 0;
+    LDPGTA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * p.nw, p.smem));
+    if (per_sm < 1) return fail(LDPGTA_E_UNSUPPORTED, "general kernel does not fit an SM (n=%d, smem=%zu)", a.n, p.smem);
+    const int64_t resident = (int64_t)per_sm * c->sm_count;
+    const unsigned blocks = (unsigned)std::min<int64_t>(a.n_draws, resident);
+    kern<<<blocks, 32 * p.nw, p.smem, c->stream>>>(a);
+    c->launches++;
+    LDPGTA_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Colourings (a_h, b_h, c_h) of the h = n - 5 high reads (every read in exactly one part) with b_h < c_h,
+// packed a | b << 16 | c << 32.  (3^h - 1) / 2 entries, generated once per h and kept on the device.
+static int ensure_hi_terms(ldpgta_ctx *c, int h)
+{
+    if (c->hi_terms[h] || h == 0) return 0;
+    std::vector<uint64_t> list;
+    const uint32_t fullh = (1u << h) - 1u;
+    for (uint32_t a = 0; a <= fullh; ++a) {
+        const uint32_t rest = fullh ^ a;
+        if (!rest) continue;
+        const uint32_t hi = 1u << (31 - __builtin_clz(rest));       // c owns the highest free read: b < c
+        const uint32_t sub = rest ^ hi;
+        uint32_t b = sub;
+        while (true) {
+            list.push_back((uint64_t)a | ((uint64_t)b << 16) | ((uint64_t)(rest ^ b) << 32));
+            if (!b) break;
+            b = (b - 1) & sub;
+        }
+    }
+    LDPGTA_CUDA(cudaMalloc((void **)&c->hi_terms[h], list.size() * 8));
+    LDPGTA_CUDA(cudaMemcpyAsync(c->hi_terms[h], list.data(), list.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
+    c->n_hi_terms[h] = (int64_t)list.size();
+    return 0;
+}
+
+int launch_general(ldpgta_ctx *c, GeneralArgs a)
+{
+    GeneralPlan p;
+    if (int rc = plan_general(c, a.n, &p)) return rc;
+    a.kl = p.kl; a.kh = p.kh; a.wc = p.wc;
+    a.terms = nullptr; a.n_terms = 0; a.wide = 0;
+    if (a.n >= 5) {
+        const int h = a.n - 5;
+        if (int rc = ensure_hi_terms(c, h)) return rc;
+        a.terms = reinterpret_cast<const u64 *>(c->hi_terms[h]);
+        a.n_terms = c->n_hi_terms[h];
+        for (int g = 0; g < c->G; ++g) a.wide |= c->nhap[g] > 16383u;
+    }
+#define LDPGTA_CASE(TH_, TL_)                                                         \
+    if (p.th == TH_ && p.tl == TL_)                                                   \
+        return p.u16 ? launch_general_t<TH_, TL_, uint16_t>(c, a, p) : launch_general_t<TH_, TL_, uint32_t>(c, a, p);
+    LDPGTA_CASE(1, 1) LDPGTA_CASE(2, 1) LDPGTA_CASE(4, 1) LDPGTA_CASE(8, 1) LDPGTA_CASE(4, 4) LDPGTA_CASE(8, 4)
+#undef LDPGTA_CASE
+    return fail(LDPGTA_E_UNSUPPORTED, "no kernel instance for n=%d", a.n);
+}
+
+}  // namespace ldpgta

@@ -19,6 +19,7 @@
 // S(n,3) three-block products.
 #pragma once
 #include "common.cuh"
+#include "poly_general.cuh"
 
 namespace ldpgta {
 
@@ -32,6 +33,9 @@ struct GeneralArgs {
     const int64_t *pos;      // optional scatter positions
     double *out;             // [*][4]
     uint32_t *counts_out;    // optional [n_draws][G][2^n]
+    const u64 *terms;        // colourings (a_h | b_h << 16 | c_h << 32) of the n-5 high reads with b_h < c_h (poly_general.cuh)
+    int64_t n_terms;
+    int wide;                // 64-bit convolution accumulators (a group with more than 16383 haplotypes)
 };
 
 struct GeneralSmem {         // byte offsets into dynamic shared memory
@@ -49,6 +53,7 @@ __host__ __device__ inline GeneralSmem general_smem_layout(const PanelView &pv, 
     off += words * 8;
     s.ltab = off; off += (wc << kl) * 8;
     s.htab = off; off += (wc << kh) * 8;
+    off = (off + 63) & ~63;                              // table rows are read with 128-bit loads
     s.ftab = off; off += (int)(sizeof(CT) * pv.G) << n;
     off = (off + 15) & ~15;
     s.red = off; off += 32 * 12 * 8;
@@ -113,9 +118,9 @@ __device__ __forceinline__ LaneSplit lane_split(uint32_t rest, int lane)
 }
 
 template <int TH, int TL, typename CT>
-__global__ void k_general(const GeneralArgs a)
+__global__ void __launch_bounds__(512, 1) k_general(const GeneralArgs a)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     const int n = a.n, kl = a.kl, kh = a.kh, G = a.pv.G;
     const int LS = 1 << kl, HS = 1 << kh, NS = 1 << n;
     const GeneralSmem lay = general_smem_layout<CT>(a.pv, n, kl, kh, a.wc);
@@ -228,6 +233,12 @@ __global__ void k_general(const GeneralArgs a)
             const CT *F = ftab;
             u64 two = 0, two_sph = 0;
             u128 three = 0;
+            if (n >= 5) {
+                u64 t3;
+                if (a.wide) poly_homog_blocked<CT, u64>(F, n, a.terms, a.n_terms, tid, T, two, two_sph, t3);
+                else poly_homog_blocked<CT, uint32_t>(F, n, a.terms, a.n_terms, tid, T, two, two_sph, t3);
+                three = t3;
+            } else
             for (uint32_t A = top + warp; A < full; A += NW) {
                 const uint32_t rest = full ^ A;
                 const u64 Fa = F[A];
@@ -271,6 +282,12 @@ __global__ void k_general(const GeneralArgs a)
             const CT *F = ftab, *Gt = ftab + NS;
             u64 ff = 0, gg = 0, fg = 0, fg_sph = 0;
             u128 ffg = 0, ggf = 0;
+            if (n >= 5) {
+                u64 t_ffg, t_ggf;
+                if (a.wide) poly_recent_blocked<CT, u64>(F, Gt, n, a.terms, a.n_terms, tid, T, ff, gg, fg, fg_sph, t_ffg, t_ggf);
+                else poly_recent_blocked<CT, uint32_t>(F, Gt, n, a.terms, a.n_terms, tid, T, ff, gg, fg, fg_sph, t_ffg, t_ggf);
+                ffg = t_ffg; ggf = t_ggf;
+            } else
             for (uint32_t A = top + warp; A < full; A += NW) {
                 const uint32_t rest = full ^ A;
                 const u64 Fa = F[A], Ga = Gt[A];
@@ -330,6 +347,8 @@ __global__ void k_general(const GeneralArgs a)
                 return e;
             };
             double two = 0, two_sph = 0, three = 0;
+            if (n >= 5) poly_distant_blocked<CT>(ftab, a.pv, n, a.terms, a.n_terms, tid, T, two, two_sph, three);
+            else
             for (uint32_t A = top + warp; A < full; A += NW) {
                 const uint32_t rest = full ^ A;
                 const double Ea = E(A);

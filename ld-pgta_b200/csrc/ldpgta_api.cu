@@ -6,15 +6,15 @@
 #include <algorithm>
 
 #include "common.cuh"
-#include "k_small.cuh"
-#include "k_general.cuh"
+#include "k_small.cuh"     // SmallArgs
+#include "k_general.cuh"   // GeneralArgs
 #include "k_stats.cuh"
 
 namespace ldpgta {
 
 thread_local std::string g_last_error;
 
-inline int fail(int code, const char *fmt, ...)
+int fail(int code, const char *fmt, ...)
 {
     char buf[512];
     va_list ap;
@@ -54,22 +54,6 @@ static bool is_pinned_or_device(const void *p)
     return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
-static PanelView make_view(const ldpgta_ctx *c, const double *proportions)
-{
-    PanelView pv;
-    memset(&pv, 0, sizeof pv);
-    pv.G = c->G;
-    for (int g = 0; g < c->G; ++g) {
-        pv.masks[g] = c->read_masks[g];
-        pv.popc[g] = c->read_popc[g];
-        pv.norm[g] = c->norm[g];
-        pv.wp[g] = c->wp[g];
-        pv.nhap[g] = c->nhap[g];
-        pv.coef[g] = proportions ? proportions[g] : 0.0;
-    }
-    return pv;
-}
-
 // (re)computes the per-read popcount table of group g after its masks changed
 static int refresh_popc(ldpgta_ctx *c, int g)
 {
@@ -102,119 +86,6 @@ static int check_kind(const ldpgta_ctx *c, int kind, const double *proportions)
 
 // ------------------------------------------------------------------ launchers
 
-template <int NR, int LPD, int WPL, int KIND>
-static int launch_small_pipe(ldpgta_ctx *c, const SmallArgs &a)
-{
-    using P = SmallPipe<NR, WPL>;
-    auto kern = k_small<NR, LPD, WPL, KIND>;
-    LDPGTA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM));
-    constexpr int DPW = 32 / LPD;
-    const int64_t tiles = (a.n_draws + DPW - 1) / DPW;
-    const int64_t want = (tiles + P::NWARPS - 1) / P::NWARPS;
-    const unsigned blocks = (unsigned)std::min<int64_t>(want, c->sm_count);      // persistent: one CTA per SM
-    kern<<<blocks, P::NWARPS * 32, P::SMEM, c->stream>>>(a);
-    c->launches++;
-    LDPGTA_CUDA(cudaGetLastError());
-    return 0;
-}
-
-template <int NR, int KIND>
-static int launch_small_k(ldpgta_ctx *c, const SmallArgs &a)
-{
-    int wmax = 0;
-    for (int g = 0; g < c->G; ++g) wmax = std::max(wmax, c->wp[g]);
-    // lanes per draw x words per lane: the smallest tile that covers a row in one pass
-    if (wmax <= 16) return launch_small_pipe<NR, 4, 4, KIND>(c, a);
-    if (wmax <= 32) return launch_small_pipe<NR, 8, 4, KIND>(c, a);
-    if (wmax <= 40) return launch_small_pipe<NR, 4, 10, KIND>(c, a);
-    if (wmax <= 64) return launch_small_pipe<NR, 8, 8, KIND>(c, a);
-    if (wmax <= 80) return launch_small_pipe<NR, 8, 10, KIND>(c, a);
-    if (wmax <= 128) return launch_small_pipe<NR, 16, 8, KIND>(c, a);
-    // longer rows (more than 8192 haplotypes): unpipelined kernel looping over 256-word chunks
-    const int threads = 128;
-    const int64_t blocks = (a.n_draws * 32 + threads - 1) / threads;
-    if (blocks > 0x7fffffffLL) return fail(LDPGTA_E_UNSUPPORTED, "batch too large for one launch");
-    k_small_direct<NR, 32, 8, KIND><<<(unsigned)blocks, threads, 0, c->stream>>>(a);
-    c->launches++;
-    LDPGTA_CUDA(cudaGetLastError());
-    return 0;
-}
-
-template <int NR>
-static int launch_small(ldpgta_ctx *c, const SmallArgs &a, int kind)
-{
-    if (kind == LDPGTA_HOMOGENEOUS) return launch_small_k<NR, LDPGTA_HOMOGENEOUS>(c, a);
-    if (kind == LDPGTA_RECENT_ADMIXTURE) return launch_small_k<NR, LDPGTA_RECENT_ADMIXTURE>(c, a);
-    return launch_small_k<NR, LDPGTA_DISTANT_ADMIXTURE>(c, a);
-}
-
-struct GeneralPlan { int th, tl, nw, kl, kh, wc; bool u16; size_t smem; };
-
-static int plan_general(const ldpgta_ctx *c, int n, GeneralPlan *p)
-{
-    static const int TH[17] = {0, 0, 0, 0, 0, 1, 2, 4, 8, 4, 8, 8, 8, 8, 8, 8, 8};
-    static const int TL[17] = {0, 0, 0, 0, 0, 1, 1, 1, 1, 4, 4, 4, 4, 4, 4, 4, 4};
-    static const int NW[17] = {0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 2, 4, 8, 16, 16, 16};
-    static const int BUDGET_KB[17] = {0, 0, 16, 16, 16, 16, 16, 20, 24, 28, 32, 48, 72, 110, 220, 220, 220};
-    if (n < 5) { p->th = 1; p->tl = 1; p->nw = 1; p->kl = n; }       // likelihoods() forced on 2..4 reads
-    else { p->th = TH[n]; p->tl = TL[n]; p->nw = NW[n]; p->kl = p->tl == 1 ? 5 : 7; }
-    p->kh = n - p->kl;
-    uint32_t nmax = 0; int wmax = 0, wsum = 0;
-    for (int g = 0; g < c->G; ++g) { nmax = std::max(nmax, c->nhap[g]); wmax = std::max(wmax, c->wp[g]); wsum += c->wp[g]; }
-    p->u16 = ((size_t)c->G << n) * 4 > 64 * 1024;
-    if (p->u16 && nmax > 65535u)
-        return fail(LDPGTA_E_UNSUPPORTED, "draws of %d reads need 16-bit count tables, panel group has %u > 65535 haplotypes", n, nmax);
-    const size_t ct = p->u16 ? 2 : 4;
-    const size_t fixed = 64 + (size_t)n * wsum * 8 + ((ct * c->G) << n) + 16 + 32 * 12 * 8;
-    const size_t per_word = ((size_t)8 << p->kl) + ((size_t)8 << p->kh);
-    const size_t cap = std::min<size_t>((size_t)c->max_smem_optin, (size_t)BUDGET_KB[n] * 1024);
-    if (fixed + 2 * per_word > (size_t)c->max_smem_optin)
-        return fail(LDPGTA_E_UNSUPPORTED, "draws of %d reads with %d group(s) do not fit shared memory (%zu B fixed)", n, c->G, fixed);
-    size_t avail = cap > fixed ? cap - fixed : 0;
-    int wc = (int)(avail / per_word);
-    wc = std::max(wc, 2);
-    wc = std::min(wc, wmax);
-    // equalise the chunks: ceil(wmax / ceil(wmax / wc))
-    const int chunks = (wmax + wc - 1) / wc;
-    wc = (wmax + chunks - 1) / chunks;
-    p->wc = wc;
-    PanelView pv = make_view(c, nullptr);
-    p->smem = p->u16 ? general_smem_layout<uint16_t>(pv, n, p->kl, p->kh, wc).total
-                     : general_smem_layout<uint32_t>(pv, n, p->kl, p->kh, wc).total;
-    if (p->smem > (size_t)c->max_smem_optin)
-        return fail(LDPGTA_E_UNSUPPORTED, "draws of %d reads need %zu B of shared memory", n, p->smem);
-    return 0;
-}
-
-template <int TH, int TL, typename CT>
-static int launch_general_t(ldpgta_ctx *c, const GeneralArgs &a, const GeneralPlan &p)
-{
-    auto kern = k_general<TH, TL, CT>;
-    LDPGTA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    int per_sm = 0;
-    LDPGTA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * p.nw, p.smem));
-    if (per_sm < 1) return fail(LDPGTA_E_UNSUPPORTED, "general kernel does not fit an SM (n=%d, smem=%zu)", a.n, p.smem);
-    const int64_t resident = (int64_t)per_sm * c->sm_count;
-    const unsigned blocks = (unsigned)std::min<int64_t>(a.n_draws, resident);
-    kern<<<blocks, 32 * p.nw, p.smem, c->stream>>>(a);
-    c->launches++;
-    LDPGTA_CUDA(cudaGetLastError());
-    return 0;
-}
-
-static int launch_general(ldpgta_ctx *c, GeneralArgs a)
-{
-    GeneralPlan p;
-    if (int rc = plan_general(c, a.n, &p)) return rc;
-    a.kl = p.kl; a.kh = p.kh; a.wc = p.wc;
-#define LDPGTA_CASE(TH_, TL_)                                                         \
-    if (p.th == TH_ && p.tl == TL_)                                                   \
-        return p.u16 ? launch_general_t<TH_, TL_, uint16_t>(c, a, p) : launch_general_t<TH_, TL_, uint32_t>(c, a, p);
-    LDPGTA_CASE(1, 1) LDPGTA_CASE(2, 1) LDPGTA_CASE(4, 1) LDPGTA_CASE(8, 1) LDPGTA_CASE(4, 4) LDPGTA_CASE(8, 4)
-#undef LDPGTA_CASE
-    return fail(LDPGTA_E_UNSUPPORTED, "no kernel instance for n=%d", a.n);
-}
-
 // draws of one size, device-resident indices and outputs
 static int run_uniform(ldpgta_ctx *c, int kind, int n, const int32_t *idx_dev, int64_t n_draws, const int64_t *pos_dev,
                        const double *proportions, double *out_dev, uint32_t *counts_dev, bool force_general = false,
@@ -226,9 +97,7 @@ static int run_uniform(ldpgta_ctx *c, int kind, int n, const int32_t *idx_dev, i
         SmallArgs a;
         a.pv = override_view ? *override_view : make_view(c, proportions);
         a.idx = idx_dev; a.n_draws = n_draws; a.pos = pos_dev; a.out = out_dev; a.counts_out = counts_dev;
-        if (n == 2) return launch_small<2>(c, a, kind);
-        if (n == 3) return launch_small<3>(c, a, kind);
-        return launch_small<4>(c, a, kind);
+        return launch_small(c, a, n, kind);
     }
     GeneralArgs a;
     a.pv = override_view ? *override_view : make_view(c, proportions);
@@ -299,6 +168,8 @@ int ldpgta_destroy(ldpgta_ctx *c)
         if (c->read_popc[g]) cudaFree(c->read_popc[g]);
         if (c->norm[g]) cudaFree(c->norm[g]);
     }
+    for (int h = 0; h < 12; ++h)
+        if (c->hi_terms[h]) cudaFree(c->hi_terms[h]);
     if (c->d_buf) cudaFree(c->d_buf);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->stream) cudaStreamDestroy(c->stream);

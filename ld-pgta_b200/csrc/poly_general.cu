@@ -1,0 +1,188 @@
+// poly_general.cu -- definitions of the blocked partition polynomials declared in poly_general.cuh.
+// Compiled with -maxrregcount=128 so that a 512-thread k_general block can call them.
+#include "common.cuh"
+#include "poly_general.cuh"
+
+namespace ldpgta {
+
+template <typename CT>
+__device__ __forceinline__ void load_row16(const CT *tab, uint32_t row, uint32_t *v);
+
+template <>
+__device__ __forceinline__ void load_row16<uint32_t>(const uint32_t *tab, uint32_t row, uint32_t *v)
+{
+    const uint4 *p = reinterpret_cast<const uint4 *>(tab + ((size_t)row << 4));
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint4 x = p[q];
+        v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+    }
+}
+
+template <>
+__device__ __forceinline__ void load_row16<uint16_t>(const uint16_t *tab, uint32_t row, uint32_t *v)
+{
+    const uint4 *p = reinterpret_cast<const uint4 *>(tab + ((size_t)row << 4));
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const uint4 x = p[q];
+        const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { v[8 * q + 2 * e] = w[e] & 0xffffu; v[8 * q + 2 * e + 1] = w[e] >> 16; }
+    }
+}
+
+// (Y*Z)[s] for the 16 subsets s of Lo; ACC = uint32_t when 16 * max(Y) * max(Z) < 2^32, else u64
+template <typename ACC>
+__device__ __forceinline__ void conv16(const uint32_t *Y, const uint32_t *Z, ACC *out)
+{
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+        ACC acc = 0;
+#pragma unroll
+        for (int b = 0; b < 16; ++b)
+            if ((b & s) == b) acc += (ACC)Y[b] * (ACC)Z[s ^ b];
+        out[s] = acc;
+    }
+}
+
+template <typename ACC>
+__device__ __forceinline__ u64 dot16(const uint32_t *X, const ACC *conv)
+{
+    u64 acc = 0;
+#pragma unroll
+    for (int a = 0; a < 16; ++a) acc += (u64)X[a] * (u64)conv[15 ^ a];
+    return acc;
+}
+
+// ---- homogeneous ------------------------------------------------------------------------------
+// returns per-thread partials: two, two_sph (u64) and three (u64; the caller sums them in 128 bits)
+template <typename CT, typename ACC>
+__device__ void poly_homog_blocked(const CT *F, int n, const u64 *terms, int64_t n_terms, int tid, int T,
+                                                   u64 &two, u64 &two_sph, u64 &three)
+{
+    const int h = n - 5;
+    const uint32_t top_row = 1u << h, usub = (1u << (n - 1)) - 1u, top = 1u << (n - 1);
+    two = 0; two_sph = 0; three = 0;
+    for (uint32_t a = tid; a < usub; a += T) {                  // a != U': the other block is not empty
+        const u64 prod = (u64)F[top | a] * (u64)F[usub ^ a];
+        const int pa = __popc(a);
+        two += prod;
+        two_sph += prod * ((2ull << pa) + (1ull << (n - 1 - pa)));
+    }
+    for (int64_t e = tid; e < n_terms; e += T) {
+        const u64 t = terms[e];
+        uint32_t X[16], Y[16], Z[16];
+        ACC c[16];
+        load_row16<CT>(F, top_row + (uint32_t)(t & 0xffffu), X);
+        load_row16<CT>(F, (uint32_t)(t >> 16) & 0xffffu, Y);
+        load_row16<CT>(F, (uint32_t)(t >> 32) & 0xffffu, Z);
+        conv16<ACC>(Y, Z, c);
+        three += dot16<ACC>(X, c);
+    }
+    if (tid == 0) {                                             // b_h = c_h = empty: both blocks inside Lo, weight 1/2
+        uint32_t X[16], Y[16];
+        ACC c[16];
+        load_row16<CT>(F, top_row + (top_row - 1u), X);
+        load_row16<CT>(F, 0u, Y);
+        conv16<ACC>(Y, Y, c);
+        three += dot16<ACC>(X, c) >> 1;
+    }
+}
+
+// ---- recent admixture: F = group 0, G = group 1 ------------------------------------------------
+template <typename CT, typename ACC>
+__device__ void poly_recent_blocked(const CT *F, const CT *G, int n, const u64 *terms, int64_t n_terms, int tid,
+                                                    int T, u64 &ff, u64 &gg, u64 &fg, u64 &fg_sph, u64 &ffg, u64 &ggf)
+{
+    const int h = n - 5;
+    const uint32_t top_row = 1u << h, usub = (1u << (n - 1)) - 1u, top = 1u << (n - 1);
+    ff = gg = fg = fg_sph = ffg = ggf = 0;
+    for (uint32_t a = tid; a < usub; a += T) {
+        const uint32_t A = top | a, R = usub ^ a;
+        const u64 fa = F[A], ga = G[A], fr = F[R], gr = G[R];
+        const u64 cross = fa * gr + ga * fr;
+        const int pa = __popc(a);
+        ff += fa * fr;
+        gg += ga * gr;
+        fg += cross;
+        fg_sph += cross * ((2ull << pa) + (1ull << (n - 1 - pa)));
+    }
+    auto triple = [&](uint32_t ra, uint32_t rb, uint32_t rc, bool special) {
+        uint32_t Xf[16], Xg[16], Yf[16], Yg[16], Zf[16], Zg[16];
+        ACC c[16];
+        load_row16<CT>(F, top_row + ra, Xf); load_row16<CT>(G, top_row + ra, Xg);
+        load_row16<CT>(F, rb, Yf); load_row16<CT>(G, rb, Yg);
+        load_row16<CT>(F, rc, Zf); load_row16<CT>(G, rc, Zg);
+        // unordered {A,B,C}, A owns the last read: two parents from F and one from G, and vice versa
+        u64 s_ffg, s_ggf;
+        conv16<ACC>(Yf, Zf, c); s_ffg = dot16<ACC>(Xg, c);
+        conv16<ACC>(Yg, Zg, c); s_ggf = dot16<ACC>(Xf, c);
+        conv16<ACC>(Yf, Zg, c); s_ffg += dot16<ACC>(Xf, c); s_ggf += dot16<ACC>(Xg, c);
+        conv16<ACC>(Yg, Zf, c); s_ffg += dot16<ACC>(Xf, c); s_ggf += dot16<ACC>(Xg, c);
+        if (special) { s_ffg >>= 1; s_ggf >>= 1; }
+        ffg += s_ffg;
+        ggf += s_ggf;
+    };
+    for (int64_t e = tid; e < n_terms; e += T) {
+        const u64 t = terms[e];
+        triple((uint32_t)(t & 0xffffu), (uint32_t)(t >> 16) & 0xffffu, (uint32_t)(t >> 32) & 0xffffu, false);
+    }
+    if (tid == 0) triple(top_row - 1u, 0u, 0u, true);
+}
+
+// ---- distant admixture: float frequencies e(S) = sum_g p_g cnt_g(S) / N_g formed on the fly -----
+template <typename CT>
+__device__ void poly_distant_blocked(const CT *ftab, const PanelView &pv, int n, const u64 *terms, int64_t n_terms,
+                                                     int tid, int T, double &two, double &two_sph, double &three)
+{
+    const int h = n - 5, G = pv.G;
+    const uint32_t top_row = 1u << h, usub = (1u << (n - 1)) - 1u, top = 1u << (n - 1);
+    auto E = [&](uint32_t S) {
+        double e = 0.0;
+        for (int g = 0; g < G; ++g) e = e + pv.coef[g] * (double)ftab[((size_t)g << n) + S] / (double)pv.nhap[g];
+        return e;
+    };
+    auto row = [&](uint32_t r, double *v) {
+#pragma unroll
+        for (int l = 0; l < 16; ++l) v[l] = E((r << 4) | l);
+    };
+    two = 0; two_sph = 0; three = 0;
+    for (uint32_t a = tid; a < usub; a += T) {
+        const double prod = E(top | a) * E(usub ^ a);
+        const int pa = __popc(a);
+        two += prod;
+        two_sph += prod * (double)((2ull << pa) + (1ull << (n - 1 - pa)));
+    }
+    auto triple = [&](uint32_t ra, uint32_t rb, uint32_t rc) {
+        double X[16], Y[16], Z[16], acc = 0.0;
+        row(top_row + ra, X); row(rb, Y); row(rc, Z);
+#pragma unroll
+        for (int s = 0; s < 16; ++s) {
+            double cv = 0.0;
+#pragma unroll
+            for (int b = 0; b < 16; ++b)
+                if ((b & s) == b) cv += Y[b] * Z[s ^ b];
+            acc += X[15 ^ s] * cv;
+        }
+        return acc;
+    };
+    for (int64_t e = tid; e < n_terms; e += T) {
+        const u64 t = terms[e];
+        three += triple((uint32_t)(t & 0xffffu), (uint32_t)(t >> 16) & 0xffffu, (uint32_t)(t >> 32) & 0xffffu);
+    }
+    if (tid == 0) three += 0.5 * triple(top_row - 1u, 0u, 0u);
+}
+
+
+#define LDPGTA_INST(CT)                                                                                              \
+    template __device__ void poly_homog_blocked<CT, uint32_t>(const CT *, int, const u64 *, int64_t, int, int, u64 &, u64 &, u64 &); \
+    template __device__ void poly_homog_blocked<CT, u64>(const CT *, int, const u64 *, int64_t, int, int, u64 &, u64 &, u64 &);      \
+    template __device__ void poly_recent_blocked<CT, uint32_t>(const CT *, const CT *, int, const u64 *, int64_t, int, int, u64 &, u64 &, u64 &, u64 &, u64 &, u64 &); \
+    template __device__ void poly_recent_blocked<CT, u64>(const CT *, const CT *, int, const u64 *, int64_t, int, int, u64 &, u64 &, u64 &, u64 &, u64 &, u64 &);      \
+    template __device__ void poly_distant_blocked<CT>(const CT *, const PanelView &, int, const u64 *, int64_t, int, int, double &, double &, double &);
+LDPGTA_INST(uint16_t)
+LDPGTA_INST(uint32_t)
+#undef LDPGTA_INST
+
+}  // namespace ldpgta

@@ -1,0 +1,36 @@
+// poly_general.cuh -- the partition polynomials of likelihoods() for 5..16 reads, evaluated from
+// the joint-frequency table(s) in shared memory (HOMOGENOUES_MODELS.py:185-225,
+// RECENT_ADMIXTURE_MODELS.py:198-247, DISTANT_ADMIXTURE_MODELS.py:215-256; weights of
+// MAKE_STATISTICAL_MODEL.py:24-102 in closed form).
+//
+// The three-block sum  S3 = sum over unordered {A,B,C} of F[A] F[B] F[C]  has S(n,3) ~ 3^n/6 terms
+// (7.1 M at n = 16) and is the expensive part.  Let A be the block that owns the last read and
+// U' the other n-1 reads: S3 = 1/2 * sum over colourings (a,b,c) of U' of G[a] F[b] F[c] with
+// G[a] = F[last | a] and F[empty] = 0.  U' is split into its 4 low reads (Lo) and h = n-5 high
+// reads (Hi); a table row is the 16 entries that share the high part.  For one colouring
+// (a_h,b_h,c_h) of Hi all 81 colourings of Lo are a trilinear form of three rows,
+//      T(X,Y,Z) = sum_a X[a] * (Y*Z)[Lo\a],   (Y*Z)[s] = sum_{b subset s} Y[b] Z[s\b],
+// evaluated from registers with compile-time indices: 97 multiply-adds for 81 terms, no subset
+// enumeration in the inner loop.  The colourings of Hi with b_h < c_h (the swap gives the same
+// value) come from a list built once per h on the host; b_h = c_h = empty is the one extra
+// term with weight 1/2.  Two-block sums are plain coalesced passes over the table.
+// The routines do not depend on the table kernel's tile shape: they are compiled once in
+// poly_general.cu and linked (relocatable device code) into every k_general instance.
+#pragma once
+#include "common.cuh"
+
+namespace ldpgta {
+
+// per-thread partials: two, two_sph and three (the caller sums them across the block in 128 bits);
+// ACC = uint32_t when 16 * N^2 < 2^32 (every group has at most 16383 haplotypes), else u64
+template <typename CT, typename ACC>
+__device__ void poly_homog_blocked(const CT *F, int n, const u64 *terms, int64_t n_terms, int tid, int T,
+                                   u64 &two, u64 &two_sph, u64 &three);
+template <typename CT, typename ACC>
+__device__ void poly_recent_blocked(const CT *F, const CT *G, int n, const u64 *terms, int64_t n_terms, int tid, int T,
+                                    u64 &ff, u64 &gg, u64 &fg, u64 &fg_sph, u64 &ffg, u64 &ggf);
+template <typename CT>
+__device__ void poly_distant_blocked(const CT *ftab, const PanelView &pv, int n, const u64 *terms, int64_t n_terms,
+                                     int tid, int T, double &two, double &two_sph, double &three);
+
+}  // namespace ldpgta
