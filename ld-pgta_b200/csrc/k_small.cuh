@@ -1,13 +1,13 @@
 // k_small.cuh -- draws of 2, 3 or 4 reads (the CLI default -M 4).
 //
 // A group of LPD lanes owns one draw, a warp owns a tile of 32/LPD draws, and every warp of a
-// persistent one-CTA-per-SM grid walks its tiles through a two-buffer shared-memory pipeline:
+// persistent one-CTA-per-SM grid (16 warps) walks its tiles through a shared-memory pipeline:
 //
 //   producer  the NR*32/LPD lanes that hold the tile's read indices each issue ONE bulk copy
 //             (cp.async.bulk, the 1-D TMA path: UBLKCP) of a whole read mask, HBM/L2 -> shared,
-//             completing on the buffer's mbarrier.  The copies for the next TWO tiles are always
-//             in flight while a tile is being computed (a buffer is refilled as soon as its
-//             masks have been pulled into registers), so the kernel is not exposed to DRAM latency.
+//             completing on the warp's mbarrier.  The buffer is refilled with the NEXT tile as soon
+//             as the current tile's masks have been pulled into registers, so the copy lands while
+//             the tile is being computed and the kernel is not exposed to DRAM latency.
 //   consumer  each lane pulls its 16-byte slots of the NR masks into registers (lane l of a draw's
 //             group takes slot j*LPD + l: conflict-free LDS.128), forms every subset intersection
 //             of two or more reads (joint_frequencies_combo, HOMOGENOUES_MODELS.py:129-163; one
@@ -185,9 +185,9 @@ __device__ __forceinline__ void small_dump(const SmallArgs &a, int64_t draw, int
 template <int NR, int WPL>
 struct SmallPipe {
     static constexpr int STAGE_BYTES = 256 * NR * WPL;                       // (32/LPD) draws * NR rows * LPD*WPL words * 8 B
-    static constexpr int NWARPS_RAW = (220 * 1024) / (2 * STAGE_BYTES);
+    static constexpr int NWARPS_RAW = (220 * 1024) / STAGE_BYTES;
     static constexpr int NWARPS = NWARPS_RAW > 16 ? 16 : (NWARPS_RAW & ~3);     // register file is allocated per 4 warps
-    static constexpr int SMEM = NWARPS * (2 * STAGE_BYTES + 16);
+    static constexpr int SMEM = NWARPS * (STAGE_BYTES + 16);
 };
 
 template <int NR, int LPD, int WPL, int KIND>
@@ -199,17 +199,17 @@ __global__ void __launch_bounds__(SmallPipe<NR, WPL>::NWARPS * 32, 1) k_small(co
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lane_in = lane % LPD, dgrp = lane / LPD;
-    unsigned char *wbase = smem + (size_t)warp * (2 * P::STAGE_BYTES);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)P::NWARPS * 2 * P::STAGE_BYTES) + 2 * warp;
+    unsigned char *wbase = smem + (size_t)warp * P::STAGE_BYTES;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (size_t)P::NWARPS * P::STAGE_BYTES) + warp;
 
-    if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
+    if (lane == 0) mbar_init(bar, 1);
     fence_proxy_async();
     __syncwarp();
 
     const int G = a.pv.G;
     const int64_t n_tiles = (a.n_draws + DPW - 1) / DPW;
     const int64_t tile0 = (int64_t)blockIdx.x * P::NWARPS + warp, tstride = (int64_t)gridDim.x * P::NWARPS;
-    // stages are (tile, group) pairs in order; stage q of this warp: tile = tile0 + (q / G) * tstride, group = q % G
+    // stages are (tile, group) pairs in order
     const int64_t my_tiles = tile0 < n_tiles ? (n_tiles - tile0 + tstride - 1) / tstride : 0;
     const int64_t n_stages = my_tiles * G;
 
@@ -220,78 +220,80 @@ __global__ void __launch_bounds__(SmallPipe<NR, WPL>::NWARPS * 32, 1) k_small(co
         if (d >= a.n_draws) d = a.n_draws - 1;                                 // ragged last tile: harmless duplicates
         return __ldg(a.idx + d * NR + lane % NR);
     };
-    auto issue = [&](int buf, int g, int32_t ridx) -> uint32_t {
+    auto issue = [&](int g, int32_t ridx) -> uint32_t {
         const int wp = a.pv.wp[g];
         const uint32_t row_bytes = (uint32_t)wp * 8u;
         uint32_t pc = 0;
-        if (lane == 0) mbar_arrive_expect_tx(&bars[buf], row_bytes * ROWS);
+        if (lane == 0) mbar_arrive_expect_tx(bar, row_bytes * ROWS);
         __syncwarp();
         if (lane < ROWS) {
-            bulk_copy_g2s(wbase + (size_t)buf * P::STAGE_BYTES + (size_t)lane * row_bytes,
-                          a.pv.masks[g] + (int64_t)ridx * wp, row_bytes, &bars[buf]);
+            bulk_copy_g2s(wbase + (size_t)lane * row_bytes, a.pv.masks[g] + (int64_t)ridx * wp, row_bytes, bar);
             pc = __ldg(a.pv.popc[g] + ridx);
         }
         return pc;
     };
 
-    // (tile, group) of the stage being consumed (cur), and of the next stage to issue (nxt = cur + 2 stages)
+    // (tile, group) of the stage being consumed (cur) and of the stage in flight / next to issue (nxt)
     int64_t cur_tile = tile0, nxt_tile = tile0;
     int cur_g = 0, nxt_g = 0;
     auto advance = [&](int64_t &tile, int &g) { if (++g == G) { g = 0; tile += tstride; } };
 
-    // prologue: stages 0 and 1 in flight, indices of the stage after them loaded
-    uint32_t pc0 = 0, pc1 = 0;               // row popcounts of the stages in buffers 0 and 1
+    // prologue: stage 0 in flight, indices of stage 1 loaded
+    uint32_t pc_cur = 0;                     // row popcounts of the stage in the buffer
     int32_t idx_nxt = 0;                     // row index of the next stage to issue
-    if (n_stages > 0) { pc0 = issue(0, nxt_g, load_idx(nxt_tile)); advance(nxt_tile, nxt_g); }
-    if (n_stages > 1) { pc1 = issue(1, nxt_g, load_idx(nxt_tile)); advance(nxt_tile, nxt_g); }
-    if (n_stages > 2) idx_nxt = load_idx(nxt_tile);
+    if (n_stages > 0) { pc_cur = issue(nxt_g, load_idx(nxt_tile)); advance(nxt_tile, nxt_g); }
+    if (n_stages > 1) idx_nxt = load_idx(nxt_tile);
 
     SmallModel<NR, KIND> model;
-    uint32_t parity0 = 0, parity1 = 0;
+    uint32_t parity = 0;
     for (int64_t q = 0; q < n_stages; ++q) {
-        const int buf = (int)(q & 1), g = cur_g;
+        const int g = cur_g;
         const int64_t draw = cur_tile * DPW + dgrp;
         const bool writer = draw < a.n_draws && lane_in == 0;
         const int wp = a.pv.wp[g];
         if (g == 0) model.init();
         advance(cur_tile, cur_g);
 
-        // single-read counts of this stage (prefetched with the indices), before the buffer state moves on
+        // single-read counts of this stage (prefetched with the indices)
         uint32_t c[NS];
 #pragma unroll
         for (int s = 0; s < NS; ++s) c[s] = 0;
-        {
-            const uint32_t pc = buf ? pc1 : pc0;
 #pragma unroll
-            for (int i = 0; i < NR; ++i) {
-                const uint32_t v = __shfl_sync(0xffffffffu, pc, dgrp * NR + i);
-                if (lane_in == 0) c[1 << i] = v;
-            }
+        for (int i = 0; i < NR; ++i) {
+            const uint32_t v = __shfl_sync(0xffffffffu, pc_cur, dgrp * NR + i);
+            if (lane_in == 0) c[1 << i] = v;
         }
 
-        if (buf) { mbar_wait(&bars[1], parity1); parity1 ^= 1u; }
-        else     { mbar_wait(&bars[0], parity0); parity0 ^= 1u; }
+        mbar_wait(bar, parity);
+        parity ^= 1u;
 
         uint4 m[NR][SLOTS];
         {
-            const unsigned char *st = wbase + (size_t)buf * P::STAGE_BYTES + (size_t)(dgrp * NR) * wp * 8;
+            const unsigned char *st = wbase + (size_t)(dgrp * NR) * wp * 8;
+            if (wp == LPD * WPL) {                          // rows fill the lane grid exactly: no bounds predicates
 #pragma unroll
-            for (int j = 0; j < SLOTS; ++j) {
-                const int w = (j * LPD + lane_in) * 2;
-                const bool in = w < wp;
+                for (int j = 0; j < SLOTS; ++j)
 #pragma unroll
-                for (int i = 0; i < NR; ++i)
-                    m[i][j] = in ? *reinterpret_cast<const uint4 *>(st + ((size_t)i * wp + w) * 8) : make_uint4(0, 0, 0, 0);
+                    for (int i = 0; i < NR; ++i)
+                        m[i][j] = *reinterpret_cast<const uint4 *>(st + ((size_t)i * (LPD * WPL) + (j * LPD + lane_in) * 2) * 8);
+            } else {
+#pragma unroll
+                for (int j = 0; j < SLOTS; ++j) {
+                    const int w = (j * LPD + lane_in) * 2;
+                    const bool in = w < wp;
+#pragma unroll
+                    for (int i = 0; i < NR; ++i)
+                        m[i][j] = in ? *reinterpret_cast<const uint4 *>(st + ((size_t)i * wp + w) * 8) : make_uint4(0, 0, 0, 0);
+                }
             }
         }
-        // the buffer is free again: refill it with stage q+2 before computing
+        // the buffer is free again: refill it with the next stage, which lands while this one is computed
         __syncwarp();
-        if (q + 2 < n_stages) {
+        if (q + 1 < n_stages) {
             fence_proxy_async();
-            const uint32_t pc_new = issue(buf, nxt_g, idx_nxt);
-            if (buf) pc1 = pc_new; else pc0 = pc_new;
+            pc_cur = issue(nxt_g, idx_nxt);
             advance(nxt_tile, nxt_g);
-            if (q + 3 < n_stages) idx_nxt = load_idx(nxt_tile);
+            if (q + 2 < n_stages) idx_nxt = load_idx(nxt_tile);
         }
 
         small_subset_counts<NR, WPL>(m, c);

@@ -1,16 +1,18 @@
 #!/bin/bash
-# Runs on the GPU box (under gpurun): bench line, reference arm, ncu launch list and one full capture.
+# Runs on the GPU box (under gpurun): bench line, reference arm, ncu launch list and full captures.
 set -u
 mkdir -p gpurun_out
-K='regex:k_small|k_general|k_llr|k_window|k_chrom|k_pack|k_build'
+K='regex:k_small|k_general|k_llr|k_window|k_chrom|k_pack|k_build|k_row|k_norm'
 ./tools/int_peaks > gpurun_out/INT_PEAKS.json 2> gpurun_out/int_peaks.err
 mkdir -p profiles && cp gpurun_out/INT_PEAKS.json profiles/INT_PEAKS.json
-timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
-timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"
+timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
+timeout 600 python bench.py --impl reference --steps 10 --warmup 2 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"
 ARGS="--steps 2 --warmup 3 --no-cpu-baseline"
 timeout 300 python bench.py $ARGS > gpurun_out/plain.log 2>&1 &&
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -c 60 --csv --log-file gpurun_out/launches.csv python bench.py $ARGS > gpurun_out/ncu_list.log 2>&1
 echo "ncu list rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_small -s 3 -c 2 -o gpurun_out/prof_ksmall -f python bench.py $ARGS > gpurun_out/ncu_full.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_small -s 3 -c 1 -o gpurun_out/prof_ksmall -f python bench.py $ARGS > gpurun_out/ncu_full.log 2>&1
 echo "ncu full rc=$?"
-tail -c 600 gpurun_out/bench.json
+./tools/ncu_general.sh 12 2000 4 prof_kgen12
+./tools/ncu_general.sh 16 600 2 prof_kgen16
+tail -c 400 gpurun_out/bench.json
