@@ -1,5 +1,6 @@
 // common.cuh -- context, error plumbing and small device helpers shared by the kernels.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -96,29 +97,35 @@ template <> struct PopcSum<0> { static __device__ __forceinline__ uint32_t run(c
 template <> struct PopcSum<1> { static __device__ __forceinline__ uint32_t run(const u64 *x) { return __popcll(x[0]); } };
 template <> struct PopcSum<2> { static __device__ __forceinline__ uint32_t run(const u64 *x) { return __popcll(x[0]) + __popcll(x[1]); } };
 
-// the same on 32-bit words (no 64-bit register pairing constraints for the allocator)
+// the same on 32-bit words (no 64-bit register pairing constraints for the allocator).  DEPTH limits the
+// number of carry-save levels: each level trades POPC (XU pipe, 16/clk/SM) for LOP3 (ALU pipe, 64/clk/SM);
+// the depth that balances the two pipes is chosen per kernel.
 __device__ __forceinline__ void csa32(uint32_t a, uint32_t b, uint32_t c, uint32_t &sum, uint32_t &carry)
 {
     sum = a ^ b ^ c;                       // one LOP3 (0x96)
     carry = (a & b) | (c & (a | b));       // one LOP3 (0xe8, majority)
 }
 
-template <int N>
+template <int N, int DEPTH>
 struct PopcSum32 {
     static __device__ __forceinline__ uint32_t run(const uint32_t *x)
     {
-        constexpr int K = N / 3, REM = N % 3;
-        uint32_t ones[K + REM], twos[K];
+        if constexpr (DEPTH == 0 || N < 3) {
+            uint32_t s = 0;
 #pragma unroll
-        for (int k = 0; k < K; ++k) csa32(x[3 * k], x[3 * k + 1], x[3 * k + 2], ones[k], twos[k]);
+            for (int i = 0; i < N; ++i) s += __popc(x[i]);
+            return s;
+        } else {
+            constexpr int K = N / 3, REM = N % 3;
+            uint32_t ones[K + REM + 1], twos[K + 1];
 #pragma unroll
-        for (int r = 0; r < REM; ++r) ones[K + r] = x[3 * K + r];
-        return PopcSum32<K + REM>::run(ones) + 2u * PopcSum32<K>::run(twos);
+            for (int k = 0; k < K; ++k) csa32(x[3 * k], x[3 * k + 1], x[3 * k + 2], ones[k], twos[k]);
+#pragma unroll
+            for (int r = 0; r < REM; ++r) ones[K + r] = x[3 * K + r];
+            return PopcSum32<K + REM, (DEPTH > 0 ? DEPTH - 1 : 0)>::run(ones) + 2u * PopcSum32<K, (DEPTH > 0 ? DEPTH - 1 : 0)>::run(twos);
+        }
     }
 };
-template <> struct PopcSum32<0> { static __device__ __forceinline__ uint32_t run(const uint32_t *) { return 0u; } };
-template <> struct PopcSum32<1> { static __device__ __forceinline__ uint32_t run(const uint32_t *x) { return __popc(x[0]); } };
-template <> struct PopcSum32<2> { static __device__ __forceinline__ uint32_t run(const uint32_t *x) { return __popc(x[0]) + __popc(x[1]); } };
 
 __device__ __forceinline__ double u128_to_double(u128 v)
 {
@@ -143,6 +150,9 @@ struct ldpgta_ctx {
     uint64_t *read_masks[ldpgta::MAXG] = {};
     uint32_t *read_popc[ldpgta::MAXG] = {};   // popcount of every read mask
     double *norm[ldpgta::MAXG] = {};          // x / nhap lookup per group
+    // 2-D tensor maps over the read masks ([n_reads][wp] uint64, box = one row) for TMA gather4 (k_small, 4 reads)
+    alignas(64) CUtensorMap tmap[ldpgta::MAXG];
+    bool tmap_ok[ldpgta::MAXG] = {};
     bool masks_owned[ldpgta::MAXG] = {};
     int64_t n_reads_g[ldpgta::MAXG] = {};
     int64_t n_reads = 0;
@@ -180,7 +190,8 @@ inline PanelView make_view(const ldpgta_ctx *c, const double *proportions)
 struct SmallArgs;
 struct GeneralArgs;
 // kernel launchers, one translation unit each (small.cu, general.cu)
-int launch_small(ldpgta_ctx *c, const SmallArgs &a, int n, int kind);
+int launch_small(ldpgta_ctx *c, SmallArgs &a, int n, int kind);
+int make_read_mask_tmap(ldpgta_ctx *c, int g);
 int launch_general(ldpgta_ctx *c, GeneralArgs a);
 
 }  // namespace ldpgta

@@ -26,6 +26,9 @@
 #include "common.cuh"
 #include "poly_closed.cuh"
 
+#ifndef LDPGTA_SMALL_CSA_DEPTH
+#define LDPGTA_SMALL_CSA_DEPTH 1  // carry-save levels before POPC (see PopcSum32): one level balances ALU and XU pipes (measured)
+#endif
 #ifndef LDPGTA_SMALL_MINB
 #define LDPGTA_SMALL_MINB 4      // k_small_direct: resident 128-thread blocks per SM the register allocation must allow
 #endif
@@ -39,6 +42,8 @@ struct SmallArgs {
     const int64_t *pos;      // optional scatter positions of the outputs
     double *out;             // [*][4]
     uint32_t *counts_out;    // optional [n_draws][G][2^NR]
+    int use_gather4;         // 4 reads per draw: one TMA gather4 per draw instead of four bulk copies
+    alignas(64) CUtensorMap tmap[2];   // read-mask tensors of groups 0 and 1 (box = one row)
 };
 
 // ---- PTX: mbarrier + bulk async copy (TMA 1-D) ---------------------------------------------
@@ -67,6 +72,13 @@ __device__ __forceinline__ void bulk_copy_g2s(void *dst_smem, const void *src_gm
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// four rows of a 2-D tensor in one instruction (sm_100 TMA tile::gather4); rows land back to back in shared memory
+__device__ __forceinline__ void tma_gather4_g2s(void *dst_smem, const CUtensorMap *tmap, int32_t col, int32_t r0, int32_t r1,
+                                                int32_t r2, int32_t r3, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                 ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -91,7 +103,7 @@ __device__ __forceinline__ void small_subset_counts(const uint4 (&m)[NR][WPL / 2
                 if ((s >> i) & 1) { x &= m[i][j].x; y &= m[i][j].y; z &= m[i][j].z; w &= m[i][j].w; }
             t[4 * j] = x; t[4 * j + 1] = y; t[4 * j + 2] = z; t[4 * j + 3] = w;
         }
-        c[s] += PopcSum32<2 * WPL>::run(t);
+        c[s] += PopcSum32<2 * WPL, LDPGTA_SMALL_CSA_DEPTH>::run(t);
     }
 }
 
@@ -191,13 +203,14 @@ struct SmallPipe {
 };
 
 template <int NR, int LPD, int WPL, int KIND>
-__global__ void __launch_bounds__(SmallPipe<NR, WPL>::NWARPS * 32, 1) k_small(const SmallArgs a)
+__global__ void __launch_bounds__(SmallPipe<NR, WPL>::NWARPS * 32, 1) k_small(const __grid_constant__ SmallArgs a)
 {
     static_assert(WPL % 2 == 0, "rows are read in 16-byte slots");
     using P = SmallPipe<NR, WPL>;
     constexpr int NS = 1 << NR, SLOTS = WPL / 2, DPW = 32 / LPD, ROWS = DPW * NR;
     extern __shared__ __align__(128) unsigned char smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);        // warp-uniform for the compiler: barrier and buffer addresses live in uniform registers
     const int lane_in = lane % LPD, dgrp = lane / LPD;
     unsigned char *wbase = smem + (size_t)warp * P::STAGE_BYTES;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (size_t)P::NWARPS * P::STAGE_BYTES) + warp;
@@ -220,16 +233,23 @@ __global__ void __launch_bounds__(SmallPipe<NR, WPL>::NWARPS * 32, 1) k_small(co
         if (d >= a.n_draws) d = a.n_draws - 1;                                 // ragged last tile: harmless duplicates
         return __ldg(a.idx + d * NR + lane % NR);
     };
-    auto issue = [&](int g, int32_t ridx) -> uint32_t {
+    auto issue = [&](int g_, int32_t ridx) -> uint32_t {
+        const int g = KIND == LDPGTA_HOMOGENEOUS ? 0 : g_;
         const int wp = a.pv.wp[g];
         const uint32_t row_bytes = (uint32_t)wp * 8u;
         uint32_t pc = 0;
         if (lane == 0) mbar_arrive_expect_tx(bar, row_bytes * ROWS);
         __syncwarp();
-        if (lane < ROWS) {
+        if (NR == 4 && a.use_gather4) {
+            // lane 4d holds read 0 of draw d; its neighbours hold reads 1..3
+            const int32_t r1 = __shfl_down_sync(0xffffffffu, ridx, 1), r2 = __shfl_down_sync(0xffffffffu, ridx, 2),
+                          r3 = __shfl_down_sync(0xffffffffu, ridx, 3);
+            if (lane < ROWS && (lane & 3) == 0)
+                tma_gather4_g2s(wbase + (size_t)lane * row_bytes, &a.tmap[g], 0, ridx, r1, r2, r3, bar);
+        } else if (lane < ROWS) {
             bulk_copy_g2s(wbase + (size_t)lane * row_bytes, a.pv.masks[g] + (int64_t)ridx * wp, row_bytes, bar);
-            pc = __ldg(a.pv.popc[g] + ridx);
         }
+        if (lane < ROWS) pc = __ldg(a.pv.popc[g] + ridx);
         return pc;
     };
 
@@ -247,7 +267,7 @@ __global__ void __launch_bounds__(SmallPipe<NR, WPL>::NWARPS * 32, 1) k_small(co
     SmallModel<NR, KIND> model;
     uint32_t parity = 0;
     for (int64_t q = 0; q < n_stages; ++q) {
-        const int g = cur_g;
+        const int g = KIND == LDPGTA_HOMOGENEOUS ? 0 : cur_g;
         const int64_t draw = cur_tile * DPW + dgrp;
         const bool writer = draw < a.n_draws && lane_in == 0;
         const int wp = a.pv.wp[g];

@@ -66,7 +66,7 @@ static int refresh_popc(ldpgta_ctx *c, int g)
         c->launches++;
         LDPGTA_CUDA(cudaGetLastError());
     }
-    return 0;
+    return make_read_mask_tmap(c, g);
 }
 
 static int check_kind(const ldpgta_ctx *c, int kind, const double *proportions)

@@ -1,5 +1,6 @@
 // small.cu -- kernels and launchers for draws of 2..4 reads (k_small.cuh).
 #include <algorithm>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "k_small.cuh"
@@ -7,7 +8,7 @@
 namespace ldpgta {
 
 template <int NR, int LPD, int WPL, int KIND>
-static int launch_small_pipe(ldpgta_ctx *c, const SmallArgs &a)
+static int launch_small_pipe(ldpgta_ctx *c, SmallArgs &a)
 {
     using P = SmallPipe<NR, WPL>;
     auto kern = k_small<NR, LPD, WPL, KIND>;
@@ -23,7 +24,7 @@ static int launch_small_pipe(ldpgta_ctx *c, const SmallArgs &a)
 }
 
 template <int NR, int KIND>
-static int launch_small_k(ldpgta_ctx *c, const SmallArgs &a)
+static int launch_small_k(ldpgta_ctx *c, SmallArgs &a)
 {
     int wmax = 0;
     for (int g = 0; g < c->G; ++g) wmax = std::max(wmax, c->wp[g]);
@@ -45,15 +46,52 @@ static int launch_small_k(ldpgta_ctx *c, const SmallArgs &a)
 }
 
 template <int NR>
-static int launch_small_n(ldpgta_ctx *c, const SmallArgs &a, int kind)
+static int launch_small_n(ldpgta_ctx *c, SmallArgs &a, int kind)
 {
     if (kind == LDPGTA_HOMOGENEOUS) return launch_small_k<NR, LDPGTA_HOMOGENEOUS>(c, a);
     if (kind == LDPGTA_RECENT_ADMIXTURE) return launch_small_k<NR, LDPGTA_RECENT_ADMIXTURE>(c, a);
     return launch_small_k<NR, LDPGTA_DISTANT_ADMIXTURE>(c, a);
 }
 
-int launch_small(ldpgta_ctx *c, const SmallArgs &a, int n, int kind)
+// Tensor map over group g's read masks: rank 2, [n_reads][wp] uint64, box = {wp, 1} (tile::gather4 fetches four
+// such boxes).  Encoded through the driver entry point so that the library does not link libcuda.
+int make_read_mask_tmap(ldpgta_ctx *c, int g)
 {
+    c->tmap_ok[g] = false;
+    if (!c->read_masks[g] || c->n_reads_g[g] <= 0 || c->wp[g] > 256) return 0;
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+            cudaGetLastError();
+            return 0;
+        }
+        encode = (encode_fn)fn;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)c->wp[g], (cuuint64_t)c->n_reads_g[g]};
+    const cuuint64_t gstride[1] = {(cuuint64_t)c->wp[g] * 8};
+    const cuuint32_t box[2] = {(cuuint32_t)c->wp[g], 1};
+    const cuuint32_t estride[2] = {1, 1};
+    const CUresult r = encode(&c->tmap[g], CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, (void *)c->read_masks[g], gdim, gstride, box, estride,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    c->tmap_ok[g] = (r == CUDA_SUCCESS);
+    return 0;
+}
+
+int launch_small(ldpgta_ctx *c, SmallArgs &a, int n, int kind)
+{
+    a.use_gather4 = 0;
+    if (n == 4 && !getenv("LDPGTA_NO_GATHER4") && a.pv.masks[0] == c->read_masks[0]) {
+        bool ok = true;
+        // each draw's four rows land at draw * 4 * row_bytes in the warp's buffer: TMA needs that 128-byte aligned
+        for (int g = 0; g < c->G && g < 2; ++g) { ok = ok && c->tmap_ok[g] && (c->wp[g] % 4 == 0); a.tmap[g] = c->tmap[g]; }
+        a.use_gather4 = (ok && c->G <= 2) ? 1 : 0;
+    }
     if (n == 2) return launch_small_n<2>(c, a, kind);
     if (n == 3) return launch_small_n<3>(c, a, kind);
     return launch_small_n<4>(c, a, kind);
