@@ -142,6 +142,8 @@ struct ldpgta_ctx {
     int words[ldpgta::MAXG] = {};   // ceil(nhap/64)
     int wp[ldpgta::MAXG] = {};      // padded to an even number of words
     cudaStream_t stream = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr;     // upload / download streams of the pipelined host path
+    std::vector<cudaEvent_t> ev_in, ev_k;
     int sm_count = 148;
     int max_smem_optin = 0;
 

@@ -47,6 +47,21 @@ static int ensure_pin(ldpgta_ctx *c, size_t bytes)
     return 0;
 }
 
+// copy streams and per-chunk events of the pipelined host path
+static int ensure_pipeline(ldpgta_ctx *c, int n_chunks)
+{
+    if (!c->s_in) LDPGTA_CUDA(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+    if (!c->s_out) LDPGTA_CUDA(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    while ((int)c->ev_in.size() < n_chunks) {
+        cudaEvent_t a, b;
+        LDPGTA_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        LDPGTA_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        c->ev_in.push_back(a);
+        c->ev_k.push_back(b);
+    }
+    return 0;
+}
+
 static bool is_pinned_or_device(const void *p)
 {
     cudaPointerAttributes at;
@@ -173,6 +188,10 @@ int ldpgta_destroy(ldpgta_ctx *c)
     if (c->d_buf) cudaFree(c->d_buf);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
+    for (cudaEvent_t e : c->ev_in) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_k) cudaEventDestroy(e);
     delete c;
     return 0;
 }
@@ -410,23 +429,39 @@ int ldpgta_likelihoods_batch(ldpgta_ctx *c, int kind, const int32_t *read_idx, c
     if (!read_idx) return fail(LDPGTA_E_INVALID, "null read_idx");
     if (draw_offsets[0] != 0) return fail(LDPGTA_E_INVALID, "draw_offsets must start at 0");
 
-    // size classes
+    // size classes (branch-free first pass: the common batch has one draw size)
     int64_t per_n[MAXN + 1] = {};
-    bool uniform = true;
-    const int n0 = (int)(draw_offsets[1] - draw_offsets[0]);
-    for (int64_t d = 0; d < n_draws; ++d) {
-        const int64_t n = draw_offsets[d + 1] - draw_offsets[d];
-        if (n < 2 || n > MAXN)
-            return fail(LDPGTA_E_UNSUPPORTED, "draw %lld has %lld reads, supported range is 2..%d", (long long)d, (long long)n, MAXN);
-        if (kind == LDPGTA_DISTANT_ADMIXTURE && n == 5)
+    const int64_t n0w = draw_offsets[1] - draw_offsets[0];
+    int64_t differs = 0;
+    for (int64_t d = 0; d < n_draws; ++d) differs |= (draw_offsets[d + 1] - draw_offsets[d]) ^ n0w;
+    const bool uniform = differs == 0;
+    const int n0 = (int)n0w;
+    if (uniform) {
+        if (n0w < 2 || n0w > MAXN)
+            return fail(LDPGTA_E_UNSUPPORTED, "draw 0 has %lld reads, supported range is 2..%d", (long long)n0w, MAXN);
+        if (kind == LDPGTA_DISTANT_ADMIXTURE && n0 == 5)
             return fail(LDPGTA_E_UNSUPPORTED, "distant_admixture has no likelihoods5 (reference: DISTANT_ADMIXTURE_MODELS.py:312-313 raises AttributeError)");
-        per_n[n]++;
-        uniform = uniform && n == n0;
+        per_n[n0] = n_draws;
+    } else {
+        for (int64_t d = 0; d < n_draws; ++d) {
+            const int64_t n = draw_offsets[d + 1] - draw_offsets[d];
+            if (n < 2 || n > MAXN)
+                return fail(LDPGTA_E_UNSUPPORTED, "draw %lld has %lld reads, supported range is 2..%d", (long long)d, (long long)n, MAXN);
+            if (kind == LDPGTA_DISTANT_ADMIXTURE && n == 5)
+                return fail(LDPGTA_E_UNSUPPORTED, "distant_admixture has no likelihoods5 (reference: DISTANT_ADMIXTURE_MODELS.py:312-313 raises AttributeError)");
+            per_n[n]++;
+        }
     }
     const int64_t nnz = draw_offsets[n_draws];
-    for (int64_t k = 0; k < nnz; ++k)
-        if (read_idx[k] < 0 || read_idx[k] >= c->n_reads)
-            return fail(LDPGTA_E_INVALID, "read index %d at %lld is outside 0..%lld", read_idx[k], (long long)k, (long long)c->n_reads - 1);
+    {
+        const uint32_t lim = (uint32_t)std::min<int64_t>(c->n_reads, 0x7fffffff);
+        uint32_t bad = 0;
+        for (int64_t k = 0; k < nnz; ++k) bad |= (uint32_t)((uint32_t)read_idx[k] >= lim);     // negative indices wrap above lim
+        if (bad)
+            for (int64_t k = 0; k < nnz; ++k)
+                if (read_idx[k] < 0 || read_idx[k] >= c->n_reads)
+                    return fail(LDPGTA_E_INVALID, "read index %d at %lld is outside 0..%lld", read_idx[k], (long long)k, (long long)c->n_reads - 1);
+    }
 
     const size_t idx_bytes = ((size_t)nnz * 4 + 15) & ~(size_t)15;
     const size_t pos_bytes = uniform ? 0 : (size_t)n_draws * 8;
@@ -436,6 +471,26 @@ int ldpgta_likelihoods_batch(ldpgta_ctx *c, int kind, const int32_t *read_idx, c
     int64_t *d_pos = (int64_t *)((char *)c->d_buf + idx_bytes);
     double *d_out = (double *)((char *)c->d_buf + idx_bytes + pos_bytes);
 
+    if (uniform && is_pinned_or_device(read_idx) && is_pinned_or_device(out)) {
+        // page-locked caller buffers: chunks flow through upload -> kernel -> download on three streams
+        const int64_t n_chunks = std::max<int64_t>(1, std::min<int64_t>(8, n_draws / 65536));
+        const int64_t per = ((n_draws + n_chunks - 1) / n_chunks + 63) & ~(int64_t)63;
+        if (int rc = ensure_pipeline(c, (int)n_chunks)) return rc;
+        int ci = 0;
+        for (int64_t d0 = 0; d0 < n_draws; d0 += per, ++ci) {
+            const int64_t nd = std::min(per, n_draws - d0);
+            LDPGTA_CUDA(cudaMemcpyAsync(d_idx + d0 * n0, read_idx + d0 * n0, (size_t)nd * n0 * 4, cudaMemcpyHostToDevice, c->s_in));
+            LDPGTA_CUDA(cudaEventRecord(c->ev_in[ci], c->s_in));
+            LDPGTA_CUDA(cudaStreamWaitEvent(c->stream, c->ev_in[ci], 0));
+            if (int rc = run_uniform(c, kind, n0, d_idx + d0 * n0, nd, nullptr, proportions, d_out + 4 * d0, nullptr)) return rc;
+            LDPGTA_CUDA(cudaEventRecord(c->ev_k[ci], c->stream));
+            LDPGTA_CUDA(cudaStreamWaitEvent(c->s_out, c->ev_k[ci], 0));
+            LDPGTA_CUDA(cudaMemcpyAsync(out + 4 * d0, d_out + 4 * d0, (size_t)nd * 32, cudaMemcpyDeviceToHost, c->s_out));
+        }
+        LDPGTA_CUDA(cudaStreamSynchronize(c->s_out));
+        LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
+        return 0;
+    }
     if (uniform) {
         const void *src = read_idx;
         if (!is_pinned_or_device(read_idx)) {

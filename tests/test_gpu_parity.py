@@ -378,3 +378,37 @@ def test_window_stats_against_python_statistics():
         _, _, p2 = eng.window_stats(lik[off[h]:], off[h:] - off[h], n_cols)
     both = L.finish_chromosome(p1 + p2, n_cols, int(counts[0]))
     assert np.max(np.abs(both - chrom)) < 1e-12
+
+
+def test_same_seed_reproduces_reference_without_replay(golden_inputs):
+    """ Drop-in property: with the reference's PYTHONHASHSEED and random seed, bootstrap() draws the same
+    read subsets as the reference did (same random.sample call sequence) and returns its likelihoods. """
+    import json, os, subprocess, sys
+    from conftest import GOLDEN, ROOT
+    code = r'''
+import bz2, pickle, random, sys, json
+sys.path.insert(0, %r)
+import ldpgta_b200 as L
+inp = pickle.load(bz2.open(%r + '/chrom_inputs.p.bz2', 'rb'))
+out = pickle.load(bz2.open(%r + '/chrom_homog_m4.p.bz2', 'rb'))
+cfg = out['cfg']
+hap = {g: inp['hap_tab'][g] for g in cfg['groups']}
+nh = {g: inp['number_of_haplotypes'][g] for g in cfg['groups']}
+random.seed(2021)
+lik, windows, _ = L.bootstrap(inp['obs_tabs'][cfg['scenario']], inp['leg_tab'], hap, nh, cfg['makeup'], L.ImplicitModels(),
+                              cfg['window_size'], cfg['subsamples'], cfg['offset'], cfg['min_reads'], cfg['max_reads'],
+                              cfg['min_score'], cfg['min_HF'])
+same_windows = {w: tuple(r) for w, r in windows.items()} == {w: tuple(r) for w, r in out['windows'].items()}
+worst = 0.0
+for w, ls in out['likelihoods'].items():
+    for mine, ref in zip(lik[w], ls):
+        for a, b in zip(mine, ref):
+            worst = max(worst, abs(a - b) / max(abs(a), abs(b), 1e-300))
+print(json.dumps({'same_windows': same_windows, 'worst': worst, 'n': sum(len(v) for v in lik.values())}))
+''' % (ROOT, GOLDEN, GOLDEN)
+    env = dict(os.environ, PYTHONHASHSEED='0')
+    res = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    got = json.loads(res.stdout.strip().splitlines()[-1])
+    assert got['same_windows'] and got['n'] == 392
+    assert got['worst'] < LIK_TOL, got
