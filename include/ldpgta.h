@@ -76,6 +76,14 @@ int ldpgta_upload_allele_rows(ldpgta_ctx *ctx, int group, const uint64_t *rows, 
 int ldpgta_build_read_masks(ldpgta_ctx *ctx, const int32_t *allele_idx, const int64_t *read_offsets,
                             int64_t n_reads);
 
+/* Read scores of supporting_dictionaries.build_score_dict (ANEUPLOIDY_TEST.py:151-189), used by
+ * build_gw_dict to filter reads (min_score, :215).  Reads are given like in ldpgta_build_read_masks;
+ * alpha[g] = ancestral share of group g / its haplotype count (:162), score_weight = the weight the
+ * reference applies to every group's haplotype count in :181-184 (the last group's alpha),
+ * min_HF as in the CLI.  out_scores[n_reads]; needs the allele rows of every group. */
+int ldpgta_read_scores(ldpgta_ctx *ctx, const int32_t *allele_idx, const int64_t *read_offsets, int64_t n_reads,
+                       const double *alpha, double score_weight, double min_HF, int32_t *out_scores);
+
 /* Alternative to the two calls above: upload ready-made read masks. */
 int ldpgta_upload_read_masks(ldpgta_ctx *ctx, int group, const uint64_t *rows, int64_t n_rows);
 /* Read masks straight from device memory laid out [n_rows][padded_words] with

@@ -26,6 +26,7 @@ SYMBOLS = (
     ('ldpgta_row_words', _c.c_int, [_P, _c.c_int]),
     ('ldpgta_upload_allele_rows', _c.c_int, [_P, _c.c_int, _P, _c.c_int64, _P]),
     ('ldpgta_build_read_masks', _c.c_int, [_P, _P, _P, _c.c_int64]),
+    ('ldpgta_read_scores', _c.c_int, [_P, _P, _P, _c.c_int64, _P, _c.c_double, _c.c_double, _P]),
     ('ldpgta_upload_read_masks', _c.c_int, [_P, _c.c_int, _P, _c.c_int64]),
     ('ldpgta_padded_row_words', _c.c_int, [_P, _c.c_int]),
     ('ldpgta_attach_read_masks_dev', _c.c_int, [_P, _c.c_int, _P, _c.c_int64]),

@@ -147,6 +147,7 @@ struct ldpgta_ctx {
     int sm_count = 148;
     int max_smem_optin = 0;
 
+    uint8_t *allele_complement = nullptr;     // per allele row: 1 = stored row is the complement of the panel row
     uint64_t *allele_rows[ldpgta::MAXG] = {};
     int64_t n_alleles[ldpgta::MAXG] = {};
     uint64_t *read_masks[ldpgta::MAXG] = {};

@@ -1,5 +1,6 @@
 // general.cu -- kernels, shared-memory planning and launcher for draws of 5..16 reads (k_general.cuh).
 #include <algorithm>
+#include <stdlib.h>
 #include <vector>
 
 #include "common.cuh"
@@ -17,6 +18,7 @@ static int plan_general(const ldpgta_ctx *c, int n, GeneralPlan *p)
     static const int BUDGET_KB[17] = {0, 0, 16, 16, 16, 16, 16, 20, 24, 28, 32, 48, 72, 110, 220, 220, 220};
     if (n < 5) { p->th = 1; p->tl = 1; p->nw = 1; p->kl = n; }       // likelihoods() forced on 2..4 reads
     else { p->th = TH[n]; p->tl = TL[n]; p->nw = NW[n]; p->kl = p->tl == 1 ? 5 : 7; }
+    if (const char *e = getenv("LDPGTA_PLAN_NW")) p->nw = atoi(e);          // tuning overrides
     p->kh = n - p->kl;
     uint32_t nmax = 0; int wmax = 0, wsum = 0;
     for (int g = 0; g < c->G; ++g) { nmax = std::max(nmax, c->nhap[g]); wmax = std::max(wmax, c->wp[g]); wsum += c->wp[g]; }
@@ -26,7 +28,9 @@ static int plan_general(const ldpgta_ctx *c, int n, GeneralPlan *p)
     const size_t ct = p->u16 ? 2 : 4;
     const size_t fixed = 64 + (size_t)n * wsum * 8 + ((ct * c->G) << n) + 64 + 16 + 32 * 12 * 8;
     const size_t per_word = ((size_t)8 << p->kl) + ((size_t)8 << p->kh);
-    const size_t cap = std::min<size_t>((size_t)c->max_smem_optin, (size_t)BUDGET_KB[n] * 1024);
+    size_t budget_kb = (size_t)BUDGET_KB[n];
+    if (const char *e = getenv("LDPGTA_PLAN_KB")) budget_kb = (size_t)atoi(e);
+    const size_t cap = std::min<size_t>((size_t)c->max_smem_optin, budget_kb * 1024);
     if (fixed + 2 * per_word > (size_t)c->max_smem_optin)
         return fail(LDPGTA_E_UNSUPPORTED, "draws of %d reads with %d group(s) do not fit shared memory (%zu B fixed)", n, c->G, fixed);
     size_t avail = cap > fixed ? cap - fixed : 0;

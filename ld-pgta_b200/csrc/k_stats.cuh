@@ -69,6 +69,82 @@ __global__ void k_row_popc(const uint64_t *__restrict__ rows, int64_t n_rows, in
     }
 }
 
+// Read scores (build_score_dict, ANEUPLOIDY_TEST.py:151-189), one warp per read.  A read's SNPs whose
+// effective allele frequency sum_g alpha_g * popcount(hap_g) lies in [0.01, 0.99] qualify (:173-175); over
+// the 2^k choices of (hap, hap ^ ones) for the k qualifying SNPs the score counts those whose haplotype
+// frequency  sum_g w * popcount(AND of the chosen rows in group g)  lies in [min_HF, 1 - min_HF] (:181-184).
+// `w` is what the reference actually applies to every group: the LAST group's alpha (its generators are
+// consumed after the comprehension variable has moved on).  The stored allele rows are hap or its
+// complement depending on the observed base; the set {hap, hap ^ ones} is the same either way.
+struct ScoreArgs {
+    const uint64_t *rows[MAXG];     // allele rows [n_alleles][wp[g]]
+    int wp[MAXG];
+    uint32_t nhap[MAXG];
+    double alpha[MAXG];
+    int G;
+    const uint8_t *complement;      // 1 = the stored row is the complement of the panel row
+    const int32_t *allele_idx;
+    const int64_t *off;
+    int64_t n_reads;
+    double w, min_HF, max_HF;
+    int32_t *out;                   // score per read; -1 = more than 12 qualifying SNPs (not evaluated)
+};
+
+__global__ void k_read_scores(const ScoreArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < a.n_reads; r += warps) {
+        const int64_t b = a.off[r], e = a.off[r + 1];
+        // qualifying SNPs of the read (:171-178)
+        int32_t q[12];
+        int k = 0;
+        bool too_many = false;
+        for (int64_t t = b; t < e; ++t) {
+            const int32_t ai = a.allele_idx[t];
+            double freq = 0.0;
+            for (int g = 0; g < a.G; ++g) {
+                uint32_t c = 0;
+                const uint64_t *row = a.rows[g] + (int64_t)ai * a.wp[g];
+                for (int w = lane; w < a.wp[g]; w += 32) c += __popcll(row[w]);
+#pragma unroll
+                for (int m = 16; m; m >>= 1) c += __shfl_xor_sync(0xffffffffu, c, m);
+                if (a.complement[ai]) c = a.nhap[g] - c;                       // popcount of the panel row itself
+                freq = freq + a.alpha[g] * (double)c;
+            }
+            if (0.01 <= freq && freq <= 0.99) {
+                if (k < 12) q[k++] = ai; else too_many = true;
+            }
+        }
+        int32_t score = 0;
+        if (too_many) score = -1;
+        else if (k > 0) {
+            for (int choice = 0; choice < (1 << k); ++choice) {
+                double freq = 0.0;
+                for (int g = 0; g < a.G; ++g) {
+                    const int wp = a.wp[g];
+                    uint32_t c = 0;
+                    for (int w = lane; w < wp; w += 32) {
+                        const int bits = (int)a.nhap[g] - 64 * w;
+                        const u64 valid = bits >= 64 ? ~0ull : (bits > 0 ? ((1ull << bits) - 1ull) : 0ull);
+                        u64 v = valid;
+                        for (int i = 0; i < k; ++i) {
+                            const u64 x = a.rows[g][(int64_t)q[i] * wp + w];
+                            v &= ((choice >> i) & 1) ? ~x : x;
+                        }
+                        c += __popcll(v);
+                    }
+#pragma unroll
+                    for (int m = 16; m; m >>= 1) c += __shfl_xor_sync(0xffffffffu, c, m);
+                    freq = freq + a.w * (double)c;
+                }
+                score += (a.min_HF <= freq && freq <= a.max_HF) ? 1 : 0;
+            }
+        }
+        if (lane == 0) a.out[r] = score;
+    }
+}
+
 // LLR(y, x), ANEUPLOIDY_TEST.py:78-90
 __device__ __forceinline__ double llr(double y, double x)
 {

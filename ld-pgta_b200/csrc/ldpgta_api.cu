@@ -185,6 +185,7 @@ int ldpgta_destroy(ldpgta_ctx *c)
     }
     for (int h = 0; h < 12; ++h)
         if (c->hi_terms[h]) cudaFree(c->hi_terms[h]);
+    if (c->allele_complement) cudaFree(c->allele_complement);
     if (c->d_buf) cudaFree(c->d_buf);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -251,6 +252,12 @@ int ldpgta_upload_allele_rows(ldpgta_ctx *c, int group, const uint64_t *rows, in
     LDPGTA_CUDA(cudaSetDevice(c->device));
     if (int rc = pack_to_device(c, group, rows, n_rows, complement, &c->allele_rows[group])) return rc;
     c->n_alleles[group] = n_rows;
+    if (group == 0) {                                  // the flags are a property of the allele, not of the group
+        if (c->allele_complement) { LDPGTA_CUDA(cudaFree(c->allele_complement)); c->allele_complement = nullptr; }
+        LDPGTA_CUDA(cudaMalloc((void **)&c->allele_complement, std::max<size_t>((size_t)n_rows, 16)));
+        if (complement) LDPGTA_CUDA(cudaMemcpy(c->allele_complement, complement, (size_t)n_rows, cudaMemcpyHostToDevice));
+        else LDPGTA_CUDA(cudaMemset(c->allele_complement, 0, std::max<size_t>((size_t)n_rows, 16)));
+    }
     return 0;
 }
 
@@ -325,6 +332,52 @@ int ldpgta_build_read_masks(ldpgta_ctx *c, const int32_t *allele_idx, const int6
     }
     c->n_reads = n_reads;
     LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int ldpgta_read_scores(ldpgta_ctx *c, const int32_t *allele_idx, const int64_t *read_offsets, int64_t n_reads,
+                       const double *alpha, double score_weight, double min_HF, int32_t *out_scores)
+{
+    if (!c || !read_offsets || !alpha || !out_scores || n_reads < 0) return fail(LDPGTA_E_INVALID, "bad arguments");
+    LDPGTA_CUDA(cudaSetDevice(c->device));
+    const int64_t n_alleles = c->n_alleles[0];
+    for (int g = 0; g < c->G; ++g) {
+        if (!c->allele_rows[g]) return fail(LDPGTA_E_STATE, "allele rows of group %d were not uploaded", g);
+        if (c->n_alleles[g] != n_alleles) return fail(LDPGTA_E_STATE, "groups hold different numbers of allele rows");
+    }
+    if (n_reads == 0) return 0;
+    if (read_offsets[0] != 0) return fail(LDPGTA_E_INVALID, "read_offsets must start at 0");
+    const int64_t nnz = read_offsets[n_reads];
+    for (int64_t r = 0; r < n_reads; ++r)
+        if (read_offsets[r + 1] < read_offsets[r]) return fail(LDPGTA_E_INVALID, "read_offsets must be non-decreasing");
+    if (nnz > 0 && !allele_idx) return fail(LDPGTA_E_INVALID, "null allele_idx");
+    for (int64_t k = 0; k < nnz; ++k)
+        if (allele_idx[k] < 0 || allele_idx[k] >= n_alleles)
+            return fail(LDPGTA_E_INVALID, "allele index %d at %lld is outside 0..%lld", allele_idx[k], (long long)k, (long long)n_alleles - 1);
+    const size_t idx_b = ((size_t)nnz * 4 + 15) & ~(size_t)15, off_b = ((size_t)(n_reads + 1) * 8 + 15) & ~(size_t)15;
+    if (int rc = ensure_dev(c, idx_b + off_b + (size_t)n_reads * 4)) return rc;
+    char *base = (char *)c->d_buf;
+    if (nnz) LDPGTA_CUDA(cudaMemcpyAsync(base, allele_idx, (size_t)nnz * 4, cudaMemcpyHostToDevice, c->stream));
+    LDPGTA_CUDA(cudaMemcpyAsync(base + idx_b, read_offsets, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    ScoreArgs a;
+    memset(&a, 0, sizeof a);
+    a.G = c->G;
+    for (int g = 0; g < c->G; ++g) { a.rows[g] = c->allele_rows[g]; a.wp[g] = c->wp[g]; a.nhap[g] = c->nhap[g]; a.alpha[g] = alpha[g]; }
+    a.complement = c->allele_complement;
+    a.allele_idx = (const int32_t *)base;
+    a.off = (const int64_t *)(base + idx_b);
+    a.n_reads = n_reads;
+    a.w = score_weight; a.min_HF = min_HF; a.max_HF = 1 - min_HF;
+    a.out = (int32_t *)(base + idx_b + off_b);
+    const unsigned blocks = (unsigned)std::min<int64_t>((n_reads * 32 + 255) / 256, (int64_t)c->sm_count * 16);
+    k_read_scores<<<blocks, 256, 0, c->stream>>>(a);
+    c->launches++;
+    LDPGTA_CUDA(cudaGetLastError());
+    LDPGTA_CUDA(cudaMemcpyAsync(out_scores, a.out, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, c->stream));
+    LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
+    for (int64_t r = 0; r < n_reads; ++r)
+        if (out_scores[r] < 0)
+            return fail(LDPGTA_E_UNSUPPORTED, "read %lld overlaps more than 12 common SNPs (2^k haplotype combinations are enumerated)", (long long)r);
     return 0;
 }
 

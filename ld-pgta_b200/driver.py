@@ -80,7 +80,9 @@ class supporting_dictionaries:
     """ reads / overlaps / positions / per-group panel rows / read scores, as
     ANEUPLOIDY_TEST.supporting_dictionaries (:96-189). Host-side in this round. """
 
-    def __init__(self, obs_tab, leg_tab, hap_tab_per_group, number_of_haplotypes_per_group, ancestral_makeup, min_HF):
+    def __init__(self, obs_tab, leg_tab, hap_tab_per_group, number_of_haplotypes_per_group, ancestral_makeup, min_HF, examine=None):
+        """ `examine` (a model object of models.py holding the device-resident allele rows) moves the read
+        scores to the GPU; without it they are computed on the host exactly as the reference does. """
         self.number_of_haplotypes_per_group = number_of_haplotypes_per_group
         self.min_HF = min_HF
         if type(ancestral_makeup) == dict:
@@ -91,9 +93,14 @@ class supporting_dictionaries:
         self.reads = self.build_reads_dict(obs_tab, self.leg_dict)
         self.overlaps = self.build_overlaps_dict(obs_tab, self.leg_dict)
         self.positions = (*self.overlaps.keys(),)
-        self.hap_tab_per_group = self.build_hap_tab_per_group(hap_tab_per_group, leg_tab, self.positions)
-        self.score = self.build_score_dict(self.reads, self.hap_tab_per_group, self.number_of_haplotypes_per_group,
-                                           self.ancestral_makeup, self.min_HF)
+        if examine is not None:
+            self.hap_tab_per_group = None              # the panel rows live on the device
+            self.score = self.build_score_dict_device(self.reads, examine, self.number_of_haplotypes_per_group,
+                                                      self.ancestral_makeup, self.min_HF)
+        else:
+            self.hap_tab_per_group = self.build_hap_tab_per_group(hap_tab_per_group, leg_tab, self.positions)
+            self.score = self.build_score_dict(self.reads, self.hap_tab_per_group, self.number_of_haplotypes_per_group,
+                                               self.ancestral_makeup, self.min_HF)
 
     def build_reads_dict(self, obs_tab, leg_dict):
         reads = collections.defaultdict(list)
@@ -113,6 +120,20 @@ class supporting_dictionaries:
         wanted = set(positions)
         return {group2: {leg[1]: hap for leg, hap in zip(leg_tab, hap_tab) if leg[1] in wanted}
                 for group2, hap_tab in hap_tab_per_group.items()}
+
+    def build_score_dict_device(self, reads_dict, examine, number_of_haplotypes_per_group, ancestral_makeup, min_HF):
+        """ build_score_dict (ANEUPLOIDY_TEST.py:151-189) on the GPU: one warp per read enumerates the 2^k
+        allele/complement combinations of its common SNPs (ldpgta_read_scores). """
+        alpha = {g: ancestral_makeup[g] / n for g, n in number_of_haplotypes_per_group.items()}
+        weight = list(alpha.values())[-1]          # the reference weights every group by the last alpha (:181-184)
+        index = examine._allele_index
+        allele_idx, offsets, ids = [], [0], []
+        for read_id, alleles in reads_dict.items():
+            allele_idx.extend(index[a] for a in alleles)
+            offsets.append(len(allele_idx))
+            ids.append(read_id)
+        scores = examine._engine.read_scores(allele_idx, offsets, [alpha[g] for g in examine._groups], weight, min_HF)
+        return dict(zip(ids, scores.tolist()))
 
     def build_score_dict(self, reads_dict, hap_tab_per_group, number_of_haplotypes_per_group, ancestral_makeup, min_HF):
         """ Number of allele/complement combinations of a read whose effective haplotype
@@ -260,10 +281,10 @@ def evaluate_draws(examine, reads_dict, draws):
 def bootstrap(obs_tab, leg_tab, hap_tab, number_of_haplotypes, ancestral_makeup, models_dict, window_size, subsamples,
               offset, min_reads, max_reads, min_score, min_HF, replay=None, device=0):
     """ ANEUPLOIDY_TEST.bootstrap (:250-287): (likelihoods, genomic_windows, fraction_of_matches). """
-    obs = supporting_dictionaries(obs_tab, leg_tab, hap_tab, number_of_haplotypes, ancestral_makeup, min_HF)
-    genomic_windows = build_gw_dict(obs, window_size, offset, min_reads, max_reads, min_score)
     examine = make_examiner(obs_tab, leg_tab, hap_tab, number_of_haplotypes, ancestral_makeup, models_dict, device=device)
     try:
+        obs = supporting_dictionaries(obs_tab, leg_tab, hap_tab, number_of_haplotypes, ancestral_makeup, min_HF, examine=examine)
+        genomic_windows = build_gw_dict(obs, window_size, offset, min_reads, max_reads, min_score)
         draws = plan_draws(genomic_windows, min_reads, max_reads, subsamples, replay=replay)
         likelihoods = evaluate_draws(examine, obs.reads, draws)
         return likelihoods, genomic_windows, examine.fraction_of_matches

@@ -88,6 +88,16 @@ class Engine:
         off = np.ascontiguousarray(read_offsets, dtype=np.int64)
         N.check(self.lib.ldpgta_build_read_masks(self._ctx, N.ptr(idx), N.ptr(off), len(off) - 1))
 
+    def read_scores(self, allele_idx, read_offsets, alpha, score_weight, min_HF):
+        """ build_score_dict (ANEUPLOIDY_TEST.py:151-189) for reads given as lists of allele rows. """
+        idx = np.ascontiguousarray(allele_idx, dtype=np.int32)
+        off = np.ascontiguousarray(read_offsets, dtype=np.int64)
+        al = np.ascontiguousarray(alpha, dtype=np.float64)
+        out = np.zeros(len(off) - 1, dtype=np.int32)
+        N.check(self.lib.ldpgta_read_scores(self._ctx, N.ptr(idx), N.ptr(off), len(off) - 1, N.ptr(al),
+                                            float(score_weight), float(min_HF), N.ptr(out)))
+        return out
+
     def upload_read_masks(self, group, rows):
         if not isinstance(rows, np.ndarray):
             rows = pack_ints(list(rows), self.n_hap[group])

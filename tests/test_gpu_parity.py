@@ -412,3 +412,20 @@ print(json.dumps({'same_windows': same_windows, 'worst': worst, 'n': sum(len(v) 
     got = json.loads(res.stdout.strip().splitlines()[-1])
     assert got['same_windows'] and got['n'] == 392
     assert got['worst'] < LIK_TOL, got
+
+
+@pytest.mark.parametrize('name', CHROM_CONFIGS)
+def test_read_scores_on_device_match_reference(name, golden_inputs):
+    """ build_score_dict (ANEUPLOIDY_TEST.py:151-189) on the GPU: exact integer scores, including the
+    reference's last-alpha weighting for unequal group sizes. """
+    args, out = chrom_case(name, golden_inputs)
+    cfg = args['cfg']
+    model = driver.make_examiner(args['obs_tab'], args['leg_tab'], args['hap_tab'], args['number_of_haplotypes'],
+                                 args['ancestral_makeup'], L.ImplicitModels())
+    try:
+        obs = driver.supporting_dictionaries(args['obs_tab'], args['leg_tab'], args['hap_tab'], args['number_of_haplotypes'],
+                                             args['ancestral_makeup'], cfg['min_HF'], examine=model)
+        assert obs.score == out['score']
+        assert list(obs.score) == list(out['score'])
+    finally:
+        model.close()
