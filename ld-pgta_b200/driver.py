@@ -89,9 +89,11 @@ class supporting_dictionaries:
             self.ancestral_makeup = {group2: ancestral_makeup[group2] for group2 in hap_tab_per_group}
         else:
             self.ancestral_makeup = {group2: 1 / len(ancestral_makeup) for group2 in hap_tab_per_group}
-        self.leg_dict = {l[1]: (l[2], l[3]) for l in leg_tab}
-        self.reads = self.build_reads_dict(obs_tab, self.leg_dict)
-        self.overlaps = self.build_overlaps_dict(obs_tab, self.leg_dict)
+        self._leg_tab = leg_tab
+        wanted = {row[0] for row in obs_tab}           # leg_dict restricted to observed positions; the full one is built on demand
+        observed_leg = {l[1]: (l[2], l[3]) for l in leg_tab if l[1] in wanted}
+        self.reads = self.build_reads_dict(obs_tab, observed_leg)
+        self.overlaps = self.build_overlaps_dict(obs_tab, observed_leg)
         self.positions = (*self.overlaps.keys(),)
         if examine is not None:
             self.hap_tab_per_group = None              # the panel rows live on the device
@@ -101,6 +103,13 @@ class supporting_dictionaries:
             self.hap_tab_per_group = self.build_hap_tab_per_group(hap_tab_per_group, leg_tab, self.positions)
             self.score = self.build_score_dict(self.reads, self.hap_tab_per_group, self.number_of_haplotypes_per_group,
                                                self.ancestral_makeup, self.min_HF)
+
+    @property
+    def leg_dict(self):
+        """ position -> (ref, alt) for the whole legend (ANEUPLOIDY_TEST.py:110). """
+        if not hasattr(self, '_leg_dict'):
+            self._leg_dict = {l[1]: (l[2], l[3]) for l in self._leg_tab}
+        return self._leg_dict
 
     def build_reads_dict(self, obs_tab, leg_dict):
         reads = collections.defaultdict(list)

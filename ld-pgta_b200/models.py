@@ -57,9 +57,9 @@ class _PanelModel:
         self._groups = groups
         self._nhap = {g: number_of_haplotypes_per_group[g] for g in groups}
         # build_hap_dict (HOMOGENOUES_MODELS.py:76-100): legend lookup, last duplicate position wins (:84)
-        by_pos = {}
-        for i, leg in enumerate(leg_tab):
-            by_pos[leg[1]] = (leg[2], leg[3], i)
+        # (only observed positions are indexed: the panel has ~20x more SNPs than a low-coverage sample touches)
+        wanted = {row[0] for row in obs_tab}
+        by_pos = {leg[1]: (leg[2], leg[3], i) for i, leg in enumerate(leg_tab) if leg[1] in wanted}
         self._allele_index = {}
         rows, comp = [], []
         mismatches = 0

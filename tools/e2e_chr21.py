@@ -1,0 +1,53 @@
+#!/usr/bin/env python3
+"""Times the phases of the drop-in bootstrap() on BASELINE.json configs[0]: chr21-sized synthetic disomy
+sample at 0.05x, 1 000 000-SNP x 5008-haplotype random panel, on one GPU.
+The reference's own phase times for the same input (measured in the survey container, 1 core):
+supporting_dictionaries 2.39 s, build_hap_dict 0.75 s, build_gw_dict 0.05 s, bootstrap loop 1.19 s,
+statistics 0.26 s."""
+import json, os, random, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import ldpgta_b200 as L
+from ldpgta_b200 import driver
+
+L_CHR21, S, N = 46709983, int(os.environ.get('SNPS', 1000000)), 5008
+random.seed(12345)
+t0 = time.time()
+positions = sorted(random.sample(range(1, L_CHR21 + 1), S))
+refalt = [tuple(random.sample('ACGT', 2)) for _ in range(S)]
+rows = [random.getrandbits(N) for _ in range(S)]
+leg = tuple(('chr21', p, r, a) for p, (r, a) in zip(positions, refalt))
+hap = {'ALL': tuple(rows)}
+nh = {'ALL': N}
+hapl = [{p: (ra[1] if (row >> b) & 1 else ra[0]) for p, row, ra in zip(positions, rows, refalt)} for b in (17, 4242)]
+# the simulator's read model (MIX_HAPLOIDS.build_obs_tab: uniform starts, 36 bp, disomy), restated
+random.seed(777)
+n_reads = int(0.05 * L_CHR21 // 36)
+obs = []
+for i in range(n_reads):
+    p = random.randrange(L_CHR21) + 1
+    h = random.choices((0, 1), k=1)[0]
+    rid = '%d.%d.%s.%d' % (p - 18, p + 17, 'AB'[h], i)
+    src = hapl[h]
+    obs.extend((q, rid, src[q]) for q in range(p - 18, p + 18) if q in src)
+obs.sort(key=lambda r: r[0])
+t_gen = time.time() - t0
+print('generated %d observations in %.1f s' % (len(obs), t_gen), file=sys.stderr)
+
+phases = {}
+def timed(name, fn, *a, **k):
+    t = time.time(); r = fn(*a, **k); phases[name] = phases.get(name, 0.0) + time.time() - t; return r
+
+random.seed(1)
+warm = timed('cuda_context_first_use (once per process)', L.Engine, [64]); warm.close()
+examine = timed('model_init (build_hap_dict + upload)', driver.make_examiner, obs, leg, hap, nh, {'ALL'}, L.ImplicitModels())
+sd = timed('supporting_dictionaries (scores on device)', driver.supporting_dictionaries, obs, leg, hap, nh, {'ALL'}, 0.05, examine=examine)
+gw = timed('build_gw_dict', driver.build_gw_dict, sd, 100000, 0, 6, 4, 2)
+draws = timed('plan_draws (random.sample)', driver.plan_draws, gw, 6, 4, 32)
+lik = timed('evaluate_draws (masks + batch on device)', driver.evaluate_draws, examine, sd.reads, draws)
+st = timed('statistics (device)', driver.statistics, lik, gw)
+examine.close()
+n_eval = sum(len(v) for v in lik.values())
+print(json.dumps({'windows': len(gw), 'evaluated_windows': len(lik), 'window_likelihoods': n_eval, 'phases_s': phases,
+                  'total_s': sum(phases.values()),
+                  'BPH_vs_SPH': st['LLRs_per_chromosome'][('BPH', 'SPH')]}, indent=1))
