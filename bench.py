@@ -413,6 +413,13 @@ def main():
     except Exception:
         pass
     achieved_wordops = wordops_per_draw * n_draws / (k_ms * 1e-3)
+    traffic = None                                            # DRAM bytes per launch from the committed ncu capture of this kernel
+    try:
+        t = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json'))).get('k_small<%d,8,10>' % n)
+        if t and n <= 4:
+            traffic = t['dram_bytes_per_launch'] * n_draws / t['draws_per_launch']
+    except Exception:
+        pass
 
     # ---- CPU baseline: oracle port on a bounded sample, one core; doubles as the parity check -------
     cpu_baseline, parity = None, None
@@ -449,7 +456,7 @@ def main():
                 'api': 'Engine.likelihoods_batch -> ldpgta_likelihoods_batch (pinned host buffers)'},
         'gpu_launches': int(launches),
         'roofline': {'bound': 'hbm', 'kernel': 'k_small<%d,8,10>' % n if n <= 4 else 'k_general (n=%d)' % n, 'achieved': achieved_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
-                     'frac': achieved_gbs / hbm_peak, 'traffic': None, 'peak_source': peak_src,
+                     'frac': achieved_gbs / hbm_peak, 'traffic': traffic, 'peak_source': peak_src,
                      'algorithmic_bytes_per_draw': bytes_per_draw, 'kernel_ms': k_ms},
         'int_roofline': {'bound': 'popc', 'achieved': achieved_wordops, 'peak': int_peak, 'unit': 'word AND+POPC/s',
                          'frac': achieved_wordops / int_peak, 'peak_source': int_src, 'wordops_per_draw': wordops_per_draw},

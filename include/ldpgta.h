@@ -48,7 +48,7 @@ enum {
 enum { LDPGTA_HOMOGENEOUS = 0, LDPGTA_RECENT_ADMIXTURE = 1, LDPGTA_DISTANT_ADMIXTURE = 2 };
 
 #define LDPGTA_MAX_GROUPS 8
-#define LDPGTA_MAX_READS_PER_DRAW 16   /* reads per draw handled on device; the reference ships tables to 18 */
+#define LDPGTA_MAX_READS_PER_DRAW 18   /* reads per draw handled on device = the largest model table the reference ships (MODELS18.p) */
 #define LDPGTA_NUM_LLR_PAIRS 5         /* (BPH,SPH) (disomy,monosomy) (BPH,disomy) (disomy,SPH) (SPH,monosomy) */
 
 const char *ldpgta_last_error(void);
@@ -93,7 +93,7 @@ int ldpgta_attach_read_masks_dev(ldpgta_ctx *ctx, int group, const uint64_t *row
 int64_t ldpgta_num_reads(const ldpgta_ctx *ctx);
 
 /* joint_frequencies_combo(normalize=False) (HOMOGENOUES_MODELS.py:129-163) for ONE draw of
- * n reads (2..16): out_counts[g][S] for S = 0 .. 2^n-1 (S = subset bitmask, entry 0 unused = 0).
+ * n reads (2..18): out_counts[g][S] for S = 0 .. 2^n-1 (S = subset bitmask, entry 0 unused = 0).
  * Parity hook: counts are bit-exact. */
 int ldpgta_joint_counts(ldpgta_ctx *ctx, const int32_t *read_idx, int n, uint32_t *out_counts);
 
@@ -109,7 +109,7 @@ int ldpgta_get_likelihoods(ldpgta_ctx *ctx, int model_kind, const int32_t *allel
 /* get_likelihoods (HOMOGENOUES_MODELS.py:272-286, RECENT_...:314-328, DISTANT_...:300-316)
  * for a batch of draws = the body of the bootstrap loop ANEUPLOIDY_TEST.py:277-286.
  *   read_idx      concatenated read indices (rows of the read-mask table)
- *   draw_offsets  n_draws+1 offsets into read_idx; draw d has 2..16 reads
+ *   draw_offsets  n_draws+1 offsets into read_idx; draw d has 2..18 reads
  *   proportions   LDPGTA_DISTANT_ADMIXTURE only: ancestral proportion per group, in the
  *                 order of the ancestral_makeup dict (sum order of DISTANT_...:138-139)
  *   out           [n_draws][4] = monosomy, disomy, SPH, BPH (likelihoods_tuple order)

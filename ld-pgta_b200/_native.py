@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libldpgta.so')
 
 HOMOGENEOUS, RECENT_ADMIXTURE, DISTANT_ADMIXTURE = 0, 1, 2
-MAX_READS_PER_DRAW = 16
+MAX_READS_PER_DRAW = 18
 NUM_LLR_PAIRS = 5
 
 # every symbol include/ldpgta.h declares: (name, restype, argtypes)

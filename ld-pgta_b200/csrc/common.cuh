@@ -165,8 +165,11 @@ struct ldpgta_ctx {
     void *d_buf = nullptr;  size_t d_buf_bytes = 0;
 
     // colourings of the high reads used by the three-block polynomial, one list per h = n - 5 (built on first use)
-    uint64_t *hi_terms[12] = {};
-    int64_t n_hi_terms[12] = {};
+    uint64_t *hi_terms[14] = {};
+    int64_t n_hi_terms[14] = {};
+    // joint-frequency tables that do not fit shared memory (17-18 reads, or two-group models at 16): one slice per resident CTA
+    unsigned char *table_scratch = nullptr;
+    size_t table_scratch_bytes = 0;
 
     int64_t launches = 0;
 };

@@ -8,25 +8,28 @@
 
 namespace ldpgta {
 
-struct GeneralPlan { int th, tl, nw, kl, kh, wc; bool u16; size_t smem; };
+struct GeneralPlan { int th, tl, nw, kl, kh, wc; bool u16, global_table; size_t smem, table_bytes; };
 
 static int plan_general(const ldpgta_ctx *c, int n, GeneralPlan *p)
 {
-    static const int TH[17] = {0, 0, 0, 0, 0, 1, 2, 4, 8, 4, 8, 8, 8, 8, 8, 8, 8};
-    static const int TL[17] = {0, 0, 0, 0, 0, 1, 1, 1, 1, 4, 4, 4, 4, 4, 4, 4, 4};
-    static const int NW[17] = {0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 2, 4, 8, 16, 16, 16};
-    static const int BUDGET_KB[17] = {0, 0, 16, 16, 16, 16, 16, 20, 24, 28, 32, 48, 72, 110, 220, 220, 220};
+    static const int TH[19] = {0, 0, 0, 0, 0, 1, 2, 4, 8, 4, 8, 8, 8, 8, 8, 8, 8, 8, 8};
+    static const int TL[19] = {0, 0, 0, 0, 0, 1, 1, 1, 1, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4};
+    static const int NW[19] = {0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 2, 4, 8, 16, 16, 16, 16, 16};
+    static const int BUDGET_KB[19] = {0, 0, 16, 16, 16, 16, 16, 20, 24, 28, 32, 48, 56, 110, 220, 220, 220, 220, 220};
     if (n < 5) { p->th = 1; p->tl = 1; p->nw = 1; p->kl = n; }       // likelihoods() forced on 2..4 reads
     else { p->th = TH[n]; p->tl = TL[n]; p->nw = NW[n]; p->kl = p->tl == 1 ? 5 : 7; }
     if (const char *e = getenv("LDPGTA_PLAN_NW")) p->nw = atoi(e);          // tuning overrides
     p->kh = n - p->kl;
     uint32_t nmax = 0; int wmax = 0, wsum = 0;
     for (int g = 0; g < c->G; ++g) { nmax = std::max(nmax, c->nhap[g]); wmax = std::max(wmax, c->wp[g]); wsum += c->wp[g]; }
-    p->u16 = ((size_t)c->G << n) * 4 > 64 * 1024;
-    if (p->u16 && nmax > 65535u)
-        return fail(LDPGTA_E_UNSUPPORTED, "draws of %d reads need 16-bit count tables, panel group has %u > 65535 haplotypes", n, nmax);
+    // joint-frequency tables: 32-bit entries in shared memory while they stay under 64 KB, then 16-bit entries (groups of
+    // at most 65535 haplotypes) up to 128 KB, otherwise one slice per resident CTA in global memory (L2-resident)
+    const size_t entries = (size_t)c->G << n;
+    p->u16 = entries * 4 > 64 * 1024 && nmax <= 65535u;
     const size_t ct = p->u16 ? 2 : 4;
-    const size_t fixed = 64 + (size_t)n * wsum * 8 + ((ct * c->G) << n) + 64 + 16 + 32 * 12 * 8;
+    p->table_bytes = entries * ct;
+    p->global_table = p->table_bytes > 128 * 1024;
+    const size_t fixed = 128 + (size_t)n * wsum * 8 + (p->global_table ? 0 : p->table_bytes) + 64 + 16 + 32 * 12 * 8;
     const size_t per_word = ((size_t)8 << p->kl) + ((size_t)8 << p->kh);
     size_t budget_kb = (size_t)BUDGET_KB[n];
     if (const char *e = getenv("LDPGTA_PLAN_KB")) budget_kb = (size_t)atoi(e);
@@ -42,15 +45,15 @@ static int plan_general(const ldpgta_ctx *c, int n, GeneralPlan *p)
     wc = (wmax + chunks - 1) / chunks;
     p->wc = wc;
     PanelView pv = make_view(c, nullptr);
-    p->smem = p->u16 ? general_smem_layout<uint16_t>(pv, n, p->kl, p->kh, wc).total
-                     : general_smem_layout<uint32_t>(pv, n, p->kl, p->kh, wc).total;
+    p->smem = p->u16 ? general_smem_layout<uint16_t>(pv, n, p->kl, p->kh, wc, !p->global_table).total
+                     : general_smem_layout<uint32_t>(pv, n, p->kl, p->kh, wc, !p->global_table).total;
     if (p->smem > (size_t)c->max_smem_optin)
         return fail(LDPGTA_E_UNSUPPORTED, "draws of %d reads need %zu B of shared memory", n, p->smem);
     return 0;
 }
 
 template <int TH, int TL, typename CT>
-static int launch_general_t(ldpgta_ctx *c, const GeneralArgs &a, const GeneralPlan &p)
+static int launch_general_t(ldpgta_ctx *c, GeneralArgs a, const GeneralPlan &p)
 {
     auto kern = k_general<TH, TL, CT>;
     LDPGTA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
@@ -59,6 +62,19 @@ static int launch_general_t(ldpgta_ctx *c, const GeneralArgs &a, const GeneralPl
     if (per_sm < 1) return fail(LDPGTA_E_UNSUPPORTED, "general kernel does not fit an SM (n=%d, smem=%zu)", a.n, p.smem);
     const int64_t resident = (int64_t)per_sm * c->sm_count;
     const unsigned blocks = (unsigned)std::min<int64_t>(a.n_draws, resident);
+    a.table_scratch = nullptr; a.table_stride = 0;
+    if (p.global_table) {
+        const size_t stride = (p.table_bytes + 255) & ~(size_t)255, need = stride * blocks;
+        if (c->table_scratch_bytes < need) {
+            LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
+            if (c->table_scratch) LDPGTA_CUDA(cudaFree(c->table_scratch));
+            c->table_scratch = nullptr; c->table_scratch_bytes = 0;
+            LDPGTA_CUDA(cudaMalloc((void **)&c->table_scratch, need));
+            c->table_scratch_bytes = need;
+        }
+        a.table_scratch = c->table_scratch;
+        a.table_stride = stride;
+    }
     kern<<<blocks, 32 * p.nw, p.smem, c->stream>>>(a);
     c->launches++;
     LDPGTA_CUDA(cudaGetLastError());

@@ -36,6 +36,8 @@ struct GeneralArgs {
     const u64 *terms;        // colourings (a_h | b_h << 16 | c_h << 32) of the n-5 high reads with b_h < c_h (poly_general.cuh)
     int64_t n_terms;
     int wide;                // 64-bit convolution accumulators (a group with more than 16383 haplotypes)
+    unsigned char *table_scratch;   // non-null: the joint-frequency tables live in global memory (L2), one slice per CTA
+    size_t table_stride;
 };
 
 struct GeneralSmem {         // byte offsets into dynamic shared memory
@@ -43,10 +45,10 @@ struct GeneralSmem {         // byte offsets into dynamic shared memory
 };
 
 template <typename CT>
-__host__ __device__ inline GeneralSmem general_smem_layout(const PanelView &pv, int n, int kl, int kh, int wc)
+__host__ __device__ inline GeneralSmem general_smem_layout(const PanelView &pv, int n, int kl, int kh, int wc, bool table_in_smem = true)
 {
     GeneralSmem s;
-    int off = 64;                                        // s_idx[16]
+    int off = 128;                                       // s_idx[32]
     s.masks = off;
     int words = 0;
     for (int g = 0; g < pv.G; ++g) words += n * pv.wp[g];
@@ -54,7 +56,7 @@ __host__ __device__ inline GeneralSmem general_smem_layout(const PanelView &pv, 
     s.ltab = off; off += (wc << kl) * 8;
     s.htab = off; off += (wc << kh) * 8;
     off = (off + 63) & ~63;                              // table rows are read with 128-bit loads
-    s.ftab = off; off += (int)(sizeof(CT) * pv.G) << n;
+    s.ftab = off; if (table_in_smem) off += (int)(sizeof(CT) * pv.G) << n;
     off = (off + 15) & ~15;
     s.red = off; off += 32 * 12 * 8;
     s.total = off;
@@ -123,12 +125,13 @@ __global__ void __launch_bounds__(512, 1) k_general(const GeneralArgs a)
     extern __shared__ __align__(128) unsigned char smem[];
     const int n = a.n, kl = a.kl, kh = a.kh, G = a.pv.G;
     const int LS = 1 << kl, HS = 1 << kh, NS = 1 << n;
-    const GeneralSmem lay = general_smem_layout<CT>(a.pv, n, kl, kh, a.wc);
+    const GeneralSmem lay = general_smem_layout<CT>(a.pv, n, kl, kh, a.wc, a.table_scratch == nullptr);
     int32_t *s_idx = reinterpret_cast<int32_t *>(smem);
     u64 *s_masks = reinterpret_cast<u64 *>(smem + lay.masks);
     u64 *ltab = reinterpret_cast<u64 *>(smem + lay.ltab);
     u64 *htab = reinterpret_cast<u64 *>(smem + lay.htab);
-    CT *ftab = reinterpret_cast<CT *>(smem + lay.ftab);
+    CT *ftab = a.table_scratch ? reinterpret_cast<CT *>(a.table_scratch + (size_t)blockIdx.x * a.table_stride)
+                               : reinterpret_cast<CT *>(smem + lay.ftab);
     u64 *red = reinterpret_cast<u64 *>(smem + lay.red);
 
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, NW = T >> 5;
@@ -255,10 +258,8 @@ __global__ void __launch_bounds__(512, 1) k_general(const GeneralArgs a)
             u64 two = 0, two_sph = 0;
             u128 three = 0;
             if (n >= 5) {
-                u64 t3;
-                if (a.wide) poly_homog_blocked<CT, u64>(F, n, a.terms, a.n_terms, tid, T, two, two_sph, t3);
-                else poly_homog_blocked<CT, uint32_t>(F, n, a.terms, a.n_terms, tid, T, two, two_sph, t3);
-                three = t3;
+                if (a.wide) poly_homog_blocked<CT, u64>(F, n, a.terms, a.n_terms, tid, T, two, two_sph, three);
+                else poly_homog_blocked<CT, uint32_t>(F, n, a.terms, a.n_terms, tid, T, two, two_sph, three);
             } else
             for (uint32_t A = top + warp; A < full; A += NW) {
                 const uint32_t rest = full ^ A;
@@ -304,10 +305,8 @@ __global__ void __launch_bounds__(512, 1) k_general(const GeneralArgs a)
             u64 ff = 0, gg = 0, fg = 0, fg_sph = 0;
             u128 ffg = 0, ggf = 0;
             if (n >= 5) {
-                u64 t_ffg, t_ggf;
-                if (a.wide) poly_recent_blocked<CT, u64>(F, Gt, n, a.terms, a.n_terms, tid, T, ff, gg, fg, fg_sph, t_ffg, t_ggf);
-                else poly_recent_blocked<CT, uint32_t>(F, Gt, n, a.terms, a.n_terms, tid, T, ff, gg, fg, fg_sph, t_ffg, t_ggf);
-                ffg = t_ffg; ggf = t_ggf;
+                if (a.wide) poly_recent_blocked<CT, u64>(F, Gt, n, a.terms, a.n_terms, tid, T, ff, gg, fg, fg_sph, ffg, ggf);
+                else poly_recent_blocked<CT, uint32_t>(F, Gt, n, a.terms, a.n_terms, tid, T, ff, gg, fg, fg_sph, ffg, ggf);
             } else
             for (uint32_t A = top + warp; A < full; A += NW) {
                 const uint32_t rest = full ^ A;

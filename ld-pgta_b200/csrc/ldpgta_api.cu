@@ -183,8 +183,9 @@ int ldpgta_destroy(ldpgta_ctx *c)
         if (c->read_popc[g]) cudaFree(c->read_popc[g]);
         if (c->norm[g]) cudaFree(c->norm[g]);
     }
-    for (int h = 0; h < 12; ++h)
+    for (int h = 0; h < 14; ++h)
         if (c->hi_terms[h]) cudaFree(c->hi_terms[h]);
+    if (c->table_scratch) cudaFree(c->table_scratch);
     if (c->allele_complement) cudaFree(c->allele_complement);
     if (c->d_buf) cudaFree(c->d_buf);
     if (c->h_pin) cudaFreeHost(c->h_pin);

@@ -59,7 +59,7 @@ __device__ __forceinline__ u64 dot16(const uint32_t *X, const ACC *conv)
 // returns per-thread partials: two, two_sph (u64) and three (u64; the caller sums them in 128 bits)
 template <typename CT, typename ACC>
 __device__ void poly_homog_blocked(const CT *F, int n, const u64 *terms, int64_t n_terms, int tid, int T,
-                                                   u64 &two, u64 &two_sph, u64 &three)
+                                                   u64 &two, u64 &two_sph, u128 &three)
 {
     const int h = n - 5;
     const uint32_t top_row = 1u << h, usub = (1u << (n - 1)) - 1u, top = 1u << (n - 1);
@@ -93,11 +93,11 @@ __device__ void poly_homog_blocked(const CT *F, int n, const u64 *terms, int64_t
 // ---- recent admixture: F = group 0, G = group 1 ------------------------------------------------
 template <typename CT, typename ACC>
 __device__ void poly_recent_blocked(const CT *F, const CT *G, int n, const u64 *terms, int64_t n_terms, int tid,
-                                                    int T, u64 &ff, u64 &gg, u64 &fg, u64 &fg_sph, u64 &ffg, u64 &ggf)
+                                                    int T, u64 &ff, u64 &gg, u64 &fg, u64 &fg_sph, u128 &ffg, u128 &ggf)
 {
     const int h = n - 5;
     const uint32_t top_row = 1u << h, usub = (1u << (n - 1)) - 1u, top = 1u << (n - 1);
-    ff = gg = fg = fg_sph = ffg = ggf = 0;
+    ff = gg = fg = fg_sph = 0; ffg = 0; ggf = 0;
     for (uint32_t a = tid; a < usub; a += T) {
         const uint32_t A = top | a, R = usub ^ a;
         const u64 fa = F[A], ga = G[A], fr = F[R], gr = G[R];
@@ -176,10 +176,10 @@ __device__ void poly_distant_blocked(const CT *ftab, const PanelView &pv, int n,
 
 
 #define LDPGTA_INST(CT)                                                                                              \
-    template __device__ void poly_homog_blocked<CT, uint32_t>(const CT *, int, const u64 *, int64_t, int, int, u64 &, u64 &, u64 &); \
-    template __device__ void poly_homog_blocked<CT, u64>(const CT *, int, const u64 *, int64_t, int, int, u64 &, u64 &, u64 &);      \
-    template __device__ void poly_recent_blocked<CT, uint32_t>(const CT *, const CT *, int, const u64 *, int64_t, int, int, u64 &, u64 &, u64 &, u64 &, u64 &, u64 &); \
-    template __device__ void poly_recent_blocked<CT, u64>(const CT *, const CT *, int, const u64 *, int64_t, int, int, u64 &, u64 &, u64 &, u64 &, u64 &, u64 &);      \
+    template __device__ void poly_homog_blocked<CT, uint32_t>(const CT *, int, const u64 *, int64_t, int, int, u64 &, u64 &, u128 &); \
+    template __device__ void poly_homog_blocked<CT, u64>(const CT *, int, const u64 *, int64_t, int, int, u64 &, u64 &, u128 &);      \
+    template __device__ void poly_recent_blocked<CT, uint32_t>(const CT *, const CT *, int, const u64 *, int64_t, int, int, u64 &, u64 &, u64 &, u64 &, u128 &, u128 &); \
+    template __device__ void poly_recent_blocked<CT, u64>(const CT *, const CT *, int, const u64 *, int64_t, int, int, u64 &, u64 &, u64 &, u64 &, u128 &, u128 &);      \
     template __device__ void poly_distant_blocked<CT>(const CT *, const PanelView &, int, const u64 *, int64_t, int, int, double &, double &, double &);
 LDPGTA_INST(uint16_t)
 LDPGTA_INST(uint32_t)

@@ -21,14 +21,14 @@
 
 namespace ldpgta {
 
-// per-thread partials: two, two_sph and three (the caller sums them across the block in 128 bits);
+// per-thread partials: two, two_sph (64-bit) and three (128-bit); the caller sums them across the block;
 // ACC = uint32_t when 16 * N^2 < 2^32 (every group has at most 16383 haplotypes), else u64
 template <typename CT, typename ACC>
 __device__ void poly_homog_blocked(const CT *F, int n, const u64 *terms, int64_t n_terms, int tid, int T,
-                                   u64 &two, u64 &two_sph, u64 &three);
+                                   u64 &two, u64 &two_sph, u128 &three);
 template <typename CT, typename ACC>
 __device__ void poly_recent_blocked(const CT *F, const CT *G, int n, const u64 *terms, int64_t n_terms, int tid, int T,
-                                    u64 &ff, u64 &gg, u64 &fg, u64 &fg_sph, u64 &ffg, u64 &ggf);
+                                    u64 &ff, u64 &gg, u64 &fg, u64 &fg_sph, u128 &ffg, u128 &ggf);
 template <typename CT>
 __device__ void poly_distant_blocked(const CT *ftab, const PanelView &pv, int n, const u64 *terms, int64_t n_terms,
                                      int tid, int T, double &two, double &two_sph, double &three);

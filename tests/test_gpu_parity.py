@@ -142,8 +142,8 @@ def test_homogeneous_all_draw_sizes(n_hap):
     rows = ld_rows(rng, 96, n_hap)
     with L.Engine([n_hap]) as eng:
         eng.upload_read_masks(0, rows)
-        for n in range(2, 17):
-            nd = 40 if n <= 8 else (6 if n <= 13 else 2)
+        for n in range(2, 19):
+            nd = 40 if n <= 8 else (6 if n <= 13 else (2 if n <= 16 else 1))
             idx, off = uniform_draws(rng, 96, n, nd)
             got = eng.likelihoods_batch(L.HOMOGENEOUS, idx, off)
             want = C.batch([rows], [n_hap], idx, off, 0)
@@ -178,8 +178,8 @@ def test_recent_and_distant_admixture(sizes):
     with L.Engine(list(sizes)) as eng:
         for g in range(2):
             eng.upload_read_masks(g, rows[g])
-        for n in list(range(2, 13)) + [14]:
-            nd = 24 if n <= 8 else 3
+        for n in list(range(2, 13)) + [14, 16]:
+            nd = 24 if n <= 8 else (3 if n <= 14 else 1)
             idx, off = uniform_draws(rng, 80, n, nd)
             got = eng.likelihoods_batch(L.RECENT_ADMIXTURE, idx, off)
             want = C.batch(_common_width(rows), list(sizes), idx, off, 1)
@@ -272,7 +272,7 @@ def test_error_behaviour():
         with pytest.raises(L.LdpgtaError, match='outside'):
             eng.likelihoods_batch(L.HOMOGENEOUS, [0, 30], [0, 2])
         with pytest.raises(L.LdpgtaError, match='supported range'):
-            eng.likelihoods_batch(L.HOMOGENEOUS, list(range(17)), [0, 17])
+            eng.likelihoods_batch(L.HOMOGENEOUS, list(range(19)), [0, 19])
         with pytest.raises(L.LdpgtaError, match='two'):
             eng.likelihoods_batch(L.RECENT_ADMIXTURE, [0, 1], [0, 2])
         assert eng.likelihoods_batch(L.HOMOGENEOUS, [], [0]).shape == (0, 4)
@@ -288,7 +288,7 @@ def test_error_behaviour():
         assert max_rel(eng.likelihoods_batch(L.HOMOGENEOUS, idx, off), C.batch([big], [70000], idx, off, 0)) < LIK_TOL
         idx, off = uniform_draws(rng, 20, 4, 4)
         assert max_rel(eng.likelihoods_batch(L.HOMOGENEOUS, idx, off), C.batch([big], [70000], idx, off, 0)) < LIK_TOL
-        with pytest.raises(L.LdpgtaError, match='65535'):
+        with pytest.raises(L.LdpgtaError, match='shared memory'):            # 15 rows of 70000 bits do not fit one SM
             eng.likelihoods_batch(L.HOMOGENEOUS, list(range(15)), [0, 15])
 
 
