@@ -29,7 +29,7 @@ static int plan_general(const ldpgta_ctx *c, int n, GeneralPlan *p)
     const size_t ct = p->u16 ? 2 : 4;
     p->table_bytes = entries * ct;
     p->global_table = p->table_bytes > 128 * 1024;
-    const size_t fixed = 128 + (size_t)n * wsum * 8 + (p->global_table ? 0 : p->table_bytes) + 64 + 16 + 32 * 12 * 8;
+    const size_t fixed = 128 + (size_t)n * wsum * 8 + (p->global_table ? 0 : p->table_bytes) + 64 + 16 + 16 * 12 * 8;
     const size_t per_word = ((size_t)8 << p->kl) + ((size_t)8 << p->kh);
     size_t budget_kb = (size_t)BUDGET_KB[n];
     if (const char *e = getenv("LDPGTA_PLAN_KB")) budget_kb = (size_t)atoi(e);

@@ -58,7 +58,7 @@ __host__ __device__ inline GeneralSmem general_smem_layout(const PanelView &pv, 
     off = (off + 63) & ~63;                              // table rows are read with 128-bit loads
     s.ftab = off; if (table_in_smem) off += (int)(sizeof(CT) * pv.G) << n;
     off = (off + 15) & ~15;
-    s.red = off; off += 32 * 12 * 8;
+    s.red = off; off += 16 * 12 * 8;
     s.total = off;
     return s;
 }
@@ -166,19 +166,29 @@ __global__ void __launch_bounds__(512, 1) k_general(const GeneralArgs a)
                 CT *F = ftab + ((size_t)g << n);
                 for (int w0 = 0; w0 < wp; w0 += a.wc) {
                     const int cw = min(a.wc, wp - w0);
-                    if (w0) __syncthreads();                 // tables of the previous chunk consumed
-                    for (int e = tid; e < (cw << kl); e += T) {
-                        const int w = e >> kl, id = e & (LS - 1);
-                        u64 v = ~0ull;
-                        for (int i = 0; i < kl; ++i)
-                            if ((id >> i) & 1) v &= M[i * wp + w0 + w];
-                        ltab[e] = v;
+                    if (w0 || g) __syncthreads();            // tables of the previous chunk (or previous group) consumed
+                    // branch-free: read i is ANDed in through (mask | keep_i) with keep_i = all ones when i is not in the subset
+                    constexpr int KL = TL == 1 ? 5 : 7;          // compile-time low split for 5 or more reads
+                    if (kl == KL) {
+                        for (int e = tid; e < (cw << KL); e += T) {
+                            const int w = e >> KL, id = e & ((1 << KL) - 1);
+                            u64 v = ~0ull;
+#pragma unroll
+                            for (int i = 0; i < KL; ++i) v &= M[i * wp + w0 + w] | (((id >> i) & 1) ? 0ull : ~0ull);
+                            ltab[e] = v;
+                        }
+                    } else {
+                        for (int e = tid; e < (cw << kl); e += T) {
+                            const int w = e >> kl, id = e & (LS - 1);
+                            u64 v = ~0ull;
+                            for (int i = 0; i < kl; ++i) v &= M[i * wp + w0 + w] | (((id >> i) & 1) ? 0ull : ~0ull);
+                            ltab[e] = v;
+                        }
                     }
                     for (int e = tid; e < (cw << kh); e += T) {
                         const int w = e >> kh, id = e & (HS - 1);
                         u64 v = ~0ull;
-                        for (int i = 0; i < kh; ++i)
-                            if ((id >> i) & 1) v &= M[(kl + i) * wp + w0 + w];
+                        for (int i = 0; i < kh; ++i) v &= M[(kl + i) * wp + w0 + w] | (((id >> i) & 1) ? 0ull : ~0ull);
                         htab[e] = v;
                     }
                     __syncthreads();
