@@ -429,3 +429,22 @@ def test_read_scores_on_device_match_reference(name, golden_inputs):
         assert list(obs.score) == list(out['score'])
     finally:
         model.close()
+
+
+def test_repeatability_stress_multi_group():
+    """ Races show up as run-to-run differences: many CTAs per SM, two groups, chunked tables; every batch is
+    evaluated three times and must be bit-identical, and a slice is checked against the oracle. """
+    rng = np.random.default_rng(77)
+    sizes = (2504, 2504)
+    rows = [ld_rows(rng, 300, s) for s in sizes]
+    with L.Engine(list(sizes)) as eng:
+        for g in range(2):
+            eng.upload_read_masks(g, rows[g])
+        for kind, prop, ck in ((L.RECENT_ADMIXTURE, None, 1), (L.DISTANT_ADMIXTURE, [0.3, 0.7], 2)):
+            for n, nd in ((4, 5000), (6, 3000), (9, 1500), (12, 600), (14, 300)):
+                idx, off = uniform_draws(rng, 300, n, nd)
+                runs = [eng.likelihoods_batch(kind, idx, off, proportions=prop) for _ in range(3)]
+                assert np.array_equal(runs[0], runs[1]) and np.array_equal(runs[0], runs[2]), (kind, n)
+                k = 12 if n <= 9 else 3
+                want = C.batch(_common_width(rows), list(sizes), idx[:k * n], off[:k + 1], ck, prop)
+                assert max_rel(runs[0][:k], want) < LIK_TOL, (kind, n)
