@@ -448,3 +448,55 @@ def test_repeatability_stress_multi_group():
                 k = 12 if n <= 9 else 3
                 want = C.batch(_common_width(rows), list(sizes), idx[:k * n], off[:k + 1], ck, prop)
                 assert max_rel(runs[0][:k], want) < LIK_TOL, (kind, n)
+
+
+def test_aneuploidy_test_files_roundtrip(tmp_path, golden_inputs):
+    """ The driver's file boundary (ANEUPLOIDY_TEST.py:368-429): OBS/LEG/HAP pickles in (plain, gz, bz2), the
+    two-pickle *.LLR.p out, `info` keys, and likelihoods_tuple records that unpickle under the reference's
+    module names. """
+    import bz2, gzip, pickle, subprocess, sys
+    from conftest import ROOT
+    args, out = chrom_case('homog_m4', golden_inputs)
+    cfg = args['cfg']
+    d = tmp_path
+    with open(d / 'sample.chr21.obs.p', 'wb') as f:
+        pickle.dump(args['obs_tab'], f); pickle.dump({'chr_id': 'chr21', 'depth': 0.45}, f)
+    with gzip.open(d / 'panel.legend.gz', 'wb') as f:
+        pickle.dump(args['leg_tab'], f)
+    with bz2.open(d / 'panel.hap.bz2', 'wb') as f:
+        pickle.dump(args['hap_tab'], f); pickle.dump(args['number_of_haplotypes'], f)
+    code = r'''
+import sys, pickle, json
+sys.path.insert(0, %r)                       # flat drop-in: the directory with the reference's module names
+from ANEUPLOIDY_TEST import aneuploidy_test
+lik, info = aneuploidy_test(%r, %r, %r, {'G0'}, %d, %d, %d, %d, %d, %d, %r, '', 'gz', seed=2021, output_dir=%r)
+print(json.dumps({'windows': len(lik), 'keys': sorted(info), 'stat_keys': sorted(info['statistics'])}))
+''' % (str(ROOT) + '/ld-pgta_b200', str(d / 'sample.chr21.obs.p'), str(d / 'panel.legend.gz'), str(d / 'panel.hap.bz2'),
+       cfg['window_size'], cfg['subsamples'], cfg['offset'], cfg['min_reads'], cfg['max_reads'], cfg['min_score'],
+       cfg['min_HF'], str(d / 'results'))
+    res = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300, cwd=str(d),
+                         env=dict(__import__('os').environ, PYTHONHASHSEED='0'))
+    assert res.returncode == 0, res.stderr[-2000:]
+    import json
+    got = json.loads(res.stdout.strip().splitlines()[-1])
+    assert got['windows'] == len(out['likelihoods'])
+    for k in ('ancestral_makeup', 'window_size', 'subsamples', 'offset', 'min_reads', 'max_reads', 'min_score', 'min_HF',
+              'statistics', 'chr_id', 'depth'):
+        assert k in got['keys']
+    for k in ('matched_alleles', 'runtime', 'num_of_windows', 'LLRs_per_chromosome', 'LLRs_per_genomic_window',
+              'reads_mean', 'window_size_mean'):
+        assert k in got['stat_keys']
+    path = d / 'results' / 'sample.chr21.LLR.p.gz'
+    assert path.exists()
+    raw = gzip.open(path, 'rb').read()
+    assert b'HOMOGENOUES_MODELS' in raw and b'ldpgta' not in raw          # records carry the reference's module name
+    sys.path.insert(0, str(ROOT) + '/ld-pgta_b200')
+    with gzip.open(path, 'rb') as f:
+        lik = pickle.load(f); info = pickle.load(f)
+    assert list(lik) == list(out['likelihoods'])
+    # same seed and hash seed as the golden run: the draws and therefore the likelihoods are the reference's
+    worst = max(max_rel(a, b) for w in lik for a, b in zip(lik[w], out['likelihoods'][w]))
+    assert worst < LIK_TOL
+    ref = out['statistics']['LLRs_per_chromosome'][('BPH', 'SPH')]
+    mine = info['statistics']['LLRs_per_chromosome'][('BPH', 'SPH')]
+    assert abs(mine['mean_of_mean'] - ref['mean_of_mean']) < STAT_TOL and abs(mine['std_of_mean'] - ref['std_of_mean']) < STAT_TOL
