@@ -167,9 +167,22 @@ __global__ void __launch_bounds__(512, 1) k_general(const GeneralArgs a)
                 for (int w0 = 0; w0 < wp; w0 += a.wc) {
                     const int cw = min(a.wc, wp - w0);
                     if (w0 || g) __syncthreads();            // tables of the previous chunk (or previous group) consumed
-                    // branch-free: read i is ANDed in through (mask | keep_i) with keep_i = all ones when i is not in the subset
+                    // branch-free: read i is ANDed in through (mask | keep_i) with keep_i = all ones when i is not in the subset.
+                    // When the block is at least as wide as a table, a thread always builds the same subset id, so its
+                    // keep masks are loop invariants.
                     constexpr int KL = TL == 1 ? 5 : 7;          // compile-time low split for 5 or more reads
-                    if (kl == KL) {
+                    if (kl == KL && T >= (1 << KL)) {
+                        const int id = tid & ((1 << KL) - 1);
+                        u64 keep[KL];
+#pragma unroll
+                        for (int i = 0; i < KL; ++i) keep[i] = ((id >> i) & 1) ? 0ull : ~0ull;
+                        for (int w = tid >> KL; w < cw; w += T >> KL) {
+                            u64 v = ~0ull;
+#pragma unroll
+                            for (int i = 0; i < KL; ++i) v &= M[i * wp + w0 + w] | keep[i];
+                            ltab[(w << KL) + id] = v;
+                        }
+                    } else if (kl == KL) {
                         for (int e = tid; e < (cw << KL); e += T) {
                             const int w = e >> KL, id = e & ((1 << KL) - 1);
                             u64 v = ~0ull;
