@@ -70,6 +70,19 @@ int ldpgta_row_words(const ldpgta_ctx *ctx, int group);
 int ldpgta_upload_allele_rows(ldpgta_ctx *ctx, int group, const uint64_t *rows, int64_t n_rows,
                               const uint8_t *complement);
 
+/* A reference panel resident on the device, shared by any number of contexts (samples) on that device:
+ * the HAP table of MAKE_REF_PANEL (one row per legend SNP and group, MAKE_REF_PANEL.py:352-368) packed once.
+ * ldpgta_gather_allele_rows then performs build_hap_dict's lookup (HOMOGENOUES_MODELS.py:84-94) as a device
+ * gather: allele row a of every group = panel row legend_idx[a], complemented inside N bits when
+ * complement[a] != 0 (the observed base is the REF allele).  Equivalent to ldpgta_upload_allele_rows without
+ * re-packing and re-uploading panel rows for every sample. */
+typedef struct ldpgta_panel ldpgta_panel;
+int ldpgta_panel_create(int device, int n_groups, const uint32_t *n_hap, int64_t n_snps, ldpgta_panel **out);
+int ldpgta_panel_upload(ldpgta_panel *panel, int group, int64_t first_snp, const uint64_t *rows, int64_t n_rows);
+int ldpgta_panel_destroy(ldpgta_panel *panel);
+int ldpgta_gather_allele_rows(ldpgta_ctx *ctx, const ldpgta_panel *panel, const int64_t *legend_idx,
+                              const uint8_t *complement, int64_t n_alleles);
+
 /* build_intrenal_hap_dict (HOMOGENOUES_MODELS.py:102-127) hoisted out of the draw loop:
  * mask of read r = AND of the allele rows allele_idx[read_offsets[r] .. read_offsets[r+1]),
  * computed on device for every group.  Replaces any earlier read masks. */

@@ -10,11 +10,11 @@ directory on sys.path makes `from ANEUPLOIDY_TEST import aneuploidy_test`
 resolve to the GPU implementation.
 """
 from ._native import (DISTANT_ADMIXTURE, HOMOGENEOUS, RECENT_ADMIXTURE, LdpgtaError, LIB_PATH, PinnedArray, load)
-from .engine import LLR_PAIRS, Engine, finish_chromosome, pack_ints
+from .engine import LLR_PAIRS, Engine, ResidentPanel, finish_chromosome, pack_ints
 from .models import ImplicitModels, distant_admixture, homogeneous, likelihoods_tuple, recent_admixture
 from .driver import (aneuploidy_test, bootstrap, build_gw_dict, effective_number_of_subsamples, evaluate_draws,
                      pick_reads, plan_draws, statistics, supporting_dictionaries)
 
 __all__ = ['Engine', 'homogeneous', 'recent_admixture', 'distant_admixture', 'bootstrap', 'aneuploidy_test',
            'statistics', 'likelihoods_tuple', 'ImplicitModels', 'LdpgtaError', 'pack_ints', 'finish_chromosome',
-           'HOMOGENEOUS', 'RECENT_ADMIXTURE', 'DISTANT_ADMIXTURE', 'LLR_PAIRS', 'load', 'LIB_PATH', 'PinnedArray']
+           'ResidentPanel', 'HOMOGENEOUS', 'RECENT_ADMIXTURE', 'DISTANT_ADMIXTURE', 'LLR_PAIRS', 'load', 'LIB_PATH', 'PinnedArray']

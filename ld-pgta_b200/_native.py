@@ -25,6 +25,10 @@ SYMBOLS = (
     ('ldpgta_destroy', _c.c_int, [_P]),
     ('ldpgta_row_words', _c.c_int, [_P, _c.c_int]),
     ('ldpgta_upload_allele_rows', _c.c_int, [_P, _c.c_int, _P, _c.c_int64, _P]),
+    ('ldpgta_panel_create', _c.c_int, [_c.c_int, _c.c_int, _P, _c.c_int64, _c.POINTER(_P)]),
+    ('ldpgta_panel_upload', _c.c_int, [_P, _c.c_int, _c.c_int64, _P, _c.c_int64]),
+    ('ldpgta_panel_destroy', _c.c_int, [_P]),
+    ('ldpgta_gather_allele_rows', _c.c_int, [_P, _P, _P, _P, _c.c_int64]),
     ('ldpgta_build_read_masks', _c.c_int, [_P, _P, _P, _c.c_int64]),
     ('ldpgta_read_scores', _c.c_int, [_P, _P, _P, _c.c_int64, _P, _c.c_double, _c.c_double, _P]),
     ('ldpgta_upload_read_masks', _c.c_int, [_P, _c.c_int, _P, _c.c_int64]),

@@ -25,6 +25,26 @@ __global__ void k_pack_rows(const uint64_t *__restrict__ src, const uint8_t *__r
     }
 }
 
+// allele row a = panel row legend_idx[a], complemented inside the group's N bits for REF alleles
+// (build_hap_dict, HOMOGENOUES_MODELS.py:84-94, as a gather from the resident panel)
+__global__ void k_gather_rows(const uint64_t *__restrict__ panel, const int64_t *__restrict__ legend_idx,
+                              const uint8_t *__restrict__ complement, uint64_t *__restrict__ dst, int64_t n_alleles, int wp,
+                              uint32_t nhap)
+{
+    const int64_t total = n_alleles * wp;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t a = e / wp;
+        const int w = (int)(e - a * wp);
+        u64 v = panel[legend_idx[a] * wp + w];
+        if (complement && complement[a]) {
+            const int bits = (int)nhap - 64 * w;
+            const u64 valid = bits >= 64 ? ~0ull : (bits > 0 ? ((1ull << bits) - 1ull) : 0ull);
+            v = ~v & valid;
+        }
+        dst[e] = v;
+    }
+}
+
 // mask[r] = AND of allele rows allele_idx[off[r] .. off[r+1])  (build_intrenal_hap_dict,
 // HOMOGENOUES_MODELS.py:112-123, once per read instead of once per draw)
 __global__ void k_build_read_masks(const uint64_t *__restrict__ rows, const int32_t *__restrict__ allele_idx,

@@ -262,6 +262,110 @@ int ldpgta_upload_allele_rows(ldpgta_ctx *c, int group, const uint64_t *rows, in
     return 0;
 }
 
+struct ldpgta_panel {
+    int device = 0, G = 0;
+    uint32_t nhap[MAXG] = {};
+    int words[MAXG] = {}, wp[MAXG] = {};
+    int64_t n_snps = 0;
+    uint64_t *rows[MAXG] = {};
+};
+
+int ldpgta_panel_create(int device, int n_groups, const uint32_t *n_hap, int64_t n_snps, ldpgta_panel **out)
+{
+    if (!out || !n_hap || n_snps < 0) return fail(LDPGTA_E_INVALID, "bad arguments");
+    if (n_groups < 1 || n_groups > MAXG) return fail(LDPGTA_E_INVALID, "n_groups must be 1..%d, got %d", MAXG, n_groups);
+    const int ndev = ldpgta_device_count();
+    if (ndev < 1) return fail(LDPGTA_E_CUDA, "no CUDA device is visible: the likelihood engine has no CPU path");
+    if (device < 0 || device >= ndev) return fail(LDPGTA_E_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
+    LDPGTA_CUDA(cudaSetDevice(device));
+    ldpgta_panel *p = new ldpgta_panel();
+    p->device = device; p->G = n_groups; p->n_snps = n_snps;
+    for (int g = 0; g < n_groups; ++g) {
+        if (n_hap[g] == 0) { delete p; return fail(LDPGTA_E_INVALID, "group %d has no haplotypes", g); }
+        p->nhap[g] = n_hap[g];
+        p->words[g] = (int)((n_hap[g] + 63u) / 64u);
+        p->wp[g] = (p->words[g] + 1) & ~1;
+        LDPGTA_CUDA(cudaMalloc((void **)&p->rows[g], std::max<size_t>((size_t)n_snps * p->wp[g] * 8, 16)));
+    }
+    *out = p;
+    return 0;
+}
+
+int ldpgta_panel_upload(ldpgta_panel *p, int group, int64_t first_snp, const uint64_t *rows, int64_t n_rows)
+{
+    if (!p || group < 0 || group >= p->G || n_rows < 0 || (n_rows > 0 && !rows)) return fail(LDPGTA_E_INVALID, "bad arguments");
+    if (first_snp < 0 || first_snp + n_rows > p->n_snps) return fail(LDPGTA_E_INVALID, "SNP range %lld..%lld is outside the panel", (long long)first_snp, (long long)(first_snp + n_rows));
+    if (n_rows == 0) return 0;
+    LDPGTA_CUDA(cudaSetDevice(p->device));
+    uint64_t *tmp = nullptr;
+    const size_t src_bytes = (size_t)n_rows * p->words[group] * 8;
+    LDPGTA_CUDA(cudaMalloc((void **)&tmp, src_bytes));
+    cudaError_t e = cudaMemcpy(tmp, rows, src_bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        const int64_t total = n_rows * p->wp[group];
+        const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, 148 * 16);
+        k_pack_rows<<<blocks, 256>>>(tmp, nullptr, p->rows[group] + first_snp * p->wp[group], n_rows, p->words[group], p->wp[group],
+                                     p->nhap[group]);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    }
+    cudaFree(tmp);
+    if (e != cudaSuccess) return fail(LDPGTA_E_CUDA, "panel upload failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int ldpgta_panel_destroy(ldpgta_panel *p)
+{
+    if (!p) return 0;
+    cudaSetDevice(p->device);
+    for (int g = 0; g < p->G; ++g)
+        if (p->rows[g]) cudaFree(p->rows[g]);
+    delete p;
+    return 0;
+}
+
+int ldpgta_gather_allele_rows(ldpgta_ctx *c, const ldpgta_panel *p, const int64_t *legend_idx, const uint8_t *complement,
+                              int64_t n_alleles)
+{
+    if (!c || !p || n_alleles < 0 || (n_alleles > 0 && !legend_idx)) return fail(LDPGTA_E_INVALID, "bad arguments");
+    if (p->device != c->device || p->G != c->G) return fail(LDPGTA_E_INVALID, "panel and context differ in device or number of groups");
+    for (int g = 0; g < c->G; ++g)
+        if (p->nhap[g] != c->nhap[g]) return fail(LDPGTA_E_INVALID, "panel group %d has %u haplotypes, context expects %u", g, p->nhap[g], c->nhap[g]);
+    for (int64_t a = 0; a < n_alleles; ++a)
+        if (legend_idx[a] < 0 || legend_idx[a] >= p->n_snps)
+            return fail(LDPGTA_E_INVALID, "legend index %lld at %lld is outside 0..%lld", (long long)legend_idx[a], (long long)a, (long long)p->n_snps - 1);
+    LDPGTA_CUDA(cudaSetDevice(c->device));
+    const size_t idx_b = ((size_t)n_alleles * 8 + 15) & ~(size_t)15;
+    if (int rc = ensure_dev(c, idx_b + (size_t)n_alleles + 16)) return rc;
+    int64_t *d_idx = (int64_t *)c->d_buf;
+    uint8_t *d_comp = (uint8_t *)c->d_buf + idx_b;
+    if (n_alleles) {
+        LDPGTA_CUDA(cudaMemcpyAsync(d_idx, legend_idx, (size_t)n_alleles * 8, cudaMemcpyHostToDevice, c->stream));
+        if (complement) LDPGTA_CUDA(cudaMemcpyAsync(d_comp, complement, (size_t)n_alleles, cudaMemcpyHostToDevice, c->stream));
+    }
+    for (int g = 0; g < c->G; ++g) {
+        if (c->allele_rows[g]) { LDPGTA_CUDA(cudaFree(c->allele_rows[g])); c->allele_rows[g] = nullptr; }
+        LDPGTA_CUDA(cudaMalloc((void **)&c->allele_rows[g], std::max<size_t>((size_t)n_alleles * c->wp[g] * 8, 16)));
+        if (n_alleles) {
+            const int64_t total = n_alleles * c->wp[g];
+            const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)c->sm_count * 16);
+            k_gather_rows<<<blocks, 256, 0, c->stream>>>(p->rows[g], d_idx, complement ? d_comp : nullptr, c->allele_rows[g], n_alleles,
+                                                         c->wp[g], c->nhap[g]);
+            c->launches++;
+            LDPGTA_CUDA(cudaGetLastError());
+        }
+        c->n_alleles[g] = n_alleles;
+    }
+    if (c->allele_complement) { LDPGTA_CUDA(cudaFree(c->allele_complement)); c->allele_complement = nullptr; }
+    LDPGTA_CUDA(cudaMalloc((void **)&c->allele_complement, std::max<size_t>((size_t)n_alleles, 16)));
+    if (n_alleles) {
+        if (complement) LDPGTA_CUDA(cudaMemcpyAsync(c->allele_complement, d_comp, (size_t)n_alleles, cudaMemcpyDeviceToDevice, c->stream));
+        else LDPGTA_CUDA(cudaMemsetAsync(c->allele_complement, 0, (size_t)n_alleles, c->stream));
+    }
+    LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 int ldpgta_upload_read_masks(ldpgta_ctx *c, int group, const uint64_t *rows, int64_t n_rows)
 {
     if (!c || group < 0 || group >= c->G) return fail(LDPGTA_E_INVALID, "bad context or group");

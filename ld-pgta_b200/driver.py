@@ -221,14 +221,14 @@ def effective_number_of_subsamples(num_of_reads, min_reads, max_reads, subsample
     return 0
 
 
-def make_examiner(obs_tab, leg_tab, hap_tab, number_of_haplotypes, ancestral_makeup, models_dict, device=0):
+def make_examiner(obs_tab, leg_tab, hap_tab, number_of_haplotypes, ancestral_makeup, models_dict, device=0, panel=None):
     """ Model selection of ANEUPLOIDY_TEST.py:263-273. """
     if type(ancestral_makeup) == set and len(ancestral_makeup) == 1:
         print('Assuming one ancestral population: %s.' % next(iter(ancestral_makeup)))
-        return homogeneous(obs_tab, leg_tab, hap_tab, number_of_haplotypes, models_dict, device=device)
+        return homogeneous(obs_tab, leg_tab, hap_tab, number_of_haplotypes, models_dict, device=device, panel=panel)
     if type(ancestral_makeup) == set and len(ancestral_makeup) == 2:
         print('Assuming recent-admixture between %s and %s.' % tuple(ancestral_makeup))
-        return recent_admixture(obs_tab, leg_tab, hap_tab, number_of_haplotypes, models_dict, device=device)
+        return recent_admixture(obs_tab, leg_tab, hap_tab, number_of_haplotypes, models_dict, device=device, panel=panel)
     if type(ancestral_makeup) == dict:
         print('Assuming the following ancestral makeup:', ", ".join("{:.1f}% {}".format(100 * v, k) for k, v in ancestral_makeup.items()))
         return distant_admixture(obs_tab, leg_tab, hap_tab, number_of_haplotypes, models_dict, ancestral_makeup, device=device)
@@ -288,9 +288,10 @@ def evaluate_draws(examine, reads_dict, draws):
 
 
 def bootstrap(obs_tab, leg_tab, hap_tab, number_of_haplotypes, ancestral_makeup, models_dict, window_size, subsamples,
-              offset, min_reads, max_reads, min_score, min_HF, replay=None, device=0):
-    """ ANEUPLOIDY_TEST.bootstrap (:250-287): (likelihoods, genomic_windows, fraction_of_matches). """
-    examine = make_examiner(obs_tab, leg_tab, hap_tab, number_of_haplotypes, ancestral_makeup, models_dict, device=device)
+              offset, min_reads, max_reads, min_score, min_HF, replay=None, device=0, panel=None):
+    """ ANEUPLOIDY_TEST.bootstrap (:250-287): (likelihoods, genomic_windows, fraction_of_matches).
+    `panel`: an engine.ResidentPanel of this chromosome shared by many samples (one or two populations). """
+    examine = make_examiner(obs_tab, leg_tab, hap_tab, number_of_haplotypes, ancestral_makeup, models_dict, device=device, panel=panel)
     try:
         obs = supporting_dictionaries(obs_tab, leg_tab, hap_tab, number_of_haplotypes, ancestral_makeup, min_HF, examine=examine)
         genomic_windows = build_gw_dict(obs, window_size, offset, min_reads, max_reads, min_score)

@@ -22,18 +22,53 @@ def pack_ints(ints, n_bits):
     in n_bits (TEST_MODULE.py:29-30 can emit 1 << N, which no panel contains). """
     W = (n_bits + 63) // 64
     nbytes = 8 * W
-    limit = 1 << n_bits
-    out = bytearray(len(ints) * nbytes)
-    for i, x in enumerate(ints):
-        if x < 0 or x >= limit:
-            raise ValueError('haplotype row %d does not fit in %d bits' % (i, n_bits))
-        out[i * nbytes:(i + 1) * nbytes] = x.to_bytes(nbytes, 'little')
-    return np.frombuffer(bytes(out), dtype='<u8').reshape(len(ints), W)
+    if len(ints) and (min(ints) < 0 or max(ints) >> n_bits):
+        bad = next(i for i, x in enumerate(ints) if x < 0 or x >> n_bits)
+        raise ValueError('haplotype row %d does not fit in %d bits' % (bad, n_bits))
+    return np.frombuffer(b''.join([x.to_bytes(nbytes, 'little') for x in ints]), dtype='<u8').reshape(len(ints), W)
 
 
 def unpack_row(row):
     """ uint64[W] -> Python int. """
     return int.from_bytes(np.ascontiguousarray(row, dtype='<u8').tobytes(), 'little')
+
+
+class ResidentPanel:
+    """ A reference panel kept on one GPU for any number of samples: the LEGEND/HAP tables of one
+    chromosome (MAKE_REF_PANEL.py:352-368) packed and uploaded once.  Model objects built with
+    `panel=` gather their allele rows from it on the device instead of re-packing panel rows
+    (build_hap_dict, HOMOGENOUES_MODELS.py:76-100). """
+
+    def __init__(self, leg_tab, hap_tab_per_group, number_of_haplotypes_per_group, device=0, chunk=65536):
+        self.lib = N.load()
+        self.groups = list(hap_tab_per_group)
+        self.n_hap = [int(number_of_haplotypes_per_group[g]) for g in self.groups]
+        self.device = device
+        self.n_snps = len(leg_tab)
+        for g in self.groups:
+            if len(hap_tab_per_group[g]) != self.n_snps:
+                raise Exception('Error: the number of SNPs in the LEGEND file differ from the number of SNPs in the HAP file.')
+        # position -> (ref, alt, legend row); a later duplicate position wins, as in the reference's dict
+        self.by_pos = {leg[1]: (leg[2], leg[3], i) for i, leg in enumerate(leg_tab)}
+        nh = np.asarray(self.n_hap, dtype=np.uint32)
+        self._p = ctypes.c_void_p()
+        N.check(self.lib.ldpgta_panel_create(device, len(self.groups), N.ptr(nh), self.n_snps, ctypes.byref(self._p)))
+        for gi, g in enumerate(self.groups):
+            tab = hap_tab_per_group[g]
+            for lo in range(0, self.n_snps, chunk):
+                rows = pack_ints(tab[lo:lo + chunk], self.n_hap[gi])
+                N.check(self.lib.ldpgta_panel_upload(self._p, gi, lo, N.ptr(np.ascontiguousarray(rows)), rows.shape[0]))
+
+    def close(self):
+        if self._p is not None and self._p.value:
+            self.lib.ldpgta_panel_destroy(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Engine:
@@ -82,6 +117,13 @@ class Engine:
             raise ValueError('complement must have one flag per row')
         N.check(self.lib.ldpgta_upload_allele_rows(self._ctx, group, N.ptr(rows), rows.shape[0], N.ptr(comp)))
         self.n_alleles = rows.shape[0]
+
+    def gather_allele_rows(self, panel, legend_idx, complement=None):
+        """ Allele rows from a ResidentPanel: row a = panel row legend_idx[a] (complemented for REF alleles). """
+        idx = np.ascontiguousarray(legend_idx, dtype=np.int64)
+        comp = None if complement is None else np.ascontiguousarray(complement, dtype=np.uint8)
+        N.check(self.lib.ldpgta_gather_allele_rows(self._ctx, panel._p, N.ptr(idx), N.ptr(comp), len(idx)))
+        self.n_alleles = len(idx)
 
     def build_read_masks(self, allele_idx, read_offsets):
         idx = np.ascontiguousarray(allele_idx, dtype=np.int32)

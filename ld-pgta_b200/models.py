@@ -52,14 +52,19 @@ class _PanelModel:
     kind = None
     tuple_type = likelihoods_tuple
 
-    def _load_panel(self, obs_tab, leg_tab, hap_tab_per_group, number_of_haplotypes_per_group, device):
+    def _load_panel(self, obs_tab, leg_tab, hap_tab_per_group, number_of_haplotypes_per_group, device, panel=None):
         groups = list(hap_tab_per_group)
         self._groups = groups
         self._nhap = {g: number_of_haplotypes_per_group[g] for g in groups}
         # build_hap_dict (HOMOGENOUES_MODELS.py:76-100): legend lookup, last duplicate position wins (:84)
         # (only observed positions are indexed: the panel has ~20x more SNPs than a low-coverage sample touches)
-        wanted = {row[0] for row in obs_tab}
-        by_pos = {leg[1]: (leg[2], leg[3], i) for i, leg in enumerate(leg_tab) if leg[1] in wanted}
+        if panel is not None:
+            if panel.groups != groups or panel.n_hap != [self._nhap[g] for g in groups] or panel.n_snps != len(leg_tab):
+                raise ValueError('the resident panel does not match the LEGEND/HAP tables of this model')
+            by_pos = panel.by_pos
+        else:
+            wanted = {row[0] for row in obs_tab}
+            by_pos = {leg[1]: (leg[2], leg[3], i) for i, leg in enumerate(leg_tab) if leg[1] in wanted}
         self._allele_index = {}
         rows, comp = [], []
         mismatches = 0
@@ -84,9 +89,12 @@ class _PanelModel:
         self._hap_tabs = hap_tab_per_group
         self._hap_dicts = {}
         self._engine = Engine([self._nhap[g] for g in groups], device=device)
-        for gi, g in enumerate(groups):
-            hap_tab = hap_tab_per_group[g]
-            self._engine.upload_allele_rows(gi, pack_ints([hap_tab[i] for i in rows], self._nhap[g]), self._complement)
+        if panel is not None:
+            self._engine.gather_allele_rows(panel, rows, self._complement)          # device gather, no re-packing
+        else:
+            for gi, g in enumerate(groups):
+                hap_tab = hap_tab_per_group[g]
+                self._engine.upload_allele_rows(gi, pack_ints([hap_tab[i] for i in rows], self._nhap[g]), self._complement)
 
     def _hap_dict_of(self, group2):
         """ The reference's hap_dict as Python ints, materialised on first use. """
@@ -201,7 +209,7 @@ class homogeneous(_PanelModel):
     """ Single-population model; same constructor and checks as HOMOGENOUES_MODELS.py:52-73. """
     kind = N.HOMOGENEOUS
 
-    def __init__(self, obs_tab, leg_tab, hap_tab_per_group, number_of_haplotypes_per_group, models_dict, device=0):
+    def __init__(self, obs_tab, leg_tab, hap_tab_per_group, number_of_haplotypes_per_group, models_dict, device=0, panel=None):
         print('Initializing the algorithm for non-admixtures:')
         if len(hap_tab_per_group) != 1:
             raise Exception('Error: The non-admixed models can not be applied when the HAP file includes multiple superpopulations/group2.')
@@ -212,7 +220,7 @@ class homogeneous(_PanelModel):
         if len(leg_tab) != len(hap_tab):
             raise Exception('Error: the number of SNPs in the LEGEND file differ from the number of SNPs in the HAP file.')
         self._group2 = group2
-        self._load_panel(obs_tab, leg_tab, {group2: hap_tab}, {group2: self.number_of_haplotypes}, device)
+        self._load_panel(obs_tab, leg_tab, {group2: hap_tab}, {group2: self.number_of_haplotypes}, device, panel)
         print('%.2f%% of the observed alleles matched the reference panel.' % (100 * self.fraction_of_matches[group2]))
 
     @property
@@ -235,7 +243,7 @@ class recent_admixture(_PanelModel):
     """ Two populations, each parent from one of them (RECENT_ADMIXTURE_MODELS.py:54-80). """
     kind = N.RECENT_ADMIXTURE
 
-    def __init__(self, obs_tab, leg_tab, hap_tab_per_group, number_of_haplotypes_per_group, models_dict, device=0):
+    def __init__(self, obs_tab, leg_tab, hap_tab_per_group, number_of_haplotypes_per_group, models_dict, device=0, panel=None):
         print('Initializing the algorithm for recent admixtures:')
         if not all(len(leg_tab) == len(hap_tab) for hap_tab in hap_tab_per_group.values()):
             raise Exception('Error: the number of SNPs in the LEGEND file differ from the number of SNPs in the HAP file.')
@@ -244,7 +252,7 @@ class recent_admixture(_PanelModel):
         self.models_dict = models_dict
         self.group2_id = tuple(hap_tab_per_group.keys())
         self.number_of_haplotypes_per_group = number_of_haplotypes_per_group
-        self._load_panel(obs_tab, leg_tab, hap_tab_per_group, number_of_haplotypes_per_group, device)
+        self._load_panel(obs_tab, leg_tab, hap_tab_per_group, number_of_haplotypes_per_group, device, panel)
         for group2 in self.group2_id:
             print('%.2f%% of the observed alleles matched the reference panel of %s.' % (100 * self.fraction_of_matches[group2], group2))
 

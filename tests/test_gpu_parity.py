@@ -500,3 +500,37 @@ print(json.dumps({'windows': len(lik), 'keys': sorted(info), 'stat_keys': sorted
     ref = out['statistics']['LLRs_per_chromosome'][('BPH', 'SPH')]
     mine = info['statistics']['LLRs_per_chromosome'][('BPH', 'SPH')]
     assert abs(mine['mean_of_mean'] - ref['mean_of_mean']) < STAT_TOL and abs(mine['std_of_mean'] - ref['std_of_mean']) < STAT_TOL
+
+
+def test_resident_panel_gather_equals_host_packing(golden_testmodule, golden_inputs):
+    """ Next row f3: the panel stays on the device and build_hap_dict becomes a gather
+    (ldpgta_panel_* + ldpgta_gather_allele_rows); results are identical to packing on the host. """
+    g = golden_testmodule
+    obs, leg, hap, nh = g['obs_tab'], g['leg_tab'], g['hap_tab'], g['number_of_haplotypes']
+    panel1 = L.ResidentPanel(leg, {'group0': hap['group0']}, nh)
+    panel2 = L.ResidentPanel(leg, hap, nh)
+    a = L.homogeneous(obs, leg, {'group0': hap['group0']}, {'group0': nh['group0']}, L.ImplicitModels())
+    b = L.homogeneous(obs, leg, {'group0': hap['group0']}, {'group0': nh['group0']}, L.ImplicitModels(), panel=panel1)
+    c = L.recent_admixture(obs, leg, hap, nh, L.ImplicitModels())
+    d = L.recent_admixture(obs, leg, hap, nh, L.ImplicitModels(), panel=panel2)
+    for rec in g['records']:
+        al = rec['alleles']
+        assert a.joint_frequencies_combo(al, normalize=False) == b.joint_frequencies_combo(al, normalize=False)
+        assert tuple(a.get_likelihoods(al)) == tuple(b.get_likelihoods(al))
+        assert tuple(c.get_likelihoods(al)) == tuple(d.get_likelihoods(al))
+    for m in (a, b, c, d):
+        m.close()
+    # several samples share one resident panel through the driver
+    args, out = chrom_case('recent_m4', golden_inputs)
+    cfg = args['cfg']
+    shared = L.ResidentPanel(args['leg_tab'], args['hap_tab'], args['number_of_haplotypes'])
+    for _ in range(2):
+        lik, _, matches = L.bootstrap(args['obs_tab'], args['leg_tab'], args['hap_tab'], args['number_of_haplotypes'],
+                                      args['ancestral_makeup'], L.ImplicitModels(), cfg['window_size'], cfg['subsamples'],
+                                      cfg['offset'], cfg['min_reads'], cfg['max_reads'], cfg['min_score'], cfg['min_HF'],
+                                      replay=out['draws'], panel=shared)
+        assert matches == out['fraction_of_matches']
+        worst = max(max_rel(x, y) for w in lik for x, y in zip(lik[w], out['likelihoods'][w]))
+        assert worst < LIK_TOL
+    for p in (panel1, panel2, shared):
+        p.close()
