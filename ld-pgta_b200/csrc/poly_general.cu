@@ -70,8 +70,10 @@ __device__ void poly_homog_blocked(const CT *F, int n, const u64 *terms, int64_t
         two += prod;
         two_sph += prod * ((2ull << pa) + (1ull << (n - 1 - pa)));
     }
+    u64 t_next = tid < n_terms ? terms[tid] : 0;                 // the colouring list is read one iteration ahead
     for (int64_t e = tid; e < n_terms; e += T) {
-        const u64 t = terms[e];
+        const u64 t = t_next;
+        if (e + T < n_terms) t_next = terms[e + T];
         uint32_t X[16], Y[16], Z[16];
         ACC c[16];
         load_row16<CT>(F, top_row + (uint32_t)(t & 0xffffu), X);
@@ -124,8 +126,10 @@ __device__ void poly_recent_blocked(const CT *F, const CT *G, int n, const u64 *
         ffg += s_ffg;
         ggf += s_ggf;
     };
+    u64 t_next = tid < n_terms ? terms[tid] : 0;
     for (int64_t e = tid; e < n_terms; e += T) {
-        const u64 t = terms[e];
+        const u64 t = t_next;
+        if (e + T < n_terms) t_next = terms[e + T];
         triple((uint32_t)(t & 0xffffu), (uint32_t)(t >> 16) & 0xffffu, (uint32_t)(t >> 32) & 0xffffu, false);
     }
     if (tid == 0) triple(top_row - 1u, 0u, 0u, true);
