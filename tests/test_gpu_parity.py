@@ -136,6 +136,21 @@ def test_bootstrap_replay_matches_reference(name, golden_inputs):
 # C-ABI against the C oracle on seeded inputs
 # ----------------------------------------------------------------------------------------
 
+def test_every_small_kernel_tiling():
+    """ One panel size per (lanes per draw, words per lane) instance of k_small, plus the unpipelined kernel. """
+    rng = np.random.default_rng(4)
+    for n_hap in (900, 1500, 2504, 3000, 5008, 6000, 9000):
+        rows = ld_rows(rng, 64, n_hap)
+        with L.Engine([n_hap]) as eng:
+            eng.upload_read_masks(0, rows)
+            for n in (2, 3, 4):
+                idx, off = uniform_draws(rng, 64, n, 61)              # 61: ragged last tile
+                got = eng.likelihoods_batch(L.HOMOGENEOUS, idx, off)
+                want = C.batch([rows], [n_hap], idx, off, 0)
+                assert max_rel(got, want) < LIK_TOL, (n_hap, n)
+                assert np.array_equal(eng.joint_counts(idx[:n])[0], C.joint_counts(rows[idx[:n]]))
+
+
 @pytest.mark.parametrize('n_hap', [50, 64, 65, 331, 2504, 5008])
 def test_homogeneous_all_draw_sizes(n_hap):
     rng = np.random.default_rng(n_hap)
