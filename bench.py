@@ -423,7 +423,7 @@ def main():
 
     # ---- CPU baseline: oracle port on a bounded sample, one core; doubles as the parity check -------
     cpu_baseline, parity = None, None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:             # rank 0 at N=1 only
         spent, n_eval, w = 0.0, 0, 0
         ref_rows, got_rows = [], []
         starts = np.concatenate([[0], np.cumsum(reads)])

@@ -119,6 +119,23 @@ __device__ __forceinline__ LaneSplit lane_split(uint32_t rest, int lane)
     return s;
 }
 
+// NW consecutive 64-bit words from shared memory (16-byte aligned when NW is even): 128-bit loads
+template <int NW_>
+__device__ __forceinline__ void load_words(const u64 *p, u64 *v, bool in)
+{
+    if (NW_ % 2 == 0) {
+#pragma unroll
+        for (int q = 0; q < NW_ / 2; ++q) {
+            const ulonglong2 x = in ? reinterpret_cast<const ulonglong2 *>(p)[q] : make_ulonglong2(0ull, 0ull);
+            v[2 * q] = x.x;
+            v[2 * q + 1] = x.y;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < NW_; ++q) v[q] = in ? p[q] : 0ull;
+    }
+}
+
 template <int TH, int TL, typename CT>
 __global__ void __launch_bounds__(512, 1) k_general(const GeneralArgs a)
 {
@@ -215,30 +232,31 @@ __global__ void __launch_bounds__(512, 1) k_general(const GeneralArgs a)
                             for (int j = 0; j < TL; ++j) acc[h][j] = 0;
                         // three words at a time: a carry-save adder folds their intersections into a "ones" and a
                         // "twos" word, so three word-ops cost two POPC.64 instead of three (POPC is the scarce pipe)
+                        // a lane owns TL consecutive low subsets (lo = lane * TL + j) and the tile TH consecutive high ones, so
+                        // both operand sets are fetched with 128-bit shared-memory loads
                         int w = 0;
                         for (; w + 3 <= cw; w += 3) {
                             u64 l[3][TL];
 #pragma unroll
-                            for (int k = 0; k < 3; ++k)
+                            for (int k = 0; k < 3; ++k) load_words<TL>(ltab + ((w + k) << kl) + lane * TL, l[k], lane * TL < LS);
 #pragma unroll
-                                for (int j = 0; j < TL; ++j)
-                                    l[k][j] = (lane + 32 * j < LS) ? ltab[((w + k) << kl) + lane + 32 * j] : 0ull;
+                            for (int h2 = 0; h2 < TH; h2 += 2) {
+                                u64 hv[3][2];
 #pragma unroll
-                            for (int h = 0; h < TH; ++h) {
-                                const u64 h0 = htab[(w << kh) + hi0 + h], h1 = htab[((w + 1) << kh) + hi0 + h],
-                                          h2 = htab[((w + 2) << kh) + hi0 + h];
+                                for (int k = 0; k < 3; ++k) load_words<(TH > 1 ? 2 : 1)>(htab + ((w + k) << kh) + hi0 + h2, hv[k], true);
 #pragma unroll
-                                for (int j = 0; j < TL; ++j) {
-                                    u64 ones, twos;
-                                    csa(h0 & l[0][j], h1 & l[1][j], h2 & l[2][j], ones, twos);
-                                    acc[h][j] += __popcll(ones) + 2 * __popcll(twos);
-                                }
+                                for (int hh = 0; hh < (TH > 1 ? 2 : 1); ++hh)
+#pragma unroll
+                                    for (int j = 0; j < TL; ++j) {
+                                        u64 ones, twos;
+                                        csa(hv[0][hh] & l[0][j], hv[1][hh] & l[1][j], hv[2][hh] & l[2][j], ones, twos);
+                                        acc[h2 + hh][j] += __popcll(ones) + 2 * __popcll(twos);
+                                    }
                             }
                         }
                         for (; w < cw; ++w) {
                             u64 l[TL];
-#pragma unroll
-                            for (int j = 0; j < TL; ++j) l[j] = (lane + 32 * j < LS) ? ltab[(w << kl) + lane + 32 * j] : 0ull;
+                            load_words<TL>(ltab + (w << kl) + lane * TL, l, lane * TL < LS);
 #pragma unroll
                             for (int h = 0; h < TH; ++h) {
                                 const u64 hv = htab[(w << kh) + hi0 + h];
@@ -250,8 +268,8 @@ __global__ void __launch_bounds__(512, 1) k_general(const GeneralArgs a)
                         for (int h = 0; h < TH; ++h)
 #pragma unroll
                             for (int j = 0; j < TL; ++j) {
-                                const int fi = ((hi0 + h) << kl) | (lane + 32 * j);
-                                if (lane + 32 * j >= LS) continue;          // fewer than 32 low subsets (n < 5)
+                                const int fi = ((hi0 + h) << kl) | (lane * TL + j);
+                                if (lane * TL + j >= LS) continue;          // fewer than 32 low subsets (n < 5)
                                 if (w0 == 0) F[fi] = (CT)acc[h][j];
                                 else F[fi] = (CT)(F[fi] + acc[h][j]);
                             }
