@@ -13,7 +13,7 @@ from ._native import (DISTANT_ADMIXTURE, HOMOGENEOUS, RECENT_ADMIXTURE, LdpgtaEr
 from .engine import LLR_PAIRS, Engine, ResidentPanel, finish_chromosome, pack_ints
 from .models import ImplicitModels, distant_admixture, homogeneous, likelihoods_tuple, recent_admixture
 from .driver import (aneuploidy_test, bootstrap, build_gw_dict, effective_number_of_subsamples, evaluate_draws,
-                     pick_reads, plan_draws, statistics, supporting_dictionaries)
+                     pick_reads, plan_draw_indices, plan_draws, statistics, supporting_dictionaries)
 
 __all__ = ['Engine', 'homogeneous', 'recent_admixture', 'distant_admixture', 'bootstrap', 'aneuploidy_test',
            'statistics', 'likelihoods_tuple', 'ImplicitModels', 'LdpgtaError', 'pack_ints', 'finish_chromosome',

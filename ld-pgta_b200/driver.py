@@ -287,16 +287,82 @@ def evaluate_draws(examine, reads_dict, draws):
     return out
 
 
+def plan_draw_indices(genomic_windows, min_reads, max_reads, subsamples, replay=None, fast_rng=None):
+    """ The same draws as plan_draws, as positions inside each window's read tuple: {window: int array [effN, k]}.
+    random.sample(range(R), k) consumes the global MT19937 stream exactly like random.sample(read_IDs, k) and
+    returns the positions it would have picked, so the draws are the reference's for a given seed.
+    `fast_rng` (a numpy Generator) switches to vectorised sampling without replacement for throughput runs
+    (e.g. 1000 subsamples per window); those draws are statistically equivalent, not the reference's stream. """
+    plan = {}
+    for window, read_IDs in genomic_windows.items():
+        R = len(read_IDs)
+        effN = effective_number_of_subsamples(R, min_reads, max_reads, subsamples)
+        if not effN:
+            continue
+        k = min(R - 1, max_reads)
+        if replay is not None:
+            pos = {r: i for i, r in enumerate(read_IDs)}
+            plan[window] = np.array([[pos[r] for r in d] for d in replay[window][:effN]], dtype=np.int64).reshape(effN, -1)
+        elif fast_rng is not None:
+            plan[window] = np.argsort(fast_rng.random((effN, R)), axis=1)[:, :k]
+        else:
+            population = range(R)
+            plan[window] = np.array([random.sample(population, k) for _ in range(effN)], dtype=np.int64).reshape(effN, k)
+    return plan
+
+
+def evaluate_draw_indices(examine, reads_dict, genomic_windows, plan):
+    """ evaluate_draws for index plans: one read-mask row per read of the evaluated windows, one device batch. """
+    if not plan:
+        return {}
+    index = examine._allele_index
+    read_row = {}
+    allele_idx, read_offsets = [], [0]
+    chunks, sizes = [], set()
+    for window, local in plan.items():
+        rows = np.empty(len(genomic_windows[window]), dtype=np.int64)
+        for j, r in enumerate(genomic_windows[window]):
+            i = read_row.get(r)
+            if i is None:
+                i = read_row[r] = len(read_offsets) - 1
+                allele_idx.extend(index[a] for a in reads_dict[r])
+                read_offsets.append(len(allele_idx))
+            rows[j] = i
+        chunks.append(rows[local])                       # [effN, k] global read rows
+        sizes.add(local.shape[1])
+    for n in sizes:
+        if n not in (2, 3, 4):
+            examine._check_table(n)
+        if n == 5 and examine.kind == N.DISTANT_ADMIXTURE:
+            raise AttributeError("'distant_admixture' object has no attribute 'likelihoods5'")
+    counts = np.array([c.shape[0] for c in chunks], dtype=np.int64)
+    widths = np.repeat(np.array([c.shape[1] for c in chunks], dtype=np.int64), counts)
+    flat = np.concatenate([c.ravel() for c in chunks]).astype(np.int32)
+    offsets = np.zeros(len(widths) + 1, dtype=np.int64)
+    np.cumsum(widths, out=offsets[1:])
+    eng = examine._engine
+    eng.build_read_masks(allele_idx, read_offsets)
+    lik = eng.likelihoods_batch(examine.kind, flat, offsets, proportions=examine._proportions())
+    T = examine.tuple_type
+    out, k = {}, 0
+    rows = lik.tolist()
+    for window, c in zip(plan, counts.tolist()):
+        out[window] = tuple(T(*rows[k + j]) for j in range(c))
+        k += c
+    return out
+
+
 def bootstrap(obs_tab, leg_tab, hap_tab, number_of_haplotypes, ancestral_makeup, models_dict, window_size, subsamples,
-              offset, min_reads, max_reads, min_score, min_HF, replay=None, device=0, panel=None):
+              offset, min_reads, max_reads, min_score, min_HF, replay=None, device=0, panel=None, fast_rng=None):
     """ ANEUPLOIDY_TEST.bootstrap (:250-287): (likelihoods, genomic_windows, fraction_of_matches).
-    `panel`: an engine.ResidentPanel of this chromosome shared by many samples (one or two populations). """
+    `panel`: an engine.ResidentPanel of this chromosome shared by many samples (one or two populations);
+    `fast_rng`: numpy Generator for vectorised draws (throughput runs; not the reference's random stream). """
     examine = make_examiner(obs_tab, leg_tab, hap_tab, number_of_haplotypes, ancestral_makeup, models_dict, device=device, panel=panel)
     try:
         obs = supporting_dictionaries(obs_tab, leg_tab, hap_tab, number_of_haplotypes, ancestral_makeup, min_HF, examine=examine)
         genomic_windows = build_gw_dict(obs, window_size, offset, min_reads, max_reads, min_score)
-        draws = plan_draws(genomic_windows, min_reads, max_reads, subsamples, replay=replay)
-        likelihoods = evaluate_draws(examine, obs.reads, draws)
+        plan = plan_draw_indices(genomic_windows, min_reads, max_reads, subsamples, replay=replay, fast_rng=fast_rng)
+        likelihoods = evaluate_draw_indices(examine, obs.reads, genomic_windows, plan)
         return likelihoods, genomic_windows, examine.fraction_of_matches
     finally:
         examine.close()
@@ -388,7 +454,8 @@ def _opener(filename):
 def aneuploidy_test(obs_filename, leg_filename, hap_filename, ancestral_makeup, window_size, subsamples, offset, min_reads,
                     max_reads, min_score, min_HF, output_filename, compress, **kwargs):
     """ ANEUPLOIDY_TEST.aneuploidy_test (:368-429): same arguments, files and return value.
-    kwargs: seed, model (MODELS*.p path; optional here -- the device needs no tables), output_dir, device. """
+    kwargs: seed, model (MODELS*.p path; optional here -- the device needs no tables), output_dir, device,
+    panel (ResidentPanel shared by samples), fast_draws (vectorised numpy draws instead of random.sample). """
     time0 = time.time()
     random.seed(a=kwargs.get('seed', None), version=2)
 
@@ -412,9 +479,11 @@ def aneuploidy_test(obs_filename, leg_filename, hap_filename, ancestral_makeup, 
     assert ancestry == {*hap_tab}, 'error: the given ancestral makup does match the superpopulations (group2) in the reference panel.'
 
     device = kwargs.get('device', 0)
+    fast_rng = np.random.default_rng(kwargs.get('seed', None)) if kwargs.get('fast_draws', False) else None
     likelihoods, genomic_windows, matched_alleles = bootstrap(obs_tab, leg_tab, hap_tab, number_of_haplotypes, ancestral_makeup,
                                                               models_dict, window_size, subsamples, offset, min_reads,
-                                                              max_reads, min_score, min_HF, device=device)
+                                                              max_reads, min_score, min_HF, device=device,
+                                                              panel=kwargs.get('panel', None), fast_rng=fast_rng)
     some_statistics = {'matched_alleles': matched_alleles, 'runtime': time.time() - time0}
     info.update({'ancestral_makeup': ancestral_makeup, 'window_size': window_size, 'subsamples': subsamples, 'offset': offset,
                  'min_reads': min_reads, 'max_reads': max_reads, 'min_score': min_score, 'min_HF': min_HF,

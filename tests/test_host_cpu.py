@@ -132,3 +132,21 @@ def test_host_statistics_helpers_match_oracle():
     assert driver.mean_and_var(xs) == O.mean_and_var(xs)
     for y, x in ((0.0, 0.5), (0.5, 0.0), (0.0, 0.0), (0.25, 0.5)):
         assert driver.LLR(y, x) == O.LLR(y, x)
+
+
+def test_index_plan_equals_read_id_plan(golden_inputs):
+    """ random.sample(range(R), k) walks the same MT19937 stream as random.sample(read_IDs, k): the index plan
+    names exactly the reads the reference drew. """
+    _, out = chrom_case('homog_m8a', golden_inputs)
+    cfg = out['cfg']
+    random.seed(2021)
+    plan = driver.plan_draw_indices(out['windows'], cfg['min_reads'], cfg['max_reads'], cfg['subsamples'])
+    got = {w: [tuple(out['windows'][w][i] for i in row) for row in rows] for w, rows in plan.items()}
+    assert got == {w: [tuple(d) for d in ds] for w, ds in out['draws'].items()}
+    replayed = driver.plan_draw_indices(out['windows'], cfg['min_reads'], cfg['max_reads'], cfg['subsamples'], replay=out['draws'])
+    assert all(np.array_equal(plan[w], replayed[w]) for w in plan)
+    fast = driver.plan_draw_indices(out['windows'], cfg['min_reads'], cfg['max_reads'], cfg['subsamples'],
+                                    fast_rng=np.random.default_rng(1))
+    for w, rows in fast.items():
+        assert rows.shape == plan[w].shape
+        assert all(len(set(r)) == len(r) and max(r) < len(out['windows'][w]) for r in rows.tolist())
