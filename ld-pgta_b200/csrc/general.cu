@@ -15,7 +15,7 @@ static int plan_general(const ldpgta_ctx *c, int n, GeneralPlan *p)
     static const int TH[19] = {0, 0, 0, 0, 0, 1, 2, 4, 8, 4, 8, 8, 8, 8, 8, 8, 8, 8, 8};
     static const int TL[19] = {0, 0, 0, 0, 0, 1, 1, 1, 1, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4};
     static const int NW[19] = {0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 2, 4, 8, 16, 16, 16, 16, 16};
-    static const int BUDGET_KB[19] = {0, 0, 16, 16, 16, 16, 16, 20, 24, 28, 32, 48, 56, 110, 220, 220, 220, 220, 220};
+    static const int BUDGET_KB[19] = {0, 0, 16, 16, 16, 16, 16, 14, 14, 20, 18, 48, 56, 110, 220, 220, 220, 220, 220};   // measured (tools/tune_general.sh)
     if (n < 5) { p->th = 1; p->tl = 1; p->nw = 1; p->kl = n; }       // likelihoods() forced on 2..4 reads
     else { p->th = TH[n]; p->tl = TL[n]; p->nw = NW[n]; p->kl = p->tl == 1 ? 5 : 7; }
     if (const char *e = getenv("LDPGTA_PLAN_NW")) p->nw = atoi(e);          // tuning overrides
