@@ -198,6 +198,7 @@ struct GeneralArgs;
 // kernel launchers, one translation unit each (small.cu, general.cu)
 int launch_small(ldpgta_ctx *c, SmallArgs &a, int n, int kind);
 int make_read_mask_tmap(ldpgta_ctx *c, int g);
+int launch_mid(ldpgta_ctx *c, SmallArgs &a, int n);      // 5-6 reads, register kernel; 1 = not applicable
 int launch_general(ldpgta_ctx *c, GeneralArgs a);
 
 }  // namespace ldpgta

@@ -4,6 +4,7 @@
 
 #include "common.cuh"
 #include "k_small.cuh"
+#include "k_mid.cuh"
 
 namespace ldpgta {
 
@@ -81,6 +82,33 @@ int make_read_mask_tmap(ldpgta_ctx *c, int g)
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     c->tmap_ok[g] = (r == CUDA_SUCCESS);
     return 0;
+}
+
+template <int NR, int W64>
+static int launch_mid_t(ldpgta_ctx *c, SmallArgs &a)
+{
+    using P = MidPipe<NR, W64>;
+    auto kern = k_mid<NR, W64>;
+    LDPGTA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM));
+    const int64_t tiles = (a.n_draws + 1) / 2;
+    const int64_t want = (tiles + P::NWARPS - 1) / P::NWARPS;
+    const unsigned blocks = (unsigned)std::min<int64_t>(want, c->sm_count);
+    kern<<<blocks, P::NWARPS * 32, P::SMEM, c->stream>>>(a);
+    c->launches++;
+    LDPGTA_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// 5 or 6 reads, one population of at most 65535 haplotypes and rows of at most 80 words: the register kernel.
+// Returns 1 when the draw shape is outside that envelope (the caller then uses the table kernel).
+int launch_mid(ldpgta_ctx *c, SmallArgs &a, int n)
+{
+    a.use_gather4 = 0;
+    if (c->G != 1 || c->nhap[0] > 65535u || c->wp[0] > 80 || getenv("LDPGTA_NO_MID")) return 1;
+    const int wp = c->wp[0];
+    if (n == 5) return wp <= 32 ? launch_mid_t<5, 2>(c, a) : wp <= 48 ? launch_mid_t<5, 3>(c, a) : launch_mid_t<5, 5>(c, a);
+    if (n == 6) return wp <= 32 ? launch_mid_t<6, 2>(c, a) : wp <= 48 ? launch_mid_t<6, 3>(c, a) : launch_mid_t<6, 5>(c, a);
+    return 1;
 }
 
 int launch_small(ldpgta_ctx *c, SmallArgs &a, int n, int kind)
