@@ -14,7 +14,7 @@
 #include "k_small.cuh"
 
 #ifndef LDPGTA_MID6_WARPS
-#define LDPGTA_MID6_WARPS 8
+#define LDPGTA_MID6_WARPS 12     // measured: 8 -> 2.99e8, 12 -> 3.20e8, 16 (spilling) -> 3.16e8 draws/s
 #endif
 
 namespace ldpgta {
@@ -24,7 +24,8 @@ struct MidPipe {
     static constexpr int STAGE_BYTES = 2 * NR * 16 * W64 * 8;                  // 2 draws * NR rows * 16 lanes * W64 words
     static constexpr int NWARPS_RAW = (200 * 1024) / STAGE_BYTES;
     static constexpr int NWARPS_FIT = NWARPS_RAW > 16 ? 16 : (NWARPS_RAW & ~3);
-    // 6 reads keep 60 mask registers and 64 counts live: 8 warps (255 registers each) instead of 16 (128, spilling)
+    // 6 reads keep 60 mask registers and 64 counts live: 12 warps (168 registers each) instead of 16 (128, spilling).
+    // (A 7-read instance was measured too: 255 registers with spills, half the speed of the table kernel.)
     static constexpr int NWARPS = (NR == 6 && NWARPS_FIT > LDPGTA_MID6_WARPS) ? LDPGTA_MID6_WARPS : NWARPS_FIT;
     static constexpr int SMEM = NWARPS * (STAGE_BYTES + 16);
 };
