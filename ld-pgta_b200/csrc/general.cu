@@ -12,13 +12,14 @@ struct GeneralPlan { int th, tl, nw, kl, kh, wc; bool u16, global_table; size_t 
 
 static int plan_general(const ldpgta_ctx *c, int n, GeneralPlan *p)
 {
-    static const int TH[19] = {0, 0, 0, 0, 0, 1, 2, 4, 8, 4, 8, 8, 8, 8, 8, 8, 8, 8, 8};
+    static const int TH[19] = {0, 0, 0, 0, 0, 1, 2, 4, 8, 2, 4, 4, 8, 8, 8, 8, 8, 8, 8};
     static const int TL[19] = {0, 0, 0, 0, 0, 1, 1, 1, 1, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4};
-    static const int NW[19] = {0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 2, 4, 8, 16, 16, 16, 16, 16};
-    static const int BUDGET_KB[19] = {0, 0, 16, 16, 16, 16, 16, 14, 14, 20, 18, 48, 56, 110, 220, 220, 220, 220, 220};   // measured (tools/tune_general.sh)
+    static const int NW[19] = {0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 4, 4, 8, 16, 16, 16, 16, 16};
+    static const int BUDGET_KB[19] = {0, 0, 16, 16, 16, 16, 16, 14, 14, 24, 24, 48, 56, 110, 220, 220, 220, 220, 220};   // measured (tools/tune_general.sh)
     if (n < 5) { p->th = 1; p->tl = 1; p->nw = 1; p->kl = n; }       // likelihoods() forced on 2..4 reads
     else { p->th = TH[n]; p->tl = TL[n]; p->nw = NW[n]; p->kl = p->tl == 1 ? 5 : 7; }
     if (const char *e = getenv("LDPGTA_PLAN_NW")) p->nw = atoi(e);          // tuning overrides
+    if (const char *e = getenv("LDPGTA_PLAN_TH")) p->th = atoi(e);
     p->kh = n - p->kl;
     uint32_t nmax = 0; int wmax = 0, wsum = 0;
     for (int g = 0; g < c->G; ++g) { nmax = std::max(nmax, c->nhap[g]); wmax = std::max(wmax, c->wp[g]); wsum += c->wp[g]; }
@@ -123,7 +124,7 @@ int launch_general(ldpgta_ctx *c, GeneralArgs a)
 #define LDPGTA_CASE(TH_, TL_)                                                         \
     if (p.th == TH_ && p.tl == TL_)                                                   \
         return p.u16 ? launch_general_t<TH_, TL_, uint16_t>(c, a, p) : launch_general_t<TH_, TL_, uint32_t>(c, a, p);
-    LDPGTA_CASE(1, 1) LDPGTA_CASE(2, 1) LDPGTA_CASE(4, 1) LDPGTA_CASE(8, 1) LDPGTA_CASE(4, 4) LDPGTA_CASE(8, 4)
+    LDPGTA_CASE(1, 1) LDPGTA_CASE(2, 1) LDPGTA_CASE(4, 1) LDPGTA_CASE(8, 1) LDPGTA_CASE(2, 4) LDPGTA_CASE(4, 4) LDPGTA_CASE(8, 4)
 #undef LDPGTA_CASE
     return fail(LDPGTA_E_UNSUPPORTED, "no kernel instance for n=%d", a.n);
 }

@@ -1,8 +1,8 @@
 #!/bin/bash
-# usage: tune_general.sh n windows subsamples "NW:KB NW:KB ..."
+# usage: tune_general.sh n windows subsamples "NW:KB NW:KB ..." [TH]
 n=$1; w=$2; s=$3
 for cfg in $4; do nw=${cfg%%:*}; kb=${cfg##*:}
-  LDPGTA_PLAN_NW=$nw LDPGTA_PLAN_KB=$kb timeout 400 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --max-reads $n --windows $w --subsamples $s --depth 0.2 > gpurun_out/tg.json 2> gpurun_out/tg.err
+  env LDPGTA_PLAN_NW=$nw LDPGTA_PLAN_KB=$kb ${5:+LDPGTA_PLAN_TH=$5} timeout 400 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --max-reads $n --windows $w --subsamples $s --depth 0.2 > gpurun_out/tg.json 2> gpurun_out/tg.err
   python -c "
-import json,sys; d=json.load(open('gpurun_out/tg.json')); print('n=$n nw=$nw kb=$kb', 'ms', round(d['ms_per_step'],4), 'draws/s', round(d['value']), 'int frac', round(d['int_roofline']['frac'],4))" || tail -2 gpurun_out/tg.err
+import json,sys; d=json.load(open('gpurun_out/tg.json')); print('n=$n nw=$nw kb=$kb th=${5:-default}', 'ms', round(d['ms_per_step'],4), 'draws/s', round(d['value']), 'int frac', round(d['int_roofline']['frac'],4))" || tail -2 gpurun_out/tg.err
 done
