@@ -253,7 +253,7 @@ def run_reference(args):
 
 
 def workload_config(args, n_windows, n_reads):
-    tag = 'configs[1]' if (args.max_reads == 4 and args.depth == 0.1 and not args.windows) else 'exploration run'
+    tag = 'configs[1]' if (args.max_reads == 4 and args.depth == 0.1 and not args.windows and args.model == 'homogeneous') else 'exploration run'
     return {'workload': '%s: 22-autosome synthetic embryo, depth %.2fx, homogeneous model, monosomy/disomy/SPH/BPH' % (tag, args.depth),
             'haplotypes': N_HAP, 'windows_per_gpu': n_windows, 'reads_per_gpu': n_reads, 'window_size': WINDOW,
             'subsamples': args.subsamples, 'max_reads': args.max_reads, 'min_reads': 6,
@@ -271,6 +271,7 @@ def main():
     ap.add_argument('--subsamples', type=int, default=32)
     ap.add_argument('--max-reads', type=int, default=4)
     ap.add_argument('--seed', type=int, default=12345)
+    ap.add_argument('--model', default='homogeneous', choices=['homogeneous', 'recent'], help='recent = two-population exploration run')
     ap.add_argument('--windows', type=int, default=0, help='limit the number of windows (exploration runs; 0 = whole genome)')
     ap.add_argument('--cpu-seconds', type=float, default=12.0, help='budget of the single-core CPU baseline leg')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -298,19 +299,27 @@ def main():
     # ---- workload: one embryo per rank ------------------------------------------------------
     wins, reads = workload_shape(args.depth, args.seed + 1000 * rank, min_reads=args.max_reads + 2, max_windows=args.windows)
     n_windows, n_reads = len(reads), int(reads.sum())
-    masks = synth_masks(torch, device, reads, N_HAP, args.seed + 1000 * rank)
     idx_host, win_of_draw = plan_draws(reads, args.subsamples, args.max_reads, args.seed + 1 + 1000 * rank)
     n_draws, n = idx_host.shape
-    eng = L.Engine([N_HAP], device=local)
-    assert masks.shape[1] == eng.padded_words[0]
-    eng.attach_read_masks_dev(0, masks.data_ptr(), n_reads, keepalive=masks)
+    if args.model == 'recent':                       # exploration: configs[3], two populations of 2504 haplotypes
+        group_sizes, kind = [N_HAP // 2, N_HAP // 2], L.RECENT_ADMIXTURE
+    else:
+        group_sizes, kind = [N_HAP], L.HOMOGENEOUS
+    eng = L.Engine(group_sizes, device=local)
+    all_masks = []
+    for g, nh in enumerate(group_sizes):
+        m = synth_masks(torch, device, reads, nh, args.seed + 1000 * rank + 77 * g)
+        assert m.shape[1] == eng.padded_words[g]
+        eng.attach_read_masks_dev(g, m.data_ptr(), n_reads, keepalive=m)
+        all_masks.append(m)
+    masks = all_masks[0]
 
     d_idx = torch.from_numpy(idx_host).to(device)
     d_out = torch.empty((n_draws, 4), dtype=torch.float64, device=device)
     stream = torch.cuda.ExternalStream(eng.stream, device=device)
 
     def step_resident():
-        eng.likelihoods_uniform_dev(L.HOMOGENEOUS, n, d_idx.data_ptr(), n_draws, d_out.data_ptr())
+        eng.likelihoods_uniform_dev(kind, n, d_idx.data_ptr(), n_draws, d_out.data_ptr())
 
     # pinned host buffers for the end-to-end leg
     pin_idx = L.PinnedArray((n_draws, n), np.int32)
@@ -319,7 +328,7 @@ def main():
     offsets = np.arange(0, n_draws * n + 1, n, dtype=np.int64)
 
     def step_e2e():
-        eng.likelihoods_batch(L.HOMOGENEOUS, pin_idx.array.reshape(-1), offsets, out=pin_out.array)
+        eng.likelihoods_batch(kind, pin_idx.array.reshape(-1), offsets, out=pin_out.array)
 
     def barrier():
         torch.cuda.synchronize()
@@ -399,7 +408,7 @@ def main():
         pass
     hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
     peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs, burst copy)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s (B200_PROFILING.md)'
-    words = (N_HAP + 63) // 64
+    words = sum((nh + 63) // 64 for nh in group_sizes)
     bytes_per_draw = n * words * 8 + n * 4 + 32               # n*W*8 mask bytes + indices in, 32 B out
     wordops_per_draw = ((1 << n) - 1) * words
     k_ms = float(np.mean(kernel_ms))
@@ -423,7 +432,7 @@ def main():
 
     # ---- CPU baseline: oracle port on a bounded sample, one core; doubles as the parity check -------
     cpu_baseline, parity = None, None
-    if not args.no_cpu_baseline and world == 1:             # rank 0 at N=1 only
+    if not args.no_cpu_baseline and world == 1 and args.model == 'homogeneous':     # rank 0 at N=1 only
         spent, n_eval, w = 0.0, 0, 0
         ref_rows, got_rows = [], []
         starts = np.concatenate([[0], np.cumsum(reads)])
@@ -455,7 +464,7 @@ def main():
                 'd2h_bytes_per_step': int(pin_out.array.nbytes), 'ms_per_step': 1e3 * e2e_s / args.steps,
                 'api': 'Engine.likelihoods_batch -> ldpgta_likelihoods_batch (pinned host buffers)'},
         'gpu_launches': int(launches),
-        'roofline': {'bound': 'hbm', 'kernel': 'k_small<%d,8,10>' % n if n <= 4 else 'k_general (n=%d)' % n, 'achieved': achieved_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
+        'roofline': {'bound': 'hbm', 'kernel': 'k_small<%d,8,10>' % n if n <= 4 else ('k_mid<%d,5>' % n if n <= 6 else 'k_general (n=%d)' % n), 'achieved': achieved_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
                      'frac': achieved_gbs / hbm_peak, 'traffic': traffic, 'peak_source': peak_src,
                      'algorithmic_bytes_per_draw': bytes_per_draw, 'kernel_ms': k_ms},
         'int_roofline': {'bound': 'popc', 'achieved': achieved_wordops, 'peak': int_peak, 'unit': 'word AND+POPC/s',
