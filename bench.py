@@ -248,7 +248,7 @@ def run_reference(args):
             'cpu_baseline': {'value': value, 'unit': 'window-likelihoods/s', 'cores': cores, 'kind': 'port', 'sample': sample,
                              'python': sys.version.split()[0], 'popcount': 'int.bit_count (reference: gmpy2.popcount or byte LUT)'},
             'e2e': {'value': value, 'unit': 'window-likelihoods/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -261,7 +261,27 @@ def workload_config(args, n_windows, n_reads):
             'parallelism': 'one embryo per GPU, windows independent, no data-path collective'}
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """ The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to
+    stdout), so file descriptor 1 is pointed at stderr for the whole run and the line goes to the saved descriptor. """
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + '\n')
+    _JSON_OUT.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=30)
@@ -475,7 +495,7 @@ def main():
     }
     if stats_ms is not None:
         line['chromosome_partials_allreduce_ms'] = stats_ms
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
