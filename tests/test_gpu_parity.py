@@ -549,3 +549,29 @@ def test_resident_panel_gather_equals_host_packing(golden_testmodule, golden_inp
         assert worst < LIK_TOL
     for p in (panel1, panel2, shared):
         p.close()
+
+
+def test_command_line_interface(tmp_path, golden_inputs):
+    """ `python ANEUPLOIDY_TEST.py OBS LEG HAP G0 -s 8 ...` (the reference's CLI, ANEUPLOIDY_TEST.py:440-493). """
+    import gzip, os, pickle, subprocess, sys
+    from conftest import ROOT
+    args, out = chrom_case('homog_m4', golden_inputs)
+    d = tmp_path
+    with open(d / 'cli.chr21.obs.p', 'wb') as f:
+        pickle.dump(args['obs_tab'], f); pickle.dump({'chr_id': 'chr21', 'depth': 0.45}, f)
+    with open(d / 'panel.legend.p', 'wb') as f:
+        pickle.dump(args['leg_tab'], f)
+    with open(d / 'panel.hap.p', 'wb') as f:
+        # the reference's CLI only accepts alphabetic group names (ANEUPLOIDY_TEST.py:480-488): G0 -> EUR
+        pickle.dump({'EUR': args['hap_tab']['G0']}, f); pickle.dump({'EUR': args['number_of_haplotypes']['G0']}, f)
+    script = os.path.join(str(ROOT), 'ld-pgta_b200', 'ANEUPLOIDY_TEST.py')
+    res = subprocess.run([sys.executable, script, str(d / 'cli.chr21.obs.p'), str(d / 'panel.legend.p'), str(d / 'panel.hap.p'),
+                          'EUR', '-s', '8', '-m', '6', '-M', '4', '-C', 'gz'], capture_output=True, text=True, timeout=300, cwd=str(d))
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert 'Chromosome-wide LLR between BPH and SPH' in res.stdout
+    with gzip.open(d / 'results' / 'cli.chr21.LLR.p.gz', 'rb') as f:
+        sys.path.insert(0, os.path.join(str(ROOT), 'ld-pgta_b200'))
+        lik = pickle.load(f); info = pickle.load(f)
+    assert list(lik) == list(out['likelihoods']) and info['subsamples'] == 8 and info['ancestral_makeup'] == {'EUR'}
+    bad = subprocess.run([sys.executable, script, 'a', 'b', 'c', 'G0'], capture_output=True, text=True, timeout=300)
+    assert bad.returncode != 0 and 'Invalid argument supplied for ancestral makeup' in bad.stderr
