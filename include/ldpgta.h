@@ -163,6 +163,19 @@ int ldpgta_window_stats(ldpgta_ctx *ctx, const double *lik, const int64_t *windo
  * std_of_mean, fraction_of_negative_LLRs. */
 int ldpgta_finish_chromosome(const double *chrom_partials, int n_cols, int first_window_draws, double *out);
 
+/* binning() of the LLR consumers (PLOT_PANEL.py:121-144, BALANCED_ROC_CURVE.py:131-154): per bin
+ * = run of windows [bin_ranges[b][0], bin_ranges[b][1]) the mean LLR and the standard error of
+ * mean_and_std_of_mean_of_rnd_var (PLOT_PANEL.py:37-48; N = draws of the bin's first window,
+ * columns truncated to the bin's shortest window).
+ *   x          [n_series][n_draws] host values, one LLR series per row, windows as in
+ *              ldpgta_window_stats; or NULL = the 5 LLR series the last ldpgta_window_stats call
+ *              of this context left on the device (n_series must be 5, same window_offsets),
+ *              so the per-draw LLRs never travel back to the host;
+ *   bin_ranges [n_bins][2]  window index ranges, every bin non-empty;
+ *   out        [n_series][n_bins][2] = (mean, std). */
+int ldpgta_bin_stats(ldpgta_ctx *ctx, const double *x, int n_series, const int64_t *window_offsets,
+                     int64_t n_windows, const int64_t *bin_ranges, int64_t n_bins, double *out);
+
 /* Page-locked host buffers so that the batch calls above copy without staging. */
 int ldpgta_host_alloc(void **ptr, int64_t bytes);
 int ldpgta_host_free(void *ptr);

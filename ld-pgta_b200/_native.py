@@ -44,6 +44,7 @@ SYMBOLS = (
     ('ldpgta_launch_count', _c.c_int64, [_P]),
     ('ldpgta_window_stats', _c.c_int, [_P, _P, _P, _c.c_int64, _c.c_int, _P, _P, _P]),
     ('ldpgta_finish_chromosome', _c.c_int, [_P, _c.c_int, _c.c_int, _P]),
+    ('ldpgta_bin_stats', _c.c_int, [_P, _P, _c.c_int, _P, _c.c_int64, _P, _c.c_int64, _P]),
     ('ldpgta_host_alloc', _c.c_int, [_c.POINTER(_P), _c.c_int64]),
     ('ldpgta_host_free', _c.c_int, [_P]),
 )

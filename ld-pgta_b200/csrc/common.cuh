@@ -163,6 +163,10 @@ struct ldpgta_ctx {
     // growable staging buffers
     void *h_pin = nullptr;  size_t h_pin_bytes = 0;
     void *d_buf = nullptr;  size_t d_buf_bytes = 0;
+    // LLRs of the last ldpgta_window_stats call, kept on the device for ldpgta_bin_stats (own allocation)
+    double *d_llr = nullptr;  size_t d_llr_bytes = 0;
+    int64_t llr_draws = -1, llr_windows = -1;
+    int64_t *d_llr_off = nullptr;  size_t d_llr_off_bytes = 0;
 
     // colourings of the high reads used by the three-block polynomial, one list per h = n - 5 (built on first use)
     uint64_t *hi_terms[14] = {};

@@ -275,4 +275,70 @@ __global__ void k_chrom_partials(const double *__restrict__ llrs, const int64_t 
     }
 }
 
+// binning() of PLOT_PANEL.py:121-144 / BALANCED_ROC_CURVE.py:131-154: one block per (series, bin).  A bin is a run
+// of windows [b0, b1); mean_and_std_of_mean_of_rnd_var (PLOT_PANEL.py:37-48) on the windows' LLR rows:
+//   N = draws of the bin's FIRST window, M = b1 - b0, mu = (sum of all values) / N,
+//   std = sqrt(sum_i (column_i - mu)^2 / (N - 1)) / M over the columns every window has (zip truncation), mean = mu / M.
+// x[n_series][n_draws]; out[n_series][n_bins][2] = (mean, std).
+__global__ void k_bin_stats(const double *__restrict__ x, int64_t n_draws, const int64_t *__restrict__ woff,
+                            const int64_t *__restrict__ ranges, int64_t n_bins, double *__restrict__ out)
+{
+    __shared__ double sh_s[32], sh_c[32];
+    __shared__ int64_t sh_min[32];
+    __shared__ double sh_mu;
+    __shared__ int64_t sh_cols;
+    const int64_t bin = blockIdx.x;
+    const double *xs = x + (int64_t)blockIdx.y * n_draws;
+    const int64_t b0 = ranges[2 * bin], b1 = ranges[2 * bin + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int64_t lo = woff[b0], hi = woff[b1];
+    Comp acc = {0.0, 0.0};
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) acc.add(xs[i]);
+    int64_t mn = INT64_MAX;
+    for (int64_t w = b0 + threadIdx.x; w < b1; w += blockDim.x) mn = min(mn, woff[w + 1] - woff[w]);
+#pragma unroll
+    for (int m = 16; m; m >>= 1) {
+        const double os = __shfl_xor_sync(0xffffffffu, acc.s, m), oc = __shfl_xor_sync(0xffffffffu, acc.c, m);
+        acc.add(os);
+        acc.c += oc;
+        mn = min(mn, (int64_t)__shfl_xor_sync(0xffffffffu, (long long)mn, m));
+    }
+    if (lane == 0) { sh_s[warp] = acc.s; sh_c[warp] = acc.c; sh_min[warp] = mn; }
+    __syncthreads();
+    const double N = (double)(woff[b0 + 1] - woff[b0]), M = (double)(b1 - b0);
+    if (threadIdx.x == 0) {
+        Comp t = {0.0, 0.0};
+        int64_t m = INT64_MAX;
+        for (int w = 0; w < nwarps; ++w) { t.add(sh_s[w]); t.c += sh_c[w]; m = min(m, sh_min[w]); }
+        sh_mu = t.value() / N;
+        sh_cols = m;
+    }
+    __syncthreads();
+    const double mu = sh_mu;
+    const int64_t cols = sh_cols;
+    Comp ss = {0.0, 0.0};
+    for (int64_t i = threadIdx.x; i < cols; i += blockDim.x) {
+        Comp col = {0.0, 0.0};
+        for (int64_t w = b0; w < b1; ++w) col.add(xs[woff[w] + i]);
+        const double d = col.value() - mu;
+        ss.add(d * d);
+    }
+#pragma unroll
+    for (int m = 16; m; m >>= 1) {
+        const double os = __shfl_xor_sync(0xffffffffu, ss.s, m), oc = __shfl_xor_sync(0xffffffffu, ss.c, m);
+        ss.add(os);
+        ss.c += oc;
+    }
+    __syncthreads();
+    if (lane == 0) { sh_s[warp] = ss.s; sh_c[warp] = ss.c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        Comp t = {0.0, 0.0};
+        for (int w = 0; w < nwarps; ++w) { t.add(sh_s[w]); t.c += sh_c[w]; }
+        double *o = out + 2 * ((int64_t)blockIdx.y * n_bins + bin);
+        o[0] = mu / M;
+        o[1] = sqrt(t.value() / (N - 1.0)) / M;      // N = 1 divides by zero, as the reference does
+    }
+}
+
 }  // namespace ldpgta

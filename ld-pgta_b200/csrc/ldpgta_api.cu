@@ -36,6 +36,18 @@ static int ensure_dev(ldpgta_ctx *c, size_t bytes)
     return 0;
 }
 
+template <class T>
+static int ensure_own(T **ptr, size_t *have, size_t bytes)
+{
+    if (*have >= bytes) return 0;
+    if (*ptr) LDPGTA_CUDA(cudaFree(*ptr));
+    *ptr = nullptr; *have = 0;
+    bytes = bytes + bytes / 4 + 4096;
+    LDPGTA_CUDA(cudaMalloc((void **)ptr, bytes));
+    *have = bytes;
+    return 0;
+}
+
 static int ensure_pin(ldpgta_ctx *c, size_t bytes)
 {
     if (c->h_pin_bytes >= bytes) return 0;
@@ -195,6 +207,8 @@ int ldpgta_destroy(ldpgta_ctx *c)
     if (c->table_scratch) cudaFree(c->table_scratch);
     if (c->allele_complement) cudaFree(c->allele_complement);
     if (c->d_buf) cudaFree(c->d_buf);
+    if (c->d_llr) cudaFree(c->d_llr);
+    if (c->d_llr_off) cudaFree(c->d_llr_off);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->s_in) cudaStreamDestroy(c->s_in);
@@ -717,13 +731,17 @@ int ldpgta_window_stats(ldpgta_ctx *c, const double *lik, const int64_t *window_
     const int ncp = n_cols + 3;
     const size_t lik_b = (size_t)n_draws * 32, off_b = ((size_t)(n_windows + 1) * 8 + 15) & ~(size_t)15;
     const size_t llr_b = (size_t)n_draws * 5 * 8, mv_b = (size_t)n_windows * 5 * 2 * 8, cp_b = (size_t)5 * ncp * 8;
-    if (int rc = ensure_dev(c, lik_b + off_b + llr_b + mv_b + cp_b + 64)) return rc;
+    if (int rc = ensure_dev(c, lik_b + mv_b + cp_b + 64)) return rc;
+    // the LLRs and the window offsets stay on the device for ldpgta_bin_stats
+    c->llr_draws = c->llr_windows = -1;
+    if (int rc = ensure_own(&c->d_llr, &c->d_llr_bytes, llr_b + 16)) return rc;
+    if (int rc = ensure_own(&c->d_llr_off, &c->d_llr_off_bytes, off_b)) return rc;
     char *p = (char *)c->d_buf;
     double *d_lik = (double *)p; p += lik_b;
-    int64_t *d_off = (int64_t *)p; p += off_b;
-    double *d_llr = (double *)p; p += llr_b;
     double *d_mv = (double *)p; p += mv_b;
     double *d_cp = (double *)p;
+    double *d_llr = c->d_llr;
+    int64_t *d_off = c->d_llr_off;
     if (n_draws) LDPGTA_CUDA(cudaMemcpyAsync(d_lik, lik, lik_b, cudaMemcpyHostToDevice, c->stream));
     LDPGTA_CUDA(cudaMemcpyAsync(d_off, window_offsets, (size_t)(n_windows + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     if (n_draws) {
@@ -740,6 +758,52 @@ int ldpgta_window_stats(ldpgta_ctx *c, const double *lik, const int64_t *window_
     if (llr_out && n_draws) LDPGTA_CUDA(cudaMemcpyAsync(llr_out, d_llr, llr_b, cudaMemcpyDeviceToHost, c->stream));
     if (window_mean_var && n_windows) LDPGTA_CUDA(cudaMemcpyAsync(window_mean_var, d_mv, mv_b, cudaMemcpyDeviceToHost, c->stream));
     if (chrom_partials) LDPGTA_CUDA(cudaMemcpyAsync(chrom_partials, d_cp, cp_b, cudaMemcpyDeviceToHost, c->stream));
+    LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
+    c->llr_draws = n_draws;
+    c->llr_windows = n_windows;
+    return 0;
+}
+
+int ldpgta_bin_stats(ldpgta_ctx *c, const double *x, int n_series, const int64_t *window_offsets, int64_t n_windows,
+                     const int64_t *bin_ranges, int64_t n_bins, double *out)
+{
+    if (!c || !window_offsets || !bin_ranges || !out || n_series < 1 || n_windows < 1 || n_bins < 0)
+        return fail(LDPGTA_E_INVALID, "bad arguments");
+    LDPGTA_CUDA(cudaSetDevice(c->device));
+    if (window_offsets[0] != 0) return fail(LDPGTA_E_INVALID, "window_offsets must start at 0");
+    const int64_t n_draws = window_offsets[n_windows];
+    for (int64_t w = 0; w < n_windows; ++w)
+        if (window_offsets[w + 1] - window_offsets[w] < 1) return fail(LDPGTA_E_INVALID, "window %lld has no draws", (long long)w);
+    for (int64_t b = 0; b < n_bins; ++b)
+        if (bin_ranges[2 * b] < 0 || bin_ranges[2 * b + 1] > n_windows || bin_ranges[2 * b] >= bin_ranges[2 * b + 1])
+            return fail(LDPGTA_E_INVALID, "bin %lld: empty or out-of-range window range [%lld, %lld)", (long long)b,
+                        (long long)bin_ranges[2 * b], (long long)bin_ranges[2 * b + 1]);
+    if (n_bins == 0) return 0;
+    if (n_series > 65535) return fail(LDPGTA_E_INVALID, "too many series");
+    const size_t x_b = x ? (size_t)n_series * n_draws * 8 : 0, off_b = ((size_t)(n_windows + 1) * 8 + 15) & ~(size_t)15;
+    const size_t rng_b = (size_t)n_bins * 16, out_b = (size_t)n_series * n_bins * 16;
+    const double *d_x;
+    const int64_t *d_off;
+    if (int rc = ensure_dev(c, x_b + off_b + rng_b + out_b + 64)) return rc;
+    char *p = (char *)c->d_buf;
+    if (x) {
+        LDPGTA_CUDA(cudaMemcpyAsync(p, x, x_b, cudaMemcpyHostToDevice, c->stream));
+        d_x = (const double *)p; p += x_b;
+        LDPGTA_CUDA(cudaMemcpyAsync(p, window_offsets, (size_t)(n_windows + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+        d_off = (const int64_t *)p; p += off_b;
+    } else {
+        if (n_series != 5 || c->llr_draws != n_draws || c->llr_windows != n_windows)
+            return fail(LDPGTA_E_INVALID, "no resident LLRs for these windows: call ldpgta_window_stats first (5 series)");
+        d_x = c->d_llr;
+        d_off = c->d_llr_off;
+    }
+    int64_t *d_rng = (int64_t *)p; p += rng_b;
+    double *d_out = (double *)p;
+    LDPGTA_CUDA(cudaMemcpyAsync(d_rng, bin_ranges, rng_b, cudaMemcpyHostToDevice, c->stream));
+    k_bin_stats<<<dim3((unsigned)n_bins, (unsigned)n_series), 128, 0, c->stream>>>(d_x, n_draws, d_off, d_rng, n_bins, d_out);
+    c->launches++;
+    LDPGTA_CUDA(cudaGetLastError());
+    LDPGTA_CUDA(cudaMemcpyAsync(out, d_out, out_b, cudaMemcpyDeviceToHost, c->stream));
     LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }

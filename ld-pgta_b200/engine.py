@@ -209,18 +209,37 @@ class Engine:
         return int(self.lib.ldpgta_launch_count(self._ctx))
 
     # ---- reductions -----------------------------------------------------------
-    def window_stats(self, lik, window_offsets, n_cols):
+    def window_stats(self, lik, window_offsets, n_cols, want_llr=True):
         """ LLRs, per-window mean / sample variance and the chromosome partial sums
-        (statistics(), ANEUPLOIDY_TEST.py:289-325) for consecutive windows of draws. """
+        (statistics(), ANEUPLOIDY_TEST.py:289-325) for consecutive windows of draws.  The per-draw LLRs also stay
+        on the device for bin_stats(None, ...); want_llr=False skips their download. """
         lik = np.ascontiguousarray(lik, dtype=np.float64)
         off = np.ascontiguousarray(window_offsets, dtype=np.int64)
         nw, nd = len(off) - 1, lik.shape[0]
-        llr = np.empty((N.NUM_LLR_PAIRS, nd), dtype=np.float64)
+        llr = np.empty((N.NUM_LLR_PAIRS, nd), dtype=np.float64) if want_llr else None
         mean_var = np.empty((N.NUM_LLR_PAIRS, nw, 2), dtype=np.float64)
         partials = np.empty((N.NUM_LLR_PAIRS, n_cols + 3), dtype=np.float64)
-        N.check(self.lib.ldpgta_window_stats(self._ctx, N.ptr(lik), N.ptr(off), nw, n_cols, N.ptr(llr), N.ptr(mean_var),
+        N.check(self.lib.ldpgta_window_stats(self._ctx, N.ptr(lik), N.ptr(off), nw, n_cols, N.ptr(llr) if want_llr else None, N.ptr(mean_var),
                                              N.ptr(partials)))
         return llr, mean_var, partials
+
+    def bin_stats(self, x, window_offsets, bin_ranges):
+        """ Mean LLR and its standard error per bin of windows (binning(), PLOT_PANEL.py:121-144).
+        x: [n_series][n_draws] values, or None = the five LLR series the last window_stats() call left on the
+        device.  bin_ranges: [n_bins][2] window index ranges.  Returns [n_series][n_bins][2] = (mean, std). """
+        off = np.ascontiguousarray(window_offsets, dtype=np.int64)
+        rng = np.ascontiguousarray(bin_ranges, dtype=np.int64).reshape(-1, 2)
+        if x is None:
+            ns, xp = N.NUM_LLR_PAIRS, None
+        else:
+            x = np.ascontiguousarray(x, dtype=np.float64)
+            x = x.reshape(1, -1) if x.ndim == 1 else x
+            if x.shape[1] != off[-1]:
+                raise ValueError('x has %d values per series, the windows hold %d draws' % (x.shape[1], off[-1]))
+            ns, xp = x.shape[0], N.ptr(x)
+        out = np.empty((ns, len(rng), 2), dtype=np.float64)
+        N.check(self.lib.ldpgta_bin_stats(self._ctx, xp, ns, N.ptr(off), len(off) - 1, N.ptr(rng), len(rng), N.ptr(out)))
+        return out
 
 
 def finish_chromosome(partials, n_cols, first_window_draws):

@@ -645,6 +645,112 @@ def statistics(likelihoods, genomic_windows):
 
 
 # --------------------------------------------------------------------------
+# SURVEY 8(f) rank 4 : consumers of the per-window LLRs (binning, crossovers)
+# --------------------------------------------------------------------------
+
+CHR_LENGTHS = dict(zip(['chr%s' % c for c in list(range(1, 23)) + ['X', 'Y']],      # hg38, PLOT_PANEL.py:20-28
+                       (248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636,
+                        138394717, 133797422, 135086622, 133275309, 114364328, 107043718, 101991189, 90338345,
+                        83257441, 80373285, 58617616, 64444167, 46709983, 50818468, 156040895, 57227415)))
+
+
+def bin_genomic_windows(windows, chr_id, num_of_bins):
+    """ PLOT_PANEL.py:96-119 (= BALANCED_ROC_CURVE.py:106-129).  Bins are keyed by their fractional borders
+    (i/num_of_bins, (i+1)/num_of_bins); the value is the half-open run (j, k) of window indices whose midpoints
+    fall in the bin, or None.  Kept quirks: the chromosome's last window never enters a bin (the final run ends
+    at its index), and a bin is only closed when a later window leaves it. """
+    size = CHR_LENGTHS[chr_id] / num_of_bins
+    mids = [(a + b) / 2 for a, b in windows]
+    name = lambda b: (b / num_of_bins, (b + 1) / num_of_bins)
+    out, i = {}, 0
+    for i in range(num_of_bins):                      # empty bins ahead of the first window (:102-105)
+        if mids[0] < (i + 1) * size:
+            break
+        out[name(i)] = None
+    start = 0
+    for k, m in enumerate(mids):                      # (:107-114)
+        if size * i <= m < size * (i + 1):
+            continue
+        out[name(i)] = (start, k)
+        start = k
+        for i in range(i + 1, num_of_bins):
+            if m < (i + 1) * size:
+                break
+            out[name(i)] = None
+    for i in range(i, num_of_bins):                   # the open bin and the empty ones behind it (:116-118)
+        out[name(i)] = (start, k) if start != k else None
+        start = k
+    return out
+
+
+def binning(LLRs_per_window, info, num_of_bins, rounding='plot'):
+    """ PLOT_PANEL.py:121-144 / BALANCED_ROC_CURVE.py:131-154: bin borders, mean LLR and standard error per bin.
+    rounding='plot' sums before dividing by N (PLOT_PANEL.py:44), 'roc' divides each window's sum (BALANCED_ROC_CURVE.py:65). """
+    bins = bin_genomic_windows([*LLRs_per_window], info['chr_id'], num_of_bins)
+    rows = [*LLRs_per_window.values()]
+    Y, E = [], []
+    for run in bins.values():
+        if run:
+            A = rows[run[0]:run[1]]
+            M, N = len(A), len(A[0])
+            mu = sum(sum(r) for r in A) / N if rounding == 'plot' else sum(sum(r) / N for r in A)
+            std = (sum((sum(c) - mu) ** 2 for c in zip(*A)) / (N - 1)) ** .5 / M
+            Y.append(mu / M)
+            E.append(std)
+        else:
+            Y.append(None)
+            E.append(None)
+    return [*bins], Y, E
+
+
+def detect_crossovers(genomic_windows, mean_of_LLRs, variance_of_LLRs, z_score=1.96, lookahead=20, recover=False):
+    """ PLOT_PANEL.detect_crossovers (:146-184) and, with recover=True, detect_crossovers_v2 (:186-245).
+    Walks the cumulative LLR curve; an extremum becomes a crossover once the curve has moved away from it by
+    z_score standard deviations (of the cumulative variance) on BOTH sides, the right side at least `lookahead`
+    windows later, the left side searched backwards from `lookahead` windows before the extremum down to the
+    previous crossover.  v2 also inserts the extremum that must lie between two crossovers of the same kind. """
+    xs = [0.5 * (a + b) for a, b in genomic_windows]
+    ys, vs = [], []
+    for m, v in zip(mean_of_LLRs, variance_of_LLRs):           # itertools.accumulate: running float sums
+        ys.append(m if not ys else ys[-1] + m)
+        vs.append(v if not vs else vs[-1] + v)
+    pts = list(zip(xs, ys, vs))
+    found = {}
+    hi = lo = None            # candidate maximum / minimum as (index, x, y, v)
+    last, last_kind = 0, 0
+
+    def skipped(pick, i0, i1):                                  # recover_skipped_extremum (:199-209)
+        M0, M2, V0, V2 = ys[i0], ys[i1], vs[i0], vs[i1]
+        cands = [((M1 - M0) / (V1 - V0) ** .5 - (M2 - M1) / (V2 - V1) ** .5, X1, M1, V1)
+                 for X1, M1, V1 in pts[i0 + 5:i1 - 4] if V0 != V1 != V2]
+        Z1, X1, M1, V1 = pick(cands, key=lambda t: t[0])
+        return X1, min(abs(M2 - M1) / (V2 - V1) ** .5, abs(M0 - M1) / (V1 - V0) ** .5)
+
+    for idx, (x, y, v) in enumerate(pts):
+        if hi is None or y > hi[2]:
+            hi = (idx, x, y, v)
+        if lo is None or y < lo[2]:
+            lo = (idx, x, y, v)
+        for kind in (+1, -1):                                   # +1: maximum (:161-168), -1: minimum (:170-177)
+            c = hi if kind > 0 else lo
+            if c is None:
+                continue
+            ci, cx, cy, cv = c
+            if not (0 < kind * (cy - y) - z_score * (v - cv) ** .5 and idx - ci >= lookahead):
+                continue
+            for x2, y2, v2 in pts[max(ci - lookahead, last):last:-1]:
+                if 0 < kind * (cy - y2) - z_score * (cv - v2) ** .5:
+                    if recover and last_kind == kind:
+                        rx, rk = skipped(min if kind > 0 else max, last, ci)
+                        found[rx] = rk
+                    found[cx] = min(kind * (cy - y2) / (cv - v2) ** .5, kind * (cy - y) / (v - cv) ** .5)
+                    hi = lo = None
+                    last, last_kind = ci, kind
+                    break
+    return found
+
+
+# --------------------------------------------------------------------------
 # exact-rational cross-check of the closed combinatorial forms (SURVEY 8a-5)
 # --------------------------------------------------------------------------
 
