@@ -11,9 +11,10 @@ collective: (embryo, chromosome, window, draw) units are independent).
 
   value      draws/s with read masks, draw indices and outputs resident in HBM (CUDA events on the
              engine's stream, max over ranks)
-  e2e        the same step through the public host API (Engine.likelihoods_batch -> C-ABI
-             ldpgta_likelihoods_batch) from pinned host buffers: index upload + kernel + result
-             download inside the timed region
+  e2e        the same step through the public host API (Engine.likelihoods_uniform -> C-ABI
+             ldpgta_likelihoods_uniform) from pinned host buffers: index upload + validation + kernel +
+             result download inside the timed region; e2e.offsets_api_ms_per_step is the same step
+             through ldpgta_likelihoods_batch (ragged API: also reads one offset per draw)
   roofline   dominant kernel k_small<4,8,10>: algorithmic bytes / measured launch time vs the
              measured HBM copy peak; int_roofline: algorithmic AND+POPC word-ops vs the POPC peak
   cpu_baseline  the CPython oracle port of the reference loop (ANEUPLOIDY_TEST.py:277-286) on a
@@ -348,6 +349,9 @@ def main():
     offsets = np.arange(0, n_draws * n + 1, n, dtype=np.int64)
 
     def step_e2e():
+        eng.likelihoods_uniform(kind, pin_idx.array, out=pin_out.array)
+
+    def step_e2e_offsets():
         eng.likelihoods_batch(kind, pin_idx.array.reshape(-1), offsets, out=pin_out.array)
 
     def barrier():
@@ -400,6 +404,15 @@ def main():
         e2e_s = float(t.item())
     e2e_value = world * n_draws * args.steps / e2e_s
     clocks = sampler.stop()
+    first_pass = pin_out.array.copy()
+    pin_out.array[:] = 0
+    for _ in range(args.warmup):
+        step_e2e_offsets()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e_offsets()
+    e2e_offsets_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+    assert np.array_equal(first_pass, pin_out.array), 'the two host APIs disagree'
     resident = d_out.cpu().numpy()
     assert np.array_equal(resident, pin_out.array), 'resident and host-API results differ'
 
@@ -482,7 +495,8 @@ def main():
         'draws_per_step_per_gpu': int(n_draws),
         'e2e': {'value': e2e_value, 'unit': 'window-likelihoods/s', 'h2d_bytes_per_step': int(pin_idx.array.nbytes),
                 'd2h_bytes_per_step': int(pin_out.array.nbytes), 'ms_per_step': 1e3 * e2e_s / args.steps,
-                'api': 'Engine.likelihoods_batch -> ldpgta_likelihoods_batch (pinned host buffers)'},
+                'api': 'Engine.likelihoods_uniform -> ldpgta_likelihoods_uniform (pinned host buffers)',
+                'offsets_api_ms_per_step': e2e_offsets_ms},
         'gpu_launches': int(launches),
         'roofline': {'bound': 'hbm', 'kernel': 'k_small<%d,8,10>' % n if n <= 4 else ('k_mid<%d,5>' % n if n <= 6 else 'k_general (n=%d)' % n), 'achieved': achieved_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
                      'frac': achieved_gbs / hbm_peak, 'traffic': traffic, 'peak_source': peak_src,

@@ -131,6 +131,12 @@ int ldpgta_get_likelihoods(ldpgta_ctx *ctx, int model_kind, const int32_t *allel
 int ldpgta_likelihoods_batch(ldpgta_ctx *ctx, int model_kind, const int32_t *read_idx,
                              const int64_t *draw_offsets, int64_t n_draws, const double *proportions,
                              double *out);
+/* The same for draws that all hold n reads (n = min(R-1, max_reads), ANEUPLOIDY_TEST.py:229, is
+ * one value for all windows with R > max_reads): read_idx[n_draws][n], no offsets.  With
+ * page-locked buffers (ldpgta_host_alloc) the call streams chunks through upload -> index
+ * validation + kernel -> download on three streams; this is the call bench.py times for `e2e`. */
+int ldpgta_likelihoods_uniform(ldpgta_ctx *ctx, int model_kind, int n, const int32_t *read_idx,
+                               int64_t n_draws, const double *proportions, double *out);
 
 /* Same computation for draws of one size n with everything already resident in HBM:
  * read_idx_dev[n_draws][n], out_dev[n_draws][4].  Asynchronous on the context's stream;

@@ -167,6 +167,7 @@ struct ldpgta_ctx {
     double *d_llr = nullptr;  size_t d_llr_bytes = 0;
     int64_t llr_draws = -1, llr_windows = -1;
     int64_t *d_llr_off = nullptr;  size_t d_llr_off_bytes = 0;
+    unsigned int *d_flag = nullptr, *h_flag = nullptr;     // device-side index validation of the pipelined host path
 
     // colourings of the high reads used by the three-block polynomial, one list per h = n - 5 (built on first use)
     uint64_t *hi_terms[14] = {};

@@ -341,4 +341,28 @@ __global__ void k_bin_stats(const double *__restrict__ x, int64_t n_draws, const
     }
 }
 
+// validation of a batch's read indices on the device (the host path used to scan them before the first copy):
+// an index outside [0, n_reads) is replaced by 0 and reported through *flag, the caller then fails the whole call.
+__global__ void k_sanitize_idx(int32_t *__restrict__ idx, int64_t count, uint32_t n_reads, unsigned int *__restrict__ flag)
+{
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t quads = ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) ? count / 4 : 0;
+    bool bad = false;
+    for (int64_t i = tid; i < quads; i += stride) {
+        int4 v = reinterpret_cast<int4 *>(idx)[i];
+        const bool b = (uint32_t)v.x >= n_reads || (uint32_t)v.y >= n_reads || (uint32_t)v.z >= n_reads || (uint32_t)v.w >= n_reads;
+        if (b) {
+            v.x = (uint32_t)v.x >= n_reads ? 0 : v.x;
+            v.y = (uint32_t)v.y >= n_reads ? 0 : v.y;
+            v.z = (uint32_t)v.z >= n_reads ? 0 : v.z;
+            v.w = (uint32_t)v.w >= n_reads ? 0 : v.w;
+            reinterpret_cast<int4 *>(idx)[i] = v;
+            bad = true;
+        }
+    }
+    for (int64_t i = quads * 4 + tid; i < count; i += stride)
+        if ((uint32_t)idx[i] >= n_reads) { idx[i] = 0; bad = true; }
+    if (bad) atomicOr(flag, 1u);
+}
+
 }  // namespace ldpgta

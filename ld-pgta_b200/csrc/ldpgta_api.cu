@@ -64,6 +64,8 @@ static int ensure_pipeline(ldpgta_ctx *c, int n_chunks)
 {
     if (!c->s_in) LDPGTA_CUDA(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
     if (!c->s_out) LDPGTA_CUDA(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    if (!c->d_flag) LDPGTA_CUDA(cudaMalloc((void **)&c->d_flag, 16));
+    if (!c->h_flag) LDPGTA_CUDA(cudaMallocHost((void **)&c->h_flag, 16));
     while ((int)c->ev_in.size() < n_chunks) {
         cudaEvent_t a, b;
         LDPGTA_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
@@ -74,11 +76,12 @@ static int ensure_pipeline(ldpgta_ctx *c, int n_chunks)
     return 0;
 }
 
-static bool is_pinned_or_device(const void *p)
+// page-locked (or managed) host memory: usable by asynchronous copies without staging and readable on the host
+static bool is_page_locked(const void *p)
 {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
 }
 
 // (re)computes the per-read popcount table of group g after its masks changed
@@ -138,6 +141,71 @@ static int run_uniform(ldpgta_ctx *c, int kind, int n, const int32_t *idx_dev, i
     a.kind = kind; a.n = n; a.kl = a.kh = a.wc = 0;
     a.idx = idx_dev; a.n_draws = n_draws; a.pos = pos_dev; a.out = out_dev; a.counts_out = counts_dev;
     return launch_general(c, a);
+}
+
+// message for the first read index outside the table (slow path, only after a failed validation)
+static int fail_bad_index(const ldpgta_ctx *c, const int32_t *read_idx, int64_t nnz)
+{
+    for (int64_t k = 0; k < nnz; ++k)
+        if (read_idx[k] < 0 || read_idx[k] >= c->n_reads)
+            return fail(LDPGTA_E_INVALID, "read index %d at %lld is outside 0..%lld", read_idx[k], (long long)k, (long long)c->n_reads - 1);
+    return fail(LDPGTA_E_INVALID, "a read index is outside 0..%lld", (long long)c->n_reads - 1);
+}
+
+// Uniform draws from page-locked host buffers: chunks flow through upload -> validation + kernel -> download on
+// three streams.  Nothing is scanned on the host before the first copy: indices are validated on the device, and
+// draw_offsets (optional) are checked chunk by chunk while earlier chunks are in flight.
+// Returns 0, a negative error, or 1 when draw_offsets turn out not to be uniform (the caller regroups).
+static int run_pipelined(ldpgta_ctx *c, int kind, int n0, const int32_t *read_idx, const int64_t *draw_offsets, int64_t n_draws,
+                         const double *proportions, double *out)
+{
+    static const int max_chunks = [] { const char *e = getenv("LDPGTA_CHUNKS"); return e ? std::max(1, atoi(e)) : 8; }();
+    const size_t idx_bytes = ((size_t)n_draws * n0 * 4 + 15) & ~(size_t)15;
+    if (int rc = ensure_dev(c, idx_bytes + (size_t)n_draws * 32)) return rc;
+    int32_t *d_idx = (int32_t *)c->d_buf;
+    double *d_out = (double *)((char *)c->d_buf + idx_bytes);
+    const int64_t n_chunks = std::max<int64_t>(1, std::min<int64_t>(max_chunks, n_draws / 32768));
+    const int64_t per = ((n_draws + n_chunks - 1) / n_chunks + 63) & ~(int64_t)63;
+    if (int rc = ensure_pipeline(c, (int)n_chunks + 1)) return rc;
+    const uint32_t lim = (uint32_t)std::min<int64_t>(c->n_reads, 0x7fffffff);
+    LDPGTA_CUDA(cudaMemsetAsync(c->d_flag, 0, 4, c->stream));
+    int ci = 0, rc = 0;
+    for (int64_t d0 = 0; d0 < n_draws; d0 += per, ++ci) {
+        const int64_t nd = std::min(per, n_draws - d0);
+        if (draw_offsets) {
+            int64_t differs = 0;
+            const int64_t base = draw_offsets[d0] - d0 * n0;
+            for (int64_t d = d0; d <= d0 + nd; ++d) differs |= (draw_offsets[d] - d * n0) ^ base;
+            if (differs | base) { rc = 1; break; }
+        }
+        LDPGTA_CUDA(cudaMemcpyAsync(d_idx + d0 * n0, read_idx + d0 * n0, (size_t)nd * n0 * 4, cudaMemcpyHostToDevice, c->s_in));
+        LDPGTA_CUDA(cudaEventRecord(c->ev_in[ci], c->s_in));
+        LDPGTA_CUDA(cudaStreamWaitEvent(c->stream, c->ev_in[ci], 0));
+        const int64_t cnt = nd * n0;
+        k_sanitize_idx<<<(unsigned)std::min<int64_t>((cnt / 4 + 255) / 256 + 1, (int64_t)c->sm_count * 4), 256, 0, c->stream>>>(
+            d_idx + d0 * n0, cnt, lim, c->d_flag);
+        c->launches++;
+        if ((rc = run_uniform(c, kind, n0, d_idx + d0 * n0, nd, nullptr, proportions, d_out + 4 * d0, nullptr))) break;
+        LDPGTA_CUDA(cudaEventRecord(c->ev_k[ci], c->stream));
+        LDPGTA_CUDA(cudaStreamWaitEvent(c->s_out, c->ev_k[ci], 0));
+        LDPGTA_CUDA(cudaMemcpyAsync(out + 4 * d0, d_out + 4 * d0, (size_t)nd * 32, cudaMemcpyDeviceToHost, c->s_out));
+    }
+    if (rc == 0) LDPGTA_CUDA(cudaMemcpyAsync(c->h_flag, c->d_flag, 4, cudaMemcpyDeviceToHost, c->s_out));
+    LDPGTA_CUDA(cudaStreamSynchronize(c->s_in));
+    LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
+    LDPGTA_CUDA(cudaStreamSynchronize(c->s_out));
+    if (rc) return rc;
+    if (*c->h_flag) return fail_bad_index(c, read_idx, n_draws * n0);
+    return 0;
+}
+
+static int check_uniform_size(int kind, int64_t n)
+{
+    if (n < 2 || n > MAXN)
+        return fail(LDPGTA_E_UNSUPPORTED, "draw 0 has %lld reads, supported range is 2..%d", (long long)n, MAXN);
+    if (kind == LDPGTA_DISTANT_ADMIXTURE && n == 5)
+        return fail(LDPGTA_E_UNSUPPORTED, "distant_admixture has no likelihoods5 (reference: DISTANT_ADMIXTURE_MODELS.py:312-313 raises AttributeError)");
+    return 0;
 }
 
 }  // namespace ldpgta
@@ -208,6 +276,8 @@ int ldpgta_destroy(ldpgta_ctx *c)
     if (c->allele_complement) cudaFree(c->allele_complement);
     if (c->d_buf) cudaFree(c->d_buf);
     if (c->d_llr) cudaFree(c->d_llr);
+    if (c->d_flag) cudaFree(c->d_flag);
+    if (c->h_flag) cudaFreeHost(c->h_flag);
     if (c->d_llr_off) cudaFree(c->d_llr_off);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -598,6 +668,30 @@ int ldpgta_likelihoods_uniform_dev(ldpgta_ctx *c, int kind, int n, const int32_t
     return run_uniform(c, kind, n, read_idx_dev, n_draws, nullptr, proportions, out_dev, nullptr);
 }
 
+int ldpgta_likelihoods_uniform(ldpgta_ctx *c, int kind, int n, const int32_t *read_idx, int64_t n_draws,
+                               const double *proportions, double *out)
+{
+    if (!c || !out || n_draws < 0) return fail(LDPGTA_E_INVALID, "bad arguments");
+    LDPGTA_CUDA(cudaSetDevice(c->device));
+    if (int rc = check_kind(c, kind, proportions)) return rc;
+    if (int rc = check_uniform_size(kind, n)) return rc;
+    if (n_draws == 0) return 0;
+    if (!read_idx) return fail(LDPGTA_E_INVALID, "null read_idx");
+    const bool pin_in = is_page_locked(read_idx), pin_out = is_page_locked(out);
+    if (pin_in && pin_out) return run_pipelined(c, kind, n, read_idx, nullptr, n_draws, proportions, out);
+    // pageable buffers go through the context's page-locked staging area
+    const size_t idx_b = ((size_t)n_draws * n * 4 + 63) & ~(size_t)63, out_b = (size_t)n_draws * 32;
+    if (int rc = ensure_pin(c, idx_b + out_b)) return rc;
+    int32_t *h_idx = (int32_t *)c->h_pin;
+    double *h_out = (double *)((char *)c->h_pin + idx_b);
+    const int32_t *src = read_idx;
+    if (!pin_in) { memcpy(h_idx, read_idx, (size_t)n_draws * n * 4); src = h_idx; }
+    const int rc = run_pipelined(c, kind, n, src, nullptr, n_draws, proportions, pin_out ? out : h_out);
+    if (rc) return rc;
+    if (!pin_out) memcpy(out, h_out, out_b);
+    return 0;
+}
+
 int ldpgta_likelihoods_batch(ldpgta_ctx *c, int kind, const int32_t *read_idx, const int64_t *draw_offsets, int64_t n_draws,
                              const double *proportions, double *out)
 {
@@ -608,6 +702,17 @@ int ldpgta_likelihoods_batch(ldpgta_ctx *c, int kind, const int32_t *read_idx, c
     if (!read_idx) return fail(LDPGTA_E_INVALID, "null read_idx");
     if (draw_offsets[0] != 0) return fail(LDPGTA_E_INVALID, "draw_offsets must start at 0");
 
+    // page-locked caller buffers holding draws of one size: the pipelined path, nothing scanned up front
+    {
+        const int64_t n0w = draw_offsets[1] - draw_offsets[0];
+        if (n_draws >= 65536 && draw_offsets[n_draws] == n_draws * n0w && n0w >= 2 && n0w <= MAXN &&
+            is_page_locked(read_idx) && is_page_locked(out)) {
+            if (int rc = check_uniform_size(kind, n0w)) return rc;
+            const int rc = run_pipelined(c, kind, (int)n0w, read_idx, draw_offsets, n_draws, proportions, out);
+            if (rc <= 0) return rc;                  // 1: sizes differ after all, regroup below
+        }
+    }
+
     // size classes (branch-free first pass: the common batch has one draw size)
     int64_t per_n[MAXN + 1] = {};
     const int64_t n0w = draw_offsets[1] - draw_offsets[0];
@@ -616,10 +721,7 @@ int ldpgta_likelihoods_batch(ldpgta_ctx *c, int kind, const int32_t *read_idx, c
     const bool uniform = differs == 0;
     const int n0 = (int)n0w;
     if (uniform) {
-        if (n0w < 2 || n0w > MAXN)
-            return fail(LDPGTA_E_UNSUPPORTED, "draw 0 has %lld reads, supported range is 2..%d", (long long)n0w, MAXN);
-        if (kind == LDPGTA_DISTANT_ADMIXTURE && n0 == 5)
-            return fail(LDPGTA_E_UNSUPPORTED, "distant_admixture has no likelihoods5 (reference: DISTANT_ADMIXTURE_MODELS.py:312-313 raises AttributeError)");
+        if (int rc = check_uniform_size(kind, n0w)) return rc;
         per_n[n0] = n_draws;
     } else {
         for (int64_t d = 0; d < n_draws; ++d) {
@@ -636,10 +738,7 @@ int ldpgta_likelihoods_batch(ldpgta_ctx *c, int kind, const int32_t *read_idx, c
         const uint32_t lim = (uint32_t)std::min<int64_t>(c->n_reads, 0x7fffffff);
         uint32_t bad = 0;
         for (int64_t k = 0; k < nnz; ++k) bad |= (uint32_t)((uint32_t)read_idx[k] >= lim);     // negative indices wrap above lim
-        if (bad)
-            for (int64_t k = 0; k < nnz; ++k)
-                if (read_idx[k] < 0 || read_idx[k] >= c->n_reads)
-                    return fail(LDPGTA_E_INVALID, "read index %d at %lld is outside 0..%lld", read_idx[k], (long long)k, (long long)c->n_reads - 1);
+        if (bad) return fail_bad_index(c, read_idx, nnz);
     }
 
     const size_t idx_bytes = ((size_t)nnz * 4 + 15) & ~(size_t)15;
@@ -650,29 +749,9 @@ int ldpgta_likelihoods_batch(ldpgta_ctx *c, int kind, const int32_t *read_idx, c
     int64_t *d_pos = (int64_t *)((char *)c->d_buf + idx_bytes);
     double *d_out = (double *)((char *)c->d_buf + idx_bytes + pos_bytes);
 
-    if (uniform && is_pinned_or_device(read_idx) && is_pinned_or_device(out)) {
-        // page-locked caller buffers: chunks flow through upload -> kernel -> download on three streams
-        const int64_t n_chunks = std::max<int64_t>(1, std::min<int64_t>(8, n_draws / 65536));
-        const int64_t per = ((n_draws + n_chunks - 1) / n_chunks + 63) & ~(int64_t)63;
-        if (int rc = ensure_pipeline(c, (int)n_chunks)) return rc;
-        int ci = 0;
-        for (int64_t d0 = 0; d0 < n_draws; d0 += per, ++ci) {
-            const int64_t nd = std::min(per, n_draws - d0);
-            LDPGTA_CUDA(cudaMemcpyAsync(d_idx + d0 * n0, read_idx + d0 * n0, (size_t)nd * n0 * 4, cudaMemcpyHostToDevice, c->s_in));
-            LDPGTA_CUDA(cudaEventRecord(c->ev_in[ci], c->s_in));
-            LDPGTA_CUDA(cudaStreamWaitEvent(c->stream, c->ev_in[ci], 0));
-            if (int rc = run_uniform(c, kind, n0, d_idx + d0 * n0, nd, nullptr, proportions, d_out + 4 * d0, nullptr)) return rc;
-            LDPGTA_CUDA(cudaEventRecord(c->ev_k[ci], c->stream));
-            LDPGTA_CUDA(cudaStreamWaitEvent(c->s_out, c->ev_k[ci], 0));
-            LDPGTA_CUDA(cudaMemcpyAsync(out + 4 * d0, d_out + 4 * d0, (size_t)nd * 32, cudaMemcpyDeviceToHost, c->s_out));
-        }
-        LDPGTA_CUDA(cudaStreamSynchronize(c->s_out));
-        LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
-        return 0;
-    }
     if (uniform) {
         const void *src = read_idx;
-        if (!is_pinned_or_device(read_idx)) {
+        if (!is_page_locked(read_idx)) {
             if (int rc = ensure_pin(c, std::max(idx_bytes, out_bytes))) return rc;
             memcpy(c->h_pin, read_idx, (size_t)nnz * 4);
             src = c->h_pin;
@@ -703,7 +782,7 @@ int ldpgta_likelihoods_batch(ldpgta_ctx *c, int kind, const int32_t *read_idx, c
                 if (int rc = run_uniform(c, kind, n, d_idx + idx_start[n], per_n[n], d_pos + pos_start[n], proportions, d_out, nullptr))
                     return rc;
     }
-    if (is_pinned_or_device(out)) {
+    if (is_page_locked(out)) {
         LDPGTA_CUDA(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, c->stream));
         LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
     } else {

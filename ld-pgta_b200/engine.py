@@ -191,6 +191,19 @@ class Engine:
         N.check(self.lib.ldpgta_likelihoods_batch(self._ctx, kind, N.ptr(idx), N.ptr(off), nd, N.ptr(prop), N.ptr(out)))
         return out
 
+    def likelihoods_uniform(self, kind, read_idx, proportions=None, out=None):
+        """ likelihoods_batch for draws of one size: read_idx[n_draws][n] (host; page-locked PinnedArray buffers
+        stream through the copy/compute pipeline).  Returns float64[n_draws, 4]. """
+        idx = np.ascontiguousarray(read_idx, dtype=np.int32)
+        if idx.ndim != 2:
+            raise ValueError('read_idx must be [n_draws][n]')
+        nd, n = idx.shape
+        if out is None:
+            out = np.empty((nd, 4), dtype=np.float64)
+        prop = None if proportions is None else np.ascontiguousarray(proportions, dtype=np.float64)
+        N.check(self.lib.ldpgta_likelihoods_uniform(self._ctx, kind, n, N.ptr(idx), nd, N.ptr(prop), N.ptr(out)))
+        return out
+
     def likelihoods_uniform_dev(self, kind, n, idx_dev_ptr, n_draws, out_dev_ptr, proportions=None):
         """ Device-resident variant (asynchronous on the engine's stream). """
         prop = None if proportions is None else np.ascontiguousarray(proportions, dtype=np.float64)

@@ -575,3 +575,52 @@ def test_command_line_interface(tmp_path, golden_inputs):
     assert list(lik) == list(out['likelihoods']) and info['subsamples'] == 8 and info['ancestral_makeup'] == {'EUR'}
     bad = subprocess.run([sys.executable, script, 'a', 'b', 'c', 'G0'], capture_output=True, text=True, timeout=300)
     assert bad.returncode != 0 and 'Invalid argument supplied for ancestral makeup' in bad.stderr
+
+
+def test_uniform_host_api_pipeline():
+    """ ldpgta_likelihoods_uniform: draws of one size as a 2-D array, page-locked and pageable buffers, equal to the
+    ragged API and to the oracle; a bad index is caught by the device-side validation and named in the error. """
+    rng = np.random.default_rng(77)
+    n_hap, n_reads = 5008, 3000
+    rows = ld_rows(rng, n_reads, n_hap)
+    with L.Engine([n_hap]) as eng:
+        eng.upload_read_masks(0, rows)
+        for n, n_draws in ((4, 200000), (3, 70001), (6, 66000), (9, 1500)):
+            idx = rng.integers(0, n_reads, size=(n_draws, n), dtype=np.int32)
+            idx[:, 1:] = (idx[:, :1] + np.arange(1, n, dtype=np.int32) * 7) % n_reads       # distinct reads in a draw
+            off = np.arange(0, n_draws * n + 1, n, dtype=np.int64)
+            ragged = eng.likelihoods_batch(L.HOMOGENEOUS, idx.reshape(-1), off)
+            pageable = eng.likelihoods_uniform(L.HOMOGENEOUS, idx)
+            pin_i, pin_o = L.PinnedArray((n_draws, n), np.int32), L.PinnedArray((n_draws, 4), np.float64)
+            pin_i.array[:] = idx
+            pinned = eng.likelihoods_uniform(L.HOMOGENEOUS, pin_i.array, out=pin_o.array)
+            via_offsets = eng.likelihoods_batch(L.HOMOGENEOUS, pin_i.array.reshape(-1), off, out=np.zeros_like(pin_o.array))
+            assert np.array_equal(ragged, pageable) and np.array_equal(ragged, pinned) and np.array_equal(ragged, via_offsets)
+            sample = rng.choice(n_draws, 300, replace=False)
+            ref = C.batch([rows], [n_hap], idx[sample].reshape(-1), np.arange(0, 300 * n + 1, n), 0)
+            assert max_rel(ragged[sample], ref) < LIK_TOL
+            # one bad index somewhere in the middle: reported with its position, from both kinds of buffer
+            k = n_draws // 2 * n + 1
+            for bad in (n_reads, -1):
+                pin_i.array.reshape(-1)[k] = bad
+                with pytest.raises(L.LdpgtaError, match=r'read index %d at %d is outside' % (bad, k)):
+                    eng.likelihoods_uniform(L.HOMOGENEOUS, pin_i.array, out=pin_o.array)
+                with pytest.raises(L.LdpgtaError, match=r'read index %d at %d is outside' % (bad, k)):
+                    eng.likelihoods_uniform(L.HOMOGENEOUS, np.array(pin_i.array))
+                if n_draws >= 65536:
+                    with pytest.raises(L.LdpgtaError, match=r'read index %d at %d is outside' % (bad, k)):
+                        eng.likelihoods_batch(L.HOMOGENEOUS, pin_i.array.reshape(-1), off, out=pin_o.array)
+            pin_i.array[:] = idx
+            assert np.array_equal(eng.likelihoods_uniform(L.HOMOGENEOUS, pin_i.array, out=pin_o.array), ragged)
+            # offsets that look uniform at both ends but are not: the pipelined path hands over to the regrouping path
+            if n_draws >= 65536 and n == 4:
+                off2 = off.copy()
+                off2[n_draws // 3] += 1                       # draw sizes 5 and 3 next to each other
+                got = eng.likelihoods_batch(L.HOMOGENEOUS, pin_i.array.reshape(-1), off2, out=pin_o.array)
+                ref2 = eng.likelihoods_batch(L.HOMOGENEOUS, idx.reshape(-1), off2)
+                assert np.array_equal(got, ref2)
+        with pytest.raises(L.LdpgtaError, match='supported range'):
+            eng.likelihoods_uniform(L.HOMOGENEOUS, np.zeros((4, 1), np.int32))
+        with pytest.raises(ValueError):
+            eng.likelihoods_uniform(L.HOMOGENEOUS, np.zeros(8, np.int32))
+        assert eng.likelihoods_uniform(L.HOMOGENEOUS, np.zeros((0, 4), np.int32)).shape == (0, 4)
