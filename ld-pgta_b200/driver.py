@@ -407,6 +407,38 @@ def statistics(likelihoods, genomic_windows, device=0):
             'LLRs_per_genomic_window': per_window, 'LLRs_per_chromosome': per_chrom}
 
 
+def packed_bootstrap(obs_tab, leg_tab, hap_tab, number_of_haplotypes, ancestral_makeup, window_size, subsamples, offset,
+                     min_reads, max_reads, min_score, min_HF, device=0, panel=None, rng=None):
+    """ bootstrap() + statistics() through packed.PackedSample; returns the reference's structures
+    (likelihoods, genomic_windows, fraction_of_matches, statistics dict). """
+    from .engine import ResidentPanel
+    from .packed import PackedSample
+    own_panel = panel is None
+    if own_panel:
+        order = list(ancestral_makeup) if type(ancestral_makeup) == dict else list(hap_tab)
+        panel = ResidentPanel(leg_tab, {g: hap_tab[g] for g in order}, number_of_haplotypes, device=device)
+    try:
+        with PackedSample(obs_tab, panel, ancestral_makeup, min_HF) as sample:
+            res = sample.run(window_size, subsamples, offset, min_reads, max_reads, min_score, rng=rng)
+            cls = {N.HOMOGENEOUS: homogeneous, N.RECENT_ADMIXTURE: recent_admixture, N.DISTANT_ADMIXTURE: distant_admixture}[sample.kind]
+            likelihoods, genomic_windows, matches = res.as_reference(cls.tuple_type)
+    finally:
+        if own_panel:
+            panel.close()
+    if not likelihoods:
+        return likelihoods, genomic_windows, matches, {'num_of_windows': 0}
+    if min(len(v) for v in likelihoods.values()) < 2:
+        raise StatisticsError('variance requires at least two data points')
+    window_size_mean, window_size_std = mean_and_std((j - i + 1 for (i, j) in likelihoods))
+    reads_mean, reads_std = mean_and_std((len(read_IDs) for window, read_IDs in genomic_windows.items() if window in likelihoods))
+    mv = res.window_mean_var.tolist()
+    per_window = {pair: {w: tuple(mv[p][k]) for k, w in enumerate(likelihoods)} for p, pair in enumerate(LLR_PAIRS)}
+    stats = {'num_of_windows': len(likelihoods), 'reads_mean': reads_mean, 'reads_std': reads_std,
+             'window_size_mean': window_size_mean, 'window_size_std': window_size_std,
+             'LLRs_per_genomic_window': per_window, 'LLRs_per_chromosome': res.llr_per_chromosome()}
+    return likelihoods, genomic_windows, matches, stats
+
+
 def print_summary(obs_filename, info):
     """ ANEUPLOIDY_TEST.print_summary (:327-343). """
     S = info['statistics']
@@ -455,7 +487,8 @@ def aneuploidy_test(obs_filename, leg_filename, hap_filename, ancestral_makeup, 
                     max_reads, min_score, min_HF, output_filename, compress, **kwargs):
     """ ANEUPLOIDY_TEST.aneuploidy_test (:368-429): same arguments, files and return value.
     kwargs: seed, model (MODELS*.p path; optional here -- the device needs no tables), output_dir, device,
-    panel (ResidentPanel shared by samples), fast_draws (vectorised numpy draws instead of random.sample). """
+    panel (ResidentPanel shared by samples), fast_draws (vectorised numpy draws instead of random.sample),
+    packed (the array-native route of packed.py: same files and results, draws from a numpy Generator). """
     time0 = time.time()
     random.seed(a=kwargs.get('seed', None), version=2)
 
@@ -480,14 +513,21 @@ def aneuploidy_test(obs_filename, leg_filename, hap_filename, ancestral_makeup, 
 
     device = kwargs.get('device', 0)
     fast_rng = np.random.default_rng(kwargs.get('seed', None)) if kwargs.get('fast_draws', False) else None
-    likelihoods, genomic_windows, matched_alleles = bootstrap(obs_tab, leg_tab, hap_tab, number_of_haplotypes, ancestral_makeup,
-                                                              models_dict, window_size, subsamples, offset, min_reads,
-                                                              max_reads, min_score, min_HF, device=device,
-                                                              panel=kwargs.get('panel', None), fast_rng=fast_rng)
+    if kwargs.get('packed', False):
+        likelihoods, genomic_windows, matched_alleles, stats = packed_bootstrap(
+            obs_tab, leg_tab, hap_tab, number_of_haplotypes, ancestral_makeup, window_size, subsamples, offset, min_reads,
+            max_reads, min_score, min_HF, device=device, panel=kwargs.get('panel', None),
+            rng=np.random.default_rng(kwargs.get('seed', None)))
+    else:
+        likelihoods, genomic_windows, matched_alleles = bootstrap(obs_tab, leg_tab, hap_tab, number_of_haplotypes, ancestral_makeup,
+                                                                  models_dict, window_size, subsamples, offset, min_reads,
+                                                                  max_reads, min_score, min_HF, device=device,
+                                                                  panel=kwargs.get('panel', None), fast_rng=fast_rng)
+        stats = statistics(likelihoods, genomic_windows, device=device)
     some_statistics = {'matched_alleles': matched_alleles, 'runtime': time.time() - time0}
     info.update({'ancestral_makeup': ancestral_makeup, 'window_size': window_size, 'subsamples': subsamples, 'offset': offset,
                  'min_reads': min_reads, 'max_reads': max_reads, 'min_score': min_score, 'min_HF': min_HF,
-                 'statistics': {**statistics(likelihoods, genomic_windows, device=device), **some_statistics}})
+                 'statistics': {**stats, **some_statistics}})
     if output_filename != None:
         save_results(likelihoods, info, compress, obs_filename, output_filename, kwargs.get('output_dir', 'results'))
     print_summary(obs_filename, info)

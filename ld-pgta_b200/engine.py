@@ -45,6 +45,8 @@ class ResidentPanel:
         self.n_hap = [int(number_of_haplotypes_per_group[g]) for g in self.groups]
         self.device = device
         self.n_snps = len(leg_tab)
+        self.last_group = list(number_of_haplotypes_per_group)[-1]      # weights the read scores (ANEUPLOIDY_TEST.py:181-184)
+        self._leg_tab, self._legend = leg_tab, None
         for g in self.groups:
             if len(hap_tab_per_group[g]) != self.n_snps:
                 raise Exception('Error: the number of SNPs in the LEGEND file differ from the number of SNPs in the HAP file.')
@@ -58,6 +60,14 @@ class ResidentPanel:
             for lo in range(0, self.n_snps, chunk):
                 rows = pack_ints(tab[lo:lo + chunk], self.n_hap[gi])
                 N.check(self.lib.ldpgta_panel_upload(self._p, gi, lo, N.ptr(np.ascontiguousarray(rows)), rows.shape[0]))
+
+    @property
+    def legend(self):
+        """ The legend as arrays (packed.PackedLegend), built on first use. """
+        if self._legend is None:
+            from .packed import PackedLegend
+            self._legend = PackedLegend(self._leg_tab)
+        return self._legend
 
     def close(self):
         if self._p is not None and self._p.value:

@@ -1,0 +1,306 @@
+"""
+packed -- the array-native route through one (sample, chromosome): SURVEY 8(f) rows 2 and 3.
+
+The reference turns the observation table into dicts of Python objects before the first likelihood is computed
+(build_hap_dict HOMOGENOUES_MODELS.py:76-100, build_reads_dict / build_overlaps_dict / build_score_dict /
+build_gw_dict ANEUPLOIDY_TEST.py:118-224); on a GPU those dict stages cost a thousand times more than the
+likelihoods.  Here the same quantities are index arrays:
+
+    PackedLegend     legend positions / ref / alt as arrays (once per panel)
+    PackedSample     obs_tab matched against a ResidentPanel: allele table (legend row + complement flag, gathered
+                     on the device), reads as CSR lists of allele rows (read masks built on the device), read scores
+                     from the device, fraction_of_matches
+    windows()        build_gw_dict as arrays: window borders + CSR of read rows, fixed or adaptive, with the
+                     reference's quirks (offset, adaptive growth in 10 kbp steps, last window dropped, empty
+                     windows kept)
+    plan()           all bootstrap draws of all windows by vectorised sampling without replacement
+    run()            draws -> likelihoods on the device -> LLR statistics on the device -> PackedResult, which can
+                     also be unfolded into the reference's (likelihoods, genomic_windows, fraction_of_matches)
+
+Draws come from a numpy Generator, not from random.sample on hash-ordered tuples, so a packed run is statistically
+equivalent to the reference's, not stream-identical (the drop-in ANEUPLOIDY_TEST.bootstrap keeps the stream).
+Everything else is pinned to the golden vectors in tests/test_packed.py (read scores, windows, fraction of matches,
+and likelihoods for replayed draws).
+"""
+from math import comb
+
+import numpy as np
+
+from . import _native as N
+from .engine import Engine, LLR_PAIRS, finish_chromosome
+
+
+class PackedLegend:
+    """ LEGEND rows (chr_id, pos, ref, alt) as arrays.  Lookup keeps the reference's dict semantics: of several rows
+    with one position the last wins (HOMOGENOUES_MODELS.py:84). """
+
+    def __init__(self, leg_tab):
+        n = len(leg_tab)
+        self.codes = {}
+        code = self.codes.setdefault
+        pos = np.fromiter((l[1] for l in leg_tab), dtype=np.int64, count=n)
+        ref = np.fromiter((code(l[2], len(self.codes)) for l in leg_tab), dtype=np.int32, count=n)
+        alt = np.fromiter((code(l[3], len(self.codes)) for l in leg_tab), dtype=np.int32, count=n)
+        order = np.argsort(pos, kind='stable')
+        self.pos, self.ref, self.alt, self.row = pos[order], ref[order], alt[order], order.astype(np.int64)
+        self.n_snps = n
+
+    def encode_bases(self, bases, count):
+        """ base strings -> codes; strings the legend never uses get -1 (they can not match). """
+        get = self.codes.get
+        return np.fromiter((get(b, -1) for b in bases), dtype=np.int32, count=count)
+
+    def match(self, pos, base):
+        """ (keep, legend row, complement flag) per observation: an observed base that equals ALT selects the panel
+        row, one that equals REF its complement, anything else is a mismatch (HOMOGENOUES_MODELS.py:89-96). """
+        j = np.searchsorted(self.pos, pos, side='right') - 1
+        hit = (j >= 0) & (self.pos[np.maximum(j, 0)] == pos)
+        j = np.where(hit, j, 0)
+        is_alt = hit & (base == self.alt[j]) & (base >= 0)
+        is_ref = hit & ~is_alt & (base == self.ref[j]) & (base >= 0)
+        return is_alt | is_ref, self.row[j], is_ref
+
+
+def sample_without_replacement(rng, R, k):
+    """ k distinct integers of range(R[d]) for every draw d (Floyd's algorithm, vectorised over draws);
+    uniform over k-subsets, order inside a draw arbitrary (the likelihoods are symmetric in the reads). """
+    R = np.asarray(R, dtype=np.int64)
+    out = np.empty((len(R), k), dtype=np.int64)
+    for i in range(k):
+        top = R - k + i                                   # Floyd: t uniform in [0, top], take top instead if already chosen
+        t = (rng.random(len(R)) * (top + 1)).astype(np.int64)
+        np.minimum(t, top, out=t)
+        if i:
+            dup = (out[:, :i] == t[:, None]).any(axis=1)
+            t = np.where(dup, top, t)
+        out[:, i] = t
+    return out
+
+
+class PackedWindows:
+    """ Genomic windows of one chromosome: borders[K][2] = (a, b-1) as in gw_dict's keys, CSR offsets / read rows. """
+
+    def __init__(self, borders, offsets, reads):
+        self.borders, self.offsets, self.reads = borders, offsets, reads
+
+    def __len__(self):
+        return len(self.borders)
+
+    @property
+    def sizes(self):
+        return np.diff(self.offsets)
+
+
+class PackedResult:
+    """ Likelihoods of all draws of a chromosome, window-major: lik[draw_offsets[w]:draw_offsets[w+1]] belong to
+    evaluated window w (borders[w]); statistics as computed on the device. """
+
+    def __init__(self, sample, windows, evaluated, draw_offsets, draws, lik, mean_var, chrom):
+        self.sample, self.windows, self.evaluated = sample, windows, evaluated
+        self.draw_offsets, self.draws, self.likelihoods = draw_offsets, draws, lik
+        self.window_mean_var, self.chromosome = mean_var, chrom
+
+    @property
+    def borders(self):
+        return self.windows.borders[self.evaluated]
+
+    def llr_per_chromosome(self):
+        """ {pair: {'mean_of_mean', 'std_of_mean', 'fraction_of_negative_LLRs'}} as in statistics() (:311-313). """
+        return {pair: {'mean_of_mean': float(self.chromosome[p, 0]), 'std_of_mean': float(self.chromosome[p, 1]),
+                       'fraction_of_negative_LLRs': float(self.chromosome[p, 2])} for p, pair in enumerate(LLR_PAIRS)}
+
+    def as_reference(self, tuple_type=None):
+        """ (likelihoods, genomic_windows, fraction_of_matches) in the reference's structures (ANEUPLOIDY_TEST.py:287). """
+        if tuple_type is None:
+            from .models import likelihoods_tuple as tuple_type
+        names = self.sample.read_names
+        gw = {(int(a), int(b)): tuple(names[r] for r in self.windows.reads[lo:hi])
+              for (a, b), lo, hi in zip(self.windows.borders.tolist(), self.windows.offsets[:-1].tolist(), self.windows.offsets[1:].tolist())}
+        rows = self.likelihoods.tolist()
+        lik = {(int(a), int(b)): tuple(tuple_type(*rows[i]) for i in range(lo, hi))
+               for (a, b), lo, hi in zip(self.borders.tolist(), self.draw_offsets[:-1].tolist(), self.draw_offsets[1:].tolist())}
+        return lik, gw, dict(self.sample.fraction_of_matches)
+
+
+class PackedObservations:
+    """ obs_tab rows that match the legend, as arrays (see pack_observations). """
+
+
+def pack_observations(obs_tab, legend):
+    """ obs_tab [(pos, read_id, base)] against a PackedLegend:
+      fraction_of_matches            1 - mismatches / len(obs_tab)                       (HOMOGENOUES_MODELS.py:98)
+      allele_rows, allele_complement the distinct observed alleles = keys of hap_dict     (:89-94)
+      read_names, read_offsets, read_alleles   reads as CSR lists of allele-table rows    (build_reads_dict, ANEUPLOIDY_TEST.py:118-127)
+      obs_pos, obs_read              position and read row of every matched observation  (build_overlaps_dict, :129-139) """
+    out = PackedObservations()
+    n = len(obs_tab)
+    pos = np.fromiter((r[0] for r in obs_tab), dtype=np.int64, count=n)
+    names = {}
+    name = names.setdefault
+    read = np.fromiter((name(r[1], len(names)) for r in obs_tab), dtype=np.int64, count=n)
+    base = legend.encode_bases((r[2] for r in obs_tab), n)
+    keep, row, is_ref = legend.match(pos, base)
+    out.fraction_of_matches = 1 - int((~keep).sum()) / n
+    # allele table: one row per distinct (legend row, ref/alt) among the matched observations
+    key = row[keep] * 2 + is_ref[keep]
+    alleles, allele_of_obs = np.unique(key, return_inverse=True)
+    out.allele_rows, out.allele_complement = alleles >> 1, (alleles & 1).astype(np.uint8)
+    # reads: CSR over allele rows, observation order kept inside a read
+    kread = read[keep]
+    order = np.argsort(kread, kind='stable')
+    codes, counts = np.unique(kread, return_counts=True)
+    all_names = list(names)
+    out.read_names = [all_names[c] for c in codes.tolist()]
+    out.read_offsets = np.zeros(len(codes) + 1, dtype=np.int64)
+    np.cumsum(counts, out=out.read_offsets[1:])
+    out.read_alleles = allele_of_obs[order].astype(np.int32)
+    out.obs_pos = pos[keep]
+    out.obs_read = np.searchsorted(codes, kread)
+    if len(out.obs_pos) > 1 and (np.diff(out.obs_pos) < 0).any():
+        raise ValueError('the observation table must be sorted by position')
+    return out
+
+
+class PackedSample:
+    """ One sample on one chromosome against a resident panel. """
+
+    def __init__(self, obs_tab, panel, ancestral_makeup, min_HF=0.05, device=None):
+        self.panel = panel
+        groups = panel.groups
+        if type(ancestral_makeup) == dict:
+            if list(ancestral_makeup) != groups:
+                raise ValueError('distant admixture: build the ResidentPanel with the groups in the order of the ancestral makeup')
+            if sum(ancestral_makeup.values()) < 0.999:
+                raise Exception('Error: ancestry proportions must sum to one.')
+            self.kind, self.proportions = N.DISTANT_ADMIXTURE, [float(ancestral_makeup[g]) for g in groups]
+            makeup = dict(ancestral_makeup)
+        else:
+            if set(ancestral_makeup) != set(groups) or len(groups) not in (1, 2):
+                raise ValueError('the ancestral makeup does not match the superpopulations of the resident panel')
+            self.kind, self.proportions = (N.HOMOGENEOUS if len(groups) == 1 else N.RECENT_ADMIXTURE), None
+            makeup = {g: 1 / len(groups) for g in groups}
+        packed = pack_observations(obs_tab, panel.legend)
+        frac = packed.fraction_of_matches
+        self.fraction_of_matches = {g: frac for g in groups}
+        self.allele_rows, self.allele_complement = packed.allele_rows, packed.allele_complement
+        self.read_names, self.read_offsets, self.read_alleles = packed.read_names, packed.read_offsets, packed.read_alleles
+        self.obs_pos, self.obs_read = packed.obs_pos, packed.obs_read
+        self.engine = Engine(panel.n_hap, device=panel.device if device is None else device)
+        self.engine.gather_allele_rows(panel, self.allele_rows, self.allele_complement)
+        self.engine.build_read_masks(self.read_alleles, self.read_offsets)
+        alpha = [makeup[g] / nh for g, nh in zip(groups, panel.n_hap)]
+        weight = makeup[panel.last_group] / panel.n_hap[groups.index(panel.last_group)]      # last-alpha quirk (:181-184)
+        self.scores = self.engine.read_scores(self.read_alleles, self.read_offsets, alpha, weight, min_HF)
+
+    def close(self):
+        self.engine.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ---- build_gw_dict (ANEUPLOIDY_TEST.py:191-224) -----------------------------------------------------------
+    def windows(self, window_size, offset, min_reads, max_reads, min_score, scores=None):
+        return build_windows(self.obs_pos, self.obs_read, self.scores if scores is None else scores,
+                             window_size, offset, min_reads, min_score)
+
+    # ---- pick_reads / effective_number_of_subsamples (:226-248) for all windows at once ---------------------------
+    @staticmethod
+    def plan(windows, min_reads, max_reads, subsamples, rng):
+        """ (evaluated windows, draw_offsets, [(draw rows, read_idx[n_draws_k][k]) per draw size k]). """
+        R = windows.sizes
+        effN = np.zeros(len(R), dtype=np.int64)
+        big = (R >= min_reads) & (R > max_reads)
+        small = (R >= min_reads) & (R <= max_reads)
+        # comb(R, max_reads) < subsamples only for R barely above max_reads: evaluate exactly below that bound
+        effN[big] = subsamples
+        bound = max_reads + 1
+        while comb(bound, max_reads) < subsamples:
+            bound += 1
+        for w in np.flatnonzero(big & (R < bound)).tolist():
+            effN[w] = comb(int(R[w]), max_reads)
+        effN[small] = np.minimum(R[small], subsamples)
+        evaluated = np.flatnonzero(effN > 0)
+        draw_offsets = np.zeros(len(evaluated) + 1, dtype=np.int64)
+        np.cumsum(effN[evaluated], out=draw_offsets[1:])
+        k_of = np.minimum(R - 1, max_reads)
+        groups = []
+        win_of_draw = np.repeat(evaluated, effN[evaluated])
+        k_draw = k_of[win_of_draw]
+        for k in np.unique(k_draw).tolist():
+            rows = np.flatnonzero(k_draw == k)
+            w = win_of_draw[rows]
+            local = sample_without_replacement(rng, R[w], k)
+            idx = windows.reads[windows.offsets[w][:, None] + local].astype(np.int32)
+            groups.append((rows, idx))
+        return evaluated, draw_offsets, groups
+
+    def evaluate(self, draw_groups, n_draws):
+        """ likelihoods [n_draws][4] for groups of uniform draws (rows of the output, read_idx[.][k]). """
+        lik = np.empty((n_draws, 4), dtype=np.float64)
+        for rows, idx in draw_groups:
+            if self.kind == N.DISTANT_ADMIXTURE and idx.shape[1] == 5:
+                raise AttributeError("'distant_admixture' object has no attribute 'likelihoods5'")
+            lik[rows] = self.engine.likelihoods_uniform(self.kind, idx, proportions=self.proportions)
+        return lik
+
+    def run(self, window_size=100000, subsamples=32, offset=0, min_reads=6, max_reads=4, min_score=2, rng=None):
+        """ bootstrap() + statistics() (ANEUPLOIDY_TEST.py:250-325) on arrays. """
+        rng = np.random.default_rng() if rng is None else rng
+        win = self.windows(window_size, offset, min_reads, max_reads, min_score)
+        evaluated, draw_offsets, groups = self.plan(win, min_reads, max_reads, subsamples, rng)
+        n_draws = int(draw_offsets[-1])
+        lik = self.evaluate(groups, n_draws)
+        mean_var = chrom = None
+        if len(evaluated):
+            counts = np.diff(draw_offsets)
+            n_cols = int(counts.min())
+            _llr, mean_var, partials = self.engine.window_stats(lik, draw_offsets, n_cols, want_llr=False)
+            chrom = finish_chromosome(partials, n_cols, int(counts[0]))
+        return PackedResult(self, win, evaluated, draw_offsets, groups, lik, mean_var, chrom)
+
+
+def build_windows(obs_pos, obs_read, scores, window_size, offset, min_reads, min_score):
+    """ build_gw_dict (ANEUPLOIDY_TEST.py:191-224) on sorted observation arrays.  A window is emitted when a later
+    position closes it, so the chromosome's last window never appears; windows without qualifying reads are kept. """
+    max_win_size, initial = 350000, 10000
+    adaptive = not window_size
+    ws = initial if adaptive else int(window_size)
+    offset = int(offset)
+    assert len(obs_pos), 'error: the observation table is empty.'
+    first, last = int(obs_pos[0]) + offset, int(obs_pos[-1]) + ws
+    ok = np.asarray(scores)[obs_read] >= min_score
+    if not adaptive:
+        K = max(0, (int(obs_pos[-1]) - first) // ws)                # windows closed by a later position
+        k = (obs_pos - first) // ws
+        sel = ok & (obs_pos >= first) & (k < K)
+        stride = max(1, len(scores))
+        pair = np.unique(k[sel] * stride + obs_read[sel])                  # distinct (window, read), window-major
+        wk, reads = pair // stride, pair % stride
+        a = first + ws * np.arange(K, dtype=np.int64)
+        borders = np.stack([a, a + ws - 1], axis=1) if K else np.empty((0, 2), dtype=np.int64)
+        offsets = np.zeros(K + 1, dtype=np.int64)
+        np.cumsum(np.bincount(wk, minlength=K), out=offsets[1:])
+        return PackedWindows(borders, offsets, reads.astype(np.int64))
+    # adaptive windows: sequential in the window borders, vectorised inside a window
+    borders, chunks, sizes = [], [], []
+    a, b = first, first + ws
+    n = len(obs_pos)
+    while b < last:
+        lo, hi = np.searchsorted(obs_pos, a, side='left'), np.searchsorted(obs_pos, b, side='left')
+        if hi >= n:
+            break                                                    # nothing beyond this window closes it
+        members = np.unique(obs_read[lo:hi][ok[lo:hi]])
+        if 0 < len(members) < min_reads and b - a <= max_win_size:
+            b += 10000
+            continue
+        borders.append((a, b - 1))
+        chunks.append(members)
+        sizes.append(len(members))
+        a, b = b, b + ws
+    offsets = np.zeros(len(borders) + 1, dtype=np.int64)
+    np.cumsum(sizes, out=offsets[1:])
+    reads = np.concatenate(chunks).astype(np.int64) if chunks else np.empty(0, dtype=np.int64)
+    return PackedWindows(np.asarray(borders, dtype=np.int64).reshape(-1, 2), offsets, reads)

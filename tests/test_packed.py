@@ -1,0 +1,163 @@
+"""
+The array-native route (ld-pgta_b200/packed.py) against the golden vectors made by running the
+reference: matching of observations to the legend, reads as CSR, windows (fixed, offset, adaptive) on the CPU;
+read scores, replayed draws and the whole run on the GPU.
+"""
+import numpy as np
+import pytest
+
+import ldpgta_oracle as O
+from conftest import CHROM_CONFIGS, chrom_case, rel_err
+
+
+def packed_inputs(name, golden_inputs):
+    from ldpgta_b200.packed import PackedLegend, pack_observations
+    args, out = chrom_case(name, golden_inputs)
+    legend = PackedLegend(args['leg_tab'])
+    return args, out, legend, pack_observations(args['obs_tab'], legend)
+
+
+@pytest.mark.parametrize('name', CHROM_CONFIGS)
+def test_pack_observations_and_windows_cpu(name, golden_inputs):
+    from ldpgta_b200.packed import build_windows
+    args, out, legend, po = packed_inputs(name, golden_inputs)
+    cfg = args['cfg']
+    g0 = cfg['groups'][0]
+    assert po.fraction_of_matches == out['fraction_of_matches'][g0]
+    # reads: same read ids, same alleles in the same order as build_reads_dict
+    leg_dict = {l[1]: (l[2], l[3]) for l in args['leg_tab']}
+    reads = {}
+    for pos, rid, base in args['obs_tab']:
+        if base in leg_dict.get(pos, ()):
+            reads.setdefault(rid, []).append((pos, base))
+    assert sorted(po.read_names) == sorted(reads) and set(out['score']) == set(reads)
+    leg_pos = [l[1] for l in args['leg_tab']]
+    leg = args['leg_tab']
+    for r, rid in enumerate(po.read_names):
+        got = []
+        for a in po.read_alleles[po.read_offsets[r]:po.read_offsets[r + 1]]:
+            l = leg[int(po.allele_rows[a])]
+            got.append((l[1], l[2] if po.allele_complement[a] else l[3]))
+        assert got == reads[rid]
+    # windows from the golden scores: same borders in the same order, same read sets
+    scores = np.array([out['score'][rid] for rid in po.read_names])
+    win = build_windows(po.obs_pos, po.obs_read, scores, cfg['window_size'], cfg['offset'], cfg['min_reads'], cfg['min_score'])
+    assert [tuple(b) for b in win.borders.tolist()] == list(out['windows'])
+    for (lo, hi), ids in zip(zip(win.offsets[:-1], win.offsets[1:]), out['windows'].values()):
+        assert {po.read_names[r] for r in win.reads[lo:hi]} == set(ids)
+
+
+def test_legend_lookup_semantics():
+    from ldpgta_b200.packed import PackedLegend, pack_observations
+    leg = [('c', 10, 'A', 'G'), ('c', 20, 'C', 'T'), ('c', 20, 'G', 'T'), ('c', 5, 'T', 'TA')]       # duplicate position, unsorted
+    legend = PackedLegend(leg)
+    obs = [(5, 'r0', 'TA'), (10, 'r0', 'A'), (10, 'r1', 'G'), (20, 'r1', 'C'), (20, 'r2', 'G'), (20, 'r2', 'T'), (30, 'r3', 'A'), (10, 'r3', 'N')]
+    with pytest.raises(ValueError):
+        pack_observations(obs + [(5, 'r4', 'T')], legend)   # matched observations must be sorted by position
+    obs = sorted(obs, key=lambda r: r[0])
+    po = pack_observations(obs, legend)
+    # the later legend row of position 20 wins: 'C' is a mismatch, 'G' is REF of row 2; unknown position and base are mismatches
+    assert po.fraction_of_matches == 1 - 3 / 8
+    alleles = {(int(r), int(c)) for r, c in zip(po.allele_rows, po.allele_complement)}
+    assert alleles == {(3, 0), (0, 1), (0, 0), (2, 1), (2, 0)}
+    assert po.read_names == ['r0', 'r1', 'r2'] and po.read_offsets.tolist() == [0, 2, 3, 5]
+
+
+def test_sampling_without_replacement_is_uniform():
+    from ldpgta_b200.packed import sample_without_replacement
+    rng = np.random.default_rng(5)
+    R = np.full(60000, 7)
+    s = sample_without_replacement(rng, R, 3)
+    assert s.min() == 0 and s.max() == 6 and all(len(set(row)) == 3 for row in s[:2000].tolist())
+    counts = np.bincount(np.sort(s, axis=1) @ np.array([49, 7, 1]), minlength=343)
+    seen = counts[counts > 0]
+    assert len(seen) == 35 and abs(seen / len(R) - 1 / 35).max() < 0.004        # all 35 subsets, equally likely
+    R = rng.integers(5, 400, size=5000)
+    s = sample_without_replacement(rng, R, 4)
+    assert (s < R[:, None]).all() and (s >= 0).all() and all(len(set(row)) == 4 for row in s.tolist())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', CHROM_CONFIGS)
+def test_packed_sample_matches_reference(name, golden_inputs):
+    import ldpgta_b200 as L
+    from ldpgta_b200.packed import PackedSample
+    args, out = chrom_case(name, golden_inputs)
+    cfg = args['cfg']
+    groups = list(cfg['makeup']) if isinstance(cfg['makeup'], dict) else list(cfg['groups'])
+    hap = {g: args['hap_tab'][g] for g in groups}
+    nhap = {g: args['number_of_haplotypes'][g] for g in args['number_of_haplotypes']}
+    panel = L.ResidentPanel(args['leg_tab'], hap, nhap)
+    with PackedSample(args['obs_tab'], panel, cfg['makeup'], cfg['min_HF']) as ps:
+        assert ps.fraction_of_matches == out['fraction_of_matches']
+        assert dict(zip(ps.read_names, ps.scores.tolist())) == out['score']
+        win = ps.windows(cfg['window_size'], cfg['offset'], cfg['min_reads'], cfg['max_reads'], cfg['min_score'])
+        assert [tuple(b) for b in win.borders.tolist()] == list(out['windows'])
+        # the reference's own draws, replayed as read rows
+        row_of = {rid: r for r, rid in enumerate(ps.read_names)}
+        by_k, ref = {}, {}
+        for w, draws in out['draws'].items():
+            for d, lik in zip(draws, out['likelihoods'][w]):
+                by_k.setdefault(len(d), []).append([row_of[r] for r in d])
+                ref.setdefault(len(d), []).append(lik)
+        worst = 0.0
+        for k, idx in by_k.items():
+            got = ps.evaluate([(np.arange(len(idx)), np.array(idx, dtype=np.int32))], len(idx))
+            for g, r in zip(got.tolist(), ref[k]):
+                worst = max(worst, max(rel_err(a, b) for a, b in zip(g, r)))
+        assert worst <= 1e-12, worst
+        # a full packed run: every window the reference evaluates is evaluated, draws are valid, statistics finite
+        res = ps.run(cfg['window_size'], cfg['subsamples'], cfg['offset'], cfg['min_reads'], cfg['max_reads'], cfg['min_score'],
+                     rng=np.random.default_rng(1))
+        lik, gw, frac = res.as_reference()
+        assert list(lik) == list(out['likelihoods']) and list(gw) == list(out['windows'])
+        assert [len(v) for v in lik.values()] == [len(v) for v in out['likelihoods'].values()]
+        sizes = dict(zip(map(tuple, win.borders.tolist()), win.sizes.tolist()))
+        for rows, idx in res.draws:
+            assert all(len(set(d)) == len(d) for d in idx.tolist())
+        for w, ids in gw.items():
+            assert set(ids) == set(out['windows'][w])
+        assert np.isfinite(res.likelihoods).all() and (res.likelihoods >= 0).all() and (res.likelihoods <= 1).all()
+        stats = res.llr_per_chromosome()
+        oracle_stats = O.statistics({w: [O.likelihoods_tuple(*l) for l in v] for w, v in lik.items()}, gw)
+        for pair, s in stats.items():
+            for key in ('mean_of_mean', 'std_of_mean', 'fraction_of_negative_LLRs'):
+                assert rel_err(s[key], oracle_stats['LLRs_per_chromosome'][pair][key]) <= 1e-9 or abs(s[key] - oracle_stats['LLRs_per_chromosome'][pair][key]) < 1e-15
+    panel.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ('homog_m4', 'recent_m6', 'distant_m6'))
+def test_aneuploidy_test_packed_option(name, tmp_path, golden_inputs):
+    """ aneuploidy_test(..., packed=True): same files, same `info` / statistics structure, the windows of the reference,
+    statistics equal to the oracle's statistics() of the returned likelihoods. """
+    import pickle
+    from ldpgta_b200 import driver
+    args, out = chrom_case(name, golden_inputs)
+    cfg = args['cfg']
+    d = tmp_path
+    with open(d / 's.chr21.obs.p', 'wb') as f:
+        pickle.dump(args['obs_tab'], f); pickle.dump({'chr_id': 'chr21', 'depth': 0.3}, f)
+    with open(d / 'leg.p', 'wb') as f:
+        pickle.dump(args['leg_tab'], f)
+    with open(d / 'hap.p', 'wb') as f:
+        pickle.dump(args['hap_tab'], f); pickle.dump(args['number_of_haplotypes'], f)
+    lik, info = driver.aneuploidy_test(str(d / 's.chr21.obs.p'), str(d / 'leg.p'), str(d / 'hap.p'), cfg['makeup'], cfg['window_size'],
+                                       cfg['subsamples'], cfg['offset'], cfg['min_reads'], cfg['max_reads'], cfg['min_score'],
+                                       cfg['min_HF'], '', 'unc', seed=3, output_dir=str(d / 'results'), packed=True)
+    assert list(lik) == list(out['likelihoods'])
+    S = info['statistics']
+    assert S['matched_alleles'] == out['fraction_of_matches'] and S['num_of_windows'] == len(lik)
+    gw = {w: ids for w, ids in out['windows'].items()}
+    ref = O.statistics({w: [O.likelihoods_tuple(*l) for l in v] for w, v in lik.items()}, gw)
+    for key in ('reads_mean', 'reads_std', 'window_size_mean', 'window_size_std'):
+        assert rel_err(S[key], ref[key]) < 1e-12
+    for pair, per_w in ref['LLRs_per_genomic_window'].items():
+        for w, (m, v) in per_w.items():
+            gm, gv = S['LLRs_per_genomic_window'][pair][w]
+            assert abs(gm - m) <= 1e-12 * max(1, abs(m)) and abs(gv - v) <= 1e-9 * max(1e-3, abs(v))
+        for key, val in ref['LLRs_per_chromosome'][pair].items():
+            assert abs(S['LLRs_per_chromosome'][pair][key] - val) <= 1e-9 * max(1e-3, abs(val))
+    with open(d / 'results' / 's.chr21.LLR.p', 'rb') as f:
+        saved = pickle.load(f)
+    assert list(saved) == list(lik) and type(next(iter(saved.values()))[0]).__name__ == 'likelihoods_tuple'
