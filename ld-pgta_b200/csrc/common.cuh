@@ -205,5 +205,7 @@ int launch_small(ldpgta_ctx *c, SmallArgs &a, int n, int kind);
 int make_read_mask_tmap(ldpgta_ctx *c, int g);
 int launch_mid(ldpgta_ctx *c, SmallArgs &a, int n);      // 5-6 reads, register kernel; 1 = not applicable
 int launch_general(ldpgta_ctx *c, GeneralArgs a);
+int launch_lanes(ldpgta_ctx *c, GeneralArgs a);          // 7-10 reads (5-6 for two-group models), register counters; 1 = not applicable
+int ensure_hi_terms(ldpgta_ctx *c, int h);               // colouring list of the three-block polynomial for h = n - 5 high reads
 
 }  // namespace ldpgta

@@ -84,7 +84,7 @@ static int launch_general_t(ldpgta_ctx *c, GeneralArgs a, const GeneralPlan &p)
 
 // Colourings (a_h, b_h, c_h) of the h = n - 5 high reads (every read in exactly one part) with b_h < c_h,
 // packed a | b << 16 | c << 32.  (3^h - 1) / 2 entries, generated once per h and kept on the device.
-static int ensure_hi_terms(ldpgta_ctx *c, int h)
+int ensure_hi_terms(ldpgta_ctx *c, int h)
 {
     if (c->hi_terms[h] || h == 0) return 0;
     std::vector<uint64_t> list;

@@ -20,6 +20,7 @@
 #pragma once
 #include "common.cuh"
 #include "poly_general.cuh"
+#include "poly_finish.cuh"
 
 namespace ldpgta {
 
@@ -288,10 +289,7 @@ __global__ void __launch_bounds__(512, 1) k_general(const GeneralArgs a)
         }
 
         // ---- phase 3: partition polynomials ----------------------------------------------
-        const double p2n1 = (double)(1u << (n - 1));
-        double p3n1 = 1.0;
-        for (int i = 1; i < n; ++i) p3n1 *= 3.0;
-        const double p3n = 3.0 * p3n1, p2n = 2.0 * p2n1;
+        const PolyScale scale = poly_scale(n);
         double res[4];
 
         if (a.kind == LDPGTA_HOMOGENEOUS) {
@@ -333,13 +331,7 @@ __global__ void __launch_bounds__(512, 1) k_general(const GeneralArgs a)
             split_u128(three, v + 2);
             block_sum_u64<6>(v, red);
             if (tid == 0) {
-                const double N = (double)a.pv.nhap[0];
-                const u64 Ff = F[full];
-                const double d_two = (double)v[0], d_sph = (double)v[1], d_three = u128_to_double(join_u128(v + 2));
-                res[0] = (double)Ff / N;
-                res[1] = (double)Ff / (p2n1 * N) + d_two / p2n1 / (N * N);
-                res[2] = (double)(Ff * ((1ull << n) + 1ull)) / (p3n * N) + d_sph / p3n / (N * N);
-                res[3] = (double)Ff / (p3n1 * N) + (2.0 * d_two) / p3n1 / (N * N) + (2.0 * d_three) / p3n1 / (N * N * N);
+                finish_homogeneous(scale, (double)a.pv.nhap[0], F[full], (double)v[0], (double)v[1], u128_to_double(join_u128(v + 2)), res);
             }
         } else if (a.kind == LDPGTA_RECENT_ADMIXTURE) {
             const CT *F = ftab, *Gt = ftab + NS;
@@ -387,16 +379,8 @@ __global__ void __launch_bounds__(512, 1) k_general(const GeneralArgs a)
             split_u128(ggf, v + 8);
             block_sum_u64<12>(v, red);
             if (tid == 0) {
-                const double M = (double)a.pv.nhap[0], N = (double)a.pv.nhap[1];
-                const double s = (double)F[full] / M + (double)Gt[full] / N;
-                const double d_ff = (double)v[0], d_gg = (double)v[1], d_fg = (double)v[2], d_sph = (double)v[3];
-                const double d_ffg = u128_to_double(join_u128(v + 4)), d_ggf = u128_to_double(join_u128(v + 8));
-                res[0] = s / 2.0;
-                res[1] = s / p2n + d_fg / p2n1 / (2.0 * M * N);
-                res[2] = s * (double)((1ull << n) + 1ull) / (2.0 * p3n) + d_sph / p3n / (2.0 * M * N);
-                res[3] = s / (2.0 * p3n1)
-                       + (d_ff / (M * M) + d_gg / (N * N) + 2.0 * d_fg / (M * N)) * 2.0 / p3n1 / 6.0
-                       + (d_ffg / M + d_ggf / N) * 2.0 / p3n1 / (6.0 * M * N);
+                finish_recent(scale, (double)a.pv.nhap[0], (double)a.pv.nhap[1], F[full], Gt[full], (double)v[0], (double)v[1], (double)v[2],
+                              (double)v[3], u128_to_double(join_u128(v + 4)), u128_to_double(join_u128(v + 8)), res);
             }
         } else {
             // distant admixture: e(S) = sum_g p_g * cnt_g(S) / N_g (DISTANT_ADMIXTURE_MODELS.py:136-139)
@@ -446,11 +430,7 @@ __global__ void __launch_bounds__(512, 1) k_general(const GeneralArgs a)
                     for (int w = 1; w < NW; ++w) { two += redd[w * 3]; two_sph += redd[w * 3 + 1]; three += redd[w * 3 + 2]; }
             }
             if (tid == 0) {
-                const double Ef = E(full);
-                res[0] = Ef;
-                res[1] = Ef / p2n1 + two / p2n1;
-                res[2] = (double)((1ull << n) + 1ull) / p3n * Ef + two_sph / p3n;
-                res[3] = Ef / p3n1 + 2.0 * two / p3n1 + 2.0 * three / p3n1;
+                finish_distant(scale, E(full), two, two_sph, three, res);
             }
         }
         if (tid == 0) {

@@ -1,0 +1,55 @@
+// lanes.cu -- launcher of k_lanes (k_lanes.cuh): draws of 7..10 reads, and 5..6 reads of two-group models.
+#include <algorithm>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "k_lanes.cuh"
+
+namespace ldpgta {
+
+template <int NR, int KL>
+static int launch_lanes_t(ldpgta_ctx *c, const GeneralArgs &a)
+{
+    constexpr int DPW = 32 >> KL;
+    static const int max_warps = [] { const char *e = getenv("LDPGTA_LANES_WARPS"); return e ? std::max(1, std::min(12, atoi(e))) : 12; }();
+    const LanesSmem lay = lanes_smem_layout<NR, KL>(a.pv);
+    const int fit = (c->max_smem_optin - 1024) / lay.per_warp;
+    if (fit < 2) return 1;                                   // rows too long for two warps per SM: the table kernel takes it
+    const int nwarps = std::min(max_warps, fit);
+    const size_t smem = (size_t)nwarps * lay.per_warp;
+    auto kern = k_lanes<NR, KL>;
+    LDPGTA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t tiles = (a.n_draws + DPW - 1) / DPW;
+    const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((tiles + nwarps - 1) / nwarps, c->sm_count));
+    kern<<<blocks, 32 * nwarps, smem, c->stream>>>(a);
+    c->launches++;
+    LDPGTA_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_lanes(ldpgta_ctx *c, GeneralArgs a)
+{
+    if (getenv("LDPGTA_NO_LANES")) return 1;
+    if (a.n < 5 || a.n > 10) return 1;
+    for (int g = 0; g < c->G; ++g)
+        if (c->wp[g] * 8 > 65536) return 1;
+    const int h = a.n - 5;
+    if (int rc = ensure_hi_terms(c, h)) return rc;
+    a.terms = reinterpret_cast<const u64 *>(c->hi_terms[h]);
+    a.n_terms = c->n_hi_terms[h];
+    a.wide = 0;
+    for (int g = 0; g < c->G; ++g) a.wide |= c->nhap[g] > 16383u;
+    a.kl = a.kh = a.wc = 0;
+    a.table_scratch = nullptr; a.table_stride = 0;
+    switch (a.n) {
+    case 5: return launch_lanes_t<5, 3>(c, a);
+    case 6: return launch_lanes_t<6, 3>(c, a);
+    case 7: return launch_lanes_t<7, 3>(c, a);
+    case 8: return launch_lanes_t<8, 4>(c, a);
+    case 9: return launch_lanes_t<9, 5>(c, a);
+    case 10: return launch_lanes_t<10, 5>(c, a);
+    }
+    return 1;
+}
+
+}  // namespace ldpgta
