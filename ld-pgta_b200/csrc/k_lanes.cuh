@@ -9,8 +9,9 @@
 //   * for every one of the 2^KH subsets hi of the other KH = NR - KL reads the lane ANDs x_w with the high reads of
 //     hi (compile-time subsets, LOP3 folds up to three inputs) and counts the result; three words at a time go
 //     through a carry-save adder, so 3 word-ops cost 2 POPC.64;  F[hi << KL | lo] lives in a register counter;
-//   * every mask word is read from shared memory exactly once per lane (a broadcast per draw), the masks arrive by
-//     bulk copies (TMA 1-D) into a double buffer, the next tile's copy runs under the current tile's arithmetic;
+//   * every mask word is read from shared memory exactly once per lane (a broadcast per draw); the masks arrive by
+//     bulk copies (TMA 1-D), and the next tile's copy is issued as soon as the counts are done, so it runs under the
+//     polynomial and under the other warps' arithmetic (single buffer: shared memory buys warps, not buffers);
 //   * the counters go to a per-draw table in shared memory and the register-blocked partition polynomials of
 //     poly_general.cu run on it, one lane group per draw, for the three model classes.
 //
@@ -28,7 +29,7 @@ struct LanesSmem {           // per-warp byte offsets / sizes
     int draw_stride;         // 64-bit words between consecutive draws of a buffer (bank-staggered)
     int buf_words;           // words per buffer
     int ftab;                // byte offset of the warp's count tables
-    int per_warp;            // bytes per warp (two buffers + tables + barriers)
+    int per_warp;            // bytes per warp (mask buffer + tables + barrier)
 };
 
 template <int NR, int KL>
@@ -45,10 +46,10 @@ __host__ __device__ inline LanesSmem lanes_smem_layout(const PanelView &pv)
     stride += stagger;
     s.draw_stride = stride;
     s.buf_words = stride * DPW;
-    s.ftab = 2 * s.buf_words * 8;
+    s.ftab = s.buf_words * 8;
     int off = s.ftab + DPW * ((pv.G << NR) * 4);
     off = (off + 15) & ~15;
-    off += 16;                                            // two mbarriers
+    off += 16;                                            // the warp's mbarrier
     s.per_warp = (off + 127) & ~127;
     return s;
 }
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(384, 1) k_lanes(const __grid_constant__ Genera
     uint32_t *ftab = reinterpret_cast<uint32_t *>(wbase + lay.ftab) + (size_t)dgrp * (G << NR);
     uint64_t *bar = reinterpret_cast<uint64_t *>(wbase + lay.per_warp - 16);
 
-    if (lane < 2) mbar_init(bar + lane, 1);
+    if (lane == 0) mbar_init(bar, 1);
     fence_proxy_async();
     __syncwarp();
 
@@ -95,10 +96,9 @@ __global__ void __launch_bounds__(384, 1) k_lanes(const __grid_constant__ Genera
     // one bulk copy per (draw, group, read) row of the tile
     uint32_t tile_bytes = 0;
     for (int g = 0; g < G; ++g) tile_bytes += (uint32_t)(DPW * NR * a.pv.wp[g] * 8);
-    auto issue = [&](int64_t tile, int b) {
-        if (lane == 0) mbar_arrive_expect_tx(bar + b, tile_bytes);
+    auto issue = [&](int64_t tile) {
+        if (lane == 0) mbar_arrive_expect_tx(bar, tile_bytes);
         __syncwarp();
-        u64 *dst0 = bufs + (size_t)b * lay.buf_words;
         int goff = 0;
         for (int g = 0; g < G; ++g) {
             const int wp = a.pv.wp[g];
@@ -107,8 +107,8 @@ __global__ void __launch_bounds__(384, 1) k_lanes(const __grid_constant__ Genera
                 int64_t draw = tile * DPW + d;
                 if (draw >= a.n_draws) draw = a.n_draws - 1;
                 const int32_t ridx = __ldg(a.idx + draw * NR + i);
-                bulk_copy_g2s(dst0 + (size_t)d * lay.draw_stride + goff + i * wp, a.pv.masks[g] + (int64_t)ridx * wp,
-                              (uint32_t)wp * 8u, bar + b);
+                bulk_copy_g2s(bufs + (size_t)d * lay.draw_stride + goff + i * wp, a.pv.masks[g] + (int64_t)ridx * wp,
+                              (uint32_t)wp * 8u, bar);
             }
             goff += NR * wp;
         }
@@ -119,22 +119,16 @@ __global__ void __launch_bounds__(384, 1) k_lanes(const __grid_constant__ Genera
     for (int i = 0; i < KL; ++i) keep[i] = ((lo >> i) & 1) ? 0ull : ~0ull;
 
     const PolyScale scale = poly_scale(NR);
-    if (my_tiles > 0) issue(tile0, 0);
-    uint32_t parity[2] = {0u, 0u};
+    if (my_tiles > 0) issue(tile0);
+    uint32_t parity = 0u;
 
     for (int64_t q = 0; q < my_tiles; ++q) {
-        const int b = (int)(q & 1);
         const int64_t tile = tile0 + q * tstride;
         const int64_t draw = tile * DPW + dgrp;
-        // the other buffer was consumed in the previous iteration (the __syncwarp at its end orders the reads)
-        if (q + 1 < my_tiles) {
-            fence_proxy_async();
-            issue(tile + tstride, b ^ 1);
-        }
-        mbar_wait(bar + b, parity[b]);
-        parity[b] ^= 1u;
+        mbar_wait(bar, parity);
+        parity ^= 1u;
 
-        const u64 *M0 = bufs + (size_t)b * lay.buf_words + (size_t)dgrp * lay.draw_stride;
+        const u64 *M0 = bufs + (size_t)dgrp * lay.draw_stride;
         int goff = 0;
         for (int g = 0; g < G; ++g) {
             const int wp = a.pv.wp[g];
@@ -142,17 +136,15 @@ __global__ void __launch_bounds__(384, 1) k_lanes(const __grid_constant__ Genera
             uint32_t acc[HS];
 #pragma unroll
             for (int h = 0; h < HS; ++h) acc[h] = 0;
-            for (int w = 0; w < wp; w += 3) {
-                u64 x[3], hm[KH][3];
+            // three words of every subset per step: x = the lane's low subset, y = x restricted to the high reads of h
+            auto triple = [&](const u64 (&lw)[KL > 0 ? KL : 1][3], const u64 (&hm)[KH][3]) {
+                u64 x[3];
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    const bool in = w + k < wp;                   // the last triple may be short: missing words count nothing
-                    u64 v = in ? ~0ull : 0ull;
+                    u64 v = ~0ull;
 #pragma unroll
-                    for (int i = 0; i < KL; ++i) v &= (in ? M[i * wp + w + k] : 0ull) | keep[i];
+                    for (int i = 0; i < KL; ++i) v &= lw[i][k] | keep[i];
                     x[k] = v;
-#pragma unroll
-                    for (int j = 0; j < KH; ++j) hm[j][k] = in ? M[(KL + j) * wp + w + k] : 0ull;
                 }
 #pragma unroll
                 for (int h = 0; h < HS; ++h) {
@@ -169,13 +161,43 @@ __global__ void __launch_bounds__(384, 1) k_lanes(const __grid_constant__ Genera
                     csa(y[0], y[1], y[2], ones, twos);
                     acc[h] += __popcll(ones) + 2 * __popcll(twos);
                 }
+            };
+            const u64 *row = M;
+            int w = 0;
+            for (; w + 3 <= wp; w += 3, row += 3) {
+                u64 lw[KL > 0 ? KL : 1][3], hm[KH][3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+#pragma unroll
+                    for (int i = 0; i < KL; ++i) lw[i][k] = row[i * wp + k];
+#pragma unroll
+                    for (int j = 0; j < KH; ++j) hm[j][k] = row[(KL + j) * wp + k];
+                }
+                triple(lw, hm);
+            }
+            if (w < wp) {                                          // one or two words left: the missing ones count nothing
+                u64 lw[KL > 0 ? KL : 1][3], hm[KH][3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const bool in = w + k < wp;
+                    const int kk = in ? k : 0;
+#pragma unroll
+                    for (int i = 0; i < KL; ++i) lw[i][k] = in ? row[i * wp + kk] : 0ull;     // x = 0 (F[0] is reset below)
+#pragma unroll
+                    for (int j = 0; j < KH; ++j) hm[j][k] = in ? row[(KL + j) * wp + kk] : 0ull;
+                }
+                triple(lw, hm);
             }
             uint32_t *F = ftab + ((size_t)g << NR);
 #pragma unroll
             for (int h = 0; h < HS; ++h) F[(h << KL) | lo] = acc[h];
             goff += NR * wp;
         }
-        __syncwarp();                                          // all lanes are done with buffer b; tables complete
+        __syncwarp();                                          // all lanes are done with the masks; tables complete
+        if (q + 1 < my_tiles) {                                // refill: the copy lands while the polynomials run
+            fence_proxy_async();
+            issue(tile + tstride);
+        }
         if (lo == 0)
             for (int g = 0; g < G; ++g) ftab[(size_t)g << NR] = 0;                 // the empty subset is not a joint frequency
         __syncwarp();
