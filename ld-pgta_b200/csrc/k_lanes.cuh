@@ -1,4 +1,4 @@
-// k_lanes.cuh -- draws of 5..10 reads: lanes own the low subsets, registers hold the high-subset counters.
+// k_lanes.cuh -- draws of 5..12 reads: lanes own the low subsets, registers hold the high-subset counters.
 //
 // The table kernel (k_general) spends more than half of its instructions outside the AND+POPC loop when a draw
 // keeps only one or two warps busy (7..10 reads): building its L/H tables chunk by chunk, block barriers, staging
@@ -70,8 +70,12 @@ __device__ __forceinline__ double group_sum_f64(double v)
     return v;
 }
 
+// 12 warps per SM (168 registers); 12 reads keep 64 packed counter registers plus 7 x 3 high words live: 8 warps (255)
+template <int NR>
+struct LanesWarps { static constexpr int MAX = NR >= 12 ? 8 : 12; };
+
 template <int NR, int KL>
-__global__ void __launch_bounds__(384, 1) k_lanes(const __grid_constant__ GeneralArgs a)
+__global__ void __launch_bounds__(32 * LanesWarps<NR>::MAX, 1) k_lanes(const __grid_constant__ GeneralArgs a)
 {
     constexpr int KH = NR - KL, HS = 1 << KH, LPD = 1 << KL, DPW = 32 / LPD, NS = 1 << NR;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -133,9 +137,13 @@ __global__ void __launch_bounds__(384, 1) k_lanes(const __grid_constant__ Genera
         for (int g = 0; g < G; ++g) {
             const int wp = a.pv.wp[g];
             const u64 *M = M0 + goff;
-            uint32_t acc[HS];
+            // counters: one register per high subset, or two 16-bit counters per register when there are 64 or more
+            // (a lane's partial count is at most 64 * wp < 2^16, checked by the launcher)
+            constexpr bool PACK = KH >= 6;
+            constexpr int NACC = PACK ? HS / 2 : HS;
+            uint32_t acc[NACC];
 #pragma unroll
-            for (int h = 0; h < HS; ++h) acc[h] = 0;
+            for (int h = 0; h < NACC; ++h) acc[h] = 0;
             // three words of every subset per step: x = the lane's low subset, y = x restricted to the high reads of h
             auto triple = [&](const u64 (&lw)[KL > 0 ? KL : 1][3], const u64 (&hm)[KH][3]) {
                 u64 x[3];
@@ -159,7 +167,9 @@ __global__ void __launch_bounds__(384, 1) k_lanes(const __grid_constant__ Genera
                     }
                     u64 ones, twos;
                     csa(y[0], y[1], y[2], ones, twos);
-                    acc[h] += __popcll(ones) + 2 * __popcll(twos);
+                    const uint32_t cnt = __popcll(ones) + 2 * __popcll(twos);
+                    if (PACK) acc[h >> 1] += cnt << (16 * (h & 1));
+                    else acc[h] += cnt;
                 }
             };
             const u64 *row = M;
@@ -190,7 +200,7 @@ __global__ void __launch_bounds__(384, 1) k_lanes(const __grid_constant__ Genera
             }
             uint32_t *F = ftab + ((size_t)g << NR);
 #pragma unroll
-            for (int h = 0; h < HS; ++h) F[(h << KL) | lo] = acc[h];
+            for (int h = 0; h < HS; ++h) F[(h << KL) | lo] = PACK ? (acc[h >> 1] >> (16 * (h & 1))) & 0xffffu : acc[h];
             goff += NR * wp;
         }
         __syncwarp();                                          // all lanes are done with the masks; tables complete

@@ -1,4 +1,4 @@
-// lanes.cu -- launcher of k_lanes (k_lanes.cuh): draws of 7..10 reads, and 5..6 reads of two-group models.
+// lanes.cu -- launcher of k_lanes (k_lanes.cuh): draws of 7..12 reads, and 5..6 reads of two-group models.
 #include <algorithm>
 #include <stdlib.h>
 
@@ -11,11 +11,11 @@ template <int NR, int KL>
 static int launch_lanes_t(ldpgta_ctx *c, const GeneralArgs &a)
 {
     constexpr int DPW = 32 >> KL;
-    static const int max_warps = [] { const char *e = getenv("LDPGTA_LANES_WARPS"); return e ? std::max(1, std::min(12, atoi(e))) : 12; }();
+    static const int max_warps = [] { const char *e = getenv("LDPGTA_LANES_WARPS"); return e ? std::max(1, atoi(e)) : 12; }();
     const LanesSmem lay = lanes_smem_layout<NR, KL>(a.pv);
     const int fit = (c->max_smem_optin - 1024) / lay.per_warp;
     if (fit < 2) return 1;                                   // rows too long for two warps per SM: the table kernel takes it
-    const int nwarps = std::min(max_warps, fit);
+    const int nwarps = std::min(std::min(max_warps, LanesWarps<NR>::MAX), fit);
     const size_t smem = (size_t)nwarps * lay.per_warp;
     auto kern = k_lanes<NR, KL>;
     LDPGTA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -30,9 +30,13 @@ static int launch_lanes_t(ldpgta_ctx *c, const GeneralArgs &a)
 int launch_lanes(ldpgta_ctx *c, GeneralArgs a)
 {
     if (getenv("LDPGTA_NO_LANES")) return 1;
-    if (a.n < 5 || a.n > 10) return 1;
+    // measured against the table kernel (tools/bench_lanes.sh): ahead up to 12 reads for one group, up to 11 for two-group
+    // models, whose polynomial (six trilinear forms per colouring) is too long for one warp at 12 reads
+    static const int max_n_env = [] { const char *e = getenv("LDPGTA_LANES_MAXN"); return e ? atoi(e) : 12; }();
+    const int max_n = std::min(max_n_env, a.kind == LDPGTA_HOMOGENEOUS ? 12 : 11);
+    if (a.n < 5 || a.n > max_n) return 1;
     for (int g = 0; g < c->G; ++g)
-        if (c->wp[g] * 8 > 65536) return 1;
+        if (c->wp[g] * 64 > 65535) return 1;           // 16-bit packed partial counts, row bytes of one bulk copy
     const int h = a.n - 5;
     if (int rc = ensure_hi_terms(c, h)) return rc;
     a.terms = reinterpret_cast<const u64 *>(c->hi_terms[h]);
@@ -48,6 +52,8 @@ int launch_lanes(ldpgta_ctx *c, GeneralArgs a)
     case 8: return launch_lanes_t<8, 4>(c, a);
     case 9: return launch_lanes_t<9, 5>(c, a);
     case 10: return launch_lanes_t<10, 5>(c, a);
+    case 11: return launch_lanes_t<11, 5>(c, a);
+    case 12: return launch_lanes_t<12, 5>(c, a);
     }
     return 1;
 }

@@ -141,7 +141,7 @@ static int run_uniform(ldpgta_ctx *c, int kind, int n, const int32_t *idx_dev, i
     a.kind = kind; a.n = n; a.kl = a.kh = a.wc = 0;
     a.idx = idx_dev; a.n_draws = n_draws; a.pos = pos_dev; a.out = out_dev; a.counts_out = counts_dev;
     a.terms = nullptr; a.n_terms = 0; a.wide = 0; a.table_scratch = nullptr; a.table_stride = 0;
-    if (n >= 5 && n <= 10) {
+    if (n >= 5 && n <= 12) {
         const int rc = launch_lanes(c, a);
         if (rc <= 0) return rc;                       // 1 = outside the register kernel's envelope
     }

@@ -2,7 +2,7 @@
 # draw sizes served by k_lanes, with and without it (run under gpurun): tools/bench_lanes.sh [model] [sizes...]
 MODEL=${1:-homogeneous}; shift
 SIZES=${@:-5 6 7 8 9 10}
-declare -A CFG=([5]="8000 32" [6]="8000 32" [7]="6000 32" [8]="4000 32" [9]="4000 16" [10]="4000 8")
+declare -A CFG=([5]="8000 32" [6]="8000 32" [7]="6000 32" [8]="4000 32" [9]="4000 16" [10]="4000 8" [11]="2000 8" [12]="2000 4")
 for n in $SIZES; do set -- ${CFG[$n]}
   for off in 0 1; do
     if [ $off = 1 ]; then export LDPGTA_NO_LANES=1; else unset LDPGTA_NO_LANES; fi
