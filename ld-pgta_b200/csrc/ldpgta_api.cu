@@ -129,21 +129,27 @@ static int run_uniform(ldpgta_ctx *c, int kind, int n, const int32_t *idx_dev, i
         a.idx = idx_dev; a.n_draws = n_draws; a.pos = pos_dev; a.out = out_dev; a.counts_out = counts_dev;
         return launch_small(c, a, n, kind);
     }
-    if ((n == 5 || n == 6) && kind == LDPGTA_HOMOGENEOUS && !force_general) {
-        SmallArgs sa;
-        sa.pv = override_view ? *override_view : make_view(c, proportions);
-        sa.idx = idx_dev; sa.n_draws = n_draws; sa.pos = pos_dev; sa.out = out_dev; sa.counts_out = counts_dev;
-        const int rc = launch_mid(c, sa, n);
-        if (rc <= 0) return rc;                       // 1 = outside the register kernel's envelope
-    }
     GeneralArgs a;
     a.pv = override_view ? *override_view : make_view(c, proportions);
     a.kind = kind; a.n = n; a.kl = a.kh = a.wc = 0;
     a.idx = idx_dev; a.n_draws = n_draws; a.pos = pos_dev; a.out = out_dev; a.counts_out = counts_dev;
     a.terms = nullptr; a.n_terms = 0; a.wide = 0; a.table_scratch = nullptr; a.table_stride = 0;
-    if (n >= 5 && n <= 12) {
+    // measured (tools/bench_lanes.sh): k_mid leads at 5 reads of a one-group model, k_lanes from 6 reads on
+    const bool mid_ok = (n == 5 || n == 6) && kind == LDPGTA_HOMOGENEOUS && !force_general;
+    if (n >= 6 && n <= 12) {
         const int rc = launch_lanes(c, a);
         if (rc <= 0) return rc;                       // 1 = outside the register kernel's envelope
+    }
+    if (mid_ok) {
+        SmallArgs sa;
+        sa.pv = a.pv;
+        sa.idx = idx_dev; sa.n_draws = n_draws; sa.pos = pos_dev; sa.out = out_dev; sa.counts_out = counts_dev;
+        const int rc = launch_mid(c, sa, n);
+        if (rc <= 0) return rc;
+    }
+    if (n == 5) {
+        const int rc = launch_lanes(c, a);
+        if (rc <= 0) return rc;
     }
     return launch_general(c, a);
 }
