@@ -253,6 +253,17 @@ def run_reference(args):
     return 0
 
 
+def kernel_name(n, model):
+    """ the kernel ldpgta_api.cu::run_uniform dispatches draws of n reads to """
+    if n <= 4:
+        return 'k_small<%d,8,10>' % n
+    if n == 5 and model == 'homogeneous':
+        return 'k_mid<5,5>'
+    if n <= (12 if model == 'homogeneous' else 11):
+        return 'k_lanes<%d,%d>' % (n, {5: 3, 6: 3, 7: 3, 8: 4}.get(n, 5))
+    return 'k_general (n=%d)' % n
+
+
 def workload_config(args, n_windows, n_reads):
     tag = 'configs[1]' if (args.max_reads == 4 and args.depth == 0.1 and not args.windows and args.model == 'homogeneous') else 'exploration run'
     return {'workload': '%s: 22-autosome synthetic embryo, depth %.2fx, homogeneous model, monosomy/disomy/SPH/BPH' % (tag, args.depth),
@@ -498,7 +509,7 @@ def main():
                 'api': 'Engine.likelihoods_uniform -> ldpgta_likelihoods_uniform (pinned host buffers)',
                 'offsets_api_ms_per_step': e2e_offsets_ms},
         'gpu_launches': int(launches),
-        'roofline': {'bound': 'hbm', 'kernel': 'k_small<%d,8,10>' % n if n <= 4 else ('k_mid<%d,5>' % n if n <= 6 else 'k_general (n=%d)' % n), 'achieved': achieved_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
+        'roofline': {'bound': 'hbm', 'kernel': kernel_name(n, args.model), 'achieved': achieved_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
                      'frac': achieved_gbs / hbm_peak, 'traffic': traffic, 'peak_source': peak_src,
                      'algorithmic_bytes_per_draw': bytes_per_draw, 'kernel_ms': k_ms},
         'int_roofline': {'bound': 'popc', 'achieved': achieved_wordops, 'peak': int_peak, 'unit': 'word AND+POPC/s',
