@@ -134,7 +134,9 @@ int ldpgta_likelihoods_batch(ldpgta_ctx *ctx, int model_kind, const int32_t *rea
 /* The same for draws that all hold n reads (n = min(R-1, max_reads), ANEUPLOIDY_TEST.py:229, is
  * one value for all windows with R > max_reads): read_idx[n_draws][n], no offsets.  With
  * page-locked buffers (ldpgta_host_alloc) the call streams chunks through upload -> index
- * validation + kernel -> download on three streams; this is the call bench.py times for `e2e`. */
+ * validation + kernel -> download on three streams, and a call that repeats the previous call's
+ * shape and buffers replays the whole pipeline as one CUDA graph; this is the call bench.py times
+ * for `e2e`. */
 int ldpgta_likelihoods_uniform(ldpgta_ctx *ctx, int model_kind, int n, const int32_t *read_idx,
                                int64_t n_draws, const double *proportions, double *out);
 
@@ -148,6 +150,8 @@ int ldpgta_synchronize(ldpgta_ctx *ctx);
 uint64_t ldpgta_stream(const ldpgta_ctx *ctx);
 /* number of kernels this context has launched since creation */
 int64_t ldpgta_launch_count(const ldpgta_ctx *ctx);
+/* number of host-pipeline calls that ran as one CUDA graph launch (see ldpgta_likelihoods_uniform) */
+int64_t ldpgta_graph_replays(const ldpgta_ctx *ctx);
 
 /* LLR + reductions of statistics() (ANEUPLOIDY_TEST.py:78-90, 51-56, 65-76, 289-325) for one
  * chromosome shard.  lik[n_draws][4] as produced above, windows = consecutive runs of draws:

@@ -43,6 +43,7 @@ SYMBOLS = (
     ('ldpgta_synchronize', _c.c_int, [_P]),
     ('ldpgta_stream', _c.c_uint64, [_P]),
     ('ldpgta_launch_count', _c.c_int64, [_P]),
+    ('ldpgta_graph_replays', _c.c_int64, [_P]),
     ('ldpgta_window_stats', _c.c_int, [_P, _P, _P, _c.c_int64, _c.c_int, _P, _P, _P]),
     ('ldpgta_finish_chromosome', _c.c_int, [_P, _c.c_int, _c.c_int, _P]),
     ('ldpgta_bin_stats', _c.c_int, [_P, _P, _c.c_int, _P, _c.c_int64, _P, _c.c_int64, _P]),

@@ -168,6 +168,11 @@ struct ldpgta_ctx {
     int64_t llr_draws = -1, llr_windows = -1;
     int64_t *d_llr_off = nullptr;  size_t d_llr_off_bytes = 0;
     unsigned int *d_flag = nullptr, *h_flag = nullptr;     // device-side index validation of the pipelined host path
+    // the pipelined host path as a CUDA graph, replayed while the call signature repeats
+    cudaGraphExec_t pipe_exec = nullptr;
+    uint64_t pipe_key = 0, pipe_seen = 0, pipe_bad = 0;
+    int64_t pipe_launches = 0, pipe_replays = 0;
+    cudaEvent_t ev_fork = nullptr, ev_join_in = nullptr, ev_join_out = nullptr;
 
     // colourings of the high reads used by the three-block polynomial, one list per h = n - 5 (built on first use)
     uint64_t *hi_terms[14] = {};

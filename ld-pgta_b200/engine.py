@@ -231,6 +231,11 @@ class Engine:
     def launch_count(self):
         return int(self.lib.ldpgta_launch_count(self._ctx))
 
+    @property
+    def graph_replays(self):
+        """ host-pipeline calls served by one CUDA graph launch """
+        return int(self.lib.ldpgta_graph_replays(self._ctx))
+
     # ---- reductions -----------------------------------------------------------
     def window_stats(self, lik, window_offsets, n_cols, want_llr=True):
         """ LLRs, per-window mean / sample variance and the chromosome partial sums

@@ -624,3 +624,52 @@ def test_uniform_host_api_pipeline():
         with pytest.raises(ValueError):
             eng.likelihoods_uniform(L.HOMOGENEOUS, np.zeros(8, np.int32))
         assert eng.likelihoods_uniform(L.HOMOGENEOUS, np.zeros((0, 4), np.int32)).shape == (0, 4)
+
+
+def test_host_pipeline_graph_replay():
+    """ Calls that repeat the previous call's shape and page-locked buffers replay one CUDA graph: refilled buffers must
+    give the new results, other shapes in between must not disturb it, bad indices must still be caught, and the table
+    kernel's global scratch (17 reads) must survive a reallocation between replays. """
+    rng = np.random.default_rng(99)
+    n_hap, n_reads = 2504, 400
+    rows = ld_rows(rng, n_reads, n_hap)
+    with L.Engine([n_hap]) as eng:
+        eng.upload_read_masks(0, rows)
+
+        def draws(n_draws, n):
+            idx = rng.integers(0, n_reads, size=(n_draws, 1), dtype=np.int32) + np.arange(n, dtype=np.int32) * 3
+            return (idx % n_reads).astype(np.int32)
+
+        def check(pin_i, pin_o, idx, n_check=64):
+            pin_i.array[:] = idx
+            got = eng.likelihoods_uniform(L.HOMOGENEOUS, pin_i.array, out=pin_o.array)
+            pick = rng.choice(len(idx), min(n_check, len(idx)), replace=False)
+            n = idx.shape[1]
+            ref = C.batch([rows], [n_hap], idx[pick].reshape(-1), np.arange(0, len(pick) * n + 1, n), 0)
+            assert max_rel(got[pick], ref) < LIK_TOL
+
+        a_i, a_o = L.PinnedArray((50000, 4), np.int32), L.PinnedArray((50000, 4), np.float64)
+        b_i, b_o = L.PinnedArray((3000, 9), np.int32), L.PinnedArray((3000, 4), np.float64)
+        c_i, c_o = L.PinnedArray((40, 17), np.int32), L.PinnedArray((40, 4), np.float64)
+        d_i, d_o = L.PinnedArray((400, 17), np.int32), L.PinnedArray((400, 4), np.float64)
+        for _ in range(4):                                   # eager, eager/capture, replay, replay -- new contents every time
+            check(a_i, a_o, draws(50000, 4))
+        launches = eng.launch_count
+        check(a_i, a_o, draws(50000, 4))
+        assert eng.launch_count > launches                   # replays are counted as kernel launches too
+        assert eng.graph_replays >= 3
+        for _ in range(3):
+            check(b_i, b_o, draws(3000, 9))
+        check(a_i, a_o, draws(50000, 4))                     # back to the first shape: its graph was replaced, still correct
+        a_i.array[:] = draws(50000, 4)
+        a_i.array[31234, 2] = n_reads + 5
+        for _ in range(3):                                   # the failing call is eager, captured or replayed: always caught
+            with pytest.raises(L.LdpgtaError, match='read index %d at %d is outside' % (n_reads + 5, 31234 * 4 + 2)):
+                eng.likelihoods_uniform(L.HOMOGENEOUS, a_i.array, out=a_o.array)
+        check(a_i, a_o, draws(50000, 4))
+        for _ in range(3):
+            check(c_i, c_o, draws(40, 17), n_check=6)        # tables in global scratch, one slice per resident CTA (40 CTAs)
+        check(d_i, d_o, draws(400, 17), n_check=6)           # more CTAs: the scratch is reallocated
+        for _ in range(3):
+            check(c_i, c_o, draws(40, 17), n_check=6)        # a stale graph would write through the freed scratch
+        assert eng.graph_replays >= 8
