@@ -140,6 +140,17 @@ int ldpgta_likelihoods_batch(ldpgta_ctx *ctx, int model_kind, const int32_t *rea
 int ldpgta_likelihoods_uniform(ldpgta_ctx *ctx, int model_kind, int n, const int32_t *read_idx,
                                int64_t n_draws, const double *proportions, double *out);
 
+/* The bootstrap loop with the draws made on the device (pick_reads, ANEUPLOIDY_TEST.py:226-233, for all
+ * windows at once): window w holds the read rows window_reads[window_offsets[w] .. window_offsets[w+1])
+ * and gets draw_offsets[w+1] - draw_offsets[w] draws of n distinct reads each (uniform over n-subsets;
+ * Philox4x32-10 counter-based generator, draw d is a pure function of (seed, d), so results do not
+ * depend on the launch shape).  Only the window lists travel up, not the draws: at 1000 subsamples
+ * per window that is 30x less than the indices.  out[n_draws][4]; idx_out (optional) [n_draws][n]
+ * returns the draws.  Not the reference's MT19937 stream -- use ldpgta_likelihoods_batch to replay it. */
+int ldpgta_bootstrap_uniform(ldpgta_ctx *ctx, int model_kind, int n, const int64_t *window_offsets,
+                             const int32_t *window_reads, int64_t n_windows, const int64_t *draw_offsets,
+                             uint64_t seed, const double *proportions, double *out, int32_t *idx_out);
+
 /* Same computation for draws of one size n with everything already resident in HBM:
  * read_idx_dev[n_draws][n], out_dev[n_draws][4].  Asynchronous on the context's stream;
  * ldpgta_synchronize() waits.  This is the call bench.py times for `value`. */

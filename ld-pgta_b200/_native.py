@@ -39,6 +39,7 @@ SYMBOLS = (
     ('ldpgta_get_likelihoods', _c.c_int, [_P, _c.c_int, _P, _P, _c.c_int, _P, _c.c_int, _P, _P]),
     ('ldpgta_likelihoods_batch', _c.c_int, [_P, _c.c_int, _P, _P, _c.c_int64, _P, _P]),
     ('ldpgta_likelihoods_uniform', _c.c_int, [_P, _c.c_int, _c.c_int, _P, _c.c_int64, _P, _P]),
+    ('ldpgta_bootstrap_uniform', _c.c_int, [_P, _c.c_int, _c.c_int, _P, _P, _c.c_int64, _P, _c.c_uint64, _P, _P, _P]),
     ('ldpgta_likelihoods_uniform_dev', _c.c_int, [_P, _c.c_int, _c.c_int, _P, _c.c_int64, _P, _P]),
     ('ldpgta_synchronize', _c.c_int, [_P]),
     ('ldpgta_stream', _c.c_uint64, [_P]),

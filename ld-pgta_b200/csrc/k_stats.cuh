@@ -365,4 +365,54 @@ __global__ void k_sanitize_idx(int32_t *__restrict__ idx, int64_t count, uint32_
     if (bad) atomicOr(flag, 1u);
 }
 
+// ---- pick_reads (ANEUPLOIDY_TEST.py:226-233) on the device ------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011): a counter-based generator, so draw d of a call is a pure function of (seed, d).
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t *out)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// One thread per draw: K distinct reads of the draw's window, uniformly over K-subsets (Floyd's algorithm; for
+// i = 0..K-1: t uniform in [0, R-K+i], taken unless already chosen, else R-K+i), written as read-mask rows.
+// Draw d belongs to the window w with draw_off[w] <= d < draw_off[w+1]; its reads are win_reads[win_off[w] ...].
+// The j-th random integer of draw d is mulhi64(x, bound) with x = 64 bits of Philox(counter = (d, j/2), key = seed).
+template <int K>
+__global__ void k_sample_draws(const int64_t *__restrict__ draw_off, const int64_t *__restrict__ win_off,
+                               const int32_t *__restrict__ win_reads, int64_t n_windows, int64_t n_draws, uint64_t seed,
+                               int32_t *__restrict__ idx_out)
+{
+    for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < n_draws; d += (int64_t)gridDim.x * blockDim.x) {
+        int64_t lo = 0, hi = n_windows;                    // upper_bound(draw_off, d) - 1
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (draw_off[mid] <= d) lo = mid; else hi = mid;
+        }
+        const int64_t base = win_off[lo];
+        const uint32_t R = (uint32_t)(win_off[lo + 1] - base);
+        uint32_t pick[K];
+        uint32_t rnd[4];
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            if ((i & 1) == 0)
+                philox4x32_10((uint32_t)d, (uint32_t)((uint64_t)d >> 32), (uint32_t)(i >> 1), 0u, (uint32_t)seed, (uint32_t)(seed >> 32), rnd);
+            const uint64_t x = (i & 1) ? ((uint64_t)rnd[3] << 32 | rnd[2]) : ((uint64_t)rnd[1] << 32 | rnd[0]);
+            const uint32_t top = R - K + i;
+            uint32_t t = (uint32_t)__umul64hi(x, (uint64_t)top + 1ull);
+            bool dup = false;
+#pragma unroll
+            for (int j = 0; j < i; ++j) dup |= pick[j] == t;
+            pick[i] = dup ? top : t;
+        }
+#pragma unroll
+        for (int i = 0; i < K; ++i) idx_out[d * K + i] = win_reads[base + pick[i]];
+    }
+}
+
 }  // namespace ldpgta

@@ -290,6 +290,15 @@ static int run_pipelined(ldpgta_ctx *c, int kind, int n0, const int32_t *read_id
     return 0;
 }
 
+template <int K>
+static void launch_sample(ldpgta_ctx *c, const int64_t *d_doff, const int64_t *d_woff, const int32_t *d_wreads, int64_t n_windows,
+                          int64_t n_draws, uint64_t seed, int32_t *d_idx)
+{
+    const unsigned blocks = (unsigned)std::min<int64_t>((n_draws + 127) / 128, (int64_t)c->sm_count * 16);
+    k_sample_draws<K><<<blocks, 128, 0, c->stream>>>(d_doff, d_woff, d_wreads, n_windows, n_draws, seed, d_idx);
+    c->launches++;
+}
+
 static int check_uniform_size(int kind, int64_t n)
 {
     if (n < 2 || n > MAXN)
@@ -783,6 +792,73 @@ int ldpgta_likelihoods_uniform(ldpgta_ctx *c, int kind, int n, const int32_t *re
     if (!pin_in) { memcpy(h_idx, read_idx, (size_t)n_draws * n * 4); src = h_idx; }
     const int rc = run_pipelined(c, kind, n, src, nullptr, n_draws, proportions, pin_out ? out : h_out);
     if (rc) return rc;
+    if (!pin_out) memcpy(out, h_out, out_b);
+    return 0;
+}
+
+int ldpgta_bootstrap_uniform(ldpgta_ctx *c, int kind, int n, const int64_t *window_offsets, const int32_t *window_reads,
+                             int64_t n_windows, const int64_t *draw_offsets, uint64_t seed, const double *proportions,
+                             double *out, int32_t *idx_out)
+{
+    if (!c || !window_offsets || !draw_offsets || !out || n_windows < 0) return fail(LDPGTA_E_INVALID, "bad arguments");
+    LDPGTA_CUDA(cudaSetDevice(c->device));
+    if (int rc = check_kind(c, kind, proportions)) return rc;
+    if (int rc = check_uniform_size(kind, n)) return rc;
+    if (window_offsets[0] != 0 || draw_offsets[0] != 0) return fail(LDPGTA_E_INVALID, "offsets must start at 0");
+    const int64_t n_draws = draw_offsets[n_windows], n_wreads = window_offsets[n_windows];
+    if (n_draws == 0) return 0;
+    if (!window_reads) return fail(LDPGTA_E_INVALID, "null window_reads");
+    for (int64_t w = 0; w < n_windows; ++w) {
+        const int64_t R = window_offsets[w + 1] - window_offsets[w], nd = draw_offsets[w + 1] - draw_offsets[w];
+        if (nd < 0 || R < 0) return fail(LDPGTA_E_INVALID, "offsets must not decrease (window %lld)", (long long)w);
+        if (nd > 0 && R < n) return fail(LDPGTA_E_INVALID, "window %lld has %lld reads, fewer than the %d of a draw", (long long)w, (long long)R, n);
+        if (R > 0x7fffffff) return fail(LDPGTA_E_INVALID, "window %lld has too many reads", (long long)w);
+    }
+    for (int64_t k = 0; k < n_wreads; ++k)
+        if (window_reads[k] < 0 || window_reads[k] >= c->n_reads)
+            return fail(LDPGTA_E_INVALID, "read index %d at %lld is outside 0..%lld", window_reads[k], (long long)k, (long long)c->n_reads - 1);
+
+    auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t woff_b = pad((size_t)(n_windows + 1) * 8), wr_b = pad((size_t)n_wreads * 4);
+    const size_t idx_b = pad((size_t)n_draws * n * 4), out_b = (size_t)n_draws * 32;
+    if (int rc = ensure_dev(c, 2 * woff_b + wr_b + idx_b + out_b)) return rc;
+    char *p = (char *)c->d_buf;
+    int64_t *d_woff = (int64_t *)p; p += woff_b;
+    int64_t *d_doff = (int64_t *)p; p += woff_b;
+    int32_t *d_wreads = (int32_t *)p; p += wr_b;
+    int32_t *d_idx = (int32_t *)p; p += idx_b;
+    double *d_out = (double *)p;
+    if (int rc = ensure_pipeline(c, 9)) return rc;
+    LDPGTA_CUDA(cudaMemcpyAsync(d_woff, window_offsets, (size_t)(n_windows + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    LDPGTA_CUDA(cudaMemcpyAsync(d_doff, draw_offsets, (size_t)(n_windows + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    LDPGTA_CUDA(cudaMemcpyAsync(d_wreads, window_reads, (size_t)n_wreads * 4, cudaMemcpyHostToDevice, c->stream));
+    switch (n) {
+#define LDPGTA_K(K_) case K_: launch_sample<K_>(c, d_doff, d_woff, d_wreads, n_windows, n_draws, seed, d_idx); break;
+        LDPGTA_K(2) LDPGTA_K(3) LDPGTA_K(4) LDPGTA_K(5) LDPGTA_K(6) LDPGTA_K(7) LDPGTA_K(8) LDPGTA_K(9) LDPGTA_K(10)
+        LDPGTA_K(11) LDPGTA_K(12) LDPGTA_K(13) LDPGTA_K(14) LDPGTA_K(15) LDPGTA_K(16) LDPGTA_K(17) LDPGTA_K(18)
+#undef LDPGTA_K
+    }
+    LDPGTA_CUDA(cudaGetLastError());
+    // kernel and download in chunks: the copy of chunk i runs under the kernel of chunk i + 1
+    const bool pin_out = is_page_locked(out);
+    double *h_out = out;
+    if (!pin_out) {
+        if (int rc = ensure_pin(c, out_b)) return rc;
+        h_out = (double *)c->h_pin;
+    }
+    const int64_t n_chunks = std::max<int64_t>(1, std::min<int64_t>(8, n_draws / 32768));
+    const int64_t per = ((n_draws + n_chunks - 1) / n_chunks + 63) & ~(int64_t)63;
+    int ci = 0;
+    for (int64_t d0 = 0; d0 < n_draws; d0 += per, ++ci) {
+        const int64_t nd = std::min(per, n_draws - d0);
+        if (int rc = run_uniform(c, kind, n, d_idx + d0 * n, nd, nullptr, proportions, d_out + 4 * d0, nullptr)) return rc;
+        LDPGTA_CUDA(cudaEventRecord(c->ev_k[ci], c->stream));
+        LDPGTA_CUDA(cudaStreamWaitEvent(c->s_out, c->ev_k[ci], 0));
+        LDPGTA_CUDA(cudaMemcpyAsync(h_out + 4 * d0, d_out + 4 * d0, (size_t)nd * 32, cudaMemcpyDeviceToHost, c->s_out));
+    }
+    if (idx_out) LDPGTA_CUDA(cudaMemcpyAsync(idx_out, d_idx, (size_t)n_draws * n * 4, cudaMemcpyDeviceToHost, c->stream));
+    LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
+    LDPGTA_CUDA(cudaStreamSynchronize(c->s_out));
     if (!pin_out) memcpy(out, h_out, out_b);
     return 0;
 }

@@ -214,6 +214,26 @@ class Engine:
         N.check(self.lib.ldpgta_likelihoods_uniform(self._ctx, kind, n, N.ptr(idx), nd, N.ptr(prop), N.ptr(out)))
         return out
 
+    def bootstrap_uniform(self, kind, n, window_offsets, window_reads, draw_offsets, seed, proportions=None, out=None,
+                          want_draws=False):
+        """ Draws made on the device (pick_reads for all windows at once) and evaluated: window w = read rows
+        window_reads[window_offsets[w]:window_offsets[w+1]], draw_offsets[w+1]-draw_offsets[w] draws of n reads.
+        Returns float64[n_draws, 4] (and the draws int32[n_draws, n] with want_draws). """
+        woff = np.ascontiguousarray(window_offsets, dtype=np.int64)
+        wr = np.ascontiguousarray(window_reads, dtype=np.int32)
+        doff = np.ascontiguousarray(draw_offsets, dtype=np.int64)
+        if len(woff) != len(doff):
+            raise ValueError('window_offsets and draw_offsets must have the same length')
+        nd = int(doff[-1])
+        if out is None:
+            out = np.empty((nd, 4), dtype=np.float64)
+        idx = np.empty((nd, n), dtype=np.int32) if want_draws else None
+        prop = None if proportions is None else np.ascontiguousarray(proportions, dtype=np.float64)
+        N.check(self.lib.ldpgta_bootstrap_uniform(self._ctx, kind, n, N.ptr(woff), N.ptr(wr), len(woff) - 1, N.ptr(doff),
+                                                  ctypes.c_uint64(int(seed) & (2 ** 64 - 1)), N.ptr(prop), N.ptr(out),
+                                                  N.ptr(idx) if want_draws else None))
+        return (out, idx) if want_draws else out
+
     def likelihoods_uniform_dev(self, kind, n, idx_dev_ptr, n_draws, out_dev_ptr, proportions=None):
         """ Device-resident variant (asynchronous on the engine's stream). """
         prop = None if proportions is None else np.ascontiguousarray(proportions, dtype=np.float64)

@@ -13,7 +13,8 @@ likelihoods.  Here the same quantities are index arrays:
     windows()        build_gw_dict as arrays: window borders + CSR of read rows, fixed or adaptive, with the
                      reference's quirks (offset, adaptive growth in 10 kbp steps, last window dropped, empty
                      windows kept)
-    plan()           all bootstrap draws of all windows by vectorised sampling without replacement
+    plan()           all bootstrap draws of all windows by vectorised sampling without replacement on the host, or
+    bootstrap_on_device()  the draws made on the device (ldpgta_bootstrap_uniform, Philox + Floyd): only window lists go up
     run()            draws -> likelihoods on the device -> LLR statistics on the device -> PackedResult, which can
                      also be unfolded into the reference's (likelihoods, genomic_windows, fraction_of_matches)
 
@@ -208,8 +209,8 @@ class PackedSample:
 
     # ---- pick_reads / effective_number_of_subsamples (:226-248) for all windows at once ---------------------------
     @staticmethod
-    def plan(windows, min_reads, max_reads, subsamples, rng):
-        """ (evaluated windows, draw_offsets, [(draw rows, read_idx[n_draws_k][k]) per draw size k]). """
+    def plan_counts(windows, min_reads, max_reads, subsamples):
+        """ (evaluated windows, draw_offsets over them, draws per window, reads per draw per window). """
         R = windows.sizes
         effN = np.zeros(len(R), dtype=np.int64)
         big = (R >= min_reads) & (R > max_reads)
@@ -225,7 +226,13 @@ class PackedSample:
         evaluated = np.flatnonzero(effN > 0)
         draw_offsets = np.zeros(len(evaluated) + 1, dtype=np.int64)
         np.cumsum(effN[evaluated], out=draw_offsets[1:])
-        k_of = np.minimum(R - 1, max_reads)
+        return evaluated, draw_offsets, effN, np.minimum(R - 1, max_reads)
+
+    @classmethod
+    def plan(cls, windows, min_reads, max_reads, subsamples, rng):
+        """ (evaluated windows, draw_offsets, [(draw rows, read_idx[n_draws_k][k]) per draw size k]), draws sampled on the host. """
+        evaluated, draw_offsets, effN, k_of = cls.plan_counts(windows, min_reads, max_reads, subsamples)
+        R = windows.sizes
         groups = []
         win_of_draw = np.repeat(evaluated, effN[evaluated])
         k_draw = k_of[win_of_draw]
@@ -237,6 +244,31 @@ class PackedSample:
             groups.append((rows, idx))
         return evaluated, draw_offsets, groups
 
+    def bootstrap_on_device(self, windows, min_reads, max_reads, subsamples, seed, want_draws=False):
+        """ plan + evaluate with the draws made on the device (ldpgta_bootstrap_uniform): only the window lists go up.
+        Returns (evaluated windows, draw_offsets, draw groups or None, likelihoods[n_draws][4]). """
+        evaluated, draw_offsets, effN, k_of = self.plan_counts(windows, min_reads, max_reads, subsamples)
+        n_draws = int(draw_offsets[-1])
+        lik = np.empty((n_draws, 4), dtype=np.float64)
+        groups = [] if want_draws else None
+        counts = effN[evaluated]
+        for k in np.unique(k_of[evaluated]).tolist():
+            if self.kind == N.DISTANT_ADMIXTURE and k == 5:
+                raise AttributeError("'distant_admixture' object has no attribute 'likelihoods5'")
+            per_window = np.where(k_of == k, effN, 0)                    # windows of other draw sizes get no draws in this call
+            doff = np.zeros(len(per_window) + 1, dtype=np.int64)
+            np.cumsum(per_window, out=doff[1:])
+            got = self.engine.bootstrap_uniform(self.kind, k, windows.offsets, windows.reads, doff, seed + k,
+                                                proportions=self.proportions, want_draws=want_draws)
+            sel = np.flatnonzero(k_of[evaluated] == k)                    # evaluated windows of this size, in order
+            rows = np.concatenate([np.arange(draw_offsets[i], draw_offsets[i + 1]) for i in sel.tolist()]) if len(sel) else np.empty(0, np.int64)
+            if want_draws:
+                lik[rows] = got[0]
+                groups.append((rows, got[1]))
+            else:
+                lik[rows] = got
+        return evaluated, draw_offsets, groups, lik
+
     def evaluate(self, draw_groups, n_draws):
         """ likelihoods [n_draws][4] for groups of uniform draws (rows of the output, read_idx[.][k]). """
         lik = np.empty((n_draws, 4), dtype=np.float64)
@@ -246,13 +278,17 @@ class PackedSample:
             lik[rows] = self.engine.likelihoods_uniform(self.kind, idx, proportions=self.proportions)
         return lik
 
-    def run(self, window_size=100000, subsamples=32, offset=0, min_reads=6, max_reads=4, min_score=2, rng=None):
-        """ bootstrap() + statistics() (ANEUPLOIDY_TEST.py:250-325) on arrays. """
-        rng = np.random.default_rng() if rng is None else rng
+    def run(self, window_size=100000, subsamples=32, offset=0, min_reads=6, max_reads=4, min_score=2, rng=None, seed=None,
+            want_draws=True):
+        """ bootstrap() + statistics() (ANEUPLOIDY_TEST.py:250-325) on arrays.  The draws come from `rng` (a numpy
+        Generator, sampled on the host) or, when `seed` is given, from the device-side sampler. """
         win = self.windows(window_size, offset, min_reads, max_reads, min_score)
-        evaluated, draw_offsets, groups = self.plan(win, min_reads, max_reads, subsamples, rng)
-        n_draws = int(draw_offsets[-1])
-        lik = self.evaluate(groups, n_draws)
+        if seed is not None:
+            evaluated, draw_offsets, groups, lik = self.bootstrap_on_device(win, min_reads, max_reads, subsamples, int(seed), want_draws)
+        else:
+            rng = np.random.default_rng() if rng is None else rng
+            evaluated, draw_offsets, groups = self.plan(win, min_reads, max_reads, subsamples, rng)
+            lik = self.evaluate(groups, int(draw_offsets[-1]))
         mean_var = chrom = None
         if len(evaluated):
             counts = np.diff(draw_offsets)

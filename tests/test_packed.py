@@ -107,22 +107,22 @@ def test_packed_sample_matches_reference(name, golden_inputs):
                 worst = max(worst, max(rel_err(a, b) for a, b in zip(g, r)))
         assert worst <= 1e-12, worst
         # a full packed run: every window the reference evaluates is evaluated, draws are valid, statistics finite
-        res = ps.run(cfg['window_size'], cfg['subsamples'], cfg['offset'], cfg['min_reads'], cfg['max_reads'], cfg['min_score'],
-                     rng=np.random.default_rng(1))
-        lik, gw, frac = res.as_reference()
-        assert list(lik) == list(out['likelihoods']) and list(gw) == list(out['windows'])
-        assert [len(v) for v in lik.values()] == [len(v) for v in out['likelihoods'].values()]
-        sizes = dict(zip(map(tuple, win.borders.tolist()), win.sizes.tolist()))
-        for rows, idx in res.draws:
-            assert all(len(set(d)) == len(d) for d in idx.tolist())
-        for w, ids in gw.items():
-            assert set(ids) == set(out['windows'][w])
-        assert np.isfinite(res.likelihoods).all() and (res.likelihoods >= 0).all() and (res.likelihoods <= 1).all()
-        stats = res.llr_per_chromosome()
-        oracle_stats = O.statistics({w: [O.likelihoods_tuple(*l) for l in v] for w, v in lik.items()}, gw)
-        for pair, s in stats.items():
-            for key in ('mean_of_mean', 'std_of_mean', 'fraction_of_negative_LLRs'):
-                assert rel_err(s[key], oracle_stats['LLRs_per_chromosome'][pair][key]) <= 1e-9 or abs(s[key] - oracle_stats['LLRs_per_chromosome'][pair][key]) < 1e-15
+        for mode in ({'rng': np.random.default_rng(1)}, {'seed': 5}):           # host-sampled and device-sampled draws
+            res = ps.run(cfg['window_size'], cfg['subsamples'], cfg['offset'], cfg['min_reads'], cfg['max_reads'], cfg['min_score'], **mode)
+            lik, gw, frac = res.as_reference()
+            assert list(lik) == list(out['likelihoods']) and list(gw) == list(out['windows'])
+            assert [len(v) for v in lik.values()] == [len(v) for v in out['likelihoods'].values()]
+            sizes = dict(zip(map(tuple, win.borders.tolist()), win.sizes.tolist()))
+            for rows, idx in res.draws:
+                assert all(len(set(d)) == len(d) for d in idx.tolist())
+            for w, ids in gw.items():
+                assert set(ids) == set(out['windows'][w])
+            assert np.isfinite(res.likelihoods).all() and (res.likelihoods >= 0).all() and (res.likelihoods <= 1).all()
+            stats = res.llr_per_chromosome()
+            oracle_stats = O.statistics({w: [O.likelihoods_tuple(*l) for l in v] for w, v in lik.items()}, gw)
+            for pair, s in stats.items():
+                for key in ('mean_of_mean', 'std_of_mean', 'fraction_of_negative_LLRs'):
+                    assert rel_err(s[key], oracle_stats['LLRs_per_chromosome'][pair][key]) <= 1e-9 or abs(s[key] - oracle_stats['LLRs_per_chromosome'][pair][key]) < 1e-15
     panel.close()
 
 
@@ -161,3 +161,85 @@ def test_aneuploidy_test_packed_option(name, tmp_path, golden_inputs):
     with open(d / 'results' / 's.chr21.LLR.p', 'rb') as f:
         saved = pickle.load(f)
     assert list(saved) == list(lik) and type(next(iter(saved.values()))[0]).__name__ == 'likelihoods_tuple'
+
+
+def philox4x32_10(c, k):
+    """ numpy restatement of Philox4x32-10 (Salmon et al., SC'11): c uint32[n,4], k uint32[2] -> uint32[n,4] """
+    c = c.astype(np.uint64).copy()
+    k0, k1 = np.uint64(k[0]), np.uint64(k[1])
+    M0, M1, mask = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c[:, 0], M1 * c[:, 2]
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & mask, p1 >> np.uint64(32), p1 & mask
+        c = np.stack([hi1 ^ c[:, 1] ^ k0, lo1, hi0 ^ c[:, 3] ^ k1, lo0], axis=1)
+        k0, k1 = (k0 + np.uint64(0x9E3779B9)) & mask, (k1 + np.uint64(0xBB67AE85)) & mask
+    return c.astype(np.uint32)
+
+
+def sample_draws_reference(window_offsets, window_reads, draw_offsets, n, seed):
+    """ what k_sample_draws must produce: Floyd's algorithm on Philox integers, draw by draw """
+    n_draws = int(draw_offsets[-1])
+    win = np.searchsorted(draw_offsets, np.arange(n_draws), side='right') - 1
+    base, R = window_offsets[win], (window_offsets[win + 1] - window_offsets[win])
+    d = np.arange(n_draws, dtype=np.uint64)
+    key = np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], dtype=np.uint32)
+    picks = np.empty((n_draws, n), dtype=np.int64)
+    for i in range(n):
+        if i % 2 == 0:
+            ctr = np.stack([d & np.uint64(0xFFFFFFFF), d >> np.uint64(32), np.full(n_draws, i // 2, np.uint64), np.zeros(n_draws, np.uint64)], axis=1)
+            rnd = philox4x32_10(ctr.astype(np.uint32), key).astype(np.uint64)
+        x = (rnd[:, 3] << np.uint64(32) | rnd[:, 2]) if i % 2 else (rnd[:, 1] << np.uint64(32) | rnd[:, 0])
+        top = R - n + i
+        t = np.array([(int(a) * (int(b) + 1)) >> 64 for a, b in zip(x.tolist(), top.tolist())], dtype=np.int64)
+        dup = (picks[:, :i] == t[:, None]).any(axis=1) if i else np.zeros(n_draws, bool)
+        picks[:, i] = np.where(dup, top, t)
+    return window_reads[base[:, None] + picks].astype(np.int32)
+
+
+def test_philox_known_answers():
+    """ Random123's published known-answer vectors for philox4x32-10 pin the restatement used as the sampler's oracle """
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = philox4x32_10(np.array([ctr], dtype=np.uint32), np.array(key, dtype=np.uint32))[0]
+        assert tuple(int(v) for v in got) == want
+
+
+@pytest.mark.gpu
+def test_device_draws_bit_exact_and_uniform():
+    import ldpgta_b200 as L
+    rng = np.random.default_rng(3)
+    n_hap, n_reads = 331, 900
+    rows = rng.integers(0, 2 ** 63, size=(n_reads, 6), dtype=np.uint64) | rng.integers(0, 2 ** 63, size=(n_reads, 6), dtype=np.uint64)
+    rows[:, -1] &= np.uint64((1 << (n_hap - 320)) - 1)
+    sizes = rng.integers(5, 60, size=40)
+    sizes[:3] = (4, 5, 7)
+    window_offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    window_reads = rng.permutation(n_reads)[:window_offsets[-1]].astype(np.int32) if window_offsets[-1] <= n_reads else rng.integers(0, n_reads, window_offsets[-1]).astype(np.int32)
+    with L.Engine([n_hap]) as eng:
+        eng.upload_read_masks(0, rows)
+        for n, seed in ((4, 12345), (3, 2 ** 63 + 11), (7, 1)):
+            per_window = np.where(sizes >= n, rng.integers(0, 50, size=len(sizes)), 0)
+            draw_offsets = np.concatenate([[0], np.cumsum(per_window)]).astype(np.int64)
+            lik, idx = eng.bootstrap_uniform(L.HOMOGENEOUS, n, window_offsets, window_reads, draw_offsets, seed, want_draws=True)
+            want = sample_draws_reference(window_offsets, window_reads, draw_offsets, n, seed)
+            assert np.array_equal(idx, want)                                   # the sampler, bit for bit
+            assert np.array_equal(lik, eng.likelihoods_uniform(L.HOMOGENEOUS, idx))     # and the likelihoods of exactly those draws
+            lik2 = eng.bootstrap_uniform(L.HOMOGENEOUS, n, window_offsets, window_reads, draw_offsets, seed)
+            assert np.array_equal(lik, lik2)
+            assert not np.array_equal(idx, eng.bootstrap_uniform(L.HOMOGENEOUS, n, window_offsets, window_reads, draw_offsets, seed + 1, want_draws=True)[1])
+        # uniformity over k-subsets: one window of 7 reads, 3 of them per draw, 35 subsets
+        woff, wr = np.array([0, 7], dtype=np.int64), np.arange(100, 107, dtype=np.int32)
+        doff = np.array([0, 140000], dtype=np.int64)
+        _, idx = eng.bootstrap_uniform(L.HOMOGENEOUS, 3, woff, wr, doff, 77, want_draws=True)
+        assert idx.min() == 100 and idx.max() == 106 and (np.diff(np.sort(idx, axis=1), axis=1) > 0).all()
+        counts = np.bincount((np.sort(idx - 100, axis=1) @ np.array([49, 7, 1])), minlength=343)
+        seen = counts[counts > 0]
+        assert len(seen) == 35 and abs(seen / 140000 - 1 / 35).max() < 0.003
+        # errors
+        from ldpgta_b200._native import LdpgtaError
+        with pytest.raises(LdpgtaError, match='fewer than'):
+            eng.bootstrap_uniform(L.HOMOGENEOUS, 8, woff, wr, doff, 1)
+        with pytest.raises(LdpgtaError, match='outside'):
+            eng.bootstrap_uniform(L.HOMOGENEOUS, 3, woff, wr + 1000, doff, 1)
