@@ -49,7 +49,7 @@ class PackedLegend:
     def encode_bases(self, bases, count):
         """ base strings -> codes; strings the legend never uses get -1 (they can not match). """
         get = self.codes.get
-        return np.fromiter((get(b, -1) for b in bases), dtype=np.int32, count=count)
+        return np.array([get(b, -1) for b in bases], dtype=np.int32).reshape(count)
 
     def match(self, pos, base):
         """ (keep, legend row, complement flag) per observation: an observed base that equals ALT selects the panel
@@ -78,6 +78,24 @@ def sample_without_replacement(rng, R, k):
     return out
 
 
+class PinnedPool:
+    """ Page-locked result buffers, reused across samples (allocating page-locked memory costs far more than a run). """
+
+    def __init__(self):
+        self.free = []
+
+    def take(self, n_draws):
+        need = max(1, int(n_draws)) * 4
+        for i, buf in enumerate(self.free):
+            if buf.array.size >= need:
+                return self.free.pop(i)
+        return N.PinnedArray((need + need // 4,), np.float64)
+
+    def give(self, buf):
+        if buf is not None and len(self.free) < 4:
+            self.free.append(buf)
+
+
 class PackedWindows:
     """ Genomic windows of one chromosome: borders[K][2] = (a, b-1) as in gw_dict's keys, CSR offsets / read rows. """
 
@@ -96,10 +114,24 @@ class PackedResult:
     """ Likelihoods of all draws of a chromosome, window-major: lik[draw_offsets[w]:draw_offsets[w+1]] belong to
     evaluated window w (borders[w]); statistics as computed on the device. """
 
-    def __init__(self, sample, windows, evaluated, draw_offsets, draws, lik, mean_var, chrom):
+    def __init__(self, sample, windows, evaluated, draw_offsets, draws, lik, mean_var, chrom, lease=None):
         self.sample, self.windows, self.evaluated = sample, windows, evaluated
         self.draw_offsets, self.draws, self.likelihoods = draw_offsets, draws, lik
         self.window_mean_var, self.chromosome = mean_var, chrom
+        self._lease = lease                 # (pool, page-locked buffer) behind `likelihoods`
+
+    def release(self):
+        """ hands the page-locked buffer behind `likelihoods` back for the next sample (the array becomes invalid) """
+        if self._lease is not None:
+            pool, buf = self._lease
+            self._lease, self.likelihoods = None, None
+            pool.give(buf)
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
 
     @property
     def borders(self):
@@ -135,11 +167,13 @@ def pack_observations(obs_tab, legend):
       obs_pos, obs_read              position and read row of every matched observation  (build_overlaps_dict, :129-139) """
     out = PackedObservations()
     n = len(obs_tab)
-    pos = np.fromiter((r[0] for r in obs_tab), dtype=np.int64, count=n)
-    names = {}
-    name = names.setdefault
-    read = np.fromiter((name(r[1], len(names)) for r in obs_tab), dtype=np.int64, count=n)
-    base = legend.encode_bases((r[2] for r in obs_tab), n)
+    cols = list(zip(*obs_tab)) if n else ((), (), ())        # one C-level pass over the tuples
+    pos = np.array(cols[0], dtype=np.int64)
+    names = dict.fromkeys(cols[1])                            # read ids in order of first appearance
+    for i, k in enumerate(names):
+        names[k] = i
+    read = np.array(list(map(names.__getitem__, cols[1])), dtype=np.int64)
+    base = legend.encode_bases(cols[2], n)
     keep, row, is_ref = legend.match(pos, base)
     out.fraction_of_matches = 1 - int((~keep).sum()) / n
     # allele table: one row per distinct (legend row, ref/alt) among the matched observations
@@ -186,12 +220,16 @@ class PackedSample:
         self.allele_rows, self.allele_complement = packed.allele_rows, packed.allele_complement
         self.read_names, self.read_offsets, self.read_alleles = packed.read_names, packed.read_offsets, packed.read_alleles
         self.obs_pos, self.obs_read = packed.obs_pos, packed.obs_read
+        if not hasattr(panel, '_result_pool'):
+            panel._result_pool = PinnedPool()
+        self.pool = panel._result_pool
         self.engine = Engine(panel.n_hap, device=panel.device if device is None else device)
         self.engine.gather_allele_rows(panel, self.allele_rows, self.allele_complement)
         self.engine.build_read_masks(self.read_alleles, self.read_offsets)
         alpha = [makeup[g] / nh for g, nh in zip(groups, panel.n_hap)]
         weight = makeup[panel.last_group] / panel.n_hap[groups.index(panel.last_group)]      # last-alpha quirk (:181-184)
         self.scores = self.engine.read_scores(self.read_alleles, self.read_offsets, alpha, weight, min_HF)
+        self._lease = None
 
     def close(self):
         self.engine.close()
@@ -249,15 +287,23 @@ class PackedSample:
         Returns (evaluated windows, draw_offsets, draw groups or None, likelihoods[n_draws][4]). """
         evaluated, draw_offsets, effN, k_of = self.plan_counts(windows, min_reads, max_reads, subsamples)
         n_draws = int(draw_offsets[-1])
-        lik = np.empty((n_draws, 4), dtype=np.float64)
+        buf = self.pool.take(n_draws)
+        lik = buf.array[:4 * n_draws].reshape(n_draws, 4)
         groups = [] if want_draws else None
-        counts = effN[evaluated]
-        for k in np.unique(k_of[evaluated]).tolist():
+        sizes = np.unique(k_of[evaluated]).tolist()
+        for k in sizes:
             if self.kind == N.DISTANT_ADMIXTURE and k == 5:
+                self.pool.give(buf)
                 raise AttributeError("'distant_admixture' object has no attribute 'likelihoods5'")
             per_window = np.where(k_of == k, effN, 0)                    # windows of other draw sizes get no draws in this call
             doff = np.zeros(len(per_window) + 1, dtype=np.int64)
             np.cumsum(per_window, out=doff[1:])
+            if len(sizes) == 1:                                          # the usual case: results land where they stay
+                got = self.engine.bootstrap_uniform(self.kind, k, windows.offsets, windows.reads, doff, seed + k,
+                                                    proportions=self.proportions, out=lik, want_draws=want_draws)
+                if want_draws:
+                    groups.append((np.arange(n_draws), got[1]))
+                continue
             got = self.engine.bootstrap_uniform(self.kind, k, windows.offsets, windows.reads, doff, seed + k,
                                                 proportions=self.proportions, want_draws=want_draws)
             sel = np.flatnonzero(k_of[evaluated] == k)                    # evaluated windows of this size, in order
@@ -267,21 +313,30 @@ class PackedSample:
                 groups.append((rows, got[1]))
             else:
                 lik[rows] = got
+        self._lease = (self.pool, buf)
         return evaluated, draw_offsets, groups, lik
 
     def evaluate(self, draw_groups, n_draws):
         """ likelihoods [n_draws][4] for groups of uniform draws (rows of the output, read_idx[.][k]). """
-        lik = np.empty((n_draws, 4), dtype=np.float64)
+        buf = self.pool.take(n_draws)
+        lik = buf.array[:4 * n_draws].reshape(n_draws, 4)
         for rows, idx in draw_groups:
             if self.kind == N.DISTANT_ADMIXTURE and idx.shape[1] == 5:
+                self.pool.give(buf)
                 raise AttributeError("'distant_admixture' object has no attribute 'likelihoods5'")
-            lik[rows] = self.engine.likelihoods_uniform(self.kind, idx, proportions=self.proportions)
+            if len(draw_groups) == 1 and len(rows) == n_draws:
+                self.engine.likelihoods_uniform(self.kind, idx, proportions=self.proportions, out=lik)
+            else:
+                lik[rows] = self.engine.likelihoods_uniform(self.kind, idx, proportions=self.proportions)
+        self._lease = (self.pool, buf)
         return lik
 
     def run(self, window_size=100000, subsamples=32, offset=0, min_reads=6, max_reads=4, min_score=2, rng=None, seed=None,
-            want_draws=True):
+            want_draws=True, keep_pinned=False):
         """ bootstrap() + statistics() (ANEUPLOIDY_TEST.py:250-325) on arrays.  The draws come from `rng` (a numpy
-        Generator, sampled on the host) or, when `seed` is given, from the device-side sampler. """
+        Generator, sampled on the host) or, when `seed` is given, from the device-side sampler.
+        keep_pinned=True leaves `likelihoods` in the page-locked buffer it was downloaded into (no copy); that view is
+        valid until the result's release() or deletion, after which the buffer serves the next sample. """
         win = self.windows(window_size, offset, min_reads, max_reads, min_score)
         if seed is not None:
             evaluated, draw_offsets, groups, lik = self.bootstrap_on_device(win, min_reads, max_reads, subsamples, int(seed), want_draws)
@@ -295,7 +350,12 @@ class PackedSample:
             n_cols = int(counts.min())
             _llr, mean_var, partials = self.engine.window_stats(lik, draw_offsets, n_cols, want_llr=False)
             chrom = finish_chromosome(partials, n_cols, int(counts[0]))
-        return PackedResult(self, win, evaluated, draw_offsets, groups, lik, mean_var, chrom)
+        lease, self._lease = self._lease, None
+        if not keep_pinned and lease is not None:
+            lik = np.array(lik)
+            lease[0].give(lease[1])
+            lease = None
+        return PackedResult(self, win, evaluated, draw_offsets, groups, lik, mean_var, chrom, lease)
 
 
 def build_windows(obs_pos, obs_read, scores, window_size, offset, min_reads, min_score):

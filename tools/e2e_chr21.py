@@ -66,6 +66,18 @@ for rep in range(3):
     t1 = time.time(); ref_lik, ref_gw, _ = res.as_reference(); phases2['unfold into the reference dicts (optional)'] = time.time() - t1
     ps.close()
     per_sample.append({'total_s': time.time() - t, 'phases_s': phases2})
+# config 5's regime: 1000 subsamples per window, draws made on the device (only the window lists go up)
+deep = []
+for rep in range(3):
+    t = time.time()
+    ps = PackedSample(obs, panel, {'ALL'}, 0.05)
+    t1 = time.time()
+    res1000 = ps.run(100000, 1000, 0, 6, 4, 2, seed=rep, want_draws=False, keep_pinned=True)
+    t2 = time.time()
+    ps.close()
+    deep.append({'total_s': time.time() - t, 'pack_s': t1 - t, 'run_s': t2 - t1, 'window_likelihoods': int(res1000.draw_offsets[-1])})
+    res1000.release()
+packed['subsamples_1000_device_draws'] = deep
 assert list(ref_gw) == list(gw) and list(ref_lik) == list(lik)
 assert all(set(a) == set(b) for a, b in zip(ref_gw.values(), gw.values()))
 packed['per_sample_runs'] = per_sample
