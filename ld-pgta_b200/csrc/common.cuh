@@ -80,6 +80,31 @@ __device__ __forceinline__ void csa(u64 a, u64 b, u64 c, u64 &sum, u64 &carry)
     carry = (a & b) | (ab & c);
 }
 
+// The same with the two LOP3s spelled out.  When a, b, c are themselves ANDs, the compiler folds each AND into the
+// xor chain ((a0 & a1) ^ x is one LOP3) and then has to form the ANDs again for the majority: 6 to 6.75 LOP3 per 32-bit
+// half of a triple instead of 5 (SASS of k_general's main loop).  Opaque lop3 keeps it at 3 ANDs + xor3 + maj.
+__device__ __forceinline__ uint32_t lop3_xor3(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t lop3_maj(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xe8;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// popc(ones) + 2 * popc(twos) of the carry-save sum of three 64-bit words
+__device__ __forceinline__ uint32_t csa_count(u64 a, u64 b, u64 c)
+{
+    const uint32_t al = (uint32_t)a, ah = (uint32_t)(a >> 32), bl = (uint32_t)b, bh = (uint32_t)(b >> 32);
+    const uint32_t cl = (uint32_t)c, ch = (uint32_t)(c >> 32);
+    const uint32_t ones = __popc(lop3_xor3(al, bl, cl)) + __popc(lop3_xor3(ah, bh, ch));
+    const uint32_t twos = __popc(lop3_maj(al, bl, cl)) + __popc(lop3_maj(ah, bh, ch));
+    return ones + 2 * twos;
+}
+
 template <int N>
 struct PopcSum {
     static __device__ __forceinline__ uint32_t run(const u64 *x)
@@ -102,8 +127,8 @@ template <> struct PopcSum<2> { static __device__ __forceinline__ uint32_t run(c
 // the depth that balances the two pipes is chosen per kernel.
 __device__ __forceinline__ void csa32(uint32_t a, uint32_t b, uint32_t c, uint32_t &sum, uint32_t &carry)
 {
-    sum = a ^ b ^ c;                       // one LOP3 (0x96)
-    carry = (a & b) | (c & (a | b));       // one LOP3 (0xe8, majority)
+    sum = lop3_xor3(a, b, c);              // one LOP3 (0x96)
+    carry = lop3_maj(a, b, c);             // one LOP3 (0xe8, majority); opaque so that the ANDs feeding a, b, c are formed once
 }
 
 template <int N, int DEPTH>

@@ -249,9 +249,7 @@ __global__ void __launch_bounds__(512, 1) k_general(const GeneralArgs a)
                                 for (int hh = 0; hh < (TH > 1 ? 2 : 1); ++hh)
 #pragma unroll
                                     for (int j = 0; j < TL; ++j) {
-                                        u64 ones, twos;
-                                        csa(hv[0][hh] & l[0][j], hv[1][hh] & l[1][j], hv[2][hh] & l[2][j], ones, twos);
-                                        acc[h2 + hh][j] += __popcll(ones) + 2 * __popcll(twos);
+                                        acc[h2 + hh][j] += csa_count(hv[0][hh] & l[0][j], hv[1][hh] & l[1][j], hv[2][hh] & l[2][j]);
                                     }
                             }
                         }

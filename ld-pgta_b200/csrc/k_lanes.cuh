@@ -165,9 +165,7 @@ __global__ void __launch_bounds__(32 * LanesWarps<NR>::MAX, 1) k_lanes(const __g
                             if ((h >> j) & 1) v &= hm[j][k];
                         y[k] = v;
                     }
-                    u64 ones, twos;
-                    csa(y[0], y[1], y[2], ones, twos);
-                    const uint32_t cnt = __popcll(ones) + 2 * __popcll(twos);
+                    const uint32_t cnt = csa_count(y[0], y[1], y[2]);
                     if (PACK) acc[h >> 1] += cnt << (16 * (h & 1));
                     else acc[h] += cnt;
                 }
