@@ -105,6 +105,25 @@ __device__ __forceinline__ uint32_t csa_count(u64 a, u64 b, u64 c)
     return ones + 2 * twos;
 }
 
+// acc += (popc(ones) + 2 * popc(twos)) << SHIFT for the carry-save sum of three 64-bit words.  The doubled terms are
+// integer multiply-adds (FMA pipe) so that only one 3-input add per triple lands on the ALU pipe, which also carries
+// all the LOP3s.
+template <int SHIFT>
+__device__ __forceinline__ void csa_accumulate(uint32_t &acc, u64 a, u64 b, u64 c)
+{
+    const uint32_t al = (uint32_t)a, ah = (uint32_t)(a >> 32), bl = (uint32_t)b, bh = (uint32_t)(b >> 32);
+    const uint32_t cl = (uint32_t)c, ch = (uint32_t)(c >> 32);
+    const uint32_t o_lo = __popc(lop3_xor3(al, bl, cl)), o_hi = __popc(lop3_xor3(ah, bh, ch));
+    const uint32_t t_lo = __popc(lop3_maj(al, bl, cl)), t_hi = __popc(lop3_maj(ah, bh, ch));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc) : "r"(t_lo), "n"(2 << SHIFT));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc) : "r"(t_hi), "n"(2 << SHIFT));
+    if (SHIFT == 0) acc += o_lo + o_hi;
+    else {
+        asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc) : "r"(o_lo), "n"(1 << SHIFT));
+        asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc) : "r"(o_hi), "n"(1 << SHIFT));
+    }
+}
+
 template <int N>
 struct PopcSum {
     static __device__ __forceinline__ uint32_t run(const u64 *x)

@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(512, 1) k_general(const GeneralArgs a)
                                 for (int hh = 0; hh < (TH > 1 ? 2 : 1); ++hh)
 #pragma unroll
                                     for (int j = 0; j < TL; ++j) {
-                                        acc[h2 + hh][j] += csa_count(hv[0][hh] & l[0][j], hv[1][hh] & l[1][j], hv[2][hh] & l[2][j]);
+                                        csa_accumulate<0>(acc[h2 + hh][j], hv[0][hh] & l[0][j], hv[1][hh] & l[1][j], hv[2][hh] & l[2][j]);
                                     }
                             }
                         }

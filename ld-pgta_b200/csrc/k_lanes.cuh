@@ -165,9 +165,8 @@ __global__ void __launch_bounds__(32 * LanesWarps<NR>::MAX, 1) k_lanes(const __g
                             if ((h >> j) & 1) v &= hm[j][k];
                         y[k] = v;
                     }
-                    const uint32_t cnt = csa_count(y[0], y[1], y[2]);
-                    if (PACK) acc[h >> 1] += cnt << (16 * (h & 1));
-                    else acc[h] += cnt;
+                    if (PACK && (h & 1)) csa_accumulate<16>(acc[h >> 1], y[0], y[1], y[2]);
+                    else csa_accumulate<0>(acc[PACK ? h >> 1 : h], y[0], y[1], y[2]);
                 }
             };
             const u64 *row = M;
