@@ -156,7 +156,24 @@ class PackedResult:
 
 
 class PackedObservations:
-    """ obs_tab rows that match the legend, as arrays (see pack_observations). """
+    """ obs_tab rows that match the legend, as arrays (see pack_observations).  save() / load() keep them as an .npz
+    next to the sample so that later runs against the same panel skip the walk over the pickled tuples. """
+    _arrays = ('allele_rows', 'allele_complement', 'read_offsets', 'read_alleles', 'obs_pos', 'obs_read')
+
+    def save(self, filename):
+        np.savez(filename, read_names=np.array(self.read_names, dtype=str), fraction_of_matches=np.float64(self.fraction_of_matches),
+                 n_snps=np.int64(self.n_snps), **{k: getattr(self, k) for k in self._arrays})
+
+    @classmethod
+    def load(cls, filename):
+        out = cls()
+        with np.load(filename) as z:
+            for k in cls._arrays:
+                setattr(out, k, z[k])
+            out.read_names = z['read_names'].tolist()
+            out.fraction_of_matches = float(z['fraction_of_matches'])
+            out.n_snps = int(z['n_snps'])
+        return out
 
 
 def pack_observations(obs_tab, legend):
@@ -166,6 +183,7 @@ def pack_observations(obs_tab, legend):
       read_names, read_offsets, read_alleles   reads as CSR lists of allele-table rows    (build_reads_dict, ANEUPLOIDY_TEST.py:118-127)
       obs_pos, obs_read              position and read row of every matched observation  (build_overlaps_dict, :129-139) """
     out = PackedObservations()
+    out.n_snps = legend.n_snps
     n = len(obs_tab)
     cols = list(zip(*obs_tab)) if n else ((), (), ())        # one C-level pass over the tuples
     pos = np.array(cols[0], dtype=np.int64)
@@ -197,7 +215,8 @@ def pack_observations(obs_tab, legend):
 
 
 class PackedSample:
-    """ One sample on one chromosome against a resident panel. """
+    """ One sample on one chromosome against a resident panel; obs_tab is the reference's list of (pos, read_id, base)
+    rows or a PackedObservations made from it earlier. """
 
     def __init__(self, obs_tab, panel, ancestral_makeup, min_HF=0.05, device=None):
         self.panel = panel
@@ -214,7 +233,12 @@ class PackedSample:
                 raise ValueError('the ancestral makeup does not match the superpopulations of the resident panel')
             self.kind, self.proportions = (N.HOMOGENEOUS if len(groups) == 1 else N.RECENT_ADMIXTURE), None
             makeup = {g: 1 / len(groups) for g in groups}
-        packed = pack_observations(obs_tab, panel.legend)
+        if isinstance(obs_tab, PackedObservations):
+            packed = obs_tab
+            if packed.n_snps != panel.n_snps or (len(packed.allele_rows) and int(packed.allele_rows.max()) >= panel.n_snps):
+                raise ValueError('these packed observations were matched against another panel')
+        else:
+            packed = pack_observations(obs_tab, panel.legend)
         frac = packed.fraction_of_matches
         self.fraction_of_matches = {g: frac for g in groups}
         self.allele_rows, self.allele_complement = packed.allele_rows, packed.allele_complement

@@ -47,6 +47,16 @@ def test_pack_observations_and_windows_cpu(name, golden_inputs):
         assert {po.read_names[r] for r in win.reads[lo:hi]} == set(ids)
 
 
+def test_packed_observations_roundtrip(tmp_path, golden_inputs):
+    from ldpgta_b200.packed import PackedObservations
+    args, out, legend, po = packed_inputs('recent_m4', golden_inputs)
+    po.save(str(tmp_path / 'sample.npz'))
+    back = PackedObservations.load(str(tmp_path / 'sample.npz'))
+    assert back.read_names == po.read_names and back.fraction_of_matches == po.fraction_of_matches and back.n_snps == len(args['leg_tab'])
+    for k in PackedObservations._arrays:
+        assert np.array_equal(getattr(back, k), getattr(po, k)) and getattr(back, k).dtype == getattr(po, k).dtype
+
+
 def test_legend_lookup_semantics():
     from ldpgta_b200.packed import PackedLegend, pack_observations
     leg = [('c', 10, 'A', 'G'), ('c', 20, 'C', 'T'), ('c', 20, 'G', 'T'), ('c', 5, 'T', 'TA')]       # duplicate position, unsorted
@@ -81,7 +91,7 @@ def test_sampling_without_replacement_is_uniform():
 @pytest.mark.parametrize('name', CHROM_CONFIGS)
 def test_packed_sample_matches_reference(name, golden_inputs):
     import ldpgta_b200 as L
-    from ldpgta_b200.packed import PackedSample
+    from ldpgta_b200.packed import PackedSample, pack_observations
     args, out = chrom_case(name, golden_inputs)
     cfg = args['cfg']
     groups = list(cfg['makeup']) if isinstance(cfg['makeup'], dict) else list(cfg['groups'])
@@ -91,6 +101,8 @@ def test_packed_sample_matches_reference(name, golden_inputs):
     with PackedSample(args['obs_tab'], panel, cfg['makeup'], cfg['min_HF']) as ps:
         assert ps.fraction_of_matches == out['fraction_of_matches']
         assert dict(zip(ps.read_names, ps.scores.tolist())) == out['score']
+        with PackedSample(pack_observations(args['obs_tab'], panel.legend), panel, cfg['makeup'], cfg['min_HF']) as again:
+            assert np.array_equal(again.scores, ps.scores) and again.read_names == ps.read_names      # from arrays: same sample
         win = ps.windows(cfg['window_size'], cfg['offset'], cfg['min_reads'], cfg['max_reads'], cfg['min_score'])
         assert [tuple(b) for b in win.borders.tolist()] == list(out['windows'])
         # the reference's own draws, replayed as read rows

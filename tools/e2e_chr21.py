@@ -78,6 +78,21 @@ for rep in range(3):
     deep.append({'total_s': time.time() - t, 'pack_s': t1 - t, 'run_s': t2 - t1, 'window_likelihoods': int(res1000.draw_offsets[-1])})
     res1000.release()
 packed['subsamples_1000_device_draws'] = deep
+# the same from observations packed once (PackedObservations.save / load): no walk over the pickled tuples
+from ldpgta_b200.packed import pack_observations, PackedObservations
+pack_observations(obs, panel.legend).save('/tmp/chr21_sample.npz')
+arr = []
+for rep in range(3):
+    t = time.time()
+    po = PackedObservations.load('/tmp/chr21_sample.npz')
+    t0 = time.time()
+    ps = PackedSample(po, panel, {'ALL'}, 0.05)
+    t1 = time.time()
+    r = ps.run(100000, 1000, 0, 6, 4, 2, seed=rep, want_draws=False, keep_pinned=True)
+    t2 = time.time()
+    ps.close(); r.release()
+    arr.append({'total_s': time.time() - t, 'load_npz_s': t0 - t, 'gather_masks_scores_s': t1 - t0, 'run_s': t2 - t1})
+packed['subsamples_1000_from_npz'] = arr
 assert list(ref_gw) == list(gw) and list(ref_lik) == list(lik)
 assert all(set(a) == set(b) for a, b in zip(ref_gw.values(), gw.values()))
 packed['per_sample_runs'] = per_sample
