@@ -260,7 +260,7 @@ def kernel_name(n, model):
     if n == 5 and model == 'homogeneous':
         return 'k_mid<5,5>'
     if n <= (12 if model == 'homogeneous' else 11):
-        return 'k_lanes<%d,%d>' % (n, {5: 3, 6: 3, 7: 3, 8: 4}.get(n, 5))
+        return 'k_lanes<%d,%d>' % (n, {5: 3, 6: 3, 7: 3, 8: 4, 9: 4}.get(n, 5))
     return 'k_general (n=%d)' % n
 
 

@@ -45,12 +45,22 @@ int launch_lanes(ldpgta_ctx *c, GeneralArgs a)
     for (int g = 0; g < c->G; ++g) a.wide |= c->nhap[g] > 16383u;
     a.kl = a.kh = a.wc = 0;
     a.table_scratch = nullptr; a.table_stride = 0;
+    static const int alt = [] { const char *e = getenv("LDPGTA_LANES_ALT"); return e ? atoi(e) : 0; }();     // tuning: the other low/high split (measured slower: tools/sweep_sizes.sh)
+    if (alt)
+        switch (a.n) {
+        case 6: return launch_lanes_t<6, 2>(c, a);
+        case 7: return launch_lanes_t<7, 4>(c, a);
+        case 8: return launch_lanes_t<8, 3>(c, a);
+        case 9: return launch_lanes_t<9, 4>(c, a);
+        case 10: return launch_lanes_t<10, 4>(c, a);
+        case 11: return launch_lanes_t<11, 4>(c, a);
+        }
     switch (a.n) {
     case 5: return launch_lanes_t<5, 3>(c, a);
     case 6: return launch_lanes_t<6, 3>(c, a);
     case 7: return launch_lanes_t<7, 3>(c, a);
     case 8: return launch_lanes_t<8, 4>(c, a);
-    case 9: return launch_lanes_t<9, 5>(c, a);
+    case 9: return launch_lanes_t<9, 4>(c, a);
     case 10: return launch_lanes_t<10, 5>(c, a);
     case 11: return launch_lanes_t<11, 5>(c, a);
     case 12: return launch_lanes_t<12, 5>(c, a);
