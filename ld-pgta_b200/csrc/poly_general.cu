@@ -59,11 +59,14 @@ __device__ __forceinline__ u64 dot16(const uint32_t *X, const ACC *conv)
 // returns per-thread partials: two, two_sph (u64) and three (u64; the caller sums them in 128 bits)
 template <typename CT, typename ACC>
 __device__ void poly_homog_blocked(const CT *F, int n, const u64 *terms, int64_t n_terms, int tid, int T,
-                                                   u64 &two, u64 &two_sph, u128 &three)
+                                                   u64 &two_out, u64 &two_sph_out, u128 &three_out)
 {
     const int h = n - 5;
     const uint32_t top_row = 1u << h, usub = (1u << (n - 1)) - 1u, top = 1u << (n - 1);
-    two = 0; two_sph = 0; three = 0;
+    // local accumulators: the outputs are references into the caller's frame, and updating them in the loops costs a
+    // generic load and store per term (the compiler cannot rule out aliasing with the table)
+    u64 two = 0, two_sph = 0;
+    u128 three = 0;
     for (uint32_t a = tid; a < usub; a += T) {                  // a != U': the other block is not empty
         const u64 prod = (u64)F[top | a] * (u64)F[usub ^ a];
         const int pa = __popc(a);
@@ -90,16 +93,19 @@ __device__ void poly_homog_blocked(const CT *F, int n, const u64 *terms, int64_t
         conv16<ACC>(Y, Y, c);
         three += dot16<ACC>(X, c) >> 1;
     }
+    two_out = two; two_sph_out = two_sph; three_out = three;
 }
 
 // ---- recent admixture: F = group 0, G = group 1 ------------------------------------------------
 template <typename CT, typename ACC>
 __device__ void poly_recent_blocked(const CT *F, const CT *G, int n, const u64 *terms, int64_t n_terms, int tid,
-                                                    int T, u64 &ff, u64 &gg, u64 &fg, u64 &fg_sph, u128 &ffg, u128 &ggf)
+                                                    int T, u64 &ff_out, u64 &gg_out, u64 &fg_out, u64 &fg_sph_out, u128 &ffg_out,
+                                                    u128 &ggf_out)
 {
     const int h = n - 5;
     const uint32_t top_row = 1u << h, usub = (1u << (n - 1)) - 1u, top = 1u << (n - 1);
-    ff = gg = fg = fg_sph = 0; ffg = 0; ggf = 0;
+    u64 ff = 0, gg = 0, fg = 0, fg_sph = 0;                      // local accumulators (see poly_homog_blocked)
+    u128 ffg = 0, ggf = 0;
     for (uint32_t a = tid; a < usub; a += T) {
         const uint32_t A = top | a, R = usub ^ a;
         const u64 fa = F[A], ga = G[A], fr = F[R], gr = G[R];
@@ -133,12 +139,13 @@ __device__ void poly_recent_blocked(const CT *F, const CT *G, int n, const u64 *
         triple((uint32_t)(t & 0xffffu), (uint32_t)(t >> 16) & 0xffffu, (uint32_t)(t >> 32) & 0xffffu, false);
     }
     if (tid == 0) triple(top_row - 1u, 0u, 0u, true);
+    ff_out = ff; gg_out = gg; fg_out = fg; fg_sph_out = fg_sph; ffg_out = ffg; ggf_out = ggf;
 }
 
 // ---- distant admixture: float frequencies e(S) = sum_g p_g cnt_g(S) / N_g formed on the fly -----
 template <typename CT>
 __device__ void poly_distant_blocked(const CT *ftab, const PanelView &pv, int n, const u64 *terms, int64_t n_terms,
-                                                     int tid, int T, double &two, double &two_sph, double &three)
+                                                     int tid, int T, double &two_out, double &two_sph_out, double &three_out)
 {
     const int h = n - 5, G = pv.G;
     const uint32_t top_row = 1u << h, usub = (1u << (n - 1)) - 1u, top = 1u << (n - 1);
@@ -151,7 +158,7 @@ __device__ void poly_distant_blocked(const CT *ftab, const PanelView &pv, int n,
 #pragma unroll
         for (int l = 0; l < 16; ++l) v[l] = E((r << 4) | l);
     };
-    two = 0; two_sph = 0; three = 0;
+    double two = 0, two_sph = 0, three = 0;                      // local accumulators (see poly_homog_blocked)
     for (uint32_t a = tid; a < usub; a += T) {
         const double prod = E(top | a) * E(usub ^ a);
         const int pa = __popc(a);
@@ -176,6 +183,7 @@ __device__ void poly_distant_blocked(const CT *ftab, const PanelView &pv, int n,
         three += triple((uint32_t)(t & 0xffffu), (uint32_t)(t >> 16) & 0xffffu, (uint32_t)(t >> 32) & 0xffffu);
     }
     if (tid == 0) three += 0.5 * triple(top_row - 1u, 0u, 0u);
+    two_out = two; two_sph_out = two_sph; three_out = three;
 }
 
 
