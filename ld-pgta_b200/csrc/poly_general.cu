@@ -5,31 +5,59 @@
 
 namespace ldpgta {
 
-template <typename CT>
+// 128-bit table loads.  The tables live in shared memory (k_lanes, k_general up to 16 reads) or in an L2-resident global
+// slice (17-18 reads, two-group models at 16); through a generic pointer every row costs generic LD.E.128s, so the
+// callers' pointer is classified once (SPACE: 0 generic, 1 shared) and shared tables are read with LDS.128.
+template <int SPACE>
+__device__ __forceinline__ uint4 load128(const void *p)
+{
+    if (SPACE == 1) {
+        uint4 v;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "r"((uint32_t)__cvta_generic_to_shared(p)));
+        return v;
+    }
+    return *reinterpret_cast<const uint4 *>(p);
+}
+
+template <typename CT, int SPACE>
 __device__ __forceinline__ void load_row16(const CT *tab, uint32_t row, uint32_t *v);
 
-template <>
-__device__ __forceinline__ void load_row16<uint32_t>(const uint32_t *tab, uint32_t row, uint32_t *v)
+template <typename CT, int SPACE>
+struct RowLoader;
+
+template <int SPACE>
+struct RowLoader<uint32_t, SPACE> {
+  static __device__ __forceinline__ void run(const uint32_t *tab, uint32_t row, uint32_t *v)
 {
     const uint4 *p = reinterpret_cast<const uint4 *>(tab + ((size_t)row << 4));
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const uint4 x = p[q];
+        const uint4 x = load128<SPACE>(p + q);
         v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
     }
 }
+};
 
-template <>
-__device__ __forceinline__ void load_row16<uint16_t>(const uint16_t *tab, uint32_t row, uint32_t *v)
+template <int SPACE>
+struct RowLoader<uint16_t, SPACE> {
+  static __device__ __forceinline__ void run(const uint16_t *tab, uint32_t row, uint32_t *v)
 {
     const uint4 *p = reinterpret_cast<const uint4 *>(tab + ((size_t)row << 4));
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-        const uint4 x = p[q];
+        const uint4 x = load128<SPACE>(p + q);
         const uint32_t w[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) { v[8 * q + 2 * e] = w[e] & 0xffffu; v[8 * q + 2 * e + 1] = w[e] >> 16; }
     }
+}
+};
+
+template <typename CT, int SPACE>
+__device__ __forceinline__ void load_row16(const CT *tab, uint32_t row, uint32_t *v)
+{
+    RowLoader<CT, SPACE>::run(tab, row, v);
 }
 
 // (Y*Z)[s] for the 16 subsets s of Lo; ACC = uint32_t when 16 * max(Y) * max(Z) < 2^32, else u64
@@ -57,9 +85,9 @@ __device__ __forceinline__ u64 dot16(const uint32_t *X, const ACC *conv)
 
 // ---- homogeneous ------------------------------------------------------------------------------
 // returns per-thread partials: two, two_sph (u64) and three (u64; the caller sums them in 128 bits)
-template <typename CT, typename ACC>
-__device__ void poly_homog_blocked(const CT *F, int n, const u64 *terms, int64_t n_terms, int tid, int T,
-                                                   u64 &two_out, u64 &two_sph_out, u128 &three_out)
+template <typename CT, typename ACC, int SPACE>
+__device__ __forceinline__ void poly_homog_impl(const CT *F, int n, const u64 *terms, int64_t n_terms, int tid, int T,
+                                                u64 &two_out, u64 &two_sph_out, u128 &three_out)
 {
     const int h = n - 5;
     const uint32_t top_row = 1u << h, usub = (1u << (n - 1)) - 1u, top = 1u << (n - 1);
@@ -79,28 +107,36 @@ __device__ void poly_homog_blocked(const CT *F, int n, const u64 *terms, int64_t
         if (e + T < n_terms) t_next = terms[e + T];
         uint32_t X[16], Y[16], Z[16];
         ACC c[16];
-        load_row16<CT>(F, top_row + (uint32_t)(t & 0xffffu), X);
-        load_row16<CT>(F, (uint32_t)(t >> 16) & 0xffffu, Y);
-        load_row16<CT>(F, (uint32_t)(t >> 32) & 0xffffu, Z);
+        load_row16<CT, SPACE>(F, top_row + (uint32_t)(t & 0xffffu), X);
+        load_row16<CT, SPACE>(F, (uint32_t)(t >> 16) & 0xffffu, Y);
+        load_row16<CT, SPACE>(F, (uint32_t)(t >> 32) & 0xffffu, Z);
         conv16<ACC>(Y, Z, c);
         three += dot16<ACC>(X, c);
     }
     if (tid == 0) {                                             // b_h = c_h = empty: both blocks inside Lo, weight 1/2
         uint32_t X[16], Y[16];
         ACC c[16];
-        load_row16<CT>(F, top_row + (top_row - 1u), X);
-        load_row16<CT>(F, 0u, Y);
+        load_row16<CT, SPACE>(F, top_row + (top_row - 1u), X);
+        load_row16<CT, SPACE>(F, 0u, Y);
         conv16<ACC>(Y, Y, c);
         three += dot16<ACC>(X, c) >> 1;
     }
     two_out = two; two_sph_out = two_sph; three_out = three;
 }
 
-// ---- recent admixture: F = group 0, G = group 1 ------------------------------------------------
 template <typename CT, typename ACC>
-__device__ void poly_recent_blocked(const CT *F, const CT *G, int n, const u64 *terms, int64_t n_terms, int tid,
-                                                    int T, u64 &ff_out, u64 &gg_out, u64 &fg_out, u64 &fg_sph_out, u128 &ffg_out,
-                                                    u128 &ggf_out)
+__device__ void poly_homog_blocked(const CT *F, int n, const u64 *terms, int64_t n_terms, int tid, int T,
+                                   u64 &two, u64 &two_sph, u128 &three)
+{
+    if (__isShared(F)) poly_homog_impl<CT, ACC, 1>(F, n, terms, n_terms, tid, T, two, two_sph, three);
+    else poly_homog_impl<CT, ACC, 0>(F, n, terms, n_terms, tid, T, two, two_sph, three);
+}
+
+// ---- recent admixture: F = group 0, G = group 1 ------------------------------------------------
+template <typename CT, typename ACC, int SPACE>
+__device__ __forceinline__ void poly_recent_impl(const CT *F, const CT *G, int n, const u64 *terms, int64_t n_terms, int tid,
+                                                 int T, u64 &ff_out, u64 &gg_out, u64 &fg_out, u64 &fg_sph_out, u128 &ffg_out,
+                                                 u128 &ggf_out)
 {
     const int h = n - 5;
     const uint32_t top_row = 1u << h, usub = (1u << (n - 1)) - 1u, top = 1u << (n - 1);
@@ -117,17 +153,20 @@ __device__ void poly_recent_blocked(const CT *F, const CT *G, int n, const u64 *
         fg_sph += cross * ((2ull << pa) + (1ull << (n - 1 - pa)));
     }
     auto triple = [&](uint32_t ra, uint32_t rb, uint32_t rc, bool special) {
-        uint32_t Xf[16], Xg[16], Yf[16], Yg[16], Zf[16], Zg[16];
+        // unordered {A,B,C}, A owns the last read: two parents from F and one from G, and vice versa.  Only one Y row and
+        // one Z row are live at a time (a row is 16 registers; all six at once do not fit 128 registers with the products).
+        uint32_t Xf[16], Xg[16], Y[16], Z[16];
         ACC c[16];
-        load_row16<CT>(F, top_row + ra, Xf); load_row16<CT>(G, top_row + ra, Xg);
-        load_row16<CT>(F, rb, Yf); load_row16<CT>(G, rb, Yg);
-        load_row16<CT>(F, rc, Zf); load_row16<CT>(G, rc, Zg);
-        // unordered {A,B,C}, A owns the last read: two parents from F and one from G, and vice versa
         u64 s_ffg, s_ggf;
-        conv16<ACC>(Yf, Zf, c); s_ffg = dot16<ACC>(Xg, c);
-        conv16<ACC>(Yg, Zg, c); s_ggf = dot16<ACC>(Xf, c);
-        conv16<ACC>(Yf, Zg, c); s_ffg += dot16<ACC>(Xf, c); s_ggf += dot16<ACC>(Xg, c);
-        conv16<ACC>(Yg, Zf, c); s_ffg += dot16<ACC>(Xf, c); s_ggf += dot16<ACC>(Xg, c);
+        load_row16<CT, SPACE>(F, top_row + ra, Xf); load_row16<CT, SPACE>(G, top_row + ra, Xg);
+        load_row16<CT, SPACE>(F, rb, Y); load_row16<CT, SPACE>(F, rc, Z);
+        conv16<ACC>(Y, Z, c); s_ffg = dot16<ACC>(Xg, c);                                          // Yf * Zf
+        load_row16<CT, SPACE>(G, rc, Z);
+        conv16<ACC>(Y, Z, c); s_ffg += dot16<ACC>(Xf, c); s_ggf = dot16<ACC>(Xg, c);              // Yf * Zg
+        load_row16<CT, SPACE>(G, rb, Y);
+        conv16<ACC>(Y, Z, c); s_ggf += dot16<ACC>(Xf, c);                                         // Yg * Zg
+        load_row16<CT, SPACE>(F, rc, Z);
+        conv16<ACC>(Y, Z, c); s_ffg += dot16<ACC>(Xf, c); s_ggf += dot16<ACC>(Xg, c);             // Yg * Zf
         if (special) { s_ffg >>= 1; s_ggf >>= 1; }
         ffg += s_ffg;
         ggf += s_ggf;
@@ -140,6 +179,14 @@ __device__ void poly_recent_blocked(const CT *F, const CT *G, int n, const u64 *
     }
     if (tid == 0) triple(top_row - 1u, 0u, 0u, true);
     ff_out = ff; gg_out = gg; fg_out = fg; fg_sph_out = fg_sph; ffg_out = ffg; ggf_out = ggf;
+}
+
+template <typename CT, typename ACC>
+__device__ void poly_recent_blocked(const CT *F, const CT *G, int n, const u64 *terms, int64_t n_terms, int tid, int T,
+                                    u64 &ff, u64 &gg, u64 &fg, u64 &fg_sph, u128 &ffg, u128 &ggf)
+{
+    if (__isShared(F) && __isShared(G)) poly_recent_impl<CT, ACC, 1>(F, G, n, terms, n_terms, tid, T, ff, gg, fg, fg_sph, ffg, ggf);
+    else poly_recent_impl<CT, ACC, 0>(F, G, n, terms, n_terms, tid, T, ff, gg, fg, fg_sph, ffg, ggf);
 }
 
 // ---- distant admixture: float frequencies e(S) = sum_g p_g cnt_g(S) / N_g formed on the fly -----
