@@ -259,7 +259,7 @@ def kernel_name(n, model):
         return 'k_small<%d,8,10>' % n
     if n == 5 and model == 'homogeneous':
         return 'k_mid<5,5>'
-    if n <= (12 if model == 'homogeneous' else 11):
+    if n <= (12 if model == 'homogeneous' else 11) and not (model == 'distant' and n == 5):
         return 'k_lanes<%d,%d>' % (n, {5: 3, 6: 3, 7: 3, 8: 4, 9: 4}.get(n, 5))
     return 'k_general (n=%d)' % n
 
@@ -303,7 +303,7 @@ def main():
     ap.add_argument('--subsamples', type=int, default=32)
     ap.add_argument('--max-reads', type=int, default=4)
     ap.add_argument('--seed', type=int, default=12345)
-    ap.add_argument('--model', default='homogeneous', choices=['homogeneous', 'recent'], help='recent = two-population exploration run')
+    ap.add_argument('--model', default='homogeneous', choices=['homogeneous', 'recent', 'distant'], help='recent / distant = two-population exploration runs')
     ap.add_argument('--windows', type=int, default=0, help='limit the number of windows (exploration runs; 0 = whole genome)')
     ap.add_argument('--cpu-seconds', type=float, default=12.0, help='budget of the single-core CPU baseline leg')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -333,8 +333,11 @@ def main():
     n_windows, n_reads = len(reads), int(reads.sum())
     idx_host, win_of_draw = plan_draws(reads, args.subsamples, args.max_reads, args.seed + 1 + 1000 * rank)
     n_draws, n = idx_host.shape
+    proportions = None
     if args.model == 'recent':                       # exploration: configs[3], two populations of 2504 haplotypes
         group_sizes, kind = [N_HAP // 2, N_HAP // 2], L.RECENT_ADMIXTURE
+    elif args.model == 'distant':                    # exploration: the same panel with ancestral proportions 0.6 / 0.4
+        group_sizes, kind, proportions = [N_HAP // 2, N_HAP // 2], L.DISTANT_ADMIXTURE, [0.6, 0.4]
     else:
         group_sizes, kind = [N_HAP], L.HOMOGENEOUS
     eng = L.Engine(group_sizes, device=local)
@@ -351,7 +354,7 @@ def main():
     stream = torch.cuda.ExternalStream(eng.stream, device=device)
 
     def step_resident():
-        eng.likelihoods_uniform_dev(kind, n, d_idx.data_ptr(), n_draws, d_out.data_ptr())
+        eng.likelihoods_uniform_dev(kind, n, d_idx.data_ptr(), n_draws, d_out.data_ptr(), proportions=proportions)
 
     # pinned host buffers for the end-to-end leg
     pin_idx = L.PinnedArray((n_draws, n), np.int32)
@@ -360,10 +363,10 @@ def main():
     offsets = np.arange(0, n_draws * n + 1, n, dtype=np.int64)
 
     def step_e2e():
-        eng.likelihoods_uniform(kind, pin_idx.array, out=pin_out.array)
+        eng.likelihoods_uniform(kind, pin_idx.array, proportions=proportions, out=pin_out.array)
 
     def step_e2e_offsets():
-        eng.likelihoods_batch(kind, pin_idx.array.reshape(-1), offsets, out=pin_out.array)
+        eng.likelihoods_batch(kind, pin_idx.array.reshape(-1), offsets, proportions=proportions, out=pin_out.array)
 
     def barrier():
         torch.cuda.synchronize()

@@ -8,9 +8,9 @@
 
 namespace ldpgta {
 
-struct GeneralPlan { int th, tl, nw, kl, kh, wc; bool u16, global_table; size_t smem, table_bytes; };
+struct GeneralPlan { int th, tl, nw, kl, kh, wc; bool u16, global_table, etab; size_t smem, table_bytes; };
 
-static int plan_general(const ldpgta_ctx *c, int n, GeneralPlan *p)
+static int plan_general(const ldpgta_ctx *c, int n, int kind, GeneralPlan *p)
 {
     static const int TH[19] = {0, 0, 0, 0, 0, 1, 2, 4, 8, 2, 4, 4, 8, 8, 8, 8, 8, 8, 8};
     static const int TL[19] = {0, 0, 0, 0, 0, 1, 1, 1, 1, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4};
@@ -30,11 +30,14 @@ static int plan_general(const ldpgta_ctx *c, int n, GeneralPlan *p)
     const size_t ct = p->u16 ? 2 : 4;
     p->table_bytes = entries * ct;
     p->global_table = p->table_bytes > 128 * 1024;
-    const size_t fixed = 128 + (size_t)n * wsum * 8 + (p->global_table ? 0 : p->table_bytes) + 64 + 16 + 16 * 12 * 8;
+    // distant admixture: e(S) as doubles next to the count tables while both fit (n <= 13 for two groups)
+    p->etab = kind == LDPGTA_DISTANT_ADMIXTURE && n >= 5 && !p->global_table &&
+              p->table_bytes + ((size_t)8 << n) + (size_t)n * wsum * 8 + 16 * 1024 <= (size_t)c->max_smem_optin;
+    const size_t fixed = 128 + (size_t)n * wsum * 8 + (p->global_table ? 0 : p->table_bytes) + (p->etab ? (size_t)8 << n : 0) + 64 + 16 + 16 * 12 * 8;
     const size_t per_word = ((size_t)8 << p->kl) + ((size_t)8 << p->kh);
     size_t budget_kb = (size_t)BUDGET_KB[n];
     if (const char *e = getenv("LDPGTA_PLAN_KB")) budget_kb = (size_t)atoi(e);
-    const size_t cap = std::min<size_t>((size_t)c->max_smem_optin, budget_kb * 1024);
+    const size_t cap = std::min<size_t>((size_t)c->max_smem_optin, budget_kb * 1024 + (p->etab ? (size_t)8 << n : 0));
     if (fixed + 2 * per_word > (size_t)c->max_smem_optin)
         return fail(LDPGTA_E_UNSUPPORTED, "draws of %d reads with %d group(s) do not fit shared memory (%zu B fixed)", n, c->G, fixed);
     size_t avail = cap > fixed ? cap - fixed : 0;
@@ -46,8 +49,8 @@ static int plan_general(const ldpgta_ctx *c, int n, GeneralPlan *p)
     wc = (wmax + chunks - 1) / chunks;
     p->wc = wc;
     PanelView pv = make_view(c, nullptr);
-    p->smem = p->u16 ? general_smem_layout<uint16_t>(pv, n, p->kl, p->kh, wc, !p->global_table).total
-                     : general_smem_layout<uint32_t>(pv, n, p->kl, p->kh, wc, !p->global_table).total;
+    p->smem = p->u16 ? general_smem_layout<uint16_t>(pv, n, p->kl, p->kh, wc, !p->global_table, p->etab).total
+                     : general_smem_layout<uint32_t>(pv, n, p->kl, p->kh, wc, !p->global_table, p->etab).total;
     if (p->smem > (size_t)c->max_smem_optin)
         return fail(LDPGTA_E_UNSUPPORTED, "draws of %d reads need %zu B of shared memory", n, p->smem);
     return 0;
@@ -111,8 +114,8 @@ int ensure_hi_terms(ldpgta_ctx *c, int h)
 int launch_general(ldpgta_ctx *c, GeneralArgs a)
 {
     GeneralPlan p;
-    if (int rc = plan_general(c, a.n, &p)) return rc;
-    a.kl = p.kl; a.kh = p.kh; a.wc = p.wc;
+    if (int rc = plan_general(c, a.n, a.kind, &p)) return rc;
+    a.kl = p.kl; a.kh = p.kh; a.wc = p.wc; a.etab = p.etab ? 1 : 0;
     a.terms = nullptr; a.n_terms = 0; a.wide = 0;
     if (a.n >= 5) {
         const int h = a.n - 5;

@@ -29,6 +29,7 @@ struct GeneralArgs {
     int kind;
     int n, kl, kh;           // reads per draw; low/high split
     int wc;                  // words per table chunk
+    int etab;                // distant admixture: tabulate e(S) in shared memory (fits for n <= 13)
     const int32_t *idx;      // [n_draws][n]
     int64_t n_draws;
     const int64_t *pos;      // optional scatter positions
@@ -42,11 +43,12 @@ struct GeneralArgs {
 };
 
 struct GeneralSmem {         // byte offsets into dynamic shared memory
-    int masks, ltab, htab, ftab, red, total;
+    int masks, ltab, htab, ftab, etab, red, total;
 };
 
 template <typename CT>
-__host__ __device__ inline GeneralSmem general_smem_layout(const PanelView &pv, int n, int kl, int kh, int wc, bool table_in_smem = true)
+__host__ __device__ inline GeneralSmem general_smem_layout(const PanelView &pv, int n, int kl, int kh, int wc, bool table_in_smem = true,
+                                                           bool etab = false)
 {
     GeneralSmem s;
     int off = 128;                                       // s_idx[32]
@@ -59,6 +61,8 @@ __host__ __device__ inline GeneralSmem general_smem_layout(const PanelView &pv, 
     off = (off + 63) & ~63;                              // table rows are read with 128-bit loads
     s.ftab = off; if (table_in_smem) off += (int)(sizeof(CT) * pv.G) << n;
     off = (off + 15) & ~15;
+    s.etab = -1;
+    if (etab) { s.etab = off; off += 8 << n; }           // e(S) of the distant model, one double per subset
     s.red = off; off += 16 * 12 * 8;
     s.total = off;
     return s;
@@ -143,7 +147,7 @@ __global__ void __launch_bounds__(512, 1) k_general(const GeneralArgs a)
     extern __shared__ __align__(128) unsigned char smem[];
     const int n = a.n, kl = a.kl, kh = a.kh, G = a.pv.G;
     const int LS = 1 << kl, HS = 1 << kh, NS = 1 << n;
-    const GeneralSmem lay = general_smem_layout<CT>(a.pv, n, kl, kh, a.wc, a.table_scratch == nullptr);
+    const GeneralSmem lay = general_smem_layout<CT>(a.pv, n, kl, kh, a.wc, a.table_scratch == nullptr, a.etab != 0);
     int32_t *s_idx = reinterpret_cast<int32_t *>(smem);
     u64 *s_masks = reinterpret_cast<u64 *>(smem + lay.masks);
     u64 *ltab = reinterpret_cast<u64 *>(smem + lay.ltab);
@@ -390,7 +394,12 @@ __global__ void __launch_bounds__(512, 1) k_general(const GeneralArgs a)
                 return e;
             };
             double two = 0, two_sph = 0, three = 0;
-            if (n >= 5) poly_distant_blocked<CT>(ftab, a.pv, n, a.terms, a.n_terms, tid, T, two, two_sph, three);
+            double *etab = a.etab ? reinterpret_cast<double *>(smem + lay.etab) : nullptr;
+            if (n >= 5 && etab) {
+                distant_fill_etab<CT>(ftab, a.pv, n, etab, tid, T);
+                __syncthreads();
+                poly_distant_etab(etab, n, a.terms, a.n_terms, tid, T, two, two_sph, three);
+            } else if (n >= 5) poly_distant_blocked<CT>(ftab, a.pv, n, a.terms, a.n_terms, tid, T, two, two_sph, three);
             else
             for (uint32_t A = top + warp; A < full; A += NW) {
                 const uint32_t rest = full ^ A;

@@ -29,11 +29,12 @@ struct LanesSmem {           // per-warp byte offsets / sizes
     int draw_stride;         // 64-bit words between consecutive draws of a buffer (bank-staggered)
     int buf_words;           // words per buffer
     int ftab;                // byte offset of the warp's count tables
+    int etab;                // byte offset of the warp's e(S) tables (distant admixture), -1 when absent
     int per_warp;            // bytes per warp (mask buffer + tables + barrier)
 };
 
 template <int NR, int KL>
-__host__ __device__ inline LanesSmem lanes_smem_layout(const PanelView &pv)
+__host__ __device__ inline LanesSmem lanes_smem_layout(const PanelView &pv, bool distant)
 {
     constexpr int DPW = 32 >> KL;
     LanesSmem s;
@@ -49,6 +50,8 @@ __host__ __device__ inline LanesSmem lanes_smem_layout(const PanelView &pv)
     s.ftab = s.buf_words * 8;
     int off = s.ftab + DPW * ((pv.G << NR) * 4);
     off = (off + 15) & ~15;
+    s.etab = -1;
+    if (distant) { s.etab = off; off += DPW * (8 << NR); }
     off += 16;                                            // the warp's mbarrier
     s.per_warp = (off + 127) & ~127;
     return s;
@@ -83,7 +86,7 @@ __global__ void __launch_bounds__(32 * LanesWarps<NR>::MAX, 1) k_lanes(const __g
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), nwarps = blockDim.x >> 5;
     const int lo = lane & (LPD - 1), dgrp = lane / LPD;
     const int G = a.pv.G;
-    const LanesSmem lay = lanes_smem_layout<NR, KL>(a.pv);
+    const LanesSmem lay = lanes_smem_layout<NR, KL>(a.pv, a.kind == LDPGTA_DISTANT_ADMIXTURE);
     unsigned char *wbase = smem + (size_t)warp * lay.per_warp;
     u64 *bufs = reinterpret_cast<u64 *>(wbase);
     uint32_t *ftab = reinterpret_cast<uint32_t *>(wbase + lay.ftab) + (size_t)dgrp * (G << NR);
@@ -245,14 +248,14 @@ __global__ void __launch_bounds__(32 * LanesWarps<NR>::MAX, 1) k_lanes(const __g
                 finish_recent(scale, (double)a.pv.nhap[0], (double)a.pv.nhap[1], F[NS - 1], Gt[NS - 1], (double)v[0], (double)v[1], (double)v[2],
                               (double)v[3], u128_to_double(join_u128(v + 4)), u128_to_double(join_u128(v + 8)), res);
         } else {
+            // e(S) = sum_g p_g * cnt_g(S) / N_g (DISTANT_ADMIXTURE_MODELS.py:136-139), tabulated once per draw
+            double *etab = reinterpret_cast<double *>(wbase + lay.etab) + ((size_t)dgrp << NR);
+            distant_fill_etab<uint32_t>(ftab, a.pv, NR, etab, lo, LPD);
+            __syncwarp();
             double two = 0, two_sph = 0, three = 0;
-            poly_distant_blocked<uint32_t>(ftab, a.pv, NR, a.terms, a.n_terms, lo, LPD, two, two_sph, three);
+            poly_distant_etab(etab, NR, a.terms, a.n_terms, lo, LPD, two, two_sph, three);
             two = group_sum_f64<LPD>(two); two_sph = group_sum_f64<LPD>(two_sph); three = group_sum_f64<LPD>(three);
-            if (lo == 0) {
-                double Ef = 0.0;                                 // e(S) = sum_g p_g * cnt_g(S) / N_g (DISTANT_ADMIXTURE_MODELS.py:136-139)
-                for (int g = 0; g < G; ++g) Ef = Ef + a.pv.coef[g] * (double)ftab[((size_t)g << NR) + NS - 1] / (double)a.pv.nhap[g];
-                finish_distant(scale, Ef, two, two_sph, three, res);
-            }
+            if (lo == 0) finish_distant(scale, etab[NS - 1], two, two_sph, three, res);
         }
         if (lo == 0 && live) {
             const int64_t o = a.pos ? a.pos[draw] : draw;

@@ -12,7 +12,7 @@ static int launch_lanes_t(ldpgta_ctx *c, const GeneralArgs &a)
 {
     constexpr int DPW = 32 >> KL;
     static const int max_warps = [] { const char *e = getenv("LDPGTA_LANES_WARPS"); return e ? std::max(1, atoi(e)) : 12; }();
-    const LanesSmem lay = lanes_smem_layout<NR, KL>(a.pv);
+    const LanesSmem lay = lanes_smem_layout<NR, KL>(a.pv, a.kind == LDPGTA_DISTANT_ADMIXTURE);
     const int fit = (c->max_smem_optin - 1024) / lay.per_warp;
     if (fit < 2) return 1;                                   // rows too long for two warps per SM: the table kernel takes it
     const int nwarps = std::min(std::min(max_warps, LanesWarps<NR>::MAX), fit);
@@ -43,7 +43,7 @@ int launch_lanes(ldpgta_ctx *c, GeneralArgs a)
     a.n_terms = c->n_hi_terms[h];
     a.wide = 0;
     for (int g = 0; g < c->G; ++g) a.wide |= c->nhap[g] > 16383u;
-    a.kl = a.kh = a.wc = 0;
+    a.kl = a.kh = a.wc = 0; a.etab = 0;
     a.table_scratch = nullptr; a.table_stride = 0;
     static const int alt = [] { const char *e = getenv("LDPGTA_LANES_ALT"); return e ? atoi(e) : 0; }();     // tuning: the other low/high split (measured slower: tools/sweep_sizes.sh)
     if (alt)

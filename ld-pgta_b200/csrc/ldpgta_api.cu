@@ -136,7 +136,7 @@ static int run_uniform(ldpgta_ctx *c, int kind, int n, const int32_t *idx_dev, i
     }
     GeneralArgs a;
     a.pv = override_view ? *override_view : make_view(c, proportions);
-    a.kind = kind; a.n = n; a.kl = a.kh = a.wc = 0;
+    a.kind = kind; a.n = n; a.kl = a.kh = a.wc = 0; a.etab = 0;
     a.idx = idx_dev; a.n_draws = n_draws; a.pos = pos_dev; a.out = out_dev; a.counts_out = counts_dev;
     a.terms = nullptr; a.n_terms = 0; a.wide = 0; a.table_scratch = nullptr; a.table_stride = 0;
     // measured (tools/bench_lanes.sh): k_mid leads at 5 reads of a one-group model, k_lanes from 6 reads on

@@ -213,15 +213,18 @@ __device__ void poly_distant_blocked(const CT *ftab, const PanelView &pv, int n,
         two_sph += prod * (double)((2ull << pa) + (1ull << (n - 1 - pa)));
     }
     auto triple = [&](uint32_t ra, uint32_t rb, uint32_t rc) {
-        double X[16], Y[16], Z[16], acc = 0.0;
-        row(top_row + ra, X); row(rb, Y); row(rc, Z);
+        // the Y and Z rows stay in registers (64), the X entries are formed where they are used: three rows of doubles
+        // do not fit 128 registers
+        double Y[16], Z[16], acc = 0.0;
+        row(rb, Y); row(rc, Z);
+        const uint32_t xrow = (top_row + ra) << 4;
 #pragma unroll
         for (int s = 0; s < 16; ++s) {
             double cv = 0.0;
 #pragma unroll
             for (int b = 0; b < 16; ++b)
                 if ((b & s) == b) cv += Y[b] * Z[s ^ b];
-            acc += X[15 ^ s] * cv;
+            acc += E(xrow | (15 ^ s)) * cv;
         }
         return acc;
     };
@@ -234,12 +237,80 @@ __device__ void poly_distant_blocked(const CT *ftab, const PanelView &pv, int n,
 }
 
 
+
+// ---- distant admixture from a tabulated e(S) ------------------------------------------------------
+template <typename CT>
+__device__ void distant_fill_etab(const CT *ftab, const PanelView &pv, int n, double *etab, int tid, int T)
+{
+    const int G = pv.G;
+    const uint32_t NS = 1u << n;
+    for (uint32_t S = tid; S < NS; S += T) {
+        double e = 0.0;
+        for (int g = 0; g < G; ++g) e = e + pv.coef[g] * (double)ftab[((size_t)g << n) + S] / (double)pv.nhap[g];
+        etab[S] = e;
+    }
+}
+
+template <int SPACE>
+__device__ __forceinline__ void poly_distant_etab_impl(const double *E, int n, const u64 *terms, int64_t n_terms, int tid, int T,
+                                                       double &two_out, double &two_sph_out, double &three_out)
+{
+    const int h = n - 5;
+    const uint32_t top_row = 1u << h, usub = (1u << (n - 1)) - 1u, top = 1u << (n - 1);
+    auto row = [&](uint32_t r, double *v) {
+        const double *p = E + ((size_t)r << 4);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const uint4 x = load128<SPACE>(p + 2 * q);
+            v[2 * q] = __hiloint2double((int)x.y, (int)x.x);
+            v[2 * q + 1] = __hiloint2double((int)x.w, (int)x.z);
+        }
+    };
+    double two = 0, two_sph = 0, three = 0;
+    for (uint32_t a = tid; a < usub; a += T) {
+        const double prod = E[top | a] * E[usub ^ a];
+        const int pa = __popc(a);
+        two += prod;
+        two_sph += prod * (double)((2ull << pa) + (1ull << (n - 1 - pa)));
+    }
+    auto triple = [&](uint32_t ra, uint32_t rb, uint32_t rc) {
+        double Y[16], Z[16], acc = 0.0;                      // the X row is read where it is used (three rows do not fit)
+        row(rb, Y); row(rc, Z);
+        const double *X = E + ((size_t)(top_row + ra) << 4);
+#pragma unroll
+        for (int s = 0; s < 16; ++s) {
+            double cv = 0.0;
+#pragma unroll
+            for (int b = 0; b < 16; ++b)
+                if ((b & s) == b) cv += Y[b] * Z[s ^ b];
+            acc += X[15 ^ s] * cv;
+        }
+        return acc;
+    };
+    u64 t_next = tid < n_terms ? terms[tid] : 0;
+    for (int64_t e = tid; e < n_terms; e += T) {
+        const u64 t = t_next;
+        if (e + T < n_terms) t_next = terms[e + T];
+        three += triple((uint32_t)(t & 0xffffu), (uint32_t)(t >> 16) & 0xffffu, (uint32_t)(t >> 32) & 0xffffu);
+    }
+    if (tid == 0) three += 0.5 * triple(top_row - 1u, 0u, 0u);
+    two_out = two; two_sph_out = two_sph; three_out = three;
+}
+
+__device__ void poly_distant_etab(const double *etab, int n, const u64 *terms, int64_t n_terms, int tid, int T,
+                                  double &two, double &two_sph, double &three)
+{
+    if (__isShared(etab)) poly_distant_etab_impl<1>(etab, n, terms, n_terms, tid, T, two, two_sph, three);
+    else poly_distant_etab_impl<0>(etab, n, terms, n_terms, tid, T, two, two_sph, three);
+}
+
 #define LDPGTA_INST(CT)                                                                                              \
     template __device__ void poly_homog_blocked<CT, uint32_t>(const CT *, int, const u64 *, int64_t, int, int, u64 &, u64 &, u128 &); \
     template __device__ void poly_homog_blocked<CT, u64>(const CT *, int, const u64 *, int64_t, int, int, u64 &, u64 &, u128 &);      \
     template __device__ void poly_recent_blocked<CT, uint32_t>(const CT *, const CT *, int, const u64 *, int64_t, int, int, u64 &, u64 &, u64 &, u64 &, u128 &, u128 &); \
     template __device__ void poly_recent_blocked<CT, u64>(const CT *, const CT *, int, const u64 *, int64_t, int, int, u64 &, u64 &, u64 &, u64 &, u128 &, u128 &);      \
-    template __device__ void poly_distant_blocked<CT>(const CT *, const PanelView &, int, const u64 *, int64_t, int, int, double &, double &, double &);
+    template __device__ void poly_distant_blocked<CT>(const CT *, const PanelView &, int, const u64 *, int64_t, int, int, double &, double &, double &); \
+    template __device__ void distant_fill_etab<CT>(const CT *, const PanelView &, int, double *, int, int);
 LDPGTA_INST(uint16_t)
 LDPGTA_INST(uint32_t)
 #undef LDPGTA_INST

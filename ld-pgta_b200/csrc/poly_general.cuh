@@ -33,4 +33,13 @@ template <typename CT>
 __device__ void poly_distant_blocked(const CT *ftab, const PanelView &pv, int n, const u64 *terms, int64_t n_terms,
                                      int tid, int T, double &two, double &two_sph, double &three);
 
+// Distant admixture with the effective frequencies tabulated once per draw: etab[S] = sum_g p_g * cnt_g(S) / N_g
+// (DISTANT_ADMIXTURE_MODELS.py:136-139) for all 2^n subsets, so that the polynomial reads doubles instead of redoing the
+// conversions and divisions at every use (an entry is used ~1.5^n times).  fill: threads tid of T, the caller
+// synchronises them before poly_distant_etab.
+template <typename CT>
+__device__ void distant_fill_etab(const CT *ftab, const PanelView &pv, int n, double *etab, int tid, int T);
+__device__ void poly_distant_etab(const double *etab, int n, const u64 *terms, int64_t n_terms, int tid, int T,
+                                  double &two, double &two_sph, double &three);
+
 }  // namespace ldpgta
