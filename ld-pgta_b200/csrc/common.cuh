@@ -224,6 +224,8 @@ struct ldpgta_ctx {
     // joint-frequency tables that do not fit shared memory (17-18 reads, or two-group models at 16): one slice per resident CTA
     unsigned char *table_scratch = nullptr;
     size_t table_scratch_bytes = 0;
+    double *etab_scratch = nullptr;           // e(S) tables of the distant model when they do not fit shared memory
+    size_t etab_scratch_bytes = 0;
 
     int64_t launches = 0;
 };

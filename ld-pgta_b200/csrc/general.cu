@@ -79,6 +79,21 @@ static int launch_general_t(ldpgta_ctx *c, GeneralArgs a, const GeneralPlan &p)
         a.table_scratch = c->table_scratch;
         a.table_stride = stride;
     }
+    a.etab_scratch = nullptr; a.etab_stride = 0;
+    if (a.kind == LDPGTA_DISTANT_ADMIXTURE && a.n >= 5 && !p.etab) {
+        // e(S) as doubles in a global slice per resident CTA (L2 / HBM): still far cheaper than forming it at every use
+        const size_t stride = (size_t)1 << a.n, need = stride * 8 * blocks;
+        if (c->etab_scratch_bytes < need) {
+            LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
+            if (c->etab_scratch) LDPGTA_CUDA(cudaFree(c->etab_scratch));
+            c->etab_scratch = nullptr; c->etab_scratch_bytes = 0;
+            LDPGTA_CUDA(cudaMalloc((void **)&c->etab_scratch, need));
+            c->etab_scratch_bytes = need;
+        }
+        a.etab = 2;
+        a.etab_scratch = c->etab_scratch;
+        a.etab_stride = stride;
+    }
     kern<<<blocks, 32 * p.nw, p.smem, c->stream>>>(a);
     c->launches++;
     LDPGTA_CUDA(cudaGetLastError());

@@ -29,7 +29,9 @@ struct GeneralArgs {
     int kind;
     int n, kl, kh;           // reads per draw; low/high split
     int wc;                  // words per table chunk
-    int etab;                // distant admixture: tabulate e(S) in shared memory (fits for n <= 13)
+    int etab;                // distant admixture: e(S) tabulated in shared memory (1) or in a global slice per CTA (2)
+    double *etab_scratch;    // the global slices, etab_stride doubles apart
+    size_t etab_stride;
     const int32_t *idx;      // [n_draws][n]
     int64_t n_draws;
     const int64_t *pos;      // optional scatter positions
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(512, 1) k_general(const GeneralArgs a)
     extern __shared__ __align__(128) unsigned char smem[];
     const int n = a.n, kl = a.kl, kh = a.kh, G = a.pv.G;
     const int LS = 1 << kl, HS = 1 << kh, NS = 1 << n;
-    const GeneralSmem lay = general_smem_layout<CT>(a.pv, n, kl, kh, a.wc, a.table_scratch == nullptr, a.etab != 0);
+    const GeneralSmem lay = general_smem_layout<CT>(a.pv, n, kl, kh, a.wc, a.table_scratch == nullptr, a.etab == 1);
     int32_t *s_idx = reinterpret_cast<int32_t *>(smem);
     u64 *s_masks = reinterpret_cast<u64 *>(smem + lay.masks);
     u64 *ltab = reinterpret_cast<u64 *>(smem + lay.ltab);
@@ -394,7 +396,8 @@ __global__ void __launch_bounds__(512, 1) k_general(const GeneralArgs a)
                 return e;
             };
             double two = 0, two_sph = 0, three = 0;
-            double *etab = a.etab ? reinterpret_cast<double *>(smem + lay.etab) : nullptr;
+            double *etab = a.etab == 1 ? reinterpret_cast<double *>(smem + lay.etab)
+                         : a.etab == 2 ? a.etab_scratch + (size_t)blockIdx.x * a.etab_stride : nullptr;
             if (n >= 5 && etab) {
                 distant_fill_etab<CT>(ftab, a.pv, n, etab, tid, T);
                 __syncthreads();

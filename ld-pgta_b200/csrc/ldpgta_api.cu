@@ -136,7 +136,7 @@ static int run_uniform(ldpgta_ctx *c, int kind, int n, const int32_t *idx_dev, i
     }
     GeneralArgs a;
     a.pv = override_view ? *override_view : make_view(c, proportions);
-    a.kind = kind; a.n = n; a.kl = a.kh = a.wc = 0; a.etab = 0;
+    a.kind = kind; a.n = n; a.kl = a.kh = a.wc = 0; a.etab = 0; a.etab_scratch = nullptr; a.etab_stride = 0;
     a.idx = idx_dev; a.n_draws = n_draws; a.pos = pos_dev; a.out = out_dev; a.counts_out = counts_dev;
     a.terms = nullptr; a.n_terms = 0; a.wide = 0; a.table_scratch = nullptr; a.table_stride = 0;
     // measured (tools/bench_lanes.sh): k_mid leads at 5 reads of a one-group model, k_lanes from 6 reads on
@@ -224,10 +224,11 @@ static int run_pipelined(ldpgta_ctx *c, int kind, int n0, const int32_t *read_id
     if (int rc = ensure_pipeline(c, (int)n_chunks + 1)) return rc;
 
     // everything the enqueued operations depend on
-    struct { int kind, n0, G; int64_t n_draws, per, n_reads; const void *idx, *out, *dbuf, *scratch; PanelView pv; } sig;
+    struct { int kind, n0, G; int64_t n_draws, per, n_reads; const void *idx, *out, *dbuf, *scratch, *escratch; PanelView pv; } sig;
     memset(&sig, 0, sizeof sig);
     sig.kind = kind; sig.n0 = n0; sig.G = c->G; sig.n_draws = n_draws; sig.per = per; sig.n_reads = c->n_reads;
-    sig.idx = read_idx; sig.out = out; sig.dbuf = c->d_buf; sig.scratch = c->table_scratch; sig.pv = make_view(c, proportions);
+    sig.idx = read_idx; sig.out = out; sig.dbuf = c->d_buf; sig.scratch = c->table_scratch; sig.escratch = c->etab_scratch;
+    sig.pv = make_view(c, proportions);
     const uint64_t key = fnv1a(&sig, sizeof sig) | 1ull;
 
     int rc = 0;
@@ -376,6 +377,7 @@ int ldpgta_destroy(ldpgta_ctx *c)
     if (c->allele_complement) cudaFree(c->allele_complement);
     if (c->d_buf) cudaFree(c->d_buf);
     if (c->d_llr) cudaFree(c->d_llr);
+    if (c->etab_scratch) cudaFree(c->etab_scratch);
     if (c->pipe_exec) cudaGraphExecDestroy(c->pipe_exec);
     if (c->ev_fork) { cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join_in); cudaEventDestroy(c->ev_join_out); }
     if (c->d_flag) cudaFree(c->d_flag);

@@ -196,9 +196,13 @@ __device__ void poly_distant_blocked(const CT *ftab, const PanelView &pv, int n,
 {
     const int h = n - 5, G = pv.G;
     const uint32_t top_row = 1u << h, usub = (1u << (n - 1)) - 1u, top = 1u << (n - 1);
+    // this path serves draws whose e(S) table does not fit shared memory (15 or more reads): every entry is formed where it
+    // is used, ~1.5^n times, so the reference's p * cnt / N becomes cnt * (p / N) -- one rounding apart (1e-16 relative)
+    double wg[MAXG];
+    for (int g = 0; g < G; ++g) wg[g] = pv.coef[g] / (double)pv.nhap[g];
     auto E = [&](uint32_t S) {
         double e = 0.0;
-        for (int g = 0; g < G; ++g) e = e + pv.coef[g] * (double)ftab[((size_t)g << n) + S] / (double)pv.nhap[g];
+        for (int g = 0; g < G; ++g) e = e + wg[g] * (double)ftab[((size_t)g << n) + S];
         return e;
     };
     auto row = [&](uint32_t r, double *v) {
