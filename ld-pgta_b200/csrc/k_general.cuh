@@ -398,12 +398,11 @@ __global__ void __launch_bounds__(512, 1) k_general(const GeneralArgs a)
             double two = 0, two_sph = 0, three = 0;
             double *etab = a.etab == 1 ? reinterpret_cast<double *>(smem + lay.etab)
                          : a.etab == 2 ? a.etab_scratch + (size_t)blockIdx.x * a.etab_stride : nullptr;
-            if (n >= 5 && etab) {
+            if (n >= 5) {                                    // the launcher always provides a table for 5 or more reads
                 distant_fill_etab<CT>(ftab, a.pv, n, etab, tid, T);
                 __syncthreads();
                 poly_distant_etab(etab, n, a.terms, a.n_terms, tid, T, two, two_sph, three);
-            } else if (n >= 5) poly_distant_blocked<CT>(ftab, a.pv, n, a.terms, a.n_terms, tid, T, two, two_sph, three);
-            else
+            } else
             for (uint32_t A = top + warp; A < full; A += NW) {
                 const uint32_t rest = full ^ A;
                 const double Ea = E(A);

@@ -189,59 +189,6 @@ __device__ void poly_recent_blocked(const CT *F, const CT *G, int n, const u64 *
     else poly_recent_impl<CT, ACC, 0>(F, G, n, terms, n_terms, tid, T, ff, gg, fg, fg_sph, ffg, ggf);
 }
 
-// ---- distant admixture: float frequencies e(S) = sum_g p_g cnt_g(S) / N_g formed on the fly -----
-template <typename CT>
-__device__ void poly_distant_blocked(const CT *ftab, const PanelView &pv, int n, const u64 *terms, int64_t n_terms,
-                                                     int tid, int T, double &two_out, double &two_sph_out, double &three_out)
-{
-    const int h = n - 5, G = pv.G;
-    const uint32_t top_row = 1u << h, usub = (1u << (n - 1)) - 1u, top = 1u << (n - 1);
-    // this path serves draws whose e(S) table does not fit shared memory (15 or more reads): every entry is formed where it
-    // is used, ~1.5^n times, so the reference's p * cnt / N becomes cnt * (p / N) -- one rounding apart (1e-16 relative)
-    double wg[MAXG];
-    for (int g = 0; g < G; ++g) wg[g] = pv.coef[g] / (double)pv.nhap[g];
-    auto E = [&](uint32_t S) {
-        double e = 0.0;
-        for (int g = 0; g < G; ++g) e = e + wg[g] * (double)ftab[((size_t)g << n) + S];
-        return e;
-    };
-    auto row = [&](uint32_t r, double *v) {
-#pragma unroll
-        for (int l = 0; l < 16; ++l) v[l] = E((r << 4) | l);
-    };
-    double two = 0, two_sph = 0, three = 0;                      // local accumulators (see poly_homog_blocked)
-    for (uint32_t a = tid; a < usub; a += T) {
-        const double prod = E(top | a) * E(usub ^ a);
-        const int pa = __popc(a);
-        two += prod;
-        two_sph += prod * (double)((2ull << pa) + (1ull << (n - 1 - pa)));
-    }
-    auto triple = [&](uint32_t ra, uint32_t rb, uint32_t rc) {
-        // the Y and Z rows stay in registers (64), the X entries are formed where they are used: three rows of doubles
-        // do not fit 128 registers
-        double Y[16], Z[16], acc = 0.0;
-        row(rb, Y); row(rc, Z);
-        const uint32_t xrow = (top_row + ra) << 4;
-#pragma unroll
-        for (int s = 0; s < 16; ++s) {
-            double cv = 0.0;
-#pragma unroll
-            for (int b = 0; b < 16; ++b)
-                if ((b & s) == b) cv += Y[b] * Z[s ^ b];
-            acc += E(xrow | (15 ^ s)) * cv;
-        }
-        return acc;
-    };
-    for (int64_t e = tid; e < n_terms; e += T) {
-        const u64 t = terms[e];
-        three += triple((uint32_t)(t & 0xffffu), (uint32_t)(t >> 16) & 0xffffu, (uint32_t)(t >> 32) & 0xffffu);
-    }
-    if (tid == 0) three += 0.5 * triple(top_row - 1u, 0u, 0u);
-    two_out = two; two_sph_out = two_sph; three_out = three;
-}
-
-
-
 // ---- distant admixture from a tabulated e(S) ------------------------------------------------------
 template <typename CT>
 __device__ void distant_fill_etab(const CT *ftab, const PanelView &pv, int n, double *etab, int tid, int T)
@@ -313,7 +260,6 @@ __device__ void poly_distant_etab(const double *etab, int n, const u64 *terms, i
     template __device__ void poly_homog_blocked<CT, u64>(const CT *, int, const u64 *, int64_t, int, int, u64 &, u64 &, u128 &);      \
     template __device__ void poly_recent_blocked<CT, uint32_t>(const CT *, const CT *, int, const u64 *, int64_t, int, int, u64 &, u64 &, u64 &, u64 &, u128 &, u128 &); \
     template __device__ void poly_recent_blocked<CT, u64>(const CT *, const CT *, int, const u64 *, int64_t, int, int, u64 &, u64 &, u64 &, u64 &, u128 &, u128 &);      \
-    template __device__ void poly_distant_blocked<CT>(const CT *, const PanelView &, int, const u64 *, int64_t, int, int, double &, double &, double &); \
     template __device__ void distant_fill_etab<CT>(const CT *, const PanelView &, int, double *, int, int);
 LDPGTA_INST(uint16_t)
 LDPGTA_INST(uint32_t)

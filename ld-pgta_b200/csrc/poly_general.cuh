@@ -29,10 +29,6 @@ __device__ void poly_homog_blocked(const CT *F, int n, const u64 *terms, int64_t
 template <typename CT, typename ACC>
 __device__ void poly_recent_blocked(const CT *F, const CT *G, int n, const u64 *terms, int64_t n_terms, int tid, int T,
                                     u64 &ff, u64 &gg, u64 &fg, u64 &fg_sph, u128 &ffg, u128 &ggf);
-template <typename CT>
-__device__ void poly_distant_blocked(const CT *ftab, const PanelView &pv, int n, const u64 *terms, int64_t n_terms,
-                                     int tid, int T, double &two, double &two_sph, double &three);
-
 // Distant admixture with the effective frequencies tabulated once per draw: etab[S] = sum_g p_g * cnt_g(S) / N_g
 // (DISTANT_ADMIXTURE_MODELS.py:136-139) for all 2^n subsets, so that the polynomial reads doubles instead of redoing the
 // conversions and divisions at every use (an entry is used ~1.5^n times).  fill: threads tid of T, the caller
