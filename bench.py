@@ -25,7 +25,6 @@ samples of the same workload.
 """
 import argparse
 import json
-import math
 import os
 import subprocess
 import sys

@@ -14,7 +14,6 @@ import os
 import pickle
 import random
 import re
-import sys
 import time
 from itertools import product
 from math import comb

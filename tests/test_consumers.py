@@ -4,7 +4,7 @@ detection.  CPU part: the oracle against vectors made by running the unmodified 
 (tests/golden/make_golden_consumers.py) and the product's host logic (bin bookkeeping, crossover scan);
 GPU part: the per-bin statistics kernel through the C-ABI.
 """
-import contextlib, io, math
+import contextlib, io
 import numpy as np
 import pytest
 

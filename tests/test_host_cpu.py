@@ -2,7 +2,6 @@
 host-side logic (packing, windowing, scores, draw planning) matches the reference's
 golden vectors, and the product fails loudly without a GPU."""
 import os
-import pickle
 import random
 import re
 import subprocess
