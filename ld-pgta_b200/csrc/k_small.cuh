@@ -205,7 +205,11 @@ struct SmallPipe {
     static constexpr int STAGE_BYTES = 256 * NR * WPL;                       // (32/LPD) draws * NR rows * LPD*WPL words * 8 B
     static constexpr int NWARPS_RAW = (220 * 1024) / STAGE_BYTES;
     static constexpr int NWARPS = NWARPS_RAW > 16 ? 16 : (NWARPS_RAW & ~3);     // register file is allocated per 4 warps
-    static constexpr int SMEM = NWARPS * (STAGE_BYTES + 16);
+    // one-group models: the counts of 32 draws (8 tiles) wait in a per-warp table so that the lookups and the float64
+    // polynomial run once per 32 draws with one draw per lane, instead of once per tile with every draw done by 8 lanes
+    static constexpr int BATCH_BYTES = 32 * 16 * 4;
+    static constexpr int BARS = NWARPS * (STAGE_BYTES + BATCH_BYTES);         // byte offset of the mbarriers
+    static constexpr int SMEM = BARS + NWARPS * 16;
 };
 
 template <int NR, int LPD, int WPL, int KIND>
@@ -219,7 +223,11 @@ __global__ void __launch_bounds__(SmallPipe<NR, WPL>::NWARPS * 32, 1) k_small(co
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);        // warp-uniform for the compiler: barrier and buffer addresses live in uniform registers
     const int lane_in = lane % LPD, dgrp = lane / LPD;
     unsigned char *wbase = smem + (size_t)warp * P::STAGE_BYTES;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (size_t)P::NWARPS * P::STAGE_BYTES) + warp;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + P::BARS) + warp;
+    // batched polynomial (one-group models): counts[quad][slot] as uint4, slot = tile-in-batch * DPW + draw-in-tile
+    uint4 *batch = reinterpret_cast<uint4 *>(smem + (size_t)P::NWARPS * P::STAGE_BYTES + (size_t)warp * P::BATCH_BYTES);
+    constexpr bool BATCHED = KIND == LDPGTA_HOMOGENEOUS;
+    constexpr int TPB = LPD;                                                  // tiles per batch: TPB * DPW = 32 draws
 
     if (lane == 0) mbar_init(bar, 1);
     fence_proxy_async();
@@ -325,8 +333,36 @@ __global__ void __launch_bounds__(SmallPipe<NR, WPL>::NWARPS * 32, 1) k_small(co
         small_subset_counts<NR, WPL>(m, c);
         small_group_sum<NR, LPD>(c, a.pv.nhap[g] <= 65535u);
         if (a.counts_out && writer) small_dump<NR>(a, draw, g, c);
-        double res[4];
-        if (model.fold(a.pv, g, c, res) && writer) small_store(a, draw, res);
+        if (BATCHED) {
+            // park this tile's counts; every TPB tiles (or at the end) each lane finishes one draw
+            const int k = (int)(q % TPB);
+            if (lane_in == 0) {
+                const int slot = k * DPW + dgrp;
+#pragma unroll
+                for (int j = 0; j < NS / 4; ++j) batch[j * 32 + slot] = make_uint4(c[4 * j], c[4 * j + 1], c[4 * j + 2], c[4 * j + 3]);
+            }
+            if (k == TPB - 1 || q + 1 == n_stages) {
+                __syncwarp();
+                uint32_t cc[NS];
+#pragma unroll
+                for (int j = 0; j < NS / 4; ++j) {
+                    const uint4 v = batch[j * 32 + lane];
+                    cc[4 * j] = v.x; cc[4 * j + 1] = v.y; cc[4 * j + 2] = v.z; cc[4 * j + 3] = v.w;
+                }
+                const int kk = lane / DPW;                                     // which tile of the batch this lane finishes
+                const int64_t tile_k = tile0 + (q - k + kk) * tstride;
+                const int64_t draw_k = tile_k * DPW + lane % DPW;
+                double res[4];
+                if (kk <= k) {
+                    model.fold(a.pv, 0, cc, res);
+                    if (draw_k < a.n_draws) small_store(a, draw_k, res);
+                }
+                __syncwarp();
+            }
+        } else {
+            double res[4];
+            if (model.fold(a.pv, g, c, res) && writer) small_store(a, draw, res);
+        }
     }
 }
 
