@@ -27,7 +27,11 @@ struct MidPipe {
     // 6 reads keep 60 mask registers and 64 counts live: 12 warps (168 registers each) instead of 16 (128, spilling).
     // (A 7-read instance was measured too: 255 registers with spills, half the speed of the table kernel.)
     static constexpr int NWARPS = (NR == 6 && NWARPS_FIT > LDPGTA_MID6_WARPS) ? LDPGTA_MID6_WARPS : NWARPS_FIT;
-    static constexpr int SMEM = NWARPS * (STAGE_BYTES + 16);
+    // the counts of 32 draws (16 tiles) wait in a per-warp table; the partition polynomial then runs once per 32 draws,
+    // one draw per lane, instead of once per tile with each draw done by 16 lanes
+    static constexpr int BATCH_BYTES = 32 * (1 << NR) * 4;
+    static constexpr int BARS = NWARPS * (STAGE_BYTES + BATCH_BYTES);
+    static constexpr int SMEM = BARS + NWARPS * 16;
 };
 
 // exact integer partition sums from the 2^NR counts (index = subset bitmask)
@@ -73,7 +77,9 @@ __global__ void __launch_bounds__(MidPipe<NR, W64>::NWARPS * 32, 1) k_mid(const 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane_in = lane % LPD, dgrp = lane / LPD;
     unsigned char *wbase = smem + (size_t)warp * P::STAGE_BYTES;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (size_t)P::NWARPS * P::STAGE_BYTES) + warp;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + P::BARS) + warp;
+    uint4 *batch = reinterpret_cast<uint4 *>(smem + (size_t)P::NWARPS * P::STAGE_BYTES + (size_t)warp * P::BATCH_BYTES);
+    constexpr int TPB = 32 / DPW;                                             // tiles per polynomial batch
 
     if (lane == 0) mbar_init(bar, 1);
     fence_proxy_async();
@@ -172,9 +178,30 @@ __global__ void __launch_bounds__(MidPipe<NR, W64>::NWARPS * 32, 1) k_mid(const 
             c[2 * s + 1] = v >> 16;
         }
         if (a.counts_out && writer) small_dump<NR>(a, draw, 0, c);
-        double res[4];
-        mid_polynomial<NR>(c, a.pv.nhap[0], res);
-        if (writer) small_store(a, draw, res);
+        // park this tile's counts: batch[quad][slot], slot = tile-in-batch * DPW + draw-in-tile
+        const int k = (int)(q % TPB);
+        if (lane_in == 0) {
+            const int slot = k * DPW + dgrp;
+#pragma unroll
+            for (int j = 0; j < NS / 4; ++j) batch[j * 32 + slot] = make_uint4(c[4 * j], c[4 * j + 1], c[4 * j + 2], c[4 * j + 3]);
+        }
+        if (k == TPB - 1 || q + 1 == my_tiles) {
+            __syncwarp();
+            uint32_t cc[NS];
+#pragma unroll
+            for (int j = 0; j < NS / 4; ++j) {
+                const uint4 v = batch[j * 32 + lane];
+                cc[4 * j] = v.x; cc[4 * j + 1] = v.y; cc[4 * j + 2] = v.z; cc[4 * j + 3] = v.w;
+            }
+            const int kk = lane / DPW;
+            const int64_t draw_k = (tile0 + (q - k + kk) * tstride) * DPW + lane % DPW;
+            if (kk <= k) {
+                double res[4];
+                mid_polynomial<NR>(cc, a.pv.nhap[0], res);
+                if (draw_k < a.n_draws) small_store(a, draw_k, res);
+            }
+            __syncwarp();
+        }
     }
 }
 
