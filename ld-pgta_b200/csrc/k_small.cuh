@@ -147,6 +147,16 @@ struct SmallModel {
         if (KIND == LDPGTA_DISTANT_ADMIXTURE)
 #pragma unroll
             for (int s = 0; s < NS; ++s) f[s] = 0.0;
+        if (KIND == LDPGTA_RECENT_ADMIXTURE) c0[0] = 0;
+    }
+    // two-group closed forms from the counts of both groups
+    static __device__ __forceinline__ void finish_recent(const PanelView &pv, const uint32_t *ca, const uint32_t *cb, double *res)
+    {
+        const double *norm0 = pv.norm[0], *norm1 = pv.norm[1];
+        double fr[NS], gr[NS];
+#pragma unroll
+        for (int s = 1; s < NS; ++s) { fr[s] = __ldg(norm0 + ca[s]); gr[s] = __ldg(norm1 + cb[s]); }
+        closed_recent<NR>(fr, gr, res);
     }
     // returns true when res[] is final
     __device__ __forceinline__ bool fold(const PanelView &pv, int g, const uint32_t *c, double *res)
@@ -164,11 +174,7 @@ struct SmallModel {
                 for (int s = 1; s < NS; ++s) c0[s] = c[s];
                 return false;
             }
-            const double *norm0 = pv.norm[0], *norm1 = pv.norm[1];
-            double fr[NS], gr[NS];
-#pragma unroll
-            for (int s = 1; s < NS; ++s) { fr[s] = __ldg(norm0 + c0[s]); gr[s] = __ldg(norm1 + c[s]); }
-            closed_recent<NR>(fr, gr, res);
+            finish_recent(pv, c0, c, res);
             return true;
         } else {
             // effective_joint_frequency, DISTANT_ADMIXTURE_MODELS.py:136-139: sum_g p_g * cnt_g / N_g, in group order
@@ -228,6 +234,8 @@ __global__ void __launch_bounds__(SmallPipe<NR, WPL>::NWARPS * 32, 1) k_small(co
     uint4 *batch = reinterpret_cast<uint4 *>(smem + (size_t)P::NWARPS * P::STAGE_BYTES + (size_t)warp * P::BATCH_BYTES);
     constexpr bool BATCHED = KIND == LDPGTA_HOMOGENEOUS;
     constexpr int TPB = LPD;                                                  // tiles per batch: TPB * DPW = 32 draws
+    // recent admixture: the same with both groups' counts packed as 16-bit halves (groups of at most 65535 haplotypes)
+    const bool batched2 = KIND == LDPGTA_RECENT_ADMIXTURE && a.pv.nhap[0] <= 65535u && a.pv.nhap[1] <= 65535u;
 
     if (lane == 0) mbar_init(bar, 1);
     fence_proxy_async();
@@ -358,6 +366,37 @@ __global__ void __launch_bounds__(SmallPipe<NR, WPL>::NWARPS * 32, 1) k_small(co
                     if (draw_k < a.n_draws) small_store(a, draw_k, res);
                 }
                 __syncwarp();
+            }
+        } else if (KIND == LDPGTA_RECENT_ADMIXTURE && batched2) {
+            double res[4];
+            if (g == 0) model.fold(a.pv, g, c, res);                           // keeps group 0's counts
+            else {
+                const int k = (int)((q >> 1) % TPB);
+                if (lane_in == 0) {
+                    const int slot = k * DPW + dgrp;
+#pragma unroll
+                    for (int j = 0; j < NS / 4; ++j)
+                        batch[j * 32 + slot] = make_uint4(model.c0[4 * j] | (c[4 * j] << 16), model.c0[4 * j + 1] | (c[4 * j + 1] << 16),
+                                                          model.c0[4 * j + 2] | (c[4 * j + 2] << 16), model.c0[4 * j + 3] | (c[4 * j + 3] << 16));
+                }
+                if (k == TPB - 1 || q + 1 == n_stages) {
+                    __syncwarp();
+                    uint32_t ca[NS], cb[NS];
+#pragma unroll
+                    for (int j = 0; j < NS / 4; ++j) {
+                        const uint4 v = batch[j * 32 + lane];
+                        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) { ca[4 * j + e] = w[e] & 0xffffu; cb[4 * j + e] = w[e] >> 16; }
+                    }
+                    const int kk = lane / DPW;
+                    const int64_t draw_k = (tile0 + ((q >> 1) - k + kk) * tstride) * DPW + lane % DPW;
+                    if (kk <= k) {
+                        SmallModel<NR, KIND>::finish_recent(a.pv, ca, cb, res);
+                        if (draw_k < a.n_draws) small_store(a, draw_k, res);
+                    }
+                    __syncwarp();
+                }
             }
         } else {
             double res[4];
