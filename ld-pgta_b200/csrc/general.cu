@@ -23,10 +23,13 @@ static int plan_general(const ldpgta_ctx *c, int n, int kind, GeneralPlan *p)
     p->kh = n - p->kl;
     uint32_t nmax = 0; int wmax = 0, wsum = 0;
     for (int g = 0; g < c->G; ++g) { nmax = std::max(nmax, c->nhap[g]); wmax = std::max(wmax, c->wp[g]); wsum += c->wp[g]; }
-    // joint-frequency tables: 32-bit entries in shared memory while they stay under 64 KB, then 16-bit entries (groups of
-    // at most 65535 haplotypes) up to 128 KB, otherwise one slice per resident CTA in global memory (L2-resident)
+    // joint-frequency tables in shared memory up to 128 KB, otherwise one slice per resident CTA in global memory (L2-resident)
     const size_t entries = (size_t)c->G << n;
-    p->u16 = entries * 4 > 64 * 1024 && nmax <= 65535u;
+    // 16-bit entries whenever the counts fit (groups of at most 65535 haplotypes): the polynomial, which waits on its table
+    // rows, reads half the bytes (measured at 13-14 reads: 0.83 -> 0.93, 0.77 -> 0.93 of the roofline; 12-13 reads of
+    // two-group models +10 %).  LDPGTA_PLAN_U32=1 restores 32-bit entries below 64 KB for comparison.
+    static const bool force_u32 = getenv("LDPGTA_PLAN_U32") != nullptr;
+    p->u16 = nmax <= 65535u && n >= 5 && (!force_u32 || entries * 4 > 64 * 1024);
     const size_t ct = p->u16 ? 2 : 4;
     p->table_bytes = entries * ct;
     p->global_table = p->table_bytes > 128 * 1024;
