@@ -30,10 +30,10 @@ static int launch_lanes_t(ldpgta_ctx *c, const GeneralArgs &a)
 int launch_lanes(ldpgta_ctx *c, GeneralArgs a)
 {
     if (getenv("LDPGTA_NO_LANES")) return 1;
-    // measured against the table kernel (tools/bench_lanes.sh): ahead up to 12 reads for one group, up to 11 for two-group
-    // models, whose polynomial (six trilinear forms per colouring) is too long for one warp at 12 reads
+    // measured against the table kernel (tools/sweep_sizes.sh with LDPGTA_LANES_MAXN): ahead up to 12 reads for one group,
+    // up to 11 for recent and 10 for distant admixture, whose polynomials are too long for one warp beyond that
     static const int max_n_env = [] { const char *e = getenv("LDPGTA_LANES_MAXN"); return e ? atoi(e) : 12; }();
-    const int max_n = std::min(max_n_env, a.kind == LDPGTA_HOMOGENEOUS ? 12 : 11);
+    const int max_n = std::min(max_n_env, a.kind == LDPGTA_HOMOGENEOUS ? 12 : a.kind == LDPGTA_RECENT_ADMIXTURE ? 11 : 10);
     if (a.n < 5 || a.n > max_n) return 1;
     for (int g = 0; g < c->G; ++g)
         if (c->wp[g] * 64 > 65535) return 1;           // 16-bit packed partial counts, row bytes of one bulk copy
