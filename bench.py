@@ -258,7 +258,7 @@ def kernel_name(n, model):
         return 'k_small<%d,8,10>' % n
     if n == 5 and model == 'homogeneous':
         return 'k_mid<5,5>'
-    if n <= {'homogeneous': 12, 'recent': 11, 'distant': 10}[model] and not (model == 'distant' and n == 5):
+    if n <= {'homogeneous': 12, 'recent': 12, 'distant': 10}[model] and not (model == 'distant' and n == 5):
         return 'k_lanes<%d,%d>' % (n, {5: 3, 6: 3, 7: 3, 8: 4, 9: 4}.get(n, 5))
     return 'k_general (n=%d)' % n
 

@@ -33,7 +33,7 @@ struct LanesSmem {           // per-warp byte offsets / sizes
     int per_warp;            // bytes per warp (mask buffer + tables + barrier)
 };
 
-template <int NR, int KL>
+template <int NR, int KL, typename CT>
 __host__ __device__ inline LanesSmem lanes_smem_layout(const PanelView &pv, bool distant)
 {
     constexpr int DPW = 32 >> KL;
@@ -48,7 +48,8 @@ __host__ __device__ inline LanesSmem lanes_smem_layout(const PanelView &pv, bool
     s.draw_stride = stride;
     s.buf_words = stride * DPW;
     s.ftab = s.buf_words * 8;
-    int off = s.ftab + DPW * ((pv.G << NR) * 4);
+    int off = s.ftab + DPW * ((pv.G << NR) * (int)sizeof(CT));
+    off = (off + 63) & ~63;
     off = (off + 15) & ~15;
     s.etab = -1;
     if (distant) { s.etab = off; off += DPW * (8 << NR); }
@@ -77,7 +78,8 @@ __device__ __forceinline__ double group_sum_f64(double v)
 template <int NR>
 struct LanesWarps { static constexpr int MAX = NR >= 12 ? 8 : 12; };
 
-template <int NR, int KL>
+// CT: count-table entries, uint16_t when every group has at most 65535 haplotypes (the polynomial reads half the bytes)
+template <int NR, int KL, typename CT>
 __global__ void __launch_bounds__(32 * LanesWarps<NR>::MAX, 1) k_lanes(const __grid_constant__ GeneralArgs a)
 {
     constexpr int KH = NR - KL, HS = 1 << KH, LPD = 1 << KL, DPW = 32 / LPD, NS = 1 << NR;
@@ -86,10 +88,10 @@ __global__ void __launch_bounds__(32 * LanesWarps<NR>::MAX, 1) k_lanes(const __g
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), nwarps = blockDim.x >> 5;
     const int lo = lane & (LPD - 1), dgrp = lane / LPD;
     const int G = a.pv.G;
-    const LanesSmem lay = lanes_smem_layout<NR, KL>(a.pv, a.kind == LDPGTA_DISTANT_ADMIXTURE);
+    const LanesSmem lay = lanes_smem_layout<NR, KL, CT>(a.pv, a.kind == LDPGTA_DISTANT_ADMIXTURE);
     unsigned char *wbase = smem + (size_t)warp * lay.per_warp;
     u64 *bufs = reinterpret_cast<u64 *>(wbase);
-    uint32_t *ftab = reinterpret_cast<uint32_t *>(wbase + lay.ftab) + (size_t)dgrp * (G << NR);
+    CT *ftab = reinterpret_cast<CT *>(wbase + lay.ftab) + (size_t)dgrp * (G << NR);
     uint64_t *bar = reinterpret_cast<uint64_t *>(wbase + lay.per_warp - 16);
 
     if (lane == 0) mbar_init(bar, 1);
@@ -198,9 +200,9 @@ __global__ void __launch_bounds__(32 * LanesWarps<NR>::MAX, 1) k_lanes(const __g
                 }
                 triple(lw, hm);
             }
-            uint32_t *F = ftab + ((size_t)g << NR);
+            CT *F = ftab + ((size_t)g << NR);
 #pragma unroll
-            for (int h = 0; h < HS; ++h) F[(h << KL) | lo] = PACK ? (acc[h >> 1] >> (16 * (h & 1))) & 0xffffu : acc[h];
+            for (int h = 0; h < HS; ++h) F[(h << KL) | lo] = (CT)(PACK ? (acc[h >> 1] >> (16 * (h & 1))) & 0xffffu : acc[h]);
             goff += NR * wp;
         }
         __syncwarp();                                          // all lanes are done with the masks; tables complete
@@ -223,8 +225,8 @@ __global__ void __launch_bounds__(32 * LanesWarps<NR>::MAX, 1) k_lanes(const __g
         if (a.kind == LDPGTA_HOMOGENEOUS) {
             u64 two = 0, two_sph = 0;
             u128 three = 0;
-            if (a.wide) poly_homog_blocked<uint32_t, u64>(ftab, NR, a.terms, a.n_terms, lo, LPD, two, two_sph, three);
-            else poly_homog_blocked<uint32_t, uint32_t>(ftab, NR, a.terms, a.n_terms, lo, LPD, two, two_sph, three);
+            if (a.wide) poly_homog_blocked<CT, u64>(ftab, NR, a.terms, a.n_terms, lo, LPD, two, two_sph, three);
+            else poly_homog_blocked<CT, uint32_t>(ftab, NR, a.terms, a.n_terms, lo, LPD, two, two_sph, three);
             u64 v[6];
             v[0] = two; v[1] = two_sph;
             split_u128(three, v + 2);
@@ -233,11 +235,11 @@ __global__ void __launch_bounds__(32 * LanesWarps<NR>::MAX, 1) k_lanes(const __g
             if (lo == 0)
                 finish_homogeneous(scale, (double)a.pv.nhap[0], ftab[NS - 1], (double)v[0], (double)v[1], u128_to_double(join_u128(v + 2)), res);
         } else if (a.kind == LDPGTA_RECENT_ADMIXTURE) {
-            const uint32_t *F = ftab, *Gt = ftab + NS;
+            const CT *F = ftab, *Gt = ftab + NS;
             u64 ff = 0, gg = 0, fg = 0, fg_sph = 0;
             u128 ffg = 0, ggf = 0;
-            if (a.wide) poly_recent_blocked<uint32_t, u64>(F, Gt, NR, a.terms, a.n_terms, lo, LPD, ff, gg, fg, fg_sph, ffg, ggf);
-            else poly_recent_blocked<uint32_t, uint32_t>(F, Gt, NR, a.terms, a.n_terms, lo, LPD, ff, gg, fg, fg_sph, ffg, ggf);
+            if (a.wide) poly_recent_blocked<CT, u64>(F, Gt, NR, a.terms, a.n_terms, lo, LPD, ff, gg, fg, fg_sph, ffg, ggf);
+            else poly_recent_blocked<CT, uint32_t>(F, Gt, NR, a.terms, a.n_terms, lo, LPD, ff, gg, fg, fg_sph, ffg, ggf);
             u64 v[12];
             v[0] = ff; v[1] = gg; v[2] = fg; v[3] = fg_sph;
             split_u128(ffg, v + 4);
@@ -250,7 +252,7 @@ __global__ void __launch_bounds__(32 * LanesWarps<NR>::MAX, 1) k_lanes(const __g
         } else {
             // e(S) = sum_g p_g * cnt_g(S) / N_g (DISTANT_ADMIXTURE_MODELS.py:136-139), tabulated once per draw
             double *etab = reinterpret_cast<double *>(wbase + lay.etab) + ((size_t)dgrp << NR);
-            distant_fill_etab<uint32_t>(ftab, a.pv, NR, etab, lo, LPD);
+            distant_fill_etab<CT>(ftab, a.pv, NR, etab, lo, LPD);
             __syncwarp();
             double two = 0, two_sph = 0, three = 0;
             poly_distant_etab(etab, NR, a.terms, a.n_terms, lo, LPD, two, two_sph, three);

@@ -7,17 +7,17 @@
 
 namespace ldpgta {
 
-template <int NR, int KL>
-static int launch_lanes_t(ldpgta_ctx *c, const GeneralArgs &a)
+template <int NR, int KL, typename CT>
+static int launch_lanes_ct(ldpgta_ctx *c, const GeneralArgs &a)
 {
     constexpr int DPW = 32 >> KL;
     static const int max_warps = [] { const char *e = getenv("LDPGTA_LANES_WARPS"); return e ? std::max(1, atoi(e)) : 12; }();
-    const LanesSmem lay = lanes_smem_layout<NR, KL>(a.pv, a.kind == LDPGTA_DISTANT_ADMIXTURE);
+    const LanesSmem lay = lanes_smem_layout<NR, KL, CT>(a.pv, a.kind == LDPGTA_DISTANT_ADMIXTURE);
     const int fit = (c->max_smem_optin - 1024) / lay.per_warp;
     if (fit < 2) return 1;                                   // rows too long for two warps per SM: the table kernel takes it
     const int nwarps = std::min(std::min(max_warps, LanesWarps<NR>::MAX), fit);
     const size_t smem = (size_t)nwarps * lay.per_warp;
-    auto kern = k_lanes<NR, KL>;
+    auto kern = k_lanes<NR, KL, CT>;
     LDPGTA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t tiles = (a.n_draws + DPW - 1) / DPW;
     const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((tiles + nwarps - 1) / nwarps, c->sm_count));
@@ -27,13 +27,23 @@ static int launch_lanes_t(ldpgta_ctx *c, const GeneralArgs &a)
     return 0;
 }
 
+// 16-bit count tables when every group fits (the usual case), else 32-bit
+template <int NR, int KL>
+static int launch_lanes_t(ldpgta_ctx *c, const GeneralArgs &a)
+{
+    static const bool force_u32 = getenv("LDPGTA_PLAN_U32") != nullptr;
+    bool small = !force_u32;
+    for (int g = 0; g < c->G; ++g) small = small && c->nhap[g] <= 65535u;
+    return small ? launch_lanes_ct<NR, KL, uint16_t>(c, a) : launch_lanes_ct<NR, KL, uint32_t>(c, a);
+}
+
 int launch_lanes(ldpgta_ctx *c, GeneralArgs a)
 {
     if (getenv("LDPGTA_NO_LANES")) return 1;
-    // measured against the table kernel (tools/sweep_sizes.sh with LDPGTA_LANES_MAXN): ahead up to 12 reads for one group,
-    // up to 11 for recent and 10 for distant admixture, whose polynomials are too long for one warp beyond that
-    static const int max_n_env = [] { const char *e = getenv("LDPGTA_LANES_MAXN"); return e ? atoi(e) : 12; }();
-    const int max_n = std::min(max_n_env, a.kind == LDPGTA_HOMOGENEOUS ? 12 : a.kind == LDPGTA_RECENT_ADMIXTURE ? 11 : 10);
+    // measured against the table kernel (tools/sweep_sizes.sh with LDPGTA_LANES_MAXN): ahead up to 12 reads for one group and
+    // for recent admixture, up to 10 for distant admixture, whose float64 polynomial is too long for one warp beyond that
+    static const int max_n_env = [] { const char *e = getenv("LDPGTA_LANES_MAXN"); return e ? atoi(e) : 0; }();      // tuning override
+    const int max_n = max_n_env ? std::min(max_n_env, 12) : a.kind == LDPGTA_DISTANT_ADMIXTURE ? 10 : 12;
     if (a.n < 5 || a.n > max_n) return 1;
     for (int g = 0; g < c->G; ++g)
         if (c->wp[g] * 64 > 65535) return 1;           // 16-bit packed partial counts, row bytes of one bulk copy
