@@ -255,3 +255,20 @@ def test_device_draws_bit_exact_and_uniform():
             eng.bootstrap_uniform(L.HOMOGENEOUS, 8, woff, wr, doff, 1)
         with pytest.raises(LdpgtaError, match='outside'):
             eng.bootstrap_uniform(L.HOMOGENEOUS, 3, woff, wr + 1000, doff, 1)
+
+
+def test_plan_counts_matches_effective_number_of_subsamples():
+    """ draws per window and reads per draw for all windows at once = effective_number_of_subsamples / pick_reads
+    (ANEUPLOIDY_TEST.py:226-248), incl. windows with fewer than max_reads + 1 reads and comb(R, max_reads) < subsamples """
+    from ldpgta_b200.packed import PackedSample, PackedWindows
+    rng = np.random.default_rng(0)
+    for min_reads, max_reads, subsamples in ((6, 4, 32), (3, 3, 5), (12, 8, 6), (4, 2, 1000), (18, 16, 32), (6, 4, 1), (2, 2, 40)):
+        R = np.concatenate([np.arange(0, 40), rng.integers(0, 400, size=200)])
+        offsets = np.concatenate([[0], np.cumsum(R)]).astype(np.int64)
+        win = PackedWindows(np.zeros((len(R), 2), np.int64), offsets, np.zeros(int(offsets[-1]), np.int64))
+        evaluated, draw_offsets, effN, k_of = PackedSample.plan_counts(win, min_reads, max_reads, subsamples)
+        want = [O.effective_number_of_subsamples(int(r), min_reads, max_reads, subsamples) for r in R]
+        assert effN.tolist() == want
+        assert evaluated.tolist() == [i for i, e in enumerate(want) if e]
+        assert np.diff(draw_offsets).tolist() == [e for e in want if e]
+        assert all(int(k_of[i]) == min(int(R[i]) - 1, max_reads) for i in evaluated.tolist())
