@@ -1,4 +1,4 @@
-// k_mid.cuh -- draws of 5 or 6 reads, single-population model: the k_small pipeline with the general
+// k_mid.cuh -- draws of 5 (or 6) reads, single-population model: the k_small pipeline with the general
 // partition polynomial evaluated from registers.
 //
 // 16 lanes own a draw (a warp: 2 draws); each lane keeps W64 64-bit words of every read mask in registers
@@ -7,8 +7,10 @@
 // 16-bit packed partial counts are added across the 16 lanes with xor-shuffles.  Masks arrive through the same
 // single-buffer bulk-copy (TMA 1-D) pipeline as in k_small.  The polynomial is the integer form of
 // likelihoods() (HOMOGENOUES_MODELS.py:185-225): exact 64-bit sums over the 15 / 31 two-block and 25 / 90
-// three-block partitions, enumerated at compile time, then the reference's few float operations.
+// three-block partitions, enumerated at compile time, then the reference's few float operations; it runs once per
+// 32 draws with one draw per lane (the counts of 16 tiles wait in a per-warp shared-memory table).
 // The table kernel (k_general) needs ~6400 warp instructions per 6-read draw; this one ~1300.
+// Serves 5 reads of one-group models; from 6 reads on k_lanes is faster (measured).
 #pragma once
 #include "common.cuh"
 #include "k_small.cuh"

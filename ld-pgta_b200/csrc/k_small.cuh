@@ -16,7 +16,10 @@
 //             partial counts are summed across the group's lanes with xor-shuffles.  Single-read
 //             frequencies are row popcounts, precomputed once per read and prefetched with the
 //             indices.  The closed-form polynomials (poly_closed.cuh) follow in float64; counts are
-//             normalised through an exact x/N lookup table instead of 15 divisions.
+//             normalised through an exact x/N lookup table instead of 15 divisions.  For one-group
+//             models and recent admixture the counts of 32 draws wait in a small per-warp table and
+//             the lookups + polynomial run once per 32 draws, one draw per lane (a tile's polynomial
+//             would otherwise be executed by all 8 lanes of each of its 4 draws).
 //
 // Algorithmic work per draw: G*(2^NR-1)*W word AND+POPC, G*NR*W*8 mask bytes in, 32 B out.
 //
