@@ -9,7 +9,9 @@ import this file; nothing under ld-pgta_b200/ does.
 Parity status: PINNED.  tests/golden/make_golden.py executes the unmodified
 reference from /root/reference and commits its inputs and outputs under
 tests/golden/; tests/test_oracle_golden.py checks every function below against
-those vectors (popcounts bit-exact, likelihoods <= 4 ulp, statistics <= 1e-13).
+those vectors (popcounts bit-exact, likelihoods <= 4 ulp, statistics <= 1e-13); the
+LLR consumers (binning, crossover detection) are pinned by
+tests/golden/make_golden_consumers.py + tests/test_consumers.py.
 
 Every function cites the reference file:line (paths into /root/reference) whose
 behaviour it restates.  Panel rows are arbitrary-precision ints exactly as in
