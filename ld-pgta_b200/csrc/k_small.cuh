@@ -142,7 +142,7 @@ __device__ __forceinline__ void small_group_sum(uint32_t *c, bool packed)
 template <int NR, int KIND>
 struct SmallModel {
     static constexpr int NS = 1 << NR;
-    uint32_t c0[KIND == LDPGTA_RECENT_ADMIXTURE ? NS : 1];
+    uint32_t c0[KIND != LDPGTA_HOMOGENEOUS ? NS : 1];        // group 0's counts (two-group models finished in batches)
     double f[KIND == LDPGTA_DISTANT_ADMIXTURE ? NS : 1];
 
     __device__ __forceinline__ void init()
@@ -150,7 +150,7 @@ struct SmallModel {
         if (KIND == LDPGTA_DISTANT_ADMIXTURE)
 #pragma unroll
             for (int s = 0; s < NS; ++s) f[s] = 0.0;
-        if (KIND == LDPGTA_RECENT_ADMIXTURE) c0[0] = 0;
+        if (KIND != LDPGTA_HOMOGENEOUS) c0[0] = 0;
     }
     // two-group closed forms from the counts of both groups
     static __device__ __forceinline__ void finish_recent(const PanelView &pv, const uint32_t *ca, const uint32_t *cb, double *res)
@@ -160,6 +160,21 @@ struct SmallModel {
 #pragma unroll
         for (int s = 1; s < NS; ++s) { fr[s] = __ldg(norm0 + ca[s]); gr[s] = __ldg(norm1 + cb[s]); }
         closed_recent<NR>(fr, gr, res);
+    }
+    // distant admixture with two groups: e(S) = p_0 cnt_0 / N_0 + p_1 cnt_1 / N_1 in group order (the operations of fold())
+    static __device__ __forceinline__ void finish_distant2(const PanelView &pv, const uint32_t *ca, const uint32_t *cb, double *res)
+    {
+        const double nh0 = (double)pv.nhap[0], p0 = pv.coef[0], nh1 = (double)pv.nhap[1], p1 = pv.coef[1];
+        double e[NS];
+        e[0] = 0.0;
+#pragma unroll
+        for (int s = 1; s < NS; ++s) {
+            double v = 0.0;
+            v = v + p0 * (double)ca[s] / nh0;
+            v = v + p1 * (double)cb[s] / nh1;
+            e[s] = v;
+        }
+        closed_single<NR>(e, res);
     }
     // returns true when res[] is final
     __device__ __forceinline__ bool fold(const PanelView &pv, int g, const uint32_t *c, double *res)
@@ -237,8 +252,9 @@ __global__ void __launch_bounds__(SmallPipe<NR, WPL>::NWARPS * 32, 1) k_small(co
     uint4 *batch = reinterpret_cast<uint4 *>(smem + (size_t)P::NWARPS * P::STAGE_BYTES + (size_t)warp * P::BATCH_BYTES);
     constexpr bool BATCHED = KIND == LDPGTA_HOMOGENEOUS;
     constexpr int TPB = LPD;                                                  // tiles per batch: TPB * DPW = 32 draws
-    // recent admixture: the same with both groups' counts packed as 16-bit halves (groups of at most 65535 haplotypes)
-    const bool batched2 = KIND == LDPGTA_RECENT_ADMIXTURE && a.pv.nhap[0] <= 65535u && a.pv.nhap[1] <= 65535u;
+    // two-group models (recent admixture, distant admixture of two groups): the same with both groups' counts packed as
+    // 16-bit halves (groups of at most 65535 haplotypes)
+    const bool batched2 = KIND != LDPGTA_HOMOGENEOUS && a.pv.G == 2 && a.pv.nhap[0] <= 65535u && a.pv.nhap[1] <= 65535u;
 
     if (lane == 0) mbar_init(bar, 1);
     fence_proxy_async();
@@ -370,10 +386,12 @@ __global__ void __launch_bounds__(SmallPipe<NR, WPL>::NWARPS * 32, 1) k_small(co
                 }
                 __syncwarp();
             }
-        } else if (KIND == LDPGTA_RECENT_ADMIXTURE && batched2) {
+        } else if (KIND != LDPGTA_HOMOGENEOUS && batched2) {
             double res[4];
-            if (g == 0) model.fold(a.pv, g, c, res);                           // keeps group 0's counts
-            else {
+            if (g == 0) {                                                      // keep group 0's counts
+#pragma unroll
+                for (int s = 1; s < NS; ++s) model.c0[s] = c[s];
+            } else {
                 const int k = (int)((q >> 1) % TPB);
                 if (lane_in == 0) {
                     const int slot = k * DPW + dgrp;
@@ -395,7 +413,8 @@ __global__ void __launch_bounds__(SmallPipe<NR, WPL>::NWARPS * 32, 1) k_small(co
                     const int kk = lane / DPW;
                     const int64_t draw_k = (tile0 + ((q >> 1) - k + kk) * tstride) * DPW + lane % DPW;
                     if (kk <= k) {
-                        SmallModel<NR, KIND>::finish_recent(a.pv, ca, cb, res);
+                        if (KIND == LDPGTA_RECENT_ADMIXTURE) SmallModel<NR, KIND>::finish_recent(a.pv, ca, cb, res);
+                        else SmallModel<NR, KIND>::finish_distant2(a.pv, ca, cb, res);
                         if (draw_k < a.n_draws) small_store(a, draw_k, res);
                     }
                     __syncwarp();
