@@ -6,7 +6,7 @@
  * entry points below are the operations its hot path performs, cut where the
  * reference's model classes and driver call into big-int arithmetic.  Each one
  * cites the reference code it replaces (paths into the reference repository).
- * The Python classes in ld-pgta_b200/ (homogeneous, recent_admixture,
+ * The Python classes in ldpgta_b200/ (homogeneous, recent_admixture,
  * distant_admixture, bootstrap, aneuploidy_test) bind these with ctypes; the
  * stub a reference maintainer would add is shown in INTEGRATION.md.
  *

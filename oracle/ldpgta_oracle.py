@@ -4,7 +4,7 @@ oracle/ldpgta_oracle.py  --  TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 A plain CPython restatement of LD-PGTA's windowed haplotype-likelihood path
 (the reference is pure Python, so the oracle is too).  Only tests/,
 __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
-import this file; nothing under ld-pgta_b200/ does.
+import this file; nothing under ldpgta_b200/ does.
 
 Parity status: PINNED.  tests/golden/make_golden.py executes the unmodified
 reference from /root/reference and commits its inputs and outputs under

@@ -486,7 +486,7 @@ sys.path.insert(0, %r)                       # flat drop-in: the directory with 
 from ANEUPLOIDY_TEST import aneuploidy_test
 lik, info = aneuploidy_test(%r, %r, %r, {'G0'}, %d, %d, %d, %d, %d, %d, %r, '', 'gz', seed=2021, output_dir=%r)
 print(json.dumps({'windows': len(lik), 'keys': sorted(info), 'stat_keys': sorted(info['statistics'])}))
-''' % (str(ROOT) + '/ld-pgta_b200', str(d / 'sample.chr21.obs.p'), str(d / 'panel.legend.gz'), str(d / 'panel.hap.bz2'),
+''' % (str(ROOT) + '/ldpgta_b200', str(d / 'sample.chr21.obs.p'), str(d / 'panel.legend.gz'), str(d / 'panel.hap.bz2'),
        cfg['window_size'], cfg['subsamples'], cfg['offset'], cfg['min_reads'], cfg['max_reads'], cfg['min_score'],
        cfg['min_HF'], str(d / 'results'))
     res = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300, cwd=str(d),
@@ -505,7 +505,7 @@ print(json.dumps({'windows': len(lik), 'keys': sorted(info), 'stat_keys': sorted
     assert path.exists()
     raw = gzip.open(path, 'rb').read()
     assert b'HOMOGENOUES_MODELS' in raw and b'ldpgta' not in raw          # records carry the reference's module name
-    sys.path.insert(0, str(ROOT) + '/ld-pgta_b200')
+    sys.path.insert(0, str(ROOT) + '/ldpgta_b200')
     with gzip.open(path, 'rb') as f:
         lik = pickle.load(f); info = pickle.load(f)
     assert list(lik) == list(out['likelihoods'])
@@ -564,13 +564,13 @@ def test_command_line_interface(tmp_path, golden_inputs):
     with open(d / 'panel.hap.p', 'wb') as f:
         # the reference's CLI only accepts alphabetic group names (ANEUPLOIDY_TEST.py:480-488): G0 -> EUR
         pickle.dump({'EUR': args['hap_tab']['G0']}, f); pickle.dump({'EUR': args['number_of_haplotypes']['G0']}, f)
-    script = os.path.join(str(ROOT), 'ld-pgta_b200', 'ANEUPLOIDY_TEST.py')
+    script = os.path.join(str(ROOT), 'ldpgta_b200', 'ANEUPLOIDY_TEST.py')
     res = subprocess.run([sys.executable, script, str(d / 'cli.chr21.obs.p'), str(d / 'panel.legend.p'), str(d / 'panel.hap.p'),
                           'EUR', '-s', '8', '-m', '6', '-M', '4', '-C', 'gz'], capture_output=True, text=True, timeout=300, cwd=str(d))
     assert res.returncode == 0, res.stderr[-2000:]
     assert 'Chromosome-wide LLR between BPH and SPH' in res.stdout
     with gzip.open(d / 'results' / 'cli.chr21.LLR.p.gz', 'rb') as f:
-        sys.path.insert(0, os.path.join(str(ROOT), 'ld-pgta_b200'))
+        sys.path.insert(0, os.path.join(str(ROOT), 'ldpgta_b200'))
         lik = pickle.load(f); info = pickle.load(f)
     assert list(lik) == list(out['likelihoods']) and info['subsamples'] == 8 and info['ancestral_makeup'] == {'EUR'}
     bad = subprocess.run([sys.executable, script, 'a', 'b', 'c', 'G0'], capture_output=True, text=True, timeout=300)

@@ -52,7 +52,7 @@ def test_no_gpu_means_loud_failure():
 
 def test_product_does_not_import_the_oracle():
     """ oracle/ is test infrastructure: nothing under the package may import, load or execute it. """
-    pkg = os.path.join(ROOT, 'ld-pgta_b200')
+    pkg = os.path.join(ROOT, 'ldpgta_b200')
     for dirpath, _, files in os.walk(pkg):
         for f in files:
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
@@ -118,7 +118,7 @@ for f in ('bootstrap', 'aneuploidy_test', 'statistics', 'LLR', 'mean_and_var', '
           'effective_number_of_subsamples', 'build_gw_dict', 'supporting_dictionaries', 'save_results', 'print_summary'):
     assert hasattr(ANEUPLOIDY_TEST, f), f
 print('ok')
-''' % os.path.join(ROOT, 'ld-pgta_b200')
+''' % os.path.join(ROOT, 'ldpgta_b200')
     out = subprocess.check_output([sys.executable, '-c', code], cwd='/tmp').decode()
     assert out.strip().endswith('ok')
 

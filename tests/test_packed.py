@@ -1,5 +1,5 @@
 """
-The array-native route (ld-pgta_b200/packed.py) against the golden vectors made by running the
+The array-native route (ldpgta_b200/packed.py) against the golden vectors made by running the
 reference: matching of observations to the legend, reads as CSR, windows (fixed, offset, adaptive) on the CPU;
 read scores, replayed draws and the whole run on the GPU.
 """

@@ -49,7 +49,7 @@ st = timed('statistics (device)', driver.statistics, lik, gw)
 examine.close()
 n_eval = sum(len(v) for v in lik.values())
 
-# the array-native route (ld-pgta_b200/packed.py): the panel is uploaded once per chromosome and shared by samples
+# the array-native route (ldpgta_b200/packed.py): the panel is uploaded once per chromosome and shared by samples
 import numpy as np
 from ldpgta_b200.packed import PackedSample
 packed = {}
