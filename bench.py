@@ -2,28 +2,38 @@
 """
 bench.py -- bootstrapped window-likelihoods per second (BASELINE.json metric).
 
-Workload (BASELINE.json configs[1]): one synthetic embryo, 22 autosomes at 0.1x, 100 kbp
-windows (about 28.7k), ~150 informative reads per window, 5008-haplotype LD-structured panel,
-32 bootstrap draws of 4 reads per window (the CLI defaults -w 100000 -s 32 -m 6 -M 4), all four
-hypotheses (monosomy, disomy, SPH, BPH) per draw.  A "step" evaluates every (window, draw) of
-the embryo once.  With N GPUs every rank owns one such embryo (weak scaling, no data-path
-collective: (embryo, chromosome, window, draw) units are independent).
+Workload (BASELINE.json configs[1]): one synthetic embryo, 22 autosomes at 0.1x, 100 kbp windows (about 28.7k),
+~150 informative reads per window, 5008-haplotype LD-structured panel, 32 bootstrap draws of 4 reads per window (the
+CLI defaults -w 100000 -s 32 -m 6 -M 4), all four hypotheses (monosomy, disomy, SPH, BPH) per draw, LLR statistics per
+window and per chromosome.  A "step" is one pass of the hot path over the embryo: pick_reads for every (window, draw),
+the likelihoods of every draw, LLRs, window mean / variance and the 22 chromosome summaries
+(ANEUPLOIDY_TEST.py:226-325).  With N GPUs every rank owns one such embryo (weak scaling, no data-path collective:
+(embryo, chromosome, window, draw) units are independent).
 
-  value      draws/s with read masks, draw indices and outputs resident in HBM (CUDA events on the
-             engine's stream, max over ranks)
-  e2e        the same step through the public host API (Engine.likelihoods_uniform -> C-ABI
-             ldpgta_likelihoods_uniform) from pinned host buffers: index upload + validation + kernel +
-             result download inside the timed region; e2e.offsets_api_ms_per_step is the same step
-             through ldpgta_likelihoods_batch (ragged API: also reads one offset per draw)
-  roofline   dominant kernel k_small<4,8,10>: algorithmic bytes / measured launch time vs the
-             measured HBM copy peak; int_roofline: algorithmic AND+POPC word-ops vs the POPC peak
-  cpu_baseline  the CPython oracle port of the reference loop (ANEUPLOIDY_TEST.py:277-286) on a
-             bounded sample of the same windows, one host core (the reference is single-threaded)
+  value      draws/s of the device-resident pipeline (ldpgta_bootstrap_stats_dev: sampler + draw kernel + reductions;
+             read masks, windows and every intermediate in HBM), CUDA events on the engine's stream, max over ranks;
+             `sustained` repeats it for >= 0.3 s and reports the median step
+  e2e        the same step through the public host API with HOST buffers, copies inside the timed region:
+               stats   Engine.bootstrap_stats -> ldpgta_bootstrap_stats: the seed goes up, the statistics come down
+                       (80 B per window + the chromosome summaries) -- this is e2e.value
+               full    the same plus the per-draw likelihoods (32 B per draw) streamed down under the kernels
+               replay  Engine.replay_stats -> ldpgta_replay_stats: draws chosen on the host (the reference's
+                       random.sample stream) go up (16 B per draw), statistics come down
+  roofline   dominant kernel k_small<4,8,10>: algorithmic bytes / launch time (CUDA events around the kernel inside the
+             timed steps) vs the measured HBM copy peak; int_roofline: algorithmic AND+POPC word-ops vs the POPC peak
+  secondary  short legs for the other BASELINE configs: configs[2] (16 reads per draw), configs[3] (recent admixture,
+             two populations) and 1000 subsamples per window, each with ms per step, draws/s and roofline fraction
+  strong / batch96 (N > 1 and, batch96, N = 1 too): ONE embryo's windows dealt to the ranks with the chromosome
+             partial sums all-reduced inside the timed step; configs[4]: 96 embryos x 1000 subsamples dealt to the ranks
+  cpu_baseline  the reference's own model class (oracle/_ref, unmodified) on one host core on a bounded sample of the
+             same windows and draws -- also the in-run parity check; the oracle port's rate beside it
 
---impl reference times the oracle port on all host cores (one process per core) on bounded
-samples of the same workload.
+--impl reference times the reference's CPU loop (ANEUPLOIDY_TEST.py:277-286 on oracle/_ref's classes; the oracle port
+when oracle/_ref is absent) on all host cores (one process per core) on bounded samples of the same workload.
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -75,7 +85,7 @@ def synth_masks(torch, device, reads_per_window, n_hap, seed, window_slice=None)
     masks = torch.zeros((total, wp), dtype=torch.int64, device=device)
     assign = torch.randint(0, FOUNDERS, (n_hap,), generator=g, device=device)
     shifts = torch.arange(64, device=device, dtype=torch.int64)
-    chunk = 32
+    chunk = max(1, min(32, int(20000 // max(1, rpw.max()))))
     for w0 in range(0, len(rpw), chunk):
         w1 = min(w0 + chunk, len(rpw))
         nr = int(starts[w1] - starts[w0])
@@ -102,8 +112,8 @@ def synth_masks(torch, device, reads_per_window, n_hap, seed, window_slice=None)
 
 
 def plan_draws(reads_per_window, subsamples, max_reads, seed):
-    """ For every window: effN = min(C(R, max_reads), subsamples) draws (ANEUPLOIDY_TEST.py:235-248) of
-    n = min(R-1, max_reads) distinct reads (:231), as global read indices.  Uniform n only. """
+    """ Host-side draws (the replay leg and the reference arm): for every window effN = min(C(R, max_reads), subsamples)
+    draws (ANEUPLOIDY_TEST.py:235-248) of n = min(R-1, max_reads) distinct reads (:231), as global read indices. """
     rng = np.random.default_rng(seed)
     R = np.asarray(reads_per_window)
     assert R.min() > max_reads, 'uniform draw size needs R > max_reads in every window'
@@ -169,20 +179,38 @@ class ClockSampler:
                 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
-def oracle_models(masks_rows, first_read, n_hap):
-    """ The oracle's model object for one window (built once, outside the timed loop, like
-    homogeneous.__init__ in the reference).  Reads are single-allele haplotypes (read_index, 'A'). """
+# ---- the CPU arm: the reference's own classes (oracle/_ref) or the oracle port --------------------------------------
+def cpu_model_class(prefer_reference=True):
+    """ (class with the signature of HOMOGENOUES_MODELS.homogeneous, kind, popcount description) """
+    if prefer_reference:
+        try:
+            import make_ref
+            if make_ref.available():
+                sys.path.insert(0, make_ref.DEST)
+                with contextlib.redirect_stdout(io.StringIO()):
+                    import HOMOGENOUES_MODELS as ref
+                pc = 'gmpy2.popcount' if type(ref.popcount).__name__ != 'popcount_lk' else 'popcount_lk (byte LUT; gmpy2 is not installed)'
+                return ref.homogeneous, 'reference', pc
+        except Exception as e:                                  # noqa: the port below is the documented fallback
+            sys.stderr.write('bench: oracle/_ref unusable (%s), timing the oracle port\n' % e)
     import ldpgta_oracle as O
+    return O.Homogeneous, 'port', 'int.bit_count (reference: gmpy2.popcount or byte LUT)'
+
+
+def cpu_window_model(cls, masks_rows, first_read, n_hap):
+    """ The model object for one window (built once, outside the timed loop, like homogeneous.__init__ in the
+    reference's bootstrap()).  Reads are single-allele haplotypes (read_index, 'A'). """
     words = (n_hap + 63) // 64
     ints = [int.from_bytes(r[:words].tobytes(), 'little') for r in masks_rows]
     leg = [('chrS', first_read + i, 'C', 'A') for i in range(len(ints))]
     obs = [(first_read + i, 'read%d' % (first_read + i), 'A') for i in range(len(ints))]
-    model = O.Homogeneous(obs, leg, {'ALL': ints}, {'ALL': n_hap}, {})
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = cls(obs, leg, {'ALL': ints}, {'ALL': n_hap}, {})
     reads = {first_read + i: [(first_read + i, 'A')] for i in range(len(ints))}
     return model, reads
 
 
-def oracle_loop(model, reads, draws):
+def cpu_loop(model, reads, draws):
     """ The timed unit: the bootstrap inner loop (ANEUPLOIDY_TEST.py:282-286 minus the progress bar). """
     t0 = time.perf_counter()
     out = [tuple(model.get_likelihoods(tuple(reads[int(r)] for r in d))) for d in draws]
@@ -193,7 +221,8 @@ _W = {}
 
 
 def _worker_init(masks, starts, idx, win, n_hap):
-    _W.update(masks=masks, starts=starts, idx=idx, win=win, n_hap=n_hap, models={})
+    cls, _, _ = cpu_model_class()
+    _W.update(masks=masks, starts=starts, idx=idx, win=win, n_hap=n_hap, models={}, cls=cls)
 
 
 def _worker_step(windows):
@@ -201,24 +230,25 @@ def _worker_step(windows):
     for w in windows:
         if w not in _W['models']:
             r0, r1 = int(_W['starts'][w]), int(_W['starts'][w + 1])
-            _W['models'][w] = oracle_models(_W['masks'][r0:r1], r0, _W['n_hap']) + (_W['idx'][_W['win'] == w],)
+            _W['models'][w] = cpu_window_model(_W['cls'], _W['masks'][r0:r1], r0, _W['n_hap']) + (_W['idx'][_W['win'] == w],)
         model, reads, draws = _W['models'][w]
-        oracle_loop(model, reads, draws)
+        cpu_loop(model, reads, draws)
         n += len(draws)
     return n
 
 
 def run_reference(args):
-    """ --impl reference: the oracle port of the reference's CPU loop on all host cores (one process per
-    core, windows dealt round-robin; model objects are built once per window outside the timed steps). """
+    """ --impl reference: the reference's CPU loop on all host cores (one process per core, windows dealt
+    round-robin; model objects are built once per window outside the timed steps). """
     import multiprocessing as mp
     import torch
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
+    _, kind, pc = cpu_model_class()
     wins, reads = workload_shape(args.depth, args.seed, min_reads=args.max_reads + 2, max_windows=args.windows)
-    per_step_windows = min(max(cores * 8, 64), len(reads))   # bounded sample, the same windows every step
+    per_step_windows = min(max(cores * 32, 256), len(reads))  # bounded sample, the same windows every step
     need = per_step_windows
     masks = synth_masks(torch, 'cpu', reads, N_HAP, args.seed, window_slice=slice(0, need)).numpy().view(np.uint64)
     idx, win = plan_draws(reads[:need], args.subsamples, args.max_reads, args.seed + 1)
@@ -245,8 +275,8 @@ def run_reference(args):
             'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t_total / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u64 popcount + f64', 'data': 'synthetic',
             'config': workload_config(args, len(reads), int(reads.sum())),
-            'cpu_baseline': {'value': value, 'unit': 'window-likelihoods/s', 'cores': cores, 'kind': 'port', 'sample': sample,
-                             'python': sys.version.split()[0], 'popcount': 'int.bit_count (reference: gmpy2.popcount or byte LUT)'},
+            'cpu_baseline': {'value': value, 'unit': 'window-likelihoods/s', 'cores': cores, 'kind': kind, 'sample': sample,
+                             'python': sys.version.split()[0], 'popcount': pc},
             'e2e': {'value': value, 'unit': 'window-likelihoods/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     emit(line)
     return 0
@@ -291,6 +321,110 @@ def emit(line):
     _JSON_OUT.flush()
 
 
+def load_peaks():
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs, burst copy)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s (B200_PROFILING.md)'
+    int_peak, int_src = 2.3e12, 'assumed 148 SM x 16 POPC.32/clk x 1.965 GHz / 2'
+    try:
+        ip = json.load(open(os.path.join(ROOT, 'profiles', 'INT_PEAKS.json')))
+        int_peak = float(ip['wordop64_and_popc_add']['ops_per_s'])
+        int_src = 'measured (profiles/INT_PEAKS.json, tools/int_peaks.cu: AND+POPC+ADD on 64-bit words)'
+    except Exception:
+        pass
+    return hbm_peak, peak_src, int_peak, int_src
+
+
+def chromosome_segments(wins, n_windows):
+    """ window offsets of the 22 chromosomes, clipped to the first n_windows windows """
+    seg = np.minimum(np.concatenate([[0], np.cumsum(wins)]), n_windows).astype(np.int64)
+    return seg[:int(np.searchsorted(seg, n_windows, side='left')) + 1]
+
+
+class Leg:
+    """ One resident workload: masks + plan on an Engine, timed through ldpgta_bootstrap_stats_dev. """
+
+    def __init__(self, L, torch, device, local, group_sizes, kind, reads, n, subsamples, seed, proportions=None, segments=None,
+                 seg_cols=None, seg_first=None):
+        self.L, self.torch, self.kind, self.n, self.proportions = L, torch, kind, n, proportions
+        self.reads, self.n_windows, self.n_reads = reads, len(reads), int(reads.sum())
+        self.eng = L.Engine(group_sizes, device=local)
+        self.masks = []
+        for g, nh in enumerate(group_sizes):
+            m = synth_masks(torch, device, reads, nh, seed + 77 * g)
+            assert m.shape[1] == self.eng.padded_words[g]
+            self.eng.attach_read_masks_dev(g, m.data_ptr(), self.n_reads, keepalive=m)
+            self.masks.append(m)
+        self.woff = np.concatenate([[0], np.cumsum(reads)]).astype(np.int64)
+        self.doff = np.arange(0, (self.n_windows + 1) * subsamples, subsamples, dtype=np.int64)
+        self.n_draws = int(self.doff[-1])
+        self.info = self.eng.set_windows(self.woff, None, self.doff, n, segment_offsets=segments, segment_cols=seg_cols, segment_first=seg_first)
+        self.stream = torch.cuda.ExternalStream(self.eng.stream, device=device)
+        self.words = sum((nh + 63) // 64 for nh in group_sizes)
+        self.seed = 0
+
+    def step(self, partials_ptr=None):
+        self.seed += 1
+        self.eng.bootstrap_stats_dev(self.kind, self.seed, proportions=self.proportions, partials_dev_ptr=partials_ptr)
+
+    def timed(self, steps, warmup, min_seconds=0.0):
+        """ per-step milliseconds (CUDA events on the engine's stream) and per-step draw-kernel milliseconds """
+        torch = self.torch
+        for _ in range(warmup):
+            self.step()
+        self.eng.synchronize()
+        if min_seconds:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(self.stream); self.step(); ev1.record(self.stream)
+            self.eng.synchronize()
+            steps = max(steps, min(20000, int(min_seconds * 1e3 / max(ev0.elapsed_time(ev1), 1e-3)) + 1))
+        self.eng.kernel_timing(True)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        ev[0].record(self.stream)
+        for k in range(steps):
+            self.step()
+            ev[k + 1].record(self.stream)
+        self.eng.synchronize()
+        kms = self.eng.kernel_times()
+        self.eng.kernel_timing(False)
+        return np.array([ev[k].elapsed_time(ev[k + 1]) for k in range(steps)]), kms, ev[0].elapsed_time(ev[-1])
+
+    def close(self):
+        self.eng.close()
+        self.masks = []
+
+
+def secondary_legs(L, torch, device, local, args, hbm_peak, int_peak):
+    """ short legs for the other BASELINE configs on rank 0 (resident pipeline, device draws, statistics included) """
+    out = []
+
+    def run(name, group_sizes, kind, depth, n, subsamples, windows, steps, proportions=None, model='homogeneous'):
+        wins, reads = workload_shape(depth, args.seed + 5, min_reads=n + 2, max_windows=windows)
+        leg = Leg(L, torch, device, local, group_sizes, kind, reads, n, subsamples, args.seed + 9, proportions,
+                  segments=chromosome_segments(wins, len(reads)))
+        ms, kms, _ = leg.timed(steps, 3, min_seconds=0.2)
+        med, kmed = float(np.median(ms)), float(np.median(kms))
+        wordops = ((1 << n) - 1) * leg.words
+        bytes_per_draw = n * leg.words * 8 + n * 4 + 32
+        out.append({'workload': name, 'kernel': kernel_name(n, model), 'windows': leg.n_windows, 'reads': leg.n_reads, 'draws_per_step': leg.n_draws,
+                    'reads_per_draw': n, 'subsamples': subsamples, 'steps': len(ms), 'ms_per_step': med, 'draw_kernel_ms': kmed,
+                    'value': leg.n_draws / (med * 1e-3), 'unit': 'window-likelihoods/s',
+                    'hbm_frac': bytes_per_draw * leg.n_draws / (kmed * 1e-3) / 1e9 / hbm_peak,
+                    'int_frac': wordops * leg.n_draws / (kmed * 1e-3) / int_peak})
+        leg.close()
+        torch.cuda.empty_cache()
+
+    run('configs[2]: 1x coverage, 16 reads per draw (2^16 subsets), homogeneous, 1024 windows x 8 draws', [N_HAP], L.HOMOGENEOUS, 1.0, 16, 8, 1024, 5)
+    run('configs[3]: recent admixture, two populations of 2504 haplotypes, 22 autosomes at 0.1x, 4 reads per draw, 32 draws per window',
+        [N_HAP // 2, N_HAP // 2], L.RECENT_ADMIXTURE, 0.1, 4, 32, 0, 20, model='recent')
+    run('configs[4] shape: 1000 subsamples per window, 4 reads per draw, homogeneous, 2048 windows at 0.1x', [N_HAP], L.HOMOGENEOUS, 0.1, 4, 1000, 2048, 5)
+    return out
+
+
 def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
@@ -306,6 +440,8 @@ def main():
     ap.add_argument('--windows', type=int, default=0, help='limit the number of windows (exploration runs; 0 = whole genome)')
     ap.add_argument('--cpu-seconds', type=float, default=12.0, help='budget of the single-core CPU baseline leg')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-secondary', action='store_true', help='skip the secondary legs (configs[2], configs[3], 1000 subsamples)')
+    ap.add_argument('--no-batch96', action='store_true', help='skip the configs[4] leg')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
@@ -327,11 +463,24 @@ def main():
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=device)
 
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    hbm_peak, peak_src, int_peak, int_src = load_peaks()
+
     # ---- workload: one embryo per rank ------------------------------------------------------
     wins, reads = workload_shape(args.depth, args.seed + 1000 * rank, min_reads=args.max_reads + 2, max_windows=args.windows)
-    n_windows, n_reads = len(reads), int(reads.sum())
-    idx_host, win_of_draw = plan_draws(reads, args.subsamples, args.max_reads, args.seed + 1 + 1000 * rank)
-    n_draws, n = idx_host.shape
+    n = args.max_reads
     proportions = None
     if args.model == 'recent':                       # exploration: configs[3], two populations of 2504 haplotypes
         group_sizes, kind = [N_HAP // 2, N_HAP // 2], L.RECENT_ADMIXTURE
@@ -339,134 +488,108 @@ def main():
         group_sizes, kind, proportions = [N_HAP // 2, N_HAP // 2], L.DISTANT_ADMIXTURE, [0.6, 0.4]
     else:
         group_sizes, kind = [N_HAP], L.HOMOGENEOUS
-    eng = L.Engine(group_sizes, device=local)
-    all_masks = []
-    for g, nh in enumerate(group_sizes):
-        m = synth_masks(torch, device, reads, nh, args.seed + 1000 * rank + 77 * g)
-        assert m.shape[1] == eng.padded_words[g]
-        eng.attach_read_masks_dev(g, m.data_ptr(), n_reads, keepalive=m)
-        all_masks.append(m)
-    masks = all_masks[0]
+    segments = chromosome_segments(wins, len(reads))
+    leg = Leg(L, torch, device, local, group_sizes, kind, reads, n, args.subsamples, args.seed + 1000 * rank, proportions, segments=segments)
+    eng, n_windows, n_reads, n_draws, n_seg = leg.eng, leg.n_windows, leg.n_reads, leg.n_draws, len(segments) - 1
 
-    d_idx = torch.from_numpy(idx_host).to(device)
-    d_out = torch.empty((n_draws, 4), dtype=torch.float64, device=device)
-    stream = torch.cuda.ExternalStream(eng.stream, device=device)
-
-    def step_resident():
-        eng.likelihoods_uniform_dev(kind, n, d_idx.data_ptr(), n_draws, d_out.data_ptr(), proportions=proportions)
-
-    # pinned host buffers for the end-to-end leg
-    pin_idx = L.PinnedArray((n_draws, n), np.int32)
-    pin_idx.array[:] = idx_host
-    pin_out = L.PinnedArray((n_draws, 4), np.float64)
-    offsets = np.arange(0, n_draws * n + 1, n, dtype=np.int64)
-
-    def step_e2e():
-        eng.likelihoods_uniform(kind, pin_idx.array, proportions=proportions, out=pin_out.array)
-
-    def step_e2e_offsets():
-        eng.likelihoods_batch(kind, pin_idx.array.reshape(-1), offsets, proportions=proportions, out=pin_out.array)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- value: resident timing -------------------------------------------------------------
+    # ---- value: the resident pipeline, K steps ------------------------------------------------
     sampler = ClockSampler(local)
     sampler.start()
     t_spin = time.perf_counter()
     while time.perf_counter() - t_spin < 0.5:               # untimed: let the SM clock leave idle before warm-up
-        step_resident()
+        leg.step()
         eng.synchronize()
     for _ in range(args.warmup):
-        step_resident()
+        leg.step()
     eng.synchronize()
     barrier()
     launches0 = eng.launch_count
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    with torch.cuda.stream(stream):
-        ev[0].record(stream)
-        for k in range(args.steps):
-            step_resident()
-            ev[k + 1].record(stream)
-    eng.synchronize()
+    step_ms, kernel_ms, total_ms = leg.timed(args.steps, 0)
     barrier()
     launches = eng.launch_count - launches0
-    total_ms = ev[0].elapsed_time(ev[-1])
-    kernel_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
-    if dist is not None:
-        t = torch.tensor([total_ms], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+    total_ms = max_over_ranks(total_ms)
     value = world * n_draws * args.steps / (total_ms * 1e-3)
+    # the same loop for at least 0.3 s: median step and median draw-kernel time (8 ms regions wobble by +-5 %)
+    sus_ms, sus_kms, _ = leg.timed(args.steps, 0, min_seconds=0.3)
+    sustained = {'steps': int(len(sus_ms)), 'median_ms_per_step': float(np.median(sus_ms)), 'mean_ms_per_step': float(np.mean(sus_ms)),
+                 'p10_ms': float(np.percentile(sus_ms, 10)), 'p90_ms': float(np.percentile(sus_ms, 90)),
+                 'median_draw_kernel_ms': float(np.median(sus_kms)),
+                 'value_at_median': world * n_draws / (max_over_ranks(float(np.median(sus_ms))) * 1e-3)}
 
-    # ---- e2e: host buffers through the public API --------------------------------------------
-    for _ in range(args.warmup):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    if dist is not None:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = world * n_draws * args.steps / e2e_s
-    clocks = sampler.stop()
-    first_pass = pin_out.array.copy()
-    pin_out.array[:] = 0
-    for _ in range(args.warmup):
-        step_e2e_offsets()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e_offsets()
-    e2e_offsets_ms = 1e3 * (time.perf_counter() - t0) / args.steps
-    assert np.array_equal(first_pass, pin_out.array), 'the two host APIs disagree'
-    resident = d_out.cpu().numpy()
-    assert np.array_equal(resident, pin_out.array), 'resident and host-API results differ'
+    # ---- e2e: host buffers through the public API ----------------------------------------------
+    ncp = leg.info['ncp']
+    pin = {'mean_var': L.PinnedArray((5, n_windows, 2), np.float64), 'stats': L.PinnedArray((n_seg, 5, 3), np.float64),
+           'lik': L.PinnedArray((n_draws, 4), np.float64)}
+    out_stats = {'mean_var': pin['mean_var'].array, 'stats': pin['stats'].array}
+    out_full = dict(out_stats, lik=pin['lik'].array)
+    idx_host, win_of_draw = plan_draws(reads, args.subsamples, n, args.seed + 1 + 1000 * rank)
+    pin_idx = L.PinnedArray((n_draws, n), np.int32)
+    pin_idx.array[:] = idx_host
+    seeds = iter(range(10 ** 6, 10 ** 9))
 
-    # ---- multi-GPU: the only exchange of the path (chromosome LLR partial sums), outside the timed step ----
-    stats_ms = None
-    if dist is not None:
-        off = np.arange(0, n_draws + 1, args.subsamples, dtype=np.int64)
-        _, _, partials = eng.window_stats(pin_out.array, off, args.subsamples)
-        tp = torch.from_numpy(partials).to(device)
-        torch.cuda.synchronize()
+    def e2e_stats():
+        eng.bootstrap_stats(kind, next(seeds), proportions=proportions, out=out_stats)
+
+    def e2e_full():
+        eng.bootstrap_stats(kind, next(seeds), proportions=proportions, out=out_full)
+
+    def e2e_replay():
+        eng.replay_stats(kind, pin_idx.array, proportions=proportions, out=out_stats)
+
+    def time_host(fn):
+        for _ in range(args.warmup):
+            fn()
+        barrier()
         t0 = time.perf_counter()
-        dist.all_reduce(tp)
-        torch.cuda.synchronize()
-        stats_ms = 1e3 * (time.perf_counter() - t0)
+        for _ in range(args.steps):
+            fn()
+        barrier()
+        return max_over_ranks(time.perf_counter() - t0)
+
+    e2e_s = {name: time_host(fn) for name, fn in (('stats', e2e_stats), ('full', e2e_full), ('replay', e2e_replay))}
+    clocks = sampler.stop()
+    stats_b = int(out_stats['mean_var'].nbytes + out_stats['stats'].nbytes)
+    e2e_modes = {
+        'stats': {'value': world * n_draws * args.steps / e2e_s['stats'], 'ms_per_step': 1e3 * e2e_s['stats'] / args.steps,
+                  'h2d_bytes_per_step': 8, 'd2h_bytes_per_step': stats_b,
+                  'api': 'Engine.bootstrap_stats -> ldpgta_bootstrap_stats: draws on the device; window mean/variance + chromosome summaries come down'},
+        'full': {'value': world * n_draws * args.steps / e2e_s['full'], 'ms_per_step': 1e3 * e2e_s['full'] / args.steps,
+                 'h2d_bytes_per_step': 8, 'd2h_bytes_per_step': stats_b + int(pin['lik'].array.nbytes),
+                 'api': 'the same call, also returning the per-draw likelihoods (32 B per draw)'},
+        'replay': {'value': world * n_draws * args.steps / e2e_s['replay'], 'ms_per_step': 1e3 * e2e_s['replay'] / args.steps,
+                   'h2d_bytes_per_step': int(pin_idx.array.nbytes), 'd2h_bytes_per_step': stats_b,
+                   'api': 'Engine.replay_stats -> ldpgta_replay_stats: host-chosen draws go up (16 B per draw), statistics come down'}}
+
+    # ---- consistency: replayed device draws give the same likelihoods and statistics through every route ----
+    chk = eng.bootstrap_stats(kind, 4242, proportions=proportions, want=('lik', 'draws', 'mean_var', 'stats'))
+    rep = eng.replay_stats(kind, chk['draws'], proportions=proportions, want=('lik', 'mean_var', 'stats'))
+    assert np.array_equal(chk['lik'], rep['lik']) and np.array_equal(chk['stats'], rep['stats']), 'device-drawn and replayed results differ'
+    d_chk = torch.from_numpy(chk['draws'].reshape(n_draws, n)).to(device)
+    d_out = torch.empty((n_draws, 4), dtype=torch.float64, device=device)
+    eng.likelihoods_uniform_dev(kind, n, d_chk.data_ptr(), n_draws, d_out.data_ptr(), proportions=proportions)
+    eng.synchronize()
+    assert np.array_equal(d_out.cpu().numpy(), chk['lik']), 'pipeline and plain batch call differ'
+
+    # ---- multi-GPU legs --------------------------------------------------------------------------
+    strong = None
+    if dist is not None:
+        strong = strong_scaling_leg(L, torch, dist, device, local, rank, world, args, kind, group_sizes, proportions, barrier, max_over_ranks)
+    batch96 = None
+    if not args.no_batch96 and args.model == 'homogeneous' and not args.windows:
+        batch96 = batch96_leg(L, torch, dist, device, rank, world, leg, barrier, max_over_ranks, segments)
 
     if rank != 0:
         if dist is not None:
+            dist.barrier()
             dist.destroy_process_group()
         return 0
 
     # ---- rooflines of the dominant kernel ------------------------------------------------------
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
-    peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs, burst copy)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s (B200_PROFILING.md)'
-    words = sum((nh + 63) // 64 for nh in group_sizes)
+    words = leg.words
     bytes_per_draw = n * words * 8 + n * 4 + 32               # n*W*8 mask bytes + indices in, 32 B out
     wordops_per_draw = ((1 << n) - 1) * words
     k_ms = float(np.mean(kernel_ms))
     achieved_gbs = bytes_per_draw * n_draws / (k_ms * 1e-3) / 1e9
-    int_peak = 2.3e12
-    int_src = 'assumed 148 SM x 16 POPC.32/clk x 1.965 GHz / 2'
-    try:
-        ip = json.load(open(os.path.join(ROOT, 'profiles', 'INT_PEAKS.json')))
-        int_peak = float(ip['wordop64_and_popc_add']['ops_per_s'])
-        int_src = 'measured (profiles/INT_PEAKS.json, tools/int_peaks.cu: AND+POPC+ADD on 64-bit words)'
-    except Exception:
-        pass
     achieved_wordops = wordops_per_draw * n_draws / (k_ms * 1e-3)
     traffic = None                                            # DRAM bytes per launch from the committed ncu capture of this kernel
     try:
@@ -476,28 +599,43 @@ def main():
     except Exception:
         pass
 
-    # ---- CPU baseline: oracle port on a bounded sample, one core; doubles as the parity check -------
+    # ---- CPU baseline: the reference's class on a bounded sample, one core; doubles as the parity check -------
     cpu_baseline, parity = None, None
     if not args.no_cpu_baseline and world == 1 and args.model == 'homogeneous':     # rank 0 at N=1 only
-        spent, n_eval, w = 0.0, 0, 0
-        ref_rows, got_rows = [], []
-        starts = np.concatenate([[0], np.cumsum(reads)])
-        while spent < args.cpu_seconds and w < n_windows:
-            r0, r1 = int(starts[w]), int(starts[w + 1])
-            model, rd = oracle_models(masks[r0:r1].cpu().numpy().view(np.uint64), r0, N_HAP)
-            sel = slice(w * args.subsamples, (w + 1) * args.subsamples)          # draws are grouped by window
-            assert (win_of_draw[sel] == w).all()
-            t, vals = oracle_loop(model, rd, idx_host[sel])
-            ref_rows.append(np.array(vals, dtype=np.float64).reshape(-1, 4))
-            got_rows.append(resident[sel])
-            spent += t; n_eval += args.subsamples; w += 1
-        sample_windows = list(range(w))
-        ref_v, got_v = np.concatenate(ref_rows), np.concatenate(got_rows)
+        masks = leg.masks[0]
+        draws = chk['draws'].reshape(n_draws, n)
+        starts = leg.woff
+
+        def sample(cls, budget, wall):
+            spent, n_eval, w, t_wall = 0.0, 0, 0, time.perf_counter()
+            ref_rows = []
+            while spent < budget and w < n_windows and time.perf_counter() - t_wall < wall:
+                r0, r1 = int(starts[w]), int(starts[w + 1])
+                model, rd = cpu_window_model(cls, masks[r0:r1].cpu().numpy().view(np.uint64), r0, N_HAP)
+                t, vals = cpu_loop(model, rd, draws[w * args.subsamples:(w + 1) * args.subsamples])
+                ref_rows.append(np.array(vals, dtype=np.float64).reshape(-1, 4))
+                spent += t; n_eval += args.subsamples; w += 1
+            return spent, n_eval, w, np.concatenate(ref_rows)
+
+        cls, kind_cpu, pc = cpu_model_class()
+        spent, n_eval, w, ref_v = sample(cls, args.cpu_seconds, 4 * args.cpu_seconds + 20)
+        got_v = chk['lik'][:n_eval]
         parity = float(np.max(np.abs(ref_v - got_v) / np.maximum(np.abs(ref_v), 1e-300)))
-        cpu_baseline = {'value': n_eval / spent, 'unit': 'window-likelihoods/s', 'cores': 1, 'kind': 'port',
-                        'sample': 'first %d windows x %d draws (%d draws, %.1f s) of the same embryo' % (len(sample_windows), args.subsamples, n_eval, spent),
-                        'python': sys.version.split()[0], 'popcount': 'int.bit_count (reference: gmpy2.popcount or byte LUT)',
-                        'host_cores_available': os.cpu_count()}
+        cpu_baseline = {'value': n_eval / spent, 'unit': 'window-likelihoods/s', 'cores': 1, 'kind': kind_cpu,
+                        'sample': 'first %d windows x %d draws (%d draws, %.1f s) of the same embryo, the draws the device made' % (w, args.subsamples, n_eval, spent),
+                        'python': sys.version.split()[0], 'popcount': pc, 'host_cores_available': os.cpu_count()}
+        if kind_cpu == 'reference':                            # the oracle port's rate beside it (int.bit_count instead of the byte LUT)
+            pcls, _, ppc = cpu_model_class(prefer_reference=False)
+            ps, pn, pw, pref = sample(pcls, min(3.0, args.cpu_seconds), 20)
+            cpu_baseline['port'] = {'value': pn / ps, 'popcount': ppc, 'sample': 'first %d windows (%.1f s)' % (pw, ps),
+                                    'max_rel_diff_vs_reference': float(np.max(np.abs(pref - ref_v[:pn]) / np.maximum(np.abs(ref_v[:pn]), 1e-300)))}
+
+    secondary = None
+    if not args.no_secondary and args.model == 'homogeneous' and not args.windows:
+        leg.close()
+        del leg, eng
+        torch.cuda.empty_cache()
+        secondary = secondary_legs(L, torch, device, local, args, hbm_peak, int_peak)
 
     line = {
         'metric': 'bootstrapped window-likelihoods/sec', 'value': value, 'unit': 'window-likelihoods/s',
@@ -506,26 +644,128 @@ def main():
         'dtype': 'u64 and/popcount + f64 polynomials', 'data': 'synthetic',
         'config': workload_config(args, n_windows, n_reads),
         'draws_per_step_per_gpu': int(n_draws),
-        'e2e': {'value': e2e_value, 'unit': 'window-likelihoods/s', 'h2d_bytes_per_step': int(pin_idx.array.nbytes),
-                'd2h_bytes_per_step': int(pin_out.array.nbytes), 'ms_per_step': 1e3 * e2e_s / args.steps,
-                'api': 'Engine.likelihoods_uniform -> ldpgta_likelihoods_uniform (pinned host buffers)',
-                'offsets_api_ms_per_step': e2e_offsets_ms},
+        'step': 'device-side draws (Philox + Floyd) -> likelihoods -> LLRs -> window mean/variance -> %d chromosome summaries' % n_seg,
+        'sustained': sustained,
+        'e2e': dict(e2e_modes['stats'], unit='window-likelihoods/s', mode='stats', **{k: v for k, v in e2e_modes.items()}),
         'gpu_launches': int(launches),
         'roofline': {'bound': 'hbm', 'kernel': kernel_name(n, args.model), 'achieved': achieved_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
                      'frac': achieved_gbs / hbm_peak, 'traffic': traffic, 'peak_source': peak_src,
-                     'algorithmic_bytes_per_draw': bytes_per_draw, 'kernel_ms': k_ms},
+                     'algorithmic_bytes_per_draw': bytes_per_draw, 'kernel_ms': k_ms,
+                     'kernel_share_of_step': k_ms / (total_ms / args.steps)},
         'int_roofline': {'bound': 'popc', 'achieved': achieved_wordops, 'peak': int_peak, 'unit': 'word AND+POPC/s',
                          'frac': achieved_wordops / int_peak, 'peak_source': int_src, 'wordops_per_draw': wordops_per_draw},
         'cpu_baseline': cpu_baseline,
         'parity_max_rel_err_vs_oracle': parity,
         'clocks': clocks,
     }
-    if stats_ms is not None:
-        line['chromosome_partials_allreduce_ms'] = stats_ms
+    if secondary is not None:
+        line['secondary'] = secondary
+    if strong is not None:
+        line['strong'] = strong
+    if batch96 is not None:
+        line['batch96'] = batch96
     emit(line)
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def strong_scaling_leg(L, torch, dist, device, local, rank, world, args, kind, group_sizes, proportions, barrier, max_over_ranks):
+    """ ONE configs[1] embryo: its windows dealt to the ranks as contiguous ranges of equal cost
+    (sharding.partition_windows), every rank computing the chromosome partial sums of its windows; ONE all_reduce of
+    the [22][5][35] partials and the finish kernel inside the timed step, everything device-resident. """
+    from ldpgta_b200 import sharding
+    wins, reads = workload_shape(args.depth, args.seed, min_reads=args.max_reads + 2)
+    n, subs = args.max_reads, args.subsamples
+    seg = chromosome_segments(wins, len(reads))
+    words = sum((nh + 63) // 64 for nh in group_sizes)
+    costs = [sharding.draw_cost(int(R), 6, n, subs, words, len(group_sizes)) for R in reads]
+    lo, hi = sharding.partition_windows(costs, world)[rank]
+    my_seg = np.clip(seg, lo, hi) - lo
+    n_seg = len(seg) - 1
+    cols = np.full(n_seg, subs, dtype=np.int32)                  # every window of the embryo has `subs` draws
+    leg = Leg(L, torch, device, local, group_sizes, kind, reads[lo:hi], n, subs, args.seed + 31 * rank, proportions, segments=my_seg,
+              seg_cols=cols, seg_first=cols)
+    ncp = leg.info['ncp']
+    partials = torch.zeros((n_seg, 5, ncp + 3), dtype=torch.float64, device=device)
+    stats = torch.zeros((n_seg, 5, 3), dtype=torch.float64, device=device)
+    steps, warm = args.steps, args.warmup
+
+    def step(ev=None):
+        leg.step(partials.data_ptr())
+        if ev is not None:
+            ev[0].record(leg.stream)
+        dist.all_reduce(partials)
+        if ev is not None:
+            ev[1].record(leg.stream)
+        leg.eng.finish_segments_dev(partials.data_ptr(), stats.data_ptr())
+
+    with torch.cuda.stream(leg.stream):
+        for _ in range(warm):
+            step()
+        leg.eng.synchronize()
+        barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(leg.stream)
+        for k in range(steps):
+            step(evs[k])
+        e1.record(leg.stream)
+        leg.eng.synchronize()
+        barrier()
+    total_ms = max_over_ranks(e0.elapsed_time(e1))
+    ar_ms = max_over_ranks(float(np.median([a.elapsed_time(b) for a, b in evs])))
+    finite = bool(torch.isfinite(stats).all().item())
+    windows_here = hi - lo
+    leg.close()
+    torch.cuda.empty_cache()
+    return {'workload': 'ONE configs[1] embryo, windows dealt to %d ranks by cost, chromosome partial sums all-reduced every step' % world,
+            'scaling': 'strong', 'value': len(reads) * subs * steps / (total_ms * 1e-3), 'unit': 'window-likelihoods/s',
+            'ms_per_step': total_ms / steps, 'windows_rank0': int(windows_here), 'allreduce_bytes': int(partials.numel() * 8),
+            'allreduce_ms_median': ar_ms, 'allreduce_share_of_step': ar_ms / (total_ms / steps), 'collective': 'torch.distributed all_reduce (NCCL) on the device-resident partials',
+            'statistics_finite': finite}
+
+
+def batch96_leg(L, torch, dist, device, rank, world, leg, barrier, max_over_ranks, segments):
+    """ configs[4]: 96 embryos x 22 autosomes x 1000 subsamples per window, embryos dealt round-robin to the ranks,
+    draws made on the device, only the chromosome statistics kept; the ranks' statistics are gathered at the end of the
+    step.  Every embryo of a rank reuses the rank's synthetic read masks with its own seed (the work per embryo is that
+    of a distinct embryo of the same shape; 96 distinct mask sets would need 265 GB). """
+    n_embryos, subs = 96, 1000
+    mine = list(range(rank, n_embryos, world))
+    eng, n_seg = leg.eng, len(segments) - 1
+    doff = np.arange(0, (leg.n_windows + 1) * subs, subs, dtype=np.int64)
+    eng.set_windows(leg.woff, None, doff, leg.n, segment_offsets=segments)
+    per_rank = (n_embryos + world - 1) // world
+    stats = torch.zeros((per_rank, n_seg, 5, 3), dtype=torch.float64, device=device)
+    gathered = torch.zeros((world, per_rank, n_seg, 5, 3), dtype=torch.float64, device=device) if dist is not None else None
+
+    def step():
+        for k, e in enumerate(mine):
+            eng.bootstrap_stats_dev(leg.kind, 1000 + e, proportions=leg.proportions)
+            eng.finish_segments_dev(None, stats[k].data_ptr())
+        if dist is not None:
+            dist.all_gather_into_tensor(gathered, stats)
+
+    with torch.cuda.stream(leg.stream):
+        step()                                                     # warm-up pass
+        eng.synchronize()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(leg.stream)
+        step()
+        e1.record(leg.stream)
+        eng.synchronize()
+        barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    total = n_embryos * leg.n_windows * subs
+    ok = bool(torch.isfinite(stats[:len(mine)]).all().item())
+    return {'workload': 'configs[4]: 96 embryos x 22 autosomes x 1000 subsamples per window (4 reads per draw), embryos dealt to %d rank(s), '
+                        'device draws, chromosome statistics only' % world,
+            'value': total / (ms * 1e-3), 'unit': 'window-likelihoods/s', 'window_likelihoods': int(total), 'seconds': ms * 1e-3,
+            'embryos_rank0': len(mine), 'statistics_finite': ok,
+            'note': 'embryos of a rank share its synthetic read masks (distinct seeds); 96 distinct mask sets would need 265 GB'}
 
 
 if __name__ == '__main__':

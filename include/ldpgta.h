@@ -164,6 +164,65 @@ int64_t ldpgta_launch_count(const ldpgta_ctx *ctx);
 /* number of host-pipeline calls that ran as one CUDA graph launch (see ldpgta_likelihoods_uniform) */
 int64_t ldpgta_graph_replays(const ldpgta_ctx *ctx);
 
+/* ---- the bootstrap loop and statistics() as one device-resident pipeline -------------------------------------
+ * The reference's bootstrap() returns the likelihoods of every draw and statistics() consumes them in place
+ * (ANEUPLOIDY_TEST.py:277-287 -> :289-325).  The calls below keep that hand-off inside HBM: the likelihoods go from the
+ * draw kernels to the LLR / window / chromosome reductions without visiting the host, and what comes back is what the
+ * caller asks for -- 80 bytes per window and a few hundred per chromosome, or additionally the per-draw likelihoods.
+ *
+ * ldpgta_set_windows makes the result of build_gw_dict (:191-224) and the draw plan (:226-248) resident:
+ *   window_offsets, window_reads  CSR of read rows per window (window w = window_reads[window_offsets[w] ..
+ *                                 window_offsets[w+1])); window_reads NULL = the rows window_offsets[w] ..
+ *                                 window_offsets[w+1] themselves (read masks stored window by window; window_offsets[0]
+ *                                 may then be any row, e.g. the first window of a shard);
+ *                                 window_offsets NULL = a replay-only plan (ldpgta_replay_stats)
+ *   draw_offsets    [n_windows+1] draws per window = effective_number_of_subsamples (:235-248), at least one each
+ *                   (windows the reference skips are not listed)
+ *   reads_per_draw  [n_windows]   min(R - 1, max_reads) of :231, 2..18
+ *   segment_offsets [n_segments+1] windows of each (embryo, chromosome) unit statistics() reduces together;
+ *                   NULL = one segment.  Several chromosomes or embryos can share one context this way.
+ *   segment_cols    [n_segments] columns of zip(*A) every window of the WHOLE chromosome has (:73); NULL = the minimum
+ *                   over the listed windows.  segment_first [n_segments] = len(A[0]) (:71); NULL = the draws of the
+ *                   segment's first listed window.  Ranks that hold a shard of a chromosome pass the global values.
+ * Replaces any earlier plan of the context; the read masks must be resident. */
+int ldpgta_set_windows(ldpgta_ctx *ctx, const int64_t *window_offsets, const int32_t *window_reads, int64_t n_windows,
+                       const int64_t *draw_offsets, const int32_t *reads_per_draw, const int64_t *segment_offsets,
+                       int n_segments, const int32_t *segment_cols, const int32_t *segment_first);
+/* bootstrap() + statistics() for the resident plan, draws made on the device (Philox4x32-10 + Floyd as in
+ * ldpgta_bootstrap_uniform; the draws of size class n use seed + n and are numbered in window order).  Nothing but the
+ * seed goes up.  Every output is optional (NULL = not wanted, not downloaded):
+ *   lik_out          [n_draws][4]          per-draw likelihoods (streamed down in chunks under the kernels)
+ *   idx_out          concatenated draws in window order, reads_per_draw[w] indices per draw
+ *   llr_out          [5][n_draws]          per-draw LLRs; also left resident for ldpgta_bin_stats(x = NULL)
+ *   window_mean_var  [5][n_windows][2]     mean and sample variance (NaN for single-draw windows)
+ *   segment_partials [n_segments][5][ncp+3] as chrom_partials of ldpgta_window_stats, ncp = max segment_cols, columns at
+ *                                          or beyond a segment's own count are zero
+ *   segment_stats    [n_segments][5][3]    mean_of_mean, std_of_mean, fraction_of_negative_LLRs (:311-313) */
+int ldpgta_bootstrap_stats(ldpgta_ctx *ctx, int model_kind, uint64_t seed, const double *proportions, double *lik_out,
+                           int32_t *idx_out, double *llr_out, double *window_mean_var, double *segment_partials,
+                           double *segment_stats);
+/* The same for draws chosen by the caller (the reference's random.sample stream, :231): read_idx = the draws of the
+ * plan in window order, reads_per_draw[w] read rows per draw. */
+int ldpgta_replay_stats(ldpgta_ctx *ctx, int model_kind, const int32_t *read_idx, const double *proportions,
+                        double *lik_out, double *llr_out, double *window_mean_var, double *segment_partials,
+                        double *segment_stats);
+/* Device-resident variants, asynchronous on the context's stream (bench.py `value`, multi-GPU shards): the first leaves
+ * likelihoods and window statistics in the plan's buffers and writes the segment partial sums to
+ * segment_partials_dev[n_segments][5][ncp+3] (NULL = the plan's own buffer, then the statistics are finished too); shards
+ * of one chromosome all-reduce (sum) that buffer and call the second, which turns partials into segment_stats_dev
+ * [n_segments][5][3] (NULL = the plan's buffers). */
+int ldpgta_bootstrap_stats_dev(ldpgta_ctx *ctx, int model_kind, uint64_t seed, const double *proportions,
+                               double *segment_partials_dev);
+int ldpgta_finish_segments_dev(ldpgta_ctx *ctx, const double *segment_partials_dev, double *segment_stats_dev);
+/* Measurement aid: with enable != 0 the calls above bracket their draw kernels (k_small / k_mid / k_lanes / k_general, not
+ * the sampler or the reductions) with CUDA events on the context's stream; ldpgta_kernel_times waits for the stream,
+ * writes the elapsed milliseconds of every bracket since the last call (at most max_entries) and returns their number. */
+int ldpgta_kernel_timing(ldpgta_ctx *ctx, int enable);
+int ldpgta_kernel_times(ldpgta_ctx *ctx, double *ms_out, int max_entries);
+/* out[10] = n_windows, n_draws, n_segments, ncp, number of draw-size classes, total read indices of the plan, and the
+ * device addresses of the plan's likelihoods [n_draws][4], window_mean_var, segment_partials, segment_stats buffers. */
+int ldpgta_plan_info(const ldpgta_ctx *ctx, int64_t *out);
+
 /* LLR + reductions of statistics() (ANEUPLOIDY_TEST.py:78-90, 51-56, 65-76, 289-325) for one
  * chromosome shard.  lik[n_draws][4] as produced above, windows = consecutive runs of draws:
  * window w owns draws [window_offsets[w], window_offsets[w+1]).
@@ -174,8 +233,9 @@ int64_t ldpgta_graph_replays(const ldpgta_ctx *ctx);
  *                                      [1] number of windows, [2] number of windows with mean < 0,
  *                                      [3 + i] column sums  sum_w x_wi  for i < n_cols
  * n_cols = the smallest draw count over the windows of the WHOLE chromosome (zip truncation of
- * :73); shards of one chromosome add their chrom_partials (that sum is the only cross-GPU
- * exchange of the path) and ldpgta_finish_chromosome() turns the sum into mean/std. */
+ * :73, at most 4096); shards of one chromosome add their chrom_partials (that sum is the only cross-GPU
+ * exchange of the path) and ldpgta_finish_chromosome() turns the sum into mean/std.  Likelihoods that are
+ * already on the device never need this call: see ldpgta_bootstrap_stats / ldpgta_replay_stats. */
 int ldpgta_window_stats(ldpgta_ctx *ctx, const double *lik, const int64_t *window_offsets,
                         int64_t n_windows, int n_cols, double *llr, double *window_mean_var,
                         double *chrom_partials);

@@ -45,6 +45,14 @@ SYMBOLS = (
     ('ldpgta_stream', _c.c_uint64, [_P]),
     ('ldpgta_launch_count', _c.c_int64, [_P]),
     ('ldpgta_graph_replays', _c.c_int64, [_P]),
+    ('ldpgta_set_windows', _c.c_int, [_P, _P, _P, _c.c_int64, _P, _P, _P, _c.c_int, _P, _P]),
+    ('ldpgta_bootstrap_stats', _c.c_int, [_P, _c.c_int, _c.c_uint64, _P, _P, _P, _P, _P, _P, _P]),
+    ('ldpgta_replay_stats', _c.c_int, [_P, _c.c_int, _P, _P, _P, _P, _P, _P, _P]),
+    ('ldpgta_bootstrap_stats_dev', _c.c_int, [_P, _c.c_int, _c.c_uint64, _P, _P]),
+    ('ldpgta_finish_segments_dev', _c.c_int, [_P, _P, _P]),
+    ('ldpgta_plan_info', _c.c_int, [_P, _P]),
+    ('ldpgta_kernel_timing', _c.c_int, [_P, _c.c_int]),
+    ('ldpgta_kernel_times', _c.c_int, [_P, _P, _c.c_int]),
     ('ldpgta_window_stats', _c.c_int, [_P, _P, _P, _c.c_int64, _c.c_int, _P, _P, _P]),
     ('ldpgta_finish_chromosome', _c.c_int, [_P, _c.c_int, _c.c_int, _P]),
     ('ldpgta_bin_stats', _c.c_int, [_P, _P, _c.c_int, _P, _c.c_int64, _P, _c.c_int64, _P]),

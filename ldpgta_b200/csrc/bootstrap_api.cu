@@ -1,0 +1,585 @@
+// bootstrap_api.cu -- the bootstrap loop and statistics() as ONE device-resident pipeline (include/ldpgta.h):
+//   ldpgta_set_windows      windows, draw plan and (embryo, chromosome) segments made resident next to the read masks
+//   ldpgta_bootstrap_stats  pick_reads on the device -> likelihoods -> LLRs -> window mean/variance -> segment sums -> finish
+//   ldpgta_replay_stats     the same for draws given by the caller (the reference's random.sample stream, replayed)
+//   ldpgta_window_stats     the reductions alone, for likelihoods that are on the host
+// Likelihoods never leave HBM between the draw kernels and the reductions (ANEUPLOIDY_TEST.py:277-325 consumes them in place).
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "k_stats.cuh"
+
+namespace ldpgta {
+
+struct SizeClass {
+    int n = 0;                     // reads per draw
+    int64_t n_windows = 0, n_draws = 0;
+    std::vector<int32_t> win;      // sample window of class window j
+    int64_t *d_doff = nullptr;     // [n_windows + 1] class-local draw offsets
+    int32_t *d_win = nullptr;      // device copy of win (nullptr: identity, the plan has one class)
+    int32_t *d_idx = nullptr;      // [n_draws][n] draws of the class
+    int64_t *d_pos = nullptr;      // [n_draws] place of each draw in the sample-wide order (nullptr: identity)
+};
+
+struct WindowPlan {
+    int64_t n_windows = 0, n_draws = 0, n_wreads = 0, nnz = 0;
+    int n_segments = 0, ncp = 0, cw = 8;
+    int64_t n_chunks = 0;
+    bool has_windows = false;
+    void *d_static = nullptr, *d_work = nullptr;
+    int64_t *d_woff = nullptr, *d_doff = nullptr, *d_segoff = nullptr;
+    int32_t *d_wreads = nullptr, *d_segcols = nullptr, *d_segfirst = nullptr;
+    std::vector<SizeClass> classes;
+    std::vector<int64_t> h_doff;   // draw offsets per window
+    std::vector<int32_t> h_n;      // reads per draw per window
+    double *d_lik = nullptr, *d_mv = nullptr, *d_runs = nullptr, *d_partials = nullptr, *d_stats = nullptr;
+    uint64_t *d_seed = nullptr;
+};
+
+void free_window_plan(ldpgta_ctx *c)
+{
+    if (!c->plan) return;
+    if (c->plan->d_static) cudaFree(c->plan->d_static);
+    if (c->plan->d_work) cudaFree(c->plan->d_work);
+    delete c->plan;
+    c->plan = nullptr;
+}
+
+template <int K>
+static void launch_sample_k(ldpgta_ctx *c, const SampleArgs &a)
+{
+    const unsigned blocks = (unsigned)std::min<int64_t>((a.n_draws + 127) / 128, (int64_t)c->sm_count * 16);
+    k_sample_draws<K><<<blocks, 128, 0, c->stream>>>(a);
+    c->launches++;
+}
+
+int launch_sample(ldpgta_ctx *c, int n, const SampleArgs &a)
+{
+    if (a.n_draws == 0) return 0;
+    switch (n) {
+#define LDPGTA_K(K_) case K_: launch_sample_k<K_>(c, a); break;
+        LDPGTA_K(2) LDPGTA_K(3) LDPGTA_K(4) LDPGTA_K(5) LDPGTA_K(6) LDPGTA_K(7) LDPGTA_K(8) LDPGTA_K(9) LDPGTA_K(10)
+        LDPGTA_K(11) LDPGTA_K(12) LDPGTA_K(13) LDPGTA_K(14) LDPGTA_K(15) LDPGTA_K(16) LDPGTA_K(17) LDPGTA_K(18)
+#undef LDPGTA_K
+        default: return fail(LDPGTA_E_UNSUPPORTED, "draws of %d reads are outside the supported range 2..%d", n, MAXN);
+    }
+    LDPGTA_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// shape of the fused reduction kernel for a column capacity
+struct StatsShape { int wpb; size_t smem; int cw; int64_t n_chunks; };
+
+static int stats_shape(const ldpgta_ctx *c, int64_t n_windows, int ncp, StatsShape *s)
+{
+    if (ncp > 4096) return fail(LDPGTA_E_UNSUPPORTED, "%d draws per window: the device reductions keep at most 4096 columns", ncp);
+    const size_t per_warp = (size_t)5 * ncp * 8;
+    s->wpb = per_warp ? (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / per_warp)) : 8;
+    s->smem = per_warp * s->wpb;
+    const int bps = s->smem ? (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / s->smem)) : 8;
+    const int64_t resident = (int64_t)c->sm_count * s->wpb * bps;
+    s->cw = (int)std::max<int64_t>(8, (n_windows + 2 * resident - 1) / (2 * resident));
+    s->n_chunks = (n_windows + s->cw - 1) / s->cw;
+    return 0;
+}
+
+// LLRs, window mean / variance, segment partial sums and (optionally) the finished segment statistics, all on c->stream
+static int stats_on_device(ldpgta_ctx *c, const double *d_lik, const int64_t *d_doff, int64_t n_windows, int64_t n_draws,
+                           const int64_t *d_segoff, const int32_t *d_segcols, const int32_t *d_segfirst, int n_segments, int ncp,
+                           const StatsShape &sh, double *d_llr, double *d_mv, double *d_runs, double *d_partials, double *d_stats)
+{
+    if (n_windows > 0) {
+        StatsArgs a;
+        a.lik = d_lik; a.doff = d_doff; a.seg_off = d_segoff; a.n_windows = n_windows; a.n_draws = n_draws;
+        a.n_segments = n_segments; a.ncp = ncp; a.cw = sh.cw; a.llr = d_llr; a.mean_var = d_mv; a.runs = d_runs;
+        if (sh.smem > 48 * 1024)
+            LDPGTA_CUDA(cudaFuncSetAttribute(k_llr_window_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem));
+        const unsigned blocks = (unsigned)std::min<int64_t>((sh.n_chunks + sh.wpb - 1) / sh.wpb, (int64_t)c->sm_count * 32);
+        k_llr_window_stats<<<blocks, sh.wpb * 32, sh.smem, c->stream>>>(a);
+        c->launches++;
+    }
+    k_segment_partials<<<dim3((unsigned)n_segments, 5), 128, 0, c->stream>>>(d_runs, d_segoff, d_segcols, ncp, sh.cw, d_partials);
+    c->launches++;
+    if (d_stats) {
+        k_finish_segments<<<(n_segments * 5 + 127) / 128, 128, 0, c->stream>>>(d_partials, d_segcols, d_segfirst, n_segments, ncp, d_stats);
+        c->launches++;
+    }
+    LDPGTA_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+// draws of every class -> likelihoods in the sample-wide order (plan->d_lik), optionally streaming them to the host
+static int time_mark(ldpgta_ctx *c)
+{
+    if (!c->time_kernels) return 0;
+    if (c->t_used == c->t_ev.size()) {
+        cudaEvent_t e;
+        LDPGTA_CUDA(cudaEventCreate(&e));
+        c->t_ev.push_back(e);
+    }
+    LDPGTA_CUDA(cudaEventRecord(c->t_ev[c->t_used++], c->stream));
+    return 0;
+}
+
+static int evaluate_classes_inner(ldpgta_ctx *c, WindowPlan *p, int kind, const double *proportions, double *lik_out_pinned);
+
+static int evaluate_classes(ldpgta_ctx *c, WindowPlan *p, int kind, const double *proportions, double *lik_out_pinned)
+{
+    if (int rc = time_mark(c)) return rc;
+    if (int rc = evaluate_classes_inner(c, p, kind, proportions, lik_out_pinned)) return rc;
+    return time_mark(c);
+}
+
+static int evaluate_classes_inner(ldpgta_ctx *c, WindowPlan *p, int kind, const double *proportions, double *lik_out_pinned)
+{
+    if (p->classes.size() == 1 && lik_out_pinned && p->n_draws >= 65536) {
+        // one draw size (the usual plan): chunks, the download of chunk i under the kernel of chunk i + 1
+        const SizeClass &k = p->classes[0];
+        const int64_t n_chunks = std::min<int64_t>(16, p->n_draws / 32768);
+        const int64_t per = ((p->n_draws + n_chunks - 1) / n_chunks + 63) & ~(int64_t)63;
+        if (int rc = ensure_pipeline(c, (int)n_chunks + 1)) return rc;
+        int ci = 0;
+        for (int64_t d0 = 0; d0 < p->n_draws; d0 += per, ++ci) {
+            const int64_t nd = std::min(per, p->n_draws - d0);
+            if (int rc = run_uniform(c, kind, k.n, k.d_idx + d0 * k.n, nd, nullptr, proportions, p->d_lik + 4 * d0, nullptr)) return rc;
+            LDPGTA_CUDA(cudaEventRecord(c->ev_k[ci], c->stream));
+            LDPGTA_CUDA(cudaStreamWaitEvent(c->s_out, c->ev_k[ci], 0));
+            LDPGTA_CUDA(cudaMemcpyAsync(lik_out_pinned + 4 * d0, p->d_lik + 4 * d0, (size_t)nd * 32, cudaMemcpyDeviceToHost, c->s_out));
+        }
+        return 0;
+    }
+    for (const SizeClass &k : p->classes)
+        if (int rc = run_uniform(c, kind, k.n, k.d_idx, k.n_draws, k.d_pos, proportions, p->d_lik, nullptr)) return rc;
+    if (lik_out_pinned) {
+        if (int rc = ensure_pipeline(c, 2)) return rc;
+        LDPGTA_CUDA(cudaEventRecord(c->ev_k[0], c->stream));
+        LDPGTA_CUDA(cudaStreamWaitEvent(c->s_out, c->ev_k[0], 0));
+        LDPGTA_CUDA(cudaMemcpyAsync(lik_out_pinned, p->d_lik, (size_t)p->n_draws * 32, cudaMemcpyDeviceToHost, c->s_out));
+    }
+    return 0;
+}
+
+static int check_plan(const ldpgta_ctx *c, int kind, const double *proportions)
+{
+    if (!c) return fail(LDPGTA_E_INVALID, "null context");
+    if (!c->plan) return fail(LDPGTA_E_STATE, "no windows are resident: call ldpgta_set_windows first");
+    if (int rc = check_kind(c, kind, proportions)) return rc;
+    for (const SizeClass &k : c->plan->classes)
+        if (int rc = check_uniform_size(kind, k.n)) return rc;
+    return 0;
+}
+
+// reductions of the resident likelihoods + downloads of what the caller asked for; waits for everything
+static int reduce_and_download(ldpgta_ctx *c, WindowPlan *p, double *lik_out, double *lik_pinned, double *llr_out,
+                               double *window_mean_var, double *segment_partials, double *segment_stats)
+{
+    StatsShape sh;
+    if (int rc = stats_shape(c, p->n_windows, p->ncp, &sh)) return rc;
+    double *d_llr = nullptr;
+    c->llr_draws = c->llr_windows = -1;
+    if (llr_out) {
+        if (int rc = ensure_own(&c->d_llr, &c->d_llr_bytes, (size_t)p->n_draws * 40 + 16)) return rc;
+        if (int rc = ensure_own(&c->d_llr_off, &c->d_llr_off_bytes, (size_t)(p->n_windows + 1) * 8)) return rc;
+        d_llr = c->d_llr;
+        LDPGTA_CUDA(cudaMemcpyAsync(c->d_llr_off, p->d_doff, (size_t)(p->n_windows + 1) * 8, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    if (int rc = stats_on_device(c, p->d_lik, p->d_doff, p->n_windows, p->n_draws, p->d_segoff, p->d_segcols, p->d_segfirst,
+                                 p->n_segments, p->ncp, sh, d_llr, p->d_mv, p->d_runs, p->d_partials, p->d_stats))
+        return rc;
+    const size_t cp_b = (size_t)p->n_segments * 5 * (p->ncp + 3) * 8;
+    if (window_mean_var && p->n_windows)
+        LDPGTA_CUDA(cudaMemcpyAsync(window_mean_var, p->d_mv, (size_t)p->n_windows * 80, cudaMemcpyDeviceToHost, c->stream));
+    if (segment_partials) LDPGTA_CUDA(cudaMemcpyAsync(segment_partials, p->d_partials, cp_b, cudaMemcpyDeviceToHost, c->stream));
+    if (segment_stats) LDPGTA_CUDA(cudaMemcpyAsync(segment_stats, p->d_stats, (size_t)p->n_segments * 120, cudaMemcpyDeviceToHost, c->stream));
+    if (llr_out && p->n_draws) LDPGTA_CUDA(cudaMemcpyAsync(llr_out, d_llr, (size_t)p->n_draws * 40, cudaMemcpyDeviceToHost, c->stream));
+    LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
+    if (lik_out) {
+        LDPGTA_CUDA(cudaStreamSynchronize(c->s_out));
+        if (lik_pinned != lik_out) memcpy(lik_out, lik_pinned, (size_t)p->n_draws * 32);
+    }
+    if (llr_out) { c->llr_draws = p->n_draws; c->llr_windows = p->n_windows; }
+    return 0;
+}
+
+}  // namespace ldpgta
+
+using namespace ldpgta;
+
+extern "C" {
+
+int ldpgta_set_windows(ldpgta_ctx *c, const int64_t *window_offsets, const int32_t *window_reads, int64_t n_windows,
+                       const int64_t *draw_offsets, const int32_t *reads_per_draw, const int64_t *segment_offsets,
+                       int n_segments, const int32_t *segment_cols, const int32_t *segment_first)
+{
+    if (!c || !draw_offsets || !reads_per_draw || n_windows < 0) return fail(LDPGTA_E_INVALID, "bad arguments");
+    if (window_reads && !window_offsets) return fail(LDPGTA_E_INVALID, "window_reads without window_offsets");
+    LDPGTA_CUDA(cudaSetDevice(c->device));
+    if (c->n_reads <= 0 && window_offsets) return fail(LDPGTA_E_STATE, "read masks are missing (upload or build them first)");
+    const int64_t one_seg[2] = {0, n_windows};
+    if (!segment_offsets) { segment_offsets = one_seg; n_segments = 1; }
+    if (n_segments < 1) return fail(LDPGTA_E_INVALID, "at least one segment is needed");
+    // consecutive-row windows address the read-mask table directly and may start anywhere in it (a shard of a sample)
+    if (draw_offsets[0] != 0 || (window_reads && window_offsets[0] != 0) || (window_offsets && window_offsets[0] < 0) || segment_offsets[0] != 0)
+        return fail(LDPGTA_E_INVALID, "offsets must start at 0");
+    if (segment_offsets[n_segments] != n_windows) return fail(LDPGTA_E_INVALID, "segment_offsets must end at n_windows");
+    for (int s = 0; s < n_segments; ++s)
+        if (segment_offsets[s + 1] < segment_offsets[s]) return fail(LDPGTA_E_INVALID, "segment_offsets must not decrease (segment %d)", s);
+    int64_t per_n[MAXN + 1] = {}, win_n[MAXN + 1] = {}, nnz = 0;
+    int64_t max_draws = 0;
+    for (int64_t w = 0; w < n_windows; ++w) {
+        const int64_t nd = draw_offsets[w + 1] - draw_offsets[w];
+        const int n = reads_per_draw[w];
+        if (nd < 1) return fail(LDPGTA_E_INVALID, "window %lld has no draws", (long long)w);
+        if (n < 2 || n > MAXN) return fail(LDPGTA_E_UNSUPPORTED, "window %lld: draws of %d reads, supported range is 2..%d", (long long)w, n, MAXN);
+        if (window_offsets) {
+            const int64_t R = window_offsets[w + 1] - window_offsets[w];
+            if (R < n) return fail(LDPGTA_E_INVALID, "window %lld has %lld reads, fewer than the %d of a draw", (long long)w, (long long)R, n);
+            if (R > 0x7fffffff) return fail(LDPGTA_E_INVALID, "window %lld has too many reads", (long long)w);
+        }
+        per_n[n] += nd; win_n[n]++; nnz += nd * n;
+        max_draws = std::max(max_draws, nd);
+    }
+    const int64_t n_draws = draw_offsets[n_windows];
+    const int64_t n_wreads = window_offsets ? window_offsets[n_windows] : 0;
+    if (window_offsets && !window_reads && n_wreads > c->n_reads)
+        return fail(LDPGTA_E_INVALID, "window_offsets address read rows up to %lld, the context holds %lld", (long long)n_wreads, (long long)c->n_reads);
+
+    // segments: columns every window has (zip truncation, ANEUPLOIDY_TEST.py:73) and the first window's draws (:71)
+    std::vector<int32_t> segcols(n_segments), segfirst(n_segments);
+    int ncp = 0;
+    for (int s = 0; s < n_segments; ++s) {
+        const int64_t lo = segment_offsets[s], hi = segment_offsets[s + 1];
+        int64_t mn = hi > lo ? INT64_MAX : 0;
+        for (int64_t w = lo; w < hi; ++w) mn = std::min(mn, draw_offsets[w + 1] - draw_offsets[w]);
+        segcols[s] = segment_cols ? segment_cols[s] : (int32_t)std::min<int64_t>(mn, 0x7fffffff);
+        segfirst[s] = segment_first ? segment_first[s] : (hi > lo ? (int32_t)(draw_offsets[lo + 1] - draw_offsets[lo]) : 0);
+        if (segcols[s] < 0 || (hi > lo && segcols[s] > mn))
+            return fail(LDPGTA_E_INVALID, "segment %d: %d columns, but one of its windows has only %lld draws", s, segcols[s], (long long)mn);
+        ncp = std::max(ncp, (int)segcols[s]);
+    }
+    StatsShape sh;
+    if (int rc = stats_shape(c, n_windows, ncp, &sh)) return rc;
+
+    LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
+    free_window_plan(c);
+    WindowPlan *p = new WindowPlan();
+    c->plan = p;
+    p->n_windows = n_windows; p->n_draws = n_draws; p->n_wreads = window_reads ? n_wreads : 0; p->nnz = nnz;
+    p->n_segments = n_segments; p->ncp = ncp; p->cw = sh.cw; p->n_chunks = sh.n_chunks;
+    p->has_windows = window_offsets != nullptr;
+    p->h_doff.assign(draw_offsets, draw_offsets + n_windows + 1);
+    p->h_n.assign(reads_per_draw, reads_per_draw + n_windows);
+    int n_classes = 0;
+    for (int n = 2; n <= MAXN; ++n) n_classes += per_n[n] > 0;
+    const bool single = n_classes <= 1;
+
+    // host images of the static arrays, one allocation and one copy
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += pad256(bytes); return o; };
+    const size_t o_woff = take(window_offsets ? (size_t)(n_windows + 1) * 8 : 0), o_doff = take((size_t)(n_windows + 1) * 8);
+    const size_t o_seg = take((size_t)(n_segments + 1) * 8), o_cols = take((size_t)n_segments * 4), o_first = take((size_t)n_segments * 4);
+    const size_t o_wreads = take((size_t)p->n_wreads * 4), o_seed = take(8);
+    struct ClsOff { size_t doff, win, pos; };
+    std::vector<ClsOff> co;
+    for (int n = 2; n <= MAXN; ++n) {
+        if (!per_n[n]) continue;
+        SizeClass k;
+        k.n = n; k.n_windows = win_n[n]; k.n_draws = per_n[n];
+        p->classes.push_back(k);
+        ClsOff o;
+        o.doff = take((size_t)(win_n[n] + 1) * 8);
+        o.win = single ? 0 : take((size_t)win_n[n] * 4);
+        o.pos = single ? 0 : take((size_t)per_n[n] * 8);
+        co.push_back(o);
+    }
+    const size_t static_bytes = std::max<size_t>(off, 256);
+    std::vector<unsigned char> img(static_bytes, 0);
+    if (window_offsets) memcpy(img.data() + o_woff, window_offsets, (size_t)(n_windows + 1) * 8);
+    memcpy(img.data() + o_doff, draw_offsets, (size_t)(n_windows + 1) * 8);
+    memcpy(img.data() + o_seg, segment_offsets, (size_t)(n_segments + 1) * 8);
+    memcpy(img.data() + o_cols, segcols.data(), (size_t)n_segments * 4);
+    memcpy(img.data() + o_first, segfirst.data(), (size_t)n_segments * 4);
+    if (p->n_wreads) memcpy(img.data() + o_wreads, window_reads, (size_t)p->n_wreads * 4);
+    for (size_t ci = 0; ci < p->classes.size(); ++ci) {
+        SizeClass &k = p->classes[ci];
+        int64_t *cd = (int64_t *)(img.data() + co[ci].doff);
+        int32_t *cwn = single ? nullptr : (int32_t *)(img.data() + co[ci].win);
+        int64_t *cp = single ? nullptr : (int64_t *)(img.data() + co[ci].pos);
+        int64_t j = 0, d = 0;
+        cd[0] = 0;
+        k.win.reserve((size_t)k.n_windows);
+        for (int64_t w = 0; w < n_windows; ++w) {
+            if (reads_per_draw[w] != k.n) continue;
+            const int64_t nd = draw_offsets[w + 1] - draw_offsets[w];
+            k.win.push_back((int32_t)w);
+            if (!single) {
+                cwn[j] = (int32_t)w;
+                for (int64_t t = 0; t < nd; ++t) cp[d + t] = draw_offsets[w] + t;
+            }
+            d += nd;
+            cd[++j] = d;
+        }
+    }
+    LDPGTA_CUDA(cudaMalloc(&p->d_static, static_bytes));
+    LDPGTA_CUDA(cudaMemcpyAsync(p->d_static, img.data(), static_bytes, cudaMemcpyHostToDevice, c->stream));
+    char *base = (char *)p->d_static;
+    p->d_woff = window_offsets ? (int64_t *)(base + o_woff) : nullptr;
+    p->d_doff = (int64_t *)(base + o_doff);
+    p->d_segoff = (int64_t *)(base + o_seg);
+    p->d_segcols = (int32_t *)(base + o_cols);
+    p->d_segfirst = (int32_t *)(base + o_first);
+    p->d_wreads = p->n_wreads ? (int32_t *)(base + o_wreads) : nullptr;
+    p->d_seed = (uint64_t *)(base + o_seed);
+    for (size_t ci = 0; ci < p->classes.size(); ++ci) {
+        p->classes[ci].d_doff = (int64_t *)(base + co[ci].doff);
+        p->classes[ci].d_win = single ? nullptr : (int32_t *)(base + co[ci].win);
+        p->classes[ci].d_pos = single ? nullptr : (int64_t *)(base + co[ci].pos);
+    }
+    // window read lists are checked on the device (the copy is clamped, the call fails)
+    if (p->n_wreads) {
+        if (int rc = ensure_pipeline(c, 1)) return rc;
+        LDPGTA_CUDA(cudaMemsetAsync(c->d_flag, 0, 4, c->stream));
+        const uint32_t lim = (uint32_t)std::min<int64_t>(c->n_reads, 0x7fffffff);
+        k_sanitize_idx<<<(unsigned)std::min<int64_t>((p->n_wreads / 4 + 255) / 256 + 1, (int64_t)c->sm_count * 4), 256, 0, c->stream>>>(
+            p->d_wreads, p->n_wreads, lim, c->d_flag);
+        c->launches++;
+        LDPGTA_CUDA(cudaMemcpyAsync(c->h_flag, c->d_flag, 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    // work buffers: draws per class, likelihoods, window statistics, runs, segment partials and statistics
+    off = 0;
+    std::vector<size_t> o_idx;
+    for (const SizeClass &k : p->classes) o_idx.push_back(take((size_t)k.n_draws * k.n * 4));
+    const size_t o_lik = take((size_t)n_draws * 32), o_mv = take((size_t)n_windows * 80);
+    const size_t o_runs = take((size_t)(sh.n_chunks + n_segments) * 5 * (ncp + 3) * 8);
+    const size_t o_part = take((size_t)n_segments * 5 * (ncp + 3) * 8), o_stats = take((size_t)n_segments * 120);
+    LDPGTA_CUDA(cudaMalloc(&p->d_work, std::max<size_t>(off, 256)));
+    base = (char *)p->d_work;
+    for (size_t ci = 0; ci < p->classes.size(); ++ci) p->classes[ci].d_idx = (int32_t *)(base + o_idx[ci]);
+    p->d_lik = (double *)(base + o_lik);
+    p->d_mv = (double *)(base + o_mv);
+    p->d_runs = (double *)(base + o_runs);
+    p->d_partials = (double *)(base + o_part);
+    p->d_stats = (double *)(base + o_stats);
+    LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
+    if (p->n_wreads && *c->h_flag) {
+        free_window_plan(c);
+        return fail_bad_index(c, window_reads, n_wreads);
+    }
+    return 0;
+}
+
+int ldpgta_bootstrap_stats(ldpgta_ctx *c, int kind, uint64_t seed, const double *proportions, double *lik_out, int32_t *idx_out,
+                           double *llr_out, double *window_mean_var, double *segment_partials, double *segment_stats)
+{
+    if (int rc = check_plan(c, kind, proportions)) return rc;
+    LDPGTA_CUDA(cudaSetDevice(c->device));
+    WindowPlan *p = c->plan;
+    if (!p->has_windows) return fail(LDPGTA_E_STATE, "the resident plan has no window read lists (replay-only): use ldpgta_replay_stats");
+    double *lik_pinned = lik_out;
+    if (lik_out && !is_page_locked(lik_out)) {
+        if (int rc = ensure_pin(c, (size_t)p->n_draws * 32)) return rc;
+        lik_pinned = (double *)c->h_pin;
+    }
+    for (const SizeClass &k : p->classes) {
+        SampleArgs sa;
+        memset(&sa, 0, sizeof sa);
+        sa.draw_off = k.d_doff; sa.win_off = p->d_woff; sa.win_reads = p->d_wreads; sa.cls_win = k.d_win;
+        sa.n_windows = k.n_windows; sa.n_draws = k.n_draws; sa.seed = seed + (uint64_t)k.n; sa.idx_out = k.d_idx;
+        if (int rc = launch_sample(c, k.n, sa)) return rc;
+    }
+    if (int rc = evaluate_classes(c, p, kind, proportions, lik_pinned)) return rc;
+    if (idx_out) {
+        // draws in the sample-wide order: window by window (classes interleave only when draw sizes differ)
+        if (p->classes.size() == 1) {
+            LDPGTA_CUDA(cudaMemcpyAsync(idx_out, p->classes[0].d_idx, (size_t)p->nnz * 4, cudaMemcpyDeviceToHost, c->stream));
+        } else {
+            std::vector<int32_t> tmp;
+            std::vector<int64_t> start(p->n_windows + 1, 0);
+            for (int64_t w = 0; w < p->n_windows; ++w) start[w + 1] = start[w] + (p->h_doff[w + 1] - p->h_doff[w]) * p->h_n[w];
+            for (const SizeClass &k : p->classes) {
+                tmp.resize((size_t)k.n_draws * k.n);
+                LDPGTA_CUDA(cudaMemcpyAsync(tmp.data(), k.d_idx, tmp.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+                LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
+                int64_t at = 0;
+                for (int32_t w : k.win) {
+                    const int64_t cnt = (p->h_doff[w + 1] - p->h_doff[w]) * k.n;
+                    memcpy(idx_out + start[w], tmp.data() + at, (size_t)cnt * 4);
+                    at += cnt;
+                }
+            }
+        }
+    }
+    return reduce_and_download(c, p, lik_out, lik_pinned, llr_out, window_mean_var, segment_partials, segment_stats);
+}
+
+int ldpgta_replay_stats(ldpgta_ctx *c, int kind, const int32_t *read_idx, const double *proportions, double *lik_out,
+                        double *llr_out, double *window_mean_var, double *segment_partials, double *segment_stats)
+{
+    if (int rc = check_plan(c, kind, proportions)) return rc;
+    if (!read_idx) return fail(LDPGTA_E_INVALID, "null read_idx");
+    LDPGTA_CUDA(cudaSetDevice(c->device));
+    WindowPlan *p = c->plan;
+    double *lik_pinned = lik_out;
+    size_t pin_lik = 0;
+    if (lik_out && !is_page_locked(lik_out)) pin_lik = (size_t)p->n_draws * 32;
+    const bool single = p->classes.size() == 1;
+    const bool stage_idx = !single || !is_page_locked(read_idx);
+    const size_t idx_b = pad256((size_t)p->nnz * 4);
+    if (pin_lik || stage_idx)
+        if (int rc = ensure_pin(c, (stage_idx ? idx_b : 0) + pin_lik)) return rc;
+    if (pin_lik) lik_pinned = (double *)((char *)c->h_pin + (stage_idx ? idx_b : 0));
+    if (int rc = ensure_pipeline(c, 1)) return rc;
+    LDPGTA_CUDA(cudaMemsetAsync(c->d_flag, 0, 4, c->stream));
+    const uint32_t lim = (uint32_t)std::min<int64_t>(c->n_reads, 0x7fffffff);
+    const int32_t *src = read_idx;
+    if (stage_idx) {
+        int32_t *h = (int32_t *)c->h_pin;
+        if (single) memcpy(h, read_idx, (size_t)p->nnz * 4);
+        else {
+            // regroup by draw size: the draws of a window are one block in both orders
+            std::vector<int64_t> start(p->n_windows + 1, 0);
+            for (int64_t w = 0; w < p->n_windows; ++w) start[w + 1] = start[w] + (p->h_doff[w + 1] - p->h_doff[w]) * p->h_n[w];
+            int64_t at = 0;
+            for (const SizeClass &k : p->classes)
+                for (int32_t w : k.win) {
+                    const int64_t cnt = (p->h_doff[w + 1] - p->h_doff[w]) * k.n;
+                    memcpy(h + at, read_idx + start[w], (size_t)cnt * 4);
+                    at += cnt;
+                }
+        }
+        src = h;
+    }
+    int64_t at = 0;
+    for (const SizeClass &k : p->classes) {
+        const int64_t cnt = k.n_draws * k.n;
+        LDPGTA_CUDA(cudaMemcpyAsync(k.d_idx, src + at, (size_t)cnt * 4, cudaMemcpyHostToDevice, c->stream));
+        k_sanitize_idx<<<(unsigned)std::min<int64_t>((cnt / 4 + 255) / 256 + 1, (int64_t)c->sm_count * 4), 256, 0, c->stream>>>(k.d_idx, cnt, lim, c->d_flag);
+        c->launches++;
+        at += cnt;
+    }
+    LDPGTA_CUDA(cudaMemcpyAsync(c->h_flag, c->d_flag, 4, cudaMemcpyDeviceToHost, c->stream));
+    if (int rc = evaluate_classes(c, p, kind, proportions, lik_out ? lik_pinned : nullptr)) return rc;
+    if (int rc = reduce_and_download(c, p, lik_out, lik_pinned, llr_out, window_mean_var, segment_partials, segment_stats)) return rc;
+    if (*c->h_flag) return fail_bad_index(c, read_idx, p->nnz);
+    return 0;
+}
+
+int ldpgta_bootstrap_stats_dev(ldpgta_ctx *c, int kind, uint64_t seed, const double *proportions, double *segment_partials_dev)
+{
+    if (int rc = check_plan(c, kind, proportions)) return rc;
+    LDPGTA_CUDA(cudaSetDevice(c->device));
+    WindowPlan *p = c->plan;
+    if (!p->has_windows) return fail(LDPGTA_E_STATE, "the resident plan has no window read lists");
+    for (const SizeClass &k : p->classes) {
+        SampleArgs sa;
+        memset(&sa, 0, sizeof sa);
+        sa.draw_off = k.d_doff; sa.win_off = p->d_woff; sa.win_reads = p->d_wreads; sa.cls_win = k.d_win;
+        sa.n_windows = k.n_windows; sa.n_draws = k.n_draws; sa.seed = seed + (uint64_t)k.n; sa.idx_out = k.d_idx;
+        if (int rc = launch_sample(c, k.n, sa)) return rc;
+    }
+    if (int rc = evaluate_classes(c, p, kind, proportions, nullptr)) return rc;
+    StatsShape sh;
+    if (int rc = stats_shape(c, p->n_windows, p->ncp, &sh)) return rc;
+    return stats_on_device(c, p->d_lik, p->d_doff, p->n_windows, p->n_draws, p->d_segoff, p->d_segcols, p->d_segfirst, p->n_segments,
+                           p->ncp, sh, nullptr, p->d_mv, p->d_runs, segment_partials_dev ? segment_partials_dev : p->d_partials,
+                           segment_partials_dev ? nullptr : p->d_stats);
+}
+
+int ldpgta_finish_segments_dev(ldpgta_ctx *c, const double *segment_partials_dev, double *segment_stats_dev)
+{
+    if (!c || !c->plan) return fail(LDPGTA_E_STATE, "no windows are resident: call ldpgta_set_windows first");
+    LDPGTA_CUDA(cudaSetDevice(c->device));
+    WindowPlan *p = c->plan;
+    k_finish_segments<<<(p->n_segments * 5 + 127) / 128, 128, 0, c->stream>>>(segment_partials_dev ? segment_partials_dev : p->d_partials,
+                                                                            p->d_segcols, p->d_segfirst, p->n_segments, p->ncp,
+                                                                            segment_stats_dev ? segment_stats_dev : p->d_stats);
+    c->launches++;
+    LDPGTA_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int ldpgta_kernel_timing(ldpgta_ctx *c, int enable)
+{
+    if (!c) return fail(LDPGTA_E_INVALID, "null context");
+    c->time_kernels = enable != 0;
+    c->t_used = 0;
+    return 0;
+}
+
+int ldpgta_kernel_times(ldpgta_ctx *c, double *ms_out, int max_entries)
+{
+    if (!c || (!ms_out && max_entries > 0)) return fail(LDPGTA_E_INVALID, "bad arguments");
+    LDPGTA_CUDA(cudaSetDevice(c->device));
+    LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
+    const int n = (int)(c->t_used / 2);
+    for (int i = 0; i < n && i < max_entries; ++i) {
+        float ms = 0.f;
+        LDPGTA_CUDA(cudaEventElapsedTime(&ms, c->t_ev[2 * i], c->t_ev[2 * i + 1]));
+        ms_out[i] = (double)ms;
+    }
+    c->t_used = 0;
+    return n;
+}
+
+int ldpgta_plan_info(const ldpgta_ctx *c, int64_t *out)
+{
+    if (!c || !out) return fail(LDPGTA_E_INVALID, "null argument");
+    if (!c->plan) return fail(LDPGTA_E_STATE, "no windows are resident: call ldpgta_set_windows first");
+    const WindowPlan *p = c->plan;
+    out[0] = p->n_windows; out[1] = p->n_draws; out[2] = p->n_segments; out[3] = p->ncp;
+    out[4] = (int64_t)p->classes.size(); out[5] = p->nnz;
+    out[6] = (int64_t)(uintptr_t)p->d_lik; out[7] = (int64_t)(uintptr_t)p->d_mv;
+    out[8] = (int64_t)(uintptr_t)p->d_partials; out[9] = (int64_t)(uintptr_t)p->d_stats;
+    return 0;
+}
+
+int ldpgta_window_stats(ldpgta_ctx *c, const double *lik, const int64_t *window_offsets, int64_t n_windows, int n_cols,
+                        double *llr_out, double *window_mean_var, double *chrom_partials)
+{
+    if (!c || !lik || !window_offsets || n_windows < 0 || n_cols < 0) return fail(LDPGTA_E_INVALID, "bad arguments");
+    LDPGTA_CUDA(cudaSetDevice(c->device));
+    if (window_offsets[0] != 0) return fail(LDPGTA_E_INVALID, "window_offsets must start at 0");
+    const int64_t n_draws = window_offsets[n_windows];
+    for (int64_t w = 0; w < n_windows; ++w) {
+        const int64_t k = window_offsets[w + 1] - window_offsets[w];
+        if (k < 1) return fail(LDPGTA_E_INVALID, "window %lld has no draws", (long long)w);
+        if (k < n_cols) return fail(LDPGTA_E_INVALID, "window %lld has %lld draws < n_cols=%d", (long long)w, (long long)k, n_cols);
+    }
+    StatsShape sh;
+    if (int rc = stats_shape(c, n_windows, n_cols, &sh)) return rc;
+    const int stride = n_cols + 3;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += pad256(bytes); return o; };
+    const size_t o_lik = take((size_t)n_draws * 32), o_seg = take(16), o_meta = take(8), o_mv = take((size_t)n_windows * 80);
+    const size_t o_runs = take((size_t)(sh.n_chunks + 1) * 5 * stride * 8), o_cp = take((size_t)5 * stride * 8);
+    if (int rc = ensure_dev(c, off)) return rc;
+    // the LLRs and the window offsets stay on the device for ldpgta_bin_stats
+    c->llr_draws = c->llr_windows = -1;
+    if (int rc = ensure_own(&c->d_llr, &c->d_llr_bytes, (size_t)n_draws * 40 + 16)) return rc;
+    if (int rc = ensure_own(&c->d_llr_off, &c->d_llr_off_bytes, (size_t)(n_windows + 1) * 8)) return rc;
+    char *base = (char *)c->d_buf;
+    double *d_lik = (double *)(base + o_lik), *d_mv = (double *)(base + o_mv), *d_runs = (double *)(base + o_runs), *d_cp = (double *)(base + o_cp);
+    int64_t *d_seg = (int64_t *)(base + o_seg);
+    int32_t *d_meta = (int32_t *)(base + o_meta);
+    const int64_t h_seg[2] = {0, n_windows};
+    const int32_t h_meta[2] = {n_cols, n_windows ? (int32_t)(window_offsets[1] - window_offsets[0]) : 0};
+    if (n_draws) LDPGTA_CUDA(cudaMemcpyAsync(d_lik, lik, (size_t)n_draws * 32, cudaMemcpyHostToDevice, c->stream));
+    LDPGTA_CUDA(cudaMemcpyAsync(c->d_llr_off, window_offsets, (size_t)(n_windows + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    LDPGTA_CUDA(cudaMemcpyAsync(d_seg, h_seg, 16, cudaMemcpyHostToDevice, c->stream));
+    LDPGTA_CUDA(cudaMemcpyAsync(d_meta, h_meta, 8, cudaMemcpyHostToDevice, c->stream));
+    if (int rc = stats_on_device(c, d_lik, c->d_llr_off, n_windows, n_draws, d_seg, d_meta, d_meta + 1, 1, n_cols, sh, c->d_llr, d_mv,
+                                 d_runs, d_cp, nullptr))
+        return rc;
+    if (llr_out && n_draws) LDPGTA_CUDA(cudaMemcpyAsync(llr_out, c->d_llr, (size_t)n_draws * 40, cudaMemcpyDeviceToHost, c->stream));
+    if (window_mean_var && n_windows) LDPGTA_CUDA(cudaMemcpyAsync(window_mean_var, d_mv, (size_t)n_windows * 80, cudaMemcpyDeviceToHost, c->stream));
+    if (chrom_partials) LDPGTA_CUDA(cudaMemcpyAsync(chrom_partials, d_cp, (size_t)5 * stride * 8, cudaMemcpyDeviceToHost, c->stream));
+    LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
+    c->llr_draws = n_draws;
+    c->llr_windows = n_windows;
+    return 0;
+}
+
+}  // extern "C"

@@ -11,6 +11,10 @@
 #include "../../include/ldpgta.h"
 
 namespace ldpgta {
+struct WindowPlan;
+}
+
+namespace ldpgta {
 
 constexpr int MAXG = LDPGTA_MAX_GROUPS;
 constexpr int MAXN = LDPGTA_MAX_READS_PER_DRAW;
@@ -227,6 +231,13 @@ struct ldpgta_ctx {
     double *etab_scratch = nullptr;           // e(S) tables of the distant model when they do not fit shared memory
     size_t etab_scratch_bytes = 0;
 
+    // windows + bootstrap plan made resident by ldpgta_set_windows (bootstrap_api.cu)
+    ldpgta::WindowPlan *plan = nullptr;
+    // optional CUDA-event brackets around the draw kernels of the resident pipeline (ldpgta_kernel_timing)
+    bool time_kernels = false;
+    std::vector<cudaEvent_t> t_ev;      // pairs (start, stop), reused
+    size_t t_used = 0;
+
     int64_t launches = 0;
 };
 
@@ -251,6 +262,35 @@ inline PanelView make_view(const ldpgta_ctx *c, const double *proportions)
 
 struct SmallArgs;
 struct GeneralArgs;
+struct SampleArgs;
+struct WindowPlan;
+
+// helpers of ldpgta_api.cu shared with bootstrap_api.cu
+int ensure_dev(ldpgta_ctx *c, size_t bytes);
+int ensure_pin(ldpgta_ctx *c, size_t bytes);
+int ensure_pipeline(ldpgta_ctx *c, int n_chunks);
+bool is_page_locked(const void *p);
+int check_kind(const ldpgta_ctx *c, int kind, const double *proportions);
+int check_uniform_size(int kind, int64_t n);
+int fail_bad_index(const ldpgta_ctx *c, const int32_t *read_idx, int64_t nnz);
+// draws of one size, device-resident indices and outputs (dispatch to k_small / k_mid / k_lanes / k_general)
+int run_uniform(ldpgta_ctx *c, int kind, int n, const int32_t *idx_dev, int64_t n_draws, const int64_t *pos_dev,
+                const double *proportions, double *out_dev, uint32_t *counts_dev, bool force_general = false,
+                const PanelView *override_view = nullptr);
+int launch_sample(ldpgta_ctx *c, int n, const SampleArgs &a);      // pick_reads on the device, n reads per draw
+void free_window_plan(ldpgta_ctx *c);
+
+template <class T>
+inline int ensure_own(T **ptr, size_t *have, size_t bytes)
+{
+    if (*have >= bytes) return 0;
+    if (*ptr) LDPGTA_CUDA(cudaFree(*ptr));
+    *ptr = nullptr; *have = 0;
+    bytes = bytes + bytes / 4 + 4096;
+    LDPGTA_CUDA(cudaMalloc((void **)ptr, bytes));
+    *have = bytes;
+    return 0;
+}
 // kernel launchers, one translation unit each (small.cu, general.cu)
 int launch_small(ldpgta_ctx *c, SmallArgs &a, int n, int kind);
 int make_read_mask_tmap(ldpgta_ctx *c, int g);

@@ -6,7 +6,7 @@ namespace ldpgta {
 
 // Pads caller rows [n_rows][words] to [n_rows][wp] and complements REF alleles inside the
 // group's N bits (hap ^ (2^N - 1), HOMOGENOUES_MODELS.py:87,94).
-__global__ void k_pack_rows(const uint64_t *__restrict__ src, const uint8_t *__restrict__ complement,
+static __global__ void k_pack_rows(const uint64_t *__restrict__ src, const uint8_t *__restrict__ complement,
                             uint64_t *__restrict__ dst, int64_t n_rows, int words, int wp, uint32_t nhap)
 {
     const int64_t total = n_rows * wp;
@@ -27,7 +27,7 @@ __global__ void k_pack_rows(const uint64_t *__restrict__ src, const uint8_t *__r
 
 // allele row a = panel row legend_idx[a], complemented inside the group's N bits for REF alleles
 // (build_hap_dict, HOMOGENOUES_MODELS.py:84-94, as a gather from the resident panel)
-__global__ void k_gather_rows(const uint64_t *__restrict__ panel, const int64_t *__restrict__ legend_idx,
+static __global__ void k_gather_rows(const uint64_t *__restrict__ panel, const int64_t *__restrict__ legend_idx,
                               const uint8_t *__restrict__ complement, uint64_t *__restrict__ dst, int64_t n_alleles, int wp,
                               uint32_t nhap)
 {
@@ -47,7 +47,7 @@ __global__ void k_gather_rows(const uint64_t *__restrict__ panel, const int64_t 
 
 // mask[r] = AND of allele rows allele_idx[off[r] .. off[r+1])  (build_intrenal_hap_dict,
 // HOMOGENOUES_MODELS.py:112-123, once per read instead of once per draw)
-__global__ void k_build_read_masks(const uint64_t *__restrict__ rows, const int32_t *__restrict__ allele_idx,
+static __global__ void k_build_read_masks(const uint64_t *__restrict__ rows, const int32_t *__restrict__ allele_idx,
                                    const int64_t *__restrict__ off, int64_t n_reads, int wp, uint64_t *__restrict__ out)
 {
     const int slots = wp >> 1;
@@ -69,14 +69,14 @@ __global__ void k_build_read_masks(const uint64_t *__restrict__ rows, const int3
 // norm[x] = x / nhap with IEEE division: joint_frequencies_combo(normalize=True) divides every count
 // by N (HOMOGENOUES_MODELS.py:160-161); counts are integers in 0..N, so a table is exact and turns
 // 15 float64 divisions per draw into 15 cached loads.
-__global__ void k_norm_table(double *__restrict__ out, uint32_t nhap)
+static __global__ void k_norm_table(double *__restrict__ out, uint32_t nhap)
 {
     for (uint32_t x = blockIdx.x * blockDim.x + threadIdx.x; x <= nhap; x += gridDim.x * blockDim.x)
         out[x] = (double)x / (double)nhap;
 }
 
 // popcount of every row (the single-read joint frequencies), one warp per row
-__global__ void k_row_popc(const uint64_t *__restrict__ rows, int64_t n_rows, int wp, uint32_t *__restrict__ out)
+static __global__ void k_row_popc(const uint64_t *__restrict__ rows, int64_t n_rows, int wp, uint32_t *__restrict__ out)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -110,7 +110,7 @@ struct ScoreArgs {
     int32_t *out;                   // score per read; -1 = more than 12 qualifying SNPs (not evaluated)
 };
 
-__global__ void k_read_scores(const ScoreArgs a)
+static __global__ void k_read_scores(const ScoreArgs a)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -175,18 +175,8 @@ __device__ __forceinline__ double llr(double y, double x)
 }
 
 // pairs of statistics() (ANEUPLOIDY_TEST.py:298): indices into (monosomy, disomy, SPH, BPH)
-__device__ __constant__ int c_pair_num[5] = {3, 1, 3, 1, 2};
-__device__ __constant__ int c_pair_den[5] = {2, 0, 1, 2, 0};
-
-__global__ void k_llr(const double *__restrict__ lik, int64_t n_draws, double *__restrict__ out)
-{
-    for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < n_draws; d += (int64_t)gridDim.x * blockDim.x) {
-        const double2 a = reinterpret_cast<const double2 *>(lik)[2 * d], b = reinterpret_cast<const double2 *>(lik)[2 * d + 1];
-        const double v[4] = {a.x, a.y, b.x, b.y};
-#pragma unroll
-        for (int p = 0; p < 5; ++p) out[p * n_draws + d] = llr(v[c_pair_num[p]], v[c_pair_den[p]]);
-    }
-}
+static __device__ __constant__ int c_pair_num[5] = {3, 1, 3, 1, 2};
+static __device__ __constant__ int c_pair_den[5] = {2, 0, 1, 2, 0};
 
 // error-free accumulation (Neumaier) so that window means match the reference's
 // exact-rational statistics.mean/variance (ANEUPLOIDY_TEST.py:51-56) to the last bits
@@ -212,67 +202,164 @@ __device__ __forceinline__ double warp_sum_comp(Comp a)
     return a.value();
 }
 
-// one warp per (pair, window): mean and sample variance of the window's LLRs
-__global__ void k_window_mean_var(const double *__restrict__ llrs, const int64_t *__restrict__ woff, int64_t n_windows,
-                                  int64_t n_draws, double *__restrict__ mean_var)
+// ---- statistics() fused: likelihoods -> LLRs -> window mean / variance -> segment partial sums, in one pass -------
+// A segment is one (embryo, chromosome): a run of consecutive windows whose LLRs statistics() (ANEUPLOIDY_TEST.py:289-325)
+// reduces together.  One warp walks a chunk of `cw` consecutive windows; lane l owns the draws l, l+32, ... of a window
+// (= columns of the reference's zip(*A), :73) and keeps the column sums of the run in its slice of shared memory.  A run
+// ends at a segment border or at the chunk's end and is flushed to slot (chunk + segment) of `runs`, so the reduction over
+// runs (k_segment_partials) needs neither atomics nor flags and adds in a fixed order: results are bit-reproducible.
+// Window mean = compensated sum / count; window variance by Welford updates per lane merged across lanes with Chan's
+// formula (single pass, no cancellation) -- statistics.mean / statistics.variance of :51-56 are exact-rational.
+struct StatsArgs {
+    const double *lik;         // [n_draws][4] monosomy, disomy, SPH, BPH
+    const int64_t *doff;       // [n_windows + 1] draws of window w = [doff[w], doff[w+1])
+    const int64_t *seg_off;    // [n_segments + 1] windows of segment s = [seg_off[s], seg_off[s+1])
+    int64_t n_windows, n_draws;
+    int n_segments;
+    int ncp;                   // column capacity: sums are kept for the first ncp draws of a window
+    int cw;                    // windows per chunk
+    double *llr;               // optional [5][n_draws] per-draw LLRs
+    double *mean_var;          // [5][n_windows][2]
+    double *runs;              // [n_chunks + n_segments][5][ncp + 3]
+};
+
+__device__ __forceinline__ int segment_of(const int64_t *seg_off, int n_segments, int64_t w)
 {
-    const int lane = threadIdx.x & 31;
-    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (gw >= 5 * n_windows) return;
-    const int p = (int)(gw / n_windows);
-    const int64_t w = gw - (int64_t)p * n_windows;
-    const int64_t b = woff[w], e = woff[w + 1];
-    const double *x = llrs + (int64_t)p * n_draws;
-    Comp acc = {0.0, 0.0};
-    for (int64_t i = b + lane; i < e; i += 32) acc.add(x[i]);
-    const double cnt = (double)(e - b);
-    const double mean = warp_sum_comp(acc) / cnt;
-    Comp sq = {0.0, 0.0};
-    for (int64_t i = b + lane; i < e; i += 32) { const double d = x[i] - mean; sq.add(d * d); }
-    const double ss = warp_sum_comp(sq);
-    if (lane == 0) {
-        mean_var[2 * gw] = mean;
-        mean_var[2 * gw + 1] = (e - b > 1) ? ss / (cnt - 1.0) : nan("");
+    int lo = 0, hi = n_segments;                                   // largest s with seg_off[s] <= w
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (seg_off[mid] <= w) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+static __global__ void k_llr_window_stats(const StatsArgs a)
+{
+    extern __shared__ double sh_cols[];                            // [warps][5][ncp]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    double *cols = sh_cols + (size_t)warp * 5 * a.ncp;
+    const int64_t n_chunks = (a.n_windows + a.cw - 1) / a.cw;
+    const int stride = a.ncp + 3;
+    for (int64_t chunk = (int64_t)blockIdx.x * wpb + warp; chunk < n_chunks; chunk += (int64_t)gridDim.x * wpb) {
+        const int64_t w0 = chunk * a.cw, w1 = min(w0 + a.cw, a.n_windows);
+        int seg = segment_of(a.seg_off, a.n_segments, w0);
+        int64_t seg_end = a.seg_off[seg + 1];
+        for (int i = lane; i < 5 * a.ncp; i += 32) cols[i] = 0.0;
+        Comp total[5];
+        double n_win = 0.0, n_neg[5];
+#pragma unroll
+        for (int p = 0; p < 5; ++p) { total[p].s = total[p].c = 0.0; n_neg[p] = 0.0; }
+        __syncwarp();
+        for (int64_t w = w0; w < w1; ++w) {
+            const int64_t b = a.doff[w], e = a.doff[w + 1];
+            Comp sum[5];
+            double cnt = 0.0, mean[5], m2[5];
+#pragma unroll
+            for (int p = 0; p < 5; ++p) { sum[p].s = sum[p].c = 0.0; mean[p] = 0.0; m2[p] = 0.0; }
+            for (int64_t i = b + lane; i < e; i += 32) {
+                const double2 u = __ldg(reinterpret_cast<const double2 *>(a.lik) + 2 * i), v = __ldg(reinterpret_cast<const double2 *>(a.lik) + 2 * i + 1);
+                const double lk[4] = {u.x, u.y, v.x, v.y};
+                cnt += 1.0;
+                const int64_t col = i - b;
+#pragma unroll
+                for (int p = 0; p < 5; ++p) {
+                    const double x = llr(lk[c_pair_num[p]], lk[c_pair_den[p]]);
+                    if (a.llr) a.llr[(int64_t)p * a.n_draws + i] = x;
+                    sum[p].add(x);
+                    const double d = x - mean[p];
+                    mean[p] += d / cnt;
+                    m2[p] += d * (x - mean[p]);
+                    if (col < a.ncp) cols[p * a.ncp + col] += x;
+                }
+            }
+            const double n_all = (double)(e - b);
+#pragma unroll
+            for (int p = 0; p < 5; ++p) {
+                // Chan et al.: merge (count, mean, M2) of lane pairs
+                double na = cnt, ma = mean[p], qa = m2[p];
+#pragma unroll
+                for (int msk = 16; msk; msk >>= 1) {
+                    const double nb = __shfl_xor_sync(0xffffffffu, na, msk), mb = __shfl_xor_sync(0xffffffffu, ma, msk),
+                                 qb = __shfl_xor_sync(0xffffffffu, qa, msk);
+                    const double nn = na + nb;
+                    if (nn > 0.0) {
+                        // symmetric in (a, b) so that both lanes of a pair hold the same result
+                        const double lo_n = (lane & msk) ? nb : na, hi_n = (lane & msk) ? na : nb;
+                        const double lo_m = (lane & msk) ? mb : ma, hi_m = (lane & msk) ? ma : mb;
+                        const double lo_q = (lane & msk) ? qb : qa, hi_q = (lane & msk) ? qa : qb;
+                        const double delta = hi_m - lo_m;
+                        ma = lo_m + delta * (hi_n / nn);
+                        qa = (lo_q + hi_q) + delta * delta * (lo_n * hi_n / nn);
+                    }
+                    na = nn;
+                }
+                const double s = warp_sum_comp(sum[p]);
+                const double m = s / n_all;
+                total[p].add(s);
+                if (m < 0.0) n_neg[p] += 1.0;
+                if (lane == 0) {
+                    double *mv = a.mean_var + 2 * ((int64_t)p * a.n_windows + w);
+                    mv[0] = m;
+                    mv[1] = (e - b > 1) ? qa / (n_all - 1.0) : nan("");
+                }
+            }
+            n_win += 1.0;
+            if (w + 1 == seg_end || w + 1 == w1) {
+                // end of the run: flush to slot (chunk + segment)
+                __syncwarp();
+                double *out = a.runs + (chunk + seg) * (int64_t)(5 * stride);
+#pragma unroll
+                for (int p = 0; p < 5; ++p) {
+                    if (lane == 0) {
+                        out[p * stride + 0] = total[p].value();
+                        out[p * stride + 1] = n_win;
+                        out[p * stride + 2] = n_neg[p];
+                    }
+                    for (int i = lane; i < a.ncp; i += 32) { out[p * stride + 3 + i] = cols[p * a.ncp + i]; cols[p * a.ncp + i] = 0.0; }
+                    total[p].s = total[p].c = 0.0; n_neg[p] = 0.0;
+                }
+                n_win = 0.0;
+                __syncwarp();
+                if (w + 1 == seg_end && w + 1 < w1)
+                    do { ++seg; seg_end = a.seg_off[seg + 1]; } while (seg_end <= w + 1 && seg + 1 < a.n_segments);   // skips empty segments
+            }
+        }
     }
 }
 
-// one block per (pair, column): deterministic sums over windows.
-//   column 0: sum_w sum_i x_wi ; column 1: #windows ; column 2: #windows with mean < 0 ;
-//   column 3+i: sum_w x_wi (i < n_cols)
-__global__ void k_chrom_partials(const double *__restrict__ llrs, const int64_t *__restrict__ woff, int64_t n_windows,
-                                 int64_t n_draws, const double *__restrict__ mean_var, int n_cols,
-                                 double *__restrict__ partials)
+// partials[s][p][0..ncp+3) = sum over the runs of segment s (fixed order, compensated); columns at or beyond the
+// segment's n_cols = zip truncation of ANEUPLOIDY_TEST.py:73 are zero.  One block per (segment, pair).
+static __global__ void k_segment_partials(const double *__restrict__ runs, const int64_t *__restrict__ seg_off, const int32_t *__restrict__ seg_cols,
+                                   int ncp, int cw, double *__restrict__ partials)
 {
-    __shared__ double sh_s[32], sh_c[32];
-    const int p = blockIdx.y, col = blockIdx.x;
-    const double *x = llrs + (int64_t)p * n_draws;
-    Comp acc = {0.0, 0.0};
-    if (col == 0) {
-        for (int64_t i = threadIdx.x; i < n_draws; i += blockDim.x) acc.add(x[i]);
-    } else if (col == 1) {
-        if (threadIdx.x == 0) acc.add((double)n_windows);
-    } else if (col == 2) {
-        for (int64_t w = threadIdx.x; w < n_windows; w += blockDim.x)
-            if (mean_var[2 * ((int64_t)p * n_windows + w)] < 0.0) acc.add(1.0);
-    } else {
-        const int i = col - 3;
-        for (int64_t w = threadIdx.x; w < n_windows; w += blockDim.x) acc.add(x[woff[w] + i]);
+    const int s = blockIdx.x, p = blockIdx.y, stride = ncp + 3;
+    const int64_t lo = seg_off[s], hi = seg_off[s + 1];
+    const int ncols = seg_cols[s];
+    double *out = partials + ((int64_t)s * 5 + p) * stride;
+    for (int col = threadIdx.x; col < stride; col += blockDim.x) {
+        Comp acc = {0.0, 0.0};
+        if (hi > lo && col < 3 + ncols)
+            for (int64_t chunk = lo / cw; chunk <= (hi - 1) / cw; ++chunk) acc.add(runs[((chunk + s) * 5 + p) * (int64_t)stride + col]);
+        out[col] = acc.value();
     }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // combine compensated partials: first within the warp, then across warps
-#pragma unroll
-    for (int m = 16; m; m >>= 1) {
-        const double os = __shfl_xor_sync(0xffffffffu, acc.s, m), oc = __shfl_xor_sync(0xffffffffu, acc.c, m);
-        acc.add(os);
-        acc.c += oc;
-    }
-    if (lane == 0) { sh_s[warp] = acc.s; sh_c[warp] = acc.c; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        Comp t = {0.0, 0.0};
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { t.add(sh_s[w]); t.c += sh_c[w]; }
-        partials[(int64_t)p * (n_cols + 3) + col] = t.value();
-    }
+}
+
+// mean_and_std_of_mean_of_rnd_var (ANEUPLOIDY_TEST.py:65-76) + fraction_of_negative_LLRs (:313) per (segment, pair) from
+// (summed) partials, the operations of ldpgta_finish_chromosome in the same order.  out[s][p][3].
+static __global__ void k_finish_segments(const double *__restrict__ partials, const int32_t *__restrict__ seg_cols,
+                                  const int32_t *__restrict__ seg_first, int n_segments, int ncp, double *__restrict__ out)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_segments * 5) return;
+    const int s = t / 5;
+    const double *q = partials + (int64_t)t * (ncp + 3);
+    const double M = q[1], N = (double)seg_first[s];
+    const double mu = q[0] / N;
+    double ss = 0.0;
+    for (int i = 0; i < seg_cols[s]; ++i) { const double d = q[3 + i] - mu; ss += d * d; }
+    out[3 * t + 0] = mu / M;
+    out[3 * t + 1] = sqrt(ss / (N - 1.0)) / M;
+    out[3 * t + 2] = q[2] / M;
 }
 
 // binning() of PLOT_PANEL.py:121-144 / BALANCED_ROC_CURVE.py:131-154: one block per (series, bin).  A bin is a run
@@ -280,7 +367,7 @@ __global__ void k_chrom_partials(const double *__restrict__ llrs, const int64_t 
 //   N = draws of the bin's FIRST window, M = b1 - b0, mu = (sum of all values) / N,
 //   std = sqrt(sum_i (column_i - mu)^2 / (N - 1)) / M over the columns every window has (zip truncation), mean = mu / M.
 // x[n_series][n_draws]; out[n_series][n_bins][2] = (mean, std).
-__global__ void k_bin_stats(const double *__restrict__ x, int64_t n_draws, const int64_t *__restrict__ woff,
+static __global__ void k_bin_stats(const double *__restrict__ x, int64_t n_draws, const int64_t *__restrict__ woff,
                             const int64_t *__restrict__ ranges, int64_t n_bins, double *__restrict__ out)
 {
     __shared__ double sh_s[32], sh_c[32];
@@ -343,7 +430,7 @@ __global__ void k_bin_stats(const double *__restrict__ x, int64_t n_draws, const
 
 // validation of a batch's read indices on the device (the host path used to scan them before the first copy):
 // an index outside [0, n_reads) is replaced by 0 and reported through *flag, the caller then fails the whole call.
-__global__ void k_sanitize_idx(int32_t *__restrict__ idx, int64_t count, uint32_t n_reads, unsigned int *__restrict__ flag)
+static __global__ void k_sanitize_idx(int32_t *__restrict__ idx, int64_t count, uint32_t n_reads, unsigned int *__restrict__ flag)
 {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t quads = ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) ? count / 4 : 0;
@@ -381,21 +468,34 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 
 // One thread per draw: K distinct reads of the draw's window, uniformly over K-subsets (Floyd's algorithm; for
 // i = 0..K-1: t uniform in [0, R-K+i], taken unless already chosen, else R-K+i), written as read-mask rows.
-// Draw d belongs to the window w with draw_off[w] <= d < draw_off[w+1]; its reads are win_reads[win_off[w] ...].
+// Draw d belongs to the window j with draw_off[j] <= d < draw_off[j+1] of the draw-size class being sampled; that is window
+// w = cls_win[j] of the sample (identity when cls_win is null), whose reads are win_reads[win_off[w] ...] (or simply the
+// rows win_off[w] ... when win_reads is null: read masks stored window by window).
 // The j-th random integer of draw d is mulhi64(x, bound) with x = 64 bits of Philox(counter = (d, j/2), key = seed).
+struct SampleArgs {
+    const int64_t *draw_off;     // [n_windows + 1] draw offsets of the class
+    const int64_t *win_off;      // read-list offsets of the sample's windows
+    const int32_t *win_reads;    // or nullptr
+    const int32_t *cls_win;      // or nullptr
+    int64_t n_windows, n_draws;
+    uint64_t seed;
+    const uint64_t *seed_dev;    // overrides seed when set (a captured launch reads the seed of the replay)
+    int32_t *idx_out;            // [n_draws][K]
+};
+
 template <int K>
-__global__ void k_sample_draws(const int64_t *__restrict__ draw_off, const int64_t *__restrict__ win_off,
-                               const int32_t *__restrict__ win_reads, int64_t n_windows, int64_t n_draws, uint64_t seed,
-                               int32_t *__restrict__ idx_out)
+static __global__ void k_sample_draws(const SampleArgs a)
 {
-    for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < n_draws; d += (int64_t)gridDim.x * blockDim.x) {
-        int64_t lo = 0, hi = n_windows;                    // upper_bound(draw_off, d) - 1
+    const uint64_t seed = a.seed_dev ? *a.seed_dev : a.seed;
+    for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < a.n_draws; d += (int64_t)gridDim.x * blockDim.x) {
+        int64_t lo = 0, hi = a.n_windows;                    // upper_bound(draw_off, d) - 1
         while (hi - lo > 1) {
             const int64_t mid = (lo + hi) >> 1;
-            if (draw_off[mid] <= d) lo = mid; else hi = mid;
+            if (a.draw_off[mid] <= d) lo = mid; else hi = mid;
         }
-        const int64_t base = win_off[lo];
-        const uint32_t R = (uint32_t)(win_off[lo + 1] - base);
+        const int64_t w = a.cls_win ? a.cls_win[lo] : lo;
+        const int64_t base = a.win_off[w];
+        const uint32_t R = (uint32_t)(a.win_off[w + 1] - base);
         uint32_t pick[K];
         uint32_t rnd[4];
 #pragma unroll
@@ -411,7 +511,7 @@ __global__ void k_sample_draws(const int64_t *__restrict__ draw_off, const int64
             pick[i] = dup ? top : t;
         }
 #pragma unroll
-        for (int i = 0; i < K; ++i) idx_out[d * K + i] = win_reads[base + pick[i]];
+        for (int i = 0; i < K; ++i) a.idx_out[d * K + i] = a.win_reads ? a.win_reads[base + pick[i]] : (int32_t)(base + pick[i]);
     }
 }
 

@@ -25,7 +25,7 @@ int fail(int code, const char *fmt, ...)
     return code;
 }
 
-static int ensure_dev(ldpgta_ctx *c, size_t bytes)
+int ensure_dev(ldpgta_ctx *c, size_t bytes)
 {
     if (c->d_buf_bytes >= bytes) return 0;
     if (c->d_buf) LDPGTA_CUDA(cudaFree(c->d_buf));
@@ -36,19 +36,7 @@ static int ensure_dev(ldpgta_ctx *c, size_t bytes)
     return 0;
 }
 
-template <class T>
-static int ensure_own(T **ptr, size_t *have, size_t bytes)
-{
-    if (*have >= bytes) return 0;
-    if (*ptr) LDPGTA_CUDA(cudaFree(*ptr));
-    *ptr = nullptr; *have = 0;
-    bytes = bytes + bytes / 4 + 4096;
-    LDPGTA_CUDA(cudaMalloc((void **)ptr, bytes));
-    *have = bytes;
-    return 0;
-}
-
-static int ensure_pin(ldpgta_ctx *c, size_t bytes)
+int ensure_pin(ldpgta_ctx *c, size_t bytes)
 {
     if (c->h_pin_bytes >= bytes) return 0;
     if (c->h_pin) LDPGTA_CUDA(cudaFreeHost(c->h_pin));
@@ -60,7 +48,7 @@ static int ensure_pin(ldpgta_ctx *c, size_t bytes)
 }
 
 // copy streams and per-chunk events of the pipelined host path
-static int ensure_pipeline(ldpgta_ctx *c, int n_chunks)
+int ensure_pipeline(ldpgta_ctx *c, int n_chunks)
 {
     if (!c->s_in) LDPGTA_CUDA(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
     if (!c->s_out) LDPGTA_CUDA(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
@@ -82,7 +70,7 @@ static int ensure_pipeline(ldpgta_ctx *c, int n_chunks)
 }
 
 // page-locked (or managed) host memory: usable by asynchronous copies without staging and readable on the host
-static bool is_page_locked(const void *p)
+bool is_page_locked(const void *p)
 {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -104,7 +92,7 @@ static int refresh_popc(ldpgta_ctx *c, int g)
     return make_read_mask_tmap(c, g);
 }
 
-static int check_kind(const ldpgta_ctx *c, int kind, const double *proportions)
+int check_kind(const ldpgta_ctx *c, int kind, const double *proportions)
 {
     if (kind == LDPGTA_HOMOGENEOUS && c->G != 1)
         return fail(LDPGTA_E_INVALID, "homogeneous model needs exactly one reference-panel group, context has %d", c->G);
@@ -122,9 +110,9 @@ static int check_kind(const ldpgta_ctx *c, int kind, const double *proportions)
 // ------------------------------------------------------------------ launchers
 
 // draws of one size, device-resident indices and outputs
-static int run_uniform(ldpgta_ctx *c, int kind, int n, const int32_t *idx_dev, int64_t n_draws, const int64_t *pos_dev,
-                       const double *proportions, double *out_dev, uint32_t *counts_dev, bool force_general = false,
-                       const PanelView *override_view = nullptr)
+int run_uniform(ldpgta_ctx *c, int kind, int n, const int32_t *idx_dev, int64_t n_draws, const int64_t *pos_dev,
+                const double *proportions, double *out_dev, uint32_t *counts_dev, bool force_general,
+                const PanelView *override_view)
 {
     if (n_draws == 0) return 0;
     if (n < 2 || n > MAXN) return fail(LDPGTA_E_UNSUPPORTED, "draws of %d reads are outside the supported range 2..%d", n, MAXN);
@@ -160,7 +148,7 @@ static int run_uniform(ldpgta_ctx *c, int kind, int n, const int32_t *idx_dev, i
 }
 
 // message for the first read index outside the table (slow path, only after a failed validation)
-static int fail_bad_index(const ldpgta_ctx *c, const int32_t *read_idx, int64_t nnz)
+int fail_bad_index(const ldpgta_ctx *c, const int32_t *read_idx, int64_t nnz)
 {
     for (int64_t k = 0; k < nnz; ++k)
         if (read_idx[k] < 0 || read_idx[k] >= c->n_reads)
@@ -291,16 +279,7 @@ static int run_pipelined(ldpgta_ctx *c, int kind, int n0, const int32_t *read_id
     return 0;
 }
 
-template <int K>
-static void launch_sample(ldpgta_ctx *c, const int64_t *d_doff, const int64_t *d_woff, const int32_t *d_wreads, int64_t n_windows,
-                          int64_t n_draws, uint64_t seed, int32_t *d_idx)
-{
-    const unsigned blocks = (unsigned)std::min<int64_t>((n_draws + 127) / 128, (int64_t)c->sm_count * 16);
-    k_sample_draws<K><<<blocks, 128, 0, c->stream>>>(d_doff, d_woff, d_wreads, n_windows, n_draws, seed, d_idx);
-    c->launches++;
-}
-
-static int check_uniform_size(int kind, int64_t n)
+int check_uniform_size(int kind, int64_t n)
 {
     if (n < 2 || n > MAXN)
         return fail(LDPGTA_E_UNSUPPORTED, "draw 0 has %lld reads, supported range is 2..%d", (long long)n, MAXN);
@@ -365,6 +344,7 @@ int ldpgta_destroy(ldpgta_ctx *c)
     if (!c) return 0;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    free_window_plan(c);
     for (int g = 0; g < c->G; ++g) {
         if (c->allele_rows[g]) cudaFree(c->allele_rows[g]);
         if (c->read_masks[g] && c->masks_owned[g]) cudaFree(c->read_masks[g]);
@@ -389,6 +369,7 @@ int ldpgta_destroy(ldpgta_ctx *c)
     if (c->s_out) cudaStreamDestroy(c->s_out);
     for (cudaEvent_t e : c->ev_in) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_k) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->t_ev) cudaEventDestroy(e);
     delete c;
     return 0;
 }
@@ -834,11 +815,12 @@ int ldpgta_bootstrap_uniform(ldpgta_ctx *c, int kind, int n, const int64_t *wind
     LDPGTA_CUDA(cudaMemcpyAsync(d_woff, window_offsets, (size_t)(n_windows + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     LDPGTA_CUDA(cudaMemcpyAsync(d_doff, draw_offsets, (size_t)(n_windows + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     LDPGTA_CUDA(cudaMemcpyAsync(d_wreads, window_reads, (size_t)n_wreads * 4, cudaMemcpyHostToDevice, c->stream));
-    switch (n) {
-#define LDPGTA_K(K_) case K_: launch_sample<K_>(c, d_doff, d_woff, d_wreads, n_windows, n_draws, seed, d_idx); break;
-        LDPGTA_K(2) LDPGTA_K(3) LDPGTA_K(4) LDPGTA_K(5) LDPGTA_K(6) LDPGTA_K(7) LDPGTA_K(8) LDPGTA_K(9) LDPGTA_K(10)
-        LDPGTA_K(11) LDPGTA_K(12) LDPGTA_K(13) LDPGTA_K(14) LDPGTA_K(15) LDPGTA_K(16) LDPGTA_K(17) LDPGTA_K(18)
-#undef LDPGTA_K
+    {
+        SampleArgs sa;
+        memset(&sa, 0, sizeof sa);
+        sa.draw_off = d_doff; sa.win_off = d_woff; sa.win_reads = d_wreads; sa.n_windows = n_windows; sa.n_draws = n_draws;
+        sa.seed = seed; sa.idx_out = d_idx;
+        launch_sample(c, n, sa);
     }
     LDPGTA_CUDA(cudaGetLastError());
     // kernel and download in chunks: the copy of chunk i runs under the kernel of chunk i + 1
@@ -965,54 +947,6 @@ int ldpgta_likelihoods_batch(ldpgta_ctx *c, int kind, const int32_t *read_idx, c
         LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
         memcpy(out, c->h_pin, out_bytes);
     }
-    return 0;
-}
-
-int ldpgta_window_stats(ldpgta_ctx *c, const double *lik, const int64_t *window_offsets, int64_t n_windows, int n_cols,
-                        double *llr_out, double *window_mean_var, double *chrom_partials)
-{
-    if (!c || !lik || !window_offsets || n_windows < 0 || n_cols < 0) return fail(LDPGTA_E_INVALID, "bad arguments");
-    LDPGTA_CUDA(cudaSetDevice(c->device));
-    if (window_offsets[0] != 0) return fail(LDPGTA_E_INVALID, "window_offsets must start at 0");
-    const int64_t n_draws = window_offsets[n_windows];
-    for (int64_t w = 0; w < n_windows; ++w) {
-        const int64_t k = window_offsets[w + 1] - window_offsets[w];
-        if (k < 1) return fail(LDPGTA_E_INVALID, "window %lld has no draws", (long long)w);
-        if (k < n_cols) return fail(LDPGTA_E_INVALID, "window %lld has %lld draws < n_cols=%d", (long long)w, (long long)k, n_cols);
-    }
-    const int ncp = n_cols + 3;
-    const size_t lik_b = (size_t)n_draws * 32, off_b = ((size_t)(n_windows + 1) * 8 + 15) & ~(size_t)15;
-    const size_t llr_b = (size_t)n_draws * 5 * 8, mv_b = (size_t)n_windows * 5 * 2 * 8, cp_b = (size_t)5 * ncp * 8;
-    if (int rc = ensure_dev(c, lik_b + mv_b + cp_b + 64)) return rc;
-    // the LLRs and the window offsets stay on the device for ldpgta_bin_stats
-    c->llr_draws = c->llr_windows = -1;
-    if (int rc = ensure_own(&c->d_llr, &c->d_llr_bytes, llr_b + 16)) return rc;
-    if (int rc = ensure_own(&c->d_llr_off, &c->d_llr_off_bytes, off_b)) return rc;
-    char *p = (char *)c->d_buf;
-    double *d_lik = (double *)p; p += lik_b;
-    double *d_mv = (double *)p; p += mv_b;
-    double *d_cp = (double *)p;
-    double *d_llr = c->d_llr;
-    int64_t *d_off = c->d_llr_off;
-    if (n_draws) LDPGTA_CUDA(cudaMemcpyAsync(d_lik, lik, lik_b, cudaMemcpyHostToDevice, c->stream));
-    LDPGTA_CUDA(cudaMemcpyAsync(d_off, window_offsets, (size_t)(n_windows + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-    if (n_draws) {
-        const unsigned b1 = (unsigned)std::min<int64_t>((n_draws + 255) / 256, (int64_t)c->sm_count * 8);
-        k_llr<<<b1, 256, 0, c->stream>>>(d_lik, n_draws, d_llr);
-        c->launches++;
-        const int64_t warps = 5 * n_windows;
-        k_window_mean_var<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, c->stream>>>(d_llr, d_off, n_windows, n_draws, d_mv);
-        c->launches++;
-    }
-    k_chrom_partials<<<dim3(ncp, 5), 256, 0, c->stream>>>(d_llr, d_off, n_windows, n_draws, d_mv, n_cols, d_cp);
-    c->launches++;
-    LDPGTA_CUDA(cudaGetLastError());
-    if (llr_out && n_draws) LDPGTA_CUDA(cudaMemcpyAsync(llr_out, d_llr, llr_b, cudaMemcpyDeviceToHost, c->stream));
-    if (window_mean_var && n_windows) LDPGTA_CUDA(cudaMemcpyAsync(window_mean_var, d_mv, mv_b, cudaMemcpyDeviceToHost, c->stream));
-    if (chrom_partials) LDPGTA_CUDA(cudaMemcpyAsync(chrom_partials, d_cp, cp_b, cudaMemcpyDeviceToHost, c->stream));
-    LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
-    c->llr_draws = n_draws;
-    c->llr_windows = n_windows;
     return 0;
 }
 

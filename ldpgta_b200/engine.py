@@ -256,6 +256,107 @@ class Engine:
         """ host-pipeline calls served by one CUDA graph launch """
         return int(self.lib.ldpgta_graph_replays(self._ctx))
 
+    # ---- bootstrap() + statistics() resident on the device ------------------------------------------
+    def set_windows(self, window_offsets, window_reads, draw_offsets, reads_per_draw, segment_offsets=None,
+                    segment_cols=None, segment_first=None):
+        """ Makes the windows (build_gw_dict as CSR arrays), the draw plan (draws per window, reads per draw) and the
+        (embryo, chromosome) segments resident; see ldpgta_set_windows.  window_reads=None: window w owns the read
+        rows window_offsets[w]:window_offsets[w+1]; window_offsets=None: replay-only plan. """
+        i64 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.int64)
+        i32 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+        woff, wr, doff, rpd = i64(window_offsets), i32(window_reads), i64(draw_offsets), i32(reads_per_draw)
+        nw = len(doff) - 1
+        if np.ndim(reads_per_draw) == 0:
+            rpd = np.full(nw, int(reads_per_draw), dtype=np.int32)
+        if len(rpd) != nw or (woff is not None and len(woff) != nw + 1):
+            raise ValueError('window_offsets, draw_offsets and reads_per_draw disagree on the number of windows')
+        soff, scols, sfirst = i64(segment_offsets), i32(segment_cols), i32(segment_first)
+        ns = 1 if soff is None else len(soff) - 1
+        for a in (scols, sfirst):
+            if a is not None and len(a) != ns:
+                raise ValueError('one value per segment is needed')
+        N.check(self.lib.ldpgta_set_windows(self._ctx, N.ptr(woff), N.ptr(wr), nw, N.ptr(doff), N.ptr(rpd), N.ptr(soff), ns,
+                                            N.ptr(scols), N.ptr(sfirst)))
+        self._plan = self.plan_info()
+        self._plan['reads_per_draw'] = rpd
+        return self._plan
+
+    def plan_info(self):
+        out = np.zeros(10, dtype=np.int64)
+        N.check(self.lib.ldpgta_plan_info(self._ctx, N.ptr(out)))
+        keys = ('n_windows', 'n_draws', 'n_segments', 'ncp', 'n_classes', 'nnz', 'lik_dev', 'mean_var_dev', 'partials_dev', 'stats_dev')
+        return dict(zip(keys, out.tolist()))
+
+    def _stats_outputs(self, want, lik_out=None, out=None):
+        p = self._plan
+        nd, nw, ns, ncp = p['n_draws'], p['n_windows'], p['n_segments'], p['ncp']
+        if out is not None:                      # caller-owned (e.g. page-locked) arrays, reused from call to call
+            shapes = {'lik': (nd, 4), 'draws': (p['nnz'],), 'llr': (N.NUM_LLR_PAIRS, nd), 'mean_var': (N.NUM_LLR_PAIRS, nw, 2),
+                      'partials': (ns, N.NUM_LLR_PAIRS, ncp + 3), 'stats': (ns, N.NUM_LLR_PAIRS, 3)}
+            for k, a in out.items():
+                if tuple(a.shape) != shapes[k] or a.dtype != (np.int32 if k == 'draws' else np.float64) or not a.flags['C_CONTIGUOUS']:
+                    raise ValueError('output %r must be a C-contiguous array of shape %r' % (k, shapes[k]))
+            return out
+        out = {}
+        if 'lik' in want:
+            out['lik'] = lik_out if lik_out is not None else np.empty((nd, 4), dtype=np.float64)
+        if 'draws' in want:
+            out['draws'] = np.empty(p['nnz'], dtype=np.int32)
+        if 'llr' in want:
+            out['llr'] = np.empty((N.NUM_LLR_PAIRS, nd), dtype=np.float64)
+        if 'mean_var' in want:
+            out['mean_var'] = np.empty((N.NUM_LLR_PAIRS, nw, 2), dtype=np.float64)
+        if 'partials' in want:
+            out['partials'] = np.empty((ns, N.NUM_LLR_PAIRS, ncp + 3), dtype=np.float64)
+        if 'stats' in want:
+            out['stats'] = np.empty((ns, N.NUM_LLR_PAIRS, 3), dtype=np.float64)
+        return out
+
+    def bootstrap_stats(self, kind, seed, proportions=None, want=('mean_var', 'stats'), lik_out=None, out=None):
+        """ bootstrap() + statistics() (ANEUPLOIDY_TEST.py:250-325) for the resident plan with the draws made on the
+        device: only the seed goes up, only `want` comes back -- any of 'lik' [n_draws][4], 'draws' (concatenated read
+        rows), 'llr' [5][n_draws], 'mean_var' [5][n_windows][2], 'partials' [n_segments][5][ncp+3],
+        'stats' [n_segments][5][3] = mean_of_mean, std_of_mean, fraction_of_negative_LLRs.  `out` (a dict of arrays with
+        those keys) replaces `want` and is filled in place. """
+        out = self._stats_outputs(want, lik_out, out)
+        prop = None if proportions is None else np.ascontiguousarray(proportions, dtype=np.float64)
+        g = lambda k: N.ptr(out[k]) if k in out else None
+        N.check(self.lib.ldpgta_bootstrap_stats(self._ctx, kind, ctypes.c_uint64(int(seed) & (2 ** 64 - 1)), N.ptr(prop), g('lik'),
+                                                g('draws'), g('llr'), g('mean_var'), g('partials'), g('stats')))
+        return out
+
+    def replay_stats(self, kind, read_idx, proportions=None, want=('lik', 'mean_var', 'stats'), lik_out=None, out=None):
+        """ The same for draws given by the caller (read rows of every draw of the plan, window order). """
+        idx = np.ascontiguousarray(read_idx, dtype=np.int32).reshape(-1)
+        if len(idx) != self._plan['nnz']:
+            raise ValueError('the plan holds %d read indices, got %d' % (self._plan['nnz'], len(idx)))
+        out = self._stats_outputs([w for w in want if w != 'draws'], lik_out, out)
+        prop = None if proportions is None else np.ascontiguousarray(proportions, dtype=np.float64)
+        g = lambda k: N.ptr(out[k]) if k in out else None
+        N.check(self.lib.ldpgta_replay_stats(self._ctx, kind, N.ptr(idx), N.ptr(prop), g('lik'), g('llr'), g('mean_var'),
+                                             g('partials'), g('stats')))
+        return out
+
+    def bootstrap_stats_dev(self, kind, seed, proportions=None, partials_dev_ptr=None):
+        """ Asynchronous, everything stays in HBM (see ldpgta_bootstrap_stats_dev). """
+        prop = None if proportions is None else np.ascontiguousarray(proportions, dtype=np.float64)
+        N.check(self.lib.ldpgta_bootstrap_stats_dev(self._ctx, kind, ctypes.c_uint64(int(seed) & (2 ** 64 - 1)), N.ptr(prop),
+                                                    ctypes.c_void_p(partials_dev_ptr) if partials_dev_ptr else None))
+
+    def finish_segments_dev(self, partials_dev_ptr=None, stats_dev_ptr=None):
+        N.check(self.lib.ldpgta_finish_segments_dev(self._ctx, ctypes.c_void_p(partials_dev_ptr) if partials_dev_ptr else None,
+                                                    ctypes.c_void_p(stats_dev_ptr) if stats_dev_ptr else None))
+
+    def kernel_timing(self, enable=True):
+        """ CUDA-event brackets around the draw kernels of bootstrap_stats / replay_stats (measurement aid). """
+        N.check(self.lib.ldpgta_kernel_timing(self._ctx, 1 if enable else 0))
+
+    def kernel_times(self, max_entries=65536):
+        """ milliseconds of every bracket since the last call (waits for the stream) """
+        out = np.zeros(max_entries, dtype=np.float64)
+        n = N.check(self.lib.ldpgta_kernel_times(self._ctx, N.ptr(out), max_entries))
+        return out[:min(n, max_entries)]
+
     # ---- reductions -----------------------------------------------------------
     def window_stats(self, lik, window_offsets, n_cols, want_llr=True):
         """ LLRs, per-window mean / sample variance and the chromosome partial sums

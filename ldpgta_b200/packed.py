@@ -356,30 +356,76 @@ class PackedSample:
         return lik
 
     def run(self, window_size=100000, subsamples=32, offset=0, min_reads=6, max_reads=4, min_score=2, rng=None, seed=None,
-            want_draws=True, keep_pinned=False):
-        """ bootstrap() + statistics() (ANEUPLOIDY_TEST.py:250-325) on arrays.  The draws come from `rng` (a numpy
-        Generator, sampled on the host) or, when `seed` is given, from the device-side sampler.
-        keep_pinned=True leaves `likelihoods` in the page-locked buffer it was downloaded into (no copy); that view is
-        valid until the result's release() or deletion, after which the buffer serves the next sample. """
+            want_draws=True, keep_pinned=False, replay=None, want_likelihoods=True):
+        """ bootstrap() + statistics() (ANEUPLOIDY_TEST.py:250-325) on arrays, as ONE device-resident pipeline
+        (ldpgta_set_windows + ldpgta_bootstrap_stats / ldpgta_replay_stats): the likelihoods go from the draw kernels to the
+        LLR / window / chromosome reductions inside HBM.  The draws come from the device-side sampler when `seed` is
+        given, from `replay` (read rows of every draw, window order: the reference's recorded random.sample stream), or
+        from `rng` (a numpy Generator, sampled on the host).  want_likelihoods=False downloads only the statistics
+        (80 bytes per window); keep_pinned=True leaves `likelihoods` in the page-locked buffer it was downloaded into (no
+        copy), valid until the result's release() or deletion, after which the buffer serves the next sample. """
         win = self.windows(window_size, offset, min_reads, max_reads, min_score)
-        if seed is not None:
-            evaluated, draw_offsets, groups, lik = self.bootstrap_on_device(win, min_reads, max_reads, subsamples, int(seed), want_draws)
+        evaluated, draw_offsets, effN, k_of = self.plan_counts(win, min_reads, max_reads, subsamples)
+        if not len(evaluated):
+            return PackedResult(self, win, evaluated, draw_offsets, [] if want_draws else None,
+                                np.empty((0, 4)) if want_likelihoods else None, None, None, None)
+        sizes = k_of[evaluated].astype(np.int32)
+        if self.kind == N.DISTANT_ADMIXTURE and (sizes == 5).any():
+            raise AttributeError("'distant_admixture' object has no attribute 'likelihoods5'")
+        # read lists of the evaluated windows only
+        counts = win.sizes[evaluated]
+        woff = np.zeros(len(evaluated) + 1, dtype=np.int64)
+        np.cumsum(counts, out=woff[1:])
+        if len(evaluated) == len(win):
+            wreads = win.reads
         else:
-            rng = np.random.default_rng() if rng is None else rng
-            evaluated, draw_offsets, groups = self.plan(win, min_reads, max_reads, subsamples, rng)
-            lik = self.evaluate(groups, int(draw_offsets[-1]))
-        mean_var = chrom = None
-        if len(evaluated):
-            counts = np.diff(draw_offsets)
-            n_cols = int(counts.min())
-            _llr, mean_var, partials = self.engine.window_stats(lik, draw_offsets, n_cols, want_llr=False)
-            chrom = finish_chromosome(partials, n_cols, int(counts[0]))
-        lease, self._lease = self._lease, None
-        if not keep_pinned and lease is not None:
+            take = np.repeat(win.offsets[:-1][evaluated] - woff[:-1], counts) + np.arange(woff[-1])
+            wreads = win.reads[take]
+        self.engine.set_windows(woff, wreads, draw_offsets, sizes)
+        n_draws = int(draw_offsets[-1])
+        want = ['mean_var', 'stats']
+        buf = lik = None
+        if want_likelihoods:
+            buf = self.pool.take(n_draws)
+            lik = buf.array[:4 * n_draws].reshape(n_draws, 4)
+            want.append('lik')
+        flat = None
+        try:
+            if seed is not None:
+                if want_draws:
+                    want.append('draws')
+                out = self.engine.bootstrap_stats(self.kind, int(seed), proportions=self.proportions, want=want, lik_out=lik)
+                flat = out.get('draws')
+            else:
+                if replay is not None:
+                    flat = np.ascontiguousarray(replay, dtype=np.int32).reshape(-1)
+                else:
+                    rng = np.random.default_rng() if rng is None else rng
+                    per_draw_k = np.repeat(sizes, np.diff(draw_offsets))
+                    starts = np.zeros(n_draws + 1, dtype=np.int64)
+                    np.cumsum(per_draw_k, out=starts[1:])
+                    flat = np.empty(int(starts[-1]), dtype=np.int32)
+                    for rows, idx in self.plan(win, min_reads, max_reads, subsamples, rng)[2]:
+                        flat[starts[rows][:, None] + np.arange(idx.shape[1])] = idx
+                out = self.engine.replay_stats(self.kind, flat, proportions=self.proportions, want=want, lik_out=lik)
+        except Exception:
+            self.pool.give(buf)
+            raise
+        groups = None
+        if want_draws and flat is not None:
+            per_draw_k = np.repeat(sizes, np.diff(draw_offsets))
+            starts = np.zeros(n_draws + 1, dtype=np.int64)
+            np.cumsum(per_draw_k, out=starts[1:])
+            groups = []
+            for k in np.unique(per_draw_k).tolist():
+                rows = np.flatnonzero(per_draw_k == k)
+                groups.append((rows, flat[starts[rows][:, None] + np.arange(k)]))
+        lease = (self.pool, buf) if buf is not None else None
+        if lik is not None and not keep_pinned:
             lik = np.array(lik)
-            lease[0].give(lease[1])
+            self.pool.give(buf)
             lease = None
-        return PackedResult(self, win, evaluated, draw_offsets, groups, lik, mean_var, chrom, lease)
+        return PackedResult(self, win, evaluated, draw_offsets, groups, lik, out['mean_var'], out['stats'][0], lease)
 
 
 def build_windows(obs_pos, obs_read, scores, window_size, offset, min_reads, min_score):

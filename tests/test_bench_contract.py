@@ -39,6 +39,8 @@ def test_reference_arm_runs_without_a_gpu():
     for k in BASE_KEYS + ('cpu_baseline', 'e2e'):
         assert k in d, k
     assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
-    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
+    import make_ref                                            # oracle/make_ref.py: the staged, unmodified reference scripts
+    assert d['cpu_baseline']['kind'] == ('reference' if make_ref.available() else 'port')
+    assert d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
     ours = json.load(open(os.path.join(ROOT, 'profiles', 'r01_bench_n1.json')))
     assert d['metric'] == ours['metric'] and d['unit'] == ours['unit'] and d['config'] == ours['config']

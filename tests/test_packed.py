@@ -118,6 +118,24 @@ def test_packed_sample_matches_reference(name, golden_inputs):
             for g, r in zip(got.tolist(), ref[k]):
                 worst = max(worst, max(rel_err(a, b) for a, b in zip(g, r)))
         assert worst <= 1e-12, worst
+        # the same draws through the device-resident pipeline (set_windows + replay_stats): the reference's likelihoods
+        # to 1e-12 and the reference's statistics() -- per window and per chromosome -- to 1e-9
+        flat = [row_of[r] for w in out['likelihoods'] for d in out['draws'][w] for r in d]
+        res = ps.run(cfg['window_size'], cfg['subsamples'], cfg['offset'], cfg['min_reads'], cfg['max_reads'], cfg['min_score'], replay=flat)
+        assert [tuple(b) for b in res.borders.tolist()] == list(out['likelihoods'])
+        ref_lik = np.array([l for w in out['likelihoods'] for l in out['likelihoods'][w]], dtype=np.float64)
+        assert np.max(np.abs(res.likelihoods - ref_lik) / np.maximum(np.abs(ref_lik), 1e-300)) <= 1e-12
+        gold = out['statistics']
+        for p_i, pair in enumerate(L.LLR_PAIRS):
+            for k, w in enumerate(out['likelihoods']):
+                m, v = gold['LLRs_per_genomic_window'][pair][w]
+                gm, gv = res.window_mean_var[p_i, k]
+                assert abs(gm - m) <= 1e-9 * max(1e-3, abs(m)) and abs(gv - v) <= 1e-9 * max(1e-3, abs(v))
+            for key, val in gold['LLRs_per_chromosome'][pair].items():
+                assert abs(res.llr_per_chromosome()[pair][key] - val) <= 1e-9 * max(1e-3, abs(val)), (pair, key)
+        stats_only = ps.run(cfg['window_size'], cfg['subsamples'], cfg['offset'], cfg['min_reads'], cfg['max_reads'], cfg['min_score'],
+                            replay=flat, want_likelihoods=False, want_draws=False)
+        assert stats_only.likelihoods is None and np.array_equal(stats_only.chromosome, res.chromosome)
         # a full packed run: every window the reference evaluates is evaluated, draws are valid, statistics finite
         for mode in ({'rng': np.random.default_rng(1)}, {'seed': 5}):           # host-sampled and device-sampled draws
             res = ps.run(cfg['window_size'], cfg['subsamples'], cfg['offset'], cfg['min_reads'], cfg['max_reads'], cfg['min_score'], **mode)
