@@ -17,10 +17,6 @@ from ldpgta_b200.HOMOGENOUES_MODELS import homogeneous
 from ldpgta_b200.RECENT_ADMIXTURE_MODELS import recent_admixture
 from ldpgta_b200.DISTANT_ADMIXTURE_MODELS import distant_admixture
 
-# the driver builds its models through these classes so that results carry the
-# per-module likelihoods_tuple the reference's *.LLR.p readers expect
-_driver.homogeneous, _driver.recent_admixture, _driver.distant_admixture = homogeneous, recent_admixture, distant_admixture
-
 leg_tuple, obs_tuple, comb_tuple = _driver.leg_tuple, _driver.obs_tuple, _driver.comb_tuple
 likelihoods_tuple = _driver.likelihoods_tuple
 popcount = _driver.popcount

@@ -4,7 +4,6 @@ constructor, methods and result record, computed on a B200 (see models.py).
 Importable flat (`import RECENT_ADMIXTURE_MODELS` with this directory on sys.path) or as
 `ldpgta_b200.RECENT_ADMIXTURE_MODELS`.
 """
-import collections as _collections
 import os as _os
 import sys as _sys
 
@@ -18,15 +17,9 @@ leg_tuple = _models.leg_tuple
 obs_tuple = _models.obs_tuple
 popcount = _models.popcount
 
-# The reference pickles likelihoods_tuple instances under the bare module name
-# 'RECENT_ADMIXTURE_MODELS' (*.LLR.p files); keep that name so old readers unpickle them.
-likelihoods_tuple = _collections.namedtuple('likelihoods_tuple', ('monosomy', 'disomy', 'SPH', 'BPH'))
-if _sys.modules.setdefault('RECENT_ADMIXTURE_MODELS', _sys.modules[__name__]) is _sys.modules[__name__]:
-    likelihoods_tuple.__module__ = 'RECENT_ADMIXTURE_MODELS'
-else:
-    likelihoods_tuple.__module__ = __name__
-
-
-class recent_admixture(_models.recent_admixture):
-    __doc__ = _models.recent_admixture.__doc__
-    tuple_type = likelihoods_tuple
+# The reference pickles likelihoods_tuple instances under the bare module name 'RECENT_ADMIXTURE_MODELS' (*.LLR.p files).  The class
+# lives in models.py (one object however this file was imported); the bare name resolves to this module unless the
+# caller has already put a module of that name (e.g. the reference's own) into sys.modules.
+likelihoods_tuple = _models.TUPLES['RECENT_ADMIXTURE_MODELS']
+_sys.modules.setdefault('RECENT_ADMIXTURE_MODELS', _sys.modules[__name__])
+recent_admixture = _models.recent_admixture

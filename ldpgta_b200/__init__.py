@@ -13,6 +13,9 @@ from .models import ImplicitModels, distant_admixture, homogeneous, likelihoods_
 from .driver import (aneuploidy_test, bootstrap, build_gw_dict, effective_number_of_subsamples, evaluate_draws,
                      pick_reads, plan_draw_indices, plan_draws, statistics, supporting_dictionaries)
 
+# registers the reference's module names for pickling (see models.TUPLES)
+from . import HOMOGENOUES_MODELS as _hm, RECENT_ADMIXTURE_MODELS as _rm, DISTANT_ADMIXTURE_MODELS as _dm  # noqa: E402,F401
+
 __all__ = ['Engine', 'homogeneous', 'recent_admixture', 'distant_admixture', 'bootstrap', 'aneuploidy_test',
            'statistics', 'likelihoods_tuple', 'ImplicitModels', 'LdpgtaError', 'pack_ints', 'finish_chromosome',
            'ResidentPanel', 'HOMOGENEOUS', 'RECENT_ADMIXTURE', 'DISTANT_ADMIXTURE', 'LLR_PAIRS', 'load', 'LIB_PATH', 'PinnedArray']

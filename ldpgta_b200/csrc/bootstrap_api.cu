@@ -33,13 +33,14 @@ struct WindowPlan {
     std::vector<SizeClass> classes;
     std::vector<int64_t> h_doff;   // draw offsets per window
     std::vector<int32_t> h_n;      // reads per draw per window
-    double *d_lik = nullptr, *d_mv = nullptr, *d_runs = nullptr, *d_partials = nullptr, *d_stats = nullptr;
+    double *d_lik = nullptr, *d_llr = nullptr, *d_mv = nullptr, *d_runs = nullptr, *d_partials = nullptr, *d_stats = nullptr;
     uint64_t *d_seed = nullptr;
 };
 
 void free_window_plan(ldpgta_ctx *c)
 {
     if (!c->plan) return;
+    if (c->llr_ptr == c->plan->d_llr) { c->llr_ptr = nullptr; c->llr_off_ptr = nullptr; c->llr_draws = c->llr_windows = -1; }
     if (c->plan->d_static) cudaFree(c->plan->d_static);
     if (c->plan->d_work) cudaFree(c->plan->d_work);
     delete c->plan;
@@ -77,9 +78,8 @@ static int stats_shape(const ldpgta_ctx *c, int64_t n_windows, int ncp, StatsSha
     const size_t per_warp = (size_t)5 * ncp * 8;
     s->wpb = per_warp ? (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / per_warp)) : 8;
     s->smem = per_warp * s->wpb;
-    const int bps = s->smem ? (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / s->smem)) : 8;
-    const int64_t resident = (int64_t)c->sm_count * s->wpb * bps;
-    s->cw = (int)std::max<int64_t>(8, (n_windows + 2 * resident - 1) / (2 * resident));
+    // chunks of up to 8 windows, shorter when that leaves fewer than ~32 warps per SM
+    s->cw = (int)std::max<int64_t>(1, std::min<int64_t>(8, n_windows / ((int64_t)c->sm_count * 32)));
     s->n_chunks = (n_windows + s->cw - 1) / s->cw;
     return 0;
 }
@@ -89,14 +89,19 @@ static int stats_on_device(ldpgta_ctx *c, const double *d_lik, const int64_t *d_
                            const int64_t *d_segoff, const int32_t *d_segcols, const int32_t *d_segfirst, int n_segments, int ncp,
                            const StatsShape &sh, double *d_llr, double *d_mv, double *d_runs, double *d_partials, double *d_stats)
 {
+    if (n_draws > 0) {
+        const unsigned blocks = (unsigned)std::min<int64_t>((n_draws + 255) / 256, (int64_t)c->sm_count * 8);
+        k_draw_llr<<<blocks, 256, 0, c->stream>>>(d_lik, n_draws, d_llr);
+        c->launches++;
+    }
     if (n_windows > 0) {
         StatsArgs a;
-        a.lik = d_lik; a.doff = d_doff; a.seg_off = d_segoff; a.n_windows = n_windows; a.n_draws = n_draws;
-        a.n_segments = n_segments; a.ncp = ncp; a.cw = sh.cw; a.llr = d_llr; a.mean_var = d_mv; a.runs = d_runs;
+        a.llr = d_llr; a.doff = d_doff; a.seg_off = d_segoff; a.n_windows = n_windows; a.n_draws = n_draws;
+        a.n_segments = n_segments; a.ncp = ncp; a.cw = sh.cw; a.mean_var = d_mv; a.runs = d_runs;
         if (sh.smem > 48 * 1024)
-            LDPGTA_CUDA(cudaFuncSetAttribute(k_llr_window_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem));
+            LDPGTA_CUDA(cudaFuncSetAttribute(k_window_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem));
         const unsigned blocks = (unsigned)std::min<int64_t>((sh.n_chunks + sh.wpb - 1) / sh.wpb, (int64_t)c->sm_count * 32);
-        k_llr_window_stats<<<blocks, sh.wpb * 32, sh.smem, c->stream>>>(a);
+        k_window_stats<<<blocks, sh.wpb * 32, sh.smem, c->stream>>>(a);
         c->launches++;
     }
     k_segment_partials<<<dim3((unsigned)n_segments, 5), 128, 0, c->stream>>>(d_runs, d_segoff, d_segcols, ncp, sh.cw, d_partials);
@@ -178,14 +183,8 @@ static int reduce_and_download(ldpgta_ctx *c, WindowPlan *p, double *lik_out, do
 {
     StatsShape sh;
     if (int rc = stats_shape(c, p->n_windows, p->ncp, &sh)) return rc;
-    double *d_llr = nullptr;
+    double *d_llr = p->d_llr;
     c->llr_draws = c->llr_windows = -1;
-    if (llr_out) {
-        if (int rc = ensure_own(&c->d_llr, &c->d_llr_bytes, (size_t)p->n_draws * 40 + 16)) return rc;
-        if (int rc = ensure_own(&c->d_llr_off, &c->d_llr_off_bytes, (size_t)(p->n_windows + 1) * 8)) return rc;
-        d_llr = c->d_llr;
-        LDPGTA_CUDA(cudaMemcpyAsync(c->d_llr_off, p->d_doff, (size_t)(p->n_windows + 1) * 8, cudaMemcpyDeviceToDevice, c->stream));
-    }
     if (int rc = stats_on_device(c, p->d_lik, p->d_doff, p->n_windows, p->n_draws, p->d_segoff, p->d_segcols, p->d_segfirst,
                                  p->n_segments, p->ncp, sh, d_llr, p->d_mv, p->d_runs, p->d_partials, p->d_stats))
         return rc;
@@ -200,7 +199,8 @@ static int reduce_and_download(ldpgta_ctx *c, WindowPlan *p, double *lik_out, do
         LDPGTA_CUDA(cudaStreamSynchronize(c->s_out));
         if (lik_pinned != lik_out) memcpy(lik_out, lik_pinned, (size_t)p->n_draws * 32);
     }
-    if (llr_out) { c->llr_draws = p->n_draws; c->llr_windows = p->n_windows; }
+    c->llr_ptr = p->d_llr; c->llr_off_ptr = p->d_doff;
+    c->llr_draws = p->n_draws; c->llr_windows = p->n_windows;
     return 0;
 }
 
@@ -352,13 +352,14 @@ int ldpgta_set_windows(ldpgta_ctx *c, const int64_t *window_offsets, const int32
     off = 0;
     std::vector<size_t> o_idx;
     for (const SizeClass &k : p->classes) o_idx.push_back(take((size_t)k.n_draws * k.n * 4));
-    const size_t o_lik = take((size_t)n_draws * 32), o_mv = take((size_t)n_windows * 80);
+    const size_t o_lik = take((size_t)n_draws * 32), o_llr = take((size_t)n_draws * 40), o_mv = take((size_t)n_windows * 80);
     const size_t o_runs = take((size_t)(sh.n_chunks + n_segments) * 5 * (ncp + 3) * 8);
     const size_t o_part = take((size_t)n_segments * 5 * (ncp + 3) * 8), o_stats = take((size_t)n_segments * 120);
     LDPGTA_CUDA(cudaMalloc(&p->d_work, std::max<size_t>(off, 256)));
     base = (char *)p->d_work;
     for (size_t ci = 0; ci < p->classes.size(); ++ci) p->classes[ci].d_idx = (int32_t *)(base + o_idx[ci]);
     p->d_lik = (double *)(base + o_lik);
+    p->d_llr = (double *)(base + o_llr);
     p->d_mv = (double *)(base + o_mv);
     p->d_runs = (double *)(base + o_runs);
     p->d_partials = (double *)(base + o_part);
@@ -484,7 +485,7 @@ int ldpgta_bootstrap_stats_dev(ldpgta_ctx *c, int kind, uint64_t seed, const dou
     StatsShape sh;
     if (int rc = stats_shape(c, p->n_windows, p->ncp, &sh)) return rc;
     return stats_on_device(c, p->d_lik, p->d_doff, p->n_windows, p->n_draws, p->d_segoff, p->d_segcols, p->d_segfirst, p->n_segments,
-                           p->ncp, sh, nullptr, p->d_mv, p->d_runs, segment_partials_dev ? segment_partials_dev : p->d_partials,
+                           p->ncp, sh, p->d_llr, p->d_mv, p->d_runs, segment_partials_dev ? segment_partials_dev : p->d_partials,
                            segment_partials_dev ? nullptr : p->d_stats);
 }
 
@@ -577,6 +578,7 @@ int ldpgta_window_stats(ldpgta_ctx *c, const double *lik, const int64_t *window_
     if (window_mean_var && n_windows) LDPGTA_CUDA(cudaMemcpyAsync(window_mean_var, d_mv, (size_t)n_windows * 80, cudaMemcpyDeviceToHost, c->stream));
     if (chrom_partials) LDPGTA_CUDA(cudaMemcpyAsync(chrom_partials, d_cp, (size_t)5 * stride * 8, cudaMemcpyDeviceToHost, c->stream));
     LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
+    c->llr_ptr = c->d_llr; c->llr_off_ptr = c->d_llr_off;
     c->llr_draws = n_draws;
     c->llr_windows = n_windows;
     return 0;

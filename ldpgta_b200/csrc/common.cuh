@@ -214,6 +214,8 @@ struct ldpgta_ctx {
     // LLRs of the last ldpgta_window_stats call, kept on the device for ldpgta_bin_stats (own allocation)
     double *d_llr = nullptr;  size_t d_llr_bytes = 0;
     int64_t llr_draws = -1, llr_windows = -1;
+    const double *llr_ptr = nullptr;          // the resident LLRs ldpgta_bin_stats(x = NULL) reads: d_llr or the plan's buffer
+    const int64_t *llr_off_ptr = nullptr;
     int64_t *d_llr_off = nullptr;  size_t d_llr_off_bytes = 0;
     unsigned int *d_flag = nullptr, *h_flag = nullptr;     // device-side index validation of the pipelined host path
     // the pipelined host path as a CUDA graph, replayed while the call signature repeats

@@ -107,61 +107,95 @@ struct ScoreArgs {
     const int64_t *off;
     int64_t n_reads;
     double w, min_HF, max_HF;
-    int32_t *out;                   // score per read; -1 = more than 12 qualifying SNPs (not evaluated)
+    int32_t *out;                   // score per read; -k = the read has k > 12 qualifying SNPs (left to k_read_scores_long)
+    const int64_t *long_items;      // k_read_scores_long: (read, chunk of 4096 combinations) pairs
+    int64_t n_long_items;
 };
+
+constexpr int SCORE_MAXQ = 24;      // qualifying SNPs per read the device enumerates (2^24 combinations)
+constexpr int SCORE_SHORT = 12;     // up to here one warp does the whole read
+
+// qualifying SNPs of read r (:171-178): allele rows whose effective frequency lies in [0.01, 0.99]; returns their number
+// (the list holds the first SCORE_MAXQ)
+__device__ __forceinline__ int score_qualifying(const ScoreArgs &a, int64_t r, int lane, int32_t *q)
+{
+    const int64_t b = a.off[r], e = a.off[r + 1];
+    int k = 0;
+    for (int64_t t = b; t < e; ++t) {
+        const int32_t ai = a.allele_idx[t];
+        double freq = 0.0;
+        for (int g = 0; g < a.G; ++g) {
+            uint32_t c = 0;
+            const uint64_t *row = a.rows[g] + (int64_t)ai * a.wp[g];
+            for (int w = lane; w < a.wp[g]; w += 32) c += __popcll(row[w]);
+#pragma unroll
+            for (int m = 16; m; m >>= 1) c += __shfl_xor_sync(0xffffffffu, c, m);
+            if (a.complement[ai]) c = a.nhap[g] - c;                       // popcount of the panel row itself
+            freq = freq + a.alpha[g] * (double)c;
+        }
+        if (0.01 <= freq && freq <= 0.99) {
+            if (k < SCORE_MAXQ) q[k] = ai;
+            ++k;
+        }
+    }
+    return k;
+}
+
+// number of combinations `choice` in [c0, c1) of (row, complemented row) per qualifying SNP whose haplotype frequency
+// lies in [min_HF, max_HF] (:181-184)
+__device__ __forceinline__ int32_t score_range(const ScoreArgs &a, const int32_t *q, int k, uint32_t c0, uint32_t c1, int lane)
+{
+    int32_t score = 0;
+    for (uint32_t choice = c0; choice < c1; ++choice) {
+        double freq = 0.0;
+        for (int g = 0; g < a.G; ++g) {
+            const int wp = a.wp[g];
+            uint32_t c = 0;
+            for (int w = lane; w < wp; w += 32) {
+                const int bits = (int)a.nhap[g] - 64 * w;
+                const u64 valid = bits >= 64 ? ~0ull : (bits > 0 ? ((1ull << bits) - 1ull) : 0ull);
+                u64 v = valid;
+                for (int i = 0; i < k; ++i) {
+                    const u64 x = a.rows[g][(int64_t)q[i] * wp + w];
+                    v &= ((choice >> i) & 1) ? ~x : x;
+                }
+                c += __popcll(v);
+            }
+#pragma unroll
+            for (int m = 16; m; m >>= 1) c += __shfl_xor_sync(0xffffffffu, c, m);
+            freq = freq + a.w * (double)c;
+        }
+        score += (a.min_HF <= freq && freq <= a.max_HF) ? 1 : 0;
+    }
+    return score;
+}
 
 static __global__ void k_read_scores(const ScoreArgs a)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < a.n_reads; r += warps) {
-        const int64_t b = a.off[r], e = a.off[r + 1];
-        // qualifying SNPs of the read (:171-178)
-        int32_t q[12];
-        int k = 0;
-        bool too_many = false;
-        for (int64_t t = b; t < e; ++t) {
-            const int32_t ai = a.allele_idx[t];
-            double freq = 0.0;
-            for (int g = 0; g < a.G; ++g) {
-                uint32_t c = 0;
-                const uint64_t *row = a.rows[g] + (int64_t)ai * a.wp[g];
-                for (int w = lane; w < a.wp[g]; w += 32) c += __popcll(row[w]);
-#pragma unroll
-                for (int m = 16; m; m >>= 1) c += __shfl_xor_sync(0xffffffffu, c, m);
-                if (a.complement[ai]) c = a.nhap[g] - c;                       // popcount of the panel row itself
-                freq = freq + a.alpha[g] * (double)c;
-            }
-            if (0.01 <= freq && freq <= 0.99) {
-                if (k < 12) q[k++] = ai; else too_many = true;
-            }
-        }
+        int32_t q[SCORE_MAXQ];
+        const int k = score_qualifying(a, r, lane, q);
         int32_t score = 0;
-        if (too_many) score = -1;
-        else if (k > 0) {
-            for (int choice = 0; choice < (1 << k); ++choice) {
-                double freq = 0.0;
-                for (int g = 0; g < a.G; ++g) {
-                    const int wp = a.wp[g];
-                    uint32_t c = 0;
-                    for (int w = lane; w < wp; w += 32) {
-                        const int bits = (int)a.nhap[g] - 64 * w;
-                        const u64 valid = bits >= 64 ? ~0ull : (bits > 0 ? ((1ull << bits) - 1ull) : 0ull);
-                        u64 v = valid;
-                        for (int i = 0; i < k; ++i) {
-                            const u64 x = a.rows[g][(int64_t)q[i] * wp + w];
-                            v &= ((choice >> i) & 1) ? ~x : x;
-                        }
-                        c += __popcll(v);
-                    }
-#pragma unroll
-                    for (int m = 16; m; m >>= 1) c += __shfl_xor_sync(0xffffffffu, c, m);
-                    freq = freq + a.w * (double)c;
-                }
-                score += (a.min_HF <= freq && freq <= a.max_HF) ? 1 : 0;
-            }
-        }
+        if (k > SCORE_SHORT) score = -k;                      // long read: the host schedules k_read_scores_long for it
+        else if (k > 0) score = score_range(a, q, k, 0u, 1u << k, lane);
         if (lane == 0) a.out[r] = score;
+    }
+}
+
+// reads with 13..24 qualifying SNPs: one warp per (read, block of 4096 combinations), counts added atomically (integers)
+static __global__ void k_read_scores_long(const ScoreArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t it = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < a.n_long_items; it += warps) {
+        const int64_t r = a.long_items[2 * it], chunk = a.long_items[2 * it + 1];
+        int32_t q[SCORE_MAXQ];
+        const int k = score_qualifying(a, r, lane, q);
+        const uint32_t c0 = (uint32_t)chunk << 12;
+        const int32_t part = score_range(a, q, k, c0, c0 + 4096u, lane);
+        if (lane == 0 && part) atomicAdd(a.out + r, part);
     }
 }
 
@@ -202,23 +236,37 @@ __device__ __forceinline__ double warp_sum_comp(Comp a)
     return a.value();
 }
 
-// ---- statistics() fused: likelihoods -> LLRs -> window mean / variance -> segment partial sums, in one pass -------
+// ---- statistics() on the device: likelihoods -> LLRs -> window mean / variance -> segment partial sums ---------------
 // A segment is one (embryo, chromosome): a run of consecutive windows whose LLRs statistics() (ANEUPLOIDY_TEST.py:289-325)
-// reduces together.  One warp walks a chunk of `cw` consecutive windows; lane l owns the draws l, l+32, ... of a window
-// (= columns of the reference's zip(*A), :73) and keeps the column sums of the run in its slice of shared memory.  A run
-// ends at a segment border or at the chunk's end and is flushed to slot (chunk + segment) of `runs`, so the reduction over
-// runs (k_segment_partials) needs neither atomics nor flags and adds in a fixed order: results are bit-reproducible.
-// Window mean = compensated sum / count; window variance by Welford updates per lane merged across lanes with Chan's
-// formula (single pass, no cancellation) -- statistics.mean / statistics.variance of :51-56 are exact-rational.
+// reduces together.
+//   k_draw_llr      one thread per draw: the five LLRs (:78-90, :298), [5][n_draws].  float64 log and division: this is
+//                   the arithmetic floor of the reductions (5 logs per draw).
+//   k_window_stats  one warp walks a chunk of `cw` consecutive windows; lane l owns the draws l, l+32, ... of a window
+//                   (= columns of the reference's zip(*A), :73) and keeps the column sums of the run in its slice of
+//                   shared memory.  A run ends at a segment border or at the chunk's end and is flushed to slot
+//                   (chunk + segment) of `runs`, so the reduction over runs (k_segment_partials) needs neither atomics nor
+//                   flags and adds in a fixed order: results are bit-reproducible.  Window mean = sum / count, variance
+//                   from the squared deviations of a second pass over the window's LLRs (registers for windows of at
+//                   most 32 draws, L1/L2 otherwise); sums of more than 32 values are Neumaier-compensated
+//                   (statistics.mean / statistics.variance of :51-56 are exact-rational).
+static __global__ void k_draw_llr(const double *__restrict__ lik, int64_t n_draws, double *__restrict__ out)
+{
+    for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < n_draws; d += (int64_t)gridDim.x * blockDim.x) {
+        const double2 a = __ldg(reinterpret_cast<const double2 *>(lik) + 2 * d), b = __ldg(reinterpret_cast<const double2 *>(lik) + 2 * d + 1);
+        const double v[4] = {a.x, a.y, b.x, b.y};
+#pragma unroll
+        for (int p = 0; p < 5; ++p) out[p * n_draws + d] = llr(v[c_pair_num[p]], v[c_pair_den[p]]);
+    }
+}
+
 struct StatsArgs {
-    const double *lik;         // [n_draws][4] monosomy, disomy, SPH, BPH
+    const double *llr;         // [5][n_draws] per-draw LLRs
     const int64_t *doff;       // [n_windows + 1] draws of window w = [doff[w], doff[w+1])
     const int64_t *seg_off;    // [n_segments + 1] windows of segment s = [seg_off[s], seg_off[s+1])
     int64_t n_windows, n_draws;
     int n_segments;
     int ncp;                   // column capacity: sums are kept for the first ncp draws of a window
     int cw;                    // windows per chunk
-    double *llr;               // optional [5][n_draws] per-draw LLRs
     double *mean_var;          // [5][n_windows][2]
     double *runs;              // [n_chunks + n_segments][5][ncp + 3]
 };
@@ -233,7 +281,7 @@ __device__ __forceinline__ int segment_of(const int64_t *seg_off, int n_segments
     return lo;
 }
 
-static __global__ void k_llr_window_stats(const StatsArgs a)
+static __global__ void k_window_stats(const StatsArgs a)
 {
     extern __shared__ double sh_cols[];                            // [warps][5][ncp]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -252,55 +300,50 @@ static __global__ void k_llr_window_stats(const StatsArgs a)
         __syncwarp();
         for (int64_t w = w0; w < w1; ++w) {
             const int64_t b = a.doff[w], e = a.doff[w + 1];
-            Comp sum[5];
-            double cnt = 0.0, mean[5], m2[5];
+            const double cnt = (double)(e - b);
+            if (e - b <= 32) {
+                // one draw per lane: both passes from registers, plain tree sums (5 roundings)
+                const bool live = b + lane < e;
+                double x[5];
 #pragma unroll
-            for (int p = 0; p < 5; ++p) { sum[p].s = sum[p].c = 0.0; mean[p] = 0.0; m2[p] = 0.0; }
-            for (int64_t i = b + lane; i < e; i += 32) {
-                const double2 u = __ldg(reinterpret_cast<const double2 *>(a.lik) + 2 * i), v = __ldg(reinterpret_cast<const double2 *>(a.lik) + 2 * i + 1);
-                const double lk[4] = {u.x, u.y, v.x, v.y};
-                cnt += 1.0;
-                const int64_t col = i - b;
+                for (int p = 0; p < 5; ++p) x[p] = live ? __ldg(a.llr + (int64_t)p * a.n_draws + b + lane) : 0.0;
 #pragma unroll
                 for (int p = 0; p < 5; ++p) {
-                    const double x = llr(lk[c_pair_num[p]], lk[c_pair_den[p]]);
-                    if (a.llr) a.llr[(int64_t)p * a.n_draws + i] = x;
-                    sum[p].add(x);
-                    const double d = x - mean[p];
-                    mean[p] += d / cnt;
-                    m2[p] += d * (x - mean[p]);
-                    if (col < a.ncp) cols[p * a.ncp + col] += x;
-                }
-            }
-            const double n_all = (double)(e - b);
-#pragma unroll
-            for (int p = 0; p < 5; ++p) {
-                // Chan et al.: merge (count, mean, M2) of lane pairs
-                double na = cnt, ma = mean[p], qa = m2[p];
-#pragma unroll
-                for (int msk = 16; msk; msk >>= 1) {
-                    const double nb = __shfl_xor_sync(0xffffffffu, na, msk), mb = __shfl_xor_sync(0xffffffffu, ma, msk),
-                                 qb = __shfl_xor_sync(0xffffffffu, qa, msk);
-                    const double nn = na + nb;
-                    if (nn > 0.0) {
-                        // symmetric in (a, b) so that both lanes of a pair hold the same result
-                        const double lo_n = (lane & msk) ? nb : na, hi_n = (lane & msk) ? na : nb;
-                        const double lo_m = (lane & msk) ? mb : ma, hi_m = (lane & msk) ? ma : mb;
-                        const double lo_q = (lane & msk) ? qb : qa, hi_q = (lane & msk) ? qa : qb;
-                        const double delta = hi_m - lo_m;
-                        ma = lo_m + delta * (hi_n / nn);
-                        qa = (lo_q + hi_q) + delta * delta * (lo_n * hi_n / nn);
+                    if (live && lane < a.ncp) cols[p * a.ncp + lane] += x[p];
+                    const double s = warp_sum_f64(x[p]);
+                    const double m = s / cnt;
+                    const double d = live ? x[p] - m : 0.0;
+                    const double ss = warp_sum_f64(d * d);
+                    total[p].add(s);
+                    if (m < 0.0) n_neg[p] += 1.0;
+                    if (lane == 0) {
+                        double *mv = a.mean_var + 2 * ((int64_t)p * a.n_windows + w);
+                        mv[0] = m;
+                        mv[1] = (e - b > 1) ? ss / (cnt - 1.0) : nan("");
                     }
-                    na = nn;
                 }
-                const double s = warp_sum_comp(sum[p]);
-                const double m = s / n_all;
-                total[p].add(s);
-                if (m < 0.0) n_neg[p] += 1.0;
-                if (lane == 0) {
-                    double *mv = a.mean_var + 2 * ((int64_t)p * a.n_windows + w);
-                    mv[0] = m;
-                    mv[1] = (e - b > 1) ? qa / (n_all - 1.0) : nan("");
+            } else {
+#pragma unroll 1
+                for (int p = 0; p < 5; ++p) {
+                    const double *x = a.llr + (int64_t)p * a.n_draws;
+                    Comp acc = {0.0, 0.0};
+                    for (int64_t i = b + lane; i < e; i += 32) {
+                        const double v = __ldg(x + i);
+                        acc.add(v);
+                        if (i - b < a.ncp) cols[p * a.ncp + (i - b)] += v;
+                    }
+                    const double s = warp_sum_comp(acc);
+                    const double m = s / cnt;
+                    Comp sq = {0.0, 0.0};
+                    for (int64_t i = b + lane; i < e; i += 32) { const double d = __ldg(x + i) - m; sq.add(d * d); }
+                    const double ss = warp_sum_comp(sq);
+                    total[p].add(s);
+                    if (m < 0.0) n_neg[p] += 1.0;
+                    if (lane == 0) {
+                        double *mv = a.mean_var + 2 * ((int64_t)p * a.n_windows + w);
+                        mv[0] = m;
+                        mv[1] = ss / (cnt - 1.0);
+                    }
                 }
             }
             n_win += 1.0;

@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <math.h>
 #include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 #include "k_small.cuh"     // SmallArgs
@@ -658,9 +659,35 @@ int ldpgta_read_scores(ldpgta_ctx *c, const int32_t *allele_idx, const int64_t *
     LDPGTA_CUDA(cudaGetLastError());
     LDPGTA_CUDA(cudaMemcpyAsync(out_scores, a.out, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, c->stream));
     LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
+    // reads that overlap more than 12 common SNPs (long or paired reads): their 2^k combinations are spread over many warps
+    std::vector<int64_t> items;
     for (int64_t r = 0; r < n_reads; ++r)
-        if (out_scores[r] < 0)
-            return fail(LDPGTA_E_UNSUPPORTED, "read %lld overlaps more than 12 common SNPs (2^k haplotype combinations are enumerated)", (long long)r);
+        if (out_scores[r] < 0) {
+            const int k = -out_scores[r];
+            if (k > SCORE_MAXQ)
+                return fail(LDPGTA_E_UNSUPPORTED, "read %lld overlaps %d common SNPs: more than 2^%d haplotype combinations per read are not enumerated",
+                            (long long)r, k, SCORE_MAXQ);
+            for (int64_t chunk = 0; chunk < ((int64_t)1 << (k - 12)); ++chunk) { items.push_back(r); items.push_back(chunk); }
+            out_scores[r] = 0;
+        }
+    if (!items.empty()) {
+        int64_t *d_items = nullptr;
+        LDPGTA_CUDA(cudaMalloc((void **)&d_items, items.size() * 8));
+        cudaError_t e = cudaMemcpyAsync(d_items, items.data(), items.size() * 8, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(a.out, out_scores, (size_t)n_reads * 4, cudaMemcpyHostToDevice, c->stream);   // zeros where the sums go
+        if (e == cudaSuccess) {
+            a.long_items = d_items;
+            a.n_long_items = (int64_t)items.size() / 2;
+            const unsigned nb = (unsigned)std::min<int64_t>((a.n_long_items * 32 + 255) / 256, (int64_t)c->sm_count * 16);
+            k_read_scores_long<<<nb, 256, 0, c->stream>>>(a);
+            c->launches++;
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out_scores, a.out, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        cudaFree(d_items);
+        if (e != cudaSuccess) return fail(LDPGTA_E_CUDA, "scoring long reads failed: %s", cudaGetErrorString(e));
+    }
     return 0;
 }
 
@@ -980,8 +1007,8 @@ int ldpgta_bin_stats(ldpgta_ctx *c, const double *x, int n_series, const int64_t
     } else {
         if (n_series != 5 || c->llr_draws != n_draws || c->llr_windows != n_windows)
             return fail(LDPGTA_E_INVALID, "no resident LLRs for these windows: call ldpgta_window_stats first (5 series)");
-        d_x = c->d_llr;
-        d_off = c->d_llr_off;
+        d_x = c->llr_ptr;
+        d_off = c->llr_off_ptr;
     }
     int64_t *d_rng = (int64_t *)p; p += rng_b;
     double *d_out = (double *)p;

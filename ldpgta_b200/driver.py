@@ -179,36 +179,35 @@ class supporting_dictionaries:
 
 
 def build_gw_dict(obs, window_size, offset, min_reads, max_reads, min_score):
-    """ Genomic windows -> read IDs, fixed or adaptive (ANEUPLOIDY_TEST.py:191-224). The last
-    window of a chromosome is never emitted and empty windows are kept, as in the reference. """
-    max_dist, max_win_size, initial_win_size = 100000, 350000, 10000
-    adaptive, window_size = (False, int(window_size)) if window_size else (True, initial_win_size)
-    offset = int(offset)
-    assert len(obs.positions), 'error: the observation table is empty.'
-    first, last = obs.positions[0] + offset, obs.positions[-1] + window_size
-    a, b = first, first + window_size
-    readIDs_in_window = set()
+    """ Genomic windows -> read IDs (ANEUPLOIDY_TEST.py:191-224), fixed or adaptive.  The window borders come from the
+    array implementation packed.build_windows (one implementation, pinned to the reference's windows in
+    tests/test_packed.py); this wrapper only turns them into the reference's dict.  A window's value is a tuple made
+    from a set that received the qualifying reads position by position, as the reference fills it, so that for a given
+    PYTHONHASHSEED the tuples come out in the reference's order (random.sample indexes into them, :231). """
+    from .packed import build_windows
+    names = list(obs.reads)
+    row_of = {name: i for i, name in enumerate(names)}
+    counts = np.fromiter((len(ids) for ids in obs.overlaps.values()), dtype=np.int64, count=len(obs.overlaps))
+    obs_pos = np.repeat(np.fromiter(obs.overlaps.keys(), dtype=np.int64, count=len(obs.overlaps)), counts)
+    obs_read = np.fromiter((row_of[r] for ids in obs.overlaps.values() for r in ids), dtype=np.int64, count=int(counts.sum()))
+    scores = np.fromiter((obs.score[name] for name in names), dtype=np.int64, count=len(names))
+    win = build_windows(obs_pos, obs_read, scores, window_size, offset, min_reads, min_score)
+    keep = scores[obs_read] >= min_score
+    lo = np.searchsorted(obs_pos, win.borders[:, 0], side='left').tolist()
+    hi = np.searchsorted(obs_pos, win.borders[:, 1], side='right').tolist()
     gw_dict = {}
-    for pos, overlapping_reads in obs.overlaps.items():
-        if pos < first:
-            continue
-        while b < last:
-            if a <= pos < b:
-                readIDs_in_window.update(r for r in overlapping_reads if min_score <= obs.score[r])
-                break
-            elif adaptive and 0 < len(readIDs_in_window) < min_reads and b - pos <= max_dist and b - a <= max_win_size:
-                b += 10000
-            else:
-                gw_dict[a, b - 1] = tuple(readIDs_in_window)
-                a, b = b, b + window_size
-                readIDs_in_window = set()
+    for (a, b), i, j in zip(win.borders.tolist(), lo, hi):
+        members = set()
+        members.update(names[r] for r in obs_read[i:j][keep[i:j]].tolist())
+        gw_dict[a, b] = tuple(members)
     return gw_dict
 
 
 def pick_reads(reads_dict, read_IDs, max_reads):
-    """ One draw without replacement of min(R-1, max_reads) reads (ANEUPLOIDY_TEST.py:226-233). """
-    drawn_read_IDs = random.sample(read_IDs, min(len(read_IDs) - 1, max_reads))
-    return tuple(reads_dict[read_ID] for read_ID in drawn_read_IDs)
+    """ One draw without replacement (ANEUPLOIDY_TEST.py:226-233): max_reads reads, or all but one when the window
+    holds no more than that; returns the reads themselves (lists of alleles). """
+    size = min(max_reads, len(read_IDs) - 1)
+    return tuple(map(reads_dict.__getitem__, random.sample(read_IDs, size)))
 
 
 def effective_number_of_subsamples(num_of_reads, min_reads, max_reads, subsamples):
@@ -439,43 +438,50 @@ def packed_bootstrap(obs_tab, leg_tab, hap_tab, number_of_haplotypes, ancestral_
 
 
 def print_summary(obs_filename, info):
-    """ ANEUPLOIDY_TEST.print_summary (:327-343). """
+    """ The console report of ANEUPLOIDY_TEST.print_summary (:327-343), same text. """
     S = info['statistics']
-    ancestral_makeup = ", ".join("{:.1f}% {}".format(100 * v, k) for k, v in info['ancestral_makeup'].items()) \
-        if type(info['ancestral_makeup']) == dict else ', '.join(info['ancestral_makeup'])
-    matched_alleles = ", ".join("{}: {:.1f}%".format(k, 100 * v) for k, v in info['statistics']['matched_alleles'].items())
-    print('\nFilename: %s' % obs_filename)
-    print('\nSummary statistics')
-    print('------------------')
-    print('Chromosome ID: %s, Depth: %.2f.' % (info['chr_id'], info['depth']))
-    print('Number of genomic windows: %d, Mean and standard error of genomic window size: %d, %d.' %
-          (S.get('num_of_windows', 0), S.get('window_size_mean', 0), S.get('window_size_std', 0)))
-    print('Mean and standard error of meaningful reads per genomic window: %.1f, %.1f.' % (S.get('reads_mean', 0), S.get('reads_std', 0)))
-    print('Ancestral makeup: %s, Fraction of alleles matched to the reference panel: %s.' % (ancestral_makeup, matched_alleles))
-    if S.get('LLRs_per_chromosome', None):
-        for (i, j), L in S['LLRs_per_chromosome'].items():
-            print(f"--- Chromosome-wide LLR between {i:s} and {j:s} ----")
-            print(f"Mean LLR: {L['mean_of_mean']:.3f}, Standard error of the mean LLR: {L['std_of_mean']:.3f}")
-            print(f"Fraction of genomic windows with a negative LLR: {L['fraction_of_negative_LLRs']:.3f}")
+    makeup = info['ancestral_makeup']
+    if isinstance(makeup, dict):
+        makeup_text = ', '.join('%.1f%% %s' % (100 * share, group) for group, share in makeup.items())
+    else:
+        makeup_text = ', '.join(makeup)
+    matched_text = ', '.join('%s: %.1f%%' % (group, 100 * frac) for group, frac in S['matched_alleles'].items())
+    report = ['', 'Filename: %s' % obs_filename, '', 'Summary statistics', '------------------',
+              'Chromosome ID: %s, Depth: %.2f.' % (info['chr_id'], info['depth']),
+              'Number of genomic windows: %d, Mean and standard error of genomic window size: %d, %d.'
+              % tuple(S.get(k, 0) for k in ('num_of_windows', 'window_size_mean', 'window_size_std')),
+              'Mean and standard error of meaningful reads per genomic window: %.1f, %.1f.' % (S.get('reads_mean', 0), S.get('reads_std', 0)),
+              'Ancestral makeup: %s, Fraction of alleles matched to the reference panel: %s.' % (makeup_text, matched_text)]
+    for (num, den), chrom in (S.get('LLRs_per_chromosome') or {}).items():
+        report += ['--- Chromosome-wide LLR between %s and %s ----' % (num, den),
+                   'Mean LLR: %.3f, Standard error of the mean LLR: %.3f' % (chrom['mean_of_mean'], chrom['std_of_mean']),
+                   'Fraction of genomic windows with a negative LLR: %.3f' % chrom['fraction_of_negative_LLRs']]
+    print('\n'.join(report))
+
+
+def llr_filename(obs_filename, output_filename, compress):
+    """ Output name rule of ANEUPLOIDY_TEST.save_results (:352-358): by default the observation file's base name with
+    everything from its last `obs.p` on replaced by `LLR.p`; gz / bz2 add their extension to either form. """
+    ext = '.' + compress if compress in ('bz2', 'gz') else ''
+    if output_filename != '':
+        return output_filename + ext
+    base = obs_filename.rsplit('/', 1)[-1]
+    stem = re.match('(.*)obs.p', base)
+    return stem.group(1) + 'LLR.p' + ext if stem else base
 
 
 def save_results(likelihoods, info, compress, obs_filename, output_filename, output_dir):
-    """ Two consecutive protocol-4 pickles, optional gz/bz2 (ANEUPLOIDY_TEST.py:345-366). """
-    Open = {'bz2': bz2.open, 'gz': gzip.open}.get(compress, open)
-    ext = ('.' + compress) * (compress in ('bz2', 'gz'))
-    obs_filename_stripped = obs_filename.rsplit('/', 1).pop()
-    default_output_filename = re.sub('(.*)obs.p(.*)', f'\\1LLR.p{ext:s}', obs_filename_stripped, 1)
-    if output_filename == '':
-        output_filename = default_output_filename
-    else:
-        output_filename += ext
-    output_dir = output_dir.rstrip('/') + '/'
-    if output_dir != '' and not os.path.exists(output_dir):
-        os.makedirs(output_dir)
-    with Open(output_dir + output_filename, "wb") as f:
-        pickle.dump(likelihoods, f, protocol=4)
-        pickle.dump(info, f, protocol=4)
-    return output_dir + output_filename
+    """ Two consecutive protocol-4 pickles (likelihoods, info), optionally gz / bz2 (ANEUPLOIDY_TEST.py:345-366);
+    returns the path written. """
+    directory = output_dir.rstrip('/') + '/'
+    if not os.path.exists(directory):
+        os.makedirs(directory)
+    path = directory + llr_filename(obs_filename, output_filename, compress)
+    opener = bz2.open if compress == 'bz2' else gzip.open if compress == 'gz' else open
+    with opener(path, 'wb') as f:
+        for obj in (likelihoods, info):
+            pickle.dump(obj, f, protocol=4)
+    return path
 
 
 def _opener(filename):
@@ -534,34 +540,40 @@ def aneuploidy_test(obs_filename, leg_filename, hap_filename, ancestral_makeup, 
     return likelihoods, info
 
 
+def parse_ancestral_makeup(tokens):
+    """ The positional ANCESTRAL_MAKEUP of the CLI (ANEUPLOIDY_TEST.py:481-489): one or two population names -> set
+    (non-admixed / recent admixture); NAME PROPORTION pairs -> dict (distant admixture). """
+    names, rest = tokens[0::2], tokens[1::2]
+    is_number = lambda t: t.replace('.', '', 1).isdigit()
+    if all(t.isalpha() for t in tokens) and len(tokens) in (1, 2):
+        return set(tokens)
+    if all(t.isalpha() for t in names) and all(map(is_number, rest)):
+        return dict(zip(names, map(float, rest)))
+    raise Exception('error: Invalid argument supplied for ancestral makeup.')
+
+
 def main(argv=None):
-    """ The CLI of ANEUPLOIDY_TEST.py:440-493. """
+    """ The command line of ANEUPLOIDY_TEST.py (:440-493): same positionals, flags and defaults. """
     import argparse
-    parser = argparse.ArgumentParser(
-        description='Builds a dictionary that lists genomic windows that contain at least three reads and gives the '
-                    'associated log-likelihood BPH/SPH ratio (LLR), on a B200 GPU.')
-    parser.add_argument('obs_filename', metavar='OBS_FILENAME', type=str, help='An observations file created by MAKE_OBS_TAB.')
-    parser.add_argument('leg_filename', metavar='LEG_FILENAME', type=str, help='A legend file of the reference panel.')
-    parser.add_argument('hap_filename', metavar='HAP_FILENAME', type=str, help='A haplotype file of the reference panel.')
+    parser = argparse.ArgumentParser(description='Log-likelihood ratios of BPH / SPH / disomy / monosomy for the genomic windows of one '
+                                                 'chromosome of a low-coverage sample, computed on a B200 GPU.')
+    for name, text in (('obs_filename', 'observations file made by MAKE_OBS_TAB'), ('leg_filename', 'legend file of the reference panel'),
+                       ('hap_filename', 'haplotype file of the reference panel')):
+        parser.add_argument(name, metavar=name.upper(), type=str, help=text)
     parser.add_argument('ancestral_makeup', metavar='ANCESTRAL_MAKEUP', nargs='+',
-                        help='One superpopulation (non-admixed), two (recent admixture), or NAME PROPORTION pairs (distant admixture).')
-    parser.add_argument('-w', '--window-size', type=int, metavar='INT', default='100000')
-    parser.add_argument('-s', '--subsamples', type=int, metavar='INT', default='32')
-    parser.add_argument('-o', '--offset', type=int, metavar='INT', default=0)
-    parser.add_argument('-m', '--min-reads', type=int, metavar='INT', default=6)
-    parser.add_argument('-M', '--max-reads', type=int, metavar='INT', default=4)
-    parser.add_argument('-F', '--min-HF', type=float, metavar='FLOAT', default=0.05)
-    parser.add_argument('-S', '--min-score', type=int, metavar='INT', default=2)
-    parser.add_argument('-O', '--output-filename', type=str, metavar='output_filename', default='')
+                        help='EUR (non-admixed) | EUR EAS (recent admixture) | EUR 0.8 EAS 0.1 SAS 0.1 (distant admixture)')
+    for short, name, kind, default, text in (
+            ('-w', '--window-size', int, '100000', 'genomic window in bp; 0 = adaptive windows holding min-reads reads'),
+            ('-s', '--subsamples', int, '32', 'bootstrap draws per genomic window'),
+            ('-o', '--offset', int, 0, 'shift of all genomic windows in bp'),
+            ('-m', '--min-reads', int, 6, 'windows with fewer scored reads are skipped'),
+            ('-M', '--max-reads', int, 4, 'reads per bootstrap draw'),
+            ('-F', '--min-HF', float, 0.05, 'haplotype frequencies in [FLOAT, 1-FLOAT] add to the score of a read'),
+            ('-S', '--min-score', int, 2, 'minimal score of a read')):
+        parser.add_argument(short, name, type=kind, metavar='FLOAT' if kind is float else 'INT', default=default, help=text)
+    parser.add_argument('-O', '--output-filename', type=str, metavar='output_filename', default='',
+                        help='default: the input name with .obs.p replaced by .LLR.p')
     parser.add_argument('-C', '--compress', metavar='gz/bz2/unc', type=str, default='unc', choices=['gz', 'bz2', 'unc'])
     args = vars(parser.parse_args(argv))
-    strings_even = all(i.isalpha() for i in args['ancestral_makeup'][0::2])
-    strings_odd = all(i.isalpha() for i in args['ancestral_makeup'][1::2])
-    floats_odd = all(i.replace('.', '', 1).isdigit() for i in args['ancestral_makeup'][1::2])
-    if strings_even and strings_odd and len(args['ancestral_makeup']) in (1, 2):
-        args['ancestral_makeup'] = set(args['ancestral_makeup'])
-    elif strings_even and floats_odd:
-        args['ancestral_makeup'] = dict(zip(args['ancestral_makeup'][0::2], map(float, args['ancestral_makeup'][1::2])))
-    else:
-        raise Exception('error: Invalid argument supplied for ancestral makeup.')
+    args['ancestral_makeup'] = parse_ancestral_makeup(args['ancestral_makeup'])
     return aneuploidy_test(**args)

@@ -94,6 +94,7 @@ class Engine:
         self.padded_words = [N.check(self.lib.ldpgta_padded_row_words(self._ctx, g)) for g in range(self.G)]
         self.n_alleles = 0
         self._keepalive = []
+        self._plan = None
 
     # ---- lifetime -------------------------------------------------------
     def close(self):
@@ -288,7 +289,7 @@ class Engine:
         return dict(zip(keys, out.tolist()))
 
     def _stats_outputs(self, want, lik_out=None, out=None):
-        p = self._plan
+        p = self._plan if self._plan is not None else self.plan_info()      # raises without a resident plan
         nd, nw, ns, ncp = p['n_draws'], p['n_windows'], p['n_segments'], p['ncp']
         if out is not None:                      # caller-owned (e.g. page-locked) arrays, reused from call to call
             shapes = {'lik': (nd, 4), 'draws': (p['nnz'],), 'llr': (N.NUM_LLR_PAIRS, nd), 'mean_var': (N.NUM_LLR_PAIRS, nw, 2),

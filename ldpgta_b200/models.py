@@ -29,7 +29,12 @@ def _namedtuple(module):
     return t
 
 
-likelihoods_tuple = _namedtuple(__name__)
+# One result-record class per reference module, defined ONCE: the reference pickles likelihoods_tuple instances under the
+# bare module names (`HOMOGENOUES_MODELS.likelihoods_tuple` in *.LLR.p), and its readers (PLOT_PANEL, BALANCED_ROC_CURVE)
+# unpickle them by that path.  The modules of those names in this package re-export these very objects, whichever way
+# they were imported (flat or as ldpgta_b200.X), so what gets pickled never depends on the import order.
+TUPLES = {name: _namedtuple(name) for name in ('HOMOGENOUES_MODELS', 'RECENT_ADMIXTURE_MODELS', 'DISTANT_ADMIXTURE_MODELS')}
+likelihoods_tuple = TUPLES['HOMOGENOUES_MODELS']
 leg_tuple = collections.namedtuple('leg_tuple', ('chr_id', 'pos', 'ref', 'alt'))
 obs_tuple = collections.namedtuple('obs_tuple', ('pos', 'read_id', 'base'))
 
@@ -208,6 +213,7 @@ class _PanelModel:
 class homogeneous(_PanelModel):
     """ Single-population model; same constructor and checks as HOMOGENOUES_MODELS.py:52-73. """
     kind = N.HOMOGENEOUS
+    tuple_type = TUPLES['HOMOGENOUES_MODELS']
 
     def __init__(self, obs_tab, leg_tab, hap_tab_per_group, number_of_haplotypes_per_group, models_dict, device=0, panel=None):
         print('Initializing the algorithm for non-admixtures:')
@@ -242,6 +248,7 @@ class homogeneous(_PanelModel):
 class recent_admixture(_PanelModel):
     """ Two populations, each parent from one of them (RECENT_ADMIXTURE_MODELS.py:54-80). """
     kind = N.RECENT_ADMIXTURE
+    tuple_type = TUPLES['RECENT_ADMIXTURE_MODELS']
 
     def __init__(self, obs_tab, leg_tab, hap_tab_per_group, number_of_haplotypes_per_group, models_dict, device=0, panel=None):
         print('Initializing the algorithm for recent admixtures:')
@@ -274,6 +281,7 @@ class recent_admixture(_PanelModel):
 class distant_admixture(_PanelModel):
     """ Any number of populations with ancestral proportions (DISTANT_ADMIXTURE_MODELS.py:53-79). """
     kind = N.DISTANT_ADMIXTURE
+    tuple_type = TUPLES['DISTANT_ADMIXTURE_MODELS']
 
     def __init__(self, obs_tab, leg_tab, hap_tab_per_group, number_of_haplotypes_per_group, models_dict, ancestral_makeup, device=0):
         print('Initializing the algorithm for distant admixtures:')

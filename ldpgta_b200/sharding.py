@@ -56,16 +56,26 @@ def allreduce_chromosome(partials, n_cols_local, first_window_draws, group=None,
     fraction_of_negative_LLRs).  n_cols is the smallest draw count over ALL windows of the
     chromosome (zip truncation, ANEUPLOIDY_TEST.py:73): ranks first agree on it (MIN), truncate
     their column sums, then add.  first_window_draws = len(A[0]) of the reference, taken from the
-    rank that owns the chromosome's first window (others pass 0; MAX picks it). """
+    rank that owns the chromosome's first window (others pass 0; MAX picks it).
+    A rank that owns NO window of the chromosome (more ranks than windows, or the cost concentrated in
+    a few windows) still takes part in both collectives: it passes partials=None and n_cols_local=None,
+    contributing nothing to the minimum and zeros to the sum.  With no window anywhere the result is NaN. """
     import torch
     import torch.distributed as dist
-    partials = np.asarray(partials, dtype=np.float64)
+    empty = partials is None or n_cols_local is None
     if not (dist.is_available() and dist.is_initialized()):
-        return finish_chromosome(partials[:, :n_cols_local + 3], n_cols_local, first_window_draws)
+        if empty:
+            return np.full((5, 3), np.nan)
+        partials = np.asarray(partials, dtype=np.float64)
+        return finish_chromosome(np.ascontiguousarray(partials[:, :n_cols_local + 3]), n_cols_local, first_window_draws)
     dev = device if device is not None else ('cuda' if dist.get_backend(group) == 'nccl' else 'cpu')
-    meta = torch.tensor([-float(n_cols_local), float(first_window_draws)], dtype=torch.float64, device=dev)
+    meta = torch.tensor([-np.inf if empty else -float(n_cols_local), 0.0 if empty else float(first_window_draws)],
+                        dtype=torch.float64, device=dev)
     dist.all_reduce(meta, op=dist.ReduceOp.MAX, group=group)          # max(-n_cols) = -min(n_cols)
+    if not np.isfinite(meta[0].item()):
+        return np.full((5, 3), np.nan)                                 # no rank holds a window of this chromosome
     n_cols, first = int(-meta[0].item()), int(meta[1].item())
-    t = torch.from_numpy(np.ascontiguousarray(partials[:, :n_cols + 3])).to(dev)
+    mine = np.zeros((5, n_cols + 3)) if empty else np.ascontiguousarray(np.asarray(partials, dtype=np.float64)[:, :n_cols + 3])
+    t = torch.from_numpy(mine).to(dev)
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return finish_chromosome(t.cpu().numpy(), n_cols, first)

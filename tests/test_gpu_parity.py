@@ -446,6 +446,33 @@ def test_read_scores_on_device_match_reference(name, golden_inputs):
         model.close()
 
 
+@pytest.mark.parametrize('name', ('homog_m4', 'distant_m4'))
+def test_read_scores_of_long_reads(name, golden_inputs):
+    """ A read that overlaps 13..15 common SNPs (long or paired reads): the reference enumerates all 2^k haplotype
+    combinations (ANEUPLOIDY_TEST.py:178-184); the device spreads them over many warps.  Checked against the oracle's
+    restatement of build_score_dict, which the golden chromosome vectors pin to the reference. """
+    args, out = chrom_case(name, golden_inputs)
+    cfg = args['cfg']
+    obs = list(args['obs_tab'])
+    seen, extra = set(), []
+    for k, (first, step) in enumerate(((40, 3), (300, 2), (900, 5))):
+        picked = []
+        for pos, _rid, base in obs[first::step]:
+            if pos not in seen and len(picked) < 13 + k:
+                picked.append((pos, base)); seen.add(pos)
+        extra += [(pos, 'long.read.%d' % k, base) for pos, base in picked]
+    obs_long = sorted(obs + extra, key=lambda r: r[0])
+    want = O.SupportingDictionaries(obs_long, args['leg_tab'], args['hap_tab'], args['number_of_haplotypes'], args['ancestral_makeup'], cfg['min_HF']).score
+    model = driver.make_examiner(obs_long, args['leg_tab'], args['hap_tab'], args['number_of_haplotypes'], args['ancestral_makeup'], L.ImplicitModels())
+    try:
+        got = driver.supporting_dictionaries(obs_long, args['leg_tab'], args['hap_tab'], args['number_of_haplotypes'],
+                                             args['ancestral_makeup'], cfg['min_HF'], examine=model).score
+    finally:
+        model.close()
+    assert got == want
+    assert all(want['long.read.%d' % k] > 0 for k in range(3))
+
+
 def test_repeatability_stress_multi_group():
     """ Races show up as run-to-run differences: many CTAs per SM, two groups, chunked tables; every batch is
     evaluated three times and must be bit-identical, and a slice is checked against the oracle. """

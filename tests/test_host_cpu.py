@@ -123,6 +123,29 @@ print('ok')
     assert out.strip().endswith('ok')
 
 
+def test_package_api_pickles_under_reference_module_names():
+    """ Results made through the package API (ldpgta_b200.homogeneous / bootstrap / aneuploidy_test) carry the same
+    result-record classes as the flat drop-in modules, whichever was imported first: *.LLR.p files name
+    HOMOGENOUES_MODELS.likelihoods_tuple etc., never a path inside this package. """
+    code = r'''
+import sys, pickle
+sys.path.insert(0, %r)
+%s
+import ldpgta_b200 as L
+from ldpgta_b200 import driver
+for cls, name in ((L.homogeneous, b'HOMOGENOUES_MODELS'), (L.recent_admixture, b'RECENT_ADMIXTURE_MODELS'), (L.distant_admixture, b'DISTANT_ADMIXTURE_MODELS')):
+    t = cls.tuple_type(1.0, 2.0, 3.0, 4.0)
+    blob = pickle.dumps({(0, 99): (t,)}, protocol=4)
+    assert name in blob and b'ldpgta' not in blob, blob
+    assert pickle.loads(blob)[(0, 99)][0] == t
+assert driver.homogeneous is L.homogeneous and driver.homogeneous.tuple_type is sys.modules['HOMOGENOUES_MODELS'].likelihoods_tuple
+print('ok')
+'''
+    for first in ('', 'sys.path.insert(0, %r); import HOMOGENOUES_MODELS, ANEUPLOIDY_TEST' % os.path.join(ROOT, 'ldpgta_b200')):
+        out = subprocess.check_output([sys.executable, '-c', code % (ROOT, first)], cwd='/tmp').decode()
+        assert out.strip().endswith('ok')
+
+
 def test_host_statistics_helpers_match_oracle():
     rng = random.Random(3)
     A = {w: tuple(rng.uniform(-1, 1) for _ in range(6)) for w in range(9)}

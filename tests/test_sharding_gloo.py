@@ -46,18 +46,21 @@ def _partials(lik_items, n_cols):
     return out
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, n_windows=37):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import torch.distributed as dist
     from ldpgta_b200 import sharding
     dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world)
-    lik, reads = _chromosome()
+    lik, reads = _chromosome(n_windows=n_windows)
     mine = sharding.shard_windows(reads, rank, world, min_reads=6, max_reads=4, subsamples=32, row_words=79)
     items = [(w, lik[w]) for w in mine]
-    n_cols_local = min(len(ls) for _, ls in items)
-    first = len(items[0][1]) if rank == 0 else 0
-    res = sharding.allreduce_chromosome(_partials(items, n_cols_local), n_cols_local, first)
+    if items:
+        n_cols_local = min(len(ls) for _, ls in items)
+        first = len(items[0][1]) if mine[0] == next(iter(lik)) else 0
+        res = sharding.allreduce_chromosome(_partials(items, n_cols_local), n_cols_local, first)
+    else:                                                   # a rank without windows still joins the collectives
+        res = sharding.allreduce_chromosome(None, None, 0)
     q.put((rank, [w for w in mine], res.tolist()))
     dist.destroy_process_group()
 
@@ -83,6 +86,28 @@ def test_two_rank_chromosome_statistics():
         for p, pair in enumerate(O.LLR_PAIRS):
             assert abs(res[p, 0] - want[pair]['mean_of_mean']) < 1e-12
             assert abs(res[p, 1] - want[pair]['std_of_mean']) < 1e-12
+            assert res[p, 2] == want[pair]['fraction_of_negative_LLRs']
+
+
+def test_more_ranks_than_windows():
+    """ world_size 3, one window: two ranks own nothing, pass the empty contribution, and all three get the statistics. """
+    world, port = 3, _free_port()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, 1)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    lik, reads = _chromosome(n_windows=1)
+    assert sorted(len(g[1]) for g in got) == [0, 0, 1]
+    want = O.statistics(lik, reads)['LLRs_per_chromosome']
+    for r in range(world):
+        res = np.array(got[r][2])
+        for p, pair in enumerate(O.LLR_PAIRS):
+            assert abs(res[p, 0] - want[pair]['mean_of_mean']) < 1e-12
             assert res[p, 2] == want[pair]['fraction_of_negative_LLRs']
 
 
