@@ -627,8 +627,9 @@ def main():
         if kind_cpu == 'reference':                            # the oracle port's rate beside it (int.bit_count instead of the byte LUT)
             pcls, _, ppc = cpu_model_class(prefer_reference=False)
             ps, pn, pw, pref = sample(pcls, min(3.0, args.cpu_seconds), 20)
+            m = min(len(pref), len(ref_v))
             cpu_baseline['port'] = {'value': pn / ps, 'popcount': ppc, 'sample': 'first %d windows (%.1f s)' % (pw, ps),
-                                    'max_rel_diff_vs_reference': float(np.max(np.abs(pref - ref_v[:pn]) / np.maximum(np.abs(ref_v[:pn]), 1e-300)))}
+                                    'max_rel_diff_vs_reference': float(np.max(np.abs(pref[:m] - ref_v[:m]) / np.maximum(np.abs(ref_v[:m]), 1e-300)))}
 
     secondary = None
     if not args.no_secondary and args.model == 'homogeneous' and not args.windows:
@@ -691,39 +692,49 @@ def strong_scaling_leg(L, torch, dist, device, local, rank, world, args, kind, g
     partials = torch.zeros((n_seg, 5, ncp + 3), dtype=torch.float64, device=device)
     stats = torch.zeros((n_seg, 5, 3), dtype=torch.float64, device=device)
     steps, warm = args.steps, args.warmup
+    sharding.connect_peers(leg.eng, partials.numel())
 
-    def step(ev=None):
+    def step(how, ev=None):
         leg.step(partials.data_ptr())
         if ev is not None:
             ev[0].record(leg.stream)
-        dist.all_reduce(partials)
+        if how == 'peer':
+            leg.eng.allreduce_chrom_dev(partials.data_ptr(), partials.numel())     # one kernel over NVLink peer memory
+        else:
+            dist.all_reduce(partials)
         if ev is not None:
             ev[1].record(leg.stream)
         leg.eng.finish_segments_dev(partials.data_ptr(), stats.data_ptr())
 
+    res = {}
     with torch.cuda.stream(leg.stream):
-        for _ in range(warm):
-            step()
-        leg.eng.synchronize()
-        barrier()
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(leg.stream)
-        for k in range(steps):
-            step(evs[k])
-        e1.record(leg.stream)
-        leg.eng.synchronize()
-        barrier()
-    total_ms = max_over_ranks(e0.elapsed_time(e1))
-    ar_ms = max_over_ranks(float(np.median([a.elapsed_time(b) for a, b in evs])))
-    finite = bool(torch.isfinite(stats).all().item())
+        for how in ('peer', 'nccl'):
+            for _ in range(warm):
+                step(how)
+            leg.eng.synchronize()
+            barrier()
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(leg.stream)
+            for k in range(steps):
+                step(how, evs[k])
+            e1.record(leg.stream)
+            leg.eng.synchronize()
+            barrier()
+            res[how] = (max_over_ranks(e0.elapsed_time(e1)), max_over_ranks(float(np.median([a.elapsed_time(b) for a, b in evs]))),
+                        stats.cpu().numpy().copy())
+    total_ms, ar_ms, st = res['peer']
+    finite = bool(np.isfinite(st).all())
     windows_here = hi - lo
     leg.close()
     torch.cuda.empty_cache()
-    return {'workload': 'ONE configs[1] embryo, windows dealt to %d ranks by cost, chromosome partial sums all-reduced every step' % world,
+    return {'workload': 'ONE configs[1] embryo, windows dealt to %d ranks by cost, chromosome partial sums summed across the GPUs every step' % world,
             'scaling': 'strong', 'value': len(reads) * subs * steps / (total_ms * 1e-3), 'unit': 'window-likelihoods/s',
             'ms_per_step': total_ms / steps, 'windows_rank0': int(windows_here), 'allreduce_bytes': int(partials.numel() * 8),
-            'allreduce_ms_median': ar_ms, 'allreduce_share_of_step': ar_ms / (total_ms / steps), 'collective': 'torch.distributed all_reduce (NCCL) on the device-resident partials',
+            'allreduce_ms_median': ar_ms, 'allreduce_share_of_step': ar_ms / (total_ms / steps),
+            'collective': 'ldpgta_allreduce_chrom_dev: one kernel over NVLink peer memory (publish, flag peers, poll locally, peer loads, rank-order sum)',
+            'nccl_comparison': {'ms_per_step': res['nccl'][0] / steps, 'allreduce_ms_median': res['nccl'][1],
+                                'collective': 'torch.distributed all_reduce (NCCL) on the same device-resident partials'},
             'statistics_finite': finite}
 
 

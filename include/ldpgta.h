@@ -49,6 +49,8 @@ enum { LDPGTA_HOMOGENEOUS = 0, LDPGTA_RECENT_ADMIXTURE = 1, LDPGTA_DISTANT_ADMIX
 
 #define LDPGTA_MAX_GROUPS 8
 #define LDPGTA_MAX_READS_PER_DRAW 18   /* reads per draw handled on device = the largest model table the reference ships (MODELS18.p) */
+#define LDPGTA_MAX_PEERS 16             /* GPUs of one node that can share a chromosome (ldpgta_comm_*) */
+#define LDPGTA_COMM_HANDLE_BYTES 128    /* opaque handle of a rank's exchange buffer */
 #define LDPGTA_NUM_LLR_PAIRS 5         /* (BPH,SPH) (disomy,monosomy) (BPH,disomy) (disomy,SPH) (SPH,monosomy) */
 
 const char *ldpgta_last_error(void);
@@ -214,6 +216,25 @@ int ldpgta_replay_stats(ldpgta_ctx *ctx, int model_kind, const int32_t *read_idx
 int ldpgta_bootstrap_stats_dev(ldpgta_ctx *ctx, int model_kind, uint64_t seed, const double *proportions,
                                double *segment_partials_dev);
 int ldpgta_finish_segments_dev(ldpgta_ctx *ctx, const double *segment_partials_dev, double *segment_stats_dev);
+/* ---- the cross-GPU exchange: the sum of the ranks' segment (chromosome) partial sums ----------------------------------
+ * One process per GPU.  When the windows of one chromosome are dealt to several GPUs, the column sums of
+ * mean_and_std_of_mean_of_rnd_var (ANEUPLOIDY_TEST.py:65-76) have to be added across them; nothing else of the path
+ * crosses GPUs.  The sum is ONE kernel over NVLink / NVSwitch peer memory (publish in own HBM, flag the peers by remote
+ * stores, poll locally, read the peers' partials by peer loads, add in rank order: every rank gets bit-identical sums);
+ * no library collective is involved.
+ *   ldpgta_comm_create   allocates this rank's exchange buffer for up to max_doubles values and writes its handle
+ *                        (LDPGTA_COMM_HANDLE_BYTES bytes, to be passed to every peer by any byte transport)
+ *   ldpgta_comm_connect  handles[world][LDPGTA_COMM_HANDLE_BYTES] of all ranks, in rank order (CUDA IPC between
+ *                        processes, direct peer access between contexts of one process)
+ *   ldpgta_allreduce_chrom_dev  partials_dev[n_doubles] (device memory, e.g. the segment_partials_dev of
+ *                        ldpgta_bootstrap_stats_dev) becomes the sum over ranks, in place, asynchronously on the context's
+ *                        stream; every rank must call it the same number of times with the same n_doubles.  A peer that
+ *                        does not arrive within ~2 s makes the NEXT call fail (the kernel never spins forever). */
+int ldpgta_comm_create(ldpgta_ctx *ctx, int rank, int world, int64_t max_doubles, unsigned char *handle_out);
+int ldpgta_comm_connect(ldpgta_ctx *ctx, const unsigned char *handles);
+int ldpgta_allreduce_chrom_dev(ldpgta_ctx *ctx, double *partials_dev, int64_t n_doubles);
+int ldpgta_comm_destroy(ldpgta_ctx *ctx);
+
 /* Measurement aid: with enable != 0 the calls above bracket their draw kernels (k_small / k_mid / k_lanes / k_general, not
  * the sampler or the reductions) with CUDA events on the context's stream; ldpgta_kernel_times waits for the stream,
  * writes the elapsed milliseconds of every bracket since the last call (at most max_entries) and returns their number. */

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'libldpgta.so')
 HOMOGENEOUS, RECENT_ADMIXTURE, DISTANT_ADMIXTURE = 0, 1, 2
 MAX_READS_PER_DRAW = 18
 NUM_LLR_PAIRS = 5
+COMM_HANDLE_BYTES = 128
 
 # every symbol include/ldpgta.h declares: (name, restype, argtypes)
 _c = ctypes
@@ -51,6 +52,10 @@ SYMBOLS = (
     ('ldpgta_bootstrap_stats_dev', _c.c_int, [_P, _c.c_int, _c.c_uint64, _P, _P]),
     ('ldpgta_finish_segments_dev', _c.c_int, [_P, _P, _P]),
     ('ldpgta_plan_info', _c.c_int, [_P, _P]),
+    ('ldpgta_comm_create', _c.c_int, [_P, _c.c_int, _c.c_int, _c.c_int64, _P]),
+    ('ldpgta_comm_connect', _c.c_int, [_P, _P]),
+    ('ldpgta_allreduce_chrom_dev', _c.c_int, [_P, _P, _c.c_int64]),
+    ('ldpgta_comm_destroy', _c.c_int, [_P]),
     ('ldpgta_kernel_timing', _c.c_int, [_P, _c.c_int]),
     ('ldpgta_kernel_times', _c.c_int, [_P, _P, _c.c_int]),
     ('ldpgta_window_stats', _c.c_int, [_P, _P, _P, _c.c_int64, _c.c_int, _P, _P, _P]),

@@ -20,6 +20,7 @@ struct SizeClass {
     int32_t *d_win = nullptr;      // device copy of win (nullptr: identity, the plan has one class)
     int32_t *d_idx = nullptr;      // [n_draws][n] draws of the class
     int64_t *d_pos = nullptr;      // [n_draws] place of each draw in the sample-wide order (nullptr: identity)
+    int32_t *d_wod = nullptr;      // [n_draws] class window of each draw (the sampler's window lookup)
 };
 
 struct WindowPlan {
@@ -104,12 +105,9 @@ static int stats_on_device(ldpgta_ctx *c, const double *d_lik, const int64_t *d_
         k_window_stats<<<blocks, sh.wpb * 32, sh.smem, c->stream>>>(a);
         c->launches++;
     }
-    k_segment_partials<<<dim3((unsigned)n_segments, 5), 128, 0, c->stream>>>(d_runs, d_segoff, d_segcols, ncp, sh.cw, d_partials);
+    k_segment_partials<<<dim3((unsigned)n_segments, 5), SEG_ROWS * SEG_COLS, 0, c->stream>>>(d_runs, d_segoff, d_segcols, d_segfirst, ncp, sh.cw,
+                                                                                          d_partials, d_stats);
     c->launches++;
-    if (d_stats) {
-        k_finish_segments<<<(n_segments * 5 + 127) / 128, 128, 0, c->stream>>>(d_partials, d_segcols, d_segfirst, n_segments, ncp, d_stats);
-        c->launches++;
-    }
     LDPGTA_CUDA(cudaGetLastError());
     return 0;
 }
@@ -282,7 +280,7 @@ int ldpgta_set_windows(ldpgta_ctx *c, const int64_t *window_offsets, const int32
     const size_t o_woff = take(window_offsets ? (size_t)(n_windows + 1) * 8 : 0), o_doff = take((size_t)(n_windows + 1) * 8);
     const size_t o_seg = take((size_t)(n_segments + 1) * 8), o_cols = take((size_t)n_segments * 4), o_first = take((size_t)n_segments * 4);
     const size_t o_wreads = take((size_t)p->n_wreads * 4), o_seed = take(8);
-    struct ClsOff { size_t doff, win, pos; };
+    struct ClsOff { size_t doff, win, pos, wod; };
     std::vector<ClsOff> co;
     for (int n = 2; n <= MAXN; ++n) {
         if (!per_n[n]) continue;
@@ -293,6 +291,7 @@ int ldpgta_set_windows(ldpgta_ctx *c, const int64_t *window_offsets, const int32
         o.doff = take((size_t)(win_n[n] + 1) * 8);
         o.win = single ? 0 : take((size_t)win_n[n] * 4);
         o.pos = single ? 0 : take((size_t)per_n[n] * 8);
+        o.wod = window_offsets ? take((size_t)per_n[n] * 4) : 0;
         co.push_back(o);
     }
     const size_t static_bytes = std::max<size_t>(off, 256);
@@ -308,6 +307,7 @@ int ldpgta_set_windows(ldpgta_ctx *c, const int64_t *window_offsets, const int32
         int64_t *cd = (int64_t *)(img.data() + co[ci].doff);
         int32_t *cwn = single ? nullptr : (int32_t *)(img.data() + co[ci].win);
         int64_t *cp = single ? nullptr : (int64_t *)(img.data() + co[ci].pos);
+        int32_t *cwod = window_offsets ? (int32_t *)(img.data() + co[ci].wod) : nullptr;
         int64_t j = 0, d = 0;
         cd[0] = 0;
         k.win.reserve((size_t)k.n_windows);
@@ -315,6 +315,7 @@ int ldpgta_set_windows(ldpgta_ctx *c, const int64_t *window_offsets, const int32
             if (reads_per_draw[w] != k.n) continue;
             const int64_t nd = draw_offsets[w + 1] - draw_offsets[w];
             k.win.push_back((int32_t)w);
+            if (cwod) std::fill(cwod + d, cwod + d + nd, (int32_t)j);
             if (!single) {
                 cwn[j] = (int32_t)w;
                 for (int64_t t = 0; t < nd; ++t) cp[d + t] = draw_offsets[w] + t;
@@ -337,6 +338,7 @@ int ldpgta_set_windows(ldpgta_ctx *c, const int64_t *window_offsets, const int32
         p->classes[ci].d_doff = (int64_t *)(base + co[ci].doff);
         p->classes[ci].d_win = single ? nullptr : (int32_t *)(base + co[ci].win);
         p->classes[ci].d_pos = single ? nullptr : (int64_t *)(base + co[ci].pos);
+        p->classes[ci].d_wod = window_offsets ? (int32_t *)(base + co[ci].wod) : nullptr;
     }
     // window read lists are checked on the device (the copy is clamped, the call fails)
     if (p->n_wreads) {
@@ -387,7 +389,7 @@ int ldpgta_bootstrap_stats(ldpgta_ctx *c, int kind, uint64_t seed, const double 
     for (const SizeClass &k : p->classes) {
         SampleArgs sa;
         memset(&sa, 0, sizeof sa);
-        sa.draw_off = k.d_doff; sa.win_off = p->d_woff; sa.win_reads = p->d_wreads; sa.cls_win = k.d_win;
+        sa.draw_off = k.d_doff; sa.win_of_draw = k.d_wod; sa.win_off = p->d_woff; sa.win_reads = p->d_wreads; sa.cls_win = k.d_win;
         sa.n_windows = k.n_windows; sa.n_draws = k.n_draws; sa.seed = seed + (uint64_t)k.n; sa.idx_out = k.d_idx;
         if (int rc = launch_sample(c, k.n, sa)) return rc;
     }
@@ -477,7 +479,7 @@ int ldpgta_bootstrap_stats_dev(ldpgta_ctx *c, int kind, uint64_t seed, const dou
     for (const SizeClass &k : p->classes) {
         SampleArgs sa;
         memset(&sa, 0, sizeof sa);
-        sa.draw_off = k.d_doff; sa.win_off = p->d_woff; sa.win_reads = p->d_wreads; sa.cls_win = k.d_win;
+        sa.draw_off = k.d_doff; sa.win_of_draw = k.d_wod; sa.win_off = p->d_woff; sa.win_reads = p->d_wreads; sa.cls_win = k.d_win;
         sa.n_windows = k.n_windows; sa.n_draws = k.n_draws; sa.seed = seed + (uint64_t)k.n; sa.idx_out = k.d_idx;
         if (int rc = launch_sample(c, k.n, sa)) return rc;
     }
@@ -494,7 +496,7 @@ int ldpgta_finish_segments_dev(ldpgta_ctx *c, const double *segment_partials_dev
     if (!c || !c->plan) return fail(LDPGTA_E_STATE, "no windows are resident: call ldpgta_set_windows first");
     LDPGTA_CUDA(cudaSetDevice(c->device));
     WindowPlan *p = c->plan;
-    k_finish_segments<<<(p->n_segments * 5 + 127) / 128, 128, 0, c->stream>>>(segment_partials_dev ? segment_partials_dev : p->d_partials,
+    k_finish_segments<<<(p->n_segments * 5 * 32 + 127) / 128, 128, 0, c->stream>>>(segment_partials_dev ? segment_partials_dev : p->d_partials,
                                                                             p->d_segcols, p->d_segfirst, p->n_segments, p->ncp,
                                                                             segment_stats_dev ? segment_stats_dev : p->d_stats);
     c->launches++;

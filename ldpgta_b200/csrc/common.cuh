@@ -235,6 +235,7 @@ struct ldpgta_ctx {
 
     // windows + bootstrap plan made resident by ldpgta_set_windows (bootstrap_api.cu)
     ldpgta::WindowPlan *plan = nullptr;
+    void *comm = nullptr;                     // peer-memory communicator (comm_api.cu)
     // optional CUDA-event brackets around the draw kernels of the resident pipeline (ldpgta_kernel_timing)
     bool time_kernels = false;
     std::vector<cudaEvent_t> t_ev;      // pairs (start, stop), reused
@@ -281,6 +282,7 @@ int run_uniform(ldpgta_ctx *c, int kind, int n, const int32_t *idx_dev, int64_t 
                 const PanelView *override_view = nullptr);
 int launch_sample(ldpgta_ctx *c, int n, const SampleArgs &a);      // pick_reads on the device, n reads per draw
 void free_window_plan(ldpgta_ctx *c);
+void free_comm(ldpgta_ctx *c);
 
 template <class T>
 inline int ensure_own(T **ptr, size_t *have, size_t bytes)

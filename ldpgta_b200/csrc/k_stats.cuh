@@ -302,25 +302,39 @@ static __global__ void k_window_stats(const StatsArgs a)
             const int64_t b = a.doff[w], e = a.doff[w + 1];
             const double cnt = (double)(e - b);
             if (e - b <= 32) {
-                // one draw per lane: both passes from registers, plain tree sums (5 roundings)
+                // one draw per lane: both passes from registers, plain tree sums (5 roundings).  The five means and
+                // the five variances are each ONE float64 division executed by lanes 0..4 side by side (a division is
+                // ~40 instructions whether one lane or all need it), the means then travel back by shuffle.
                 const bool live = b + lane < e;
-                double x[5];
+                double x[5], sum[5];
 #pragma unroll
                 for (int p = 0; p < 5; ++p) x[p] = live ? __ldg(a.llr + (int64_t)p * a.n_draws + b + lane) : 0.0;
 #pragma unroll
                 for (int p = 0; p < 5; ++p) {
                     if (live && lane < a.ncp) cols[p * a.ncp + lane] += x[p];
-                    const double s = warp_sum_f64(x[p]);
-                    const double m = s / cnt;
-                    const double d = live ? x[p] - m : 0.0;
-                    const double ss = warp_sum_f64(d * d);
-                    total[p].add(s);
+                    sum[p] = warp_sum_f64(x[p]);
+                    total[p].add(sum[p]);
+                }
+                double mine = sum[0];
+#pragma unroll
+                for (int p = 1; p < 5; ++p) mine = lane == p ? sum[p] : mine;
+                const double mean_l = mine / cnt;                          // lane p < 5: mean of pair p
+                double sq[5];
+#pragma unroll
+                for (int p = 0; p < 5; ++p) {
+                    const double m = __shfl_sync(0xffffffffu, mean_l, p);
                     if (m < 0.0) n_neg[p] += 1.0;
-                    if (lane == 0) {
-                        double *mv = a.mean_var + 2 * ((int64_t)p * a.n_windows + w);
-                        mv[0] = m;
-                        mv[1] = (e - b > 1) ? ss / (cnt - 1.0) : nan("");
-                    }
+                    const double d = live ? x[p] - m : 0.0;
+                    sq[p] = warp_sum_f64(d * d);
+                }
+                double ss = sq[0];
+#pragma unroll
+                for (int p = 1; p < 5; ++p) ss = lane == p ? sq[p] : ss;
+                const double var_l = (e - b > 1) ? ss / (cnt - 1.0) : nan("");
+                if (lane < 5) {
+                    double *mv = a.mean_var + 2 * ((int64_t)lane * a.n_windows + w);
+                    mv[0] = mean_l;
+                    mv[1] = var_l;
                 }
             } else {
 #pragma unroll 1
@@ -371,38 +385,82 @@ static __global__ void k_window_stats(const StatsArgs a)
 }
 
 // partials[s][p][0..ncp+3) = sum over the runs of segment s (fixed order, compensated); columns at or beyond the
-// segment's n_cols = zip truncation of ANEUPLOIDY_TEST.py:73 are zero.  One block per (segment, pair).
-static __global__ void k_segment_partials(const double *__restrict__ runs, const int64_t *__restrict__ seg_off, const int32_t *__restrict__ seg_cols,
-                                   int ncp, int cw, double *__restrict__ partials)
+// segment's n_cols = zip truncation of ANEUPLOIDY_TEST.py:73 are zero.  One block per (segment, pair): 16 rows of 64
+// threads, row r adds the runs r, r+16, ... of a column, the rows are then combined in row order (so the result does not
+// depend on timing).  With stats != nullptr the block also finishes the (segment, pair): see segment_finish.
+constexpr int SEG_ROWS = 16, SEG_COLS = 64;
+
+// mean_and_std_of_mean_of_rnd_var (ANEUPLOIDY_TEST.py:65-76) + fraction_of_negative_LLRs (:313) of one (segment, pair) by
+// one warp: q = its partials.  The operations and their order are those of ldpgta_finish_chromosome (the squared
+// deviations are added column by column); lanes only fetch the columns.
+__device__ __forceinline__ void segment_finish(const double *q, int ncols, int first_draws, double *out3, int lane)
 {
-    const int s = blockIdx.x, p = blockIdx.y, stride = ncp + 3;
-    const int64_t lo = seg_off[s], hi = seg_off[s + 1];
-    const int ncols = seg_cols[s];
-    double *out = partials + ((int64_t)s * 5 + p) * stride;
-    for (int col = threadIdx.x; col < stride; col += blockDim.x) {
-        Comp acc = {0.0, 0.0};
-        if (hi > lo && col < 3 + ncols)
-            for (int64_t chunk = lo / cw; chunk <= (hi - 1) / cw; ++chunk) acc.add(runs[((chunk + s) * 5 + p) * (int64_t)stride + col]);
-        out[col] = acc.value();
+    const double M = q[1], N = (double)first_draws;
+    const double mu = q[0] / N;
+    double ss = 0.0;
+    for (int i0 = 0; i0 < ncols; i0 += 32) {
+        const double mine = i0 + lane < ncols ? q[3 + i0 + lane] : 0.0;
+        const int cnt = min(32, ncols - i0);
+        for (int j = 0; j < cnt; ++j) {
+            const double d = __shfl_sync(0xffffffffu, mine, j) - mu;
+            ss += d * d;
+        }
+    }
+    if (lane == 0) {
+        out3[0] = mu / M;
+        out3[1] = sqrt(ss / (N - 1.0)) / M;
+        out3[2] = q[2] / M;
     }
 }
 
-// mean_and_std_of_mean_of_rnd_var (ANEUPLOIDY_TEST.py:65-76) + fraction_of_negative_LLRs (:313) per (segment, pair) from
-// (summed) partials, the operations of ldpgta_finish_chromosome in the same order.  out[s][p][3].
-static __global__ void k_finish_segments(const double *__restrict__ partials, const int32_t *__restrict__ seg_cols,
-                                  const int32_t *__restrict__ seg_first, int n_segments, int ncp, double *__restrict__ out)
+static __global__ void __launch_bounds__(SEG_ROWS * SEG_COLS) k_segment_partials(const double *__restrict__ runs, const int64_t *__restrict__ seg_off,
+                                                                                 const int32_t *__restrict__ seg_cols, const int32_t *__restrict__ seg_first,
+                                                                                 int ncp, int cw, double *__restrict__ partials, double *__restrict__ stats)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ double sh_s[SEG_ROWS][SEG_COLS], sh_c[SEG_ROWS][SEG_COLS];
+    const int s = blockIdx.x, p = blockIdx.y, stride = ncp + 3;
+    const int64_t lo = seg_off[s], hi = seg_off[s + 1];
+    const int ncols = seg_cols[s];
+    const int cx = threadIdx.x % SEG_COLS, row = threadIdx.x / SEG_COLS;
+    double *out = partials + ((int64_t)s * 5 + p) * stride;
+    const int64_t c_lo = hi > lo ? lo / cw : 0, c_hi = hi > lo ? (hi - 1) / cw + 1 : 0;      // runs of this segment: slots chunk + s
+    for (int col0 = 0; col0 < stride; col0 += SEG_COLS) {
+        const int col = col0 + cx;
+        Comp acc = {0.0, 0.0};
+        if (col < 3 + ncols && col < stride) {
+            const double *src = runs + ((c_lo + s) * 5 + p) * (int64_t)stride + col;
+            const int64_t step = (int64_t)5 * stride;
+            int64_t k = c_lo + row;
+            for (; k + 3 * SEG_ROWS < c_hi; k += 4 * SEG_ROWS) {                             // four loads in flight
+                const double v0 = src[(k - c_lo) * step], v1 = src[(k - c_lo + SEG_ROWS) * step],
+                             v2 = src[(k - c_lo + 2 * SEG_ROWS) * step], v3 = src[(k - c_lo + 3 * SEG_ROWS) * step];
+                acc.add(v0); acc.add(v1); acc.add(v2); acc.add(v3);
+            }
+            for (; k < c_hi; k += SEG_ROWS) acc.add(src[(k - c_lo) * step]);
+        }
+        sh_s[row][cx] = acc.s; sh_c[row][cx] = acc.c;
+        __syncthreads();
+        if (row == 0 && col < stride) {
+            Comp t = {0.0, 0.0};
+#pragma unroll
+            for (int r = 0; r < SEG_ROWS; ++r) { t.add(sh_s[r][cx]); t.c += sh_c[r][cx]; }
+            out[col] = t.value();
+        }
+        __syncthreads();
+    }
+    if (stats && threadIdx.x < 32) {
+        __threadfence_block();
+        segment_finish(out, ncols, seg_first[s], stats + 3 * ((int64_t)s * 5 + p), threadIdx.x);
+    }
+}
+
+// the finish alone, for partials that were summed across GPUs first: one warp per (segment, pair).  out[s][p][3].
+static __global__ void k_finish_segments(const double *__restrict__ partials, const int32_t *__restrict__ seg_cols,
+                                         const int32_t *__restrict__ seg_first, int n_segments, int ncp, double *__restrict__ out)
+{
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (t >= n_segments * 5) return;
-    const int s = t / 5;
-    const double *q = partials + (int64_t)t * (ncp + 3);
-    const double M = q[1], N = (double)seg_first[s];
-    const double mu = q[0] / N;
-    double ss = 0.0;
-    for (int i = 0; i < seg_cols[s]; ++i) { const double d = q[3 + i] - mu; ss += d * d; }
-    out[3 * t + 0] = mu / M;
-    out[3 * t + 1] = sqrt(ss / (N - 1.0)) / M;
-    out[3 * t + 2] = q[2] / M;
+    segment_finish(partials + (int64_t)t * (ncp + 3), seg_cols[t / 5], seg_first[t / 5], out + 3 * (int64_t)t, threadIdx.x & 31);
 }
 
 // binning() of PLOT_PANEL.py:121-144 / BALANCED_ROC_CURVE.py:131-154: one block per (series, bin).  A bin is a run
@@ -517,6 +575,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 // The j-th random integer of draw d is mulhi64(x, bound) with x = 64 bits of Philox(counter = (d, j/2), key = seed).
 struct SampleArgs {
     const int64_t *draw_off;     // [n_windows + 1] draw offsets of the class
+    const int32_t *win_of_draw;  // optional [n_draws]: class window of every draw (saves the search)
     const int64_t *win_off;      // read-list offsets of the sample's windows
     const int32_t *win_reads;    // or nullptr
     const int32_t *cls_win;      // or nullptr
@@ -532,10 +591,12 @@ static __global__ void k_sample_draws(const SampleArgs a)
     const uint64_t seed = a.seed_dev ? *a.seed_dev : a.seed;
     for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < a.n_draws; d += (int64_t)gridDim.x * blockDim.x) {
         int64_t lo = 0, hi = a.n_windows;                    // upper_bound(draw_off, d) - 1
-        while (hi - lo > 1) {
-            const int64_t mid = (lo + hi) >> 1;
-            if (a.draw_off[mid] <= d) lo = mid; else hi = mid;
-        }
+        if (a.win_of_draw) lo = a.win_of_draw[d];
+        else
+            while (hi - lo > 1) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (a.draw_off[mid] <= d) lo = mid; else hi = mid;
+            }
         const int64_t w = a.cls_win ? a.cls_win[lo] : lo;
         const int64_t base = a.win_off[w];
         const uint32_t R = (uint32_t)(a.win_off[w + 1] - base);

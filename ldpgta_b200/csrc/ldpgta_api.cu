@@ -346,6 +346,7 @@ int ldpgta_destroy(ldpgta_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_window_plan(c);
+    free_comm(c);
     for (int g = 0; g < c->G; ++g) {
         if (c->allele_rows[g]) cudaFree(c->allele_rows[g]);
         if (c->read_masks[g] && c->masks_owned[g]) cudaFree(c->read_masks[g]);

@@ -348,6 +348,25 @@ class Engine:
         N.check(self.lib.ldpgta_finish_segments_dev(self._ctx, ctypes.c_void_p(partials_dev_ptr) if partials_dev_ptr else None,
                                                     ctypes.c_void_p(stats_dev_ptr) if stats_dev_ptr else None))
 
+    # ---- the cross-GPU exchange (peer memory over NVLink, comm_api.cu) -------------------------------------------
+    def comm_create(self, rank, world, max_doubles):
+        """ Allocates this rank's exchange buffer; returns its handle (bytes) for the peers. """
+        h = np.zeros(N.COMM_HANDLE_BYTES, dtype=np.uint8)
+        N.check(self.lib.ldpgta_comm_create(self._ctx, rank, world, int(max_doubles), N.ptr(h)))
+        return h.tobytes()
+
+    def comm_connect(self, handles):
+        """ handles: the bytes objects of comm_create of every rank, in rank order. """
+        blob = np.frombuffer(b''.join(handles), dtype=np.uint8).copy()
+        N.check(self.lib.ldpgta_comm_connect(self._ctx, N.ptr(blob)))
+
+    def allreduce_chrom_dev(self, partials_dev_ptr, n_doubles):
+        """ In-place sum over ranks of a device buffer of float64 (asynchronous on the engine's stream). """
+        N.check(self.lib.ldpgta_allreduce_chrom_dev(self._ctx, ctypes.c_void_p(partials_dev_ptr), int(n_doubles)))
+
+    def comm_destroy(self):
+        N.check(self.lib.ldpgta_comm_destroy(self._ctx))
+
     def kernel_timing(self, enable=True):
         """ CUDA-event brackets around the draw kernels of bootstrap_stats / replay_stats (measurement aid). """
         N.check(self.lib.ldpgta_kernel_timing(self._ctx, 1 if enable else 0))

@@ -79,3 +79,17 @@ def allreduce_chromosome(partials, n_cols_local, first_window_draws, group=None,
     t = torch.from_numpy(mine).to(dev)
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return finish_chromosome(t.cpu().numpy(), n_cols, first)
+
+
+def connect_peers(engine, n_doubles, group=None):
+    """ Sets up the peer-memory exchange of ldpgta_allreduce_chrom_dev between the ranks of a torch.distributed group
+    (one process per GPU): every rank allocates its buffer, the handles travel by all_gather_object (plumbing only), and
+    each rank maps the peers' buffers.  Afterwards engine.allreduce_chrom_dev(ptr, n) sums device buffers across the
+    ranks in one kernel over NVLink, with no collective library in the data path. """
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    mine = engine.comm_create(rank, world, n_doubles)
+    handles = [None] * world
+    dist.all_gather_object(handles, mine, group=group)
+    engine.comm_connect(handles)
+    dist.barrier(group=group)                    # every rank has mapped every buffer before the first exchange

@@ -64,3 +64,40 @@ def test_large_n_vs_python_oracle(n):
 def test_llr():
     for y, x in ((0.0, 0.5), (0.5, 0.0), (0.0, 0.0), (0.25, 0.5), (3e-7, 1e-9)):
         assert C.lib().oracle_llr(y, x) == pytest.approx(O.LLR(y, x), rel=1e-15, abs=0)
+
+
+def large_draw_rows(rec, inputs):
+    """ packed read masks of one large_draws record, per panel group (hap_dict of the oracle = build_hap_dict) """
+    obs, leg = inputs['obs_tabs']['disomy'], inputs['leg_tab']
+    rows = {}
+    for g in ('G0', 'G1'):
+        hd, _ = O.build_hap_dict(obs, leg, inputs['hap_tab'][g], inputs['number_of_haplotypes'][g])
+        rows[g] = C.pack_rows(O.read_masks(hd, rec['alleles']), inputs['number_of_haplotypes'][g])
+    return rows
+
+
+def test_large_draws_vs_reference_build(golden_inputs):
+    """ 10..16 (..18 when generated) reads per draw: the C checker against the UNMODIFIED reference run with
+    MAKE_STATISTICAL_MODEL.BUILD tables (tests/golden/make_golden_large.py): joint-frequency tables bit-exact (sha256),
+    likelihoods of all three model classes to 1e-14. """
+    import hashlib
+    from conftest import load_golden
+    g = load_golden('large_draws.p.bz2')
+    nh = golden_inputs['number_of_haplotypes']
+    assert set(range(10, 17)) <= set(g['records'])
+    worst = 0.0
+    for n, rec in sorted(g['records'].items()):
+        rows = large_draw_rows(rec, golden_inputs)
+        cnt = C.joint_counts(rows['G0'])
+        assert hashlib.sha256(cnt.astype('<u4').tobytes()).hexdigest() == rec['counts_sha256_G0'], n
+        assert int(cnt[-1]) == rec['full_set_count_G0']
+        if rec['counts_G0'] is not None:
+            assert {s: int(c) for s, c in enumerate(cnt) if s} == rec['counts_G0']
+        idx, off = np.arange(n, dtype=np.int32), np.array([0, n], dtype=np.int64)
+        both = _pad(rows['G0'], rows['G1'])
+        got = {'homog_G0': C.batch([rows['G0']], [nh['G0']], idx, off, 0)[0],
+               'recent': C.batch(both, [nh['G0'], nh['G1']], idx, off, 1)[0],
+               'distant': C.batch(both, [nh['G0'], nh['G1']], idx, off, 2, [rec['makeup']['G0'], rec['makeup']['G1']])[0]}
+        for key, vals in got.items():
+            worst = max(worst, max(rel_err(a, b) for a, b in zip(vals, rec[key])))
+    assert worst < 1e-14, worst

@@ -147,3 +147,29 @@ def test_llr_sentinels():
     assert O.LLR(0.5, 0.0) == 1.23456789
     assert O.LLR(0.0, 0.0) == 0
     assert O.LLR(0.25, 0.5) == pytest.approx(-0.6931471805599453, rel=1e-15)
+
+
+def test_chr21_full_panel_bootstrap_replay():
+    """ configs[0] of BASELINE.json: chr21-sized disomy sample at 0.05x on a 5008-haplotype panel through the UNMODIFIED
+    reference bootstrap() / statistics() (tests/golden/make_golden_large.py, SNP density reduced to keep the fixture
+    small; the panel is regenerated from its seed).  The oracle replays the recorded draws. """
+    import hashlib
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+    import make_golden_large as G
+    out = load_golden('chr21_5008.p.bz2')
+    leg, rows = G.chr21_panel()
+    assert hashlib.sha256(b''.join(r.to_bytes(626, 'little') for r in rows)).hexdigest() == out['panel_sha256']
+    cfg = out['cfg']
+    lik, windows, matches = O.bootstrap(out['obs_tab'], leg, {'ALL': rows}, {'ALL': G.CHR21_HAP}, {'ALL'}, O.make_models(4),
+                                        cfg['window_size'], cfg['subsamples'], cfg['offset'], cfg['min_reads'], cfg['max_reads'],
+                                        cfg['min_score'], cfg['min_HF'], replay=out['draws'])
+    assert list(windows) == list(out['windows']) and matches == out['fraction_of_matches']
+    assert {w: frozenset(r) for w, r in windows.items()} == {w: frozenset(r) for w, r in out['windows'].items()}
+    assert list(lik) == list(out['likelihoods']) and len(lik) > 400
+    worst = max(rel_err(a, b) for w in lik for mine, ref in zip(lik[w], out['likelihoods'][w]) for a, b in zip(mine, ref))
+    assert worst < LIK_TOL, worst
+    st = O.statistics({w: tuple(O.likelihoods_tuple(*l) for l in ls) for w, ls in out['likelihoods'].items()}, out['windows'])
+    for pair in O.LLR_PAIRS:
+        assert st['LLRs_per_chromosome'][pair] == out['statistics']['LLRs_per_chromosome'][pair]

@@ -35,6 +35,8 @@ __global__ void __launch_bounds__(256) k_peak(uint32_t *out, long long *cycles, 
                              : "+r"(r[i]) : "r"(a), "r"(b));
             } else if (MODE == 5) {     // 1 POPC : 1 IMAD (fma pipe)
                 asm volatile("mad.lo.u32 %0, %0, %1, %2;\n\tpopc.b32 %0, %0;" : "+r"(r[i]) : "r"(a), "r"(b));
+            } else if (MODE == 6) {     // IMAD.32 only
+                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r[i]) : "r"(a), "r"(b));
             }
         }
     }
@@ -74,6 +76,34 @@ __global__ void __launch_bounds__(256) k_wordop(uint32_t *out, long long *cycles
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) s += acc[i][j];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+// the multiply-adds of the partition polynomials: 64-bit integer a*b+c (k_general's exact class sums) and float64 fma
+// (distant admixture), and float64 log (the LLRs of statistics())
+template <int MODE>
+__global__ void __launch_bounds__(256) k_peak64(double *out, long long *cycles, uint64_t seed)
+{
+    uint64_t r[CHAINS];
+    double d[CHAINS];
+    const uint64_t a = seed | 1ull, b = seed * 0x9e3779b97f4a7c15ull + threadIdx.x;
+    const double fa = 1.0000001, fb = 1e-9 * (double)(threadIdx.x + 1);
+#pragma unroll
+    for (int i = 0; i < CHAINS; ++i) { r[i] = seed + i * 0x9e3779b9u + threadIdx.x; d[i] = 1.0 + 1e-3 * (double)(i + threadIdx.x); }
+    long long t0 = clock64();
+    for (int it = 0; it < ITERS / 4; ++it) {
+#pragma unroll
+        for (int i = 0; i < CHAINS; ++i) {
+            if (MODE == 0) asm volatile("mad.lo.u64 %0, %0, %1, %2;" : "+l"(r[i]) : "l"(a), "l"(b));
+            else if (MODE == 1) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(fa), "d"(fb));
+            else d[i] = log(d[i]) + 2.5;
+        }
+    }
+    long long t1 = clock64();
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < CHAINS; ++i) s += d[i] + (double)r[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
@@ -119,6 +149,13 @@ int main()
     time_it([&] { k_peak<3><<<blocks, 256>>>(d_out, d_cyc, 4u); }, blocks, n, "popc_plus_1lop3_pairs", sms, d_cyc, false);
     time_it([&] { k_peak<4><<<blocks, 256>>>(d_out, d_cyc, 5u); }, blocks, n, "popc_plus_3lop3_groups", sms, d_cyc, false);
     time_it([&] { k_peak<5><<<blocks, 256>>>(d_out, d_cyc, 6u); }, blocks, n, "popc_plus_1imad_pairs", sms, d_cyc, false);
+    time_it([&] { k_peak<6><<<blocks, 256>>>(d_out, d_cyc, 8u); }, blocks, n, "imad32", sms, d_cyc, false);
+    double *d_out64;
+    CK(cudaMalloc(&d_out64, (size_t)blocks * 256 * 8));
+    const double n4 = (double)(ITERS / 4) * CHAINS;
+    time_it([&] { k_peak64<0><<<blocks, 256>>>(d_out64, d_cyc, 9ull); }, blocks, n4, "imad64_lo", sms, d_cyc, false);
+    time_it([&] { k_peak64<1><<<blocks, 256>>>(d_out64, d_cyc, 10ull); }, blocks, n4, "dfma", sms, d_cyc, false);
+    time_it([&] { k_peak64<2><<<blocks, 256>>>(d_out64, d_cyc, 11ull); }, blocks, n4, "log_f64", sms, d_cyc, false);
     time_it([&] { k_wordop<<<blocks, 256>>>(d_out, d_cyc, 7ull); }, blocks, (double)(ITERS / 4) * 32, "wordop64_and_popc_add", sms, d_cyc, true);
     printf("}\n");
     return 0;
