@@ -32,7 +32,8 @@ struct PeerComm {
     bool opened[LDPGTA_MAX_PEERS] = {};
     bool connected = false;
     uint64_t epoch = 0;
-    unsigned int *h_status = nullptr;    // page-locked mirror of the device status word
+    unsigned int *h_status = nullptr;    // page-locked, device-mapped status word (written by the kernel on a time-out)
+    unsigned int *d_status = nullptr;    // its device address
 };
 
 struct CommView {
@@ -51,28 +52,34 @@ static __global__ void __launch_bounds__(1024) k_allreduce_peer(const CommView v
     const int par = (int)(epoch & 1ull);
     double *own = v.data[v.rank] + (int64_t)par * v.max_doubles;
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) own[i] = partials[i];
-    __threadfence_system();
-    __syncthreads();
+    __syncthreads();                                   // the block's stores are ordered before the fence of the flag writers
     if ((int)threadIdx.x < v.world) {
         // raise my flag in peer t's memory, then wait for peer t's flag in mine
         const int t = threadIdx.x;
+        __threadfence_system();
         volatile unsigned long long *theirs = v.arrive[t] + par * LDPGTA_MAX_PEERS + v.rank;
         *theirs = epoch;
         volatile unsigned long long *mine = v.arrive[v.rank] + par * LDPGTA_MAX_PEERS + t;
         const long long t0 = clock64();
         while (*mine < epoch) {
             if (clock64() - t0 > 4000000000ll) {                      // ~2 s: a peer is gone; report instead of hanging the GPU
-                atomicExch(v.status, 1u);
+                *v.status = 1u;                                       // page-locked host memory, read by the next call
                 break;
             }
-            __nanosleep(64);
         }
         __threadfence_system();
     }
     __syncthreads();
+    // peer loads (NVLink), all ranks' values of an element in flight together, added in rank order
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        double x[LDPGTA_MAX_PEERS];
+#pragma unroll
+        for (int r = 0; r < LDPGTA_MAX_PEERS; ++r)
+            if (r < v.world) x[r] = __ldcv(v.data[r] + (int64_t)par * v.max_doubles + i);
         double s = 0.0;
-        for (int r = 0; r < v.world; ++r) s += __ldcv(v.data[r] + (int64_t)par * v.max_doubles + i);
+#pragma unroll
+        for (int r = 0; r < LDPGTA_MAX_PEERS; ++r)
+            if (r < v.world) s += x[r];
         partials[i] = s;
     }
 }
@@ -111,8 +118,9 @@ int ldpgta_comm_create(ldpgta_ctx *c, int rank, int world, int64_t max_doubles, 
     pc->rank = rank; pc->world = world; pc->max_doubles = max_doubles;
     LDPGTA_CUDA(cudaMalloc((void **)&pc->mine, comm_bytes(max_doubles)));
     LDPGTA_CUDA(cudaMemset(pc->mine, 0, comm_bytes(max_doubles)));
-    LDPGTA_CUDA(cudaMallocHost((void **)&pc->h_status, 16));
+    LDPGTA_CUDA(cudaHostAlloc((void **)&pc->h_status, 16, cudaHostAllocMapped));
     *pc->h_status = 0;
+    LDPGTA_CUDA(cudaHostGetDevicePointer((void **)&pc->d_status, pc->h_status, 0));
     LDPGTA_CUDA(cudaDeviceSynchronize());
     CommHandle h;
     memset(&h, 0, sizeof h);
@@ -173,14 +181,13 @@ int ldpgta_allreduce_chrom_dev(ldpgta_ctx *c, double *partials_dev, int64_t n_do
         v.data[r] = (double *)pc->peer[r];
         v.arrive[r] = (unsigned long long *)(pc->peer[r] + (size_t)2 * pc->max_doubles * 8);
     }
-    v.status = (unsigned int *)(pc->mine + (size_t)2 * pc->max_doubles * 8 + 2 * LDPGTA_MAX_PEERS * 8);
+    v.status = pc->d_status;
     v.rank = pc->rank; v.world = pc->world; v.max_doubles = pc->max_doubles;
     pc->epoch++;
     const int threads = (int)std::min<int64_t>(1024, std::max<int64_t>(64, (n_doubles + 31) / 32 * 32));
     k_allreduce_peer<<<1, threads, 0, c->stream>>>(v, partials_dev, n_doubles, (unsigned long long)pc->epoch);
     c->launches++;
     LDPGTA_CUDA(cudaGetLastError());
-    LDPGTA_CUDA(cudaMemcpyAsync(pc->h_status, v.status, 4, cudaMemcpyDeviceToHost, c->stream));
     return 0;
 }
 

@@ -93,6 +93,29 @@ static int refresh_popc(ldpgta_ctx *c, int g)
     return make_read_mask_tmap(c, g);
 }
 
+// Index arrays are validated where they are used: the uploaded copy is checked (and clamped) by k_sanitize_idx on the
+// stream, the caller reads c->h_flag after its synchronisation and only then looks for the offending entry on the host.
+static int check_idx_on_device(ldpgta_ctx *c, int32_t *d_idx, int64_t count, int64_t lim, bool first)
+{
+    if (int rc = ensure_pipeline(c, 1)) return rc;
+    if (first) LDPGTA_CUDA(cudaMemsetAsync(c->d_flag, 0, 4, c->stream));
+    if (count > 0) {
+        k_sanitize_idx<<<(unsigned)std::min<int64_t>((count / 4 + 255) / 256 + 1, (int64_t)c->sm_count * 4), 256, 0, c->stream>>>(
+            d_idx, count, (uint32_t)std::min<int64_t>(lim, 0x7fffffff), c->d_flag);
+        c->launches++;
+    }
+    LDPGTA_CUDA(cudaMemcpyAsync(c->h_flag, c->d_flag, 4, cudaMemcpyDeviceToHost, c->stream));
+    return 0;
+}
+
+static int fail_bad_allele(const int32_t *allele_idx, int64_t nnz, int64_t n_alleles)
+{
+    for (int64_t k = 0; k < nnz; ++k)
+        if (allele_idx[k] < 0 || allele_idx[k] >= n_alleles)
+            return fail(LDPGTA_E_INVALID, "allele index %d at %lld is outside 0..%lld", allele_idx[k], (long long)k, (long long)n_alleles - 1);
+    return fail(LDPGTA_E_INVALID, "an allele index is outside 0..%lld", (long long)n_alleles - 1);
+}
+
 int check_kind(const ldpgta_ctx *c, int kind, const double *proportions)
 {
     if (kind == LDPGTA_HOMOGENEOUS && c->G != 1)
@@ -448,6 +471,10 @@ struct ldpgta_panel {
     int words[MAXG] = {}, wp[MAXG] = {};
     int64_t n_snps = 0;
     uint64_t *rows[MAXG] = {};
+    cudaStream_t stream = nullptr;
+    uint64_t *stage = nullptr;
+    size_t stage_bytes = 0;
+    int sm_count = 148;
 };
 
 int ldpgta_panel_create(int device, int n_groups, const uint32_t *n_hap, int64_t n_snps, ldpgta_panel **out)
@@ -460,6 +487,7 @@ int ldpgta_panel_create(int device, int n_groups, const uint32_t *n_hap, int64_t
     LDPGTA_CUDA(cudaSetDevice(device));
     ldpgta_panel *p = new ldpgta_panel();
     p->device = device; p->G = n_groups; p->n_snps = n_snps;
+    LDPGTA_CUDA(cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device));
     for (int g = 0; g < n_groups; ++g) {
         if (n_hap[g] == 0) { delete p; return fail(LDPGTA_E_INVALID, "group %d has no haplotypes", g); }
         p->nhap[g] = n_hap[g];
@@ -477,19 +505,24 @@ int ldpgta_panel_upload(ldpgta_panel *p, int group, int64_t first_snp, const uin
     if (first_snp < 0 || first_snp + n_rows > p->n_snps) return fail(LDPGTA_E_INVALID, "SNP range %lld..%lld is outside the panel", (long long)first_snp, (long long)(first_snp + n_rows));
     if (n_rows == 0) return 0;
     LDPGTA_CUDA(cudaSetDevice(p->device));
-    uint64_t *tmp = nullptr;
+    // staging buffer and stream belong to the panel: chunks of one upload reuse them, nothing touches the default stream
     const size_t src_bytes = (size_t)n_rows * p->words[group] * 8;
-    LDPGTA_CUDA(cudaMalloc((void **)&tmp, src_bytes));
-    cudaError_t e = cudaMemcpy(tmp, rows, src_bytes, cudaMemcpyHostToDevice);
+    if (!p->stream) LDPGTA_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    if (p->stage_bytes < src_bytes) {
+        if (p->stage) LDPGTA_CUDA(cudaFree(p->stage));
+        p->stage = nullptr; p->stage_bytes = 0;
+        LDPGTA_CUDA(cudaMalloc((void **)&p->stage, src_bytes));
+        p->stage_bytes = src_bytes;
+    }
+    cudaError_t e = cudaMemcpyAsync(p->stage, rows, src_bytes, cudaMemcpyHostToDevice, p->stream);
     if (e == cudaSuccess) {
         const int64_t total = n_rows * p->wp[group];
-        const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, 148 * 16);
-        k_pack_rows<<<blocks, 256>>>(tmp, nullptr, p->rows[group] + first_snp * p->wp[group], n_rows, p->words[group], p->wp[group],
-                                     p->nhap[group]);
+        const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)p->sm_count * 16);
+        k_pack_rows<<<blocks, 256, 0, p->stream>>>(p->stage, nullptr, p->rows[group] + first_snp * p->wp[group], n_rows, p->words[group],
+                                                   p->wp[group], p->nhap[group]);
         e = cudaGetLastError();
-        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);        // the caller's rows may be reused on return
     }
-    cudaFree(tmp);
     if (e != cudaSuccess) return fail(LDPGTA_E_CUDA, "panel upload failed: %s", cudaGetErrorString(e));
     return 0;
 }
@@ -500,6 +533,8 @@ int ldpgta_panel_destroy(ldpgta_panel *p)
     cudaSetDevice(p->device);
     for (int g = 0; g < p->G; ++g)
         if (p->rows[g]) cudaFree(p->rows[g]);
+    if (p->stage) cudaFree(p->stage);
+    if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
     return 0;
 }
@@ -591,14 +626,12 @@ int ldpgta_build_read_masks(ldpgta_ctx *c, const int32_t *allele_idx, const int6
     for (int64_t r = 0; r < n_reads; ++r)
         if (read_offsets[r + 1] < read_offsets[r]) return fail(LDPGTA_E_INVALID, "read_offsets must be non-decreasing");
     if (nnz > 0 && !allele_idx) return fail(LDPGTA_E_INVALID, "null allele_idx");
-    for (int64_t k = 0; k < nnz; ++k)
-        if (allele_idx[k] < 0 || allele_idx[k] >= n_alleles)
-            return fail(LDPGTA_E_INVALID, "allele index %d at %lld is outside 0..%lld", allele_idx[k], (long long)k, (long long)n_alleles - 1);
     const size_t idx_bytes = ((size_t)nnz * 4 + 15) & ~(size_t)15, off_bytes = (size_t)(n_reads + 1) * 8;
     if (int rc = ensure_dev(c, idx_bytes + off_bytes)) return rc;
     int32_t *d_idx = (int32_t *)c->d_buf;
     int64_t *d_off = (int64_t *)((char *)c->d_buf + idx_bytes);
     if (nnz) LDPGTA_CUDA(cudaMemcpyAsync(d_idx, allele_idx, (size_t)nnz * 4, cudaMemcpyHostToDevice, c->stream));
+    if (int rc = check_idx_on_device(c, d_idx, nnz, n_alleles, true)) return rc;
     LDPGTA_CUDA(cudaMemcpyAsync(d_off, read_offsets, off_bytes, cudaMemcpyHostToDevice, c->stream));
     for (int g = 0; g < c->G; ++g) {
         if (c->read_masks[g] && c->masks_owned[g]) LDPGTA_CUDA(cudaFree(c->read_masks[g]));
@@ -617,6 +650,7 @@ int ldpgta_build_read_masks(ldpgta_ctx *c, const int32_t *allele_idx, const int6
     }
     c->n_reads = n_reads;
     LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
+    if (*c->h_flag) return fail_bad_allele(allele_idx, nnz, n_alleles);
     return 0;
 }
 
@@ -636,13 +670,11 @@ int ldpgta_read_scores(ldpgta_ctx *c, const int32_t *allele_idx, const int64_t *
     for (int64_t r = 0; r < n_reads; ++r)
         if (read_offsets[r + 1] < read_offsets[r]) return fail(LDPGTA_E_INVALID, "read_offsets must be non-decreasing");
     if (nnz > 0 && !allele_idx) return fail(LDPGTA_E_INVALID, "null allele_idx");
-    for (int64_t k = 0; k < nnz; ++k)
-        if (allele_idx[k] < 0 || allele_idx[k] >= n_alleles)
-            return fail(LDPGTA_E_INVALID, "allele index %d at %lld is outside 0..%lld", allele_idx[k], (long long)k, (long long)n_alleles - 1);
     const size_t idx_b = ((size_t)nnz * 4 + 15) & ~(size_t)15, off_b = ((size_t)(n_reads + 1) * 8 + 15) & ~(size_t)15;
     if (int rc = ensure_dev(c, idx_b + off_b + (size_t)n_reads * 4)) return rc;
     char *base = (char *)c->d_buf;
     if (nnz) LDPGTA_CUDA(cudaMemcpyAsync(base, allele_idx, (size_t)nnz * 4, cudaMemcpyHostToDevice, c->stream));
+    if (int rc = check_idx_on_device(c, (int32_t *)base, nnz, n_alleles, true)) return rc;
     LDPGTA_CUDA(cudaMemcpyAsync(base + idx_b, read_offsets, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     ScoreArgs a;
     memset(&a, 0, sizeof a);
@@ -660,6 +692,7 @@ int ldpgta_read_scores(ldpgta_ctx *c, const int32_t *allele_idx, const int64_t *
     LDPGTA_CUDA(cudaGetLastError());
     LDPGTA_CUDA(cudaMemcpyAsync(out_scores, a.out, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, c->stream));
     LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
+    if (*c->h_flag) return fail_bad_allele(allele_idx, nnz, n_alleles);
     // reads that overlap more than 12 common SNPs (long or paired reads): their 2^k combinations are spread over many warps
     std::vector<int64_t> items;
     for (int64_t r = 0; r < n_reads; ++r)
@@ -825,9 +858,6 @@ int ldpgta_bootstrap_uniform(ldpgta_ctx *c, int kind, int n, const int64_t *wind
         if (nd > 0 && R < n) return fail(LDPGTA_E_INVALID, "window %lld has %lld reads, fewer than the %d of a draw", (long long)w, (long long)R, n);
         if (R > 0x7fffffff) return fail(LDPGTA_E_INVALID, "window %lld has too many reads", (long long)w);
     }
-    for (int64_t k = 0; k < n_wreads; ++k)
-        if (window_reads[k] < 0 || window_reads[k] >= c->n_reads)
-            return fail(LDPGTA_E_INVALID, "read index %d at %lld is outside 0..%lld", window_reads[k], (long long)k, (long long)c->n_reads - 1);
 
     auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const size_t woff_b = pad((size_t)(n_windows + 1) * 8), wr_b = pad((size_t)n_wreads * 4);
@@ -843,6 +873,7 @@ int ldpgta_bootstrap_uniform(ldpgta_ctx *c, int kind, int n, const int64_t *wind
     LDPGTA_CUDA(cudaMemcpyAsync(d_woff, window_offsets, (size_t)(n_windows + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     LDPGTA_CUDA(cudaMemcpyAsync(d_doff, draw_offsets, (size_t)(n_windows + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     LDPGTA_CUDA(cudaMemcpyAsync(d_wreads, window_reads, (size_t)n_wreads * 4, cudaMemcpyHostToDevice, c->stream));
+    if (int rc = check_idx_on_device(c, d_wreads, n_wreads, c->n_reads, true)) return rc;
     {
         SampleArgs sa;
         memset(&sa, 0, sizeof sa);
@@ -871,6 +902,7 @@ int ldpgta_bootstrap_uniform(ldpgta_ctx *c, int kind, int n, const int64_t *wind
     if (idx_out) LDPGTA_CUDA(cudaMemcpyAsync(idx_out, d_idx, (size_t)n_draws * n * 4, cudaMemcpyDeviceToHost, c->stream));
     LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
     LDPGTA_CUDA(cudaStreamSynchronize(c->s_out));
+    if (*c->h_flag) return fail_bad_index(c, window_reads, n_wreads);
     if (!pin_out) memcpy(out, h_out, out_b);
     return 0;
 }
