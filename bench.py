@@ -186,9 +186,18 @@ def cpu_model_class(prefer_reference=True):
         try:
             import make_ref
             if make_ref.available():
-                sys.path.insert(0, make_ref.DEST)
-                with contextlib.redirect_stdout(io.StringIO()):
-                    import HOMOGENOUES_MODELS as ref
+                # loaded by file path under a private name: the bare name HOMOGENOUES_MODELS may already belong to the
+                # GPU drop-in (ldpgta_b200 registers it), and the CPU arm must never time that
+                import importlib.util
+                name = '_ldpgta_reference_HOMOGENOUES_MODELS'
+                ref = sys.modules.get(name)
+                if ref is None:
+                    spec = importlib.util.spec_from_file_location(name, os.path.join(make_ref.DEST, 'HOMOGENOUES_MODELS.py'))
+                    ref = importlib.util.module_from_spec(spec)
+                    sys.modules[name] = ref
+                    with contextlib.redirect_stdout(io.StringIO()):
+                        spec.loader.exec_module(ref)
+                assert ref.__file__.startswith(make_ref.DEST) and not hasattr(ref.homogeneous, '_engine')
                 pc = 'gmpy2.popcount' if type(ref.popcount).__name__ != 'popcount_lk' else 'popcount_lk (byte LUT; gmpy2 is not installed)'
                 return ref.homogeneous, 'reference', pc
         except Exception as e:                                  # noqa: the port below is the documented fallback

@@ -254,7 +254,7 @@ int ldpgta_plan_info(const ldpgta_ctx *ctx, int64_t *out);
  *                                      [1] number of windows, [2] number of windows with mean < 0,
  *                                      [3 + i] column sums  sum_w x_wi  for i < n_cols
  * n_cols = the smallest draw count over the windows of the WHOLE chromosome (zip truncation of
- * :73, at most 4096); shards of one chromosome add their chrom_partials (that sum is the only cross-GPU
+ * :73); shards of one chromosome add their chrom_partials (that sum is the only cross-GPU
  * exchange of the path) and ldpgta_finish_chromosome() turns the sum into mean/std.  Likelihoods that are
  * already on the device never need this call: see ldpgta_bootstrap_stats / ldpgta_replay_stats. */
 int ldpgta_window_stats(ldpgta_ctx *ctx, const double *lik, const int64_t *window_offsets,

@@ -25,8 +25,7 @@ struct SizeClass {
 
 struct WindowPlan {
     int64_t n_windows = 0, n_draws = 0, n_wreads = 0, nnz = 0;
-    int n_segments = 0, ncp = 0, cw = 8;
-    int64_t n_chunks = 0;
+    int n_segments = 0, ncp = 0;
     bool has_windows = false;
     void *d_static = nullptr, *d_work = nullptr;
     int64_t *d_woff = nullptr, *d_doff = nullptr, *d_segoff = nullptr;
@@ -34,7 +33,7 @@ struct WindowPlan {
     std::vector<SizeClass> classes;
     std::vector<int64_t> h_doff;   // draw offsets per window
     std::vector<int32_t> h_n;      // reads per draw per window
-    double *d_lik = nullptr, *d_llr = nullptr, *d_mv = nullptr, *d_runs = nullptr, *d_partials = nullptr, *d_stats = nullptr;
+    double *d_lik = nullptr, *d_llr = nullptr, *d_mv = nullptr, *d_wsum = nullptr, *d_partials = nullptr, *d_stats = nullptr;
     uint64_t *d_seed = nullptr;
 };
 
@@ -70,43 +69,28 @@ int launch_sample(ldpgta_ctx *c, int n, const SampleArgs &a)
     return 0;
 }
 
-// shape of the fused reduction kernel for a column capacity
-struct StatsShape { int wpb; size_t smem; int cw; int64_t n_chunks; };
-
-static int stats_shape(const ldpgta_ctx *c, int64_t n_windows, int ncp, StatsShape *s)
-{
-    if (ncp > 4096) return fail(LDPGTA_E_UNSUPPORTED, "%d draws per window: the device reductions keep at most 4096 columns", ncp);
-    const size_t per_warp = (size_t)5 * ncp * 8;
-    s->wpb = per_warp ? (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / per_warp)) : 8;
-    s->smem = per_warp * s->wpb;
-    // chunks of up to 8 windows, shorter when that leaves fewer than ~32 warps per SM
-    s->cw = (int)std::max<int64_t>(1, std::min<int64_t>(8, n_windows / ((int64_t)c->sm_count * 32)));
-    s->n_chunks = (n_windows + s->cw - 1) / s->cw;
-    return 0;
-}
-
-// LLRs, window mean / variance, segment partial sums and (optionally) the finished segment statistics, all on c->stream
+// LLRs (when not already written by the draw kernels), window mean / variance, segment partial sums and (optionally) the
+// finished segment statistics, all on c->stream
 static int stats_on_device(ldpgta_ctx *c, const double *d_lik, const int64_t *d_doff, int64_t n_windows, int64_t n_draws,
                            const int64_t *d_segoff, const int32_t *d_segcols, const int32_t *d_segfirst, int n_segments, int ncp,
-                           const StatsShape &sh, double *d_llr, double *d_mv, double *d_runs, double *d_partials, double *d_stats)
+                           double *d_llr, double *d_mv, double *d_wsum, double *d_partials, double *d_stats)
 {
-    if (n_draws > 0) {
+    if (n_draws > 0 && d_lik) {                       // d_lik == nullptr: the draw kernels have written the LLRs already
         const unsigned blocks = (unsigned)std::min<int64_t>((n_draws + 255) / 256, (int64_t)c->sm_count * 8);
         k_draw_llr<<<blocks, 256, 0, c->stream>>>(d_lik, n_draws, d_llr);
         c->launches++;
     }
     if (n_windows > 0) {
         StatsArgs a;
-        a.llr = d_llr; a.doff = d_doff; a.seg_off = d_segoff; a.n_windows = n_windows; a.n_draws = n_draws;
-        a.n_segments = n_segments; a.ncp = ncp; a.cw = sh.cw; a.mean_var = d_mv; a.runs = d_runs;
-        if (sh.smem > 48 * 1024)
-            LDPGTA_CUDA(cudaFuncSetAttribute(k_window_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem));
-        const unsigned blocks = (unsigned)std::min<int64_t>((sh.n_chunks + sh.wpb - 1) / sh.wpb, (int64_t)c->sm_count * 32);
-        k_window_stats<<<blocks, sh.wpb * 32, sh.smem, c->stream>>>(a);
+        a.llr = d_llr; a.doff = d_doff; a.n_windows = n_windows; a.n_draws = n_draws; a.mean_var = d_mv; a.wsum = d_wsum;
+        const unsigned blocks = (unsigned)std::min<int64_t>((n_windows + 7) / 8, (int64_t)c->sm_count * 32);
+        k_window_stats<<<blocks, 256, 0, c->stream>>>(a);
         c->launches++;
     }
-    k_segment_partials<<<dim3((unsigned)n_segments, 5), SEG_ROWS * SEG_COLS, 0, c->stream>>>(d_runs, d_segoff, d_segcols, d_segfirst, ncp, sh.cw,
-                                                                                          d_partials, d_stats);
+    SegmentArgs sa;
+    sa.llr = d_llr; sa.doff = d_doff; sa.wsum = d_wsum; sa.mean_var = d_mv; sa.seg_off = d_segoff; sa.seg_cols = d_segcols;
+    sa.seg_first = d_segfirst; sa.n_windows = n_windows; sa.n_draws = n_draws; sa.ncp = ncp; sa.partials = d_partials; sa.stats = d_stats;
+    k_segment_partials<<<dim3((unsigned)n_segments, 5), SEG_ROWS * SEG_COLS, 0, c->stream>>>(sa);
     c->launches++;
     LDPGTA_CUDA(cudaGetLastError());
     return 0;
@@ -147,7 +131,9 @@ static int evaluate_classes_inner(ldpgta_ctx *c, WindowPlan *p, int kind, const 
         int ci = 0;
         for (int64_t d0 = 0; d0 < p->n_draws; d0 += per, ++ci) {
             const int64_t nd = std::min(per, p->n_draws - d0);
-            if (int rc = run_uniform(c, kind, k.n, k.d_idx + d0 * k.n, nd, nullptr, proportions, p->d_lik + 4 * d0, nullptr)) return rc;
+            if (int rc = run_uniform(c, kind, k.n, k.d_idx + d0 * k.n, nd, nullptr, proportions, p->d_lik + 4 * d0, nullptr, false, nullptr,
+                                     p->d_llr + d0, p->n_draws))
+                return rc;
             LDPGTA_CUDA(cudaEventRecord(c->ev_k[ci], c->stream));
             LDPGTA_CUDA(cudaStreamWaitEvent(c->s_out, c->ev_k[ci], 0));
             LDPGTA_CUDA(cudaMemcpyAsync(lik_out_pinned + 4 * d0, p->d_lik + 4 * d0, (size_t)nd * 32, cudaMemcpyDeviceToHost, c->s_out));
@@ -155,7 +141,8 @@ static int evaluate_classes_inner(ldpgta_ctx *c, WindowPlan *p, int kind, const 
         return 0;
     }
     for (const SizeClass &k : p->classes)
-        if (int rc = run_uniform(c, kind, k.n, k.d_idx, k.n_draws, k.d_pos, proportions, p->d_lik, nullptr)) return rc;
+        if (int rc = run_uniform(c, kind, k.n, k.d_idx, k.n_draws, k.d_pos, proportions, p->d_lik, nullptr, false, nullptr, p->d_llr, p->n_draws))
+            return rc;
     if (lik_out_pinned) {
         if (int rc = ensure_pipeline(c, 2)) return rc;
         LDPGTA_CUDA(cudaEventRecord(c->ev_k[0], c->stream));
@@ -179,12 +166,10 @@ static int check_plan(const ldpgta_ctx *c, int kind, const double *proportions)
 static int reduce_and_download(ldpgta_ctx *c, WindowPlan *p, double *lik_out, double *lik_pinned, double *llr_out,
                                double *window_mean_var, double *segment_partials, double *segment_stats)
 {
-    StatsShape sh;
-    if (int rc = stats_shape(c, p->n_windows, p->ncp, &sh)) return rc;
     double *d_llr = p->d_llr;
     c->llr_draws = c->llr_windows = -1;
-    if (int rc = stats_on_device(c, p->d_lik, p->d_doff, p->n_windows, p->n_draws, p->d_segoff, p->d_segcols, p->d_segfirst,
-                                 p->n_segments, p->ncp, sh, d_llr, p->d_mv, p->d_runs, p->d_partials, p->d_stats))
+    if (int rc = stats_on_device(c, nullptr, p->d_doff, p->n_windows, p->n_draws, p->d_segoff, p->d_segcols, p->d_segfirst,
+                                 p->n_segments, p->ncp, d_llr, p->d_mv, p->d_wsum, p->d_partials, p->d_stats))
         return rc;
     const size_t cp_b = (size_t)p->n_segments * 5 * (p->ncp + 3) * 8;
     if (window_mean_var && p->n_windows)
@@ -258,15 +243,12 @@ int ldpgta_set_windows(ldpgta_ctx *c, const int64_t *window_offsets, const int32
             return fail(LDPGTA_E_INVALID, "segment %d: %d columns, but one of its windows has only %lld draws", s, segcols[s], (long long)mn);
         ncp = std::max(ncp, (int)segcols[s]);
     }
-    StatsShape sh;
-    if (int rc = stats_shape(c, n_windows, ncp, &sh)) return rc;
-
     LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
     free_window_plan(c);
     WindowPlan *p = new WindowPlan();
     c->plan = p;
     p->n_windows = n_windows; p->n_draws = n_draws; p->n_wreads = window_reads ? n_wreads : 0; p->nnz = nnz;
-    p->n_segments = n_segments; p->ncp = ncp; p->cw = sh.cw; p->n_chunks = sh.n_chunks;
+    p->n_segments = n_segments; p->ncp = ncp;
     p->has_windows = window_offsets != nullptr;
     p->h_doff.assign(draw_offsets, draw_offsets + n_windows + 1);
     p->h_n.assign(reads_per_draw, reads_per_draw + n_windows);
@@ -355,7 +337,7 @@ int ldpgta_set_windows(ldpgta_ctx *c, const int64_t *window_offsets, const int32
     std::vector<size_t> o_idx;
     for (const SizeClass &k : p->classes) o_idx.push_back(take((size_t)k.n_draws * k.n * 4));
     const size_t o_lik = take((size_t)n_draws * 32), o_llr = take((size_t)n_draws * 40), o_mv = take((size_t)n_windows * 80);
-    const size_t o_runs = take((size_t)(sh.n_chunks + n_segments) * 5 * (ncp + 3) * 8);
+    const size_t o_wsum = take((size_t)n_windows * 40);
     const size_t o_part = take((size_t)n_segments * 5 * (ncp + 3) * 8), o_stats = take((size_t)n_segments * 120);
     LDPGTA_CUDA(cudaMalloc(&p->d_work, std::max<size_t>(off, 256)));
     base = (char *)p->d_work;
@@ -363,7 +345,7 @@ int ldpgta_set_windows(ldpgta_ctx *c, const int64_t *window_offsets, const int32
     p->d_lik = (double *)(base + o_lik);
     p->d_llr = (double *)(base + o_llr);
     p->d_mv = (double *)(base + o_mv);
-    p->d_runs = (double *)(base + o_runs);
+    p->d_wsum = (double *)(base + o_wsum);
     p->d_partials = (double *)(base + o_part);
     p->d_stats = (double *)(base + o_stats);
     LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
@@ -484,10 +466,8 @@ int ldpgta_bootstrap_stats_dev(ldpgta_ctx *c, int kind, uint64_t seed, const dou
         if (int rc = launch_sample(c, k.n, sa)) return rc;
     }
     if (int rc = evaluate_classes(c, p, kind, proportions, nullptr)) return rc;
-    StatsShape sh;
-    if (int rc = stats_shape(c, p->n_windows, p->ncp, &sh)) return rc;
-    return stats_on_device(c, p->d_lik, p->d_doff, p->n_windows, p->n_draws, p->d_segoff, p->d_segcols, p->d_segfirst, p->n_segments,
-                           p->ncp, sh, p->d_llr, p->d_mv, p->d_runs, segment_partials_dev ? segment_partials_dev : p->d_partials,
+    return stats_on_device(c, nullptr, p->d_doff, p->n_windows, p->n_draws, p->d_segoff, p->d_segcols, p->d_segfirst, p->n_segments,
+                           p->ncp, p->d_llr, p->d_mv, p->d_wsum, segment_partials_dev ? segment_partials_dev : p->d_partials,
                            segment_partials_dev ? nullptr : p->d_stats);
 }
 
@@ -551,20 +531,18 @@ int ldpgta_window_stats(ldpgta_ctx *c, const double *lik, const int64_t *window_
         if (k < 1) return fail(LDPGTA_E_INVALID, "window %lld has no draws", (long long)w);
         if (k < n_cols) return fail(LDPGTA_E_INVALID, "window %lld has %lld draws < n_cols=%d", (long long)w, (long long)k, n_cols);
     }
-    StatsShape sh;
-    if (int rc = stats_shape(c, n_windows, n_cols, &sh)) return rc;
     const int stride = n_cols + 3;
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t o = off; off += pad256(bytes); return o; };
     const size_t o_lik = take((size_t)n_draws * 32), o_seg = take(16), o_meta = take(8), o_mv = take((size_t)n_windows * 80);
-    const size_t o_runs = take((size_t)(sh.n_chunks + 1) * 5 * stride * 8), o_cp = take((size_t)5 * stride * 8);
+    const size_t o_wsum = take((size_t)n_windows * 40), o_cp = take((size_t)5 * stride * 8);
     if (int rc = ensure_dev(c, off)) return rc;
     // the LLRs and the window offsets stay on the device for ldpgta_bin_stats
     c->llr_draws = c->llr_windows = -1;
     if (int rc = ensure_own(&c->d_llr, &c->d_llr_bytes, (size_t)n_draws * 40 + 16)) return rc;
     if (int rc = ensure_own(&c->d_llr_off, &c->d_llr_off_bytes, (size_t)(n_windows + 1) * 8)) return rc;
     char *base = (char *)c->d_buf;
-    double *d_lik = (double *)(base + o_lik), *d_mv = (double *)(base + o_mv), *d_runs = (double *)(base + o_runs), *d_cp = (double *)(base + o_cp);
+    double *d_lik = (double *)(base + o_lik), *d_mv = (double *)(base + o_mv), *d_wsum = (double *)(base + o_wsum), *d_cp = (double *)(base + o_cp);
     int64_t *d_seg = (int64_t *)(base + o_seg);
     int32_t *d_meta = (int32_t *)(base + o_meta);
     const int64_t h_seg[2] = {0, n_windows};
@@ -573,8 +551,8 @@ int ldpgta_window_stats(ldpgta_ctx *c, const double *lik, const int64_t *window_
     LDPGTA_CUDA(cudaMemcpyAsync(c->d_llr_off, window_offsets, (size_t)(n_windows + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     LDPGTA_CUDA(cudaMemcpyAsync(d_seg, h_seg, 16, cudaMemcpyHostToDevice, c->stream));
     LDPGTA_CUDA(cudaMemcpyAsync(d_meta, h_meta, 8, cudaMemcpyHostToDevice, c->stream));
-    if (int rc = stats_on_device(c, d_lik, c->d_llr_off, n_windows, n_draws, d_seg, d_meta, d_meta + 1, 1, n_cols, sh, c->d_llr, d_mv,
-                                 d_runs, d_cp, nullptr))
+    if (int rc = stats_on_device(c, d_lik, c->d_llr_off, n_windows, n_draws, d_seg, d_meta, d_meta + 1, 1, n_cols, c->d_llr, d_mv,
+                                 d_wsum, d_cp, nullptr))
         return rc;
     if (llr_out && n_draws) LDPGTA_CUDA(cudaMemcpyAsync(llr_out, c->d_llr, (size_t)n_draws * 40, cudaMemcpyDeviceToHost, c->stream));
     if (window_mean_var && n_windows) LDPGTA_CUDA(cudaMemcpyAsync(window_mean_var, d_mv, (size_t)n_windows * 80, cudaMemcpyDeviceToHost, c->stream));

@@ -175,6 +175,27 @@ struct PopcSum32 {
     }
 };
 
+// LLR(y, x), ANEUPLOIDY_TEST.py:78-90: log(y / x) with the sentinels for vanishing likelihoods
+__device__ __forceinline__ double llr_of(double y, double x)
+{
+    if (x != 0.0 && y != 0.0) return log(y / x);
+    if (x != 0.0) return -1.23456789;
+    if (y != 0.0) return +1.23456789;
+    return 0.0;
+}
+
+// the five LLRs of statistics() (:298) of one draw, res = (monosomy, disomy, SPH, BPH), into llr[5][stride] at column o:
+// (BPH,SPH) (disomy,monosomy) (BPH,disomy) (disomy,SPH) (SPH,monosomy).  The draw kernels call this where they store the
+// likelihoods, so the reductions start from LLRs that never had to be re-read.
+__device__ __forceinline__ void store_llrs(double *__restrict__ llr, int64_t stride, int64_t o, const double *res)
+{
+    llr[o] = llr_of(res[3], res[2]);
+    llr[stride + o] = llr_of(res[1], res[0]);
+    llr[2 * stride + o] = llr_of(res[3], res[1]);
+    llr[3 * stride + o] = llr_of(res[1], res[2]);
+    llr[4 * stride + o] = llr_of(res[2], res[0]);
+}
+
 __device__ __forceinline__ double u128_to_double(u128 v)
 {
     return (double)(u64)(v >> 64) * 18446744073709551616.0 + (double)(u64)v;
@@ -279,7 +300,7 @@ int fail_bad_index(const ldpgta_ctx *c, const int32_t *read_idx, int64_t nnz);
 // draws of one size, device-resident indices and outputs (dispatch to k_small / k_mid / k_lanes / k_general)
 int run_uniform(ldpgta_ctx *c, int kind, int n, const int32_t *idx_dev, int64_t n_draws, const int64_t *pos_dev,
                 const double *proportions, double *out_dev, uint32_t *counts_dev, bool force_general = false,
-                const PanelView *override_view = nullptr);
+                const PanelView *override_view = nullptr, double *llr_dev = nullptr, int64_t llr_stride = 0);
 int launch_sample(ldpgta_ctx *c, int n, const SampleArgs &a);      // pick_reads on the device, n reads per draw
 void free_window_plan(ldpgta_ctx *c);
 void free_comm(ldpgta_ctx *c);

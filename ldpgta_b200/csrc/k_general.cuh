@@ -37,6 +37,8 @@ struct GeneralArgs {
     const int64_t *pos;      // optional scatter positions
     double *out;             // [*][4]
     uint32_t *counts_out;    // optional [n_draws][G][2^n]
+    double *llr;             // optional [5][llr_stride]: the five LLRs of every draw
+    int64_t llr_stride;
     const u64 *terms;        // colourings (a_h | b_h << 16 | c_h << 32) of the n-5 high reads with b_h < c_h (poly_general.cuh)
     int64_t n_terms;
     int wide;                // 64-bit convolution accumulators (a group with more than 16383 haplotypes)
@@ -447,6 +449,7 @@ __global__ void __launch_bounds__(512, 1) k_general(const GeneralArgs a)
             double2 *dst = reinterpret_cast<double2 *>(a.out + 4 * o);
             dst[0] = make_double2(res[0], res[1]);
             dst[1] = make_double2(res[2], res[3]);
+            if (a.llr) store_llrs(a.llr, a.llr_stride, o, res);
         }
     }
 }

@@ -264,6 +264,7 @@ __global__ void __launch_bounds__(32 * LanesWarps<NR>::MAX, 1) k_lanes(const __g
             double2 *dst = reinterpret_cast<double2 *>(a.out + 4 * o);
             dst[0] = make_double2(res[0], res[1]);
             dst[1] = make_double2(res[2], res[3]);
+            if (a.llr) store_llrs(a.llr, a.llr_stride, o, res);
         }
         __syncwarp();                                          // tables are rewritten by the next tile
     }

@@ -45,6 +45,8 @@ struct SmallArgs {
     const int64_t *pos;      // optional scatter positions of the outputs
     double *out;             // [*][4]
     uint32_t *counts_out;    // optional [n_draws][G][2^NR]
+    double *llr;             // optional [5][llr_stride]: the five LLRs of every draw, written with the likelihoods
+    int64_t llr_stride;
     int use_gather4;         // 4 reads per draw: one TMA gather4 per draw instead of four bulk copies
     alignas(64) CUtensorMap tmap[2];   // read-mask tensors of groups 0 and 1 (box = one row)
 };
@@ -212,6 +214,7 @@ __device__ __forceinline__ void small_store(const SmallArgs &a, int64_t draw, co
     double2 *dst = reinterpret_cast<double2 *>(a.out + 4 * o);
     dst[0] = make_double2(res[0], res[1]);
     dst[1] = make_double2(res[2], res[3]);
+    if (a.llr) store_llrs(a.llr, a.llr_stride, o, res);
 }
 
 template <int NR>

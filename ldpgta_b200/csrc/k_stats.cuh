@@ -199,15 +199,6 @@ static __global__ void k_read_scores_long(const ScoreArgs a)
     }
 }
 
-// LLR(y, x), ANEUPLOIDY_TEST.py:78-90
-__device__ __forceinline__ double llr(double y, double x)
-{
-    if (x != 0.0 && y != 0.0) return log(y / x);
-    if (x != 0.0) return -1.23456789;
-    if (y != 0.0) return +1.23456789;
-    return 0.0;
-}
-
 // pairs of statistics() (ANEUPLOIDY_TEST.py:298): indices into (monosomy, disomy, SPH, BPH)
 static __device__ __constant__ int c_pair_num[5] = {3, 1, 3, 1, 2};
 static __device__ __constant__ int c_pair_den[5] = {2, 0, 1, 2, 0};
@@ -241,154 +232,89 @@ __device__ __forceinline__ double warp_sum_comp(Comp a)
 // reduces together.
 //   k_draw_llr      one thread per draw: the five LLRs (:78-90, :298), [5][n_draws].  float64 log and division: this is
 //                   the arithmetic floor of the reductions (5 logs per draw).
-//   k_window_stats  one warp walks a chunk of `cw` consecutive windows; lane l owns the draws l, l+32, ... of a window
-//                   (= columns of the reference's zip(*A), :73) and keeps the column sums of the run in its slice of
-//                   shared memory.  A run ends at a segment border or at the chunk's end and is flushed to slot
-//                   (chunk + segment) of `runs`, so the reduction over runs (k_segment_partials) needs neither atomics nor
-//                   flags and adds in a fixed order: results are bit-reproducible.  Window mean = sum / count, variance
-//                   from the squared deviations of a second pass over the window's LLRs (registers for windows of at
-//                   most 32 draws, L1/L2 otherwise); sums of more than 32 values are Neumaier-compensated
-//                   (statistics.mean / statistics.variance of :51-56 are exact-rational).
+//                   (the draw kernels of the resident pipeline write the LLRs themselves: store_llrs, common.cuh)
+//   k_window_stats  one warp per window: mean and sample variance of the five LLR series (:51-56, :309)
+//   k_segment_partials  one block per (segment, pair): totals and the column sums of zip(*A) (:73) over the segment's
+//                   windows, fixed summation order (no atomics), optionally finished into mean / std (:65-76)
 static __global__ void k_draw_llr(const double *__restrict__ lik, int64_t n_draws, double *__restrict__ out)
 {
     for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < n_draws; d += (int64_t)gridDim.x * blockDim.x) {
         const double2 a = __ldg(reinterpret_cast<const double2 *>(lik) + 2 * d), b = __ldg(reinterpret_cast<const double2 *>(lik) + 2 * d + 1);
         const double v[4] = {a.x, a.y, b.x, b.y};
 #pragma unroll
-        for (int p = 0; p < 5; ++p) out[p * n_draws + d] = llr(v[c_pair_num[p]], v[c_pair_den[p]]);
+        for (int p = 0; p < 5; ++p) out[p * n_draws + d] = llr_of(v[c_pair_num[p]], v[c_pair_den[p]]);
     }
 }
 
 struct StatsArgs {
     const double *llr;         // [5][n_draws] per-draw LLRs
     const int64_t *doff;       // [n_windows + 1] draws of window w = [doff[w], doff[w+1])
-    const int64_t *seg_off;    // [n_segments + 1] windows of segment s = [seg_off[s], seg_off[s+1])
     int64_t n_windows, n_draws;
-    int n_segments;
-    int ncp;                   // column capacity: sums are kept for the first ncp draws of a window
-    int cw;                    // windows per chunk
     double *mean_var;          // [5][n_windows][2]
-    double *runs;              // [n_chunks + n_segments][5][ncp + 3]
+    double *wsum;              // [5][n_windows] sum of the window's LLRs (feeds the chromosome totals)
 };
 
-__device__ __forceinline__ int segment_of(const int64_t *seg_off, int n_segments, int64_t w)
-{
-    int lo = 0, hi = n_segments;                                   // largest s with seg_off[s] <= w
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (seg_off[mid] <= w) lo = mid; else hi = mid;
-    }
-    return lo;
-}
-
+// One warp per window (and all five LLR pairs): mean = sum / count, variance from the squared deviations of a second
+// pass -- registers for windows of at most 32 draws, L1/L2 otherwise; sums of more than 32 values are Neumaier-compensated
+// (statistics.mean / statistics.variance of ANEUPLOIDY_TEST.py:51-56 are exact-rational).
 static __global__ void k_window_stats(const StatsArgs a)
 {
-    extern __shared__ double sh_cols[];                            // [warps][5][ncp]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    double *cols = sh_cols + (size_t)warp * 5 * a.ncp;
-    const int64_t n_chunks = (a.n_windows + a.cw - 1) / a.cw;
-    const int stride = a.ncp + 3;
-    for (int64_t chunk = (int64_t)blockIdx.x * wpb + warp; chunk < n_chunks; chunk += (int64_t)gridDim.x * wpb) {
-        const int64_t w0 = chunk * a.cw, w1 = min(w0 + a.cw, a.n_windows);
-        int seg = segment_of(a.seg_off, a.n_segments, w0);
-        int64_t seg_end = a.seg_off[seg + 1];
-        for (int i = lane; i < 5 * a.ncp; i += 32) cols[i] = 0.0;
-        Comp total[5];
-        double n_win = 0.0, n_neg[5];
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < a.n_windows; w += warps) {
+        const int64_t b = a.doff[w], e = a.doff[w + 1];
+        const double cnt = (double)(e - b);
+        double sum[5], sq[5];
+        if (e - b <= 32) {
+            // one draw per lane, plain tree sums (5 roundings)
+            const bool live = b + lane < e;
+            double x[5];
 #pragma unroll
-        for (int p = 0; p < 5; ++p) { total[p].s = total[p].c = 0.0; n_neg[p] = 0.0; }
-        __syncwarp();
-        for (int64_t w = w0; w < w1; ++w) {
-            const int64_t b = a.doff[w], e = a.doff[w + 1];
-            const double cnt = (double)(e - b);
-            if (e - b <= 32) {
-                // one draw per lane: both passes from registers, plain tree sums (5 roundings).  The five means and
-                // the five variances are each ONE float64 division executed by lanes 0..4 side by side (a division is
-                // ~40 instructions whether one lane or all need it), the means then travel back by shuffle.
-                const bool live = b + lane < e;
-                double x[5], sum[5];
+            for (int p = 0; p < 5; ++p) x[p] = live ? __ldg(a.llr + (int64_t)p * a.n_draws + b + lane) : 0.0;
 #pragma unroll
-                for (int p = 0; p < 5; ++p) x[p] = live ? __ldg(a.llr + (int64_t)p * a.n_draws + b + lane) : 0.0;
+            for (int p = 0; p < 5; ++p) sum[p] = warp_sum_f64(x[p]);
+            // the five means are ONE float64 division executed by lanes 0..4 side by side (a division is ~40 instructions
+            // whether one lane or all need it); they travel back by shuffle
+            double mine = sum[0];
 #pragma unroll
-                for (int p = 0; p < 5; ++p) {
-                    if (live && lane < a.ncp) cols[p * a.ncp + lane] += x[p];
-                    sum[p] = warp_sum_f64(x[p]);
-                    total[p].add(sum[p]);
-                }
-                double mine = sum[0];
+            for (int p = 1; p < 5; ++p) mine = lane == p ? sum[p] : mine;
+            const double mean_l = mine / cnt;
 #pragma unroll
-                for (int p = 1; p < 5; ++p) mine = lane == p ? sum[p] : mine;
-                const double mean_l = mine / cnt;                          // lane p < 5: mean of pair p
-                double sq[5];
-#pragma unroll
-                for (int p = 0; p < 5; ++p) {
-                    const double m = __shfl_sync(0xffffffffu, mean_l, p);
-                    if (m < 0.0) n_neg[p] += 1.0;
-                    const double d = live ? x[p] - m : 0.0;
-                    sq[p] = warp_sum_f64(d * d);
-                }
-                double ss = sq[0];
-#pragma unroll
-                for (int p = 1; p < 5; ++p) ss = lane == p ? sq[p] : ss;
-                const double var_l = (e - b > 1) ? ss / (cnt - 1.0) : nan("");
-                if (lane < 5) {
-                    double *mv = a.mean_var + 2 * ((int64_t)lane * a.n_windows + w);
-                    mv[0] = mean_l;
-                    mv[1] = var_l;
-                }
-            } else {
-#pragma unroll 1
-                for (int p = 0; p < 5; ++p) {
-                    const double *x = a.llr + (int64_t)p * a.n_draws;
-                    Comp acc = {0.0, 0.0};
-                    for (int64_t i = b + lane; i < e; i += 32) {
-                        const double v = __ldg(x + i);
-                        acc.add(v);
-                        if (i - b < a.ncp) cols[p * a.ncp + (i - b)] += v;
-                    }
-                    const double s = warp_sum_comp(acc);
-                    const double m = s / cnt;
-                    Comp sq = {0.0, 0.0};
-                    for (int64_t i = b + lane; i < e; i += 32) { const double d = __ldg(x + i) - m; sq.add(d * d); }
-                    const double ss = warp_sum_comp(sq);
-                    total[p].add(s);
-                    if (m < 0.0) n_neg[p] += 1.0;
-                    if (lane == 0) {
-                        double *mv = a.mean_var + 2 * ((int64_t)p * a.n_windows + w);
-                        mv[0] = m;
-                        mv[1] = ss / (cnt - 1.0);
-                    }
-                }
+            for (int p = 0; p < 5; ++p) {
+                const double m = __shfl_sync(0xffffffffu, mean_l, p);
+                const double d = live ? x[p] - m : 0.0;
+                sq[p] = warp_sum_f64(d * d);
             }
-            n_win += 1.0;
-            if (w + 1 == seg_end || w + 1 == w1) {
-                // end of the run: flush to slot (chunk + segment)
-                __syncwarp();
-                double *out = a.runs + (chunk + seg) * (int64_t)(5 * stride);
+            double ss = sq[0];
 #pragma unroll
-                for (int p = 0; p < 5; ++p) {
-                    if (lane == 0) {
-                        out[p * stride + 0] = total[p].value();
-                        out[p * stride + 1] = n_win;
-                        out[p * stride + 2] = n_neg[p];
-                    }
-                    for (int i = lane; i < a.ncp; i += 32) { out[p * stride + 3 + i] = cols[p * a.ncp + i]; cols[p * a.ncp + i] = 0.0; }
-                    total[p].s = total[p].c = 0.0; n_neg[p] = 0.0;
+            for (int p = 1; p < 5; ++p) ss = lane == p ? sq[p] : ss;
+            if (lane < 5) {
+                double *mv = a.mean_var + 2 * ((int64_t)lane * a.n_windows + w);
+                mv[0] = mean_l;
+                mv[1] = (e - b > 1) ? ss / (cnt - 1.0) : nan("");
+                a.wsum[(int64_t)lane * a.n_windows + w] = mine;
+            }
+        } else {
+#pragma unroll 1
+            for (int p = 0; p < 5; ++p) {
+                const double *x = a.llr + (int64_t)p * a.n_draws;
+                Comp acc = {0.0, 0.0};
+                for (int64_t i = b + lane; i < e; i += 32) acc.add(__ldg(x + i));
+                const double s = warp_sum_comp(acc);
+                const double m = s / cnt;
+                Comp q = {0.0, 0.0};
+                for (int64_t i = b + lane; i < e; i += 32) { const double d = __ldg(x + i) - m; q.add(d * d); }
+                const double ss = warp_sum_comp(q);
+                if (lane == 0) {
+                    double *mv = a.mean_var + 2 * ((int64_t)p * a.n_windows + w);
+                    mv[0] = m;
+                    mv[1] = ss / (cnt - 1.0);
+                    a.wsum[(int64_t)p * a.n_windows + w] = s;
                 }
-                n_win = 0.0;
-                __syncwarp();
-                if (w + 1 == seg_end && w + 1 < w1)
-                    do { ++seg; seg_end = a.seg_off[seg + 1]; } while (seg_end <= w + 1 && seg + 1 < a.n_segments);   // skips empty segments
             }
         }
     }
 }
-
-// partials[s][p][0..ncp+3) = sum over the runs of segment s (fixed order, compensated); columns at or beyond the
-// segment's n_cols = zip truncation of ANEUPLOIDY_TEST.py:73 are zero.  One block per (segment, pair): 16 rows of 64
-// threads, row r adds the runs r, r+16, ... of a column, the rows are then combined in row order (so the result does not
-// depend on timing).  With stats != nullptr the block also finishes the (segment, pair): see segment_finish.
-constexpr int SEG_ROWS = 16, SEG_COLS = 64;
 
 // mean_and_std_of_mean_of_rnd_var (ANEUPLOIDY_TEST.py:65-76) + fraction_of_negative_LLRs (:313) of one (segment, pair) by
 // one warp: q = its partials.  The operations and their order are those of ldpgta_finish_chromosome (the squared
@@ -413,44 +339,90 @@ __device__ __forceinline__ void segment_finish(const double *q, int ncols, int f
     }
 }
 
-static __global__ void __launch_bounds__(SEG_ROWS * SEG_COLS) k_segment_partials(const double *__restrict__ runs, const int64_t *__restrict__ seg_off,
-                                                                                 const int32_t *__restrict__ seg_cols, const int32_t *__restrict__ seg_first,
-                                                                                 int ncp, int cw, double *__restrict__ partials, double *__restrict__ stats)
+// partials[s][p][0..ncp+3) of segment s = windows [seg_off[s], seg_off[s+1]) and LLR pair p, one block per (s, p):
+//   [0] sum over windows of the window sums, [1] number of windows, [2] number of windows with a negative mean,
+//   [3 + i] sum over windows of the LLR of draw i, for the columns i every window of the chromosome has (zip truncation,
+//   ANEUPLOIDY_TEST.py:73; the other columns are zero).
+// SEG_ROWS x SEG_COLS threads: row r adds the windows r, r + SEG_ROWS, ... of a column (four loads in flight), the rows are
+// then combined in row order; every sum is Neumaier-compensated and its order is fixed by the launch shape, so results are
+// bit-reproducible.  With stats != nullptr the block also finishes the (segment, pair): see segment_finish.
+constexpr int SEG_ROWS = 32, SEG_COLS = 32;
+
+struct SegmentArgs {
+    const double *llr;         // [5][n_draws]
+    const int64_t *doff;       // [n_windows + 1]
+    const double *wsum;        // [5][n_windows]
+    const double *mean_var;    // [5][n_windows][2]
+    const int64_t *seg_off;
+    const int32_t *seg_cols, *seg_first;
+    int64_t n_windows, n_draws;
+    int ncp;
+    double *partials;          // [n_segments][5][ncp + 3]
+    double *stats;             // optional [n_segments][5][3]
+};
+
+static __global__ void __launch_bounds__(SEG_ROWS * SEG_COLS) k_segment_partials(const SegmentArgs a)
 {
-    __shared__ double sh_s[SEG_ROWS][SEG_COLS], sh_c[SEG_ROWS][SEG_COLS];
-    const int s = blockIdx.x, p = blockIdx.y, stride = ncp + 3;
-    const int64_t lo = seg_off[s], hi = seg_off[s + 1];
-    const int ncols = seg_cols[s];
+    __shared__ double sh_s[SEG_ROWS][SEG_COLS + 1], sh_c[SEG_ROWS][SEG_COLS + 1];
+    const int s = blockIdx.x, p = blockIdx.y, stride = a.ncp + 3;
+    const int64_t lo = a.seg_off[s], hi = a.seg_off[s + 1];
+    const int ncols = a.seg_cols[s];
     const int cx = threadIdx.x % SEG_COLS, row = threadIdx.x / SEG_COLS;
-    double *out = partials + ((int64_t)s * 5 + p) * stride;
-    const int64_t c_lo = hi > lo ? lo / cw : 0, c_hi = hi > lo ? (hi - 1) / cw + 1 : 0;      // runs of this segment: slots chunk + s
-    for (int col0 = 0; col0 < stride; col0 += SEG_COLS) {
-        const int col = col0 + cx;
-        Comp acc = {0.0, 0.0};
-        if (col < 3 + ncols && col < stride) {
-            const double *src = runs + ((c_lo + s) * 5 + p) * (int64_t)stride + col;
-            const int64_t step = (int64_t)5 * stride;
-            int64_t k = c_lo + row;
-            for (; k + 3 * SEG_ROWS < c_hi; k += 4 * SEG_ROWS) {                             // four loads in flight
-                const double v0 = src[(k - c_lo) * step], v1 = src[(k - c_lo + SEG_ROWS) * step],
-                             v2 = src[(k - c_lo + 2 * SEG_ROWS) * step], v3 = src[(k - c_lo + 3 * SEG_ROWS) * step];
-                acc.add(v0); acc.add(v1); acc.add(v2); acc.add(v3);
-            }
-            for (; k < c_hi; k += SEG_ROWS) acc.add(src[(k - c_lo) * step]);
+    double *out = a.partials + ((int64_t)s * 5 + p) * stride;
+    const double *x = a.llr + (int64_t)p * a.n_draws;
+    // head: totals over the windows (thread t takes windows t, t + 1024, ...)
+    {
+        Comp tot = {0.0, 0.0};
+        double neg = 0.0;
+        for (int64_t w = lo + threadIdx.x; w < hi; w += SEG_ROWS * SEG_COLS) {
+            tot.add(a.wsum[(int64_t)p * a.n_windows + w]);
+            neg += a.mean_var[2 * ((int64_t)p * a.n_windows + w)] < 0.0 ? 1.0 : 0.0;
         }
-        sh_s[row][cx] = acc.s; sh_c[row][cx] = acc.c;
-        __syncthreads();
-        if (row == 0 && col < stride) {
-            Comp t = {0.0, 0.0};
 #pragma unroll
-            for (int r = 0; r < SEG_ROWS; ++r) { t.add(sh_s[r][cx]); t.c += sh_c[r][cx]; }
-            out[col] = t.value();
+        for (int m = 16; m; m >>= 1) {
+            const double os = __shfl_xor_sync(0xffffffffu, tot.s, m), oc = __shfl_xor_sync(0xffffffffu, tot.c, m);
+            tot.add(os);
+            tot.c += oc;
+            neg += __shfl_xor_sync(0xffffffffu, neg, m);
+        }
+        if (cx == 0) { sh_s[row][0] = tot.s; sh_c[row][0] = tot.c; sh_s[row][1] = neg; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            Comp t = {0.0, 0.0};
+            double n = 0.0;
+            for (int r = 0; r < SEG_ROWS; ++r) { t.add(sh_s[r][0]); t.c += sh_c[r][0]; n += sh_s[r][1]; }
+            out[0] = t.value();
+            out[1] = (double)(hi - lo);
+            out[2] = n;
         }
         __syncthreads();
     }
-    if (stats && threadIdx.x < 32) {
+    // columns
+    for (int col0 = 0; col0 < a.ncp; col0 += SEG_COLS) {
+        const int col = col0 + cx;
+        Comp acc = {0.0, 0.0};
+        if (col < ncols) {
+            int64_t w = lo + row;
+            for (; w + 3 * SEG_ROWS < hi; w += 4 * SEG_ROWS) {
+                const double v0 = x[a.doff[w] + col], v1 = x[a.doff[w + SEG_ROWS] + col], v2 = x[a.doff[w + 2 * SEG_ROWS] + col],
+                             v3 = x[a.doff[w + 3 * SEG_ROWS] + col];
+                acc.add(v0); acc.add(v1); acc.add(v2); acc.add(v3);
+            }
+            for (; w < hi; w += SEG_ROWS) acc.add(x[a.doff[w] + col]);
+        }
+        sh_s[row][cx] = acc.s; sh_c[row][cx] = acc.c;
+        __syncthreads();
+        if (row == 0 && col < a.ncp) {
+            Comp t = {0.0, 0.0};
+#pragma unroll
+            for (int r = 0; r < SEG_ROWS; ++r) { t.add(sh_s[r][cx]); t.c += sh_c[r][cx]; }
+            out[3 + col] = t.value();
+        }
+        __syncthreads();
+    }
+    if (a.stats && threadIdx.x < 32) {
         __threadfence_block();
-        segment_finish(out, ncols, seg_first[s], stats + 3 * ((int64_t)s * 5 + p), threadIdx.x);
+        segment_finish(out, ncols, a.seg_first[s], a.stats + 3 * ((int64_t)s * 5 + p), threadIdx.x);
     }
 }
 

@@ -136,7 +136,7 @@ int check_kind(const ldpgta_ctx *c, int kind, const double *proportions)
 // draws of one size, device-resident indices and outputs
 int run_uniform(ldpgta_ctx *c, int kind, int n, const int32_t *idx_dev, int64_t n_draws, const int64_t *pos_dev,
                 const double *proportions, double *out_dev, uint32_t *counts_dev, bool force_general,
-                const PanelView *override_view)
+                const PanelView *override_view, double *llr_dev, int64_t llr_stride)
 {
     if (n_draws == 0) return 0;
     if (n < 2 || n > MAXN) return fail(LDPGTA_E_UNSUPPORTED, "draws of %d reads are outside the supported range 2..%d", n, MAXN);
@@ -144,12 +144,14 @@ int run_uniform(ldpgta_ctx *c, int kind, int n, const int32_t *idx_dev, int64_t 
         SmallArgs a;
         a.pv = override_view ? *override_view : make_view(c, proportions);
         a.idx = idx_dev; a.n_draws = n_draws; a.pos = pos_dev; a.out = out_dev; a.counts_out = counts_dev;
+        a.llr = llr_dev; a.llr_stride = llr_stride;
         return launch_small(c, a, n, kind);
     }
     GeneralArgs a;
     a.pv = override_view ? *override_view : make_view(c, proportions);
     a.kind = kind; a.n = n; a.kl = a.kh = a.wc = 0; a.etab = 0; a.etab_scratch = nullptr; a.etab_stride = 0;
     a.idx = idx_dev; a.n_draws = n_draws; a.pos = pos_dev; a.out = out_dev; a.counts_out = counts_dev;
+    a.llr = llr_dev; a.llr_stride = llr_stride;
     a.terms = nullptr; a.n_terms = 0; a.wide = 0; a.table_scratch = nullptr; a.table_stride = 0;
     // measured (tools/bench_lanes.sh): k_mid leads at 5 reads of a one-group model, k_lanes from 6 reads on
     const bool mid_ok = (n == 5 || n == 6) && kind == LDPGTA_HOMOGENEOUS && !force_general;
@@ -161,6 +163,7 @@ int run_uniform(ldpgta_ctx *c, int kind, int n, const int32_t *idx_dev, int64_t 
         SmallArgs sa;
         sa.pv = a.pv;
         sa.idx = idx_dev; sa.n_draws = n_draws; sa.pos = pos_dev; sa.out = out_dev; sa.counts_out = counts_dev;
+        sa.llr = llr_dev; sa.llr_stride = llr_stride;
         const int rc = launch_mid(c, sa, n);
         if (rc <= 0) return rc;
     }

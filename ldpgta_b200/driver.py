@@ -229,7 +229,7 @@ def make_examiner(obs_tab, leg_tab, hap_tab, number_of_haplotypes, ancestral_mak
         return recent_admixture(obs_tab, leg_tab, hap_tab, number_of_haplotypes, models_dict, device=device, panel=panel)
     if type(ancestral_makeup) == dict:
         print('Assuming the following ancestral makeup:', ", ".join("{:.1f}% {}".format(100 * v, k) for k, v in ancestral_makeup.items()))
-        return distant_admixture(obs_tab, leg_tab, hap_tab, number_of_haplotypes, models_dict, ancestral_makeup, device=device)
+        return distant_admixture(obs_tab, leg_tab, hap_tab, number_of_haplotypes, models_dict, ancestral_makeup, device=device, panel=panel)
     raise Exception('error: unsupported ancestral-makeup.')
 
 
@@ -353,7 +353,7 @@ def evaluate_draw_indices(examine, reads_dict, genomic_windows, plan):
 def bootstrap(obs_tab, leg_tab, hap_tab, number_of_haplotypes, ancestral_makeup, models_dict, window_size, subsamples,
               offset, min_reads, max_reads, min_score, min_HF, replay=None, device=0, panel=None, fast_rng=None):
     """ ANEUPLOIDY_TEST.bootstrap (:250-287): (likelihoods, genomic_windows, fraction_of_matches).
-    `panel`: an engine.ResidentPanel of this chromosome shared by many samples (one or two populations);
+    `panel`: an engine.ResidentPanel of this chromosome shared by many samples (for a dict makeup: groups in the makeup's order);
     `fast_rng`: numpy Generator for vectorised draws (throughput runs; not the reference's random stream). """
     examine = make_examiner(obs_tab, leg_tab, hap_tab, number_of_haplotypes, ancestral_makeup, models_dict, device=device, panel=panel)
     try:

@@ -283,7 +283,7 @@ class distant_admixture(_PanelModel):
     kind = N.DISTANT_ADMIXTURE
     tuple_type = TUPLES['DISTANT_ADMIXTURE_MODELS']
 
-    def __init__(self, obs_tab, leg_tab, hap_tab_per_group, number_of_haplotypes_per_group, models_dict, ancestral_makeup, device=0):
+    def __init__(self, obs_tab, leg_tab, hap_tab_per_group, number_of_haplotypes_per_group, models_dict, ancestral_makeup, device=0, panel=None):
         print('Initializing the algorithm for distant admixtures:')
         if not all(len(leg_tab) == len(hap_tab) for hap_tab in hap_tab_per_group.values()):
             raise Exception('Error: the number of SNPs in the LEGEND file differ from the number of SNPs in the HAP file.')
@@ -298,7 +298,8 @@ class distant_admixture(_PanelModel):
         # device groups follow the ancestral_makeup order: that is the summation order of
         # effective_joint_frequency (:138-139); panel groups outside the makeup carry no weight
         ordered = {g: hap_tab_per_group[g] for g in ancestral_makeup}
-        self._load_panel(obs_tab, leg_tab, ordered, number_of_haplotypes_per_group, device)
+        # a ResidentPanel shared by many samples must hold its groups in that same order (engine.ResidentPanel(leg, {g: hap[g] for g in makeup}, ...))
+        self._load_panel(obs_tab, leg_tab, ordered, number_of_haplotypes_per_group, device, panel)
         self.fraction_of_matches = {g: self.fraction_of_matches[next(iter(ordered))] for g in hap_tab_per_group}
         self._hap_tabs = hap_tab_per_group
         self._nhap = {g: number_of_haplotypes_per_group[g] for g in hap_tab_per_group}

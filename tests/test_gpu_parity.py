@@ -659,6 +659,18 @@ def test_resident_panel_gather_equals_host_packing(golden_testmodule, golden_inp
         assert worst < LIK_TOL
     for p in (panel1, panel2, shared):
         p.close()
+    # distant admixture: the shared panel holds its groups in the order of the ancestral makeup (G1 first here)
+    args, out = chrom_case('distant_m6', golden_inputs)
+    cfg = args['cfg']
+    order = list(args['ancestral_makeup'])
+    shared = L.ResidentPanel(args['leg_tab'], {g: args['hap_tab'][g] for g in order}, args['number_of_haplotypes'])
+    lik, _, matches = L.bootstrap(args['obs_tab'], args['leg_tab'], args['hap_tab'], args['number_of_haplotypes'],
+                                  args['ancestral_makeup'], L.ImplicitModels(), cfg['window_size'], cfg['subsamples'],
+                                  cfg['offset'], cfg['min_reads'], cfg['max_reads'], cfg['min_score'], cfg['min_HF'],
+                                  replay=out['draws'], panel=shared)
+    assert matches == out['fraction_of_matches']
+    assert max(max_rel(x, y) for w in lik for x, y in zip(lik[w], out['likelihoods'][w])) < LIK_TOL
+    shared.close()
 
 
 def test_command_line_interface(tmp_path, golden_inputs):
