@@ -99,6 +99,16 @@ static int stats_on_device(ldpgta_ctx *c, const double *d_lik, const int64_t *d_
 static size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
 
 // draws of every class -> likelihoods in the sample-wide order (plan->d_lik), optionally streaming them to the host
+// The draw kernels for 5 or more reads write the five LLRs of a draw next to its likelihoods (their per-draw epilogue is
+// negligible); for 2..4 reads (k_small: 0.4 ns per draw) the LLRs are a separate pass over the likelihoods (k_draw_llr),
+// measured equal in total and leaving the dominant kernel to its AND / POPC work.
+static bool llr_fused(const WindowPlan *p)
+{
+    for (const SizeClass &k : p->classes)
+        if (k.n <= 4) return false;
+    return true;
+}
+
 static int time_mark(ldpgta_ctx *c)
 {
     if (!c->time_kernels) return 0;
@@ -132,7 +142,7 @@ static int evaluate_classes_inner(ldpgta_ctx *c, WindowPlan *p, int kind, const 
         for (int64_t d0 = 0; d0 < p->n_draws; d0 += per, ++ci) {
             const int64_t nd = std::min(per, p->n_draws - d0);
             if (int rc = run_uniform(c, kind, k.n, k.d_idx + d0 * k.n, nd, nullptr, proportions, p->d_lik + 4 * d0, nullptr, false, nullptr,
-                                     p->d_llr + d0, p->n_draws))
+                                     llr_fused(p) ? p->d_llr + d0 : nullptr, p->n_draws))
                 return rc;
             LDPGTA_CUDA(cudaEventRecord(c->ev_k[ci], c->stream));
             LDPGTA_CUDA(cudaStreamWaitEvent(c->s_out, c->ev_k[ci], 0));
@@ -141,7 +151,8 @@ static int evaluate_classes_inner(ldpgta_ctx *c, WindowPlan *p, int kind, const 
         return 0;
     }
     for (const SizeClass &k : p->classes)
-        if (int rc = run_uniform(c, kind, k.n, k.d_idx, k.n_draws, k.d_pos, proportions, p->d_lik, nullptr, false, nullptr, p->d_llr, p->n_draws))
+        if (int rc = run_uniform(c, kind, k.n, k.d_idx, k.n_draws, k.d_pos, proportions, p->d_lik, nullptr, false, nullptr,
+                                 llr_fused(p) ? p->d_llr : nullptr, p->n_draws))
             return rc;
     if (lik_out_pinned) {
         if (int rc = ensure_pipeline(c, 2)) return rc;
@@ -168,7 +179,7 @@ static int reduce_and_download(ldpgta_ctx *c, WindowPlan *p, double *lik_out, do
 {
     double *d_llr = p->d_llr;
     c->llr_draws = c->llr_windows = -1;
-    if (int rc = stats_on_device(c, nullptr, p->d_doff, p->n_windows, p->n_draws, p->d_segoff, p->d_segcols, p->d_segfirst,
+    if (int rc = stats_on_device(c, llr_fused(p) ? nullptr : p->d_lik, p->d_doff, p->n_windows, p->n_draws, p->d_segoff, p->d_segcols, p->d_segfirst,
                                  p->n_segments, p->ncp, d_llr, p->d_mv, p->d_wsum, p->d_partials, p->d_stats))
         return rc;
     const size_t cp_b = (size_t)p->n_segments * 5 * (p->ncp + 3) * 8;
@@ -466,7 +477,7 @@ int ldpgta_bootstrap_stats_dev(ldpgta_ctx *c, int kind, uint64_t seed, const dou
         if (int rc = launch_sample(c, k.n, sa)) return rc;
     }
     if (int rc = evaluate_classes(c, p, kind, proportions, nullptr)) return rc;
-    return stats_on_device(c, nullptr, p->d_doff, p->n_windows, p->n_draws, p->d_segoff, p->d_segcols, p->d_segfirst, p->n_segments,
+    return stats_on_device(c, llr_fused(p) ? nullptr : p->d_lik, p->d_doff, p->n_windows, p->n_draws, p->d_segoff, p->d_segcols, p->d_segfirst, p->n_segments,
                            p->ncp, p->d_llr, p->d_mv, p->d_wsum, segment_partials_dev ? segment_partials_dev : p->d_partials,
                            segment_partials_dev ? nullptr : p->d_stats);
 }

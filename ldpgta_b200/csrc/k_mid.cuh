@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(MidPipe<NR, W64>::NWARPS * 32, 1) k_mid(const 
             if (kk <= k) {
                 double res[4];
                 mid_polynomial<NR>(cc, a.pv.nhap[0], res);
-                if (draw_k < a.n_draws) small_store(a, draw_k, res);
+                if (draw_k < a.n_draws) small_store<true>(a, draw_k, res);
             }
             __syncwarp();
         }

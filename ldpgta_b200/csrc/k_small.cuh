@@ -90,6 +90,15 @@ __device__ __forceinline__ void tma_gather4_g2s(void *dst_smem, const CUtensorMa
     asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
                  ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(smem_u32(bar)) : "memory");
 }
+// per-lane asynchronous 16-byte copies global -> shared (LDGSTS): every lane stages exactly the slots it will read
+// back itself, so completion is a per-thread cp.async.wait_group and no barrier or elected producer is involved
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src_gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ void fence_proxy_async()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -208,13 +217,15 @@ struct SmallModel {
     }
 };
 
+// WITH_LLR: also write the draw's five LLRs (k_mid); k_small leaves them to k_draw_llr (see bootstrap_api.cu: llr_fused)
+template <bool WITH_LLR = false>
 __device__ __forceinline__ void small_store(const SmallArgs &a, int64_t draw, const double *res)
 {
     const int64_t o = a.pos ? a.pos[draw] : draw;
     double2 *dst = reinterpret_cast<double2 *>(a.out + 4 * o);
     dst[0] = make_double2(res[0], res[1]);
     dst[1] = make_double2(res[2], res[3]);
-    if (a.llr) store_llrs(a.llr, a.llr_stride, o, res);
+    if (WITH_LLR && a.llr) store_llrs(a.llr, a.llr_stride, o, res);
 }
 
 template <int NR>
@@ -239,7 +250,10 @@ struct SmallPipe {
     static constexpr int SMEM = BARS + NWARPS * 16;
 };
 
-template <int NR, int LPD, int WPL, int KIND>
+// CA = true: the masks are staged by per-lane cp.async (LDGSTS) instead of TMA.  A lane copies the 16-byte slots it later
+// reads into registers (slot j * LPD + lane_in of each of its draw's reads), ~30 instructions per tile; the TMA route
+// spends ~4x that on electing a lane, moving per-draw coordinates into uniform registers and arming the mbarrier.
+template <int NR, int LPD, int WPL, int KIND, bool CA = false>
 __global__ void __launch_bounds__(SmallPipe<NR, WPL>::NWARPS * 32, 1) k_small(const __grid_constant__ SmallArgs a)
 {
     static_assert(WPL % 2 == 0, "rows are read in 16-byte slots");
@@ -302,11 +316,48 @@ __global__ void __launch_bounds__(SmallPipe<NR, WPL>::NWARPS * 32, 1) k_small(co
     int cur_g = 0, nxt_g = 0;
     auto advance = [&](int64_t &tile, int &g) { if (++g == G) { g = 0; tile += tstride; } };
 
+    // ---- CA staging: every lane handles the NR reads of its own draw ----
+    const bool idx_vec = (reinterpret_cast<uintptr_t>(a.idx) & 15) == 0;
+    int32_t ca_idx[NR];                      // read rows of this lane's draw in the next stage to issue
+    uint32_t ca_pc_nxt[NR];                  // their popcounts (stage in flight)
+    auto ca_load_idx = [&](int64_t tile) {
+        int64_t d = tile * DPW + dgrp;
+        if (d >= a.n_draws) d = a.n_draws - 1;
+        if (NR == 4 && idx_vec) {
+            const int4 v = __ldg(reinterpret_cast<const int4 *>(a.idx) + d);
+            ca_idx[0] = v.x; ca_idx[1] = v.y; ca_idx[2 % NR] = v.z; ca_idx[3 % NR] = v.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < NR; ++i) ca_idx[i] = __ldg(a.idx + d * NR + i);
+        }
+    };
+    auto ca_issue = [&](int g_) {
+        const int g = KIND == LDPGTA_HOMOGENEOUS ? 0 : g_;
+        const int wp = a.pv.wp[g];
+        unsigned char *st = wbase + (size_t)(dgrp * NR) * wp * 8;
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            const uint64_t *src = a.pv.masks[g] + (int64_t)ca_idx[i] * wp;
+#pragma unroll
+            for (int j = 0; j < SLOTS; ++j) {
+                const int w = (j * LPD + lane_in) * 2;
+                if (wp == LPD * WPL || w < wp) cp_async16(st + ((size_t)i * wp + w) * 8, src + w);
+            }
+            ca_pc_nxt[i] = __ldg(a.pv.popc[g] + ca_idx[i]);
+        }
+        cp_async_commit();
+    };
+
     // prologue: stage 0 in flight, indices of stage 1 loaded
     uint32_t pc_cur = 0;                     // row popcounts of the stage in the buffer
     int32_t idx_nxt = 0;                     // row index of the next stage to issue
-    if (n_stages > 0) { pc_cur = issue(nxt_g, load_idx(nxt_tile)); advance(nxt_tile, nxt_g); }
-    if (n_stages > 1) idx_nxt = load_idx(nxt_tile);
+    if (CA) {
+        if (n_stages > 0) { ca_load_idx(nxt_tile); ca_issue(nxt_g); advance(nxt_tile, nxt_g); }
+        if (n_stages > 1 && nxt_g == 0) ca_load_idx(nxt_tile);
+    } else {
+        if (n_stages > 0) { pc_cur = issue(nxt_g, load_idx(nxt_tile)); advance(nxt_tile, nxt_g); }
+        if (n_stages > 1) idx_nxt = load_idx(nxt_tile);
+    }
 
     SmallModel<NR, KIND> model;
     uint32_t parity = 0;
@@ -322,14 +373,19 @@ __global__ void __launch_bounds__(SmallPipe<NR, WPL>::NWARPS * 32, 1) k_small(co
         uint32_t c[NS];
 #pragma unroll
         for (int s = 0; s < NS; ++s) c[s] = 0;
+        if (CA) {
 #pragma unroll
-        for (int i = 0; i < NR; ++i) {
-            const uint32_t v = __shfl_sync(0xffffffffu, pc_cur, dgrp * NR + i);
-            if (lane_in == 0) c[1 << i] = v;
+            for (int i = 0; i < NR; ++i) if (lane_in == 0) c[1 << i] = ca_pc_nxt[i];
+            cp_async_wait_all();
+        } else {
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                const uint32_t v = __shfl_sync(0xffffffffu, pc_cur, dgrp * NR + i);
+                if (lane_in == 0) c[1 << i] = v;
+            }
+            mbar_wait(bar, parity);
+            parity ^= 1u;
         }
-
-        mbar_wait(bar, parity);
-        parity ^= 1u;
 
         uint4 m[NR][SLOTS];
         {
@@ -353,7 +409,13 @@ __global__ void __launch_bounds__(SmallPipe<NR, WPL>::NWARPS * 32, 1) k_small(co
         }
         // the buffer is free again: refill it with the next stage, which lands while this one is computed
         __syncwarp();
-        if (q + 1 < n_stages) {
+        if (CA) {
+            if (q + 1 < n_stages) {
+                ca_issue(nxt_g);                                   // same draw indices for every group of a tile
+                advance(nxt_tile, nxt_g);
+                if (q + 2 < n_stages && nxt_g == 0) ca_load_idx(nxt_tile);
+            }
+        } else if (q + 1 < n_stages) {
             fence_proxy_async();
             pc_cur = issue(nxt_g, idx_nxt);
             advance(nxt_tile, nxt_g);

@@ -12,7 +12,9 @@ template <int NR, int LPD, int WPL, int KIND>
 static int launch_small_pipe(ldpgta_ctx *c, SmallArgs &a)
 {
     using P = SmallPipe<NR, WPL>;
-    auto kern = k_small<NR, LPD, WPL, KIND>;
+    // staging by per-lane cp.async (default) or by TMA gather4 / bulk copies (LDPGTA_SMALL_TMA=1), see k_small.cuh
+    static const bool use_tma = getenv("LDPGTA_SMALL_TMA") != nullptr;
+    auto kern = use_tma ? k_small<NR, LPD, WPL, KIND, false> : k_small<NR, LPD, WPL, KIND, true>;
     LDPGTA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM));
     constexpr int DPW = 32 / LPD;
     const int64_t tiles = (a.n_draws + DPW - 1) / DPW;
