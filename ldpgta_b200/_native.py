@@ -8,7 +8,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libldpgta.so')
+# LDPGTA_LIB: an alternative build of the library (kernel experiments, tools/build_variant.py); default = the in-tree build
+LIB_PATH = os.environ.get('LDPGTA_LIB') or os.path.join(_HERE, 'libldpgta.so')
 
 HOMOGENEOUS, RECENT_ADMIXTURE, DISTANT_ADMIXTURE = 0, 1, 2
 MAX_READS_PER_DRAW = 18

@@ -331,19 +331,35 @@ __global__ void __launch_bounds__(SmallPipe<NR, WPL>::NWARPS * 32, 1) k_small(co
             for (int i = 0; i < NR; ++i) ca_idx[i] = __ldg(a.idx + d * NR + i);
         }
     };
+    const uint32_t ca_dst0 = smem_u32(wbase) + (uint32_t)(dgrp * NR) * (uint32_t)(LPD * WPL * 8) + (uint32_t)lane_in * 16u;   // exact rows
     auto ca_issue = [&](int g_) {
         const int g = KIND == LDPGTA_HOMOGENEOUS ? 0 : g_;
         const int wp = a.pv.wp[g];
-        unsigned char *st = wbase + (size_t)(dgrp * NR) * wp * 8;
+        const uint64_t *masks = a.pv.masks[g];
+        const uint32_t *popc = a.pv.popc[g];
+        if (wp == LPD * WPL) {
+            // rows fill the lane grid exactly: slot j of read i sits j * LPD * 16 bytes after the lane's first slot
 #pragma unroll
-        for (int i = 0; i < NR; ++i) {
-            const uint64_t *src = a.pv.masks[g] + (int64_t)ca_idx[i] * wp;
+            for (int i = 0; i < NR; ++i) {
+                const char *src = reinterpret_cast<const char *>(masks + (int64_t)ca_idx[i] * (LPD * WPL)) + lane_in * 16;
 #pragma unroll
-            for (int j = 0; j < SLOTS; ++j) {
-                const int w = (j * LPD + lane_in) * 2;
-                if (wp == LPD * WPL || w < wp) cp_async16(st + ((size_t)i * wp + w) * 8, src + w);
+                for (int j = 0; j < SLOTS; ++j)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ca_dst0 + (uint32_t)(i * LPD * WPL * 8 + j * LPD * 16)),
+                                 "l"(src + j * LPD * 16) : "memory");
+                ca_pc_nxt[i] = __ldg(popc + ca_idx[i]);
             }
-            ca_pc_nxt[i] = __ldg(a.pv.popc[g] + ca_idx[i]);
+        } else {
+            unsigned char *st = wbase + (size_t)(dgrp * NR) * wp * 8;
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                const uint64_t *src = masks + (int64_t)ca_idx[i] * wp;
+#pragma unroll
+                for (int j = 0; j < SLOTS; ++j) {
+                    const int w = (j * LPD + lane_in) * 2;
+                    if (w < wp) cp_async16(st + ((size_t)i * wp + w) * 8, src + w);
+                }
+                ca_pc_nxt[i] = __ldg(popc + ca_idx[i]);
+            }
         }
         cp_async_commit();
     };
@@ -423,6 +439,45 @@ __global__ void __launch_bounds__(SmallPipe<NR, WPL>::NWARPS * 32, 1) k_small(co
         }
 
         small_subset_counts<NR, WPL>(m, c);
+#ifndef LDPGTA_SMALL_NO_PACKED_BATCH
+        if (BATCHED && NS >= 8 && a.pv.nhap[0] <= 65535u && !a.counts_out) {
+            // one-group model, counts below 2^16: two counters per register from the lane partials on -- through the
+            // group's xor-shuffles and the per-warp batch table -- and unpacked once per draw by the lane that finishes it
+            uint32_t pk[NS / 2];
+#pragma unroll
+            for (int t = 0; t < NS / 2; ++t) {
+                pk[t] = c[2 * t] + (c[2 * t + 1] << 16);
+#pragma unroll
+                for (int msk = LPD / 2; msk; msk >>= 1) pk[t] += __shfl_xor_sync(0xffffffffu, pk[t], msk);
+            }
+            const int k = (int)(q % TPB);
+            if (lane_in == 0) {
+                const int slot = k * DPW + dgrp;
+#pragma unroll
+                for (int j = 0; j < NS / 8; ++j) batch[j * 32 + slot] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            }
+            if (k == TPB - 1 || q + 1 == n_stages) {
+                __syncwarp();
+                uint32_t cc[NS];
+#pragma unroll
+                for (int j = 0; j < NS / 8; ++j) {
+                    const uint4 v = batch[j * 32 + lane];
+                    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { cc[8 * j + 2 * e] = w4[e] & 0xffffu; cc[8 * j + 2 * e + 1] = w4[e] >> 16; }
+                }
+                const int kk = lane / DPW;
+                const int64_t draw_k = (tile0 + (q - k + kk) * tstride) * DPW + lane % DPW;
+                double res[4];
+                if (kk <= k) {
+                    model.fold(a.pv, 0, cc, res);
+                    if (draw_k < a.n_draws) small_store(a, draw_k, res);
+                }
+                __syncwarp();
+            }
+            continue;
+        }
+#endif
         small_group_sum<NR, LPD>(c, a.pv.nhap[g] <= 65535u);
         if (a.counts_out && writer) small_dump<NR>(a, draw, g, c);
         if (BATCHED) {
