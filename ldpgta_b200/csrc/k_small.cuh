@@ -250,9 +250,11 @@ struct SmallPipe {
     static constexpr int SMEM = BARS + NWARPS * 16;
 };
 
-// CA = true: the masks are staged by per-lane cp.async (LDGSTS) instead of TMA.  A lane copies the 16-byte slots it later
-// reads into registers (slot j * LPD + lane_in of each of its draw's reads), ~30 instructions per tile; the TMA route
-// spends ~4x that on electing a lane, moving per-draw coordinates into uniform registers and arming the mbarrier.
+// CA = true (experiment, LDPGTA_SMALL_CPASYNC=1): the masks are staged by per-lane cp.async (LDGSTS) instead of TMA.  A lane
+// copies the 16-byte slots it later reads into registers (slot j * LPD + lane_in of each of its draw's reads): ~80 SASS
+// instructions per tile against ~120 for the TMA route (electing a lane, per-draw coordinates into uniform registers,
+// arming the mbarrier), yet the kernel is no faster (the AND / carry-save / POPC core is 650 of ~950 instructions per tile
+// and the register file, not the issue rate of the staging code, limits the warps in flight).
 template <int NR, int LPD, int WPL, int KIND, bool CA = false>
 __global__ void __launch_bounds__(SmallPipe<NR, WPL>::NWARPS * 32, 1) k_small(const __grid_constant__ SmallArgs a)
 {

@@ -12,9 +12,10 @@ template <int NR, int LPD, int WPL, int KIND>
 static int launch_small_pipe(ldpgta_ctx *c, SmallArgs &a)
 {
     using P = SmallPipe<NR, WPL>;
-    // staging by per-lane cp.async (default) or by TMA gather4 / bulk copies (LDPGTA_SMALL_TMA=1), see k_small.cuh
-    static const bool use_tma = getenv("LDPGTA_SMALL_TMA") != nullptr;
-    auto kern = use_tma ? k_small<NR, LPD, WPL, KIND, false> : k_small<NR, LPD, WPL, KIND, true>;
+    // staging by TMA (gather4 / bulk copies; default) or by per-lane cp.async (LDPGTA_SMALL_CPASYNC=1): measured equal for one
+    // group (0.3748 vs 0.3752 ms per configs[1] step), 12 % slower for two groups -- see k_small.cuh and DESIGN.md
+    static const bool use_ca = [] { const char *e = getenv("LDPGTA_SMALL_CPASYNC"); return e && *e && *e != '0'; }();
+    auto kern = use_ca ? k_small<NR, LPD, WPL, KIND, true> : k_small<NR, LPD, WPL, KIND, false>;
     LDPGTA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM));
     constexpr int DPW = 32 / LPD;
     const int64_t tiles = (a.n_draws + DPW - 1) / DPW;
