@@ -73,7 +73,7 @@ int launch_sample(ldpgta_ctx *c, int n, const SampleArgs &a)
 // finished segment statistics, all on c->stream
 static int stats_on_device(ldpgta_ctx *c, const double *d_lik, const int64_t *d_doff, int64_t n_windows, int64_t n_draws,
                            const int64_t *d_segoff, const int32_t *d_segcols, const int32_t *d_segfirst, int n_segments, int ncp,
-                           double *d_llr, double *d_mv, double *d_wsum, double *d_partials, double *d_stats)
+                           double *d_llr, double *d_mv, double *d_wsum, double *d_partials, double *d_stats, double *mv_host = nullptr)
 {
     if (n_draws > 0 && d_lik) {                       // d_lik == nullptr: the draw kernels have written the LLRs already
         const unsigned blocks = (unsigned)std::min<int64_t>((n_draws + 255) / 256, (int64_t)c->sm_count * 8);
@@ -86,6 +86,13 @@ static int stats_on_device(ldpgta_ctx *c, const double *d_lik, const int64_t *d_
         const unsigned blocks = (unsigned)std::min<int64_t>((n_windows + 7) / 8, (int64_t)c->sm_count * 32);
         k_window_stats<<<blocks, 256, 0, c->stream>>>(a);
         c->launches++;
+        if (mv_host) {
+            // the window statistics (80 bytes per window) start their way down while the segment sums are formed
+            if (int rc = ensure_pipeline(c, 2)) return rc;
+            LDPGTA_CUDA(cudaEventRecord(c->ev_in[0], c->stream));
+            LDPGTA_CUDA(cudaStreamWaitEvent(c->s_out, c->ev_in[0], 0));
+            LDPGTA_CUDA(cudaMemcpyAsync(mv_host, d_mv, (size_t)n_windows * 80, cudaMemcpyDeviceToHost, c->s_out));
+        }
     }
     SegmentArgs sa;
     sa.llr = d_llr; sa.doff = d_doff; sa.wsum = d_wsum; sa.mean_var = d_mv; sa.seg_off = d_segoff; sa.seg_cols = d_segcols;
@@ -135,7 +142,8 @@ static int evaluate_classes_inner(ldpgta_ctx *c, WindowPlan *p, int kind, const 
     if (p->classes.size() == 1 && lik_out_pinned && p->n_draws >= 65536) {
         // one draw size (the usual plan): chunks, the download of chunk i under the kernel of chunk i + 1
         const SizeClass &k = p->classes[0];
-        const int64_t n_chunks = std::min<int64_t>(16, p->n_draws / 32768);
+        static const int64_t max_chunks = [] { const char *e = getenv("LDPGTA_FULL_CHUNKS"); return e && atoi(e) > 0 ? (int64_t)atoi(e) : (int64_t)16; }();
+        const int64_t n_chunks = std::max<int64_t>(1, std::min<int64_t>(max_chunks, p->n_draws / 32768));
         const int64_t per = ((p->n_draws + n_chunks - 1) / n_chunks + 63) & ~(int64_t)63;
         if (int rc = ensure_pipeline(c, (int)n_chunks + 1)) return rc;
         int ci = 0;
@@ -180,19 +188,15 @@ static int reduce_and_download(ldpgta_ctx *c, WindowPlan *p, double *lik_out, do
     double *d_llr = p->d_llr;
     c->llr_draws = c->llr_windows = -1;
     if (int rc = stats_on_device(c, llr_fused(p) ? nullptr : p->d_lik, p->d_doff, p->n_windows, p->n_draws, p->d_segoff, p->d_segcols, p->d_segfirst,
-                                 p->n_segments, p->ncp, d_llr, p->d_mv, p->d_wsum, p->d_partials, p->d_stats))
+                                 p->n_segments, p->ncp, d_llr, p->d_mv, p->d_wsum, p->d_partials, p->d_stats, window_mean_var))
         return rc;
     const size_t cp_b = (size_t)p->n_segments * 5 * (p->ncp + 3) * 8;
-    if (window_mean_var && p->n_windows)
-        LDPGTA_CUDA(cudaMemcpyAsync(window_mean_var, p->d_mv, (size_t)p->n_windows * 80, cudaMemcpyDeviceToHost, c->stream));
     if (segment_partials) LDPGTA_CUDA(cudaMemcpyAsync(segment_partials, p->d_partials, cp_b, cudaMemcpyDeviceToHost, c->stream));
     if (segment_stats) LDPGTA_CUDA(cudaMemcpyAsync(segment_stats, p->d_stats, (size_t)p->n_segments * 120, cudaMemcpyDeviceToHost, c->stream));
     if (llr_out && p->n_draws) LDPGTA_CUDA(cudaMemcpyAsync(llr_out, d_llr, (size_t)p->n_draws * 40, cudaMemcpyDeviceToHost, c->stream));
     LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
-    if (lik_out) {
-        LDPGTA_CUDA(cudaStreamSynchronize(c->s_out));
-        if (lik_pinned != lik_out) memcpy(lik_out, lik_pinned, (size_t)p->n_draws * 32);
-    }
+    if (lik_out || window_mean_var) LDPGTA_CUDA(cudaStreamSynchronize(c->s_out));
+    if (lik_out && lik_pinned != lik_out) memcpy(lik_out, lik_pinned, (size_t)p->n_draws * 32);
     c->llr_ptr = p->d_llr; c->llr_off_ptr = p->d_doff;
     c->llr_draws = p->n_draws; c->llr_windows = p->n_windows;
     return 0;
