@@ -257,6 +257,8 @@ struct ldpgta_ctx {
     // windows + bootstrap plan made resident by ldpgta_set_windows (bootstrap_api.cu)
     ldpgta::WindowPlan *plan = nullptr;
     void *comm = nullptr;                     // peer-memory communicator (comm_api.cu)
+    // page-locked, device-mapped block for the inputs and the result of single get_likelihoods calls
+    unsigned char *h_io = nullptr, *d_io = nullptr;
     // optional CUDA-event brackets around the draw kernels of the resident pipeline (ldpgta_kernel_timing)
     bool time_kernels = false;
     std::vector<cudaEvent_t> t_ev;      // pairs (start, stop), reused

@@ -66,6 +66,45 @@ static __global__ void k_build_read_masks(const uint64_t *__restrict__ rows, con
     }
 }
 
+// One call of model.get_likelihoods(alleles) (HOMOGENOUES_MODELS.py:272-286): build_intrenal_hap_dict for the n
+// haplotypes of the call, their popcounts and the identity draw 0..n-1 in ONE launch (one block per group); the inputs
+// come straight from page-locked host memory the device can read (no staging copies for a few hundred bytes).
+struct SingleArgs {
+    const uint64_t *rows[MAXG];     // allele rows [n_alleles][wp[g]]
+    uint64_t *masks[MAXG];          // out: [n][wp[g]] scratch read masks
+    uint32_t *popc[MAXG];           // out: [n]
+    int wp[MAXG];
+    const int32_t *allele_idx;      // device-visible host memory
+    const int64_t *off;             // [n + 1]
+    int32_t *draw;                  // out: [n] = 0..n-1
+    int n;
+};
+
+static __global__ void k_prepare_single(const SingleArgs a)
+{
+    const int g = blockIdx.x, wp = a.wp[g], slots = wp >> 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int e = threadIdx.x; e < a.n * slots; e += blockDim.x) {
+        const int r = e / slots, s_ = e - r * slots;
+        uint4 v = make_uint4(~0u, ~0u, ~0u, ~0u);
+        const int64_t b = a.off[r], eend = a.off[r + 1];
+        for (int64_t k = b; k < eend; ++k) {
+            const uint4 m = ldg128(a.rows[g] + (int64_t)a.allele_idx[k] * wp + 2 * s_);
+            v.x &= m.x; v.y &= m.y; v.z &= m.z; v.w &= m.w;
+        }
+        *reinterpret_cast<uint4 *>(a.masks[g] + (int64_t)r * wp + 2 * s_) = v;
+    }
+    if (g == 0 && threadIdx.x < a.n) a.draw[threadIdx.x] = threadIdx.x;
+    __syncthreads();
+    for (int r = warp; r < a.n; r += nw) {
+        uint32_t c = 0;
+        for (int w = lane; w < wp; w += 32) c += __popcll(a.masks[g][(int64_t)r * wp + w]);
+#pragma unroll
+        for (int m = 16; m; m >>= 1) c += __shfl_xor_sync(0xffffffffu, c, m);
+        if (lane == 0) a.popc[g][r] = c;
+    }
+}
+
 // norm[x] = x / nhap with IEEE division: joint_frequencies_combo(normalize=True) divides every count
 // by N (HOMOGENOUES_MODELS.py:160-161); counts are integers in 0..N, so a table is exact and turns
 // 15 float64 divisions per draw into 15 cached loads.

@@ -392,6 +392,7 @@ int ldpgta_destroy(ldpgta_ctx *c)
     if (c->h_flag) cudaFreeHost(c->h_flag);
     if (c->d_llr_off) cudaFree(c->d_llr_off);
     if (c->h_pin) cudaFreeHost(c->h_pin);
+    if (c->h_io) cudaFreeHost(c->h_io);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_out) cudaStreamDestroy(c->s_out);
@@ -775,6 +776,42 @@ int ldpgta_get_likelihoods(ldpgta_ctx *c, int kind, const int32_t *allele_idx, c
     for (int64_t k = 0; k < nnz; ++k)
         if (allele_idx[k] < 0 || allele_idx[k] >= n_alleles)
             return fail(LDPGTA_E_INVALID, "allele index %d is outside 0..%lld", allele_idx[k], (long long)n_alleles - 1);
+    // The usual call (a handful of alleles, no count table wanted): inputs and result live in one page-locked block the
+    // device reads and writes directly -- one preparation launch, the draw kernel, one synchronisation, no copies.
+    constexpr int IO_IDX = 1024, IO_BYTES = IO_IDX * 4 + (MAXN + 1) * 8 + 32;
+    if (!counts_out && nnz <= IO_IDX) {
+        if (!c->h_io) {
+            LDPGTA_CUDA(cudaHostAlloc((void **)&c->h_io, IO_BYTES, cudaHostAllocMapped));
+            LDPGTA_CUDA(cudaHostGetDevicePointer((void **)&c->d_io, c->h_io, 0));
+        }
+        size_t off = 0;
+        auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 15) & ~(size_t)15; return o; };
+        const size_t o_draw = take((size_t)n * 4);
+        size_t o_rows[MAXG], o_pc[MAXG];
+        for (int g = 0; g < c->G; ++g) { o_rows[g] = take((size_t)n * c->wp[g] * 8); o_pc[g] = take((size_t)n * 4); }
+        if (int rc = ensure_dev(c, off)) return rc;
+        char *base = (char *)c->d_buf;
+        memcpy(c->h_io, allele_idx, (size_t)nnz * 4);
+        memcpy(c->h_io + IO_IDX * 4, read_offsets, (size_t)(n + 1) * 8);
+        SingleArgs sa;
+        memset(&sa, 0, sizeof sa);
+        PanelView pv = make_view(c, proportions);
+        for (int g = 0; g < c->G; ++g) {
+            sa.rows[g] = c->allele_rows[g]; sa.masks[g] = (uint64_t *)(base + o_rows[g]); sa.popc[g] = (uint32_t *)(base + o_pc[g]);
+            sa.wp[g] = c->wp[g];
+            pv.masks[g] = sa.masks[g]; pv.popc[g] = sa.popc[g];
+        }
+        sa.allele_idx = (const int32_t *)c->d_io; sa.off = (const int64_t *)(c->d_io + IO_IDX * 4);
+        sa.draw = (int32_t *)(base + o_draw); sa.n = n;
+        k_prepare_single<<<c->G, 256, 0, c->stream>>>(sa);
+        c->launches++;
+        LDPGTA_CUDA(cudaGetLastError());
+        double *d_res = (double *)(c->d_io + IO_IDX * 4 + (MAXN + 1) * 8);
+        if (int rc = run_uniform(c, kind, n, sa.draw, 1, nullptr, proportions, d_res, nullptr, general_formula != 0, &pv)) return rc;
+        LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
+        memcpy(out, c->h_io + IO_IDX * 4 + (MAXN + 1) * 8, 32);
+        return 0;
+    }
     // scratch layout: [allele_idx][offsets][draw idx 0..n-1][out 4][counts][scratch rows per group]
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 15) & ~(size_t)15; return o; };
