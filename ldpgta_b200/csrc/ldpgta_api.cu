@@ -778,7 +778,7 @@ int ldpgta_get_likelihoods(ldpgta_ctx *c, int kind, const int32_t *allele_idx, c
             return fail(LDPGTA_E_INVALID, "allele index %d is outside 0..%lld", allele_idx[k], (long long)n_alleles - 1);
     // The usual call (a handful of alleles, no count table wanted): inputs and result live in one page-locked block the
     // device reads and writes directly -- one preparation launch, the draw kernel, one synchronisation, no copies.
-    constexpr int IO_IDX = 1024, IO_BYTES = IO_IDX * 4 + (MAXN + 1) * 8 + 32;
+    constexpr int IO_IDX = 1024, IO_OUT = IO_IDX * 4 + (((MAXN + 1) * 8 + 15) & ~15), IO_BYTES = IO_OUT + 32;      // the result is stored as two double2
     if (!counts_out && nnz <= IO_IDX) {
         if (!c->h_io) {
             LDPGTA_CUDA(cudaHostAlloc((void **)&c->h_io, IO_BYTES, cudaHostAllocMapped));
@@ -806,10 +806,10 @@ int ldpgta_get_likelihoods(ldpgta_ctx *c, int kind, const int32_t *allele_idx, c
         k_prepare_single<<<c->G, 256, 0, c->stream>>>(sa);
         c->launches++;
         LDPGTA_CUDA(cudaGetLastError());
-        double *d_res = (double *)(c->d_io + IO_IDX * 4 + (MAXN + 1) * 8);
+        double *d_res = (double *)(c->d_io + IO_OUT);
         if (int rc = run_uniform(c, kind, n, sa.draw, 1, nullptr, proportions, d_res, nullptr, general_formula != 0, &pv)) return rc;
         LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
-        memcpy(out, c->h_io + IO_IDX * 4 + (MAXN + 1) * 8, 32);
+        memcpy(out, c->h_io + IO_OUT, 32);
         return 0;
     }
     // scratch layout: [allele_idx][offsets][draw idx 0..n-1][out 4][counts][scratch rows per group]
