@@ -33,8 +33,9 @@ struct WindowPlan {
     std::vector<SizeClass> classes;
     std::vector<int64_t> h_doff;   // draw offsets per window
     std::vector<int32_t> h_n;      // reads per draw per window
-    double *d_lik = nullptr, *d_llr = nullptr, *d_mv = nullptr, *d_wsum = nullptr, *d_partials = nullptr, *d_stats = nullptr;
+    double *d_lik = nullptr, *d_llr = nullptr, *d_mv = nullptr, *d_wsum = nullptr, *d_split = nullptr, *d_partials = nullptr, *d_stats = nullptr;
     uint64_t *d_seed = nullptr;
+    unsigned int *d_arrived = nullptr;
 };
 
 void free_window_plan(ldpgta_ctx *c)
@@ -73,16 +74,12 @@ int launch_sample(ldpgta_ctx *c, int n, const SampleArgs &a)
 // finished segment statistics, all on c->stream
 static int stats_on_device(ldpgta_ctx *c, const double *d_lik, const int64_t *d_doff, int64_t n_windows, int64_t n_draws,
                            const int64_t *d_segoff, const int32_t *d_segcols, const int32_t *d_segfirst, int n_segments, int ncp,
-                           double *d_llr, double *d_mv, double *d_wsum, double *d_partials, double *d_stats, double *mv_host = nullptr)
+                           double *d_llr, double *d_mv, double *d_wsum, double *d_split, unsigned int *d_arrived, double *d_partials, double *d_stats,
+                           double *mv_host = nullptr)
 {
-    if (n_draws > 0 && d_lik) {                       // d_lik == nullptr: the draw kernels have written the LLRs already
-        const unsigned blocks = (unsigned)std::min<int64_t>((n_draws + 255) / 256, (int64_t)c->sm_count * 8);
-        k_draw_llr<<<blocks, 256, 0, c->stream>>>(d_lik, n_draws, d_llr);
-        c->launches++;
-    }
     if (n_windows > 0) {
         StatsArgs a;
-        a.llr = d_llr; a.doff = d_doff; a.n_windows = n_windows; a.n_draws = n_draws; a.mean_var = d_mv; a.wsum = d_wsum;
+        a.llr = d_llr; a.lik = d_lik; a.doff = d_doff; a.n_windows = n_windows; a.n_draws = n_draws; a.mean_var = d_mv; a.wsum = d_wsum;      // d_lik == nullptr: the draw kernels have written the LLRs already
         const unsigned blocks = (unsigned)std::min<int64_t>((n_windows + 7) / 8, (int64_t)c->sm_count * 32);
         k_window_stats<<<blocks, 256, 0, c->stream>>>(a);
         c->launches++;
@@ -96,8 +93,8 @@ static int stats_on_device(ldpgta_ctx *c, const double *d_lik, const int64_t *d_
     }
     SegmentArgs sa;
     sa.llr = d_llr; sa.doff = d_doff; sa.wsum = d_wsum; sa.mean_var = d_mv; sa.seg_off = d_segoff; sa.seg_cols = d_segcols;
-    sa.seg_first = d_segfirst; sa.n_windows = n_windows; sa.n_draws = n_draws; sa.ncp = ncp; sa.partials = d_partials; sa.stats = d_stats;
-    k_segment_partials<<<dim3((unsigned)n_segments, 5), SEG_ROWS * SEG_COLS, 0, c->stream>>>(sa);
+    sa.seg_first = d_segfirst; sa.n_windows = n_windows; sa.n_draws = n_draws; sa.ncp = ncp; sa.partials = d_partials; sa.stats = d_stats; sa.split = d_split; sa.arrived = d_arrived;
+    k_segment_partials<<<dim3((unsigned)n_segments, 5, SEG_SPLIT), SEG_ROWS * SEG_COLS, 0, c->stream>>>(sa);
     c->launches++;
     LDPGTA_CUDA(cudaGetLastError());
     return 0;
@@ -188,7 +185,7 @@ static int reduce_and_download(ldpgta_ctx *c, WindowPlan *p, double *lik_out, do
     double *d_llr = p->d_llr;
     c->llr_draws = c->llr_windows = -1;
     if (int rc = stats_on_device(c, llr_fused(p) ? nullptr : p->d_lik, p->d_doff, p->n_windows, p->n_draws, p->d_segoff, p->d_segcols, p->d_segfirst,
-                                 p->n_segments, p->ncp, d_llr, p->d_mv, p->d_wsum, p->d_partials, p->d_stats, window_mean_var))
+                                 p->n_segments, p->ncp, d_llr, p->d_mv, p->d_wsum, p->d_split, p->d_arrived, p->d_partials, p->d_stats, window_mean_var))
         return rc;
     const size_t cp_b = (size_t)p->n_segments * 5 * (p->ncp + 3) * 8;
     if (segment_partials) LDPGTA_CUDA(cudaMemcpyAsync(segment_partials, p->d_partials, cp_b, cudaMemcpyDeviceToHost, c->stream));
@@ -352,7 +349,7 @@ int ldpgta_set_windows(ldpgta_ctx *c, const int64_t *window_offsets, const int32
     std::vector<size_t> o_idx;
     for (const SizeClass &k : p->classes) o_idx.push_back(take((size_t)k.n_draws * k.n * 4));
     const size_t o_lik = take((size_t)n_draws * 32), o_llr = take((size_t)n_draws * 40), o_mv = take((size_t)n_windows * 80);
-    const size_t o_wsum = take((size_t)n_windows * 40);
+    const size_t o_wsum = take((size_t)n_windows * 40), o_split = take((size_t)n_segments * 5 * SEG_SPLIT * (ncp + 3) * 8), o_arr = take((size_t)n_segments * 20);
     const size_t o_part = take((size_t)n_segments * 5 * (ncp + 3) * 8), o_stats = take((size_t)n_segments * 120);
     LDPGTA_CUDA(cudaMalloc(&p->d_work, std::max<size_t>(off, 256)));
     base = (char *)p->d_work;
@@ -361,6 +358,9 @@ int ldpgta_set_windows(ldpgta_ctx *c, const int64_t *window_offsets, const int32
     p->d_llr = (double *)(base + o_llr);
     p->d_mv = (double *)(base + o_mv);
     p->d_wsum = (double *)(base + o_wsum);
+    p->d_split = (double *)(base + o_split);
+    p->d_arrived = (unsigned int *)(base + o_arr);
+    LDPGTA_CUDA(cudaMemsetAsync(p->d_arrived, 0, (size_t)n_segments * 20, c->stream));
     p->d_partials = (double *)(base + o_part);
     p->d_stats = (double *)(base + o_stats);
     LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
@@ -482,7 +482,7 @@ int ldpgta_bootstrap_stats_dev(ldpgta_ctx *c, int kind, uint64_t seed, const dou
     }
     if (int rc = evaluate_classes(c, p, kind, proportions, nullptr)) return rc;
     return stats_on_device(c, llr_fused(p) ? nullptr : p->d_lik, p->d_doff, p->n_windows, p->n_draws, p->d_segoff, p->d_segcols, p->d_segfirst, p->n_segments,
-                           p->ncp, p->d_llr, p->d_mv, p->d_wsum, segment_partials_dev ? segment_partials_dev : p->d_partials,
+                           p->ncp, p->d_llr, p->d_mv, p->d_wsum, p->d_split, p->d_arrived, segment_partials_dev ? segment_partials_dev : p->d_partials,
                            segment_partials_dev ? nullptr : p->d_stats);
 }
 
@@ -550,7 +550,7 @@ int ldpgta_window_stats(ldpgta_ctx *c, const double *lik, const int64_t *window_
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t o = off; off += pad256(bytes); return o; };
     const size_t o_lik = take((size_t)n_draws * 32), o_seg = take(16), o_meta = take(8), o_mv = take((size_t)n_windows * 80);
-    const size_t o_wsum = take((size_t)n_windows * 40), o_cp = take((size_t)5 * stride * 8);
+    const size_t o_wsum = take((size_t)n_windows * 40), o_cp = take((size_t)5 * stride * 8), o_split = take((size_t)5 * SEG_SPLIT * stride * 8), o_arr = take(32);
     if (int rc = ensure_dev(c, off)) return rc;
     // the LLRs and the window offsets stay on the device for ldpgta_bin_stats
     c->llr_draws = c->llr_windows = -1;
@@ -566,8 +566,9 @@ int ldpgta_window_stats(ldpgta_ctx *c, const double *lik, const int64_t *window_
     LDPGTA_CUDA(cudaMemcpyAsync(c->d_llr_off, window_offsets, (size_t)(n_windows + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     LDPGTA_CUDA(cudaMemcpyAsync(d_seg, h_seg, 16, cudaMemcpyHostToDevice, c->stream));
     LDPGTA_CUDA(cudaMemcpyAsync(d_meta, h_meta, 8, cudaMemcpyHostToDevice, c->stream));
+    LDPGTA_CUDA(cudaMemsetAsync(base + o_arr, 0, 32, c->stream));
     if (int rc = stats_on_device(c, d_lik, c->d_llr_off, n_windows, n_draws, d_seg, d_meta, d_meta + 1, 1, n_cols, c->d_llr, d_mv,
-                                 d_wsum, d_cp, nullptr))
+                                 d_wsum, (double *)(base + o_split), (unsigned int *)(base + o_arr), d_cp, nullptr))
         return rc;
     if (llr_out && n_draws) LDPGTA_CUDA(cudaMemcpyAsync(llr_out, c->d_llr, (size_t)n_draws * 40, cudaMemcpyDeviceToHost, c->stream));
     if (window_mean_var && n_windows) LDPGTA_CUDA(cudaMemcpyAsync(window_mean_var, d_mv, (size_t)n_windows * 80, cudaMemcpyDeviceToHost, c->stream));

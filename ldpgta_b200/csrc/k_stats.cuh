@@ -286,7 +286,8 @@ static __global__ void k_draw_llr(const double *__restrict__ lik, int64_t n_draw
 }
 
 struct StatsArgs {
-    const double *llr;         // [5][n_draws] per-draw LLRs
+    double *llr;               // [5][n_draws] per-draw LLRs: read, or written here when lik is given
+    const double *lik;         // optional [n_draws][4]: the LLRs are formed here (one pass less than k_draw_llr + reading them back)
     const int64_t *doff;       // [n_windows + 1] draws of window w = [doff[w], doff[w+1])
     int64_t n_windows, n_draws;
     double *mean_var;          // [5][n_windows][2]
@@ -308,8 +309,22 @@ static __global__ void k_window_stats(const StatsArgs a)
             // one draw per lane, plain tree sums (5 roundings)
             const bool live = b + lane < e;
             double x[5];
+            if (a.lik) {
+                double v[4] = {0.0, 0.0, 0.0, 0.0};
+                if (live) {
+                    const double2 u0 = __ldg(reinterpret_cast<const double2 *>(a.lik) + 2 * (b + lane)),
+                                  u1 = __ldg(reinterpret_cast<const double2 *>(a.lik) + 2 * (b + lane) + 1);
+                    v[0] = u0.x; v[1] = u0.y; v[2] = u1.x; v[3] = u1.y;
+                }
 #pragma unroll
-            for (int p = 0; p < 5; ++p) x[p] = live ? __ldg(a.llr + (int64_t)p * a.n_draws + b + lane) : 0.0;
+                for (int p = 0; p < 5; ++p) {
+                    x[p] = live ? llr_of(v[c_pair_num[p]], v[c_pair_den[p]]) : 0.0;
+                    if (live) a.llr[(int64_t)p * a.n_draws + b + lane] = x[p];
+                }
+            } else {
+#pragma unroll
+                for (int p = 0; p < 5; ++p) x[p] = live ? a.llr[(int64_t)p * a.n_draws + b + lane] : 0.0;
+            }
 #pragma unroll
             for (int p = 0; p < 5; ++p) sum[p] = warp_sum_f64(x[p]);
             // the five means are ONE float64 division executed by lanes 0..4 side by side (a division is ~40 instructions
@@ -336,13 +351,21 @@ static __global__ void k_window_stats(const StatsArgs a)
         } else {
 #pragma unroll 1
             for (int p = 0; p < 5; ++p) {
-                const double *x = a.llr + (int64_t)p * a.n_draws;
+                double *x = a.llr + (int64_t)p * a.n_draws;
                 Comp acc = {0.0, 0.0};
-                for (int64_t i = b + lane; i < e; i += 32) acc.add(__ldg(x + i));
+                for (int64_t i = b + lane; i < e; i += 32) {
+                    double v;
+                    if (a.lik) {
+                        const double y = a.lik[4 * i + c_pair_num[p]], z = a.lik[4 * i + c_pair_den[p]];
+                        v = llr_of(y, z);
+                        x[i] = v;                                   // read back below by the lane that wrote it
+                    } else v = x[i];
+                    acc.add(v);
+                }
                 const double s = warp_sum_comp(acc);
                 const double m = s / cnt;
                 Comp q = {0.0, 0.0};
-                for (int64_t i = b + lane; i < e; i += 32) { const double d = __ldg(x + i) - m; q.add(d * d); }
+                for (int64_t i = b + lane; i < e; i += 32) { const double d = x[i] - m; q.add(d * d); }
                 const double ss = warp_sum_comp(q);
                 if (lane == 0) {
                     double *mv = a.mean_var + 2 * ((int64_t)p * a.n_windows + w);
@@ -385,7 +408,7 @@ __device__ __forceinline__ void segment_finish(const double *q, int ncols, int f
 // SEG_ROWS x SEG_COLS threads: row r adds the windows r, r + SEG_ROWS, ... of a column (four loads in flight), the rows are
 // then combined in row order; every sum is Neumaier-compensated and its order is fixed by the launch shape, so results are
 // bit-reproducible.  With stats != nullptr the block also finishes the (segment, pair): see segment_finish.
-constexpr int SEG_ROWS = 32, SEG_COLS = 32;
+constexpr int SEG_ROWS = 32, SEG_COLS = 32, SEG_SPLIT = 4;
 
 struct SegmentArgs {
     const double *llr;         // [5][n_draws]
@@ -398,16 +421,22 @@ struct SegmentArgs {
     int ncp;
     double *partials;          // [n_segments][5][ncp + 3]
     double *stats;             // optional [n_segments][5][3]
+    double *split;             // scratch [n_segments][5][SEG_SPLIT][ncp + 3]: a segment's windows are dealt to SEG_SPLIT blocks
+    unsigned int *arrived;     // [n_segments][5] zero on entry, zero again on exit
 };
 
 static __global__ void __launch_bounds__(SEG_ROWS * SEG_COLS) k_segment_partials(const SegmentArgs a)
 {
     __shared__ double sh_s[SEG_ROWS][SEG_COLS + 1], sh_c[SEG_ROWS][SEG_COLS + 1];
-    const int s = blockIdx.x, p = blockIdx.y, stride = a.ncp + 3;
-    const int64_t lo = a.seg_off[s], hi = a.seg_off[s + 1];
+    __shared__ bool sh_last;
+    const int s = blockIdx.x, p = blockIdx.y, z = blockIdx.z, stride = a.ncp + 3;
+    const int64_t seg_lo = a.seg_off[s], seg_hi = a.seg_off[s + 1];
+    // block z of SEG_SPLIT takes a contiguous share of the segment's windows
+    const int64_t share = (seg_hi - seg_lo + SEG_SPLIT - 1) / SEG_SPLIT;
+    const int64_t lo = min(seg_lo + (int64_t)z * share, seg_hi), hi = min(lo + share, seg_hi);
     const int ncols = a.seg_cols[s];
     const int cx = threadIdx.x % SEG_COLS, row = threadIdx.x / SEG_COLS;
-    double *out = a.partials + ((int64_t)s * 5 + p) * stride;
+    double *mine = a.split + (((int64_t)s * 5 + p) * SEG_SPLIT + z) * stride;
     const double *x = a.llr + (int64_t)p * a.n_draws;
     // head: totals over the windows (thread t takes windows t, t + 1024, ...)
     {
@@ -430,9 +459,9 @@ static __global__ void __launch_bounds__(SEG_ROWS * SEG_COLS) k_segment_partials
             Comp t = {0.0, 0.0};
             double n = 0.0;
             for (int r = 0; r < SEG_ROWS; ++r) { t.add(sh_s[r][0]); t.c += sh_c[r][0]; n += sh_s[r][1]; }
-            out[0] = t.value();
-            out[1] = (double)(hi - lo);
-            out[2] = n;
+            mine[0] = t.value();
+            mine[1] = (double)(hi - lo);
+            mine[2] = n;
         }
         __syncthreads();
     }
@@ -455,10 +484,29 @@ static __global__ void __launch_bounds__(SEG_ROWS * SEG_COLS) k_segment_partials
             Comp t = {0.0, 0.0};
 #pragma unroll
             for (int r = 0; r < SEG_ROWS; ++r) { t.add(sh_s[r][cx]); t.c += sh_c[r][cx]; }
-            out[3 + col] = t.value();
+            mine[3 + col] = t.value();
         }
         __syncthreads();
     }
+    // the last of the segment's SEG_SPLIT blocks adds the shares in share order (whichever block that is, the sum is the same)
+    __threadfence();
+    if (threadIdx.x == 0) {
+        const unsigned int seen = atomicAdd(a.arrived + s * 5 + p, 1u);
+        sh_last = seen == SEG_SPLIT - 1;
+        if (sh_last) a.arrived[s * 5 + p] = 0u;                       // ready for the next launch
+    }
+    __syncthreads();
+    if (!sh_last) return;
+    __threadfence();
+    double *out = a.partials + ((int64_t)s * 5 + p) * stride;
+    const double *all = a.split + ((int64_t)s * 5 + p) * SEG_SPLIT * stride;
+    for (int col = threadIdx.x; col < stride; col += blockDim.x) {
+        Comp t = {0.0, 0.0};
+#pragma unroll
+        for (int k = 0; k < SEG_SPLIT; ++k) t.add(__ldcg(all + (int64_t)k * stride + col));
+        out[col] = t.value();
+    }
+    __syncthreads();
     if (a.stats && threadIdx.x < 32) {
         __threadfence_block();
         segment_finish(out, ncols, a.seg_first[s], a.stats + 3 * ((int64_t)s * 5 + p), threadIdx.x);
