@@ -701,7 +701,7 @@ def strong_scaling_leg(L, torch, dist, device, local, rank, world, args, kind, g
     partials = torch.zeros((n_seg, 5, ncp + 3), dtype=torch.float64, device=device)
     stats = torch.zeros((n_seg, 5, 3), dtype=torch.float64, device=device)
     steps, warm = args.steps, args.warmup
-    sharding.connect_peers(leg.eng, partials.numel())
+    peer_ok = sharding.connect_peers(leg.eng, partials.numel())      # False: no peer access / IPC on this box, all_reduce only
 
     def step(how, ev=None):
         leg.step(partials.data_ptr())
@@ -717,7 +717,7 @@ def strong_scaling_leg(L, torch, dist, device, local, rank, world, args, kind, g
 
     res = {}
     with torch.cuda.stream(leg.stream):
-        for how in ('peer', 'nccl'):
+        for how in (('peer', 'nccl') if peer_ok else ('nccl',)):
             for _ in range(warm):
                 step(how)
             leg.eng.synchronize()
@@ -732,7 +732,7 @@ def strong_scaling_leg(L, torch, dist, device, local, rank, world, args, kind, g
             barrier()
             res[how] = (max_over_ranks(e0.elapsed_time(e1)), max_over_ranks(float(np.median([a.elapsed_time(b) for a, b in evs]))),
                         stats.cpu().numpy().copy())
-    total_ms, ar_ms, st = res['peer']
+    total_ms, ar_ms, st = res['peer' if peer_ok else 'nccl']
     finite = bool(np.isfinite(st).all())
     windows_here = hi - lo
     leg.close()
@@ -741,7 +741,8 @@ def strong_scaling_leg(L, torch, dist, device, local, rank, world, args, kind, g
             'scaling': 'strong', 'value': len(reads) * subs * steps / (total_ms * 1e-3), 'unit': 'window-likelihoods/s',
             'ms_per_step': total_ms / steps, 'windows_rank0': int(windows_here), 'allreduce_bytes': int(partials.numel() * 8),
             'allreduce_ms_median': ar_ms, 'allreduce_share_of_step': ar_ms / (total_ms / steps),
-            'collective': 'ldpgta_allreduce_chrom_dev: one kernel over NVLink peer memory (publish, flag peers, poll locally, peer loads, rank-order sum)',
+            'collective': 'ldpgta_allreduce_chrom_dev: one kernel over NVLink peer memory (publish, flag peers, poll locally, peer loads, rank-order sum)' if peer_ok
+                          else 'torch.distributed all_reduce (NCCL): peer memory could not be mapped on this box',
             'nccl_comparison': {'ms_per_step': res['nccl'][0] / steps, 'allreduce_ms_median': res['nccl'][1],
                                 'collective': 'torch.distributed all_reduce (NCCL) on the same device-resident partials'},
             'statistics_finite': finite}

@@ -408,7 +408,10 @@ __device__ __forceinline__ void segment_finish(const double *q, int ncols, int f
 // SEG_ROWS x SEG_COLS threads: row r adds the windows r, r + SEG_ROWS, ... of a column (four loads in flight), the rows are
 // then combined in row order; every sum is Neumaier-compensated and its order is fixed by the launch shape, so results are
 // bit-reproducible.  With stats != nullptr the block also finishes the (segment, pair): see segment_finish.
-constexpr int SEG_ROWS = 32, SEG_COLS = 32, SEG_SPLIT = 4;
+#ifndef LDPGTA_SEG_SPLIT
+#define LDPGTA_SEG_SPLIT 1     // blocks per (segment, pair); measured on configs[1]: 1 -> 21 us, 4 -> 30 us (the launch is latency-bound)
+#endif
+constexpr int SEG_ROWS = 32, SEG_COLS = 32, SEG_SPLIT = LDPGTA_SEG_SPLIT;
 
 struct SegmentArgs {
     const double *llr;         // [5][n_draws]

@@ -85,11 +85,25 @@ def connect_peers(engine, n_doubles, group=None):
     """ Sets up the peer-memory exchange of ldpgta_allreduce_chrom_dev between the ranks of a torch.distributed group
     (one process per GPU): every rank allocates its buffer, the handles travel by all_gather_object (plumbing only), and
     each rank maps the peers' buffers.  Afterwards engine.allreduce_chrom_dev(ptr, n) sums device buffers across the
-    ranks in one kernel over NVLink, with no collective library in the data path. """
+    ranks in one kernel over NVLink, with no collective library in the data path.
+    Returns True when EVERY rank is connected.  A rank that fails (no peer access between two GPUs, IPC disabled in the
+    container) still takes part in the collectives below, so nobody hangs; the callers then keep using all_reduce. """
+    import torch
     import torch.distributed as dist
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    mine = engine.comm_create(rank, world, n_doubles)
+    try:
+        mine = engine.comm_create(rank, world, n_doubles)
+    except Exception:
+        mine = None
     handles = [None] * world
     dist.all_gather_object(handles, mine, group=group)
-    engine.comm_connect(handles)
-    dist.barrier(group=group)                    # every rank has mapped every buffer before the first exchange
+    ok = all(h is not None for h in handles)
+    if ok:
+        try:
+            engine.comm_connect(handles)
+        except Exception:
+            ok = False
+    dev = 'cuda' if dist.get_backend(group) == 'nccl' else 'cpu'
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)      # also: every rank has mapped every buffer before the first exchange
+    return bool(flag.item())

@@ -72,7 +72,7 @@ def _worker(rank, world, port, q):
                     dist.all_reduce(t)
                 else:
                     if 'connected' not in out:
-                        sharding.connect_peers(eng, t.numel())
+                        assert sharding.connect_peers(eng, t.numel())
                         out['connected'] = True
                     for _ in range(3):                                   # repeated exchanges reuse the two buffers
                         t.copy_(torch.from_numpy(mine))
