@@ -26,6 +26,7 @@ struct SizeClass {
 struct WindowPlan {
     int64_t n_windows = 0, n_draws = 0, n_wreads = 0, nnz = 0;
     int n_segments = 0, ncp = 0;
+    int64_t max_draws = 0;         // most draws of a window
     bool has_windows = false;
     void *d_static = nullptr, *d_work = nullptr;
     int64_t *d_woff = nullptr, *d_doff = nullptr, *d_segoff = nullptr;
@@ -75,8 +76,16 @@ int launch_sample(ldpgta_ctx *c, int n, const SampleArgs &a)
 static int stats_on_device(ldpgta_ctx *c, const double *d_lik, const int64_t *d_doff, int64_t n_windows, int64_t n_draws,
                            const int64_t *d_segoff, const int32_t *d_segcols, const int32_t *d_segfirst, int n_segments, int ncp,
                            double *d_llr, double *d_mv, double *d_wsum, double *d_split, unsigned int *d_arrived, double *d_partials, double *d_stats,
-                           double *mv_host = nullptr)
+                           double *mv_host = nullptr, int64_t max_draws_per_window = 0)
 {
+    // LLRs: windows of at most 32 draws form them inside k_window_stats (one draw per lane); longer windows would make
+    // that one warp walk the window five times, so the LLRs come from the fully parallel k_draw_llr first
+    if (d_lik && n_draws > 0 && max_draws_per_window > 32) {
+        const unsigned blocks = (unsigned)std::min<int64_t>((n_draws + 255) / 256, (int64_t)c->sm_count * 8);
+        k_draw_llr<<<blocks, 256, 0, c->stream>>>(d_lik, n_draws, d_llr);
+        c->launches++;
+        d_lik = nullptr;
+    }
     if (n_windows > 0) {
         StatsArgs a;
         a.llr = d_llr; a.lik = d_lik; a.doff = d_doff; a.n_windows = n_windows; a.n_draws = n_draws; a.mean_var = d_mv; a.wsum = d_wsum;      // d_lik == nullptr: the draw kernels have written the LLRs already
@@ -185,7 +194,7 @@ static int reduce_and_download(ldpgta_ctx *c, WindowPlan *p, double *lik_out, do
     double *d_llr = p->d_llr;
     c->llr_draws = c->llr_windows = -1;
     if (int rc = stats_on_device(c, llr_fused(p) ? nullptr : p->d_lik, p->d_doff, p->n_windows, p->n_draws, p->d_segoff, p->d_segcols, p->d_segfirst,
-                                 p->n_segments, p->ncp, d_llr, p->d_mv, p->d_wsum, p->d_split, p->d_arrived, p->d_partials, p->d_stats, window_mean_var))
+                                 p->n_segments, p->ncp, d_llr, p->d_mv, p->d_wsum, p->d_split, p->d_arrived, p->d_partials, p->d_stats, window_mean_var, p->max_draws))
         return rc;
     const size_t cp_b = (size_t)p->n_segments * 5 * (p->ncp + 3) * 8;
     if (segment_partials) LDPGTA_CUDA(cudaMemcpyAsync(segment_partials, p->d_partials, cp_b, cudaMemcpyDeviceToHost, c->stream));
@@ -260,7 +269,7 @@ int ldpgta_set_windows(ldpgta_ctx *c, const int64_t *window_offsets, const int32
     WindowPlan *p = new WindowPlan();
     c->plan = p;
     p->n_windows = n_windows; p->n_draws = n_draws; p->n_wreads = window_reads ? n_wreads : 0; p->nnz = nnz;
-    p->n_segments = n_segments; p->ncp = ncp;
+    p->n_segments = n_segments; p->ncp = ncp; p->max_draws = max_draws;
     p->has_windows = window_offsets != nullptr;
     p->h_doff.assign(draw_offsets, draw_offsets + n_windows + 1);
     p->h_n.assign(reads_per_draw, reads_per_draw + n_windows);
@@ -483,7 +492,7 @@ int ldpgta_bootstrap_stats_dev(ldpgta_ctx *c, int kind, uint64_t seed, const dou
     if (int rc = evaluate_classes(c, p, kind, proportions, nullptr)) return rc;
     return stats_on_device(c, llr_fused(p) ? nullptr : p->d_lik, p->d_doff, p->n_windows, p->n_draws, p->d_segoff, p->d_segcols, p->d_segfirst, p->n_segments,
                            p->ncp, p->d_llr, p->d_mv, p->d_wsum, p->d_split, p->d_arrived, segment_partials_dev ? segment_partials_dev : p->d_partials,
-                           segment_partials_dev ? nullptr : p->d_stats);
+                           segment_partials_dev ? nullptr : p->d_stats, nullptr, p->max_draws);
 }
 
 int ldpgta_finish_segments_dev(ldpgta_ctx *c, const double *segment_partials_dev, double *segment_stats_dev)
@@ -567,8 +576,10 @@ int ldpgta_window_stats(ldpgta_ctx *c, const double *lik, const int64_t *window_
     LDPGTA_CUDA(cudaMemcpyAsync(d_seg, h_seg, 16, cudaMemcpyHostToDevice, c->stream));
     LDPGTA_CUDA(cudaMemcpyAsync(d_meta, h_meta, 8, cudaMemcpyHostToDevice, c->stream));
     LDPGTA_CUDA(cudaMemsetAsync(base + o_arr, 0, 32, c->stream));
+    int64_t most = 0;
+    for (int64_t w = 0; w < n_windows; ++w) most = std::max(most, window_offsets[w + 1] - window_offsets[w]);
     if (int rc = stats_on_device(c, d_lik, c->d_llr_off, n_windows, n_draws, d_seg, d_meta, d_meta + 1, 1, n_cols, c->d_llr, d_mv,
-                                 d_wsum, (double *)(base + o_split), (unsigned int *)(base + o_arr), d_cp, nullptr))
+                                 d_wsum, (double *)(base + o_split), (unsigned int *)(base + o_arr), d_cp, nullptr, nullptr, most))
         return rc;
     if (llr_out && n_draws) LDPGTA_CUDA(cudaMemcpyAsync(llr_out, c->d_llr, (size_t)n_draws * 40, cudaMemcpyDeviceToHost, c->stream));
     if (window_mean_var && n_windows) LDPGTA_CUDA(cudaMemcpyAsync(window_mean_var, d_mv, (size_t)n_windows * 80, cudaMemcpyDeviceToHost, c->stream));

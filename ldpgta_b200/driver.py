@@ -309,10 +309,12 @@ def plan_draw_indices(genomic_windows, min_reads, max_reads, subsamples, replay=
     return plan
 
 
-def evaluate_draw_indices(examine, reads_dict, genomic_windows, plan):
-    """ evaluate_draws for index plans: one read-mask row per read of the evaluated windows, one device batch. """
+def evaluate_draw_indices(examine, reads_dict, genomic_windows, plan, with_stats=False):
+    """ evaluate_draws for index plans: one read-mask row per read of the evaluated windows, one device batch.
+    with_stats=True returns (likelihoods, window_mean_var[5][n_windows][2], chromosome[5][3]) from ONE device-resident pass
+    (ldpgta_set_windows + ldpgta_replay_stats): the likelihoods feed the LLR reductions without leaving HBM. """
     if not plan:
-        return {}
+        return ({}, None, None) if with_stats else {}
     index = examine._allele_index
     read_row = {}
     allele_idx, read_offsets = [], [0]
@@ -340,18 +342,26 @@ def evaluate_draw_indices(examine, reads_dict, genomic_windows, plan):
     np.cumsum(widths, out=offsets[1:])
     eng = examine._engine
     eng.build_read_masks(allele_idx, read_offsets)
-    lik = eng.likelihoods_batch(examine.kind, flat, offsets, proportions=examine._proportions())
+    mean_var = chrom = None
+    if with_stats:
+        draw_offsets = np.zeros(len(counts) + 1, dtype=np.int64)
+        np.cumsum(counts, out=draw_offsets[1:])
+        eng.set_windows(None, None, draw_offsets, np.array([c.shape[1] for c in chunks], dtype=np.int32))     # replay-only plan
+        res = eng.replay_stats(examine.kind, flat, proportions=examine._proportions(), want=('lik', 'mean_var', 'stats'))
+        lik, mean_var, chrom = res['lik'], res['mean_var'], res['stats'][0]
+    else:
+        lik = eng.likelihoods_batch(examine.kind, flat, offsets, proportions=examine._proportions())
     T = examine.tuple_type
     out, k = {}, 0
     rows = lik.tolist()
     for window, c in zip(plan, counts.tolist()):
         out[window] = tuple(T(*rows[k + j]) for j in range(c))
         k += c
-    return out
+    return (out, mean_var, chrom) if with_stats else out
 
 
 def bootstrap(obs_tab, leg_tab, hap_tab, number_of_haplotypes, ancestral_makeup, models_dict, window_size, subsamples,
-              offset, min_reads, max_reads, min_score, min_HF, replay=None, device=0, panel=None, fast_rng=None):
+              offset, min_reads, max_reads, min_score, min_HF, replay=None, device=0, panel=None, fast_rng=None, _stats_out=None):
     """ ANEUPLOIDY_TEST.bootstrap (:250-287): (likelihoods, genomic_windows, fraction_of_matches).
     `panel`: an engine.ResidentPanel of this chromosome shared by many samples (for a dict makeup: groups in the makeup's order);
     `fast_rng`: numpy Generator for vectorised draws (throughput runs; not the reference's random stream). """
@@ -360,7 +370,12 @@ def bootstrap(obs_tab, leg_tab, hap_tab, number_of_haplotypes, ancestral_makeup,
         obs = supporting_dictionaries(obs_tab, leg_tab, hap_tab, number_of_haplotypes, ancestral_makeup, min_HF, examine=examine)
         genomic_windows = build_gw_dict(obs, window_size, offset, min_reads, max_reads, min_score)
         plan = plan_draw_indices(genomic_windows, min_reads, max_reads, subsamples, replay=replay, fast_rng=fast_rng)
-        likelihoods = evaluate_draw_indices(examine, obs.reads, genomic_windows, plan)
+        if _stats_out is not None and plan and min(len(v) for v in plan.values()) >= 2:
+            # aneuploidy_test: statistics() from the same device pass (filled into _stats_out for the caller)
+            likelihoods, mean_var, chrom = evaluate_draw_indices(examine, obs.reads, genomic_windows, plan, with_stats=True)
+            _stats_out.update(device_statistics(likelihoods, genomic_windows, mean_var, chrom))
+        else:
+            likelihoods = evaluate_draw_indices(examine, obs.reads, genomic_windows, plan)
         return likelihoods, genomic_windows, examine.fraction_of_matches
     finally:
         examine.close()
@@ -382,6 +397,20 @@ def chromosome_arrays(likelihoods):
     off[1:] = np.cumsum(counts)
     lik = np.array([tuple(l) for v in likelihoods.values() for l in v], dtype=np.float64).reshape(-1, 4)
     return lik, off, min(counts), counts[0]
+
+
+def device_statistics(likelihoods, genomic_windows, mean_var, chrom):
+    """ The dictionary of ANEUPLOIDY_TEST.statistics (:289-325) from reductions the device has already made:
+    mean_var[5][n_windows][2] in the order of `likelihoods`, chrom[5][3]. """
+    window_size_mean, window_size_std = mean_and_std((j - i + 1 for (i, j) in likelihoods))
+    reads_mean, reads_std = mean_and_std((len(read_IDs) for window, read_IDs in genomic_windows.items() if window in likelihoods))
+    mv = np.asarray(mean_var).tolist()
+    per_window = {pair: {w: tuple(mv[p][k]) for k, w in enumerate(likelihoods)} for p, pair in enumerate(LLR_PAIRS)}
+    per_chrom = {pair: {'mean_of_mean': float(chrom[p][0]), 'std_of_mean': float(chrom[p][1]),
+                        'fraction_of_negative_LLRs': float(chrom[p][2])} for p, pair in enumerate(LLR_PAIRS)}
+    return {'num_of_windows': len(likelihoods), 'reads_mean': reads_mean, 'reads_std': reads_std,
+            'window_size_mean': window_size_mean, 'window_size_std': window_size_std,
+            'LLRs_per_genomic_window': per_window, 'LLRs_per_chromosome': per_chrom}
 
 
 def statistics(likelihoods, genomic_windows, device=0):
@@ -524,11 +553,13 @@ def aneuploidy_test(obs_filename, leg_filename, hap_filename, ancestral_makeup, 
             max_reads, min_score, min_HF, device=device, panel=kwargs.get('panel', None),
             rng=np.random.default_rng(kwargs.get('seed', None)))
     else:
+        stats = {}
         likelihoods, genomic_windows, matched_alleles = bootstrap(obs_tab, leg_tab, hap_tab, number_of_haplotypes, ancestral_makeup,
                                                                   models_dict, window_size, subsamples, offset, min_reads,
                                                                   max_reads, min_score, min_HF, device=device,
-                                                                  panel=kwargs.get('panel', None), fast_rng=fast_rng)
-        stats = statistics(likelihoods, genomic_windows, device=device)
+                                                                  panel=kwargs.get('panel', None), fast_rng=fast_rng, _stats_out=stats)
+        if not stats:                                   # nothing evaluated, or a window with one draw (statistics() raises there)
+            stats = statistics(likelihoods, genomic_windows, device=device)
     some_statistics = {'matched_alleles': matched_alleles, 'runtime': time.time() - time0}
     info.update({'ancestral_makeup': ancestral_makeup, 'window_size': window_size, 'subsamples': subsamples, 'offset': offset,
                  'min_reads': min_reads, 'max_reads': max_reads, 'min_score': min_score, 'min_HF': min_HF,
