@@ -70,17 +70,27 @@ static __global__ void __launch_bounds__(1024) k_allreduce_peer(const CommView v
         __threadfence_system();
     }
     __syncthreads();
-    // peer loads (NVLink), all ranks' values of an element in flight together, added in rank order
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-        double x[LDPGTA_MAX_PEERS];
+    // peer loads (NVLink): the exchange is latency, so a thread puts the values of up to four of its elements from every
+    // rank in flight together (4 x world loads) before adding them in rank order
+    constexpr int EPT = 4;
+    for (int64_t i0 = threadIdx.x; i0 < n; i0 += (int64_t)EPT * blockDim.x) {
+        double x[EPT][LDPGTA_MAX_PEERS];
 #pragma unroll
-        for (int r = 0; r < LDPGTA_MAX_PEERS; ++r)
-            if (r < v.world) x[r] = __ldcv(v.data[r] + (int64_t)par * v.max_doubles + i);
-        double s = 0.0;
+        for (int k = 0; k < EPT; ++k) {
+            const int64_t i = i0 + (int64_t)k * blockDim.x;
 #pragma unroll
-        for (int r = 0; r < LDPGTA_MAX_PEERS; ++r)
-            if (r < v.world) s += x[r];
-        partials[i] = s;
+            for (int r = 0; r < LDPGTA_MAX_PEERS; ++r)
+                if (r < v.world && i < n) x[k][r] = __ldcv(v.data[r] + (int64_t)par * v.max_doubles + i);
+        }
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+            const int64_t i = i0 + (int64_t)k * blockDim.x;
+            double s = 0.0;
+#pragma unroll
+            for (int r = 0; r < LDPGTA_MAX_PEERS; ++r)
+                if (r < v.world) s += x[k][r];
+            if (i < n) partials[i] = s;
+        }
     }
 }
 

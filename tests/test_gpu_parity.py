@@ -266,7 +266,7 @@ def test_large_draws_vs_reference_build(golden_inputs):
                 distant.close()
     finally:
         homog.close(); recent.close()
-    assert set(range(10, 17)) <= set(g['records'])
+    assert set(range(10, 19)) <= set(g['records'])
 
 
 def test_chr21_full_panel_vs_reference_bootstrap():

@@ -84,7 +84,7 @@ def test_large_draws_vs_reference_build(golden_inputs):
     from conftest import load_golden
     g = load_golden('large_draws.p.bz2')
     nh = golden_inputs['number_of_haplotypes']
-    assert set(range(10, 17)) <= set(g['records'])
+    assert set(range(10, 19)) <= set(g['records'])
     worst = 0.0
     for n, rec in sorted(g['records'].items()):
         rows = large_draw_rows(rec, golden_inputs)
