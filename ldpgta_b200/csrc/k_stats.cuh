@@ -474,10 +474,12 @@ static __global__ void __launch_bounds__(SEG_ROWS * SEG_COLS) k_segment_partials
         Comp acc = {0.0, 0.0};
         if (col < ncols) {
             int64_t w = lo + row;
-            for (; w + 3 * SEG_ROWS < hi; w += 4 * SEG_ROWS) {
-                const double v0 = x[a.doff[w] + col], v1 = x[a.doff[w + SEG_ROWS] + col], v2 = x[a.doff[w + 2 * SEG_ROWS] + col],
-                             v3 = x[a.doff[w + 3 * SEG_ROWS] + col];
-                acc.add(v0); acc.add(v1); acc.add(v2); acc.add(v3);
+            for (; w + 7 * SEG_ROWS < hi; w += 8 * SEG_ROWS) {                       // eight loads in flight
+                double v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = x[a.doff[w + k * SEG_ROWS] + col];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc.add(v[k]);
             }
             for (; w < hi; w += SEG_ROWS) acc.add(x[a.doff[w] + col]);
         }
