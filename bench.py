@@ -645,7 +645,10 @@ def main():
         leg.close()
         del leg, eng
         torch.cuda.empty_cache()
-        secondary = secondary_legs(L, torch, device, local, args, hbm_peak, int_peak)
+        try:
+            secondary = secondary_legs(L, torch, device, local, args, hbm_peak, int_peak)
+        except Exception as e:                                  # the headline line must survive a failing side leg
+            secondary = [{'error': '%s: %s' % (type(e).__name__, e)}]
 
     line = {
         'metric': 'bootstrapped window-likelihoods/sec', 'value': value, 'unit': 'window-likelihoods/s',

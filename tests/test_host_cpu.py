@@ -17,12 +17,21 @@ import ldpgta_b200 as L
 from ldpgta_b200 import _native, driver
 
 
+import shutil
+
+# libldpgta.so is a build artefact (git-ignored): on a checkout that has not been built and has no nvcc to build it, the
+# tests that need the library skip instead of erroring; with nvcc present conftest's session fixture has built it already
+needs_library = pytest.mark.skipif(not os.path.exists(_native.LIB_PATH), reason='libldpgta.so has not been built (python __graft_entry__.py, needs nvcc)')
+needs_cuobjdump = pytest.mark.skipif(shutil.which('cuobjdump') is None, reason='cuobjdump (CUDA toolkit) is not installed')
+
+
 def header_functions():
     text = open(os.path.join(ROOT, 'include', 'ldpgta.h')).read()
     text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
     return sorted(set(re.findall(r'\b(ldpgta_[a-z_0-9]+)\s*\(', text)))
 
 
+@needs_library
 def test_library_exports_every_declared_symbol():
     lib = L.load()
     declared = header_functions()
@@ -37,11 +46,14 @@ def test_library_exports_every_declared_symbol():
     assert lib.ldpgta_version() >= 100
 
 
+@needs_library
+@needs_cuobjdump
 def test_library_is_sm100a_native():
     out = subprocess.run(['cuobjdump', '-lelf', L.LIB_PATH], capture_output=True, text=True).stdout
     assert 'sm_100a' in out
 
 
+@needs_library
 def test_no_gpu_means_loud_failure():
     lib = L.load()
     if lib.ldpgta_device_count() > 0:
