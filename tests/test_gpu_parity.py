@@ -622,9 +622,17 @@ print(json.dumps({'windows': len(lik), 'keys': sorted(info), 'stat_keys': sorted
     # same seed and hash seed as the golden run: the draws and therefore the likelihoods are the reference's
     worst = max(max_rel(a, b) for w in lik for a, b in zip(lik[w], out['likelihoods'][w]))
     assert worst < LIK_TOL
-    ref = out['statistics']['LLRs_per_chromosome'][('BPH', 'SPH')]
-    mine = info['statistics']['LLRs_per_chromosome'][('BPH', 'SPH')]
-    assert abs(mine['mean_of_mean'] - ref['mean_of_mean']) < STAT_TOL and abs(mine['std_of_mean'] - ref['std_of_mean']) < STAT_TOL
+    # statistics() comes from the same device pass as the likelihoods: every pair, per chromosome and per window, against
+    # the reference's recorded statistics
+    for pair in L.LLR_PAIRS:
+        ref, mine = out['statistics']['LLRs_per_chromosome'][pair], info['statistics']['LLRs_per_chromosome'][pair]
+        for key in ('mean_of_mean', 'std_of_mean', 'fraction_of_negative_LLRs'):
+            assert abs(mine[key] - ref[key]) <= STAT_TOL * max(1e-3, abs(ref[key])), (pair, key)
+        for w, (m, v) in out['statistics']['LLRs_per_genomic_window'][pair].items():
+            gm, gv = info['statistics']['LLRs_per_genomic_window'][pair][w]
+            assert abs(gm - m) <= STAT_TOL * max(1e-3, abs(m)) and abs(gv - v) <= STAT_TOL * max(1e-3, abs(v))
+    for key in ('num_of_windows', 'reads_mean', 'reads_std', 'window_size_mean', 'window_size_std'):
+        assert info['statistics'][key] == out['statistics'][key]
 
 
 def test_resident_panel_gather_equals_host_packing(golden_testmodule, golden_inputs):
