@@ -140,7 +140,7 @@ int launch_general(ldpgta_ctx *c, GeneralArgs a)
         if (int rc = ensure_hi_terms(c, h)) return rc;
         a.terms = reinterpret_cast<const u64 *>(c->hi_terms[h]);
         a.n_terms = c->n_hi_terms[h];
-        for (int g = 0; g < c->G; ++g) a.wide |= c->nhap[g] > 16383u;
+        for (int g = 0; g < c->G; ++g) a.wide |= c->nhap[g] > (a.kind == LDPGTA_RECENT_ADMIXTURE ? 11585u : 16383u);   // 32-bit convolution sums: 16 (recent: 32) products of two counts
     }
 #define LDPGTA_CASE(TH_, TL_)                                                         \
     if (p.th == TH_ && p.tl == TL_)                                                   \

@@ -52,7 +52,7 @@ int launch_lanes(ldpgta_ctx *c, GeneralArgs a)
     a.terms = reinterpret_cast<const u64 *>(c->hi_terms[h]);
     a.n_terms = c->n_hi_terms[h];
     a.wide = 0;
-    for (int g = 0; g < c->G; ++g) a.wide |= c->nhap[g] > 16383u;
+    for (int g = 0; g < c->G; ++g) a.wide |= c->nhap[g] > (a.kind == LDPGTA_RECENT_ADMIXTURE ? 11585u : 16383u);   // 32-bit convolution sums: 16 (recent: 32) products of two counts
     a.kl = a.kh = a.wc = 0; a.etab = 0; a.etab_scratch = nullptr; a.etab_stride = 0;
     a.table_scratch = nullptr; a.table_stride = 0;
     static const int alt = [] { const char *e = getenv("LDPGTA_LANES_ALT"); return e ? atoi(e) : 0; }();     // tuning: the other low/high split (measured slower: tools/sweep_sizes.sh)

@@ -74,6 +74,20 @@ __device__ __forceinline__ void conv16(const uint32_t *Y, const uint32_t *Z, ACC
     }
 }
 
+// out[s] += (Y*Z)[s]
+template <typename ACC>
+__device__ __forceinline__ void conv16_add(const uint32_t *Y, const uint32_t *Z, ACC *out)
+{
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+        ACC acc = out[s];
+#pragma unroll
+        for (int b = 0; b < 16; ++b)
+            if ((b & s) == b) acc += (ACC)Y[b] * (ACC)Z[s ^ b];
+        out[s] = acc;
+    }
+}
+
 template <typename ACC>
 __device__ __forceinline__ u64 dot16(const uint32_t *X, const ACC *conv)
 {
@@ -159,14 +173,17 @@ __device__ __forceinline__ void poly_recent_impl(const CT *F, const CT *G, int n
         ACC c[16];
         u64 s_ffg, s_ggf;
         load_row16<CT, SPACE>(F, top_row + ra, Xf); load_row16<CT, SPACE>(G, top_row + ra, Xg);
+        // the two mixed convolutions Yf*Zg and Yg*Zf enter both sums with the same partner (Xf for ffg, Xg for ggf), so they
+        // are accumulated into one array and dotted once: 4 convolutions + 4 dot products per colouring instead of 4 + 6
+        // (two more row loads; 32 * max(F) * max(G) stays below 2^32 whenever ACC is 32-bit: groups of at most 11585)
         load_row16<CT, SPACE>(F, rb, Y); load_row16<CT, SPACE>(F, rc, Z);
         conv16<ACC>(Y, Z, c); s_ffg = dot16<ACC>(Xg, c);                                          // Yf * Zf
         load_row16<CT, SPACE>(G, rc, Z);
-        conv16<ACC>(Y, Z, c); s_ffg += dot16<ACC>(Xf, c); s_ggf = dot16<ACC>(Xg, c);              // Yf * Zg
-        load_row16<CT, SPACE>(G, rb, Y);
+        conv16<ACC>(Y, Z, c);                                                                     // Yf * Zg
+        load_row16<CT, SPACE>(G, rb, Y); load_row16<CT, SPACE>(F, rc, Z);
+        conv16_add<ACC>(Y, Z, c); s_ffg += dot16<ACC>(Xf, c); s_ggf = dot16<ACC>(Xg, c);          // + Yg * Zf
+        load_row16<CT, SPACE>(G, rc, Z);
         conv16<ACC>(Y, Z, c); s_ggf += dot16<ACC>(Xf, c);                                         // Yg * Zg
-        load_row16<CT, SPACE>(F, rc, Z);
-        conv16<ACC>(Y, Z, c); s_ffg += dot16<ACC>(Xf, c); s_ggf += dot16<ACC>(Xg, c);             // Yg * Zf
         if (special) { s_ffg >>= 1; s_ggf >>= 1; }
         ffg += s_ffg;
         ggf += s_ggf;

@@ -209,6 +209,27 @@ def test_recent_and_distant_admixture(sizes):
                 assert np.array_equal(cnt[g], C.joint_counts(rows[g][idx[:n]]))
 
 
+@pytest.mark.parametrize('sizes', [(11585, 11585), (12000, 9000), (16383, 16383), (16400, 300)])
+def test_recent_admixture_accumulator_width(sizes):
+    """ Groups around the sizes at which the polynomial's 32-bit convolution sums would overflow (recent admixture adds two
+    convolutions of 16 products: 32 * N0 * N1 < 2^32 holds up to 11585 haplotypes per group), with dense rows so that the
+    counts really are that large. """
+    rng = np.random.default_rng(sizes[0])
+    rows = [ld_rows(rng, 48, s, founders=2, density=0.95) | np.uint64(0x7fffffffffffffff) for s in sizes]
+    for r, s in zip(rows, sizes):
+        tail = s - 64 * ((s + 63) // 64 - 1)
+        if tail < 64:
+            r[:, -1] &= np.uint64((1 << tail) - 1)
+    with L.Engine(list(sizes)) as eng:
+        for g in range(2):
+            eng.upload_read_masks(g, rows[g])
+        for n in (5, 6, 9, 12, 13):
+            idx, off = uniform_draws(rng, 48, n, 4 if n < 12 else 2)
+            got = eng.likelihoods_batch(L.RECENT_ADMIXTURE, idx, off)
+            want = C.batch(_common_width(rows), list(sizes), idx, off, 1)
+            assert max_rel(got, want) < LIK_TOL, (sizes, n, max_rel(got, want))
+
+
 def _common_width(rows):
     W = max(r.shape[1] for r in rows)
     out = []
