@@ -145,6 +145,26 @@ __device__ __forceinline__ void load_words(const u64 *p, u64 *v, bool in)
     }
 }
 
+// Layout of one word's 2^kl low-subset ANDs.  With TL = 4 a lane owns the low subsets 4 l .. 4 l + 3 (kl = 7: 128 of them);
+// stored in subset order the lane's 32 bytes sit 32 bytes apart from its neighbour's and a 128-bit load hits every bank
+// twice (1.8e8 conflicts per n=16 launch in ncu, mio_throttle the top stall).  So the first and the second pair of a lane's
+// subsets go to two 512-byte halves in which the lanes' 16-byte pieces are contiguous: two conflict-free LDS.128.
+template <int TL>
+__device__ __forceinline__ int ltab_pos(int id)
+{
+    return TL == 4 ? ((id >> 1) & 1) * 64 + (id >> 2) * 2 + (id & 1) : id;
+}
+template <int TL>
+__device__ __forceinline__ void load_low(const u64 *word_base, int lane, u64 *v, bool in)
+{
+    if (TL == 4) {
+        const ulonglong2 x = reinterpret_cast<const ulonglong2 *>(word_base)[lane], y = reinterpret_cast<const ulonglong2 *>(word_base + 64)[lane];
+        v[0] = x.x; v[1] = x.y; v[2 % TL] = y.x; v[3 % TL] = y.y;
+    } else {
+        load_words<TL>(word_base + lane * TL, v, in);
+    }
+}
+
 template <int TH, int TL, typename CT>
 __global__ void __launch_bounds__(512, 1) k_general(const GeneralArgs a)
 {
@@ -206,7 +226,7 @@ __global__ void __launch_bounds__(512, 1) k_general(const GeneralArgs a)
                             u64 v = ~0ull;
 #pragma unroll
                             for (int i = 0; i < KL; ++i) v &= M[i * wp + w0 + w] | keep[i];
-                            ltab[(w << KL) + id] = v;
+                            ltab[(w << KL) + ltab_pos<TL>(id)] = v;
                         }
                     } else if (kl == KL) {
                         for (int e = tid; e < (cw << KL); e += T) {
@@ -214,7 +234,7 @@ __global__ void __launch_bounds__(512, 1) k_general(const GeneralArgs a)
                             u64 v = ~0ull;
 #pragma unroll
                             for (int i = 0; i < KL; ++i) v &= M[i * wp + w0 + w] | (((id >> i) & 1) ? 0ull : ~0ull);
-                            ltab[e] = v;
+                            ltab[(w << KL) + ltab_pos<TL>(id)] = v;
                         }
                     } else {
                         for (int e = tid; e < (cw << kl); e += T) {
@@ -247,7 +267,7 @@ __global__ void __launch_bounds__(512, 1) k_general(const GeneralArgs a)
                         for (; w + 3 <= cw; w += 3) {
                             u64 l[3][TL];
 #pragma unroll
-                            for (int k = 0; k < 3; ++k) load_words<TL>(ltab + ((w + k) << kl) + lane * TL, l[k], lane * TL < LS);
+                            for (int k = 0; k < 3; ++k) load_low<TL>(ltab + ((w + k) << kl), lane, l[k], lane * TL < LS);
 #pragma unroll
                             for (int h2 = 0; h2 < TH; h2 += 2) {
                                 u64 hv[3][2];
@@ -263,7 +283,7 @@ __global__ void __launch_bounds__(512, 1) k_general(const GeneralArgs a)
                         }
                         for (; w < cw; ++w) {
                             u64 l[TL];
-                            load_words<TL>(ltab + (w << kl) + lane * TL, l, lane * TL < LS);
+                            load_low<TL>(ltab + (w << kl), lane, l, lane * TL < LS);
 #pragma unroll
                             for (int h = 0; h < TH; ++h) {
                                 const u64 hv = htab[(w << kh) + hi0 + h];
