@@ -111,6 +111,45 @@ def test_more_ranks_than_windows():
             assert res[p, 2] == want[pair]['fraction_of_negative_LLRs']
 
 
+class _NoPeerEngine:
+    """ stands for an Engine on a box where peer memory cannot be mapped: rank 1's buffer allocation fails """
+    def __init__(self, rank):
+        self.rank = rank
+
+    def comm_create(self, rank, world, n):
+        if self.rank == 1:
+            raise RuntimeError('no peer access')
+        return b'x' * 128
+
+    def comm_connect(self, handles):
+        raise AssertionError('must not be reached when a rank has no handle')
+
+
+def _peer_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from ldpgta_b200 import sharding
+    dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world)
+    q.put((rank, sharding.connect_peers(_NoPeerEngine(rank), 1000)))
+    dist.destroy_process_group()
+
+
+def test_connect_peers_degrades_without_hanging():
+    """ One rank cannot set up its exchange buffer: every rank still passes the collectives of connect_peers and all of
+    them learn that the peer path is off (the callers then use all_reduce). """
+    world, port = 2, _free_port()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_peer_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got == [(0, False), (1, False)]
+
+
 def test_partition_is_balanced_and_contiguous():
     sys.path.insert(0, ROOT)
     from ldpgta_b200 import sharding
