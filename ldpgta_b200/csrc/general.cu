@@ -39,6 +39,10 @@ static int plan_general(const ldpgta_ctx *c, int n, int kind, GeneralPlan *p)
     const size_t fixed = 128 + (size_t)n * wsum * 8 + (p->global_table ? 0 : p->table_bytes) + (p->etab ? (size_t)8 << n : 0) + 64 + 16 + 16 * 12 * 8;
     const size_t per_word = ((size_t)8 << p->kl) + ((size_t)8 << p->kh);
     size_t budget_kb = (size_t)BUDGET_KB[n];
+    // distant admixture with e(S) in a global slice: its polynomial re-reads 128-byte rows through L1, which is what the
+    // shared-memory carve-out leaves of 256 KB.  192 KB of chunk tables instead of 220 KB: 16 reads 11.3 -> 9.9 ms, 17 reads
+    // 16.8 -> 13.4 ms per 592 draws (the integer models lose 1-2 % with it and keep 220 KB)
+    if (kind == LDPGTA_DISTANT_ADMIXTURE && n >= 5 && !p->etab) budget_kb = std::min<size_t>(budget_kb, 192);
     if (const char *e = getenv("LDPGTA_PLAN_KB")) budget_kb = (size_t)atoi(e);
     const size_t cap = std::min<size_t>((size_t)c->max_smem_optin, budget_kb * 1024 + (p->etab ? (size_t)8 << n : 0));
     if (fixed + 2 * per_word > (size_t)c->max_smem_optin)
@@ -47,9 +51,19 @@ static int plan_general(const ldpgta_ctx *c, int n, int kind, GeneralPlan *p)
     int wc = (int)(avail / per_word);
     wc = std::max(wc, 2);
     wc = std::min(wc, wmax);
-    // equalise the chunks: ceil(wmax / ceil(wmax / wc))
-    const int chunks = (wmax + wc - 1) / wc;
-    wc = (wmax + chunks - 1) / chunks;
+    // the counting loop folds three words into two POPC.64 (carry-save), so a chunk is a multiple of three words wherever
+    // the table is built in several chunks: e.g. 79 words as 15 x 5 + 4 cost 53 POPC.64 per subset, as 14 x 5 + 9 cost 56
+    if (wc < wmax && wc >= 3 && !getenv("LDPGTA_PLAN_NO_WC3")) {
+        wc -= wc % 3;
+        // the fewest multiples of three that still give the same number of chunks
+        const int chunks = (wmax + wc - 1) / wc;
+        int even = (wmax + chunks - 1) / chunks;
+        even += (3 - even % 3) % 3;
+        if (even <= wc) wc = even;
+    } else {
+        const int chunks = (wmax + wc - 1) / wc;             // equalise the chunks: ceil(wmax / ceil(wmax / wc))
+        wc = (wmax + chunks - 1) / chunks;
+    }
     p->wc = wc;
     PanelView pv = make_view(c, nullptr);
     p->smem = p->u16 ? general_smem_layout<uint16_t>(pv, n, p->kl, p->kh, wc, !p->global_table, p->etab).total

@@ -244,6 +244,23 @@ __global__ void __launch_bounds__(512, 1) k_general(const GeneralArgs a)
                             ltab[e] = v;
                         }
                     }
+                    if (kh >= 3) {
+                        // a thread builds the eight high subsets that differ in the last three reads from their common part:
+                        // kh + 4 ANDs for eight entries instead of 8 kh (the build was 8 % of the kernel at 17 reads); the eight
+                        // stores of a warp are each 256 contiguous bytes
+                        const int qs = kh - 3, Q = 1 << qs;
+                        const u64 *Mh = M + (size_t)kl * wp + w0;
+                        for (int e = tid; e < (cw << qs); e += T) {
+                            const int w = e >> qs, r = e & (Q - 1);
+                            u64 b = ~0ull;
+                            for (int i = 0; i < qs; ++i) b &= Mh[i * wp + w] | (((r >> i) & 1) ? 0ull : ~0ull);
+                            const u64 m0 = Mh[qs * wp + w], m1 = Mh[(qs + 1) * wp + w], m2 = Mh[(qs + 2) * wp + w];
+                            u64 *o = htab + (w << kh) + r;
+                            const u64 b0 = b & m0, b1 = b & m1;
+                            o[0] = b; o[Q] = b0; o[2 * Q] = b1; o[3 * Q] = b0 & m1;
+                            o[4 * Q] = b & m2; o[5 * Q] = b0 & m2; o[6 * Q] = b1 & m2; o[7 * Q] = b0 & m1 & m2;
+                        }
+                    } else
                     for (int e = tid; e < (cw << kh); e += T) {
                         const int w = e >> kh, id = e & (HS - 1);
                         u64 v = ~0ull;
@@ -259,6 +276,15 @@ __global__ void __launch_bounds__(512, 1) k_general(const GeneralArgs a)
                         for (int h = 0; h < TH; ++h)
 #pragma unroll
                             for (int j = 0; j < TL; ++j) acc[h][j] = 0;
+                        // a table in global memory (16-bit entries): the counts of the previous chunks are requested before the
+                        // word loop instead of after it, where their L2 latency was 8 % of the kernel at 18 reads (ncu)
+                        constexpr bool PRE = TL == 4 && sizeof(CT) == 2;
+                        uint2 before[PRE ? TH : 1];
+                        const bool pre = PRE && w0 && a.table_scratch != nullptr;
+                        if (pre)
+#pragma unroll
+                            for (int h = 0; h < (PRE ? TH : 1); ++h)
+                                before[h] = *reinterpret_cast<const uint2 *>(F + (((size_t)(hi0 + h) << kl) | (size_t)(lane * 4)));
                         // three words at a time: a carry-save adder folds their intersections into a "ones" and a
                         // "twos" word, so three word-ops cost two POPC.64 instead of three (POPC is the scarce pipe)
                         // a lane owns TL consecutive low subsets (lo = lane * TL + j) and the tile TH consecutive high ones, so
@@ -300,7 +326,8 @@ __global__ void __launch_bounds__(512, 1) k_general(const GeneralArgs a)
                                 CT *row = F + (((size_t)(hi0 + h) << kl) | (size_t)(lane * 4));
                                 if (sizeof(CT) == 2) {
                                     uint2 v = make_uint2(acc[h][0] | (acc[h][1] << 16), acc[h][2] | (acc[h][3] << 16));
-                                    if (w0) { const uint2 o = *reinterpret_cast<const uint2 *>(row); v.x += o.x; v.y += o.y; }   // no carry: counts < 2^16
+                                    if (pre) { v.x += before[PRE ? h : 0].x; v.y += before[PRE ? h : 0].y; }
+                                    else if (w0) { const uint2 o = *reinterpret_cast<const uint2 *>(row); v.x += o.x; v.y += o.y; }   // no carry: counts < 2^16
                                     *reinterpret_cast<uint2 *>(row) = v;
                                 } else {
                                     uint4 v = make_uint4(acc[h][0], acc[h][1], acc[h][2], acc[h][3]);
@@ -440,9 +467,13 @@ __global__ void __launch_bounds__(512, 1) k_general(const GeneralArgs a)
             double *etab = a.etab == 1 ? reinterpret_cast<double *>(smem + lay.etab)
                          : a.etab == 2 ? a.etab_scratch + (size_t)blockIdx.x * a.etab_stride : nullptr;
             if (n >= 5) {                                    // the launcher always provides a table for 5 or more reads
-                distant_fill_etab<CT>(ftab, a.pv, n, etab, tid, T);
+                // e(S) in shared memory is bank-swizzled (poly_general.cuh).  Not in a global slice: L2 has no banks to
+                // conflict on and the eight addresses of a row cost 64-bit arithmetic there (17 reads: -17 %), nor below 12
+                // reads, where the fill outweighs the polynomial.
+                const bool swz = a.etab == 1 && n >= 12;
+                distant_fill_etab<CT>(ftab, a.pv, n, etab, tid, T, swz);
                 __syncthreads();
-                poly_distant_etab(etab, n, a.terms, a.n_terms, tid, T, two, two_sph, three);
+                poly_distant_etab(etab, n, a.terms, a.n_terms, tid, T, two, two_sph, three, swz);
             } else
             for (uint32_t A = top + warp; A < full; A += NW) {
                 const uint32_t rest = full ^ A;

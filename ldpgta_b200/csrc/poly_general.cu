@@ -208,35 +208,37 @@ __device__ void poly_recent_blocked(const CT *F, const CT *G, int n, const u64 *
 
 // ---- distant admixture from a tabulated e(S) ------------------------------------------------------
 template <typename CT>
-__device__ void distant_fill_etab(const CT *ftab, const PanelView &pv, int n, double *etab, int tid, int T)
+__device__ void distant_fill_etab(const CT *ftab, const PanelView &pv, int n, double *etab, int tid, int T, bool swz)
 {
     const int G = pv.G;
     const uint32_t NS = 1u << n;
     for (uint32_t S = tid; S < NS; S += T) {
         double e = 0.0;
         for (int g = 0; g < G; ++g) e = e + pv.coef[g] * (double)ftab[((size_t)g << n) + S] / (double)pv.nhap[g];
-        etab[S] = e;
+        etab[swz ? etab_swizzle(S) : S] = e;
     }
 }
 
-template <int SPACE>
+template <int SPACE, bool SWZ>
 __device__ __forceinline__ void poly_distant_etab_impl(const double *E, int n, const u64 *terms, int64_t n_terms, int tid, int T,
                                                        double &two_out, double &two_sph_out, double &three_out)
 {
     const int h = n - 5;
     const uint32_t top_row = 1u << h, usub = (1u << (n - 1)) - 1u, top = 1u << (n - 1);
+    auto at = [&](uint32_t S) { return E[SWZ ? etab_swizzle(S) : S]; };
     auto row = [&](uint32_t r, double *v) {
         const double *p = E + ((size_t)r << 4);
+        const uint32_t m = SWZ ? fold3(r) : 0u;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            const uint4 x = load128<SPACE>(p + 2 * q);
+            const uint4 x = load128<SPACE>(p + 2 * (q ^ m));
             v[2 * q] = __hiloint2double((int)x.y, (int)x.x);
             v[2 * q + 1] = __hiloint2double((int)x.w, (int)x.z);
         }
     };
     double two = 0, two_sph = 0, three = 0;
     for (uint32_t a = tid; a < usub; a += T) {
-        const double prod = E[top | a] * E[usub ^ a];
+        const double prod = at(top | a) * at(usub ^ a);
         const int pa = __popc(a);
         two += prod;
         two_sph += prod * (double)((2ull << pa) + (1ull << (n - 1 - pa)));
@@ -245,13 +247,14 @@ __device__ __forceinline__ void poly_distant_etab_impl(const double *E, int n, c
         double Y[16], Z[16], acc = 0.0;                      // the X row is read where it is used (three rows do not fit)
         row(rb, Y); row(rc, Z);
         const double *X = E + ((size_t)(top_row + ra) << 4);
+        const uint32_t mx = SWZ ? fold3(top_row + ra) << 1 : 0u;
 #pragma unroll
         for (int s = 0; s < 16; ++s) {
             double cv = 0.0;
 #pragma unroll
             for (int b = 0; b < 16; ++b)
                 if ((b & s) == b) cv += Y[b] * Z[s ^ b];
-            acc += X[15 ^ s] * cv;
+            acc += X[(15 ^ s) ^ mx] * cv;
         }
         return acc;
     };
@@ -266,10 +269,15 @@ __device__ __forceinline__ void poly_distant_etab_impl(const double *E, int n, c
 }
 
 __device__ void poly_distant_etab(const double *etab, int n, const u64 *terms, int64_t n_terms, int tid, int T,
-                                  double &two, double &two_sph, double &three)
+                                  double &two, double &two_sph, double &three, bool swz)
 {
-    if (__isShared(etab)) poly_distant_etab_impl<1>(etab, n, terms, n_terms, tid, T, two, two_sph, three);
-    else poly_distant_etab_impl<0>(etab, n, terms, n_terms, tid, T, two, two_sph, three);
+    if (swz) {
+        if (__isShared(etab)) poly_distant_etab_impl<1, true>(etab, n, terms, n_terms, tid, T, two, two_sph, three);
+        else poly_distant_etab_impl<0, true>(etab, n, terms, n_terms, tid, T, two, two_sph, three);
+    } else {
+        if (__isShared(etab)) poly_distant_etab_impl<1, false>(etab, n, terms, n_terms, tid, T, two, two_sph, three);
+        else poly_distant_etab_impl<0, false>(etab, n, terms, n_terms, tid, T, two, two_sph, three);
+    }
 }
 
 #define LDPGTA_INST(CT)                                                                                              \
@@ -277,7 +285,7 @@ __device__ void poly_distant_etab(const double *etab, int n, const u64 *terms, i
     template __device__ void poly_homog_blocked<CT, u64>(const CT *, int, const u64 *, int64_t, int, int, u64 &, u64 &, u128 &);      \
     template __device__ void poly_recent_blocked<CT, uint32_t>(const CT *, const CT *, int, const u64 *, int64_t, int, int, u64 &, u64 &, u64 &, u64 &, u128 &, u128 &); \
     template __device__ void poly_recent_blocked<CT, u64>(const CT *, const CT *, int, const u64 *, int64_t, int, int, u64 &, u64 &, u64 &, u64 &, u128 &, u128 &);      \
-    template __device__ void distant_fill_etab<CT>(const CT *, const PanelView &, int, double *, int, int);
+    template __device__ void distant_fill_etab<CT>(const CT *, const PanelView &, int, double *, int, int, bool);
 LDPGTA_INST(uint16_t)
 LDPGTA_INST(uint32_t)
 #undef LDPGTA_INST

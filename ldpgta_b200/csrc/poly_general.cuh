@@ -33,9 +33,24 @@ __device__ void poly_recent_blocked(const CT *F, const CT *G, int n, const u64 *
 // (DISTANT_ADMIXTURE_MODELS.py:136-139) for all 2^n subsets, so that the polynomial reads doubles instead of redoing the
 // conversions and divisions at every use (an entry is used ~1.5^n times).  fill: threads tid of T, the caller
 // synchronises them before poly_distant_etab.
+//
+// Bank swizzle of e(S) (k_general, when the table is in shared memory).  The threads of a warp take consecutive colourings of the list, which
+// share a_h and run through the subsets b_h of the reads outside it, so their Y rows (and Z rows) differ in the lowest free
+// high reads.  A row of e(S) is 128 bytes -- all 32 banks -- so in subset order the eight 128-bit loads of a quarter warp
+// hit the same bank group: 7.9 wavefronts per load over the real lists (tools/bank_conflicts.py), and the load/store unit,
+// not the DMULs, bounds the polynomial (ncu at 13 reads: 85 % short_scoreboard).  Swizzled, the 16-byte unit u of row r sits
+// at u ^ fold3(r): flipping any read moves the unit to another bank group, 1.7 wavefronts per load (12-14 reads: +15 %,
+// +26 %, +50 % draws/s).  The same swizzle on the integer tables (32-byte rows, 3.5 -> 1.7 wavefronts) cost more in address arithmetic than
+// it saved -- their polynomials are bound by instruction issue, not by the load/store unit -- and was dropped.
+__host__ __device__ __forceinline__ uint32_t fold3(uint32_t x)
+{
+    x ^= x >> 12; x ^= x >> 6; x ^= x >> 3;
+    return x & 7u;
+}
+__host__ __device__ __forceinline__ uint32_t etab_swizzle(uint32_t S) { return S ^ (fold3(S >> 4) << 1); }
 template <typename CT>
-__device__ void distant_fill_etab(const CT *ftab, const PanelView &pv, int n, double *etab, int tid, int T);
+__device__ void distant_fill_etab(const CT *ftab, const PanelView &pv, int n, double *etab, int tid, int T, bool swz = false);
 __device__ void poly_distant_etab(const double *etab, int n, const u64 *terms, int64_t n_terms, int tid, int T,
-                                  double &two, double &two_sph, double &three);
+                                  double &two, double &two_sph, double &three, bool swz = false);
 
 }  // namespace ldpgta
