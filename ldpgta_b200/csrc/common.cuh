@@ -248,6 +248,8 @@ struct ldpgta_ctx {
     // colourings of the high reads used by the three-block polynomial, one list per h = n - 5 (built on first use)
     uint64_t *hi_terms[14] = {};
     int64_t n_hi_terms[14] = {};
+    uint64_t *run_terms[14][4] = {};       // the same colourings as runs of 2^bits that share a_h (poly_general.cuh), bits 1..3
+    int64_t n_run_terms[14][4] = {};
     // joint-frequency tables that do not fit shared memory (17-18 reads, or two-group models at 16): one slice per resident CTA
     unsigned char *table_scratch = nullptr;
     size_t table_scratch_bytes = 0;
@@ -324,6 +326,7 @@ int make_read_mask_tmap(ldpgta_ctx *c, int g);
 int launch_mid(ldpgta_ctx *c, SmallArgs &a, int n);      // 5-6 reads, register kernel; 1 = not applicable
 int launch_general(ldpgta_ctx *c, GeneralArgs a);
 int launch_lanes(ldpgta_ctx *c, GeneralArgs a);          // 7-10 reads (5-6 for two-group models), register counters; 1 = not applicable
+int ensure_run_terms(ldpgta_ctx *c, int h, int bits);    // ... as runs of up to 2^bits colourings with a common a_h
 int ensure_hi_terms(ldpgta_ctx *c, int h);               // colouring list of the three-block polynomial for h = n - 5 high reads
 
 }  // namespace ldpgta

@@ -143,6 +143,35 @@ int ensure_hi_terms(ldpgta_ctx *c, int h)
     return 0;
 }
 
+// The same colourings as runs: a | b_base << 16 | l << 32 stands for b_h = b_base | x over the subsets x of l, where l holds
+// the `bits` highest reads outside a_h below the very highest one (which belongs to c_h), or all of them when there are fewer.
+int ensure_run_terms(ldpgta_ctx *c, int h, int bits)
+{
+    if (c->run_terms[h][bits]) return 0;
+    std::vector<uint64_t> list;
+    const uint32_t fullh = (1u << h) - 1u;
+    for (uint32_t a = 0; a < fullh; ++a) {
+        const uint32_t rest = fullh ^ a, hi = 1u << (31 - __builtin_clz(rest)), sub = rest ^ hi;
+        // the HIGHEST reads of sub go into l: consecutive runs (the lanes of a warp) then differ in the lowest reads outside
+        // a_h and their rows spread over the shared-memory banks; with the lowest reads in l every lane of a quarter warp hit
+        // the same bank group (16 reads: 3.30 instead of 2.99 ms)
+        uint32_t l = 0, left = sub;
+        for (int k = 0; k < bits && left; ++k) { const uint32_t top = 1u << (31 - __builtin_clz(left)); l |= top; left ^= top; }
+        const uint32_t upper = sub ^ l;
+        uint32_t b = upper;
+        while (true) {
+            list.push_back((uint64_t)a | ((uint64_t)b << 16) | ((uint64_t)l << 32));
+            if (!b) break;
+            b = (b - 1) & upper;
+        }
+    }
+    LDPGTA_CUDA(cudaMalloc((void **)&c->run_terms[h][bits], list.size() * 8));
+    LDPGTA_CUDA(cudaMemcpyAsync(c->run_terms[h][bits], list.data(), list.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
+    c->n_run_terms[h][bits] = (int64_t)list.size();
+    return 0;
+}
+
 int launch_general(ldpgta_ctx *c, GeneralArgs a)
 {
     GeneralPlan p;
@@ -155,6 +184,27 @@ int launch_general(ldpgta_ctx *c, GeneralArgs a)
         a.terms = reinterpret_cast<const u64 *>(c->hi_terms[h]);
         a.n_terms = c->n_hi_terms[h];
         for (int g = 0; g < c->G; ++g) a.wide |= c->nhap[g] > (a.kind == LDPGTA_RECENT_ADMIXTURE ? 11585u : 16383u);   // 32-bit convolution sums: 16 (recent: 32) products of two counts
+    }
+    // integer models from 13 reads (enough runs to balance the block): the colourings come in runs that share the X row, as
+    // long as the 32-bit sums hold 2^bits convolutions -- 16 (recent admixture: 32) products of two counts each.  Measured
+    // against single colourings (LDPGTA_PLAN_NO_RUNS=1), 5008 haplotypes: 13..18 reads +3, +4, +7, +10, +15, +16 % draws/s.
+    a.runs = 0;
+    static const bool no_runs = getenv("LDPGTA_PLAN_NO_RUNS") != nullptr;
+    if (a.n >= 13 && a.kind != LDPGTA_DISTANT_ADMIXTURE && !a.wide && !no_runs) {
+        uint64_t nmax = 0;
+        for (int g = 0; g < c->G; ++g) nmax = std::max<uint64_t>(nmax, c->nhap[g]);
+        const uint64_t per_conv = (a.kind == LDPGTA_RECENT_ADMIXTURE ? 32u : 16u) * nmax * nmax;
+        int bits = 0;
+        const int want = a.n >= 15 ? 3 : 2;                      // runs of 4 keep the few colourings of 13-14 reads balanced
+        while (bits < want && (per_conv << (bits + 1)) <= 0xffffffffull) ++bits;
+        if (const char *e = getenv("LDPGTA_PLAN_RUN_BITS")) bits = std::min(bits, atoi(e));
+        if (bits >= 1) {
+            const int h = a.n - 5;
+            if (int rc = ensure_run_terms(c, h, bits)) return rc;
+            a.terms = reinterpret_cast<const u64 *>(c->run_terms[h][bits]);
+            a.n_terms = c->n_run_terms[h][bits];
+            a.runs = 1;
+        }
     }
 #define LDPGTA_CASE(TH_, TL_)                                                         \
     if (p.th == TH_ && p.tl == TL_)                                                   \

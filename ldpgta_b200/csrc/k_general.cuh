@@ -42,6 +42,7 @@ struct GeneralArgs {
     const u64 *terms;        // colourings (a_h | b_h << 16 | c_h << 32) of the n-5 high reads with b_h < c_h (poly_general.cuh)
     int64_t n_terms;
     int wide;                // 64-bit convolution accumulators (a group with more than 16383 haplotypes)
+    int runs;                // terms lists runs of colourings with a common a_h (poly_general.cuh), integer models only
     unsigned char *table_scratch;   // non-null: the joint-frequency tables live in global memory (L2), one slice per CTA
     size_t table_stride;
 };
@@ -370,7 +371,7 @@ __global__ void __launch_bounds__(512, 1) k_general(const GeneralArgs a)
             u128 three = 0;
             if (n >= 5) {
                 if (a.wide) poly_homog_blocked<CT, u64>(F, n, a.terms, a.n_terms, tid, T, two, two_sph, three);
-                else poly_homog_blocked<CT, uint32_t>(F, n, a.terms, a.n_terms, tid, T, two, two_sph, three);
+                else poly_homog_blocked<CT, uint32_t>(F, n, a.terms, a.n_terms, tid, T, two, two_sph, three, a.runs != 0);
             } else
             for (uint32_t A = top + warp; A < full; A += NW) {
                 const uint32_t rest = full ^ A;
@@ -411,7 +412,7 @@ __global__ void __launch_bounds__(512, 1) k_general(const GeneralArgs a)
             u128 ffg = 0, ggf = 0;
             if (n >= 5) {
                 if (a.wide) poly_recent_blocked<CT, u64>(F, Gt, n, a.terms, a.n_terms, tid, T, ff, gg, fg, fg_sph, ffg, ggf);
-                else poly_recent_blocked<CT, uint32_t>(F, Gt, n, a.terms, a.n_terms, tid, T, ff, gg, fg, fg_sph, ffg, ggf);
+                else poly_recent_blocked<CT, uint32_t>(F, Gt, n, a.terms, a.n_terms, tid, T, ff, gg, fg, fg_sph, ffg, ggf, a.runs != 0);
             } else
             for (uint32_t A = top + warp; A < full; A += NW) {
                 const uint32_t rest = full ^ A;

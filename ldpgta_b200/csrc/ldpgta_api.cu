@@ -381,6 +381,9 @@ int ldpgta_destroy(ldpgta_ctx *c)
     }
     for (int h = 0; h < 14; ++h)
         if (c->hi_terms[h]) cudaFree(c->hi_terms[h]);
+    for (int h = 0; h < 14; ++h)
+        for (int b = 0; b < 4; ++b)
+            if (c->run_terms[h][b]) cudaFree(c->run_terms[h][b]);
     if (c->table_scratch) cudaFree(c->table_scratch);
     if (c->allele_complement) cudaFree(c->allele_complement);
     if (c->d_buf) cudaFree(c->d_buf);

@@ -99,7 +99,7 @@ __device__ __forceinline__ u64 dot16(const uint32_t *X, const ACC *conv)
 
 // ---- homogeneous ------------------------------------------------------------------------------
 // returns per-thread partials: two, two_sph (u64) and three (u64; the caller sums them in 128 bits)
-template <typename CT, typename ACC, int SPACE>
+template <typename CT, typename ACC, int SPACE, bool RUNS>
 __device__ __forceinline__ void poly_homog_impl(const CT *F, int n, const u64 *terms, int64_t n_terms, int tid, int T,
                                                 u64 &two_out, u64 &two_sph_out, u128 &three_out)
 {
@@ -116,6 +116,35 @@ __device__ __forceinline__ void poly_homog_impl(const CT *F, int n, const u64 *t
         two_sph += prod * ((2ull << pa) + (1ull << (n - 1 - pa)));
     }
     u64 t_next = tid < n_terms ? terms[tid] : 0;                 // the colouring list is read one iteration ahead
+    if (RUNS) {
+        const uint32_t fullh = top_row - 1u;
+        for (int64_t e = tid; e < n_terms; e += T) {
+            const u64 t = t_next;
+            if (e + T < n_terms) t_next = terms[e + T];
+            const uint32_t ra = (uint32_t)(t & 0xffffu), base = (uint32_t)(t >> 16) & 0xffffu, l = (uint32_t)(t >> 32) & 0xffffu;
+            const uint32_t rest = fullh ^ ra;
+            uint32_t Y[16], Z[16];
+            ACC c[16];
+#pragma unroll
+            for (int s = 0; s < 16; ++s) c[s] = 0;
+            // the colourings of the run: b_h = base | x over the subsets x of l, c_h the others.  A fixed trip count with the
+            // subsets formed from the single reads of l: the row addresses do not depend on the previous iteration, so the
+            // loads are scheduled ahead of the products (a loop over x = (x - 1) & l exposed every load's latency)
+            const uint32_t l0 = l & (0u - l), l12 = l ^ l0, l1 = l12 & (0u - l12), l2 = l12 ^ l1;
+            const int cnt = 1 << __popc(l);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (i < cnt) {
+                    const uint32_t rb = base | ((i & 1) ? l0 : 0u) | ((i & 2) ? l1 : 0u) | ((i & 4) ? l2 : 0u);
+                    load_row16<CT, SPACE>(F, rb, Y);
+                    load_row16<CT, SPACE>(F, rest ^ rb, Z);
+                    conv16_add<ACC>(Y, Z, c);
+                }
+            }
+            load_row16<CT, SPACE>(F, top_row + ra, Y);           // X, once per run
+            three += dot16<ACC>(Y, c);
+        }
+    } else
     for (int64_t e = tid; e < n_terms; e += T) {
         const u64 t = t_next;
         if (e + T < n_terms) t_next = terms[e + T];
@@ -140,14 +169,21 @@ __device__ __forceinline__ void poly_homog_impl(const CT *F, int n, const u64 *t
 
 template <typename CT, typename ACC>
 __device__ void poly_homog_blocked(const CT *F, int n, const u64 *terms, int64_t n_terms, int tid, int T,
-                                   u64 &two, u64 &two_sph, u128 &three)
+                                   u64 &two, u64 &two_sph, u128 &three, bool runs)
 {
-    if (__isShared(F)) poly_homog_impl<CT, ACC, 1>(F, n, terms, n_terms, tid, T, two, two_sph, three);
-    else poly_homog_impl<CT, ACC, 0>(F, n, terms, n_terms, tid, T, two, two_sph, three);
+    if constexpr (sizeof(ACC) == 4) {                            // the launcher asks for runs with 32-bit sums only
+        if (runs) {
+            if (__isShared(F)) poly_homog_impl<CT, ACC, 1, true>(F, n, terms, n_terms, tid, T, two, two_sph, three);
+            else poly_homog_impl<CT, ACC, 0, true>(F, n, terms, n_terms, tid, T, two, two_sph, three);
+            return;
+        }
+    }
+    if (__isShared(F)) poly_homog_impl<CT, ACC, 1, false>(F, n, terms, n_terms, tid, T, two, two_sph, three);
+    else poly_homog_impl<CT, ACC, 0, false>(F, n, terms, n_terms, tid, T, two, two_sph, three);
 }
 
 // ---- recent admixture: F = group 0, G = group 1 ------------------------------------------------
-template <typename CT, typename ACC, int SPACE>
+template <typename CT, typename ACC, int SPACE, bool RUNS>
 __device__ __forceinline__ void poly_recent_impl(const CT *F, const CT *G, int n, const u64 *terms, int64_t n_terms, int tid,
                                                  int T, u64 &ff_out, u64 &gg_out, u64 &fg_out, u64 &fg_sph_out, u128 &ffg_out,
                                                  u128 &ggf_out)
@@ -189,6 +225,41 @@ __device__ __forceinline__ void poly_recent_impl(const CT *F, const CT *G, int n
         ggf += s_ggf;
     };
     u64 t_next = tid < n_terms ? terms[tid] : 0;
+    if (RUNS) {
+        // runs of colourings that share a_h: three convolution sums (Yf*Zf, Yf*Zg + Yg*Zf, Yg*Zg) and four dot products per run
+        const uint32_t fullh = top_row - 1u;
+        for (int64_t e = tid; e < n_terms; e += T) {
+            const u64 t = t_next;
+            if (e + T < n_terms) t_next = terms[e + T];
+            const uint32_t ra = (uint32_t)(t & 0xffffu), base = (uint32_t)(t >> 16) & 0xffffu, l = (uint32_t)(t >> 32) & 0xffffu;
+            const uint32_t rest = fullh ^ ra;
+            uint32_t Y[16], Z[16];
+            ACC cff[16], cmix[16], cgg[16];
+#pragma unroll
+            for (int s = 0; s < 16; ++s) { cff[s] = 0; cmix[s] = 0; cgg[s] = 0; }
+            const uint32_t l0 = l & (0u - l), l12 = l ^ l0, l1 = l12 & (0u - l12), l2 = l12 ^ l1;
+            const int cnt = 1 << __popc(l);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (i < cnt) {
+                    const uint32_t rb = base | ((i & 1) ? l0 : 0u) | ((i & 2) ? l1 : 0u) | ((i & 4) ? l2 : 0u), rc = rest ^ rb;
+                    load_row16<CT, SPACE>(F, rb, Y); load_row16<CT, SPACE>(F, rc, Z);
+                    conv16_add<ACC>(Y, Z, cff);                                                   // Yf * Zf
+                    load_row16<CT, SPACE>(G, rc, Z);
+                    conv16_add<ACC>(Y, Z, cmix);                                                  // Yf * Zg
+                    load_row16<CT, SPACE>(G, rb, Y);
+                    conv16_add<ACC>(Y, Z, cgg);                                                   // Yg * Zg
+                    load_row16<CT, SPACE>(F, rc, Z);
+                    conv16_add<ACC>(Y, Z, cmix);                                                  // Yg * Zf
+                }
+            }
+            load_row16<CT, SPACE>(F, top_row + ra, Y); load_row16<CT, SPACE>(G, top_row + ra, Z); // Xf, Xg
+            ffg += dot16<ACC>(Z, cff);
+            ffg += dot16<ACC>(Y, cmix);
+            ggf += dot16<ACC>(Z, cmix);
+            ggf += dot16<ACC>(Y, cgg);
+        }
+    } else
     for (int64_t e = tid; e < n_terms; e += T) {
         const u64 t = t_next;
         if (e + T < n_terms) t_next = terms[e + T];
@@ -200,10 +271,18 @@ __device__ __forceinline__ void poly_recent_impl(const CT *F, const CT *G, int n
 
 template <typename CT, typename ACC>
 __device__ void poly_recent_blocked(const CT *F, const CT *G, int n, const u64 *terms, int64_t n_terms, int tid, int T,
-                                    u64 &ff, u64 &gg, u64 &fg, u64 &fg_sph, u128 &ffg, u128 &ggf)
+                                    u64 &ff, u64 &gg, u64 &fg, u64 &fg_sph, u128 &ffg, u128 &ggf, bool runs)
 {
-    if (__isShared(F) && __isShared(G)) poly_recent_impl<CT, ACC, 1>(F, G, n, terms, n_terms, tid, T, ff, gg, fg, fg_sph, ffg, ggf);
-    else poly_recent_impl<CT, ACC, 0>(F, G, n, terms, n_terms, tid, T, ff, gg, fg, fg_sph, ffg, ggf);
+    const bool sh = __isShared(F) && __isShared(G);
+    if constexpr (sizeof(ACC) == 4) {
+        if (runs) {
+            if (sh) poly_recent_impl<CT, ACC, 1, true>(F, G, n, terms, n_terms, tid, T, ff, gg, fg, fg_sph, ffg, ggf);
+            else poly_recent_impl<CT, ACC, 0, true>(F, G, n, terms, n_terms, tid, T, ff, gg, fg, fg_sph, ffg, ggf);
+            return;
+        }
+    }
+    if (sh) poly_recent_impl<CT, ACC, 1, false>(F, G, n, terms, n_terms, tid, T, ff, gg, fg, fg_sph, ffg, ggf);
+    else poly_recent_impl<CT, ACC, 0, false>(F, G, n, terms, n_terms, tid, T, ff, gg, fg, fg_sph, ffg, ggf);
 }
 
 // ---- distant admixture from a tabulated e(S) ------------------------------------------------------
@@ -281,10 +360,10 @@ __device__ void poly_distant_etab(const double *etab, int n, const u64 *terms, i
 }
 
 #define LDPGTA_INST(CT)                                                                                              \
-    template __device__ void poly_homog_blocked<CT, uint32_t>(const CT *, int, const u64 *, int64_t, int, int, u64 &, u64 &, u128 &); \
-    template __device__ void poly_homog_blocked<CT, u64>(const CT *, int, const u64 *, int64_t, int, int, u64 &, u64 &, u128 &);      \
-    template __device__ void poly_recent_blocked<CT, uint32_t>(const CT *, const CT *, int, const u64 *, int64_t, int, int, u64 &, u64 &, u64 &, u64 &, u128 &, u128 &); \
-    template __device__ void poly_recent_blocked<CT, u64>(const CT *, const CT *, int, const u64 *, int64_t, int, int, u64 &, u64 &, u64 &, u64 &, u128 &, u128 &);      \
+    template __device__ void poly_homog_blocked<CT, uint32_t>(const CT *, int, const u64 *, int64_t, int, int, u64 &, u64 &, u128 &, bool); \
+    template __device__ void poly_homog_blocked<CT, u64>(const CT *, int, const u64 *, int64_t, int, int, u64 &, u64 &, u128 &, bool);      \
+    template __device__ void poly_recent_blocked<CT, uint32_t>(const CT *, const CT *, int, const u64 *, int64_t, int, int, u64 &, u64 &, u64 &, u64 &, u128 &, u128 &, bool); \
+    template __device__ void poly_recent_blocked<CT, u64>(const CT *, const CT *, int, const u64 *, int64_t, int, int, u64 &, u64 &, u64 &, u64 &, u128 &, u128 &, bool);      \
     template __device__ void distant_fill_etab<CT>(const CT *, const PanelView &, int, double *, int, int, bool);
 LDPGTA_INST(uint16_t)
 LDPGTA_INST(uint32_t)

@@ -22,13 +22,20 @@
 namespace ldpgta {
 
 // per-thread partials: two, two_sph (64-bit) and three (128-bit); the caller sums them across the block;
-// ACC = uint32_t when 16 * N^2 < 2^32 (every group has at most 16383 haplotypes), else u64
+// ACC = uint32_t when 16 * N^2 < 2^32 (every group has at most 16383 haplotypes), else u64.
+//
+// runs = true: `terms` is a list of RUNS of colourings instead (general.cu: ensure_run_terms).  T(X,Y,Z) is linear in the
+// convolution, and the colourings that share a_h share X, so their convolutions can be summed first and dotted with X once:
+// a run a_h | b_base << 16 | l << 32 stands for the colourings b_h = b_base | x over the subsets x of l (up to three of the
+// lowest reads outside a_h), and costs 81 IMADs per colouring plus one X row and 16 wide multiply-adds per run instead of
+// per colouring -- the polynomial is bound by instruction issue, and this is 1.4x fewer instructions.  The 32-bit sums hold
+// 2^|l| convolutions, which is why the launcher bounds |l| by the panel size.
 template <typename CT, typename ACC>
 __device__ void poly_homog_blocked(const CT *F, int n, const u64 *terms, int64_t n_terms, int tid, int T,
-                                   u64 &two, u64 &two_sph, u128 &three);
+                                   u64 &two, u64 &two_sph, u128 &three, bool runs = false);
 template <typename CT, typename ACC>
 __device__ void poly_recent_blocked(const CT *F, const CT *G, int n, const u64 *terms, int64_t n_terms, int tid, int T,
-                                    u64 &ff, u64 &gg, u64 &fg, u64 &fg_sph, u128 &ffg, u128 &ggf);
+                                    u64 &ff, u64 &gg, u64 &fg, u64 &fg_sph, u128 &ffg, u128 &ggf, bool runs = false);
 // Distant admixture with the effective frequencies tabulated once per draw: etab[S] = sum_g p_g * cnt_g(S) / N_g
 // (DISTANT_ADMIXTURE_MODELS.py:136-139) for all 2^n subsets, so that the polynomial reads doubles instead of redoing the
 // conversions and divisions at every use (an entry is used ~1.5^n times).  fill: threads tid of T, the caller

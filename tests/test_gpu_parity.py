@@ -230,6 +230,31 @@ def test_recent_admixture_accumulator_width(sizes):
             assert max_rel(got, want) < LIK_TOL, (sizes, n, max_rel(got, want))
 
 
+@pytest.mark.parametrize('model,sizes', [('homogeneous', (5792,)), ('homogeneous', (5793,)), ('homogeneous', (8191,)),
+                                         ('homogeneous', (8192,)), ('homogeneous', (11585,)), ('homogeneous', (11586,)),
+                                         ('recent', (4096, 4096)), ('recent', (4097, 3000)), ('recent', (5792, 5792)),
+                                         ('recent', (5793, 100)), ('recent', (8191, 8191)), ('recent', (8192, 8192))])
+def test_polynomial_run_lengths(model, sizes):
+    """ From 15 reads the integer polynomials sum the convolutions of up to 2, 4 or 8 colourings that share the X row in 32-bit
+    accumulators before the dot product (poly_general.cuh); how many depends on the panel size.  Panels on both sides of every
+    threshold, with nearly all-ones rows so that the sums come as close to 2^32 as they can. """
+    rng = np.random.default_rng(sum(sizes))
+    rows = [ld_rows(rng, 24, s, founders=2, density=0.95) | np.uint64(0x7fffffffffffffff) for s in sizes]
+    for r, s in zip(rows, sizes):
+        tail = s - 64 * ((s + 63) // 64 - 1)
+        if tail < 64:
+            r[:, -1] &= np.uint64((1 << tail) - 1)
+    kind, code = (L.HOMOGENEOUS, 0) if model == 'homogeneous' else (L.RECENT_ADMIXTURE, 1)
+    with L.Engine(list(sizes)) as eng:
+        for g in range(len(sizes)):
+            eng.upload_read_masks(g, rows[g])
+        for n in (15, 16):
+            idx, off = uniform_draws(rng, 24, n, 2)
+            got = eng.likelihoods_batch(kind, idx, off)
+            want = C.batch(_common_width(rows), list(sizes), idx, off, code)
+            assert max_rel(got, want) < LIK_TOL, (model, sizes, n, max_rel(got, want))
+
+
 def _common_width(rows):
     W = max(r.shape[1] for r in rows)
     out = []
