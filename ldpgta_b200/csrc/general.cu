@@ -154,7 +154,9 @@ int ensure_run_terms(ldpgta_ctx *c, int h, int bits)
         const uint32_t rest = fullh ^ a, hi = 1u << (31 - __builtin_clz(rest)), sub = rest ^ hi;
         // the HIGHEST reads of sub go into l: consecutive runs (the lanes of a warp) then differ in the lowest reads outside
         // a_h and their rows spread over the shared-memory banks; with the lowest reads in l every lane of a quarter warp hit
-        // the same bank group (16 reads: 3.30 instead of 2.99 ms)
+        // the same bank group (16 reads: 3.30 instead of 2.71 ms).  Dealing the runs into groups of eight with every row
+        // residue mod 4 twice (2 wavefronts per load, the floor for 32-byte rows, instead of 3.5) gained 1.5 % at 16 reads
+        // and lost 4-5 % at 17-18 reads, where the tables are in L2 and neighbouring runs share sectors: not kept.
         uint32_t l = 0, left = sub;
         for (int k = 0; k < bits && left; ++k) { const uint32_t top = 1u << (31 - __builtin_clz(left)); l |= top; left ^= top; }
         const uint32_t upper = sub ^ l;
