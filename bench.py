@@ -744,7 +744,7 @@ def strong_scaling_leg(L, torch, dist, device, local, rank, world, args, kind, g
             'scaling': 'strong', 'value': len(reads) * subs * steps / (total_ms * 1e-3), 'unit': 'window-likelihoods/s',
             'ms_per_step': total_ms / steps, 'windows_rank0': int(windows_here), 'allreduce_bytes': int(partials.numel() * 8),
             'allreduce_ms_median': ar_ms, 'allreduce_share_of_step': ar_ms / (total_ms / steps),
-            'collective': 'ldpgta_allreduce_chrom_dev: one kernel over NVLink peer memory (publish, flag peers, poll locally, peer loads, rank-order sum)' if peer_ok
+            'collective': 'ldpgta_allreduce_chrom_dev: one kernel over NVLink peer memory (push to every peer, flag, poll locally, rank-order sum from own HBM)' if peer_ok
                           else 'torch.distributed all_reduce (NCCL): peer memory could not be mapped on this box',
             'nccl_comparison': {'ms_per_step': res['nccl'][0] / steps, 'allreduce_ms_median': res['nccl'][1],
                                 'collective': 'torch.distributed all_reduce (NCCL) on the same device-resident partials'},

@@ -219,8 +219,8 @@ int ldpgta_finish_segments_dev(ldpgta_ctx *ctx, const double *segment_partials_d
 /* ---- the cross-GPU exchange: the sum of the ranks' segment (chromosome) partial sums ----------------------------------
  * One process per GPU.  When the windows of one chromosome are dealt to several GPUs, the column sums of
  * mean_and_std_of_mean_of_rnd_var (ANEUPLOIDY_TEST.py:65-76) have to be added across them; nothing else of the path
- * crosses GPUs.  The sum is ONE kernel over NVLink / NVSwitch peer memory (publish in own HBM, flag the peers by remote
- * stores, poll locally, read the peers' partials by peer loads, add in rank order: every rank gets bit-identical sums);
+ * crosses GPUs.  The sum is ONE kernel over NVLink / NVSwitch peer memory (store the partials into every peer's buffer,
+ * flag the peers, poll locally, add the world's slots from own memory in rank order: every rank gets bit-identical sums);
  * no library collective is involved.
  *   ldpgta_comm_create   allocates this rank's exchange buffer for up to max_doubles values and writes its handle
  *                        (LDPGTA_COMM_HANDLE_BYTES bytes, to be passed to every peer by any byte transport)

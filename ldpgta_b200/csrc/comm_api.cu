@@ -1,9 +1,10 @@
 // comm_api.cu -- the one cross-GPU exchange of the path: the sum of the ranks' chromosome partial sums
 // (mean_and_std_of_mean_of_rnd_var needs sums over ALL windows of a chromosome, ANEUPLOIDY_TEST.py:65-76), done by ONE
 // kernel over NVLink / NVSwitch peer memory instead of a library collective.  The payload is a few tens of kilobytes, so
-// the exchange is pure latency: every rank publishes its partials in its own HBM, raises a flag in every peer's memory
-// (remote stores), waits for the peers' flags in its own memory (local polling) and then reads the peers' partials through
-// peer loads, adding them in rank order -- every rank obtains bit-identical sums.
+// the exchange is pure latency, and it is a PUSH: every rank stores its partials into its slot of every peer's buffer
+// (posted remote stores), raises a flag in every peer's memory, waits for the peers' flags in its own memory (local
+// polling) and then adds the world's slots from its own HBM in rank order -- every rank obtains bit-identical sums, and
+// no load crosses NVLink (the first version pulled the peers' partials with peer loads: one more round trip per pass).
 //
 // One process per GPU: buffers are shared through CUDA IPC handles, exchanged by the caller (torch.distributed
 // all_gather_object in ldpgta_b200/sharding.py, any byte transport will do).  Contexts of one process (tests) use the
@@ -27,7 +28,7 @@ static_assert(sizeof(CommHandle) <= LDPGTA_COMM_HANDLE_BYTES, "handle must fit t
 struct PeerComm {
     int rank = 0, world = 1;
     int64_t max_doubles = 0;
-    unsigned char *mine = nullptr;       // own allocation: [2][max_doubles] doubles, then [2][MAXPEERS] arrival epochs, then status
+    unsigned char *mine = nullptr;       // own allocation: [2][world][max_doubles] doubles, then [2][MAXPEERS] arrival epochs
     unsigned char *peer[LDPGTA_MAX_PEERS] = {};
     bool opened[LDPGTA_MAX_PEERS] = {};
     bool connected = false;
@@ -37,21 +38,27 @@ struct PeerComm {
 };
 
 struct CommView {
-    double *data[LDPGTA_MAX_PEERS];              // peers' [2][max_doubles]
+    double *data[LDPGTA_MAX_PEERS];              // peers' [2][world][max_doubles]: slot [parity][r] is written by rank r
     unsigned long long *arrive[LDPGTA_MAX_PEERS];   // peers' [2][MAXPEERS]
     unsigned int *status;                        // own: 1 = a peer did not arrive in time
     int rank, world;
     int64_t max_doubles;
 };
 
-static size_t comm_bytes(int64_t max_doubles) { return (size_t)2 * max_doubles * 8 + 2 * LDPGTA_MAX_PEERS * 8 + 64; }
+static size_t comm_data_bytes(int world, int64_t max_doubles) { return (size_t)2 * world * max_doubles * 8; }
+static size_t comm_bytes(int world, int64_t max_doubles) { return comm_data_bytes(world, max_doubles) + 2 * LDPGTA_MAX_PEERS * 8 + 64; }
 
 // partials (in place) = sum over ranks, rank order.  One CTA.
 static __global__ void __launch_bounds__(1024) k_allreduce_peer(const CommView v, double *__restrict__ partials, int64_t n, unsigned long long epoch)
 {
     const int par = (int)(epoch & 1ull);
-    double *own = v.data[v.rank] + (int64_t)par * v.max_doubles;
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) own[i] = partials[i];
+    const int64_t slot = ((int64_t)par * v.world + v.rank) * v.max_doubles;      // my slot, the same offset in every buffer
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const double x = partials[i];
+#pragma unroll
+        for (int r = 0; r < LDPGTA_MAX_PEERS; ++r)
+            if (r < v.world) v.data[r][slot + i] = x;
+    }
     __syncthreads();                                   // the block's stores are ordered before the fence of the flag writers
     if ((int)threadIdx.x < v.world) {
         // raise my flag in peer t's memory, then wait for peer t's flag in mine
@@ -70,27 +77,11 @@ static __global__ void __launch_bounds__(1024) k_allreduce_peer(const CommView v
         __threadfence_system();
     }
     __syncthreads();
-    // peer loads (NVLink): the exchange is latency, so a thread puts the values of up to four of its elements from every
-    // rank in flight together (4 x world loads) before adding them in rank order
-    constexpr int EPT = 4;
-    for (int64_t i0 = threadIdx.x; i0 < n; i0 += (int64_t)EPT * blockDim.x) {
-        double x[EPT][LDPGTA_MAX_PEERS];
-#pragma unroll
-        for (int k = 0; k < EPT; ++k) {
-            const int64_t i = i0 + (int64_t)k * blockDim.x;
-#pragma unroll
-            for (int r = 0; r < LDPGTA_MAX_PEERS; ++r)
-                if (r < v.world && i < n) x[k][r] = __ldcv(v.data[r] + (int64_t)par * v.max_doubles + i);
-        }
-#pragma unroll
-        for (int k = 0; k < EPT; ++k) {
-            const int64_t i = i0 + (int64_t)k * blockDim.x;
-            double s = 0.0;
-#pragma unroll
-            for (int r = 0; r < LDPGTA_MAX_PEERS; ++r)
-                if (r < v.world) s += x[k][r];
-            if (i < n) partials[i] = s;
-        }
+    const double *mine = v.data[v.rank] + (int64_t)par * v.world * v.max_doubles;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        double s = 0.0;
+        for (int r = 0; r < v.world; ++r) s += __ldcv(mine + (int64_t)r * v.max_doubles + i);     // written by the peers: not through L1
+        partials[i] = s;
     }
 }
 
@@ -126,8 +117,8 @@ int ldpgta_comm_create(ldpgta_ctx *c, int rank, int world, int64_t max_doubles, 
     PeerComm *pc = new PeerComm();
     c->comm = pc;
     pc->rank = rank; pc->world = world; pc->max_doubles = max_doubles;
-    LDPGTA_CUDA(cudaMalloc((void **)&pc->mine, comm_bytes(max_doubles)));
-    LDPGTA_CUDA(cudaMemset(pc->mine, 0, comm_bytes(max_doubles)));
+    LDPGTA_CUDA(cudaMalloc((void **)&pc->mine, comm_bytes(world, max_doubles)));
+    LDPGTA_CUDA(cudaMemset(pc->mine, 0, comm_bytes(world, max_doubles)));
     LDPGTA_CUDA(cudaHostAlloc((void **)&pc->h_status, 16, cudaHostAllocMapped));
     *pc->h_status = 0;
     LDPGTA_CUDA(cudaHostGetDevicePointer((void **)&pc->d_status, pc->h_status, 0));
@@ -189,7 +180,7 @@ int ldpgta_allreduce_chrom_dev(ldpgta_ctx *c, double *partials_dev, int64_t n_do
     memset(&v, 0, sizeof v);
     for (int r = 0; r < pc->world; ++r) {
         v.data[r] = (double *)pc->peer[r];
-        v.arrive[r] = (unsigned long long *)(pc->peer[r] + (size_t)2 * pc->max_doubles * 8);
+        v.arrive[r] = (unsigned long long *)(pc->peer[r] + comm_data_bytes(pc->world, pc->max_doubles));
     }
     v.status = pc->d_status;
     v.rank = pc->rank; v.world = pc->world; v.max_doubles = pc->max_doubles;
