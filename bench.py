@@ -297,7 +297,7 @@ def kernel_name(n, model):
         return 'k_small<%d,8,10>' % n
     if n == 5 and model == 'homogeneous':
         return 'k_mid<5,5>'
-    if n <= {'homogeneous': 12, 'recent': 12, 'distant': 10}[model] and not (model == 'distant' and n == 5):
+    if n <= 12 and not (model == 'distant' and n == 5):        # (distant admixture of three or more groups: up to 10)
         return 'k_lanes<%d,%d>' % (n, {5: 3, 6: 3, 7: 3, 8: 4, 9: 4}.get(n, 5))
     return 'k_general (n=%d)' % n
 

@@ -34,15 +34,16 @@ static int plan_general(const ldpgta_ctx *c, int n, int kind, GeneralPlan *p)
     p->table_bytes = entries * ct;
     p->global_table = p->table_bytes > 128 * 1024;
     // distant admixture: e(S) as doubles next to the count tables while both fit (n <= 13 for two groups)
-    p->etab = kind == LDPGTA_DISTANT_ADMIXTURE && n >= 5 && !p->global_table &&
+    // (three or more groups only: two groups use the integer form, poly_general.cuh Cubic2)
+    p->etab = kind == LDPGTA_DISTANT_ADMIXTURE && c->G > 2 && n >= 5 && !p->global_table &&
               p->table_bytes + ((size_t)8 << n) + (size_t)n * wsum * 8 + 16 * 1024 <= (size_t)c->max_smem_optin;
-    const size_t fixed = 128 + (size_t)n * wsum * 8 + (p->global_table ? 0 : p->table_bytes) + (p->etab ? (size_t)8 << n : 0) + 64 + 16 + 16 * 12 * 8;
+    const size_t fixed = 128 + (size_t)n * wsum * 8 + (p->global_table ? 0 : p->table_bytes) + (p->etab ? (size_t)8 << n : 0) + 64 + 16 + 16 * 22 * 8;
     const size_t per_word = ((size_t)8 << p->kl) + ((size_t)8 << p->kh);
     size_t budget_kb = (size_t)BUDGET_KB[n];
     // distant admixture with e(S) in a global slice: its polynomial re-reads 128-byte rows through L1, which is what the
     // shared-memory carve-out leaves of 256 KB.  192 KB of chunk tables instead of 220 KB: 16 reads 11.3 -> 9.9 ms, 17 reads
     // 16.8 -> 13.4 ms per 592 draws (the integer models lose 1-2 % with it and keep 220 KB)
-    if (kind == LDPGTA_DISTANT_ADMIXTURE && n >= 5 && !p->etab) budget_kb = std::min<size_t>(budget_kb, 192);
+    if (kind == LDPGTA_DISTANT_ADMIXTURE && c->G > 2 && n >= 5 && !p->etab) budget_kb = std::min<size_t>(budget_kb, 192);
     if (const char *e = getenv("LDPGTA_PLAN_KB")) budget_kb = (size_t)atoi(e);
     const size_t cap = std::min<size_t>((size_t)c->max_smem_optin, budget_kb * 1024 + (p->etab ? (size_t)8 << n : 0));
     if (fixed + 2 * per_word > (size_t)c->max_smem_optin)
@@ -97,7 +98,7 @@ static int launch_general_t(ldpgta_ctx *c, GeneralArgs a, const GeneralPlan &p)
         a.table_stride = stride;
     }
     a.etab_scratch = nullptr; a.etab_stride = 0;
-    if (a.kind == LDPGTA_DISTANT_ADMIXTURE && a.n >= 5 && !p.etab) {
+    if (a.kind == LDPGTA_DISTANT_ADMIXTURE && a.pv.G > 2 && a.n >= 5 && !p.etab) {
         // e(S) as doubles in a global slice per resident CTA (L2 / HBM): still far cheaper than forming it at every use
         const size_t stride = (size_t)1 << a.n, need = stride * 8 * blocks;
         if (c->etab_scratch_bytes < need) {
@@ -185,17 +186,17 @@ int launch_general(ldpgta_ctx *c, GeneralArgs a)
         if (int rc = ensure_hi_terms(c, h)) return rc;
         a.terms = reinterpret_cast<const u64 *>(c->hi_terms[h]);
         a.n_terms = c->n_hi_terms[h];
-        for (int g = 0; g < c->G; ++g) a.wide |= c->nhap[g] > (a.kind == LDPGTA_RECENT_ADMIXTURE ? 11585u : 16383u);   // 32-bit convolution sums: 16 (recent: 32) products of two counts
+        for (int g = 0; g < c->G; ++g) a.wide |= c->nhap[g] > (c->G == 2 ? 11585u : 16383u);   // 32-bit convolution sums: 16 (two groups: 32) products of two counts
     }
     // integer models from 13 reads (enough runs to balance the block): the colourings come in runs that share the X row, as
     // long as the 32-bit sums hold 2^bits convolutions -- 16 (recent admixture: 32) products of two counts each.  Measured
     // against single colourings (LDPGTA_PLAN_NO_RUNS=1), 5008 haplotypes: 13..18 reads +3, +4, +7, +10, +15, +16 % draws/s.
     a.runs = 0;
     static const bool no_runs = getenv("LDPGTA_PLAN_NO_RUNS") != nullptr;
-    if (a.n >= 13 && a.kind != LDPGTA_DISTANT_ADMIXTURE && !a.wide && !no_runs) {
+    if (a.n >= 13 && (a.kind != LDPGTA_DISTANT_ADMIXTURE || c->G == 2) && c->G <= 2 && !a.wide && !no_runs) {
         uint64_t nmax = 0;
         for (int g = 0; g < c->G; ++g) nmax = std::max<uint64_t>(nmax, c->nhap[g]);
-        const uint64_t per_conv = (a.kind == LDPGTA_RECENT_ADMIXTURE ? 32u : 16u) * nmax * nmax;
+        const uint64_t per_conv = (c->G == 2 ? 32u : 16u) * nmax * nmax;
         int bits = 0;
         const int want = a.n >= 15 ? 3 : 2;                      // runs of 4 keep the few colourings of 13-14 reads balanced
         while (bits < want && (per_conv << (bits + 1)) <= 0xffffffffull) ++bits;

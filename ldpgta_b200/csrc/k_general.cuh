@@ -68,7 +68,7 @@ __host__ __device__ inline GeneralSmem general_smem_layout(const PanelView &pv, 
     off = (off + 15) & ~15;
     s.etab = -1;
     if (etab) { s.etab = off; off += 8 << n; }           // e(S) of the distant model, one double per subset
-    s.red = off; off += 16 * 12 * 8;
+    s.red = off; off += 16 * 22 * 8;                     // block sums: up to 22 values per warp (two-group distant model)
     s.total = off;
     return s;
 }
@@ -455,8 +455,27 @@ __global__ void __launch_bounds__(512, 1) k_general(const GeneralArgs a)
                 finish_recent(scale, (double)a.pv.nhap[0], (double)a.pv.nhap[1], F[full], Gt[full], (double)v[0], (double)v[1], (double)v[2],
                               (double)v[3], u128_to_double(join_u128(v + 4)), u128_to_double(join_u128(v + 8)), res);
             }
+        } else if (G == 2 && n >= 5) {
+            // distant admixture of two groups: e(S) is linear in the two count tables, so the sums over partitions are exact
+            // integer sums (poly_general.cuh: Cubic2), scaled by powers of p_g / N_g at the end
+            const CT *F = ftab, *Gt = ftab + NS;
+            Cubic2 c;
+            if (a.wide) poly_distant2_blocked<CT, u64>(F, Gt, n, a.terms, a.n_terms, tid, T, c);
+            else poly_distant2_blocked<CT, uint32_t>(F, Gt, n, a.terms, a.n_terms, tid, T, c, a.runs != 0);
+            u64 v[22];
+            v[0] = c.ff; v[1] = c.gg; v[2] = c.fg; v[3] = c.ff_sph; v[4] = c.gg_sph; v[5] = c.fg_sph;
+            split_u128(c.s0, v + 6); split_u128(c.s1, v + 10); split_u128(c.s2, v + 14); split_u128(c.s3, v + 18);
+            block_sum_u64<22>(v, red);
+            if (tid == 0) {
+                const double c0 = a.pv.coef[0], c1 = a.pv.coef[1], N0 = (double)a.pv.nhap[0], N1 = (double)a.pv.nhap[1];
+                const double Ef = 0.0 + c0 * (double)F[full] / N0 + c1 * (double)Gt[full] / N1;      // as DISTANT_ADMIXTURE_MODELS.py:136-139
+                finish_distant2(scale, c0 / N0, c1 / N1, Ef, (double)v[0], (double)v[1], (double)v[2], (double)v[3], (double)v[4], (double)v[5],
+                                u128_to_double(join_u128(v + 6)), u128_to_double(join_u128(v + 10)), u128_to_double(join_u128(v + 14)),
+                                u128_to_double(join_u128(v + 18)), res);
+            }
         } else {
-            // distant admixture: e(S) = sum_g p_g * cnt_g(S) / N_g (DISTANT_ADMIXTURE_MODELS.py:136-139)
+            // distant admixture of three or more groups (and forced 2..4 reads): e(S) = sum_g p_g * cnt_g(S) / N_g
+            // (DISTANT_ADMIXTURE_MODELS.py:136-139)
             double cg[MAXG];
             for (int g = 0; g < G; ++g) cg[g] = a.pv.coef[g];
             auto E = [&](uint32_t S) {

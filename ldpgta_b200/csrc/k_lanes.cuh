@@ -34,7 +34,7 @@ struct LanesSmem {           // per-warp byte offsets / sizes
 };
 
 template <int NR, int KL, typename CT>
-__host__ __device__ inline LanesSmem lanes_smem_layout(const PanelView &pv, bool distant)
+__host__ __device__ inline LanesSmem lanes_smem_layout(const PanelView &pv, bool etab)       // etab: room for e(S) of a distant model with three or more groups
 {
     constexpr int DPW = 32 >> KL;
     LanesSmem s;
@@ -52,7 +52,7 @@ __host__ __device__ inline LanesSmem lanes_smem_layout(const PanelView &pv, bool
     off = (off + 63) & ~63;
     off = (off + 15) & ~15;
     s.etab = -1;
-    if (distant) { s.etab = off; off += DPW * (8 << NR); }
+    if (etab) { s.etab = off; off += DPW * (8 << NR); }
     off += 16;                                            // the warp's mbarrier
     s.per_warp = (off + 127) & ~127;
     return s;
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(32 * LanesWarps<NR>::MAX, 1) k_lanes(const __g
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), nwarps = blockDim.x >> 5;
     const int lo = lane & (LPD - 1), dgrp = lane / LPD;
     const int G = a.pv.G;
-    const LanesSmem lay = lanes_smem_layout<NR, KL, CT>(a.pv, a.kind == LDPGTA_DISTANT_ADMIXTURE);
+    const LanesSmem lay = lanes_smem_layout<NR, KL, CT>(a.pv, a.kind == LDPGTA_DISTANT_ADMIXTURE && a.pv.G > 2);
     unsigned char *wbase = smem + (size_t)warp * lay.per_warp;
     u64 *bufs = reinterpret_cast<u64 *>(wbase);
     CT *ftab = reinterpret_cast<CT *>(wbase + lay.ftab) + (size_t)dgrp * (G << NR);
@@ -249,8 +249,26 @@ __global__ void __launch_bounds__(32 * LanesWarps<NR>::MAX, 1) k_lanes(const __g
             if (lo == 0)
                 finish_recent(scale, (double)a.pv.nhap[0], (double)a.pv.nhap[1], F[NS - 1], Gt[NS - 1], (double)v[0], (double)v[1], (double)v[2],
                               (double)v[3], u128_to_double(join_u128(v + 4)), u128_to_double(join_u128(v + 8)), res);
+        } else if (G == 2) {
+            // distant admixture of two groups as exact integer sums (poly_general.cuh: Cubic2)
+            const CT *F = ftab, *Gt = ftab + NS;
+            Cubic2 c;
+            if (a.wide) poly_distant2_blocked<CT, u64>(F, Gt, NR, a.terms, a.n_terms, lo, LPD, c);
+            else poly_distant2_blocked<CT, uint32_t>(F, Gt, NR, a.terms, a.n_terms, lo, LPD, c);
+            u64 v[22];
+            v[0] = c.ff; v[1] = c.gg; v[2] = c.fg; v[3] = c.ff_sph; v[4] = c.gg_sph; v[5] = c.fg_sph;
+            split_u128(c.s0, v + 6); split_u128(c.s1, v + 10); split_u128(c.s2, v + 14); split_u128(c.s3, v + 18);
+#pragma unroll
+            for (int k = 0; k < 22; ++k) v[k] = group_sum_u64<LPD>(v[k]);
+            if (lo == 0) {
+                const double c0 = a.pv.coef[0], c1 = a.pv.coef[1], N0 = (double)a.pv.nhap[0], N1 = (double)a.pv.nhap[1];
+                const double Ef = 0.0 + c0 * (double)F[NS - 1] / N0 + c1 * (double)Gt[NS - 1] / N1;
+                finish_distant2(scale, c0 / N0, c1 / N1, Ef, (double)v[0], (double)v[1], (double)v[2], (double)v[3], (double)v[4], (double)v[5],
+                                u128_to_double(join_u128(v + 6)), u128_to_double(join_u128(v + 10)), u128_to_double(join_u128(v + 14)),
+                                u128_to_double(join_u128(v + 18)), res);
+            }
         } else {
-            // e(S) = sum_g p_g * cnt_g(S) / N_g (DISTANT_ADMIXTURE_MODELS.py:136-139), tabulated once per draw
+            // three or more groups: e(S) = sum_g p_g * cnt_g(S) / N_g (DISTANT_ADMIXTURE_MODELS.py:136-139), tabulated once per draw
             double *etab = reinterpret_cast<double *>(wbase + lay.etab) + ((size_t)dgrp << NR);
             distant_fill_etab<CT>(ftab, a.pv, NR, etab, lo, LPD);
             __syncwarp();

@@ -12,7 +12,7 @@ static int launch_lanes_ct(ldpgta_ctx *c, const GeneralArgs &a)
 {
     constexpr int DPW = 32 >> KL;
     static const int max_warps = [] { const char *e = getenv("LDPGTA_LANES_WARPS"); return e ? std::max(1, atoi(e)) : 12; }();
-    const LanesSmem lay = lanes_smem_layout<NR, KL, CT>(a.pv, a.kind == LDPGTA_DISTANT_ADMIXTURE);
+    const LanesSmem lay = lanes_smem_layout<NR, KL, CT>(a.pv, a.kind == LDPGTA_DISTANT_ADMIXTURE && a.pv.G > 2);
     const int fit = (c->max_smem_optin - 1024) / lay.per_warp;
     if (fit < 2) return 1;                                   // rows too long for two warps per SM: the table kernel takes it
     const int nwarps = std::min(std::min(max_warps, LanesWarps<NR>::MAX), fit);
@@ -43,7 +43,9 @@ int launch_lanes(ldpgta_ctx *c, GeneralArgs a)
     // measured against the table kernel (tools/sweep_sizes.sh with LDPGTA_LANES_MAXN): ahead up to 12 reads for one group and
     // for recent admixture, up to 10 for distant admixture, whose float64 polynomial is too long for one warp beyond that
     static const int max_n_env = [] { const char *e = getenv("LDPGTA_LANES_MAXN"); return e ? atoi(e) : 0; }();      // tuning override
-    const int max_n = max_n_env ? std::min(max_n_env, 12) : a.kind == LDPGTA_DISTANT_ADMIXTURE ? 10 : 12;
+    // (two-group distant admixture runs the integer polynomial of recent admixture: poly_general.cuh, Cubic2)
+    const bool float_poly = a.kind == LDPGTA_DISTANT_ADMIXTURE && c->G > 2;
+    const int max_n = max_n_env ? std::min(max_n_env, 12) : float_poly ? 10 : 12;
     if (a.n < 5 || a.n > max_n) return 1;
     for (int g = 0; g < c->G; ++g)
         if (c->wp[g] * 64 > 65535) return 1;           // 16-bit packed partial counts, row bytes of one bulk copy
@@ -52,7 +54,7 @@ int launch_lanes(ldpgta_ctx *c, GeneralArgs a)
     a.terms = reinterpret_cast<const u64 *>(c->hi_terms[h]);
     a.n_terms = c->n_hi_terms[h];
     a.wide = 0;
-    for (int g = 0; g < c->G; ++g) a.wide |= c->nhap[g] > (a.kind == LDPGTA_RECENT_ADMIXTURE ? 11585u : 16383u);   // 32-bit convolution sums: 16 (recent: 32) products of two counts
+    for (int g = 0; g < c->G; ++g) a.wide |= c->nhap[g] > (c->G == 2 ? 11585u : 16383u);   // 32-bit convolution sums: 16 (two groups: 32) products of two counts
     a.kl = a.kh = a.wc = 0; a.etab = 0; a.etab_scratch = nullptr; a.etab_stride = 0;
     a.table_scratch = nullptr; a.table_stride = 0;
     static const int alt = [] { const char *e = getenv("LDPGTA_LANES_ALT"); return e ? atoi(e) : 0; }();     // tuning: the other low/high split (measured slower: tools/sweep_sizes.sh)

@@ -52,4 +52,16 @@ __device__ __forceinline__ void finish_distant(const PolyScale &s, double Ef, do
     res[3] = Ef / s.p3n1 + 2.0 * two / s.p3n1 + 2.0 * three / s.p3n1;
 }
 
+// two-group distant admixture from the integer sums of poly_distant2_blocked (poly_general.cuh); Ef = e(full)
+__device__ __forceinline__ void finish_distant2(const PolyScale &s, double alpha, double beta, double Ef, double ff, double gg, double fg,
+                                                double ff_sph, double gg_sph, double fg_sph, double s0, double s1, double s2, double s3,
+                                                double *res)
+{
+    const double a2 = alpha * alpha, ab = alpha * beta, b2 = beta * beta;
+    const double two = a2 * ff + ab * fg + b2 * gg;
+    const double two_sph = a2 * ff_sph + ab * fg_sph + b2 * gg_sph;
+    const double three = a2 * alpha * s0 + a2 * beta * s1 + alpha * b2 * s2 + b2 * beta * s3;
+    finish_distant(s, Ef, two, two_sph, three, res);
+}
+
 }  // namespace ldpgta

@@ -183,46 +183,52 @@ __device__ void poly_homog_blocked(const CT *F, int n, const u64 *terms, int64_t
 }
 
 // ---- recent admixture: F = group 0, G = group 1 ------------------------------------------------
-template <typename CT, typename ACC, int SPACE, bool RUNS>
+// FULL: also the pure triples (S0 = FFF, S3 = GGG) and the SPH-weighted ff and gg, for the two-group distant model; ffg = S1
+// (two factors from F), ggf = S2
+template <typename CT, typename ACC, int SPACE, bool RUNS, bool FULL>
 __device__ __forceinline__ void poly_recent_impl(const CT *F, const CT *G, int n, const u64 *terms, int64_t n_terms, int tid,
-                                                 int T, u64 &ff_out, u64 &gg_out, u64 &fg_out, u64 &fg_sph_out, u128 &ffg_out,
-                                                 u128 &ggf_out)
+                                                 int T, Cubic2 &out)
 {
     const int h = n - 5;
     const uint32_t top_row = 1u << h, usub = (1u << (n - 1)) - 1u, top = 1u << (n - 1);
-    u64 ff = 0, gg = 0, fg = 0, fg_sph = 0;                      // local accumulators (see poly_homog_blocked)
-    u128 ffg = 0, ggf = 0;
+    u64 ff = 0, gg = 0, fg = 0, fg_sph = 0, ff_sph = 0, gg_sph = 0;   // local accumulators (see poly_homog_blocked)
+    u128 ffg = 0, ggf = 0, fff = 0, ggg = 0;
     for (uint32_t a = tid; a < usub; a += T) {
         const uint32_t A = top | a, R = usub ^ a;
         const u64 fa = F[A], ga = G[A], fr = F[R], gr = G[R];
         const u64 cross = fa * gr + ga * fr;
         const int pa = __popc(a);
+        const u64 w = (2ull << pa) + (1ull << (n - 1 - pa));
         ff += fa * fr;
         gg += ga * gr;
         fg += cross;
-        fg_sph += cross * ((2ull << pa) + (1ull << (n - 1 - pa)));
+        fg_sph += cross * w;
+        if (FULL) { ff_sph += fa * fr * w; gg_sph += ga * gr * w; }
     }
     auto triple = [&](uint32_t ra, uint32_t rb, uint32_t rc, bool special) {
         // unordered {A,B,C}, A owns the last read: two parents from F and one from G, and vice versa.  Only one Y row and
         // one Z row are live at a time (a row is 16 registers; all six at once do not fit 128 registers with the products).
         uint32_t Xf[16], Xg[16], Y[16], Z[16];
         ACC c[16];
-        u64 s_ffg, s_ggf;
+        u64 s_ffg, s_ggf, s_fff = 0, s_ggg = 0;
         load_row16<CT, SPACE>(F, top_row + ra, Xf); load_row16<CT, SPACE>(G, top_row + ra, Xg);
         // the two mixed convolutions Yf*Zg and Yg*Zf enter both sums with the same partner (Xf for ffg, Xg for ggf), so they
         // are accumulated into one array and dotted once: 4 convolutions + 4 dot products per colouring instead of 4 + 6
         // (two more row loads; 32 * max(F) * max(G) stays below 2^32 whenever ACC is 32-bit: groups of at most 11585)
         load_row16<CT, SPACE>(F, rb, Y); load_row16<CT, SPACE>(F, rc, Z);
         conv16<ACC>(Y, Z, c); s_ffg = dot16<ACC>(Xg, c);                                          // Yf * Zf
+        if (FULL) s_fff = dot16<ACC>(Xf, c);
         load_row16<CT, SPACE>(G, rc, Z);
         conv16<ACC>(Y, Z, c);                                                                     // Yf * Zg
         load_row16<CT, SPACE>(G, rb, Y); load_row16<CT, SPACE>(F, rc, Z);
         conv16_add<ACC>(Y, Z, c); s_ffg += dot16<ACC>(Xf, c); s_ggf = dot16<ACC>(Xg, c);          // + Yg * Zf
         load_row16<CT, SPACE>(G, rc, Z);
         conv16<ACC>(Y, Z, c); s_ggf += dot16<ACC>(Xf, c);                                         // Yg * Zg
-        if (special) { s_ffg >>= 1; s_ggf >>= 1; }
+        if (FULL) s_ggg = dot16<ACC>(Xg, c);
+        if (special) { s_ffg >>= 1; s_ggf >>= 1; s_fff >>= 1; s_ggg >>= 1; }
         ffg += s_ffg;
         ggf += s_ggf;
+        if (FULL) { fff += s_fff; ggg += s_ggg; }
     };
     u64 t_next = tid < n_terms ? terms[tid] : 0;
     if (RUNS) {
@@ -258,6 +264,7 @@ __device__ __forceinline__ void poly_recent_impl(const CT *F, const CT *G, int n
             ffg += dot16<ACC>(Y, cmix);
             ggf += dot16<ACC>(Z, cmix);
             ggf += dot16<ACC>(Y, cgg);
+            if (FULL) { fff += dot16<ACC>(Y, cff); ggg += dot16<ACC>(Z, cgg); }
         }
     } else
     for (int64_t e = tid; e < n_terms; e += T) {
@@ -266,23 +273,40 @@ __device__ __forceinline__ void poly_recent_impl(const CT *F, const CT *G, int n
         triple((uint32_t)(t & 0xffffu), (uint32_t)(t >> 16) & 0xffffu, (uint32_t)(t >> 32) & 0xffffu, false);
     }
     if (tid == 0) triple(top_row - 1u, 0u, 0u, true);
-    ff_out = ff; gg_out = gg; fg_out = fg; fg_sph_out = fg_sph; ffg_out = ffg; ggf_out = ggf;
+    out.ff = ff; out.gg = gg; out.fg = fg; out.fg_sph = fg_sph; out.ff_sph = ff_sph; out.gg_sph = gg_sph;
+    out.s0 = fff; out.s1 = ffg; out.s2 = ggf; out.s3 = ggg;
+}
+
+template <typename CT, typename ACC, bool FULL>
+__device__ __forceinline__ void poly_recent_dispatch(const CT *F, const CT *G, int n, const u64 *terms, int64_t n_terms, int tid, int T,
+                                                     Cubic2 &out, bool runs)
+{
+    const bool sh = __isShared(F) && __isShared(G);
+    if constexpr (sizeof(ACC) == 4) {
+        if (runs) {
+            if (sh) poly_recent_impl<CT, ACC, 1, true, FULL>(F, G, n, terms, n_terms, tid, T, out);
+            else poly_recent_impl<CT, ACC, 0, true, FULL>(F, G, n, terms, n_terms, tid, T, out);
+            return;
+        }
+    }
+    if (sh) poly_recent_impl<CT, ACC, 1, false, FULL>(F, G, n, terms, n_terms, tid, T, out);
+    else poly_recent_impl<CT, ACC, 0, false, FULL>(F, G, n, terms, n_terms, tid, T, out);
 }
 
 template <typename CT, typename ACC>
 __device__ void poly_recent_blocked(const CT *F, const CT *G, int n, const u64 *terms, int64_t n_terms, int tid, int T,
                                     u64 &ff, u64 &gg, u64 &fg, u64 &fg_sph, u128 &ffg, u128 &ggf, bool runs)
 {
-    const bool sh = __isShared(F) && __isShared(G);
-    if constexpr (sizeof(ACC) == 4) {
-        if (runs) {
-            if (sh) poly_recent_impl<CT, ACC, 1, true>(F, G, n, terms, n_terms, tid, T, ff, gg, fg, fg_sph, ffg, ggf);
-            else poly_recent_impl<CT, ACC, 0, true>(F, G, n, terms, n_terms, tid, T, ff, gg, fg, fg_sph, ffg, ggf);
-            return;
-        }
-    }
-    if (sh) poly_recent_impl<CT, ACC, 1, false>(F, G, n, terms, n_terms, tid, T, ff, gg, fg, fg_sph, ffg, ggf);
-    else poly_recent_impl<CT, ACC, 0, false>(F, G, n, terms, n_terms, tid, T, ff, gg, fg, fg_sph, ffg, ggf);
+    Cubic2 c;
+    poly_recent_dispatch<CT, ACC, false>(F, G, n, terms, n_terms, tid, T, c, runs);
+    ff = c.ff; gg = c.gg; fg = c.fg; fg_sph = c.fg_sph; ffg = c.s1; ggf = c.s2;
+}
+
+template <typename CT, typename ACC>
+__device__ void poly_distant2_blocked(const CT *F, const CT *G, int n, const u64 *terms, int64_t n_terms, int tid, int T, Cubic2 &out,
+                                      bool runs)
+{
+    poly_recent_dispatch<CT, ACC, true>(F, G, n, terms, n_terms, tid, T, out, runs);
 }
 
 // ---- distant admixture from a tabulated e(S) ------------------------------------------------------
@@ -364,6 +388,8 @@ __device__ void poly_distant_etab(const double *etab, int n, const u64 *terms, i
     template __device__ void poly_homog_blocked<CT, u64>(const CT *, int, const u64 *, int64_t, int, int, u64 &, u64 &, u128 &, bool);      \
     template __device__ void poly_recent_blocked<CT, uint32_t>(const CT *, const CT *, int, const u64 *, int64_t, int, int, u64 &, u64 &, u64 &, u64 &, u128 &, u128 &, bool); \
     template __device__ void poly_recent_blocked<CT, u64>(const CT *, const CT *, int, const u64 *, int64_t, int, int, u64 &, u64 &, u64 &, u64 &, u128 &, u128 &, bool);      \
+    template __device__ void poly_distant2_blocked<CT, uint32_t>(const CT *, const CT *, int, const u64 *, int64_t, int, int, Cubic2 &, bool); \
+    template __device__ void poly_distant2_blocked<CT, u64>(const CT *, const CT *, int, const u64 *, int64_t, int, int, Cubic2 &, bool);      \
     template __device__ void distant_fill_etab<CT>(const CT *, const PanelView &, int, double *, int, int, bool);
 LDPGTA_INST(uint16_t)
 LDPGTA_INST(uint32_t)

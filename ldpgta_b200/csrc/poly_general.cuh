@@ -36,7 +36,22 @@ __device__ void poly_homog_blocked(const CT *F, int n, const u64 *terms, int64_t
 template <typename CT, typename ACC>
 __device__ void poly_recent_blocked(const CT *F, const CT *G, int n, const u64 *terms, int64_t n_terms, int tid, int T,
                                     u64 &ff, u64 &gg, u64 &fg, u64 &fg_sph, u128 &ffg, u128 &ggf, bool runs = false);
-// Distant admixture with the effective frequencies tabulated once per draw: etab[S] = sum_g p_g * cnt_g(S) / N_g
+// Distant admixture of TWO groups as an integer form.  e(S) = alpha F[S] + beta G[S] (alpha = p_0 / N_0, beta = p_1 / N_1) is
+// linear in the two count tables, so the sums of products of e over the partitions expand into the exact integer sums that the
+// recent-admixture routine already forms, plus the two pure ones:
+//     sum e_A e_B e_C = alpha^3 S0 + alpha^2 beta S1 + alpha beta^2 S2 + beta^3 S3,   S_k = triples with k factors from G
+//     sum e_A e_R     = alpha^2 ff + alpha beta fg + beta^2 gg                       (and the same with the SPH weights)
+// -- no e(S) table, no float64 convolutions (they ran at a quarter of the IMAD rate and, from 15 reads, out of L2), and the
+// rounding of 3^(n-1)/2 floating-point additions is replaced by four conversions.  Same arguments as poly_recent_blocked.
+struct Cubic2 {
+    u64 ff, gg, fg, ff_sph, gg_sph, fg_sph;
+    u128 s0, s1, s2, s3;
+};
+template <typename CT, typename ACC>
+__device__ void poly_distant2_blocked(const CT *F, const CT *G, int n, const u64 *terms, int64_t n_terms, int tid, int T, Cubic2 &out,
+                                      bool runs = false);
+
+// Distant admixture of three or more groups, with the effective frequencies tabulated once per draw: etab[S] = sum_g p_g * cnt_g(S) / N_g
 // (DISTANT_ADMIXTURE_MODELS.py:136-139) for all 2^n subsets, so that the polynomial reads doubles instead of redoing the
 // conversions and divisions at every use (an entry is used ~1.5^n times).  fill: threads tid of T, the caller
 // synchronises them before poly_distant_etab.
