@@ -172,19 +172,17 @@ struct SmallModel {
         for (int s = 1; s < NS; ++s) { fr[s] = __ldg(norm0 + ca[s]); gr[s] = __ldg(norm1 + cb[s]); }
         closed_recent<NR>(fr, gr, res);
     }
-    // distant admixture with two groups: e(S) = p_0 cnt_0 / N_0 + p_1 cnt_1 / N_1 in group order (the operations of fold())
+    // distant admixture with two groups: e(S) = p_0 cnt_0 / N_0 + p_1 cnt_1 / N_1 (DISTANT_ADMIXTURE_MODELS.py:136-139) as
+    // alpha cnt_0 + beta cnt_1 with alpha = p_0 / N_0, beta = p_1 / N_1: two float64 divisions per draw instead of two per
+    // subset (30 at four reads: 0.587 -> 0.508 ms per configs[1]-sized step), the scaling the integer form of the larger draws
+    // uses too (poly_general.cuh: Cubic2); e(S) differs from the reference's rounding by at most 2 ulp
     static __device__ __forceinline__ void finish_distant2(const PanelView &pv, const uint32_t *ca, const uint32_t *cb, double *res)
     {
-        const double nh0 = (double)pv.nhap[0], p0 = pv.coef[0], nh1 = (double)pv.nhap[1], p1 = pv.coef[1];
+        const double alpha = pv.coef[0] / (double)pv.nhap[0], beta = pv.coef[1] / (double)pv.nhap[1];
         double e[NS];
         e[0] = 0.0;
 #pragma unroll
-        for (int s = 1; s < NS; ++s) {
-            double v = 0.0;
-            v = v + p0 * (double)ca[s] / nh0;
-            v = v + p1 * (double)cb[s] / nh1;
-            e[s] = v;
-        }
+        for (int s = 1; s < NS; ++s) e[s] = alpha * (double)ca[s] + beta * (double)cb[s];
         closed_single<NR>(e, res);
     }
     // returns true when res[] is final

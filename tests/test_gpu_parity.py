@@ -228,6 +228,12 @@ def test_recent_admixture_accumulator_width(sizes):
             got = eng.likelihoods_batch(L.RECENT_ADMIXTURE, idx, off)
             want = C.batch(_common_width(rows), list(sizes), idx, off, 1)
             assert max_rel(got, want) < LIK_TOL, (sizes, n, max_rel(got, want))
+            if n != 5:
+                # distant admixture of two groups runs the same integer convolutions (poly_general.cuh: Cubic2)
+                prop = [0.35, 0.65]
+                got = eng.likelihoods_batch(L.DISTANT_ADMIXTURE, idx, off, proportions=prop)
+                want = C.batch(_common_width(rows), list(sizes), idx, off, 2, prop)
+                assert max_rel(got, want) < LIK_TOL, ('distant', sizes, n, max_rel(got, want))
 
 
 @pytest.mark.parametrize('model,sizes', [('homogeneous', (5792,)), ('homogeneous', (5793,)), ('homogeneous', (8191,)),
@@ -253,6 +259,11 @@ def test_polynomial_run_lengths(model, sizes):
             got = eng.likelihoods_batch(kind, idx, off)
             want = C.batch(_common_width(rows), list(sizes), idx, off, code)
             assert max_rel(got, want) < LIK_TOL, (model, sizes, n, max_rel(got, want))
+            if model == 'recent':                                 # distant admixture of two groups shares the run lists
+                prop = [0.8, 0.2]
+                got = eng.likelihoods_batch(L.DISTANT_ADMIXTURE, idx, off, proportions=prop)
+                want = C.batch(_common_width(rows), list(sizes), idx, off, 2, prop)
+                assert max_rel(got, want) < LIK_TOL, ('distant', sizes, n, max_rel(got, want))
 
 
 def _common_width(rows):
