@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(32 * LanesWarps<NR>::MAX, 1) k_lanes(const __g
             u64 two = 0, two_sph = 0;
             u128 three = 0;
             if (a.wide) poly_homog_blocked<CT, u64>(ftab, NR, a.terms, a.n_terms, lo, LPD, two, two_sph, three);
-            else poly_homog_blocked<CT, uint32_t>(ftab, NR, a.terms, a.n_terms, lo, LPD, two, two_sph, three);
+            else poly_homog_blocked<CT, uint32_t>(ftab, NR, a.terms, a.n_terms, lo, LPD, two, two_sph, three, a.runs != 0);
             u64 v[6];
             v[0] = two; v[1] = two_sph;
             split_u128(three, v + 2);
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(32 * LanesWarps<NR>::MAX, 1) k_lanes(const __g
             u64 ff = 0, gg = 0, fg = 0, fg_sph = 0;
             u128 ffg = 0, ggf = 0;
             if (a.wide) poly_recent_blocked<CT, u64>(F, Gt, NR, a.terms, a.n_terms, lo, LPD, ff, gg, fg, fg_sph, ffg, ggf);
-            else poly_recent_blocked<CT, uint32_t>(F, Gt, NR, a.terms, a.n_terms, lo, LPD, ff, gg, fg, fg_sph, ffg, ggf);
+            else poly_recent_blocked<CT, uint32_t>(F, Gt, NR, a.terms, a.n_terms, lo, LPD, ff, gg, fg, fg_sph, ffg, ggf, a.runs != 0);
             u64 v[12];
             v[0] = ff; v[1] = gg; v[2] = fg; v[3] = fg_sph;
             split_u128(ffg, v + 4);
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(32 * LanesWarps<NR>::MAX, 1) k_lanes(const __g
             const CT *F = ftab, *Gt = ftab + NS;
             Cubic2 c;
             if (a.wide) poly_distant2_blocked<CT, u64>(F, Gt, NR, a.terms, a.n_terms, lo, LPD, c);
-            else poly_distant2_blocked<CT, uint32_t>(F, Gt, NR, a.terms, a.n_terms, lo, LPD, c);
+            else poly_distant2_blocked<CT, uint32_t>(F, Gt, NR, a.terms, a.n_terms, lo, LPD, c, a.runs != 0);
             u64 v[22];
             v[0] = c.ff; v[1] = c.gg; v[2] = c.fg; v[3] = c.ff_sph; v[4] = c.gg_sph; v[5] = c.fg_sph;
             split_u128(c.s0, v + 6); split_u128(c.s1, v + 10); split_u128(c.s2, v + 14); split_u128(c.s3, v + 18);

@@ -55,6 +55,23 @@ int launch_lanes(ldpgta_ctx *c, GeneralArgs a)
     a.n_terms = c->n_hi_terms[h];
     a.wide = 0;
     for (int g = 0; g < c->G; ++g) a.wide |= c->nhap[g] > (c->G == 2 ? 11585u : 16383u);   // 32-bit convolution sums: 16 (two groups: 32) products of two counts
+    // 12 reads: the colourings in runs of four that share the X row (poly_general.cuh), when the 32-bit convolution sums hold
+    // four convolutions (LDPGTA_PLAN_NO_RUNS=1 for comparison: +1.5 % one group, +3 % two groups; at 10 and 11 reads the 32
+    // lanes of a draw have too few runs to share and lose 3-8 %)
+    a.runs = 0;
+    if (a.n >= 12 && !float_poly && !a.wide && !getenv("LDPGTA_PLAN_NO_RUNS")) {
+        uint64_t nmax = 0;
+        for (int g = 0; g < c->G; ++g) nmax = std::max<uint64_t>(nmax, c->nhap[g]);
+        const uint64_t per_conv = (c->G == 2 ? 32u : 16u) * nmax * nmax;
+        int bits = 0;
+        while (bits < 2 && (per_conv << (bits + 1)) <= 0xffffffffull) ++bits;
+        if (bits >= 1) {
+            if (int rc = ensure_run_terms(c, h, bits)) return rc;
+            a.terms = reinterpret_cast<const u64 *>(c->run_terms[h][bits]);
+            a.n_terms = c->n_run_terms[h][bits];
+            a.runs = 1;
+        }
+    }
     a.kl = a.kh = a.wc = 0; a.etab = 0; a.etab_scratch = nullptr; a.etab_stride = 0;
     a.table_scratch = nullptr; a.table_stride = 0;
     static const int alt = [] { const char *e = getenv("LDPGTA_LANES_ALT"); return e ? atoi(e) : 0; }();     // tuning: the other low/high split (measured slower: tools/sweep_sizes.sh)
