@@ -10,7 +10,7 @@ median of the steps), draws/s, and three rooflines:
          peak) PLUS the time of the partition polynomial's multiply-adds against the measured IMAD.32 / DFMA peaks -- the
          two phases run one after the other inside a CTA.  Multiply-adds per draw: (3^(n-5) - 1) / 2 colourings x
          (81 + 2 * 16 / R) for one population (conv16, and a 64-bit dot16 per run of R colourings that share the X row:
-         R = 8 from 15 reads, 4 at 13-14, 1 below), x (4 * 81 + 4 * 32 / R) for recent admixture, x (4 * 81 + 6 * 32 / R)
+         R = 8 from 15 reads, 4 at 12-14, 1 below), x (4 * 81 + 4 * 32 / R) for recent admixture, x (4 * 81 + 6 * 32 / R)
          for distant admixture of two groups (the same integer convolutions, six dot products); see csrc/poly_general.cu.
   hbm    algorithmic bytes (n * W * 8 * G + 4 n + 32 per draw) against the measured copy peak (matters for 2..5 reads)
 
@@ -77,7 +77,7 @@ def main():
         t_count = ops * (4.0 / 3.0) / popc32                 # carry-save: three words, two POPC.64 = four POPC.32
         if n >= 5:
             terms = (3 ** (n - 5) - 1) / 2 + 1
-            run = 8 if n >= 15 else 4 if n >= 13 else 1
+            run = 8 if n >= 15 else 4 if n >= 12 else 1
             t_poly = terms * (81 + 32 / run if model == 'homogeneous' else 4 * 81 + 4 * 32 / run if model == 'recent' else 4 * 81 + 6 * 32 / run) / imad32
         else:
             t_poly = 0.0
