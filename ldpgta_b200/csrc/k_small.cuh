@@ -296,6 +296,12 @@ __global__ void __launch_bounds__(SmallPipe<NR, WPL>::NWARPS * 32, 1) k_small(co
         const int wp = a.pv.wp[g];
         const uint32_t row_bytes = (uint32_t)wp * 8u;
         uint32_t pc = 0;
+#ifdef LDPGTA_SMALL_COMPUTE_ONLY
+        // measurement build (tools/gather_roof.sh): no copies at all, the arithmetic runs on whatever the buffers hold
+        if (lane == 0) mbar_arrive_expect_tx(bar, 0);
+        __syncwarp();
+        return pc;
+#endif
         if (lane == 0) mbar_arrive_expect_tx(bar, row_bytes * ROWS);
         __syncwarp();
         if (NR == 4 && a.use_gather4) {
@@ -438,7 +444,16 @@ __global__ void __launch_bounds__(SmallPipe<NR, WPL>::NWARPS * 32, 1) k_small(co
             if (q + 2 < n_stages) idx_nxt = load_idx(nxt_tile);
         }
 
+#ifdef LDPGTA_SMALL_GATHER_ONLY
+        // measurement build (tools/gather_roof.sh): the staging pipeline and the register loads without the AND / POPC work --
+        // how fast the masks of this draw pattern can be gathered at all
+#pragma unroll
+        for (int i = 0; i < NR; ++i)
+#pragma unroll
+            for (int j = 0; j < SLOTS; ++j) c[3] += m[i][j].x ^ m[i][j].y ^ m[i][j].z ^ m[i][j].w;
+#else
         small_subset_counts<NR, WPL>(m, c);
+#endif
 #ifndef LDPGTA_SMALL_NO_PACKED_BATCH
         if (BATCHED && NS >= 8 && a.pv.nhap[0] <= 65535u && !a.counts_out) {
             // one-group model, counts below 2^16: two counters per register from the lane partials on -- through the
