@@ -134,17 +134,45 @@ static int time_mark(ldpgta_ctx *c)
     return 0;
 }
 
-static int evaluate_classes_inner(ldpgta_ctx *c, WindowPlan *p, int kind, const double *proportions, double *lik_out_pinned);
+// idx_up: page-locked host draws of a one-class plan that still have to go up (ldpgta_replay_stats); lim = reads in the table
+static int evaluate_classes_inner(ldpgta_ctx *c, WindowPlan *p, int kind, const double *proportions, double *lik_out_pinned,
+                                  const int32_t *idx_up, uint32_t lim);
 
-static int evaluate_classes(ldpgta_ctx *c, WindowPlan *p, int kind, const double *proportions, double *lik_out_pinned)
+static int evaluate_classes(ldpgta_ctx *c, WindowPlan *p, int kind, const double *proportions, double *lik_out_pinned,
+                            const int32_t *idx_up = nullptr, uint32_t lim = 0)
 {
     if (int rc = time_mark(c)) return rc;
-    if (int rc = evaluate_classes_inner(c, p, kind, proportions, lik_out_pinned)) return rc;
+    if (int rc = evaluate_classes_inner(c, p, kind, proportions, lik_out_pinned, idx_up, lim)) return rc;
     return time_mark(c);
 }
 
-static int evaluate_classes_inner(ldpgta_ctx *c, WindowPlan *p, int kind, const double *proportions, double *lik_out_pinned)
+static int evaluate_classes_inner(ldpgta_ctx *c, WindowPlan *p, int kind, const double *proportions, double *lik_out_pinned,
+                                  const int32_t *idx_up, uint32_t lim)
 {
+    if (idx_up && !lik_out_pinned) {
+        // host-chosen draws of one size, statistics only: the draws go up in chunks on the upload stream, chunk i + 1 under the
+        // kernel of chunk i (one copy followed by one kernel: 0.78 ms per configs[1] step, of which 0.27 ms is the 14.7 MB copy)
+        const SizeClass &k = p->classes[0];
+        static const int64_t max_chunks = [] { const char *e = getenv("LDPGTA_REPLAY_CHUNKS"); return e && atoi(e) > 0 ? (int64_t)atoi(e) : (int64_t)4; }();
+        const int64_t n_chunks = std::max<int64_t>(1, std::min<int64_t>(max_chunks, p->n_draws / 65536));
+        const int64_t per = ((p->n_draws + n_chunks - 1) / n_chunks + 63) & ~(int64_t)63;
+        if (int rc = ensure_pipeline(c, (int)n_chunks + 1)) return rc;
+        LDPGTA_CUDA(cudaEventRecord(c->ev_k[0], c->stream));                    // the upload stream starts after what is queued here (flag reset)
+        LDPGTA_CUDA(cudaStreamWaitEvent(c->s_in, c->ev_k[0], 0));
+        int ci = 0;
+        for (int64_t d0 = 0; d0 < p->n_draws; d0 += per, ++ci) {
+            const int64_t nd = std::min(per, p->n_draws - d0), cnt = nd * k.n;
+            LDPGTA_CUDA(cudaMemcpyAsync(k.d_idx + d0 * k.n, idx_up + d0 * k.n, (size_t)cnt * 4, cudaMemcpyHostToDevice, c->s_in));
+            LDPGTA_CUDA(cudaEventRecord(c->ev_in[ci], c->s_in));
+            LDPGTA_CUDA(cudaStreamWaitEvent(c->stream, c->ev_in[ci], 0));
+            k_sanitize_idx<<<(unsigned)std::min<int64_t>((cnt / 4 + 255) / 256 + 1, (int64_t)c->sm_count * 4), 256, 0, c->stream>>>(k.d_idx + d0 * k.n, cnt, lim, c->d_flag);
+            c->launches++;
+            if (int rc = run_uniform(c, kind, k.n, k.d_idx + d0 * k.n, nd, nullptr, proportions, p->d_lik + 4 * d0, nullptr, false, nullptr,
+                                     llr_fused(p) ? p->d_llr + d0 : nullptr, p->n_draws))
+                return rc;
+        }
+        return 0;
+    }
     if (p->classes.size() == 1 && lik_out_pinned && p->n_draws >= 65536) {
         // one draw size (the usual plan): chunks, the download of chunk i under the kernel of chunk i + 1
         const SizeClass &k = p->classes[0];
@@ -461,16 +489,19 @@ int ldpgta_replay_stats(ldpgta_ctx *c, int kind, const int32_t *read_idx, const 
         }
         src = h;
     }
+    // one draw size, statistics only, enough draws: the upload is chunked under the kernels (evaluate_classes)
+    const bool chunked_up = single && !lik_out && p->n_draws >= 131072;
     int64_t at = 0;
-    for (const SizeClass &k : p->classes) {
-        const int64_t cnt = k.n_draws * k.n;
-        LDPGTA_CUDA(cudaMemcpyAsync(k.d_idx, src + at, (size_t)cnt * 4, cudaMemcpyHostToDevice, c->stream));
-        k_sanitize_idx<<<(unsigned)std::min<int64_t>((cnt / 4 + 255) / 256 + 1, (int64_t)c->sm_count * 4), 256, 0, c->stream>>>(k.d_idx, cnt, lim, c->d_flag);
-        c->launches++;
-        at += cnt;
-    }
+    if (!chunked_up)
+        for (const SizeClass &k : p->classes) {
+            const int64_t cnt = k.n_draws * k.n;
+            LDPGTA_CUDA(cudaMemcpyAsync(k.d_idx, src + at, (size_t)cnt * 4, cudaMemcpyHostToDevice, c->stream));
+            k_sanitize_idx<<<(unsigned)std::min<int64_t>((cnt / 4 + 255) / 256 + 1, (int64_t)c->sm_count * 4), 256, 0, c->stream>>>(k.d_idx, cnt, lim, c->d_flag);
+            c->launches++;
+            at += cnt;
+        }
+    if (int rc = evaluate_classes(c, p, kind, proportions, lik_out ? lik_pinned : nullptr, chunked_up ? src : nullptr, lim)) return rc;
     LDPGTA_CUDA(cudaMemcpyAsync(c->h_flag, c->d_flag, 4, cudaMemcpyDeviceToHost, c->stream));
-    if (int rc = evaluate_classes(c, p, kind, proportions, lik_out ? lik_pinned : nullptr)) return rc;
     if (int rc = reduce_and_download(c, p, lik_out, lik_pinned, llr_out, window_mean_var, segment_partials, segment_stats)) return rc;
     if (*c->h_flag) return fail_bad_index(c, read_idx, p->nnz);
     return 0;
