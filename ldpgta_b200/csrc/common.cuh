@@ -225,6 +225,12 @@ struct ldpgta_ctx {
     // 2-D tensor maps over the read masks ([n_reads][wp] uint64, box = one row) for TMA gather4 (k_small, 4 reads)
     alignas(64) CUtensorMap tmap[ldpgta::MAXG];
     bool tmap_ok[ldpgta::MAXG] = {};
+    // two-group panels: both groups' masks of a read in one 80-word row (k_small_both), built on first use and dropped when
+    // either group's masks change
+    uint64_t *masks_both = nullptr;
+    size_t masks_both_bytes = 0;
+    bool both_valid = false, both_tmap_ok = false;
+    alignas(64) CUtensorMap tmap_both;
     bool masks_owned[ldpgta::MAXG] = {};
     int64_t n_reads_g[ldpgta::MAXG] = {};
     int64_t n_reads = 0;

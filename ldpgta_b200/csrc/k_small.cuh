@@ -562,6 +562,153 @@ __global__ void __launch_bounds__(SmallPipe<NR, WPL>::NWARPS * 32, 1) k_small(co
     }
 }
 
+// ---- two groups in one row --------------------------------------------------------------------------------------
+// Recent admixture and distant admixture of two groups at 4 reads per draw gathered their masks group by group: two stages
+// per tile of 320-byte rows, which the memory system serves worse than the 640-byte rows of a one-group panel of the same
+// total size (gather-only builds: 0.395 against 0.317 ms per configs[1]-sized step, tools/gather_roof.sh).  Here both groups'
+// masks of a read sit in ONE row [group 0 | group 1] of a combined table (built once on the device, small.cu: ensure_both),
+// so a tile is one stage of the one-group shape <4, 8, 10>.  The intersections are formed on the whole row; the words of a
+// subset are popcounted in two carry-save trees, group 0 = slots below `split` (16-byte units), group 1 = the others -- the
+// boundary falls inside slot row SJ, where lanes below `lsplit` belong to group 0, so that row enters both trees masked --
+// and the two counts travel as the 16-bit halves of one register through the group's shuffles into the batched finish.
+struct SmallBothArgs {
+    SmallArgs base;          // pv / idx / n_draws / pos / out as in k_small; masks and tensor map of group 0 are not used
+    const uint64_t *both;    // [n_reads][80] combined rows
+    int lsplit;              // lanes (of the 8 of a draw) whose slot in row SJ belongs to group 0
+    alignas(64) CUtensorMap tmap_both;
+};
+
+template <int KIND, int SJ>
+__global__ void __launch_bounds__(SmallPipe<4, 10>::NWARPS * 32, 1) k_small_both(const __grid_constant__ SmallBothArgs b)
+{
+    constexpr int NR = 4, LPD = 8, WPL = 10, NS = 16, SLOTS = 5, DPW = 4, ROWS = 16, TPB = LPD;
+    using P = SmallPipe<NR, WPL>;
+    const SmallArgs &a = b.base;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane_in = lane % LPD, dgrp = lane / LPD;
+    unsigned char *wbase = smem + (size_t)warp * P::STAGE_BYTES;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + P::BARS) + warp;
+    uint4 *batch = reinterpret_cast<uint4 *>(smem + (size_t)P::NWARPS * P::STAGE_BYTES + (size_t)warp * P::BATCH_BYTES);
+    if (lane == 0) mbar_init(bar, 1);
+    fence_proxy_async();
+    __syncwarp();
+
+    const int64_t n_tiles = (a.n_draws + DPW - 1) / DPW;
+    const int64_t tile0 = (int64_t)blockIdx.x * P::NWARPS + warp, tstride = (int64_t)gridDim.x * P::NWARPS;
+    const int64_t n_stages = tile0 < n_tiles ? (n_tiles - tile0 + tstride - 1) / tstride : 0;
+    constexpr uint32_t ROW_BYTES = LPD * WPL * 8;
+
+    auto load_idx = [&](int64_t tile) -> int32_t {
+        if (lane >= ROWS) return 0;
+        int64_t d = tile * DPW + lane / NR;
+        if (d >= a.n_draws) d = a.n_draws - 1;
+        return __ldg(a.idx + d * NR + lane % NR);
+    };
+    // returns the row's two popcounts packed (group 0 | group 1 << 16)
+    auto issue = [&](int32_t ridx) -> uint32_t {
+        if (lane == 0) mbar_arrive_expect_tx(bar, ROW_BYTES * ROWS);
+        __syncwarp();
+        if (a.use_gather4) {
+            const int32_t r1 = __shfl_down_sync(0xffffffffu, ridx, 1), r2 = __shfl_down_sync(0xffffffffu, ridx, 2),
+                          r3 = __shfl_down_sync(0xffffffffu, ridx, 3);
+            if (lane < ROWS && (lane & 3) == 0) tma_gather4_g2s(wbase + (size_t)lane * ROW_BYTES, &b.tmap_both, 0, ridx, r1, r2, r3, bar);
+        } else if (lane < ROWS) {
+            bulk_copy_g2s(wbase + (size_t)lane * ROW_BYTES, b.both + (int64_t)ridx * (LPD * WPL), ROW_BYTES, bar);
+        }
+        return lane < ROWS ? (__ldg(a.pv.popc[0] + ridx) | (__ldg(a.pv.popc[1] + ridx) << 16)) : 0u;
+    };
+
+    uint32_t pc_cur = 0;
+    int32_t idx_nxt = 0;
+    int64_t nxt_tile = tile0;
+    if (n_stages > 0) { pc_cur = issue(load_idx(nxt_tile)); nxt_tile += tstride; }
+    if (n_stages > 1) idx_nxt = load_idx(nxt_tile);
+    const uint32_t mA = lane_in < b.lsplit ? ~0u : 0u;       // slot row SJ: group 0 for these lanes, group 1 for the others
+
+    uint32_t parity = 0;
+    for (int64_t q = 0; q < n_stages; ++q) {
+        // pk[s] = count of subset s in group 0 | group 1 << 16, this lane's share
+        uint32_t pk[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) pk[s] = 0;
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            const uint32_t v = __shfl_sync(0xffffffffu, pc_cur, dgrp * NR + i);
+            if (lane_in == 0) pk[1 << i] = v;
+        }
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        uint4 m[NR][SLOTS];
+        {
+            const unsigned char *st = wbase + (size_t)(dgrp * NR) * ROW_BYTES;
+#pragma unroll
+            for (int j = 0; j < SLOTS; ++j)
+#pragma unroll
+                for (int i = 0; i < NR; ++i)
+                    m[i][j] = *reinterpret_cast<const uint4 *>(st + ((size_t)i * (LPD * WPL) + (j * LPD + lane_in) * 2) * 8);
+        }
+        __syncwarp();
+        if (q + 1 < n_stages) {
+            fence_proxy_async();
+            pc_cur = issue(idx_nxt);
+            nxt_tile += tstride;
+            if (q + 2 < n_stages) idx_nxt = load_idx(nxt_tile);
+        }
+#pragma unroll
+        for (int s = 3; s < NS; ++s) {
+            if ((s & (s - 1)) == 0) continue;
+            uint32_t ta[4 * (SJ + 1)], tb[4 * (SLOTS - SJ)];
+#pragma unroll
+            for (int j = 0; j < SLOTS; ++j) {
+                uint32_t x = ~0u, y = ~0u, z = ~0u, w = ~0u;
+#pragma unroll
+                for (int i = 0; i < NR; ++i)
+                    if ((s >> i) & 1) { x &= m[i][j].x; y &= m[i][j].y; z &= m[i][j].z; w &= m[i][j].w; }
+                if (j < SJ) { ta[4 * j] = x; ta[4 * j + 1] = y; ta[4 * j + 2] = z; ta[4 * j + 3] = w; }
+                else if (j > SJ) { const int k = j - SJ; tb[4 * k] = x; tb[4 * k + 1] = y; tb[4 * k + 2] = z; tb[4 * k + 3] = w; }
+                else {
+                    ta[4 * j] = x & mA; ta[4 * j + 1] = y & mA; ta[4 * j + 2] = z & mA; ta[4 * j + 3] = w & mA;
+                    tb[0] = x & ~mA; tb[1] = y & ~mA; tb[2] = z & ~mA; tb[3] = w & ~mA;
+                }
+            }
+            pk[s] = PopcSum32<4 * (SJ + 1), LDPGTA_SMALL_CSA_DEPTH>::run(ta) + (PopcSum32<4 * (SLOTS - SJ), LDPGTA_SMALL_CSA_DEPTH>::run(tb) << 16);
+        }
+#pragma unroll
+        for (int s = 1; s < NS; ++s)
+#pragma unroll
+            for (int msk = LPD / 2; msk; msk >>= 1) pk[s] += __shfl_xor_sync(0xffffffffu, pk[s], msk);
+        // park the tile's counts; every TPB tiles (or at the end) each lane finishes one draw
+        const int k = (int)(q % TPB);
+        if (lane_in == 0) {
+            const int slot = k * DPW + dgrp;
+#pragma unroll
+            for (int j = 0; j < NS / 4; ++j) batch[j * 32 + slot] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        }
+        if (k == TPB - 1 || q + 1 == n_stages) {
+            __syncwarp();
+            uint32_t ca[NS], cb[NS];
+#pragma unroll
+            for (int j = 0; j < NS / 4; ++j) {
+                const uint4 v = batch[j * 32 + lane];
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { ca[4 * j + e] = w[e] & 0xffffu; cb[4 * j + e] = w[e] >> 16; }
+            }
+            const int kk = lane / DPW;
+            const int64_t draw_k = (tile0 + (q - k + kk) * tstride) * DPW + lane % DPW;
+            if (kk <= k) {
+                double res[4];
+                if (KIND == LDPGTA_RECENT_ADMIXTURE) SmallModel<NR, KIND>::finish_recent(a.pv, ca, cb, res);
+                else SmallModel<NR, KIND>::finish_distant2(a.pv, ca, cb, res);
+                if (draw_k < a.n_draws) small_store(a, draw_k, res);
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // ---- direct kernel (no staging): rows longer than one pass of a lane group ---------------------
 template <int NR, int LPD, int WPL, int KIND>
 __global__ void __launch_bounds__(128, LDPGTA_SMALL_MINB) k_small_direct(const SmallArgs a)

@@ -82,6 +82,7 @@ bool is_page_locked(const void *p)
 static int refresh_popc(ldpgta_ctx *c, int g)
 {
     if (c->read_popc[g]) { LDPGTA_CUDA(cudaFree(c->read_popc[g])); c->read_popc[g] = nullptr; }
+    c->both_valid = false;                                    // the combined two-group rows are rebuilt on their next use
     const int64_t n = c->n_reads_g[g];
     LDPGTA_CUDA(cudaMalloc((void **)&c->read_popc[g], std::max<size_t>((size_t)n * 4, 16)));
     if (n) {
@@ -381,6 +382,7 @@ int ldpgta_destroy(ldpgta_ctx *c)
     }
     for (int h = 0; h < 14; ++h)
         if (c->hi_terms[h]) cudaFree(c->hi_terms[h]);
+    if (c->masks_both) cudaFree(c->masks_both);
     for (int h = 0; h < 14; ++h)
         for (int b = 0; b < 4; ++b)
             if (c->run_terms[h][b]) cudaFree(c->run_terms[h][b]);

@@ -87,6 +87,85 @@ int make_read_mask_tmap(ldpgta_ctx *c, int g)
     return 0;
 }
 
+// ---- combined rows of a two-group panel (k_small_both) ----------------------------------------------------------
+static __global__ void k_interleave_rows(const uint64_t *__restrict__ m0, const uint64_t *__restrict__ m1, int wp0, int wp1, int64_t n_reads,
+                                         uint64_t *__restrict__ out)
+{
+    // one warp per read, 80 words per row: [group 0 | group 1 | zero]
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_reads; r += warps)
+        for (int w = lane; w < 80; w += 32)
+            out[r * 80 + w] = w < wp0 ? m0[r * wp0 + w] : w < wp0 + wp1 ? m1[r * wp1 + (w - wp0)] : 0ull;
+}
+
+static int ensure_both(ldpgta_ctx *c)
+{
+    if (c->both_valid) return 0;
+    const int64_t n = c->n_reads;
+    const size_t need = std::max<size_t>((size_t)n * 640, 16);
+    if (c->masks_both_bytes < need) {
+        if (c->masks_both) { LDPGTA_CUDA(cudaStreamSynchronize(c->stream)); LDPGTA_CUDA(cudaFree(c->masks_both)); c->masks_both = nullptr; c->masks_both_bytes = 0; }
+        const cudaError_t e = cudaMalloc((void **)&c->masks_both, need);
+        if (e != cudaSuccess) { cudaGetLastError(); return 1; }           // no room for the second copy: the two-stage kernel runs
+        c->masks_both_bytes = need;
+    }
+    k_interleave_rows<<<(unsigned)std::min<int64_t>((n * 32 + 255) / 256 + 1, (int64_t)c->sm_count * 16), 256, 0, c->stream>>>(
+        c->read_masks[0], c->read_masks[1], c->wp[0], c->wp[1], n, c->masks_both);
+    c->launches++;
+    LDPGTA_CUDA(cudaGetLastError());
+    // tensor map [n_reads][80] uint64, box = one row (tile::gather4 fetches four)
+    c->both_tmap_ok = false;
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (n > 0 && cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn) {
+        const cuuint64_t gdim[2] = {80, (cuuint64_t)n};
+        const cuuint64_t gstride[1] = {640};
+        const cuuint32_t box[2] = {80, 1};
+        const cuuint32_t estride[2] = {1, 1};
+        const CUresult r = ((encode_fn)fn)(&c->tmap_both, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, (void *)c->masks_both, gdim, gstride, box, estride,
+                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        c->both_tmap_ok = r == CUDA_SUCCESS;
+    } else {
+        cudaGetLastError();
+    }
+    c->both_valid = true;
+    return 0;
+}
+
+// 4 reads per draw, two groups whose rows together fill the 80-word tile and whose boundary lies in the third slot row
+// (group 0 of 32..47 words, e.g. 2504 + 2504 haplotypes): one gather per read instead of one per read and group.
+// Returns 1 when the shape is outside that envelope.
+template <int KIND>
+static int launch_small_both(ldpgta_ctx *c, SmallArgs &a)
+{
+    static const bool off = [] { const char *e = getenv("LDPGTA_SMALL_NO_BOTH"); return e && *e && *e != '0'; }();
+    const int wp0 = c->wp[0], wp1 = c->wp[1];
+    if (off || c->G != 2 || wp0 + wp1 > 80 || wp0 + wp1 <= 64 || wp0 < 32 || wp0 >= 48 || c->nhap[0] > 65535u || c->nhap[1] > 65535u ||
+        a.counts_out || a.pv.masks[0] != c->read_masks[0] || a.pv.masks[1] != c->read_masks[1] || a.n_draws < 4096)
+        return 1;
+    if (int rc = ensure_both(c)) return rc;
+    using P = SmallPipe<4, 10>;
+    SmallBothArgs b;
+    b.base = a;
+    b.base.use_gather4 = (c->both_tmap_ok && !getenv("LDPGTA_NO_GATHER4")) ? 1 : 0;
+    b.both = c->masks_both;
+    b.lsplit = wp0 / 2 - 16;                                   // slot row 2 holds slots 16..23
+    b.tmap_both = c->tmap_both;
+    auto kern = k_small_both<KIND, 2>;
+    LDPGTA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM));
+    const int64_t tiles = (a.n_draws + 3) / 4;
+    const unsigned blocks = (unsigned)std::min<int64_t>((tiles + P::NWARPS - 1) / P::NWARPS, c->sm_count);
+    kern<<<blocks, P::NWARPS * 32, P::SMEM, c->stream>>>(b);
+    c->launches++;
+    LDPGTA_CUDA(cudaGetLastError());
+    return 0;
+}
+
 template <int NR, int W64>
 static int launch_mid_t(ldpgta_ctx *c, SmallArgs &a)
 {
@@ -125,6 +204,10 @@ int launch_small(ldpgta_ctx *c, SmallArgs &a, int n, int kind)
     }
     if (n == 2) return launch_small_n<2>(c, a, kind);
     if (n == 3) return launch_small_n<3>(c, a, kind);
+    if (kind != LDPGTA_HOMOGENEOUS) {
+        const int rc = kind == LDPGTA_RECENT_ADMIXTURE ? launch_small_both<LDPGTA_RECENT_ADMIXTURE>(c, a) : launch_small_both<LDPGTA_DISTANT_ADMIXTURE>(c, a);
+        if (rc <= 0) return rc;
+    }
     return launch_small_n<4>(c, a, kind);
 }
 

@@ -266,6 +266,32 @@ def test_polynomial_run_lengths(model, sizes):
                 assert max_rel(got, want) < LIK_TOL, ('distant', sizes, n, max_rel(got, want))
 
 
+@pytest.mark.parametrize('sizes', [(2504, 2504), (2100, 2900), (3000, 2008), (2048, 2560)])
+def test_two_groups_in_one_row(sizes):
+    """ Batches of at least 4096 four-read draws of a two-group panel whose rows together fill the 80-word tile run on the
+    combined-row kernel (k_small_both: one gather per read for both groups, the boundary inside the third slot row); the
+    sizes put the boundary at different lanes, including none (2048 = 32 words exactly). """
+    rng = np.random.default_rng(sizes[0])
+    rows = [ld_rows(rng, 300, s) for s in sizes]
+    idx, off = uniform_draws(rng, 300, 4, 6000)
+    with L.Engine(list(sizes)) as eng:
+        for g in range(2):
+            eng.upload_read_masks(g, rows[g])
+        got = eng.likelihoods_batch(L.RECENT_ADMIXTURE, idx, off)
+        want = C.batch(_common_width(rows), list(sizes), idx, off, 1)
+        assert max_rel(got, want) < LIK_TOL, ('recent', sizes, max_rel(got, want))
+        prop = [0.25, 0.75]
+        got = eng.likelihoods_batch(L.DISTANT_ADMIXTURE, idx, off, proportions=prop)
+        want = C.batch(_common_width(rows), list(sizes), idx, off, 2, prop)
+        assert max_rel(got, want) < LIK_TOL, ('distant', sizes, max_rel(got, want))
+        # new masks for one group: the combined rows are rebuilt
+        rows[1] = ld_rows(rng, 300, sizes[1])
+        eng.upload_read_masks(1, rows[1])
+        got = eng.likelihoods_batch(L.RECENT_ADMIXTURE, idx, off)
+        want = C.batch(_common_width(rows), list(sizes), idx, off, 1)
+        assert max_rel(got, want) < LIK_TOL, ('recent, new masks', sizes, max_rel(got, want))
+
+
 def _common_width(rows):
     W = max(r.shape[1] for r in rows)
     out = []
