@@ -37,12 +37,18 @@ struct WindowPlan {
     double *d_lik = nullptr, *d_llr = nullptr, *d_mv = nullptr, *d_wsum = nullptr, *d_split = nullptr, *d_partials = nullptr, *d_stats = nullptr;
     uint64_t *d_seed = nullptr;
     unsigned int *d_arrived = nullptr;
+    // chunks of up to CH_WIN consecutive windows of one segment (k_window_stats_chunks / _block); 0 when a window has more than
+    // CHUNK_MAX_DRAWS draws
+    int64_t n_chunks = 0;
+    bool warp_chunks = false;
+    int64_t *d_chunk_win = nullptr, *d_cseg_off = nullptr;
+    double *d_colpart = nullptr;
 };
 
 void free_window_plan(ldpgta_ctx *c)
 {
     if (!c->plan) return;
-    if (c->llr_ptr == c->plan->d_llr) { c->llr_ptr = nullptr; c->llr_off_ptr = nullptr; c->llr_draws = c->llr_windows = -1; }
+    if (c->llr_ptr == c->plan->d_llr) { c->llr_ptr = nullptr; c->llr_off_ptr = nullptr; c->llr_draws = c->llr_windows = -1; c->llr_lazy_lik = nullptr; }
     if (c->plan->d_static) cudaFree(c->plan->d_static);
     if (c->plan->d_work) cudaFree(c->plan->d_work);
     delete c->plan;
@@ -76,8 +82,39 @@ int launch_sample(ldpgta_ctx *c, int n, const SampleArgs &a)
 static int stats_on_device(ldpgta_ctx *c, const double *d_lik, const int64_t *d_doff, int64_t n_windows, int64_t n_draws,
                            const int64_t *d_segoff, const int32_t *d_segcols, const int32_t *d_segfirst, int n_segments, int ncp,
                            double *d_llr, double *d_mv, double *d_wsum, double *d_split, unsigned int *d_arrived, double *d_partials, double *d_stats,
-                           double *mv_host = nullptr, int64_t max_draws_per_window = 0)
+                           double *mv_host = nullptr, int64_t max_draws_per_window = 0, const WindowPlan *chunks = nullptr, bool want_llr = true)
 {
+    if (chunks && chunks->n_chunks > 0 && n_windows > 0) {
+        // no window has more than CHUNK_MAX_DRAWS draws: the column sums are formed next to the window statistics, chunk by chunk
+        ChunkStatsArgs a;
+        a.st.llr = d_llr; a.st.lik = d_lik; a.st.doff = d_doff; a.st.n_windows = n_windows; a.st.n_draws = n_draws; a.st.mean_var = d_mv; a.st.wsum = d_wsum;
+        a.chunk_win = chunks->d_chunk_win; a.n_chunks = chunks->n_chunks; a.colpart = chunks->d_colpart; a.ncp = ncp; a.write_llr = want_llr ? 1 : 0;
+        const unsigned blocks = (unsigned)std::min<int64_t>(chunks->n_chunks, (int64_t)c->sm_count * 64);
+        if (max_draws_per_window <= 32) {
+            if (chunks->warp_chunks) k_window_stats_warpchunks<<<(unsigned)std::min<int64_t>((chunks->n_chunks + 7) / 8, (int64_t)c->sm_count * 32), 256, 0, c->stream>>>(a);
+            else k_window_stats_chunks<<<blocks, CH_WIN * 32, 0, c->stream>>>(a);
+        }
+        // threads x draws per thread by the longest window; the register budget (LLRs + column sums of DPT draws per pair)
+        // decides how many blocks share an SM while one of them sits in a barrier
+        else if (max_draws_per_window <= 256) k_window_stats_block<1, 256, 4><<<blocks, 256, 0, c->stream>>>(a);
+        else if (max_draws_per_window <= 512) k_window_stats_block<2, 256, 4><<<blocks, 256, 0, c->stream>>>(a);
+        else if (max_draws_per_window <= 1024) k_window_stats_block<4, 256, 2><<<blocks, 256, 0, c->stream>>>(a);      // measured: <2, 512, 2> is 20 % slower
+        else k_window_stats_block<4, 512, 1><<<blocks, 512, 0, c->stream>>>(a);
+        c->launches++;
+        if (mv_host) {
+            if (int rc = ensure_pipeline(c, 2)) return rc;
+            LDPGTA_CUDA(cudaEventRecord(c->ev_in[0], c->stream));
+            LDPGTA_CUDA(cudaStreamWaitEvent(c->s_out, c->ev_in[0], 0));
+            LDPGTA_CUDA(cudaMemcpyAsync(mv_host, d_mv, (size_t)n_windows * 80, cudaMemcpyDeviceToHost, c->s_out));
+        }
+        SegChunkArgs sa;
+        sa.colpart = chunks->d_colpart; sa.cseg_off = chunks->d_cseg_off; sa.seg_off = d_segoff; sa.seg_cols = d_segcols; sa.seg_first = d_segfirst;
+        sa.ncp = ncp; sa.partials = d_partials; sa.stats = d_stats; sa.arrived = d_arrived;
+        k_segment_from_chunks<<<dim3((unsigned)n_segments, 5, (unsigned)((ncp + 2 + SC_COLS - 1) / SC_COLS)), SC_ROWS * SC_COLS, 0, c->stream>>>(sa);
+        c->launches++;
+        LDPGTA_CUDA(cudaGetLastError());
+        return 0;
+    }
     // LLRs: windows of at most 32 draws form them inside k_window_stats (one draw per lane); longer windows would make
     // that one warp walk the window five times, so the LLRs come from the fully parallel k_draw_llr first
     if (d_lik && n_draws > 0 && max_draws_per_window > 32) {
@@ -108,6 +145,8 @@ static int stats_on_device(ldpgta_ctx *c, const double *d_lik, const int64_t *d_
     LDPGTA_CUDA(cudaGetLastError());
     return 0;
 }
+
+constexpr int64_t CHUNK_MAX_DRAWS = 2048;           // k_window_stats_block<4, 512>
 
 static size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
 
@@ -221,8 +260,13 @@ static int reduce_and_download(ldpgta_ctx *c, WindowPlan *p, double *lik_out, do
 {
     double *d_llr = p->d_llr;
     c->llr_draws = c->llr_windows = -1;
+    c->llr_lazy_lik = nullptr;
+    // the LLR matrix is written when the caller wants it; otherwise ldpgta_bin_stats forms it from the resident likelihoods
+    // the first time it is asked for (k_draw_llr)
+    const bool lazy = !llr_fused(p) && p->n_chunks > 0 && !llr_out;
     if (int rc = stats_on_device(c, llr_fused(p) ? nullptr : p->d_lik, p->d_doff, p->n_windows, p->n_draws, p->d_segoff, p->d_segcols, p->d_segfirst,
-                                 p->n_segments, p->ncp, d_llr, p->d_mv, p->d_wsum, p->d_split, p->d_arrived, p->d_partials, p->d_stats, window_mean_var, p->max_draws))
+                                 p->n_segments, p->ncp, d_llr, p->d_mv, p->d_wsum, p->d_split, p->d_arrived, p->d_partials, p->d_stats, window_mean_var, p->max_draws,
+                                 p, !lazy))
         return rc;
     const size_t cp_b = (size_t)p->n_segments * 5 * (p->ncp + 3) * 8;
     if (segment_partials) LDPGTA_CUDA(cudaMemcpyAsync(segment_partials, p->d_partials, cp_b, cudaMemcpyDeviceToHost, c->stream));
@@ -233,6 +277,7 @@ static int reduce_and_download(ldpgta_ctx *c, WindowPlan *p, double *lik_out, do
     if (lik_out && lik_pinned != lik_out) memcpy(lik_out, lik_pinned, (size_t)p->n_draws * 32);
     c->llr_ptr = p->d_llr; c->llr_off_ptr = p->d_doff;
     c->llr_draws = p->n_draws; c->llr_windows = p->n_windows;
+    c->llr_lazy_lik = lazy ? p->d_lik : nullptr;
     return 0;
 }
 
@@ -311,6 +356,23 @@ int ldpgta_set_windows(ldpgta_ctx *c, const int64_t *window_offsets, const int32
     const size_t o_woff = take(window_offsets ? (size_t)(n_windows + 1) * 8 : 0), o_doff = take((size_t)(n_windows + 1) * 8);
     const size_t o_seg = take((size_t)(n_segments + 1) * 8), o_cols = take((size_t)n_segments * 4), o_first = take((size_t)n_segments * 4);
     const size_t o_wreads = take((size_t)p->n_wreads * 4), o_seed = take(8);
+    // chunk table of the fused window / column reductions
+    static const bool no_chunks = [] { const char *e = getenv("LDPGTA_NO_CHUNK_STATS"); return e && atoi(e) != 0; }();
+    std::vector<int64_t> chunk_win, cseg_off;
+    if (!no_chunks && max_draws <= CHUNK_MAX_DRAWS && n_windows > 0) {
+        // windows per chunk: CH_WIN; with at most 32 draws per window a chunk may also be walked by one warp (LDPGTA_STATS_WARP=k)
+        static const int warp_chunk = [] { const char *e = getenv("LDPGTA_STATS_WARP"); return e ? atoi(e) : 0; }();
+        p->warp_chunks = max_draws <= 32 && warp_chunk > 0;
+        const int per_chunk = p->warp_chunks ? warp_chunk : CH_WIN;
+        cseg_off.push_back(0);
+        for (int s = 0; s < n_segments; ++s) {
+            for (int64_t w = segment_offsets[s]; w < segment_offsets[s + 1]; w += per_chunk) chunk_win.push_back(w);
+            cseg_off.push_back((int64_t)chunk_win.size());
+        }
+        p->n_chunks = (int64_t)chunk_win.size();
+        chunk_win.push_back(n_windows);
+    }
+    const size_t o_chunk = take(chunk_win.size() * 8), o_cseg = take(cseg_off.size() * 8);
     struct ClsOff { size_t doff, win, pos, wod; };
     std::vector<ClsOff> co;
     for (int n = 2; n <= MAXN; ++n) {
@@ -333,6 +395,10 @@ int ldpgta_set_windows(ldpgta_ctx *c, const int64_t *window_offsets, const int32
     memcpy(img.data() + o_cols, segcols.data(), (size_t)n_segments * 4);
     memcpy(img.data() + o_first, segfirst.data(), (size_t)n_segments * 4);
     if (p->n_wreads) memcpy(img.data() + o_wreads, window_reads, (size_t)p->n_wreads * 4);
+    if (p->n_chunks) {
+        memcpy(img.data() + o_chunk, chunk_win.data(), chunk_win.size() * 8);
+        memcpy(img.data() + o_cseg, cseg_off.data(), cseg_off.size() * 8);
+    }
     for (size_t ci = 0; ci < p->classes.size(); ++ci) {
         SizeClass &k = p->classes[ci];
         int64_t *cd = (int64_t *)(img.data() + co[ci].doff);
@@ -365,6 +431,8 @@ int ldpgta_set_windows(ldpgta_ctx *c, const int64_t *window_offsets, const int32
     p->d_segfirst = (int32_t *)(base + o_first);
     p->d_wreads = p->n_wreads ? (int32_t *)(base + o_wreads) : nullptr;
     p->d_seed = (uint64_t *)(base + o_seed);
+    p->d_chunk_win = p->n_chunks ? (int64_t *)(base + o_chunk) : nullptr;
+    p->d_cseg_off = p->n_chunks ? (int64_t *)(base + o_cseg) : nullptr;
     for (size_t ci = 0; ci < p->classes.size(); ++ci) {
         p->classes[ci].d_doff = (int64_t *)(base + co[ci].doff);
         p->classes[ci].d_win = single ? nullptr : (int32_t *)(base + co[ci].win);
@@ -388,6 +456,7 @@ int ldpgta_set_windows(ldpgta_ctx *c, const int64_t *window_offsets, const int32
     const size_t o_lik = take((size_t)n_draws * 32), o_llr = take((size_t)n_draws * 40), o_mv = take((size_t)n_windows * 80);
     const size_t o_wsum = take((size_t)n_windows * 40), o_split = take((size_t)n_segments * 5 * SEG_SPLIT * (ncp + 3) * 8), o_arr = take((size_t)n_segments * 20);
     const size_t o_part = take((size_t)n_segments * 5 * (ncp + 3) * 8), o_stats = take((size_t)n_segments * 120);
+    const size_t o_colpart = take((size_t)p->n_chunks * 5 * (ncp + 2) * 8);
     LDPGTA_CUDA(cudaMalloc(&p->d_work, std::max<size_t>(off, 256)));
     base = (char *)p->d_work;
     for (size_t ci = 0; ci < p->classes.size(); ++ci) p->classes[ci].d_idx = (int32_t *)(base + o_idx[ci]);
@@ -400,6 +469,7 @@ int ldpgta_set_windows(ldpgta_ctx *c, const int64_t *window_offsets, const int32
     LDPGTA_CUDA(cudaMemsetAsync(p->d_arrived, 0, (size_t)n_segments * 20, c->stream));
     p->d_partials = (double *)(base + o_part);
     p->d_stats = (double *)(base + o_stats);
+    p->d_colpart = p->n_chunks ? (double *)(base + o_colpart) : nullptr;
     LDPGTA_CUDA(cudaStreamSynchronize(c->stream));
     if (p->n_wreads && *c->h_flag) {
         free_window_plan(c);
@@ -521,9 +591,11 @@ int ldpgta_bootstrap_stats_dev(ldpgta_ctx *c, int kind, uint64_t seed, const dou
         if (int rc = launch_sample(c, k.n, sa)) return rc;
     }
     if (int rc = evaluate_classes(c, p, kind, proportions, nullptr)) return rc;
+    // the resident likelihoods change and the LLR matrix is not written: what ldpgta_bin_stats would read is gone
+    if (c->llr_ptr == p->d_llr) { c->llr_draws = c->llr_windows = -1; c->llr_lazy_lik = nullptr; }
     return stats_on_device(c, llr_fused(p) ? nullptr : p->d_lik, p->d_doff, p->n_windows, p->n_draws, p->d_segoff, p->d_segcols, p->d_segfirst, p->n_segments,
                            p->ncp, p->d_llr, p->d_mv, p->d_wsum, p->d_split, p->d_arrived, segment_partials_dev ? segment_partials_dev : p->d_partials,
-                           segment_partials_dev ? nullptr : p->d_stats, nullptr, p->max_draws);
+                           segment_partials_dev ? nullptr : p->d_stats, nullptr, p->max_draws, p, false);
 }
 
 int ldpgta_finish_segments_dev(ldpgta_ctx *c, const double *segment_partials_dev, double *segment_stats_dev)

@@ -243,6 +243,7 @@ struct ldpgta_ctx {
     int64_t llr_draws = -1, llr_windows = -1;
     const double *llr_ptr = nullptr;          // the resident LLRs ldpgta_bin_stats(x = NULL) reads: d_llr or the plan's buffer
     const int64_t *llr_off_ptr = nullptr;
+    const double *llr_lazy_lik = nullptr;     // resident likelihoods [llr_draws][4] from which llr_ptr still has to be formed (k_draw_llr), or nullptr
     int64_t *d_llr_off = nullptr;  size_t d_llr_off_bytes = 0;
     unsigned int *d_flag = nullptr, *h_flag = nullptr;     // device-side index validation of the pipelined host path
     // the pipelined host path as a CUDA graph, replayed while the call signature repeats

@@ -459,24 +459,48 @@ __global__ void __launch_bounds__(SmallPipe<NR, WPL>::NWARPS * 32, 1) k_small(co
             // one-group model, counts below 2^16: two counters per register from the lane partials on -- through the
             // group's xor-shuffles and the per-warp batch table -- and unpacked once per draw by the lane that finishes it
             uint32_t pk[NS / 2];
-#pragma unroll
-            for (int t = 0; t < NS / 2; ++t) {
-                pk[t] = c[2 * t] + (c[2 * t + 1] << 16);
-#pragma unroll
-                for (int msk = LPD / 2; msk; msk >>= 1) pk[t] += __shfl_xor_sync(0xffffffffu, pk[t], msk);
-            }
             const int k = (int)(q % TPB);
-            if (lane_in == 0) {
-                const int slot = k * DPW + dgrp;
+            // as many packed counters as lanes in the group (4 reads, 8 lanes): a transposing reduction -- every step halves
+            // the counters a lane carries, 7 shuffles instead of 24 -- leaves counter i summed in lane i, which stores it
+            #ifdef LDPGTA_SMALL_BUTTERFLY
+            constexpr bool TRANSPOSE = false;                               // A/B build: every counter through the full butterfly
+#else
+            constexpr bool TRANSPOSE = NS / 2 == LPD && LPD == 8;
+#endif
+            constexpr int PLANE = TRANSPOSE ? 36 : 32;                      // uint4 stride of a table plane (+16 words: the 32 stores hit 32 banks)
+            if (TRANSPOSE) {
 #pragma unroll
-                for (int j = 0; j < NS / 8; ++j) batch[j * 32 + slot] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                for (int t = 0; t < NS / 2; ++t) pk[t] = c[2 * t] + (c[2 * t + 1] << 16);
+#pragma unroll
+                for (int h = LPD / 2; h; h >>= 1) {
+                    const bool up = (lane_in & h) != 0;
+#pragma unroll
+                    for (int t = 0; t < h; ++t) {
+                        const uint32_t send = up ? pk[t] : pk[t + h], keep = up ? pk[t + h] : pk[t];
+                        pk[t] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+                    }
+                }
+                const int slot = k * DPW + dgrp;
+                reinterpret_cast<uint32_t *>(batch)[(lane_in >> 2) * (PLANE * 4) + slot * 4 + (lane_in & 3)] = pk[0];
+            } else {
+#pragma unroll
+                for (int t = 0; t < NS / 2; ++t) {
+                    pk[t] = c[2 * t] + (c[2 * t + 1] << 16);
+#pragma unroll
+                    for (int msk = LPD / 2; msk; msk >>= 1) pk[t] += __shfl_xor_sync(0xffffffffu, pk[t], msk);
+                }
+                if (lane_in == 0) {
+                    const int slot = k * DPW + dgrp;
+#pragma unroll
+                    for (int j = 0; j < NS / 8; ++j) batch[j * 32 + slot] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                }
             }
             if (k == TPB - 1 || q + 1 == n_stages) {
                 __syncwarp();
                 uint32_t cc[NS];
 #pragma unroll
                 for (int j = 0; j < NS / 8; ++j) {
-                    const uint4 v = batch[j * 32 + lane];
+                    const uint4 v = batch[j * PLANE + lane];
                     const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) { cc[8 * j + 2 * e] = w4[e] & 0xffffu; cc[8 * j + 2 * e + 1] = w4[e] >> 16; }

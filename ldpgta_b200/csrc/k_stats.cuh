@@ -294,6 +294,56 @@ struct StatsArgs {
     double *wsum;              // [5][n_windows] sum of the window's LLRs (feeds the chromosome totals)
 };
 
+// A window of at most 32 draws on one warp, one draw per lane: the five LLRs (formed from the likelihoods, or read), their
+// plain tree sums (5 roundings), mean and sample variance; writes mean_var / wsum and leaves the lane's LLRs in x[] (0 for
+// lanes without a draw), the LLR sum of pair `lane` in mine and its mean in mean_l (lanes 0..4).
+__device__ __forceinline__ void window_le32(const StatsArgs &a, int64_t w, int64_t b, int64_t e, int lane, bool write_llr,
+                                            double (&x)[5], double &mine, double &mean_l)
+{
+    const double cnt = (double)(e - b);
+    const bool live = b + lane < e;
+    double sum[5], sq[5];
+    if (a.lik) {
+        double v[4] = {0.0, 0.0, 0.0, 0.0};
+        if (live) {
+            const double2 u0 = __ldg(reinterpret_cast<const double2 *>(a.lik) + 2 * (b + lane)),
+                          u1 = __ldg(reinterpret_cast<const double2 *>(a.lik) + 2 * (b + lane) + 1);
+            v[0] = u0.x; v[1] = u0.y; v[2] = u1.x; v[3] = u1.y;
+        }
+#pragma unroll
+        for (int p = 0; p < 5; ++p) {
+            x[p] = live ? llr_of(v[c_pair_num[p]], v[c_pair_den[p]]) : 0.0;
+            if (live && write_llr) a.llr[(int64_t)p * a.n_draws + b + lane] = x[p];
+        }
+    } else {
+#pragma unroll
+        for (int p = 0; p < 5; ++p) x[p] = live ? a.llr[(int64_t)p * a.n_draws + b + lane] : 0.0;
+    }
+#pragma unroll
+    for (int p = 0; p < 5; ++p) sum[p] = warp_sum_f64(x[p]);
+    // the five means are ONE float64 division executed by lanes 0..4 side by side (a division is ~40 instructions
+    // whether one lane or all need it); they travel back by shuffle
+    mine = sum[0];
+#pragma unroll
+    for (int p = 1; p < 5; ++p) mine = lane == p ? sum[p] : mine;
+    mean_l = mine / cnt;
+#pragma unroll
+    for (int p = 0; p < 5; ++p) {
+        const double m = __shfl_sync(0xffffffffu, mean_l, p);
+        const double d = live ? x[p] - m : 0.0;
+        sq[p] = warp_sum_f64(d * d);
+    }
+    double ss = sq[0];
+#pragma unroll
+    for (int p = 1; p < 5; ++p) ss = lane == p ? sq[p] : ss;
+    if (lane < 5) {
+        double *mv = a.mean_var + 2 * ((int64_t)lane * a.n_windows + w);
+        mv[0] = mean_l;
+        mv[1] = (e - b > 1) ? ss / (cnt - 1.0) : nan("");
+        a.wsum[(int64_t)lane * a.n_windows + w] = mine;
+    }
+}
+
 // One warp per window (and all five LLR pairs): mean = sum / count, variance from the squared deviations of a second
 // pass -- registers for windows of at most 32 draws, L1/L2 otherwise; sums of more than 32 values are Neumaier-compensated
 // (statistics.mean / statistics.variance of ANEUPLOIDY_TEST.py:51-56 are exact-rational).
@@ -304,50 +354,9 @@ static __global__ void k_window_stats(const StatsArgs a)
     for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < a.n_windows; w += warps) {
         const int64_t b = a.doff[w], e = a.doff[w + 1];
         const double cnt = (double)(e - b);
-        double sum[5], sq[5];
         if (e - b <= 32) {
-            // one draw per lane, plain tree sums (5 roundings)
-            const bool live = b + lane < e;
-            double x[5];
-            if (a.lik) {
-                double v[4] = {0.0, 0.0, 0.0, 0.0};
-                if (live) {
-                    const double2 u0 = __ldg(reinterpret_cast<const double2 *>(a.lik) + 2 * (b + lane)),
-                                  u1 = __ldg(reinterpret_cast<const double2 *>(a.lik) + 2 * (b + lane) + 1);
-                    v[0] = u0.x; v[1] = u0.y; v[2] = u1.x; v[3] = u1.y;
-                }
-#pragma unroll
-                for (int p = 0; p < 5; ++p) {
-                    x[p] = live ? llr_of(v[c_pair_num[p]], v[c_pair_den[p]]) : 0.0;
-                    if (live) a.llr[(int64_t)p * a.n_draws + b + lane] = x[p];
-                }
-            } else {
-#pragma unroll
-                for (int p = 0; p < 5; ++p) x[p] = live ? a.llr[(int64_t)p * a.n_draws + b + lane] : 0.0;
-            }
-#pragma unroll
-            for (int p = 0; p < 5; ++p) sum[p] = warp_sum_f64(x[p]);
-            // the five means are ONE float64 division executed by lanes 0..4 side by side (a division is ~40 instructions
-            // whether one lane or all need it); they travel back by shuffle
-            double mine = sum[0];
-#pragma unroll
-            for (int p = 1; p < 5; ++p) mine = lane == p ? sum[p] : mine;
-            const double mean_l = mine / cnt;
-#pragma unroll
-            for (int p = 0; p < 5; ++p) {
-                const double m = __shfl_sync(0xffffffffu, mean_l, p);
-                const double d = live ? x[p] - m : 0.0;
-                sq[p] = warp_sum_f64(d * d);
-            }
-            double ss = sq[0];
-#pragma unroll
-            for (int p = 1; p < 5; ++p) ss = lane == p ? sq[p] : ss;
-            if (lane < 5) {
-                double *mv = a.mean_var + 2 * ((int64_t)lane * a.n_windows + w);
-                mv[0] = mean_l;
-                mv[1] = (e - b > 1) ? ss / (cnt - 1.0) : nan("");
-                a.wsum[(int64_t)lane * a.n_windows + w] = mine;
-            }
+            double x[5], mine, mean_l;
+            window_le32(a, w, b, e, lane, true, x, mine, mean_l);
         } else {
 #pragma unroll 1
             for (int p = 0; p < 5; ++p) {
@@ -383,11 +392,12 @@ static __global__ void k_window_stats(const StatsArgs a)
 // deviations are added column by column); lanes only fetch the columns.
 __device__ __forceinline__ void segment_finish(const double *q, int ncols, int first_draws, double *out3, int lane)
 {
-    const double M = q[1], N = (double)first_draws;
-    const double mu = q[0] / N;
+    // q may have been written by other blocks of this launch (k_segment_from_chunks): read it from L2
+    const double M = __ldcg(q + 1), N = (double)first_draws;
+    const double mu = __ldcg(q) / N;
     double ss = 0.0;
     for (int i0 = 0; i0 < ncols; i0 += 32) {
-        const double mine = i0 + lane < ncols ? q[3 + i0 + lane] : 0.0;
+        const double mine = i0 + lane < ncols ? __ldcg(q + 3 + i0 + lane) : 0.0;
         const int cnt = min(32, ncols - i0);
         for (int j = 0; j < cnt; ++j) {
             const double d = __shfl_sync(0xffffffffu, mine, j) - mu;
@@ -397,7 +407,7 @@ __device__ __forceinline__ void segment_finish(const double *q, int ncols, int f
     if (lane == 0) {
         out3[0] = mu / M;
         out3[1] = sqrt(ss / (N - 1.0)) / M;
-        out3[2] = q[2] / M;
+        out3[2] = __ldcg(q + 2) / M;
     }
 }
 
@@ -525,6 +535,256 @@ static __global__ void k_finish_segments(const double *__restrict__ partials, co
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (t >= n_segments * 5) return;
     segment_finish(partials + (int64_t)t * (ncp + 3), seg_cols[t / 5], seg_first[t / 5], out + 3 * (int64_t)t, threadIdx.x & 31);
+}
+
+// ---- the same reductions with the column sums formed next to the window statistics --------------------------------------
+// k_segment_partials walks the whole LLR matrix (40 bytes per draw) a second time for the column sums of zip(*A).  Here a
+// block takes a *chunk* of up to CH_WIN consecutive windows of ONE segment (chunk table made by ldpgta_set_windows) and adds
+// the chunk's LLRs column by column while they are in registers:
+//   colpart[chunk][pair][0] = sum of the window sums, [1] = windows with a negative mean, [2 + i] = sum of column i (i < ncp).
+// k_segment_from_chunks then adds (ncp + 2) * 8 bytes per (chunk, pair) instead of reading every LLR, and the LLR matrix need
+// not be written at all when nobody asked for it.  Summation orders are fixed by the launch shape (bit-reproducible).
+//   k_window_stats_chunks      no window has more than 32 draws: one window per warp (window_le32), CH_WIN warps
+//   k_window_stats_block<DPT, NT>  windows of up to NT * DPT draws: the block takes its windows one after the other, thread t
+//                              owns draws t, t + NT, ... of each (LLRs in registers for the second pass and the column sums)
+constexpr int CH_WIN = 8;
+
+struct ChunkStatsArgs {
+    StatsArgs st;
+    const int64_t *chunk_win;  // [n_chunks + 1] first window of each chunk (a chunk never straddles a segment)
+    int64_t n_chunks;
+    double *colpart;           // [n_chunks][5][ncp + 2]
+    int ncp;
+    int write_llr;
+};
+
+static __global__ void __launch_bounds__(CH_WIN * 32, 4) k_window_stats_chunks(const ChunkStatsArgs a)
+{
+    __shared__ double xs[CH_WIN][5][32];
+    __shared__ double tot[CH_WIN][5][2];
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5, cstride = a.ncp + 2;
+    for (int64_t ch = blockIdx.x; ch < a.n_chunks; ch += gridDim.x) {
+        const int64_t w0 = a.chunk_win[ch];
+        const int nw = (int)(a.chunk_win[ch + 1] - w0);
+        if (wi < nw) {
+            const int64_t w = w0 + wi, b = a.st.doff[w], e = a.st.doff[w + 1];
+            double x[5], mine, mean_l;
+            window_le32(a.st, w, b, e, lane, a.write_llr != 0, x, mine, mean_l);
+#pragma unroll
+            for (int p = 0; p < 5; ++p) xs[wi][p][lane] = x[p];
+            if (lane < 5) { tot[wi][lane][0] = mine; tot[wi][lane][1] = mean_l < 0.0 ? 1.0 : 0.0; }
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < 5 * cstride; t += CH_WIN * 32) {
+            const int p = t / cstride, j = t % cstride;
+            double s = 0.0;
+            if (j >= 2) for (int k = 0; k < nw; ++k) s += xs[k][p][j - 2];
+            else        for (int k = 0; k < nw; ++k) s += tot[k][p][j];
+            a.colpart[(ch * 5 + p) * cstride + j] = s;
+        }
+        __syncthreads();
+    }
+}
+
+// the same without shared memory or block barriers: ONE WARP takes the windows of a chunk one after the other and keeps the
+// column sums in registers (lane i = column i)
+static __global__ void __launch_bounds__(256, 4) k_window_stats_warpchunks(const ChunkStatsArgs a)
+{
+    const int lane = threadIdx.x & 31, cstride = a.ncp + 2;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t ch = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; ch < a.n_chunks; ch += warps) {
+        const int64_t w0 = a.chunk_win[ch];
+        const int nw = (int)(a.chunk_win[ch + 1] - w0);
+        double col[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, tsum = 0.0, tneg = 0.0;
+        for (int k = 0; k < nw; ++k) {
+            const int64_t w = w0 + k, b = a.st.doff[w], e = a.st.doff[w + 1];
+            double x[5], mine, mean_l;
+            window_le32(a.st, w, b, e, lane, a.write_llr != 0, x, mine, mean_l);
+#pragma unroll
+            for (int p = 0; p < 5; ++p) col[p] += x[p];
+            tsum += mine;                                    // lanes 0..4: pair `lane`
+            tneg += mean_l < 0.0 ? 1.0 : 0.0;
+        }
+        double *out = a.colpart + ch * 5 * cstride;
+#pragma unroll
+        for (int p = 0; p < 5; ++p)
+            if (lane < a.ncp) out[p * cstride + 2 + lane] = col[p];
+        if (lane < 5) { out[lane * cstride] = tsum; out[lane * cstride + 1] = tneg; }
+    }
+}
+
+template <int DPT, int NT, int MINB>
+static __global__ void __launch_bounds__(NT, MINB) k_window_stats_block(const ChunkStatsArgs a)
+{
+    constexpr int NW = NT / 32;
+    __shared__ double red[NW][5], red2[NW][5];
+    const int t = threadIdx.x, lane = t & 31, wi = t >> 5, cstride = a.ncp + 2;
+    for (int64_t ch = blockIdx.x; ch < a.n_chunks; ch += gridDim.x) {
+        const int64_t w0 = a.chunk_win[ch];
+        const int nw = (int)(a.chunk_win[ch + 1] - w0);
+        double col[5][DPT];
+#pragma unroll
+        for (int p = 0; p < 5; ++p)
+#pragma unroll
+            for (int j = 0; j < DPT; ++j) col[p][j] = 0.0;
+        Comp tsum = {0.0, 0.0};          // threads 0..4: sum of the window sums and negative means of pair t
+        double tneg = 0.0;
+        // the likelihoods of the next window are requested before this window's arithmetic and barriers
+        double2 nx[DPT][2];
+        int64_t nb = a.st.doff[w0], ne = a.st.doff[w0 + 1];
+        auto fetch = [&](int64_t b_, int64_t e_) {
+#pragma unroll
+            for (int j = 0; j < DPT; ++j) {
+                const int64_t i = b_ + t + NT * j;
+                if (a.st.lik && i < e_) {
+                    nx[j][0] = __ldg(reinterpret_cast<const double2 *>(a.st.lik) + 2 * i);
+                    nx[j][1] = __ldg(reinterpret_cast<const double2 *>(a.st.lik) + 2 * i + 1);
+                } else nx[j][0] = nx[j][1] = make_double2(0.0, 0.0);
+            }
+        };
+        fetch(nb, ne);
+        for (int k = 0; k < nw; ++k) {
+            const int64_t w = w0 + k, b = nb, e = ne;
+            const double cnt = (double)(e - b);
+            double x[5][DPT];
+            Comp acc[5];
+            double2 cur[DPT][2];
+#pragma unroll
+            for (int j = 0; j < DPT; ++j) { cur[j][0] = nx[j][0]; cur[j][1] = nx[j][1]; }
+            if (k + 1 < nw) { nb = e; ne = a.st.doff[w + 2]; fetch(nb, ne); }
+#pragma unroll
+            for (int p = 0; p < 5; ++p) acc[p] = {0.0, 0.0};
+#pragma unroll
+            for (int j = 0; j < DPT; ++j) {
+                const int64_t i = b + t + NT * j;
+                const bool live = i < e;
+                if (a.st.lik) {
+                    const double v[4] = {cur[j][0].x, cur[j][0].y, cur[j][1].x, cur[j][1].y};
+#pragma unroll
+                    for (int p = 0; p < 5; ++p) {
+                        x[p][j] = live ? llr_of(v[c_pair_num[p]], v[c_pair_den[p]]) : 0.0;
+                        if (live && a.write_llr) a.st.llr[(int64_t)p * a.st.n_draws + i] = x[p][j];
+                    }
+                } else {
+#pragma unroll
+                    for (int p = 0; p < 5; ++p) x[p][j] = live ? a.st.llr[(int64_t)p * a.st.n_draws + i] : 0.0;
+                }
+#pragma unroll
+                for (int p = 0; p < 5; ++p) acc[p].add(x[p][j]);
+            }
+#pragma unroll
+            for (int p = 0; p < 5; ++p) {
+                const double v = warp_sum_comp(acc[p]);
+                if (lane == 0) red[wi][p] = v;
+            }
+            __syncthreads();
+            // every warp combines the warps' sums itself (lanes 0..4, pair `lane`): no second barrier before the deviations
+            double sum_l = 0.0, mean_l = 0.0;
+            if (lane < 5) {
+                Comp c = {0.0, 0.0};
+#pragma unroll
+                for (int r = 0; r < NW; ++r) c.add(red[r][lane]);
+                sum_l = c.value();
+                mean_l = sum_l / cnt;
+            }
+#pragma unroll
+            for (int p = 0; p < 5; ++p) {
+                const double m = __shfl_sync(0xffffffffu, mean_l, p);
+                Comp q = {0.0, 0.0};
+#pragma unroll
+                for (int j = 0; j < DPT; ++j) {
+                    const double d = (b + t + NT * j < e) ? x[p][j] - m : 0.0;
+                    q.add(d * d);
+                    col[p][j] += x[p][j];
+                }
+                const double v = warp_sum_comp(q);
+                if (lane == 0) red2[wi][p] = v;
+            }
+            __syncthreads();
+            if (t < 5) {
+                Comp c = {0.0, 0.0};
+#pragma unroll
+                for (int r = 0; r < NW; ++r) c.add(red2[r][t]);
+                double *mv = a.st.mean_var + 2 * ((int64_t)t * a.st.n_windows + w);
+                mv[0] = mean_l;
+                mv[1] = (e - b > 1) ? c.value() / (cnt - 1.0) : nan("");
+                a.st.wsum[(int64_t)t * a.st.n_windows + w] = sum_l;
+                tsum.add(sum_l);
+                tneg += mean_l < 0.0 ? 1.0 : 0.0;
+            }
+        }
+        double *out = a.colpart + ch * 5 * cstride;
+#pragma unroll
+        for (int p = 0; p < 5; ++p)
+#pragma unroll
+            for (int j = 0; j < DPT; ++j)
+                if (t + NT * j < a.ncp) out[p * cstride + 2 + t + NT * j] = col[p][j];
+        if (t < 5) { out[t * cstride] = tsum.value(); out[t * cstride + 1] = tneg; }
+    }
+}
+
+struct SegChunkArgs {
+    const double *colpart;     // [n_chunks][5][ncp + 2]
+    const int64_t *cseg_off;   // [n_segments + 1] chunks of segment s = [cseg_off[s], cseg_off[s+1])
+    const int64_t *seg_off;
+    const int32_t *seg_cols, *seg_first;
+    int ncp;
+    double *partials;          // [n_segments][5][ncp + 3]
+    double *stats;             // optional [n_segments][5][3]
+    unsigned int *arrived;     // [n_segments][5] zero on entry, zero again on exit
+};
+constexpr int SC_ROWS = 16, SC_COLS = 32;
+
+// one block per (segment, pair, 32 entries of the chunk rows): SC_ROWS x SC_COLS threads, row r adds the chunks r,
+// r + SC_ROWS, ... of its entry (Neumaier-compensated, four loads in flight), the rows are combined in row order; the last
+// block of a (segment, pair) to finish also runs segment_finish.  Layout of partials as k_segment_partials.
+static __global__ void __launch_bounds__(SC_ROWS * SC_COLS) k_segment_from_chunks(const SegChunkArgs a)
+{
+    __shared__ double sh_s[SC_ROWS][SC_COLS + 1], sh_c[SC_ROWS][SC_COLS + 1];
+    __shared__ bool sh_last;
+    const int s = blockIdx.x, p = blockIdx.y, stride = a.ncp + 3, cstride = a.ncp + 2;
+    const int64_t lo = a.cseg_off[s], hi = a.cseg_off[s + 1];
+    const int ncols = a.seg_cols[s];
+    const int cx = threadIdx.x % SC_COLS, row = threadIdx.x / SC_COLS;
+    const int j = blockIdx.z * SC_COLS + cx;                 // entry of the chunk rows
+    const int64_t CS = 5 * (int64_t)cstride;
+    Comp acc = {0.0, 0.0};
+    if (j < cstride) {
+        const double *x = a.colpart + (int64_t)p * cstride + j;
+        int64_t c = lo + row;
+        for (; c + 3 * SC_ROWS < hi; c += 4 * SC_ROWS) {
+            double v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = __ldg(x + (c + k * SC_ROWS) * CS);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc.add(v[k]);
+        }
+        for (; c < hi; c += SC_ROWS) acc.add(__ldg(x + c * CS));
+    }
+    sh_s[row][cx] = acc.s; sh_c[row][cx] = acc.c;
+    __syncthreads();
+    double *out = a.partials + ((int64_t)s * 5 + p) * stride;
+    if (row == 0 && j < cstride) {
+        Comp t = {0.0, 0.0};
+#pragma unroll
+        for (int r = 0; r < SC_ROWS; ++r) { t.add(sh_s[r][cx]); t.c += sh_c[r][cx]; }
+        const double v = t.value();
+        if (j == 0) out[0] = v;
+        else if (j == 1) { out[2] = v; out[1] = (double)(a.seg_off[s + 1] - a.seg_off[s]); }
+        else out[1 + j] = (j - 2 < ncols) ? v : 0.0;
+    }
+    if (!a.stats) return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int seen = atomicAdd(a.arrived + s * 5 + p, 1u);
+        sh_last = seen == gridDim.z - 1;
+        if (sh_last) a.arrived[s * 5 + p] = 0u;                       // ready for the next launch
+    }
+    __syncthreads();
+    if (!sh_last) return;
+    __threadfence();
+    if (threadIdx.x < 32) segment_finish(out, ncols, a.seg_first[s], a.stats + 3 * ((int64_t)s * 5 + p), threadIdx.x);
 }
 
 // binning() of PLOT_PANEL.py:121-144 / BALANCED_ROC_CURVE.py:131-154: one block per (series, bin).  A bin is a run

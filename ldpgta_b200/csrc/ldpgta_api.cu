@@ -1085,6 +1085,13 @@ int ldpgta_bin_stats(ldpgta_ctx *c, const double *x, int n_series, const int64_t
     } else {
         if (n_series != 5 || c->llr_draws != n_draws || c->llr_windows != n_windows)
             return fail(LDPGTA_E_INVALID, "no resident LLRs for these windows: call ldpgta_window_stats first (5 series)");
+        if (c->llr_lazy_lik && n_draws > 0) {
+            // the statistics pass did not need the LLR matrix; form it now from the likelihoods it left on the device
+            const unsigned blocks = (unsigned)std::min<int64_t>((n_draws + 255) / 256, (int64_t)c->sm_count * 8);
+            k_draw_llr<<<blocks, 256, 0, c->stream>>>(c->llr_lazy_lik, n_draws, const_cast<double *>(c->llr_ptr));
+            c->launches++;
+            c->llr_lazy_lik = nullptr;
+        }
         d_x = c->llr_ptr;
         d_off = c->llr_off_ptr;
     }

@@ -90,10 +90,14 @@ def test_fused_equals_unfused_and_oracle_uniform():
         # replayed draws give the same likelihoods and statistics
         rep = eng.replay_stats(L.HOMOGENEOUS, res['draws'], want=('lik', 'mean_var', 'stats'))
         assert np.array_equal(rep['lik'], res['lik']) and np.array_equal(rep['stats'], res['stats'])
-        # bin_stats on the resident LLRs still works after the fused call
+        # bin_stats on the resident LLRs still works after the fused call -- also after a statistics-only call, which does not
+        # write the LLR matrix (it is then formed from the resident likelihoods on first use)
+        eng.bootstrap_stats(L.HOMOGENEOUS, 99, want=('stats',))
+        bins_lazy = eng.bin_stats(None, doff, [[0, 10], [10, 57]])
         eng.bootstrap_stats(L.HOMOGENEOUS, 99, want=('llr',))
         bins = eng.bin_stats(None, doff, [[0, 10], [10, 57]])
         assert bins.shape == (5, 2, 2) and np.isfinite(bins).all()
+        assert np.array_equal(bins_lazy, bins)
 
 
 def test_fused_consecutive_rows_and_two_groups():
@@ -156,6 +160,36 @@ def test_fused_mixed_draw_sizes():
             eng.replay_stats(L.HOMOGENEOUS, bad)
 
 
+def test_chunked_column_sums_long_segments():
+    """ Segments of hundreds of windows with ragged draw counts <= 32 (the chunked reductions: k_window_stats_chunks +
+    k_segment_from_chunks, every row of the segment kernel busy, an empty segment, a one-window segment) against the
+    reductions of ldpgta_window_stats on the same likelihoods (k_window_stats + k_segment_partials) and the oracle. """
+    rng = np.random.default_rng(21)
+    n_hap = 96
+    rows, woff, wreads, R = make_case(rng, 1500, 4, 9, n_hap=n_hap, shuffle=False)
+    per = rng.integers(5, 33, size=len(R))
+    per[rng.integers(0, len(R), 40)] = 32
+    doff = np.concatenate([[0], np.cumsum(per)]).astype(np.int64)
+    seg_off = np.array([0, 811, 811, 812, 1500], dtype=np.int64)
+    with L.Engine([n_hap]) as eng:
+        eng.upload_read_masks(0, rows)
+        eng.set_windows(woff, None, doff, 3, segment_offsets=seg_off)
+        res = eng.bootstrap_stats(L.HOMOGENEOUS, 5, want=('lik', 'mean_var', 'partials', 'stats'))
+        only = eng.bootstrap_stats(L.HOMOGENEOUS, 5, want=('partials', 'stats'))
+        assert np.array_equal(only['partials'], res['partials']) and np.array_equal(only['stats'], res['stats'], equal_nan=True)
+        for s in (0, 2, 3):
+            lo, hi = doff[seg_off[s]], doff[seg_off[s + 1]]
+            cols = int(per[seg_off[s]:seg_off[s + 1]].min())
+            _, mv, part = eng.window_stats(res['lik'][lo:hi], doff[seg_off[s]:seg_off[s + 1] + 1] - lo, cols)
+            assert np.array_equal(mv, res['mean_var'][:, seg_off[s]:seg_off[s + 1]], equal_nan=True)
+            assert np.allclose(res['partials'][s][:, :cols + 3], part, rtol=1e-13, atol=1e-12)
+            assert not res['partials'][s][:, cols + 3:].any()
+        keep = np.array([0, 300], dtype=np.int64)            # the oracle's statistics() on the first 300 windows as one segment
+        eng.set_windows(woff[:301], None, doff[:301], 3, segment_offsets=keep)
+        sub = eng.bootstrap_stats(L.HOMOGENEOUS, 5, want=('lik', 'mean_var', 'stats'))
+        check_against_oracle(sub, sub['lik'], doff[:301], keep)
+
+
 def test_fused_many_draws_per_window():
     """ 1000 subsamples per window (configs[4]); one window short of the others truncates the columns (:73). """
     rng = np.random.default_rng(14)
@@ -170,6 +204,37 @@ def test_fused_many_draws_per_window():
         assert info['ncp'] == 377
         res = eng.bootstrap_stats(L.HOMOGENEOUS, 7, want=('lik', 'mean_var', 'partials', 'stats'))
         check_against_oracle(res, res['lik'], doff, np.array([0, len(R)]))
+
+
+@pytest.mark.parametrize('most', [33, 256, 300, 512, 2048, 2100])
+def test_fused_window_sizes_of_the_block_kernels(most):
+    """ Windows of 33..2048 draws go through k_window_stats_block<1|2|4|8> (a block per window, column sums per chunk of
+    windows), more than 2048 through k_draw_llr + k_window_stats + k_segment_partials; ragged windows, two segments, one
+    of them longer than a chunk. """
+    rng = np.random.default_rng(100 + most)
+    n_hap = 70
+    rows, woff, wreads, R = make_case(rng, 21, 5, 12, n_hap=n_hap)
+    per = rng.integers(max(2, most // 3), most + 1, size=len(R))
+    per[3] = most
+    doff = np.concatenate([[0], np.cumsum(per)]).astype(np.int64)
+    seg_off = np.array([0, 4, 21], dtype=np.int64)
+    with L.Engine([n_hap]) as eng:
+        eng.upload_read_masks(0, rows)
+        info = eng.set_windows(woff, wreads, doff, 2, segment_offsets=seg_off)
+        assert info['ncp'] == max(per[:4].min(), per[4:].min())
+        res = eng.bootstrap_stats(L.HOMOGENEOUS, 3, want=('lik', 'llr', 'mean_var', 'partials', 'stats'))
+        only = eng.bootstrap_stats(L.HOMOGENEOUS, 3, want=('mean_var', 'partials', 'stats'))
+        for k in ('mean_var', 'partials', 'stats'):
+            assert np.array_equal(only[k], res[k], equal_nan=True), k
+        lazy = eng.bin_stats(None, doff, [[0, 4], [4, 21]])
+        assert np.array_equal(lazy, eng.bin_stats(res['llr'], doff, [[0, 4], [4, 21]]), equal_nan=True)
+        check_against_oracle(res, res['lik'], doff, seg_off)
+        for s in range(2):
+            lo, hi = doff[seg_off[s]], doff[seg_off[s + 1]]
+            cols = int(per[seg_off[s]:seg_off[s + 1]].min())
+            _, mv, part = eng.window_stats(res['lik'][lo:hi], doff[seg_off[s]:seg_off[s + 1] + 1] - lo, cols)
+            assert np.allclose(res['partials'][s][:, :cols + 3], part, rtol=1e-13, atol=1e-12)
+            assert not res['partials'][s][:, cols + 3:].any()
 
 
 def test_shards_of_a_chromosome_add_up():
