@@ -41,6 +41,7 @@ struct WindowPlan {
     // CHUNK_MAX_DRAWS draws
     int64_t n_chunks = 0;
     bool warp_chunks = false;
+    std::vector<int64_t> h_chunk_win;   // host copy of the chunk table (window ranges of the download slices)
     int64_t *d_chunk_win = nullptr, *d_cseg_off = nullptr;
     double *d_colpart = nullptr;
 };
@@ -82,30 +83,42 @@ int launch_sample(ldpgta_ctx *c, int n, const SampleArgs &a)
 static int stats_on_device(ldpgta_ctx *c, const double *d_lik, const int64_t *d_doff, int64_t n_windows, int64_t n_draws,
                            const int64_t *d_segoff, const int32_t *d_segcols, const int32_t *d_segfirst, int n_segments, int ncp,
                            double *d_llr, double *d_mv, double *d_wsum, double *d_split, unsigned int *d_arrived, double *d_partials, double *d_stats,
-                           double *mv_host = nullptr, int64_t max_draws_per_window = 0, const WindowPlan *chunks = nullptr, bool want_llr = true)
+                           double *mv_host = nullptr, int64_t max_draws_per_window = 0, const WindowPlan *chunks = nullptr, bool want_llr = true, bool slice_mv = true)
 {
     if (chunks && chunks->n_chunks > 0 && n_windows > 0) {
         // no window has more than CHUNK_MAX_DRAWS draws: the column sums are formed next to the window statistics, chunk by chunk
         ChunkStatsArgs a;
         a.st.llr = d_llr; a.st.lik = d_lik; a.st.doff = d_doff; a.st.n_windows = n_windows; a.st.n_draws = n_draws; a.st.mean_var = d_mv; a.st.wsum = d_wsum;
         a.chunk_win = chunks->d_chunk_win; a.n_chunks = chunks->n_chunks; a.colpart = chunks->d_colpart; a.ncp = ncp; a.write_llr = want_llr ? 1 : 0;
-        const unsigned blocks = (unsigned)std::min<int64_t>(chunks->n_chunks, (int64_t)c->sm_count * 64);
-        if (max_draws_per_window <= 32) {
-            if (chunks->warp_chunks) k_window_stats_warpchunks<<<(unsigned)std::min<int64_t>((chunks->n_chunks + 7) / 8, (int64_t)c->sm_count * 32), 256, 0, c->stream>>>(a);
-            else k_window_stats_chunks<<<blocks, CH_WIN * 32, 0, c->stream>>>(a);
-        }
-        // threads x draws per thread by the longest window; the register budget (LLRs + column sums of DPT draws per pair)
-        // decides how many blocks share an SM while one of them sits in a barrier
-        else if (max_draws_per_window <= 256) k_window_stats_block<1, 256, 4><<<blocks, 256, 0, c->stream>>>(a);
-        else if (max_draws_per_window <= 512) k_window_stats_block<2, 256, 4><<<blocks, 256, 0, c->stream>>>(a);
-        else if (max_draws_per_window <= 1024) k_window_stats_block<4, 256, 2><<<blocks, 256, 0, c->stream>>>(a);      // measured: <2, 512, 2> is 20 % slower
-        else k_window_stats_block<4, 512, 1><<<blocks, 512, 0, c->stream>>>(a);
-        c->launches++;
-        if (mv_host) {
-            if (int rc = ensure_pipeline(c, 2)) return rc;
-            LDPGTA_CUDA(cudaEventRecord(c->ev_in[0], c->stream));
-            LDPGTA_CUDA(cudaStreamWaitEvent(c->s_out, c->ev_in[0], 0));
-            LDPGTA_CUDA(cudaMemcpyAsync(mv_host, d_mv, (size_t)n_windows * 80, cudaMemcpyDeviceToHost, c->s_out));
+        // the window statistics (80 bytes per window) go down while later windows are still being reduced: the chunks are cut
+        // into slices, slice i's rows of mean_var[5][n_windows][2] travel under the kernel of slice i + 1
+        static const int max_slices = [] { const char *e = getenv("LDPGTA_STATS_SLICES"); return e && atoi(e) > 0 ? atoi(e) : 2; }();      // measured on configs[1]: 1 / 2 / 4 / 8 slices -> 0.504 / 0.492 / 0.493 / 0.513 ms per call
+        const int n_slices = mv_host && slice_mv ? (int)std::max<int64_t>(1, std::min<int64_t>(max_slices, chunks->n_chunks / 512)) : 1;
+        if (mv_host) if (int rc = ensure_pipeline(c, n_slices + 1)) return rc;
+        const int64_t per_slice = (chunks->n_chunks + n_slices - 1) / n_slices;
+        int si = 0;
+        for (int64_t c0 = 0; c0 < chunks->n_chunks; c0 += per_slice, ++si) {
+            const int64_t c1 = std::min(c0 + per_slice, chunks->n_chunks);
+            a.chunk_win = chunks->d_chunk_win + c0; a.n_chunks = c1 - c0; a.colpart = chunks->d_colpart + c0 * 5 * (ncp + 2);
+            const unsigned blocks = (unsigned)std::min<int64_t>(a.n_chunks, (int64_t)c->sm_count * 64);
+            if (max_draws_per_window <= 32) {
+                if (chunks->warp_chunks) k_window_stats_warpchunks<<<(unsigned)std::min<int64_t>((a.n_chunks + 7) / 8, (int64_t)c->sm_count * 32), 256, 0, c->stream>>>(a);
+                else k_window_stats_chunks<<<blocks, CH_WIN * 32, 0, c->stream>>>(a);
+            }
+            // threads x draws per thread by the longest window; the register budget (LLRs + column sums of DPT draws per pair)
+            // decides how many blocks share an SM while one of them sits in a barrier
+            else if (max_draws_per_window <= 256) k_window_stats_block<1, 256, 4><<<blocks, 256, 0, c->stream>>>(a);
+            else if (max_draws_per_window <= 512) k_window_stats_block<2, 256, 4><<<blocks, 256, 0, c->stream>>>(a);
+            else if (max_draws_per_window <= 1024) k_window_stats_block<4, 256, 2><<<blocks, 256, 0, c->stream>>>(a);      // measured: <2, 512, 2> is 20 % slower
+            else k_window_stats_block<4, 512, 1><<<blocks, 512, 0, c->stream>>>(a);
+            c->launches++;
+            if (mv_host) {
+                const int64_t w_lo = chunks->h_chunk_win[c0], w_hi = chunks->h_chunk_win[c1];
+                LDPGTA_CUDA(cudaEventRecord(c->ev_in[si], c->stream));
+                LDPGTA_CUDA(cudaStreamWaitEvent(c->s_out, c->ev_in[si], 0));
+                LDPGTA_CUDA(cudaMemcpy2DAsync(mv_host + 2 * w_lo, (size_t)n_windows * 16, d_mv + 2 * w_lo, (size_t)n_windows * 16, (size_t)(w_hi - w_lo) * 16, 5,
+                                              cudaMemcpyDeviceToHost, c->s_out));
+            }
         }
         SegChunkArgs sa;
         sa.colpart = chunks->d_colpart; sa.cseg_off = chunks->d_cseg_off; sa.seg_off = d_segoff; sa.seg_cols = d_segcols; sa.seg_first = d_segfirst;
@@ -266,7 +279,7 @@ static int reduce_and_download(ldpgta_ctx *c, WindowPlan *p, double *lik_out, do
     const bool lazy = !llr_fused(p) && p->n_chunks > 0 && !llr_out;
     if (int rc = stats_on_device(c, llr_fused(p) ? nullptr : p->d_lik, p->d_doff, p->n_windows, p->n_draws, p->d_segoff, p->d_segcols, p->d_segfirst,
                                  p->n_segments, p->ncp, d_llr, p->d_mv, p->d_wsum, p->d_split, p->d_arrived, p->d_partials, p->d_stats, window_mean_var, p->max_draws,
-                                 p, !lazy))
+                                 p, !lazy, !lik_out))                 // the likelihoods' own download keeps the copy engine busy: no slices
         return rc;
     const size_t cp_b = (size_t)p->n_segments * 5 * (p->ncp + 3) * 8;
     if (segment_partials) LDPGTA_CUDA(cudaMemcpyAsync(segment_partials, p->d_partials, cp_b, cudaMemcpyDeviceToHost, c->stream));
@@ -397,6 +410,7 @@ int ldpgta_set_windows(ldpgta_ctx *c, const int64_t *window_offsets, const int32
     if (p->n_wreads) memcpy(img.data() + o_wreads, window_reads, (size_t)p->n_wreads * 4);
     if (p->n_chunks) {
         memcpy(img.data() + o_chunk, chunk_win.data(), chunk_win.size() * 8);
+        p->h_chunk_win = chunk_win;
         memcpy(img.data() + o_cseg, cseg_off.data(), cseg_off.size() * 8);
     }
     for (size_t ci = 0; ci < p->classes.size(); ++ci) {

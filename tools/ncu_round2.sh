@@ -12,10 +12,10 @@ echo "launch list rc=$?"
 summarise() {   # <report> <units per launch> <out>
   python tools/ncu_summary.py $1 > $3 2>&1; python tools/ncu_opmix.py $1 $2 >> $3 2>&1; rm -f $1
 }
-for k in k_small k_window_stats k_segment_partials k_sample_draws; do
+for k in k_small k_window_stats_chunks k_segment_from_chunks k_sample_draws; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -o gpurun_out/r02_$k -f python bench.py $A > gpurun_out/ncu_$k.log 2>&1
   echo "$k rc=$?"
-  case $k in k_small) U=229904;; k_window_stats) U=28738;; k_segment_partials) U=110;; *) U=919616;; esac    # tiles of 4 draws / windows / blocks / draws
+  case $k in k_small) U=229904;; k_window_stats_chunks) U=28738;; k_segment_from_chunks) U=220;; *) U=919616;; esac    # tiles of 4 draws / windows / blocks / draws
   summarise gpurun_out/r02_$k.ncu-rep $U gpurun_out/r02_ncu_$k.txt
 done
 G="--steps 1 --warmup 3 --no-cpu-baseline --max-reads 16 --windows 592 --subsamples 2 --depth 0.2"
