@@ -237,7 +237,9 @@ int ldpgta_comm_destroy(ldpgta_ctx *ctx);
 
 /* Measurement aid: with enable != 0 the calls above bracket their draw kernels (k_small / k_mid / k_lanes / k_general, not
  * the sampler or the reductions) with CUDA events on the context's stream; ldpgta_kernel_times waits for the stream,
- * writes the elapsed milliseconds of every bracket since the last call (at most max_entries) and returns their number. */
+ * writes the elapsed milliseconds of every bracket since the last call (at most max_entries) and returns their number.
+ * enable == 2 brackets the reductions of ldpgta_bootstrap_stats_dev (window statistics + segment sums) instead, 3 its
+ * window-statistics kernel alone, 4 its sampler. */
 int ldpgta_kernel_timing(ldpgta_ctx *ctx, int enable);
 int ldpgta_kernel_times(ldpgta_ctx *ctx, double *ms_out, int max_entries);
 /* out[10] = n_windows, n_draws, n_segments, ncp, number of draw-size classes, total read indices of the plan, and the

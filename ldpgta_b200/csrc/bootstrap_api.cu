@@ -78,6 +78,18 @@ int launch_sample(ldpgta_ctx *c, int n, const SampleArgs &a)
     return 0;
 }
 
+static int time_mark(ldpgta_ctx *c, int what = 1)
+{
+    if (c->time_kernels != what) return 0;
+    if (c->t_used == c->t_ev.size()) {
+        cudaEvent_t e;
+        LDPGTA_CUDA(cudaEventCreate(&e));
+        c->t_ev.push_back(e);
+    }
+    LDPGTA_CUDA(cudaEventRecord(c->t_ev[c->t_used++], c->stream));
+    return 0;
+}
+
 // LLRs (when not already written by the draw kernels), window mean / variance, segment partial sums and (optionally) the
 // finished segment statistics, all on c->stream
 static int stats_on_device(ldpgta_ctx *c, const double *d_lik, const int64_t *d_doff, int64_t n_windows, int64_t n_draws,
@@ -97,13 +109,14 @@ static int stats_on_device(ldpgta_ctx *c, const double *d_lik, const int64_t *d_
         if (mv_host) if (int rc = ensure_pipeline(c, n_slices + 1)) return rc;
         const int64_t per_slice = (chunks->n_chunks + n_slices - 1) / n_slices;
         int si = 0;
+        if (int rc = time_mark(c, 3)) return rc;
         for (int64_t c0 = 0; c0 < chunks->n_chunks; c0 += per_slice, ++si) {
             const int64_t c1 = std::min(c0 + per_slice, chunks->n_chunks);
             a.chunk_win = chunks->d_chunk_win + c0; a.n_chunks = c1 - c0; a.colpart = chunks->d_colpart + c0 * 5 * (ncp + 2);
             const unsigned blocks = (unsigned)std::min<int64_t>(a.n_chunks, (int64_t)c->sm_count * 64);
             if (max_draws_per_window <= 32) {
                 if (chunks->warp_chunks) k_window_stats_warpchunks<<<(unsigned)std::min<int64_t>((a.n_chunks + 7) / 8, (int64_t)c->sm_count * 32), 256, 0, c->stream>>>(a);
-                else k_window_stats_chunks<<<blocks, CH_WIN * 32, 0, c->stream>>>(a);
+                else k_window_stats_chunks<<<blocks, CH_WIN * 32, 0, c->stream>>>(a);       // persistent blocks with the next chunk's loads in flight: measured no faster
             }
             // threads x draws per thread by the longest window; the register budget (LLRs + column sums of DPT draws per pair)
             // decides how many blocks share an SM while one of them sits in a barrier
@@ -120,6 +133,7 @@ static int stats_on_device(ldpgta_ctx *c, const double *d_lik, const int64_t *d_
                                               cudaMemcpyDeviceToHost, c->s_out));
             }
         }
+        if (int rc = time_mark(c, 3)) return rc;
         SegChunkArgs sa;
         sa.colpart = chunks->d_colpart; sa.cseg_off = chunks->d_cseg_off; sa.seg_off = d_segoff; sa.seg_cols = d_segcols; sa.seg_first = d_segfirst;
         sa.ncp = ncp; sa.partials = d_partials; sa.stats = d_stats; sa.arrived = d_arrived;
@@ -172,18 +186,6 @@ static bool llr_fused(const WindowPlan *p)
     for (const SizeClass &k : p->classes)
         if (k.n <= 4) return false;
     return true;
-}
-
-static int time_mark(ldpgta_ctx *c)
-{
-    if (!c->time_kernels) return 0;
-    if (c->t_used == c->t_ev.size()) {
-        cudaEvent_t e;
-        LDPGTA_CUDA(cudaEventCreate(&e));
-        c->t_ev.push_back(e);
-    }
-    LDPGTA_CUDA(cudaEventRecord(c->t_ev[c->t_used++], c->stream));
-    return 0;
 }
 
 // idx_up: page-locked host draws of a one-class plan that still have to go up (ldpgta_replay_stats); lim = reads in the table
@@ -597,6 +599,7 @@ int ldpgta_bootstrap_stats_dev(ldpgta_ctx *c, int kind, uint64_t seed, const dou
     LDPGTA_CUDA(cudaSetDevice(c->device));
     WindowPlan *p = c->plan;
     if (!p->has_windows) return fail(LDPGTA_E_STATE, "the resident plan has no window read lists");
+    if (int rc = time_mark(c, 4)) return rc;
     for (const SizeClass &k : p->classes) {
         SampleArgs sa;
         memset(&sa, 0, sizeof sa);
@@ -604,12 +607,16 @@ int ldpgta_bootstrap_stats_dev(ldpgta_ctx *c, int kind, uint64_t seed, const dou
         sa.n_windows = k.n_windows; sa.n_draws = k.n_draws; sa.seed = seed + (uint64_t)k.n; sa.idx_out = k.d_idx;
         if (int rc = launch_sample(c, k.n, sa)) return rc;
     }
+    if (int rc = time_mark(c, 4)) return rc;
     if (int rc = evaluate_classes(c, p, kind, proportions, nullptr)) return rc;
     // the resident likelihoods change and the LLR matrix is not written: what ldpgta_bin_stats would read is gone
     if (c->llr_ptr == p->d_llr) { c->llr_draws = c->llr_windows = -1; c->llr_lazy_lik = nullptr; }
-    return stats_on_device(c, llr_fused(p) ? nullptr : p->d_lik, p->d_doff, p->n_windows, p->n_draws, p->d_segoff, p->d_segcols, p->d_segfirst, p->n_segments,
+    if (int rc = time_mark(c, 2)) return rc;
+    const int rc_stats = stats_on_device(c, llr_fused(p) ? nullptr : p->d_lik, p->d_doff, p->n_windows, p->n_draws, p->d_segoff, p->d_segcols, p->d_segfirst, p->n_segments,
                            p->ncp, p->d_llr, p->d_mv, p->d_wsum, p->d_split, p->d_arrived, segment_partials_dev ? segment_partials_dev : p->d_partials,
                            segment_partials_dev ? nullptr : p->d_stats, nullptr, p->max_draws, p, false);
+    if (rc_stats) return rc_stats;
+    return time_mark(c, 2);
 }
 
 int ldpgta_finish_segments_dev(ldpgta_ctx *c, const double *segment_partials_dev, double *segment_stats_dev)
@@ -628,7 +635,7 @@ int ldpgta_finish_segments_dev(ldpgta_ctx *c, const double *segment_partials_dev
 int ldpgta_kernel_timing(ldpgta_ctx *c, int enable)
 {
     if (!c) return fail(LDPGTA_E_INVALID, "null context");
-    c->time_kernels = enable != 0;
+    c->time_kernels = enable >= 2 && enable <= 4 ? enable : (enable != 0);
     c->t_used = 0;
     return 0;
 }

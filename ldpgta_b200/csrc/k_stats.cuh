@@ -242,6 +242,17 @@ static __global__ void k_read_scores_long(const ScoreArgs a)
 static __device__ __constant__ int c_pair_num[5] = {3, 1, 3, 1, 2};
 static __device__ __constant__ int c_pair_den[5] = {2, 0, 1, 2, 0};
 
+// the five LLRs of one draw from v = (monosomy, disomy, SPH, BPH), pairs as above with compile-time indices (indexing v[]
+// through the constant tables would put it in local memory)
+__device__ __forceinline__ void five_llrs(const double (&v)[4], double (&x)[5])
+{
+    x[0] = llr_of(v[3], v[2]);
+    x[1] = llr_of(v[1], v[0]);
+    x[2] = llr_of(v[3], v[1]);
+    x[3] = llr_of(v[1], v[2]);
+    x[4] = llr_of(v[2], v[0]);
+}
+
 // error-free accumulation (Neumaier) so that window means match the reference's
 // exact-rational statistics.mean/variance (ANEUPLOIDY_TEST.py:51-56) to the last bits
 struct Comp {
@@ -280,8 +291,10 @@ static __global__ void k_draw_llr(const double *__restrict__ lik, int64_t n_draw
     for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < n_draws; d += (int64_t)gridDim.x * blockDim.x) {
         const double2 a = __ldg(reinterpret_cast<const double2 *>(lik) + 2 * d), b = __ldg(reinterpret_cast<const double2 *>(lik) + 2 * d + 1);
         const double v[4] = {a.x, a.y, b.x, b.y};
+        double x[5];
+        five_llrs(v, x);
 #pragma unroll
-        for (int p = 0; p < 5; ++p) out[p * n_draws + d] = llr_of(v[c_pair_num[p]], v[c_pair_den[p]]);
+        for (int p = 0; p < 5; ++p) out[p * n_draws + d] = x[p];
     }
 }
 
@@ -310,11 +323,10 @@ __device__ __forceinline__ void window_le32(const StatsArgs &a, int64_t w, int64
                           u1 = __ldg(reinterpret_cast<const double2 *>(a.lik) + 2 * (b + lane) + 1);
             v[0] = u0.x; v[1] = u0.y; v[2] = u1.x; v[3] = u1.y;
         }
+        five_llrs(v, x);                                   // lanes without a draw: LLR(0, 0) = 0
 #pragma unroll
-        for (int p = 0; p < 5; ++p) {
-            x[p] = live ? llr_of(v[c_pair_num[p]], v[c_pair_den[p]]) : 0.0;
+        for (int p = 0; p < 5; ++p)
             if (live && write_llr) a.llr[(int64_t)p * a.n_draws + b + lane] = x[p];
-        }
     } else {
 #pragma unroll
         for (int p = 0; p < 5; ++p) x[p] = live ? a.llr[(int64_t)p * a.n_draws + b + lane] : 0.0;
@@ -659,11 +671,13 @@ static __global__ void __launch_bounds__(NT, MINB) k_window_stats_block(const Ch
                 const int64_t i = b + t + NT * j;
                 const bool live = i < e;
                 if (a.st.lik) {
-                    const double v[4] = {cur[j][0].x, cur[j][0].y, cur[j][1].x, cur[j][1].y};
+                    const double v[4] = {cur[j][0].x, cur[j][0].y, cur[j][1].x, cur[j][1].y};      // zeros without a draw: LLR(0, 0) = 0
+                    double xj[5];
+                    five_llrs(v, xj);
 #pragma unroll
                     for (int p = 0; p < 5; ++p) {
-                        x[p][j] = live ? llr_of(v[c_pair_num[p]], v[c_pair_den[p]]) : 0.0;
-                        if (live && a.write_llr) a.st.llr[(int64_t)p * a.st.n_draws + i] = x[p][j];
+                        x[p][j] = xj[p];
+                        if (live && a.write_llr) a.st.llr[(int64_t)p * a.st.n_draws + i] = xj[p];
                     }
                 } else {
 #pragma unroll

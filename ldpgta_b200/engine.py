@@ -368,8 +368,9 @@ class Engine:
         N.check(self.lib.ldpgta_comm_destroy(self._ctx))
 
     def kernel_timing(self, enable=True):
-        """ CUDA-event brackets around the draw kernels of bootstrap_stats / replay_stats (measurement aid). """
-        N.check(self.lib.ldpgta_kernel_timing(self._ctx, 1 if enable else 0))
+        """ CUDA-event brackets around the draw kernels of bootstrap_stats / replay_stats (measurement aid);
+        enable=2: around the reductions of bootstrap_stats_dev instead, 3: its window-statistics kernel, 4: its sampler. """
+        N.check(self.lib.ldpgta_kernel_timing(self._ctx, int(enable) if enable in (2, 3, 4) else (1 if enable else 0)))
 
     def kernel_times(self, max_entries=65536):
         """ milliseconds of every bracket since the last call (waits for the stream) """

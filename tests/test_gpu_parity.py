@@ -545,8 +545,10 @@ def test_window_stats_against_python_statistics():
         assert abs(chrom[p, 0] - c['mean_of_mean']) <= STAT_TOL * max(1, abs(c['mean_of_mean']))
         assert abs(chrom[p, 1] - c['std_of_mean']) <= STAT_TOL * max(1, abs(c['std_of_mean']))
         assert chrom[p, 2] == c['fraction_of_negative_LLRs']
-        ref_llr = [O.LLR(getattr(l, pair[0]), getattr(l, pair[1])) for ls in likd.values() for l in ls]
-        assert max_rel(llr[p], ref_llr) < 1e-14
+        # the device forms log(y / x) without rounding the quotient first (common.cuh: log_ratio); math.log(y / x) carries
+        # that rounding: up to 2^-53 absolute, which is all of the difference when y ~ x
+        ref_llr = np.array([O.LLR(getattr(l, pair[0]), getattr(l, pair[1])) for ls in likd.values() for l in ls])
+        assert np.all(np.abs(llr[p] - ref_llr) <= 1e-15 * np.abs(ref_llr) + 1.2e-16)
     # sharding: partials of two halves of the chromosome add up to the whole (the only cross-GPU exchange)
     with L.Engine([1]) as eng:
         h = 100
@@ -554,6 +556,53 @@ def test_window_stats_against_python_statistics():
         _, _, p2 = eng.window_stats(lik[off[h]:], off[h:] - off[h], n_cols)
     both = L.finish_chromosome(p1 + p2, n_cols, int(counts[0]))
     assert np.max(np.abs(both - chrom)) < 1e-12
+
+
+def test_llr_log_ratio_accuracy():
+    """ LLR = log(y / x) (ANEUPLOIDY_TEST.py:78-90) on the device: one division for quotient and atanh argument
+    (common.cuh: log_ratio).  Against a long-double value of the true logarithm it stays within 2.5 ulp -- relative accuracy
+    also where y ~ x -- and it is never further from the reference's math.log(y / x) than that value's own error bound
+    (1 ulp + the 2^-53 of the rounded quotient).  Subnormal likelihoods take the library route; zeros give the sentinels. """
+    rng = np.random.default_rng(31)
+    n = 32 * 4000
+    y = np.exp(-40.0 * rng.random(n))
+    x = y * (1.0 + (rng.random(n) - 0.5) * 2.0 ** (-rng.integers(0, 45, size=n)))
+    far = slice(0, n // 4)                                                          # far apart: |log| up to ~600
+    y[far], x[far] = np.exp(-600.0 * rng.random(n // 4)), np.exp(-600.0 * rng.random(n // 4))
+    edge = slice(n // 4, n // 4 + 4000)                                             # at the range-reduction boundaries
+    x[edge] = y[edge] * (np.where(rng.random(4000) < 0.5, 2.0 ** 0.5, 0.5 ** 0.5) + 1e-7 * (rng.random(4000) - 0.5))
+    x[-64:-32] = y[-64:-32]                                                         # equal: exactly 0
+    y[-32:-16] = 5e-324 * rng.integers(1, 1000, size=16)                           # subnormal numerators
+    x[-16:] = 5e-324 * rng.integers(1, 1000, size=16)                              # subnormal denominators
+    lik = np.ones((n, 4))
+    lik[:, 3], lik[:, 2] = y, x                                                    # pair 0 = (BPH, SPH)
+    off = np.arange(0, n + 1, 32, dtype=np.int64)
+    with L.Engine([1]) as eng:
+        llr, _, _ = eng.window_stats(lik, off, 32)
+    got = llr[0]
+    yl, xl = y.astype(np.longdouble), x.astype(np.longdouble)
+    near = (y > 0.5 * x) & (y < 2.0 * x)
+    truth = np.where(near, np.log1p((yl - xl) / xl), np.log(yl / xl))
+    ulp = np.spacing(np.abs(truth.astype(np.float64)))
+    err = np.abs(got.astype(np.longdouble) - truth).astype(np.float64)
+    normal = (y >= 2.3e-308) & (x >= 2.3e-308)
+    assert np.all(err[normal] <= 2.5 * ulp[normal]), float(np.max(err[normal] / ulp[normal]))      # 1.99 on a host model of the routine over 2e7 pairs
+    # subnormal likelihoods: the library's division and logarithm, i.e. the reference's own arithmetic (a subnormal quotient
+    # has lost bits, an overflowing one gives inf, exactly as CPython's y / x does)
+    with np.errstate(over='ignore', divide='ignore'):
+        ref = np.log(y / x)
+    sub = ~normal
+    assert np.array_equal(np.isinf(got[sub]), np.isinf(ref[sub]))
+    fin = sub & np.isfinite(ref)
+    assert np.all(np.abs(got[fin] - ref[fin]) <= 2.0 * np.spacing(np.abs(ref[fin])))
+    assert np.all(np.abs(got[normal] - ref[normal]) <= 3.0 * ulp[normal] + 2.0 ** -53)
+    assert np.all(got[-64:-32] == 0.0)
+    assert np.all(llr[1] == 0.0)                                                   # (disomy, monosomy) = log(1 / 1)
+    # sentinels (:83-85)
+    lik2 = np.array([[0.0, 1.0, 0.0, 1.0], [1.0, 0.0, 1.0, 0.0], [0.0, 0.0, 0.0, 0.0]])
+    with L.Engine([1]) as eng:
+        s, _, _ = eng.window_stats(lik2, np.array([0, 3], dtype=np.int64), 3)
+    assert s[0].tolist() == [1.23456789, -1.23456789, 0.0] and s[1].tolist() == [1.23456789, -1.23456789, 0.0]
 
 
 def test_same_seed_reproduces_reference_without_replay(golden_inputs):
