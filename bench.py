@@ -391,7 +391,7 @@ class Leg:
             ev0.record(self.stream); self.step(); ev1.record(self.stream)
             self.eng.synchronize()
             steps = max(steps, min(20000, int(min_seconds * 1e3 / max(ev0.elapsed_time(ev1), 1e-3)) + 1))
-        self.eng.kernel_timing(True)
+        self.eng.kernel_timing(True, stride=4)                    # the draw kernel of every fourth step is bracketed (a pair of events costs ~5 us)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
         ev[0].record(self.stream)
         for k in range(steps):

@@ -239,7 +239,8 @@ int ldpgta_comm_destroy(ldpgta_ctx *ctx);
  * the sampler or the reductions) with CUDA events on the context's stream; ldpgta_kernel_times waits for the stream,
  * writes the elapsed milliseconds of every bracket since the last call (at most max_entries) and returns their number.
  * enable == 2 brackets the reductions of ldpgta_bootstrap_stats_dev (window statistics + segment sums) instead, 3 its
- * window-statistics kernel alone, 4 its sampler. */
+ * window-statistics kernel alone, 4 its sampler.  Bits 8..23 of enable = stride k: only every k-th bracket is recorded (a pair
+ * of events costs the stream about 5 us, 1 % of a configs[1] step). */
 int ldpgta_kernel_timing(ldpgta_ctx *ctx, int enable);
 int ldpgta_kernel_times(ldpgta_ctx *ctx, double *ms_out, int max_entries);
 /* out[10] = n_windows, n_draws, n_segments, ncp, number of draw-size classes, total read indices of the plan, and the

@@ -81,6 +81,9 @@ int launch_sample(ldpgta_ctx *c, int n, const SampleArgs &a)
 static int time_mark(ldpgta_ctx *c, int what = 1)
 {
     if (c->time_kernels != what) return 0;
+    // marks come in (start, stop) pairs: bracket number t_marks / 2 is recorded when it is a multiple of the stride
+    const uint64_t bracket = c->t_marks++ / 2;
+    if (c->t_stride > 1 && bracket % (uint64_t)c->t_stride) return 0;
     if (c->t_used == c->t_ev.size()) {
         cudaEvent_t e;
         LDPGTA_CUDA(cudaEventCreate(&e));
@@ -635,7 +638,10 @@ int ldpgta_finish_segments_dev(ldpgta_ctx *c, const double *segment_partials_dev
 int ldpgta_kernel_timing(ldpgta_ctx *c, int enable)
 {
     if (!c) return fail(LDPGTA_E_INVALID, "null context");
-    c->time_kernels = enable >= 2 && enable <= 4 ? enable : (enable != 0);
+    const int mode = enable & 0xff, stride = (enable >> 8) & 0xffff;
+    c->time_kernels = mode >= 2 && mode <= 4 ? mode : (mode != 0);
+    c->t_stride = stride > 1 ? stride : 1;
+    c->t_marks = 0;
     c->t_used = 0;
     return 0;
 }

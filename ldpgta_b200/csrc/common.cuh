@@ -320,6 +320,8 @@ struct ldpgta_ctx {
     int time_kernels = 0;            // 1: events around the draw kernels, 2: around the reductions instead (ldpgta_kernel_timing)
     std::vector<cudaEvent_t> t_ev;      // pairs (start, stop), reused
     size_t t_used = 0;
+    int t_stride = 1;                // only every t_stride-th bracket is recorded (an event pair costs the stream ~5 us)
+    uint64_t t_marks = 0;
 
     int64_t launches = 0;
 };

@@ -367,10 +367,12 @@ class Engine:
     def comm_destroy(self):
         N.check(self.lib.ldpgta_comm_destroy(self._ctx))
 
-    def kernel_timing(self, enable=True):
+    def kernel_timing(self, enable=True, stride=1):
         """ CUDA-event brackets around the draw kernels of bootstrap_stats / replay_stats (measurement aid);
-        enable=2: around the reductions of bootstrap_stats_dev instead, 3: its window-statistics kernel, 4: its sampler. """
-        N.check(self.lib.ldpgta_kernel_timing(self._ctx, int(enable) if enable in (2, 3, 4) else (1 if enable else 0)))
+        enable=2: around the reductions of bootstrap_stats_dev instead, 3: its window-statistics kernel, 4: its sampler.
+        stride=k records only every k-th bracket (an event pair costs the stream about 5 us). """
+        mode = int(enable) if enable in (2, 3, 4) else (1 if enable else 0)
+        N.check(self.lib.ldpgta_kernel_timing(self._ctx, mode | (max(1, int(stride)) << 8 if mode else 0)))
 
     def kernel_times(self, max_entries=65536):
         """ milliseconds of every bracket since the last call (waits for the stream) """
