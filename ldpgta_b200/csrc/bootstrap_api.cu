@@ -108,7 +108,8 @@ static int stats_on_device(ldpgta_ctx *c, const double *d_lik, const int64_t *d_
         // the window statistics (80 bytes per window) go down while later windows are still being reduced: the chunks are cut
         // into slices, slice i's rows of mean_var[5][n_windows][2] travel under the kernel of slice i + 1
         static const int max_slices = [] { const char *e = getenv("LDPGTA_STATS_SLICES"); return e && atoi(e) > 0 ? atoi(e) : 2; }();      // measured on configs[1]: 1 / 2 / 4 / 8 slices -> 0.504 / 0.492 / 0.493 / 0.513 ms per call
-        const int n_slices = mv_host && slice_mv ? (int)std::max<int64_t>(1, std::min<int64_t>(max_slices, chunks->n_chunks / 512)) : 1;
+        // (pageable destinations make every copy a synchronous staged one: no slices there)
+        const int n_slices = mv_host && slice_mv && is_page_locked(mv_host) ? (int)std::max<int64_t>(1, std::min<int64_t>(max_slices, chunks->n_chunks / 512)) : 1;
         if (mv_host) if (int rc = ensure_pipeline(c, n_slices + 1)) return rc;
         const int64_t per_slice = (chunks->n_chunks + n_slices - 1) / n_slices;
         int si = 0;

@@ -206,6 +206,38 @@ def test_fused_many_draws_per_window():
         check_against_oracle(res, res['lik'], doff, np.array([0, len(R)]))
 
 
+def test_sliced_statistics_download_into_pinned_buffers():
+    """ With page-locked result buffers and enough chunks the window statistics go down in slices under the reductions of
+    the later windows (strided 2-D copies into mean_var[5][n_windows][2]); same numbers as the one-copy route that
+    pageable buffers take, also when the likelihoods are downloaded in the same call. """
+    rng = np.random.default_rng(23)
+    n_hap, n_win = 64, 9001                                       # 1126 chunks: two slices
+    rows, woff, wreads, R = make_case(rng, n_win, 3, 6, n_hap=n_hap, shuffle=False)
+    per = rng.integers(2, 6, size=n_win)
+    doff = np.concatenate([[0], np.cumsum(per)]).astype(np.int64)
+    seg_off = np.array([0, 4000, n_win], dtype=np.int64)
+    with L.Engine([n_hap]) as eng:
+        eng.upload_read_masks(0, rows)
+        info = eng.set_windows(woff, None, doff, 2, segment_offsets=seg_off)
+        plain = eng.bootstrap_stats(L.HOMOGENEOUS, 77, want=('lik', 'mean_var', 'partials', 'stats'))
+        pins = {'mean_var': L.PinnedArray((5, n_win, 2), np.float64), 'stats': L.PinnedArray((2, 5, 3), np.float64),
+                'lik': L.PinnedArray((int(doff[-1]), 4), np.float64)}
+        for p_ in pins.values():
+            p_.array[...] = -7.0
+        out = {'mean_var': pins['mean_var'].array, 'stats': pins['stats'].array}
+        eng.bootstrap_stats(L.HOMOGENEOUS, 77, out=out)
+        assert np.array_equal(out['mean_var'], plain['mean_var'], equal_nan=True) and np.array_equal(out['stats'], plain['stats'])
+        out['mean_var'][...] = -7.0
+        out['lik'] = pins['lik'].array
+        eng.bootstrap_stats(L.HOMOGENEOUS, 77, out=out)
+        assert np.array_equal(out['lik'], plain['lik']) and np.array_equal(out['mean_var'], plain['mean_var'], equal_nan=True)
+        rep = eng.replay_stats(L.HOMOGENEOUS, eng.bootstrap_stats(L.HOMOGENEOUS, 77, want=('draws',))['draws'],
+                               out={'mean_var': pins['mean_var'].array, 'stats': pins['stats'].array})
+        assert np.array_equal(rep['mean_var'], plain['mean_var'], equal_nan=True) and np.array_equal(rep['stats'], plain['stats'])
+    for p_ in pins.values():
+        p_.free()
+
+
 @pytest.mark.parametrize('most', [33, 256, 300, 512, 2048, 2100])
 def test_fused_window_sizes_of_the_block_kernels(most):
     """ Windows of 33..2048 draws go through k_window_stats_block<1|2|4|8> (a block per window, column sums per chunk of
