@@ -27,6 +27,8 @@ struct WindowPlan {
     int64_t n_windows = 0, n_draws = 0, n_wreads = 0, nnz = 0;
     int n_segments = 0, ncp = 0;
     int64_t max_draws = 0;         // most draws of a window
+    int64_t max_rows = 0;          // most reads of a window (0 without window read ranges)
+    bool consecutive = false;      // windows are runs of consecutive rows of the read-mask table
     bool has_windows = false;
     void *d_static = nullptr, *d_work = nullptr;
     int64_t *d_woff = nullptr, *d_doff = nullptr, *d_segoff = nullptr;
@@ -250,6 +252,22 @@ static int evaluate_classes_inner(ldpgta_ctx *c, WindowPlan *p, int kind, const 
         }
         return 0;
     }
+    // many draws per window (e.g. 1000 subsamples), 4 reads each, windows = runs of consecutive rows: the window-resident kernel
+    static const int64_t win_min_draws = [] { const char *e = getenv("LDPGTA_WIN_MIN_DRAWS"); return e ? (int64_t)atoll(e) : (int64_t)256; }();
+    if (p->classes.size() == 1 && p->classes[0].n == 4 && kind == LDPGTA_HOMOGENEOUS && p->consecutive && win_min_draws > 0 &&
+        p->n_draws >= win_min_draws * p->n_windows) {
+        const int rc = launch_small_windows(c, p->classes[0].d_idx, p->n_draws, p->d_lik, p->d_woff, p->d_doff, p->n_windows, p->max_rows);
+        if (rc < 0) return rc;
+        if (rc == 0) {
+            if (lik_out_pinned) {
+                if (int rc2 = ensure_pipeline(c, 2)) return rc2;
+                LDPGTA_CUDA(cudaEventRecord(c->ev_k[0], c->stream));
+                LDPGTA_CUDA(cudaStreamWaitEvent(c->s_out, c->ev_k[0], 0));
+                LDPGTA_CUDA(cudaMemcpyAsync(lik_out_pinned, p->d_lik, (size_t)p->n_draws * 32, cudaMemcpyDeviceToHost, c->s_out));
+            }
+            return 0;
+        }
+    }
     for (const SizeClass &k : p->classes)
         if (int rc = run_uniform(c, kind, k.n, k.d_idx, k.n_draws, k.d_pos, proportions, p->d_lik, nullptr, false, nullptr,
                                  llr_fused(p) ? p->d_llr : nullptr, p->n_draws))
@@ -324,7 +342,7 @@ int ldpgta_set_windows(ldpgta_ctx *c, const int64_t *window_offsets, const int32
     for (int s = 0; s < n_segments; ++s)
         if (segment_offsets[s + 1] < segment_offsets[s]) return fail(LDPGTA_E_INVALID, "segment_offsets must not decrease (segment %d)", s);
     int64_t per_n[MAXN + 1] = {}, win_n[MAXN + 1] = {}, nnz = 0;
-    int64_t max_draws = 0;
+    int64_t max_draws = 0, max_rows = 0;
     for (int64_t w = 0; w < n_windows; ++w) {
         const int64_t nd = draw_offsets[w + 1] - draw_offsets[w];
         const int n = reads_per_draw[w];
@@ -334,6 +352,7 @@ int ldpgta_set_windows(ldpgta_ctx *c, const int64_t *window_offsets, const int32
             const int64_t R = window_offsets[w + 1] - window_offsets[w];
             if (R < n) return fail(LDPGTA_E_INVALID, "window %lld has %lld reads, fewer than the %d of a draw", (long long)w, (long long)R, n);
             if (R > 0x7fffffff) return fail(LDPGTA_E_INVALID, "window %lld has too many reads", (long long)w);
+            max_rows = std::max(max_rows, R);
         }
         per_n[n] += nd; win_n[n]++; nnz += nd * n;
         max_draws = std::max(max_draws, nd);
@@ -363,6 +382,8 @@ int ldpgta_set_windows(ldpgta_ctx *c, const int64_t *window_offsets, const int32
     p->n_windows = n_windows; p->n_draws = n_draws; p->n_wreads = window_reads ? n_wreads : 0; p->nnz = nnz;
     p->n_segments = n_segments; p->ncp = ncp; p->max_draws = max_draws;
     p->has_windows = window_offsets != nullptr;
+    p->consecutive = window_offsets != nullptr && window_reads == nullptr;
+    p->max_rows = max_rows;
     p->h_doff.assign(draw_offsets, draw_offsets + n_windows + 1);
     p->h_n.assign(reads_per_draw, reads_per_draw + n_windows);
     int n_classes = 0;

@@ -733,6 +733,127 @@ __global__ void __launch_bounds__(SmallPipe<4, 10>::NWARPS * 32, 1) k_small_both
     }
 }
 
+// ---- window-resident kernel: many draws per window (e.g. 1000 bootstrap subsamples) --------------------------------
+// With hundreds of draws per window every read of the window is drawn many times; gathering the masks of each draw again
+// costs L2 -> shared-memory traffic and ~120 staging instructions per tile for rows that were on the SM a microsecond ago.
+// Here a persistent CTA takes a whole window: ONE bulk copy brings the window's R consecutive read masks (R * 640 bytes) and
+// its R popcounts into shared memory, then the 16 warps walk the window's draws in tiles of four, every lane loading its
+// slots of its draw's four rows straight from the resident block into registers (the LDS that k_small needs anyway) -- no
+// per-tile copies, barriers or popcount loads.  Arithmetic, packed counters, transposing reduction and batched finish are
+// those of k_small<4, 8, 10, HOMOGENEOUS>.  Windows must be runs of consecutive rows of the read-mask table.
+struct SmallWinArgs {
+    SmallArgs base;          // pv / idx [n_draws][4] (absolute rows) / out; pos, counts_out, llr are not used
+    const int64_t *woff;     // [n_windows + 1] first row of each window
+    const int64_t *doff;     // [n_windows + 1] first draw of each window
+    int64_t n_windows;
+    int rcap;                // rows the shared-memory block holds
+};
+
+struct SmallWinSmem {
+    static constexpr int NWARPS = 16, BATCH_BYTES = 36 * 16 * 2 + 128;        // two planes of the transposed table (see k_small)
+    static constexpr int bytes(int rcap) { return rcap * 640 + ((rcap * 4 + 127) & ~127) + NWARPS * BATCH_BYTES + 64; }
+};
+
+static __global__ void __launch_bounds__(SmallWinSmem::NWARPS * 32, 1) k_small_win(const __grid_constant__ SmallWinArgs w)
+{
+    constexpr int NR = 4, LPD = 8, WPL = 10, NS = 16, SLOTS = 5, DPW = 4, TPB = 8, PLANE = 36, ROW_BYTES = 640;
+    const SmallArgs &a = w.base;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane_in = lane % LPD, dgrp = lane / LPD;
+    unsigned char *rows = smem;
+    uint32_t *pcs = reinterpret_cast<uint32_t *>(smem + (size_t)w.rcap * ROW_BYTES);
+    unsigned char *after = reinterpret_cast<unsigned char *>(pcs) + ((w.rcap * 4 + 127) & ~127);
+    uint4 *batch = reinterpret_cast<uint4 *>(after + (size_t)warp * SmallWinSmem::BATCH_BYTES);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(after + (size_t)SmallWinSmem::NWARPS * SmallWinSmem::BATCH_BYTES);
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    fence_proxy_async();
+    __syncthreads();
+    const double *norm = a.pv.norm[0];
+    const int4 *idx4 = reinterpret_cast<const int4 *>(a.idx);
+    uint32_t parity = 0;
+    for (int64_t win = blockIdx.x; win < w.n_windows; win += gridDim.x) {
+        const int64_t r0 = w.woff[win], d0 = w.doff[win];
+        const int R = (int)(w.woff[win + 1] - r0);
+        const int64_t D = w.doff[win + 1] - d0;
+        // the window's masks: one bulk copy; its popcounts: plain loads
+        if (threadIdx.x == 0) {
+            fence_proxy_async();                                              // the block was read through the generic proxy until the barrier above
+            mbar_arrive_expect_tx(bar, (uint32_t)R * ROW_BYTES);
+            bulk_copy_g2s(rows, a.pv.masks[0] + r0 * (LPD * WPL), (uint32_t)R * ROW_BYTES, bar);
+        }
+        for (int i = threadIdx.x; i < R; i += blockDim.x) pcs[i] = __ldg(a.pv.popc[0] + r0 + i);
+        const int64_t n_tiles = (D + DPW - 1) / DPW;
+        const int64_t my_tiles = warp < n_tiles ? (n_tiles - warp + SmallWinSmem::NWARPS - 1) / SmallWinSmem::NWARPS : 0;
+        // the draw of this lane's group in the warp's first tile (prefetched one tile ahead)
+        auto load_draw = [&](int64_t q) -> int4 {
+            int64_t d = (warp + q * SmallWinSmem::NWARPS) * DPW + dgrp;
+            if (d >= D) d = D - 1;                                            // ragged last tile: harmless duplicates
+            return __ldg(idx4 + d0 + d);
+        };
+        int4 nxt = my_tiles > 0 ? load_draw(0) : make_int4(0, 0, 0, 0);
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        __syncthreads();                                                      // popcounts visible
+        for (int64_t q = 0; q < my_tiles; ++q) {
+            const int4 cur = nxt;
+            if (q + 1 < my_tiles) nxt = load_draw(q + 1);
+            const int lr[NR] = {cur.x - (int)r0, cur.y - (int)r0, cur.z - (int)r0, cur.w - (int)r0};
+            uint32_t c[NS];
+#pragma unroll
+            for (int s = 0; s < NS; ++s) c[s] = 0;
+#pragma unroll
+            for (int i = 0; i < NR; ++i) if (lane_in == 0) c[1 << i] = pcs[lr[i]];
+            uint4 m[NR][SLOTS];
+#pragma unroll
+            for (int j = 0; j < SLOTS; ++j)
+#pragma unroll
+                for (int i = 0; i < NR; ++i)
+                    m[i][j] = *reinterpret_cast<const uint4 *>(rows + (size_t)lr[i] * ROW_BYTES + (j * LPD + lane_in) * 16);
+            small_subset_counts<NR, WPL>(m, c);
+            uint32_t pk[NS / 2];
+#pragma unroll
+            for (int t = 0; t < NS / 2; ++t) pk[t] = c[2 * t] + (c[2 * t + 1] << 16);
+#pragma unroll
+            for (int h = LPD / 2; h; h >>= 1) {
+                const bool up = (lane_in & h) != 0;
+#pragma unroll
+                for (int t = 0; t < h; ++t) {
+                    const uint32_t send = up ? pk[t] : pk[t + h], keep = up ? pk[t + h] : pk[t];
+                    pk[t] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+                }
+            }
+            const int k = (int)(q % TPB);
+            reinterpret_cast<uint32_t *>(batch)[(lane_in >> 2) * (PLANE * 4) + (k * DPW + dgrp) * 4 + (lane_in & 3)] = pk[0];
+            if (k == TPB - 1 || q + 1 == my_tiles) {
+                __syncwarp();
+                uint32_t cc[NS];
+#pragma unroll
+                for (int j = 0; j < NS / 8; ++j) {
+                    const uint4 v = batch[j * PLANE + lane];
+                    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { cc[8 * j + 2 * e] = w4[e] & 0xffffu; cc[8 * j + 2 * e + 1] = w4[e] >> 16; }
+                }
+                const int kk = lane / DPW;
+                const int64_t draw_k = (warp + (q - k + kk) * SmallWinSmem::NWARPS) * DPW + lane % DPW;      // within the window
+                if (kk <= k && draw_k < D) {
+                    double fr[NS], res[4];
+#pragma unroll
+                    for (int s = 1; s < NS; ++s) fr[s] = __ldg(norm + cc[s]);
+                    closed_single<NR>(fr, res);
+                    double2 *dst = reinterpret_cast<double2 *>(a.out + 4 * (d0 + draw_k));
+                    dst[0] = make_double2(res[0], res[1]);
+                    dst[1] = make_double2(res[2], res[3]);
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();                                                      // every warp is done with the block before it is refilled
+    }
+}
+
 // ---- direct kernel (no staging): rows longer than one pass of a lane group ---------------------
 template <int NR, int LPD, int WPL, int KIND>
 __global__ void __launch_bounds__(128, LDPGTA_SMALL_MINB) k_small_direct(const SmallArgs a)

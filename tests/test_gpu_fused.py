@@ -206,6 +206,35 @@ def test_fused_many_draws_per_window():
         check_against_oracle(res, res['lik'], doff, np.array([0, len(R)]))
 
 
+def test_window_resident_kernel_many_draws_per_window():
+    """ Plans with hundreds of draws per window, 4 reads per draw, 5008 haplotypes and windows that are runs of consecutive
+    rows take k_small_win (a window's masks resident in shared memory): likelihoods bit-identical to the per-draw gather
+    kernel behind ldpgta_bootstrap_uniform, statistics equal to the oracle's, ragged windows (4 reads .. 170 reads, draw
+    counts not multiples of the tile or the batch). """
+    rng = np.random.default_rng(29)
+    n_hap = 5008
+    R = np.array([4, 170, 33, 5, 96, 150, 61, 12, 140])
+    rows = random_rows(rng, int(R.sum()), n_hap)
+    woff = np.concatenate([[0], np.cumsum(R)]).astype(np.int64)
+    per = np.array([300, 1000, 257, 999, 512, 1001, 333, 700, 64])
+    doff = np.concatenate([[0], np.cumsum(per)]).astype(np.int64)
+    seg_off = np.array([0, 4, 9], dtype=np.int64)
+    with L.Engine([n_hap]) as eng:
+        eng.upload_read_masks(0, rows)
+        old_lik, old_idx = eng.bootstrap_uniform(L.HOMOGENEOUS, 4, woff, np.arange(len(rows), dtype=np.int32), doff, 5 + 4, want_draws=True)
+        launches = eng.launch_count
+        eng.set_windows(woff, None, doff, 4, segment_offsets=seg_off)
+        res = eng.bootstrap_stats(L.HOMOGENEOUS, 5, want=('lik', 'draws', 'mean_var', 'stats'))
+        assert np.array_equal(res['draws'].reshape(-1, 4), old_idx)
+        assert np.array_equal(res['lik'], old_lik)
+        check_against_oracle(res, res['lik'], doff, seg_off)
+        again = eng.bootstrap_stats(L.HOMOGENEOUS, 5, want=('lik', 'stats'))
+        assert np.array_equal(again['lik'], res['lik']) and np.array_equal(again['stats'], res['stats'])
+        rep = eng.replay_stats(L.HOMOGENEOUS, res['draws'], want=('lik', 'stats'))
+        assert np.array_equal(rep['lik'], res['lik']) and np.array_equal(rep['stats'], res['stats'])
+        del launches
+
+
 def test_sliced_statistics_download_into_pinned_buffers():
     """ With page-locked result buffers and enough chunks the window statistics go down in slices under the reductions of
     the later windows (strided 2-D copies into mean_var[5][n_windows][2]); same numbers as the one-copy route that
