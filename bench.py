@@ -291,8 +291,10 @@ def run_reference(args):
     return 0
 
 
-def kernel_name(n, model):
-    """ the kernel ldpgta_api.cu::run_uniform dispatches draws of n reads to """
+def kernel_name(n, model, subsamples=32):
+    """ the kernel ldpgta_api.cu::run_uniform / bootstrap_api.cu dispatch draws of n reads to """
+    if n == 4 and model == 'homogeneous' and subsamples >= 256:
+        return 'k_small_win (window-resident masks)'
     if n <= 4:
         return 'k_small<%d,8,10>' % n
     if n == 5 and model == 'homogeneous':
@@ -419,7 +421,7 @@ def secondary_legs(L, torch, device, local, args, hbm_peak, int_peak):
         med, kmed = float(np.median(ms)), float(np.median(kms))
         wordops = ((1 << n) - 1) * leg.words
         bytes_per_draw = n * leg.words * 8 + n * 4 + 32
-        out.append({'workload': name, 'kernel': kernel_name(n, model), 'windows': leg.n_windows, 'reads': leg.n_reads, 'draws_per_step': leg.n_draws,
+        out.append({'workload': name, 'kernel': kernel_name(n, model, subsamples), 'windows': leg.n_windows, 'reads': leg.n_reads, 'draws_per_step': leg.n_draws,
                     'reads_per_draw': n, 'subsamples': subsamples, 'steps': len(ms), 'ms_per_step': med, 'draw_kernel_ms': kmed,
                     'value': leg.n_draws / (med * 1e-3), 'unit': 'window-likelihoods/s',
                     'hbm_frac': bytes_per_draw * leg.n_draws / (kmed * 1e-3) / 1e9 / hbm_peak,
