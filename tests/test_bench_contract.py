@@ -36,7 +36,9 @@ def test_committed_bench_line_has_the_contract_keys():
     legs = {leg['workload'].split(':')[0] for leg in d['secondary']}
     assert {'configs[2]', 'configs[3]', 'configs[4] shape'} <= legs
     for leg in d['secondary']:
-        assert leg['value'] > 0 and leg['ms_per_step'] > 0 and 0 < leg['int_frac'] < 1.6
+        # int_frac is word AND+POPC per second over the measured DIRECT peak; the carry-save counting of k_small / k_small_win
+        # trades POPCs for LOP3s, so more than 1 is expected (k_small_win: 1.6) -- twice the peak would be a units error
+        assert leg['value'] > 0 and leg['ms_per_step'] > 0 and 0 < leg['int_frac'] < 2.0
     assert d['batch96']['window_likelihoods'] == 96 * d['config']['windows_per_gpu'] * 1000 and d['batch96']['statistics_finite']
     for n in (2, 4, 8):                                                              # the scaling lines of the same round
         m = json.load(open(os.path.join(ROOT, 'profiles', 'r02_bench_n%d.json' % n)))
