@@ -360,7 +360,7 @@ class Leg:
     """ One resident workload: masks + plan on an Engine, timed through ldpgta_bootstrap_stats_dev. """
 
     def __init__(self, L, torch, device, local, group_sizes, kind, reads, n, subsamples, seed, proportions=None, segments=None,
-                 seg_cols=None, seg_first=None):
+                 seg_cols=None, seg_first=None, list_fraction=None):
         self.L, self.torch, self.kind, self.n, self.proportions = L, torch, kind, n, proportions
         self.reads, self.n_windows, self.n_reads = reads, len(reads), int(reads.sum())
         self.eng = L.Engine(group_sizes, device=local)
@@ -373,7 +373,17 @@ class Leg:
         self.woff = np.concatenate([[0], np.cumsum(reads)]).astype(np.int64)
         self.doff = np.arange(0, (self.n_windows + 1) * subsamples, subsamples, dtype=np.int64)
         self.n_draws = int(self.doff[-1])
-        self.info = self.eng.set_windows(self.woff, None, self.doff, n, segment_offsets=segments, segment_cols=seg_cols, segment_first=seg_first)
+        wreads = None
+        if list_fraction is not None:
+            # windows as read lists, the way packed.py hands them over: a window keeps list_fraction of its run of rows (reads
+            # below min_score leave gaps), at least n + 2 of them
+            rng = np.random.default_rng(seed + 4242)
+            keep = rng.random(self.n_reads) < list_fraction
+            first = np.arange(self.n_reads) - np.repeat(self.woff[:-1], reads)
+            keep |= first < n + 2
+            wreads = np.flatnonzero(keep).astype(np.int32)
+            self.woff = np.concatenate([[0], np.cumsum(np.add.reduceat(keep, self.woff[:-1]))]).astype(np.int64)
+        self.info = self.eng.set_windows(self.woff, wreads, self.doff, n, segment_offsets=segments, segment_cols=seg_cols, segment_first=seg_first)
         self.stream = torch.cuda.ExternalStream(self.eng.stream, device=device)
         self.words = sum((nh + 63) // 64 for nh in group_sizes)
         self.seed = 0
@@ -413,10 +423,10 @@ def secondary_legs(L, torch, device, local, args, hbm_peak, int_peak):
     """ short legs for the other BASELINE configs on rank 0 (resident pipeline, device draws, statistics included) """
     out = []
 
-    def run(name, group_sizes, kind, depth, n, subsamples, windows, steps, proportions=None, model='homogeneous'):
+    def run(name, group_sizes, kind, depth, n, subsamples, windows, steps, proportions=None, model='homogeneous', list_fraction=None):
         wins, reads = workload_shape(depth, args.seed + 5, min_reads=n + 2, max_windows=windows)
         leg = Leg(L, torch, device, local, group_sizes, kind, reads, n, subsamples, args.seed + 9, proportions,
-                  segments=chromosome_segments(wins, len(reads)))
+                  segments=chromosome_segments(wins, len(reads)), list_fraction=list_fraction)
         ms, kms, _ = leg.timed(steps, 3, min_seconds=0.2)
         med, kmed = float(np.median(ms)), float(np.median(kms))
         wordops = ((1 << n) - 1) * leg.words
@@ -433,6 +443,8 @@ def secondary_legs(L, torch, device, local, args, hbm_peak, int_peak):
     run('configs[3]: recent admixture, two populations of 2504 haplotypes, 22 autosomes at 0.1x, 4 reads per draw, 32 draws per window',
         [N_HAP // 2, N_HAP // 2], L.RECENT_ADMIXTURE, 0.1, 4, 32, 0, 20, model='recent')
     run('configs[4] shape: 1000 subsamples per window, 4 reads per draw, homogeneous, 2048 windows at 0.1x', [N_HAP], L.HOMOGENEOUS, 0.1, 4, 1000, 2048, 5)
+    run('configs[4] shape, windows as read lists (85 % of each window\'s rows, as packed.py hands them over): 1000 subsamples per window, '
+        '4 reads per draw, homogeneous, 2048 windows at 0.1x', [N_HAP], L.HOMOGENEOUS, 0.1, 4, 1000, 2048, 5, list_fraction=0.85)
     return out
 
 

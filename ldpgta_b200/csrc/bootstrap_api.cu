@@ -46,6 +46,14 @@ struct WindowPlan {
     std::vector<int64_t> h_chunk_win;   // host copy of the chunk table (window ranges of the download slices)
     int64_t *d_chunk_win = nullptr, *d_cseg_off = nullptr;
     double *d_colpart = nullptr;
+    // windows given as read lists, many 4-read draws per window: the read masks in the order of the lists (every window a run
+    // of consecutive rows of the copy) and the sampler's positions inside the windows, for k_small_win (ensure_wmasks)
+    uint64_t *d_wmasks = nullptr;
+    uint32_t *d_wpopc = nullptr;
+    int32_t *d_pick = nullptr;     // [n_draws][4]
+    uint64_t wm_epoch = 0;         // ldpgta_ctx::masks_epoch the copy was made at
+    bool wm_refused = false;       // the copy did not fit next to the table: not tried again
+    bool picks_fresh = false;      // d_pick holds the positions of the draws that are in classes[0].d_idx
 };
 
 void free_window_plan(ldpgta_ctx *c)
@@ -54,6 +62,9 @@ void free_window_plan(ldpgta_ctx *c)
     if (c->llr_ptr == c->plan->d_llr) { c->llr_ptr = nullptr; c->llr_off_ptr = nullptr; c->llr_draws = c->llr_windows = -1; c->llr_lazy_lik = nullptr; }
     if (c->plan->d_static) cudaFree(c->plan->d_static);
     if (c->plan->d_work) cudaFree(c->plan->d_work);
+    if (c->plan->d_wmasks) cudaFree(c->plan->d_wmasks);
+    if (c->plan->d_wpopc) cudaFree(c->plan->d_wpopc);
+    if (c->plan->d_pick) cudaFree(c->plan->d_pick);
     delete c->plan;
     c->plan = nullptr;
 }
@@ -195,19 +206,86 @@ static bool llr_fused(const WindowPlan *p)
 }
 
 // idx_up: page-locked host draws of a one-class plan that still have to go up (ldpgta_replay_stats); lim = reads in the table
+// sampled: the draws are the device sampler's (every draw inside its window), not the caller's
 static int evaluate_classes_inner(ldpgta_ctx *c, WindowPlan *p, int kind, const double *proportions, double *lik_out_pinned,
-                                  const int32_t *idx_up, uint32_t lim);
+                                  const int32_t *idx_up, uint32_t lim, bool sampled);
 
 static int evaluate_classes(ldpgta_ctx *c, WindowPlan *p, int kind, const double *proportions, double *lik_out_pinned,
-                            const int32_t *idx_up = nullptr, uint32_t lim = 0)
+                            const int32_t *idx_up = nullptr, uint32_t lim = 0, bool sampled = false)
 {
     if (int rc = time_mark(c)) return rc;
-    if (int rc = evaluate_classes_inner(c, p, kind, proportions, lik_out_pinned, idx_up, lim)) return rc;
+    if (int rc = evaluate_classes_inner(c, p, kind, proportions, lik_out_pinned, idx_up, lim, sampled)) return rc;
     return time_mark(c);
 }
 
+// mean draws per window from which k_small_win replaces k_small (0 = never)
+static int64_t win_min_draws()
+{
+    static const int64_t v = [] { const char *e = getenv("LDPGTA_WIN_MIN_DRAWS"); return e ? (int64_t)atoll(e) : (int64_t)256; }();
+    return v;
+}
+
+// one group, 4 reads per draw, enough draws per window for the window-resident kernel
+static bool plan_wants_small_windows(const ldpgta_ctx *c, const WindowPlan *p, int kind)
+{
+    return kind == LDPGTA_HOMOGENEOUS && p->classes.size() == 1 && p->classes[0].n == 4 && win_min_draws() > 0 && p->n_windows > 0 &&
+           p->n_draws >= win_min_draws() * p->n_windows && small_windows_ok(c, p->max_rows);
+}
+
+// Windows given as read lists (packed.py: reads that fail min_score leave gaps): the plan keeps the read masks in the order of
+// the lists, so that every window is a run of consecutive rows of the copy, and the sampler also writes each draw's positions
+// inside its window.  *ok = false when the plan is not eligible or the copy does not fit (the caller takes k_small).
+static int ensure_wmasks(ldpgta_ctx *c, WindowPlan *p, int kind, bool *ok)
+{
+    *ok = false;
+    if (!p->n_wreads || p->wm_refused || !plan_wants_small_windows(c, p, kind)) return 0;
+    if (p->d_wmasks && p->wm_epoch == c->masks_epoch) { *ok = true; return 0; }
+    if (!p->d_wmasks) {
+        const size_t need = (size_t)p->n_wreads * 644 + (size_t)p->n_draws * 16;
+        size_t free_b = 0, total_b = 0;
+        LDPGTA_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        if (free_b < need + ((size_t)1 << 30)) { p->wm_refused = true; return 0; }
+        if (cudaMalloc((void **)&p->d_wmasks, (size_t)p->n_wreads * 640) != cudaSuccess || cudaMalloc((void **)&p->d_wpopc, (size_t)p->n_wreads * 4) != cudaSuccess ||
+            cudaMalloc((void **)&p->d_pick, (size_t)p->n_draws * 16) != cudaSuccess) {
+            (void)cudaGetLastError();                                  // an optimisation that does not fit is not an error
+            if (p->d_wmasks) cudaFree(p->d_wmasks);
+            if (p->d_wpopc) cudaFree(p->d_wpopc);
+            if (p->d_pick) cudaFree(p->d_pick);
+            p->d_wmasks = nullptr; p->d_wpopc = nullptr; p->d_pick = nullptr;
+            p->wm_refused = true;
+            return 0;
+        }
+    }
+    const int64_t total = p->n_wreads * 40;
+    k_gather_listed_rows<<<(unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)c->sm_count * 16), 256, 0, c->stream>>>(
+        c->read_masks[0], c->read_popc[0], p->d_wreads, p->n_wreads, 80, p->d_wmasks, p->d_wpopc);
+    c->launches++;
+    LDPGTA_CUDA(cudaGetLastError());
+    p->wm_epoch = c->masks_epoch;
+    p->picks_fresh = false;
+    *ok = true;
+    return 0;
+}
+
+// the sampler of every class; with window-ordered masks it also leaves the positions inside the windows (k_small_win)
+static int sample_classes(ldpgta_ctx *c, WindowPlan *p, int kind, uint64_t seed)
+{
+    bool picks = false;
+    if (int rc = ensure_wmasks(c, p, kind, &picks)) return rc;
+    for (const SizeClass &k : p->classes) {
+        SampleArgs sa;
+        memset(&sa, 0, sizeof sa);
+        sa.draw_off = k.d_doff; sa.win_of_draw = k.d_wod; sa.win_off = p->d_woff; sa.win_reads = p->d_wreads; sa.cls_win = k.d_win;
+        sa.n_windows = k.n_windows; sa.n_draws = k.n_draws; sa.seed = seed + (uint64_t)k.n; sa.idx_out = k.d_idx;
+        sa.pick_out = picks ? p->d_pick : nullptr;
+        if (int rc = launch_sample(c, k.n, sa)) return rc;
+    }
+    p->picks_fresh = picks;
+    return 0;
+}
+
 static int evaluate_classes_inner(ldpgta_ctx *c, WindowPlan *p, int kind, const double *proportions, double *lik_out_pinned,
-                                  const int32_t *idx_up, uint32_t lim)
+                                  const int32_t *idx_up, uint32_t lim, bool sampled)
 {
     if (idx_up && !lik_out_pinned) {
         // host-chosen draws of one size, statistics only: the draws go up in chunks on the upload stream, chunk i + 1 under the
@@ -252,11 +330,15 @@ static int evaluate_classes_inner(ldpgta_ctx *c, WindowPlan *p, int kind, const 
         }
         return 0;
     }
-    // many draws per window (e.g. 1000 subsamples), 4 reads each, windows = runs of consecutive rows: the window-resident kernel
-    static const int64_t win_min_draws = [] { const char *e = getenv("LDPGTA_WIN_MIN_DRAWS"); return e ? (int64_t)atoll(e) : (int64_t)256; }();
-    if (p->classes.size() == 1 && p->classes[0].n == 4 && kind == LDPGTA_HOMOGENEOUS && p->consecutive && win_min_draws > 0 &&
-        p->n_draws >= win_min_draws * p->n_windows) {
-        const int rc = launch_small_windows(c, p->classes[0].d_idx, p->n_draws, p->d_lik, p->d_woff, p->d_doff, p->n_windows, p->max_rows);
+    // many draws per window (e.g. 1000 subsamples), 4 reads each, drawn on the device: the window-resident kernel, on the
+    // read-mask table itself (windows = runs of consecutive rows) or on the plan's window-ordered copy (windows = read lists).
+    // Draws of the caller (ldpgta_replay_stats) may name any row of the table and take k_small.
+    const bool by_lists = p->picks_fresh && p->d_wmasks && p->wm_epoch == c->masks_epoch;
+    if (sampled && (p->consecutive || by_lists) && plan_wants_small_windows(c, p, kind)) {
+        const int rc = p->consecutive
+                           ? launch_small_windows(c, p->classes[0].d_idx, p->n_draws, p->d_lik, p->d_woff, p->d_doff, p->n_windows, p->max_rows)
+                           : launch_small_windows(c, p->d_pick, p->n_draws, p->d_lik, p->d_woff, p->d_doff, p->n_windows, p->max_rows,
+                                                  p->d_wmasks, p->d_wpopc, true);
         if (rc < 0) return rc;
         if (rc == 0) {
             if (lik_out_pinned) {
@@ -531,14 +613,8 @@ int ldpgta_bootstrap_stats(ldpgta_ctx *c, int kind, uint64_t seed, const double 
         if (int rc = ensure_pin(c, (size_t)p->n_draws * 32)) return rc;
         lik_pinned = (double *)c->h_pin;
     }
-    for (const SizeClass &k : p->classes) {
-        SampleArgs sa;
-        memset(&sa, 0, sizeof sa);
-        sa.draw_off = k.d_doff; sa.win_of_draw = k.d_wod; sa.win_off = p->d_woff; sa.win_reads = p->d_wreads; sa.cls_win = k.d_win;
-        sa.n_windows = k.n_windows; sa.n_draws = k.n_draws; sa.seed = seed + (uint64_t)k.n; sa.idx_out = k.d_idx;
-        if (int rc = launch_sample(c, k.n, sa)) return rc;
-    }
-    if (int rc = evaluate_classes(c, p, kind, proportions, lik_pinned)) return rc;
+    if (int rc = sample_classes(c, p, kind, seed)) return rc;
+    if (int rc = evaluate_classes(c, p, kind, proportions, lik_pinned, nullptr, 0, true)) return rc;
     if (idx_out) {
         // draws in the sample-wide order: window by window (classes interleave only when draw sizes differ)
         if (p->classes.size() == 1) {
@@ -611,6 +687,7 @@ int ldpgta_replay_stats(ldpgta_ctx *c, int kind, const int32_t *read_idx, const 
             c->launches++;
             at += cnt;
         }
+    p->picks_fresh = false;                                           // the draws are the caller's now
     if (int rc = evaluate_classes(c, p, kind, proportions, lik_out ? lik_pinned : nullptr, chunked_up ? src : nullptr, lim)) return rc;
     LDPGTA_CUDA(cudaMemcpyAsync(c->h_flag, c->d_flag, 4, cudaMemcpyDeviceToHost, c->stream));
     if (int rc = reduce_and_download(c, p, lik_out, lik_pinned, llr_out, window_mean_var, segment_partials, segment_stats)) return rc;
@@ -625,15 +702,9 @@ int ldpgta_bootstrap_stats_dev(ldpgta_ctx *c, int kind, uint64_t seed, const dou
     WindowPlan *p = c->plan;
     if (!p->has_windows) return fail(LDPGTA_E_STATE, "the resident plan has no window read lists");
     if (int rc = time_mark(c, 4)) return rc;
-    for (const SizeClass &k : p->classes) {
-        SampleArgs sa;
-        memset(&sa, 0, sizeof sa);
-        sa.draw_off = k.d_doff; sa.win_of_draw = k.d_wod; sa.win_off = p->d_woff; sa.win_reads = p->d_wreads; sa.cls_win = k.d_win;
-        sa.n_windows = k.n_windows; sa.n_draws = k.n_draws; sa.seed = seed + (uint64_t)k.n; sa.idx_out = k.d_idx;
-        if (int rc = launch_sample(c, k.n, sa)) return rc;
-    }
+    if (int rc = sample_classes(c, p, kind, seed)) return rc;
     if (int rc = time_mark(c, 4)) return rc;
-    if (int rc = evaluate_classes(c, p, kind, proportions, nullptr)) return rc;
+    if (int rc = evaluate_classes(c, p, kind, proportions, nullptr, nullptr, 0, true)) return rc;
     // the resident likelihoods change and the LLR matrix is not written: what ldpgta_bin_stats would read is gone
     if (c->llr_ptr == p->d_llr) { c->llr_draws = c->llr_windows = -1; c->llr_lazy_lik = nullptr; }
     if (int rc = time_mark(c, 2)) return rc;

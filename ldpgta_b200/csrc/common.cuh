@@ -278,6 +278,7 @@ struct ldpgta_ctx {
     uint64_t *masks_both = nullptr;
     size_t masks_both_bytes = 0;
     bool both_valid = false, both_tmap_ok = false;
+    uint64_t masks_epoch = 0;                 // bumped whenever a group's read masks change (copies derived from them are rebuilt)
     alignas(64) CUtensorMap tmap_both;
     bool masks_owned[ldpgta::MAXG] = {};
     int64_t n_reads_g[ldpgta::MAXG] = {};
@@ -380,7 +381,8 @@ inline int ensure_own(T **ptr, size_t *have, size_t bytes)
 // kernel launchers, one translation unit each (small.cu, general.cu)
 int launch_small(ldpgta_ctx *c, SmallArgs &a, int n, int kind);
 int launch_small_windows(ldpgta_ctx *c, const int32_t *d_idx, int64_t n_draws, double *d_out, const int64_t *d_woff, const int64_t *d_doff,
-                         int64_t n_windows, int64_t max_rows);
+                         int64_t n_windows, int64_t max_rows, const uint64_t *masks = nullptr, const uint32_t *popc = nullptr, bool local = false);
+bool small_windows_ok(const ldpgta_ctx *c, int64_t max_rows);
 int make_read_mask_tmap(ldpgta_ctx *c, int g);
 int launch_mid(ldpgta_ctx *c, SmallArgs &a, int n);      // 5-6 reads, register kernel; 1 = not applicable
 int launch_general(ldpgta_ctx *c, GeneralArgs a);

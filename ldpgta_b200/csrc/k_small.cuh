@@ -740,9 +740,14 @@ __global__ void __launch_bounds__(SmallPipe<4, 10>::NWARPS * 32, 1) k_small_both
 // its R popcounts into shared memory, then the 16 warps walk the window's draws in tiles of four, every lane loading its
 // slots of its draw's four rows straight from the resident block into registers (the LDS that k_small needs anyway) -- no
 // per-tile copies, barriers or popcount loads.  Arithmetic, packed counters, transposing reduction and batched finish are
-// those of k_small<4, 8, 10, HOMOGENEOUS>.  Windows must be runs of consecutive rows of the read-mask table.
+// those of k_small<4, 8, 10, HOMOGENEOUS>.  Windows are runs of consecutive rows: of the read-mask table itself, or -- for
+// windows given as read lists -- of a window-ordered copy of the masks that the plan keeps (bootstrap_api.cu: ensure_wmasks),
+// with the sampler's positions inside the window as draw indices.
 struct SmallWinArgs {
-    SmallArgs base;          // pv / idx [n_draws][4] (absolute rows) / out; pos, counts_out, llr are not used
+    SmallArgs base;          // pv / idx [n_draws][4] / out; pos, counts_out, llr are not used
+    const uint64_t *masks;   // the table the windows are runs of: the context's read masks, or the plan's window-ordered copy
+    const uint32_t *popc;    // its row popcounts
+    int local;               // idx holds positions inside the window (window given as a read list) instead of rows of the table
     const int64_t *woff;     // [n_windows + 1] first row of each window
     const int64_t *doff;     // [n_windows + 1] first draw of each window
     int64_t n_windows;
@@ -781,9 +786,9 @@ static __global__ void __launch_bounds__(SmallWinSmem::NWARPS * 32, 1) k_small_w
         if (threadIdx.x == 0) {
             fence_proxy_async();                                              // the block was read through the generic proxy until the barrier above
             mbar_arrive_expect_tx(bar, (uint32_t)R * ROW_BYTES);
-            bulk_copy_g2s(rows, a.pv.masks[0] + r0 * (LPD * WPL), (uint32_t)R * ROW_BYTES, bar);
+            bulk_copy_g2s(rows, w.masks + r0 * (LPD * WPL), (uint32_t)R * ROW_BYTES, bar);
         }
-        for (int i = threadIdx.x; i < R; i += blockDim.x) pcs[i] = __ldg(a.pv.popc[0] + r0 + i);
+        for (int i = threadIdx.x; i < R; i += blockDim.x) pcs[i] = __ldg(w.popc + r0 + i);
         const int64_t n_tiles = (D + DPW - 1) / DPW;
         const int64_t my_tiles = warp < n_tiles ? (n_tiles - warp + SmallWinSmem::NWARPS - 1) / SmallWinSmem::NWARPS : 0;
         // the draw of this lane's group in the warp's first tile (prefetched one tile ahead)
@@ -799,7 +804,8 @@ static __global__ void __launch_bounds__(SmallWinSmem::NWARPS * 32, 1) k_small_w
         for (int64_t q = 0; q < my_tiles; ++q) {
             const int4 cur = nxt;
             if (q + 1 < my_tiles) nxt = load_draw(q + 1);
-            const int lr[NR] = {cur.x - (int)r0, cur.y - (int)r0, cur.z - (int)r0, cur.w - (int)r0};
+            const int sub = w.local ? 0 : (int)r0;
+            const int lr[NR] = {cur.x - sub, cur.y - sub, cur.z - sub, cur.w - sub};
             uint32_t c[NS];
 #pragma unroll
             for (int s = 0; s < NS; ++s) c[s] = 0;

@@ -105,6 +105,22 @@ static __global__ void k_prepare_single(const SingleArgs a)
     }
 }
 
+// out[i] = rows[list[i]] (and the rows' popcounts): the read masks in the order of the plan's window read lists, so that every
+// window is a run of consecutive rows (k_small_win)
+static __global__ void k_gather_listed_rows(const uint64_t *__restrict__ rows, const uint32_t *__restrict__ popc, const int32_t *__restrict__ list,
+                                            int64_t n, int wp, uint64_t *__restrict__ out, uint32_t *__restrict__ out_popc)
+{
+    const int slots = wp >> 1;
+    const int64_t total = n * slots;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e / slots;
+        const int s_ = (int)(e - i * slots);
+        const int64_t r = list[i];
+        *reinterpret_cast<uint4 *>(out + i * wp + 2 * s_) = ldg128(rows + r * wp + 2 * s_);
+        if (s_ == 0) out_popc[i] = popc[r];
+    }
+}
+
 // norm[x] = x / nhap with IEEE division: joint_frequencies_combo(normalize=True) divides every count
 // by N (HOMOGENOUES_MODELS.py:160-161); counts are integers in 0..N, so a table is exact and turns
 // 15 float64 divisions per draw into 15 cached loads.
@@ -921,6 +937,7 @@ struct SampleArgs {
     uint64_t seed;
     const uint64_t *seed_dev;    // overrides seed when set (a captured launch reads the seed of the replay)
     int32_t *idx_out;            // [n_draws][K]
+    int32_t *pick_out;           // optional [n_draws][K]: positions inside the window's read list (k_small_win on read lists)
 };
 
 template <int K>
@@ -954,6 +971,10 @@ static __global__ void k_sample_draws(const SampleArgs a)
         }
 #pragma unroll
         for (int i = 0; i < K; ++i) a.idx_out[d * K + i] = a.win_reads ? a.win_reads[base + pick[i]] : (int32_t)(base + pick[i]);
+        if (a.pick_out) {
+#pragma unroll
+            for (int i = 0; i < K; ++i) a.pick_out[d * K + i] = (int32_t)pick[i];
+        }
     }
 }
 

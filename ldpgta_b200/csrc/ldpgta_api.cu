@@ -83,6 +83,7 @@ static int refresh_popc(ldpgta_ctx *c, int g)
 {
     if (c->read_popc[g]) { LDPGTA_CUDA(cudaFree(c->read_popc[g])); c->read_popc[g] = nullptr; }
     c->both_valid = false;                                    // the combined two-group rows are rebuilt on their next use
+    c->masks_epoch++;
     const int64_t n = c->n_reads_g[g];
     LDPGTA_CUDA(cudaMalloc((void **)&c->read_popc[g], std::max<size_t>((size_t)n * 4, 16)));
     if (n) {

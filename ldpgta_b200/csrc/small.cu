@@ -193,22 +193,29 @@ int launch_mid(ldpgta_ctx *c, SmallArgs &a, int n)
     return 1;
 }
 
+// the context's panel and the plan's largest window fit the window-resident kernel: one group of at most 65535 haplotypes in
+// rows of exactly 80 words, 4 .. 4096 rows that fit the shared-memory block
+bool small_windows_ok(const ldpgta_ctx *c, int64_t max_rows)
+{
+    return c->G == 1 && c->wp[0] == 80 && c->nhap[0] <= 65535u && max_rows >= 4 && max_rows <= 4096 &&
+           SmallWinSmem::bytes((int)max_rows) <= c->max_smem_optin;
+}
+
 // Window-resident kernel for plans with many draws per window (k_small.cuh: k_small_win).  Returns 1 when the plan is outside
 // its envelope (the caller launches k_small): one group of at most 65535 haplotypes in rows of exactly 80 words, 4 reads per
 // draw, windows that are runs of consecutive rows and fit the shared-memory block.
 int launch_small_windows(ldpgta_ctx *c, const int32_t *d_idx, int64_t n_draws, double *d_out, const int64_t *d_woff, const int64_t *d_doff,
-                         int64_t n_windows, int64_t max_rows)
+                         int64_t n_windows, int64_t max_rows, const uint64_t *masks, const uint32_t *popc, bool local)
 {
-    if (c->G != 1 || c->wp[0] != 80 || c->nhap[0] > 65535u || n_windows < 1) return 1;
+    if (!small_windows_ok(c, max_rows) || n_windows < 1) return 1;
     SmallArgs a;
     a.pv = make_view(c, nullptr);
     a.idx = d_idx; a.n_draws = n_draws; a.pos = nullptr; a.out = d_out; a.counts_out = nullptr; a.llr = nullptr; a.llr_stride = 0; a.use_gather4 = 0;
-    if (max_rows < 4 || max_rows > 4096) return 1;
     const int rcap = (int)max_rows;
     const int bytes = SmallWinSmem::bytes(rcap);
-    if (bytes > c->max_smem_optin) return 1;
     SmallWinArgs w;
     w.base = a; w.woff = d_woff; w.doff = d_doff; w.n_windows = n_windows; w.rcap = rcap;
+    w.masks = masks ? masks : c->read_masks[0]; w.popc = popc ? popc : c->read_popc[0]; w.local = local ? 1 : 0;
     LDPGTA_CUDA(cudaFuncSetAttribute(k_small_win, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     k_small_win<<<(unsigned)std::min<int64_t>(n_windows, c->sm_count), SmallWinSmem::NWARPS * 32, bytes, c->stream>>>(w);
     c->launches++;

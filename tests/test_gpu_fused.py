@@ -235,6 +235,55 @@ def test_window_resident_kernel_many_draws_per_window():
         del launches
 
 
+def test_window_resident_kernel_on_read_lists():
+    """ The same kernel for windows given as READ LISTS (what packed.py hands over: reads in arbitrary row order, rows that no
+    window uses, rows shared by neighbouring windows): the plan keeps a window-ordered copy of the masks and the sampler's
+    positions inside the windows.  Draws and likelihoods bit-identical to the per-draw gather kernel, statistics equal to the
+    oracle's; the copy is made once (one more launch in the first call than in the second) and again after the read masks
+    change; draws of the caller (replay) give the same numbers through k_small. """
+    rng = np.random.default_rng(31)
+    n_hap = 5008
+    R = np.array([4, 170, 33, 5, 96, 150, 61, 12, 140])
+    n_rows = int(R.sum()) + 50                                     # 50 rows belong to no window
+    rows = random_rows(rng, n_rows, n_hap)
+    wreads = rng.permutation(n_rows)[:int(R.sum())].astype(np.int32)
+    woff = np.concatenate([[0], np.cumsum(R)]).astype(np.int64)
+    wreads[woff[2]:woff[2] + 3] = wreads[woff[1]:woff[1] + 3]      # neighbours share reads
+    per = np.array([300, 1000, 257, 999, 512, 1001, 333, 700, 64])
+    doff = np.concatenate([[0], np.cumsum(per)]).astype(np.int64)
+    seg_off = np.array([0, 4, 9], dtype=np.int64)
+    with L.Engine([n_hap]) as eng:
+        eng.upload_read_masks(0, rows)
+        old_lik, old_idx = eng.bootstrap_uniform(L.HOMOGENEOUS, 4, woff, wreads, doff, 5 + 4, want_draws=True)
+        eng.set_windows(woff, wreads, doff, 4, segment_offsets=seg_off)
+        before = eng.launch_count
+        res = eng.bootstrap_stats(L.HOMOGENEOUS, 5, want=('lik', 'draws', 'mean_var', 'stats'))
+        first = eng.launch_count - before
+        assert np.array_equal(res['draws'].reshape(-1, 4), old_idx)
+        assert np.array_equal(res['lik'], old_lik)
+        check_against_oracle(res, res['lik'], doff, seg_off)
+        before = eng.launch_count
+        again = eng.bootstrap_stats(L.HOMOGENEOUS, 5, want=('lik', 'draws', 'mean_var', 'stats'))
+        assert first - (eng.launch_count - before) == 1            # the window-ordered copy was gathered in the first call only
+        assert np.array_equal(again['lik'], res['lik']) and np.array_equal(again['stats'], res['stats'])
+        rep = eng.replay_stats(L.HOMOGENEOUS, res['draws'], want=('lik', 'stats'))
+        assert np.array_equal(rep['lik'], res['lik']) and np.array_equal(rep['stats'], res['stats'])
+        # statistics only, another seed: equal to the per-draw kernel on the same draws
+        other = eng.bootstrap_stats(L.HOMOGENEOUS, 6, want=('draws', 'stats', 'mean_var'))
+        rep = eng.replay_stats(L.HOMOGENEOUS, other['draws'], want=('stats', 'mean_var'))
+        assert np.array_equal(rep['stats'], other['stats']) and np.array_equal(rep['mean_var'], other['mean_var'], equal_nan=True)
+        # new read masks under the same plan: the copy follows
+        rows2 = random_rows(rng, n_rows, n_hap, density=0.4)
+        eng.upload_read_masks(0, rows2)
+        new_lik, new_idx = eng.bootstrap_uniform(L.HOMOGENEOUS, 4, woff, wreads, doff, 5 + 4, want_draws=True)
+        eng.set_windows(woff, wreads, doff, 4, segment_offsets=seg_off)
+        res2 = eng.bootstrap_stats(L.HOMOGENEOUS, 5, want=('lik',))
+        assert np.array_equal(res2['lik'], new_lik) and not np.array_equal(new_lik, old_lik)
+        eng.upload_read_masks(0, rows)                             # ... also when the plan stays
+        res3 = eng.bootstrap_stats(L.HOMOGENEOUS, 5, want=('lik',))
+        assert np.array_equal(res3['lik'], old_lik)
+
+
 def test_sliced_statistics_download_into_pinned_buffers():
     """ With page-locked result buffers and enough chunks the window statistics go down in slices under the reductions of
     the later windows (strided 2-D copies into mean_var[5][n_windows][2]); same numbers as the one-copy route that
