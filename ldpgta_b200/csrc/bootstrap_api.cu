@@ -53,7 +53,8 @@ struct WindowPlan {
     int32_t *d_pick = nullptr;     // [n_draws][4]
     uint64_t wm_epoch = 0;         // ldpgta_ctx::masks_epoch the copy was made at
     bool wm_refused = false;       // the copy did not fit next to the table: not tried again
-    bool picks_fresh = false;      // d_pick holds the positions of the draws that are in classes[0].d_idx
+    bool picks_fresh = false;      // d_pick holds the positions of the current draws
+    bool rows_fresh = true;        // classes[].d_idx holds the rows of the current draws (false: the sampler wrote positions only)
 };
 
 void free_window_plan(ldpgta_ctx *c)
@@ -267,17 +268,21 @@ static int ensure_wmasks(ldpgta_ctx *c, WindowPlan *p, int kind, bool *ok)
     return 0;
 }
 
-// the sampler of every class; with window-ordered masks it also leaves the positions inside the windows (k_small_win)
-static int sample_classes(ldpgta_ctx *c, WindowPlan *p, int kind, uint64_t seed)
+// the sampler of every class; with window-ordered masks it also leaves the positions inside the windows (k_small_win), and
+// then writes the rows of the table only when somebody reads them (need_rows: the caller's `draws`, or k_small under a
+// download of the likelihoods) -- 16 bytes per draw and four dependent loads less
+static int sample_classes(ldpgta_ctx *c, WindowPlan *p, int kind, uint64_t seed, bool need_rows)
 {
     bool picks = false;
     if (int rc = ensure_wmasks(c, p, kind, &picks)) return rc;
+    p->rows_fresh = !picks || need_rows;
     for (const SizeClass &k : p->classes) {
         SampleArgs sa;
         memset(&sa, 0, sizeof sa);
         sa.draw_off = k.d_doff; sa.win_of_draw = k.d_wod; sa.win_off = p->d_woff; sa.win_reads = p->d_wreads; sa.cls_win = k.d_win;
         sa.n_windows = k.n_windows; sa.n_draws = k.n_draws; sa.seed = seed + (uint64_t)k.n; sa.idx_out = k.d_idx;
         sa.pick_out = picks ? p->d_pick : nullptr;
+        if (!p->rows_fresh) sa.idx_out = nullptr;
         if (int rc = launch_sample(c, k.n, sa)) return rc;
     }
     p->picks_fresh = picks;
@@ -311,7 +316,7 @@ static int evaluate_classes_inner(ldpgta_ctx *c, WindowPlan *p, int kind, const 
         }
         return 0;
     }
-    if (p->classes.size() == 1 && lik_out_pinned && p->n_draws >= 65536) {
+    if (p->classes.size() == 1 && lik_out_pinned && p->n_draws >= 65536 && p->rows_fresh) {
         // one draw size (the usual plan): chunks, the download of chunk i under the kernel of chunk i + 1
         const SizeClass &k = p->classes[0];
         static const int64_t max_chunks = [] { const char *e = getenv("LDPGTA_FULL_CHUNKS"); return e && atoi(e) > 0 ? (int64_t)atoi(e) : (int64_t)8; }();      // measured: 4 / 8 / 16 / 32 chunks -> 0.72 / 0.70 / 0.74 / 0.85 ms
@@ -350,6 +355,7 @@ static int evaluate_classes_inner(ldpgta_ctx *c, WindowPlan *p, int kind, const 
             return 0;
         }
     }
+    if (!p->rows_fresh) return fail(LDPGTA_E_STATE, "the sampler left positions only, but the draw kernel needs the rows of the draws");
     for (const SizeClass &k : p->classes)
         if (int rc = run_uniform(c, kind, k.n, k.d_idx, k.n_draws, k.d_pos, proportions, p->d_lik, nullptr, false, nullptr,
                                  llr_fused(p) ? p->d_llr : nullptr, p->n_draws))
@@ -613,7 +619,7 @@ int ldpgta_bootstrap_stats(ldpgta_ctx *c, int kind, uint64_t seed, const double 
         if (int rc = ensure_pin(c, (size_t)p->n_draws * 32)) return rc;
         lik_pinned = (double *)c->h_pin;
     }
-    if (int rc = sample_classes(c, p, kind, seed)) return rc;
+    if (int rc = sample_classes(c, p, kind, seed, idx_out != nullptr || lik_out != nullptr)) return rc;
     if (int rc = evaluate_classes(c, p, kind, proportions, lik_pinned, nullptr, 0, true)) return rc;
     if (idx_out) {
         // draws in the sample-wide order: window by window (classes interleave only when draw sizes differ)
@@ -688,6 +694,7 @@ int ldpgta_replay_stats(ldpgta_ctx *c, int kind, const int32_t *read_idx, const 
             at += cnt;
         }
     p->picks_fresh = false;                                           // the draws are the caller's now
+    p->rows_fresh = true;
     if (int rc = evaluate_classes(c, p, kind, proportions, lik_out ? lik_pinned : nullptr, chunked_up ? src : nullptr, lim)) return rc;
     LDPGTA_CUDA(cudaMemcpyAsync(c->h_flag, c->d_flag, 4, cudaMemcpyDeviceToHost, c->stream));
     if (int rc = reduce_and_download(c, p, lik_out, lik_pinned, llr_out, window_mean_var, segment_partials, segment_stats)) return rc;
@@ -702,7 +709,7 @@ int ldpgta_bootstrap_stats_dev(ldpgta_ctx *c, int kind, uint64_t seed, const dou
     WindowPlan *p = c->plan;
     if (!p->has_windows) return fail(LDPGTA_E_STATE, "the resident plan has no window read lists");
     if (int rc = time_mark(c, 4)) return rc;
-    if (int rc = sample_classes(c, p, kind, seed)) return rc;
+    if (int rc = sample_classes(c, p, kind, seed, false)) return rc;
     if (int rc = time_mark(c, 4)) return rc;
     if (int rc = evaluate_classes(c, p, kind, proportions, nullptr, nullptr, 0, true)) return rc;
     // the resident likelihoods change and the LLR matrix is not written: what ldpgta_bin_stats would read is gone

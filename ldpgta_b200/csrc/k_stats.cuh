@@ -936,7 +936,7 @@ struct SampleArgs {
     int64_t n_windows, n_draws;
     uint64_t seed;
     const uint64_t *seed_dev;    // overrides seed when set (a captured launch reads the seed of the replay)
-    int32_t *idx_out;            // [n_draws][K]
+    int32_t *idx_out;            // [n_draws][K] rows of the read-mask table (optional when pick_out is all the draw kernel reads)
     int32_t *pick_out;           // optional [n_draws][K]: positions inside the window's read list (k_small_win on read lists)
 };
 
@@ -969,8 +969,10 @@ static __global__ void k_sample_draws(const SampleArgs a)
             for (int j = 0; j < i; ++j) dup |= pick[j] == t;
             pick[i] = dup ? top : t;
         }
+        if (a.idx_out) {
 #pragma unroll
-        for (int i = 0; i < K; ++i) a.idx_out[d * K + i] = a.win_reads ? a.win_reads[base + pick[i]] : (int32_t)(base + pick[i]);
+            for (int i = 0; i < K; ++i) a.idx_out[d * K + i] = a.win_reads ? a.win_reads[base + pick[i]] : (int32_t)(base + pick[i]);
+        }
         if (a.pick_out) {
 #pragma unroll
             for (int i = 0; i < K; ++i) a.pick_out[d * K + i] = (int32_t)pick[i];

@@ -272,6 +272,12 @@ def test_window_resident_kernel_on_read_lists():
         other = eng.bootstrap_stats(L.HOMOGENEOUS, 6, want=('draws', 'stats', 'mean_var'))
         rep = eng.replay_stats(L.HOMOGENEOUS, other['draws'], want=('stats', 'mean_var'))
         assert np.array_equal(rep['stats'], other['stats']) and np.array_equal(rep['mean_var'], other['mean_var'], equal_nan=True)
+        # nothing but statistics asked for: the sampler writes positions only (no rows of the table) -- same numbers, and the
+        # rows are back when a later call wants them
+        only = eng.bootstrap_stats(L.HOMOGENEOUS, 6, want=('stats', 'mean_var'))
+        assert np.array_equal(only['stats'], other['stats']) and np.array_equal(only['mean_var'], other['mean_var'], equal_nan=True)
+        back = eng.bootstrap_stats(L.HOMOGENEOUS, 5, want=('draws', 'stats'))
+        assert np.array_equal(back['draws'], res['draws']) and np.array_equal(back['stats'], res['stats'])
         # new read masks under the same plan: the copy follows
         rows2 = random_rows(rng, n_rows, n_hap, density=0.4)
         eng.upload_read_masks(0, rows2)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """ Where a resident step of configs[1] goes, measured in the pipeline (warm L2, back-to-back launches) rather than under
 ncu: median step with no inner events, with events around the draw kernel, with events around the reductions.
-usage: python tools/step_parts.py [--subsamples S] [--windows W] """
+usage: python tools/step_parts.py [--subsamples S] [--windows W] [--list-fraction F] """
 import argparse
 import json
 import os
@@ -19,12 +19,14 @@ def main():
     ap.add_argument('--subsamples', type=int, default=32)
     ap.add_argument('--windows', type=int, default=0)
     ap.add_argument('--steps', type=int, default=400)
+    ap.add_argument('--list-fraction', type=float, default=None, help='windows as read lists keeping this fraction of their rows (bench.Leg)')
     a = ap.parse_args()
     import torch
     import ldpgta_b200 as L
     device = torch.device('cuda:0')
     wins, reads = B.workload_shape(0.1, 12345, min_reads=6, max_windows=a.windows)
-    leg = B.Leg(L, torch, device, 0, [B.N_HAP], L.HOMOGENEOUS, reads, 4, a.subsamples, 12345, None, segments=B.chromosome_segments(wins, len(reads)))
+    leg = B.Leg(L, torch, device, 0, [B.N_HAP], L.HOMOGENEOUS, reads, 4, a.subsamples, 12345, None, segments=B.chromosome_segments(wins, len(reads)),
+                list_fraction=a.list_fraction)
     eng = leg.eng
 
     def loop(mode):
