@@ -199,7 +199,11 @@ int ldpgta_set_windows(ldpgta_ctx *ctx, const int64_t *window_offsets, const int
  *   window_mean_var  [5][n_windows][2]     mean and sample variance (NaN for single-draw windows)
  *   segment_partials [n_segments][5][ncp+3] as chrom_partials of ldpgta_window_stats, ncp = max segment_cols, columns at
  *                                          or beyond a segment's own count are zero
- *   segment_stats    [n_segments][5][3]    mean_of_mean, std_of_mean, fraction_of_negative_LLRs (:311-313) */
+ *   segment_stats    [n_segments][5][3]    mean_of_mean, std_of_mean, fraction_of_negative_LLRs (:311-313)
+ * Memory: a one-group plan of 4-read draws with 256 or more draws per window on average (e.g. 1000 subsamples) whose
+ * windows are read lists keeps, from its first call on, a window-ordered copy of the listed read masks (644 bytes per
+ * listed read + 16 per draw) for the window-resident draw kernel; the copy is skipped when it would not leave 1 GiB free,
+ * refreshed when the read masks change, and released with the plan.  Results do not depend on it. */
 int ldpgta_bootstrap_stats(ldpgta_ctx *ctx, int model_kind, uint64_t seed, const double *proportions, double *lik_out,
                            int32_t *idx_out, double *llr_out, double *window_mean_var, double *segment_partials,
                            double *segment_stats);
