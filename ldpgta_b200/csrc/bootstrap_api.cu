@@ -53,6 +53,7 @@ struct WindowPlan {
     int32_t *d_pick = nullptr;     // [n_draws][4]
     uint64_t wm_epoch = 0;         // ldpgta_ctx::masks_epoch the copy was made at
     bool wm_refused = false;       // the copy did not fit next to the table: not tried again
+    int64_t n_reads_planned = 0;   // rows of the read-mask table when the windows were checked against it
     bool picks_fresh = false;      // d_pick holds the positions of the current draws
     bool rows_fresh = true;        // classes[].d_idx holds the rows of the current draws (false: the sampler wrote positions only)
 };
@@ -376,6 +377,10 @@ static int check_plan(const ldpgta_ctx *c, int kind, const double *proportions)
     if (int rc = check_kind(c, kind, proportions)) return rc;
     for (const SizeClass &k : c->plan->classes)
         if (int rc = check_uniform_size(kind, k.n)) return rc;
+    // the windows were checked against the table that was resident then; a smaller table would be read out of bounds
+    if (c->plan->has_windows && c->n_reads < c->plan->n_reads_planned)
+        return fail(LDPGTA_E_STATE, "the read-mask table shrank from %lld to %lld rows under the resident windows: call ldpgta_set_windows again",
+                    (long long)c->plan->n_reads_planned, (long long)c->n_reads);
     return 0;
 }
 
@@ -470,6 +475,7 @@ int ldpgta_set_windows(ldpgta_ctx *c, const int64_t *window_offsets, const int32
     p->n_windows = n_windows; p->n_draws = n_draws; p->n_wreads = window_reads ? n_wreads : 0; p->nnz = nnz;
     p->n_segments = n_segments; p->ncp = ncp; p->max_draws = max_draws;
     p->has_windows = window_offsets != nullptr;
+    p->n_reads_planned = window_offsets ? c->n_reads : 0;
     p->consecutive = window_offsets != nullptr && window_reads == nullptr;
     p->max_rows = max_rows;
     p->h_doff.assign(draw_offsets, draw_offsets + n_windows + 1);

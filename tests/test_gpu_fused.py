@@ -288,6 +288,10 @@ def test_window_resident_kernel_on_read_lists():
         eng.upload_read_masks(0, rows)                             # ... also when the plan stays
         res3 = eng.bootstrap_stats(L.HOMOGENEOUS, 5, want=('lik',))
         assert np.array_equal(res3['lik'], old_lik)
+        # a table with fewer rows than the windows were checked against: refused, not read out of bounds
+        eng.upload_read_masks(0, rows[:100])
+        with pytest.raises(L.LdpgtaError):
+            eng.bootstrap_stats(L.HOMOGENEOUS, 5, want=('stats',))
 
 
 def test_sliced_statistics_download_into_pinned_buffers():
